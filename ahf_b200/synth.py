@@ -1,0 +1,182 @@
+"""Synthetic inputs for the AHF hot path (BASELINE.json `configs`).
+
+A box holds (i) a jittered lattice (Zel'dovich-style Gaussian displacements, sigma ~ 0.3 cell, small
+Gaussian velocities) and (ii) Plummer spheres (about 30 % of the particles, masses log-uniform over
+about 3 decades, isotropic Gaussian velocities with the Plummer 1-D dispersion).  Everything is
+equal-mass dark matter (GADGET type 1), z = 0.
+
+Two views of the same particles are produced:
+
+* internal units, exactly what the reference holds in `struct particle` after
+  `io_gadget_scale_particles` (reference src/libio/io_gadget.c:919-925): `pos` = x / boxsize as
+  float32 in [0,1), `mom` = float32(v) * float32(1/(boxsize*100)) at a = 1;
+* a GADGET-1 single file (reference src/libio/io_gadget_header_def.h:41-66, io_gadget.c:426-568)
+  plus an `AHF.input` so that the compiled reference (oracle/_ref/ahf_ref) can be run on the same data.
+
+The box size is a power of two (Mpc/h) so that x / boxsize is exact in float32 and both views agree
+bit for bit.
+"""
+from __future__ import annotations
+
+import os
+import struct
+from dataclasses import dataclass
+
+import numpy as np
+
+GRAV = 4.3006485e-9      # reference src/param.h:44  [Mpc km^2 / (Msun s^2)]
+RHOC0 = 2.7755397e11     # reference src/param.h:43  [h^2 Msun / Mpc^3]
+H0 = 100.0               # reference src/param.h:42
+
+
+@dataclass
+class Box:
+    """One synthetic snapshot in both unit systems."""
+    n1d: int
+    boxsize: float           # Mpc/h
+    omega0: float
+    lambda0: float
+    pmass: float             # Msun/h per particle
+    pos: np.ndarray          # (N,3) float32, box units [0,1)
+    mom: np.ndarray          # (N,3) float32, internal velocity units
+    ids: np.ndarray          # (N,) uint64
+    vel_kms: np.ndarray      # (N,3) float32 as written to the GADGET file
+    clump_centres: np.ndarray  # (nc,3) float64 box units
+    clump_npart: np.ndarray    # (nc,) int64
+    clump_scale: np.ndarray    # (nc,) float64 Plummer a in box units
+
+    @property
+    def npart(self) -> int:
+        return int(self.pos.shape[0])
+
+
+def default_boxsize(n1d: int) -> float:
+    """0.5 Mpc/h per mean inter-particle spacing, rounded to a power of two."""
+    return float(2 ** int(round(np.log2(0.5 * n1d))))
+
+
+def make_box(n1d: int, seed: int = 42, clump_frac: float = 0.3, n_clumps: int | None = None,
+             boxsize: float | None = None, omega0: float = 0.3, lambda0: float = 0.7,
+             sigma_cell: float = 0.3, mass_decades: float = 3.0) -> Box:
+    rng = np.random.default_rng(seed)
+    box = default_boxsize(n1d) if boxsize is None else float(boxsize)
+    ntot = n1d ** 3
+    if n_clumps is None:
+        n_clumps = max(1, int(round(20 * (n1d / 128.0) ** 3)))
+    pmass = omega0 * RHOC0 * box ** 3 / ntot
+
+    # ---- clump membership: log-uniform masses over `mass_decades`, total = clump_frac * ntot
+    n_cl_target = int(clump_frac * ntot)
+    w = 10.0 ** (rng.uniform(0.0, mass_decades, size=n_clumps))
+    cn = np.maximum(30, np.floor(w / w.sum() * n_cl_target)).astype(np.int64)
+    n_cl = int(cn.sum())
+    n_lat = ntot - n_cl
+    if n_lat <= 0:
+        raise ValueError("clump fraction too large")
+
+    # ---- lattice part: a random subset of lattice sites keeps the total at n1d^3
+    sites = rng.choice(ntot, size=n_lat, replace=False) if n_lat < ntot else np.arange(ntot)
+    sites.sort()
+    iz = sites // (n1d * n1d)
+    iy = (sites // n1d) % n1d
+    ix = sites % n1d
+    cell = box / n1d
+    lat = (np.stack([ix, iy, iz], axis=1).astype(np.float64) + 0.5) * cell
+    lat += rng.normal(0.0, sigma_cell * cell, size=lat.shape)
+    vlat = rng.normal(0.0, 50.0, size=lat.shape)
+
+    # ---- Plummer clumps
+    centres = rng.uniform(0.0, box, size=(n_clumps, 3))
+    mass = cn * pmass
+    a_pl = np.clip(0.1 * (mass / 1e14) ** (1.0 / 3.0), 0.05, 0.15)          # Mpc/h
+    cpos = np.empty((n_cl, 3))
+    cvel = np.empty((n_cl, 3))
+    o = 0
+    for c in range(n_clumps):
+        m = int(cn[c])
+        u = rng.uniform(1e-9, 1.0 - 1e-6, size=m)
+        r = a_pl[c] / np.sqrt(u ** (-2.0 / 3.0) - 1.0)
+        r = np.minimum(r, 20.0 * a_pl[c])
+        d = rng.normal(size=(m, 3))
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        cpos[o:o + m] = centres[c] + d * r[:, None]
+        sig2 = GRAV * mass[c] / (6.0 * a_pl[c]) / np.sqrt(1.0 + (r / a_pl[c]) ** 2)
+        bulk = rng.normal(0.0, 200.0, size=3)
+        cvel[o:o + m] = bulk + rng.normal(size=(m, 3)) * np.sqrt(sig2)[:, None]
+        o += m
+
+    x = np.concatenate([lat, cpos], axis=0)
+    v = np.concatenate([vlat, cvel], axis=0)
+    x = np.mod(x, box)
+    x32 = x.astype(np.float32)
+    # float32(box) must stay below box after rounding: pull the rare x32 == box down
+    x32 = np.where(x32 >= np.float32(box), np.nextafter(np.float32(box), np.float32(0.0)), x32).astype(np.float32)
+    v32 = v.astype(np.float32)
+
+    pos = (x32 * np.float32(1.0 / box)).astype(np.float32)               # exact: box is 2^k
+    scale_mom = 1.0 / (box * 1.0 * 100.0)                                  # a = 1 (io_gadget.c:921-923)
+    mom = (v32 * np.float32(scale_mom)).astype(np.float32)
+    ids = np.arange(ntot, dtype=np.uint64)
+    return Box(n1d=n1d, boxsize=box, omega0=omega0, lambda0=lambda0, pmass=pmass, pos=pos, mom=mom, ids=ids,
+               vel_kms=v32, clump_centres=centres / box, clump_npart=cn, clump_scale=a_pl / box)
+
+
+def write_gadget1(box: Box, path: str) -> None:
+    """Little-endian GADGET-1, all particles of type 1 with massarr[1] > 0 (no MASS block)."""
+    n = box.npart
+    if n >= 2 ** 31 // 12:
+        raise ValueError("single GADGET file limited by 32-bit block lengths; split the snapshot")
+    hdr = bytearray(256)
+    np_ = [0, n, 0, 0, 0, 0]
+    massarr = [0.0, box.pmass / 1e10, 0.0, 0.0, 0.0, 0.0]                  # GADGET_MUNIT = 1e10 Msun/h
+    struct.pack_into("<6i", hdr, 0, *np_)
+    struct.pack_into("<6d", hdr, 24, *massarr)
+    struct.pack_into("<2d", hdr, 72, 1.0, 0.0)                             # expansion, redshift
+    struct.pack_into("<2i", hdr, 88, 0, 0)
+    struct.pack_into("<6I", hdr, 96, *np_)
+    struct.pack_into("<2i", hdr, 120, 0, 1)                                # flagcooling, numfiles
+    struct.pack_into("<4d", hdr, 128, box.boxsize, box.omega0, box.lambda0, 0.7)
+
+    def block(f, payload: bytes):
+        f.write(struct.pack("<I", len(payload)))
+        f.write(payload)
+        f.write(struct.pack("<I", len(payload)))
+
+    x = (box.pos.astype(np.float32) * np.float32(box.boxsize)).astype("<f4")  # exact inverse of the scaling
+    with open(path, "wb") as f:
+        block(f, bytes(hdr))
+        block(f, x.tobytes())
+        block(f, box.vel_kms.astype("<f4").tobytes())
+        block(f, box.ids.astype("<u4").tobytes())
+
+
+def write_ahf_input(path: str, ic_filename: str, prefix: str, lgrid_domain: int, *, lgrid_max: int = 16777216,
+                    nper_dom: float = 2.0, nper_ref: float = 2.5, vesc_tune: float = 1.5, nmin: int = 20,
+                    rho_vir: int = 0, dvir: float = 200.0, max_gather_rad: float = 3.0) -> None:
+    """AHF.input with the AHF.input-example settings (reference AHF.input-example:16-41)."""
+    with open(path, "w") as f:
+        f.write("[AHF]\n")
+        f.write(f"ic_filename       = {ic_filename}\n")
+        f.write("ic_filetype       = 60\n")
+        f.write(f"outfile_prefix    = {prefix}\n")
+        f.write(f"LgridDomain       = {lgrid_domain}\n")
+        f.write(f"LgridMax          = {lgrid_max}\n")
+        f.write(f"NperDomCell       = {nper_dom}\n")
+        f.write(f"NperRefCell       = {nper_ref}\n")
+        f.write(f"VescTune          = {vesc_tune}\n")
+        f.write(f"NminPerHalo       = {nmin}\n")
+        f.write(f"RhoVir            = {rho_vir}\n")
+        f.write(f"Dvir              = {dvir}\n")
+        f.write(f"MaxGatherRad      = {max_gather_rad}\n")
+        f.write("LevelDomainDecomp = 6\nNcpuReading       = 1\n\n")
+        f.write("[GADGET]\nGADGET_LUNIT      = 1.\nGADGET_MUNIT      = 1e10\n")
+
+
+def write_reference_case(box: Box, workdir: str, lgrid_domain: int | None = None, **kw) -> str:
+    """Write snapshot + AHF.input into `workdir`; returns the AHF.input path."""
+    os.makedirs(workdir, exist_ok=True)
+    snap = os.path.join(workdir, "snap.gadget")
+    write_gadget1(box, snap)
+    inp = os.path.join(workdir, "AHF.input")
+    write_ahf_input(inp, snap, os.path.join(workdir, "ref"), lgrid_domain or box.n1d, **kw)
+    return inp
