@@ -57,7 +57,7 @@ def default_boxsize(n1d: int) -> float:
 
 def make_box(n1d: int, seed: int = 42, clump_frac: float = 0.3, n_clumps: int | None = None,
              boxsize: float | None = None, omega0: float = 0.3, lambda0: float = 0.7,
-             sigma_cell: float = 0.3, mass_decades: float = 3.0) -> Box:
+             sigma_cell: float = 0.3, mass_decades: float = 3.0, centres_box: np.ndarray | None = None) -> Box:
     rng = np.random.default_rng(seed)
     box = default_boxsize(n1d) if boxsize is None else float(boxsize)
     ntot = n1d ** 3
@@ -87,6 +87,9 @@ def make_box(n1d: int, seed: int = 42, clump_frac: float = 0.3, n_clumps: int | 
 
     # ---- Plummer clumps
     centres = rng.uniform(0.0, box, size=(n_clumps, 3))
+    if centres_box is not None:                       # explicit centres (box units) for the first clumps
+        cb = np.asarray(centres_box, dtype=np.float64).reshape(-1, 3)
+        centres[:cb.shape[0]] = cb[:n_clumps] * box
     mass = cn * pmass
     a_pl = np.clip(0.1 * (mass / 1e14) ** (1.0 / 3.0), 0.05, 0.15)          # Mpc/h
     cpos = np.empty((n_cl, 3))

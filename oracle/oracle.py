@@ -1,0 +1,221 @@
+"""TEST INFRASTRUCTURE: ctypes view of oracle/libahf_oracle.so (the CPU checker) and readers for the
+dumps written by the hooked reference binary (oracle/_ref/ahf_ref, oracle/ref_hooks.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libahf_oracle.so")
+REF_BIN = os.path.join(HERE, "_ref", "ahf_ref")
+REF_BIN_MM = os.path.join(HERE, "_ref", "ahf_ref_mm")
+
+_lib = None
+
+
+def build(force: bool = False) -> None:
+    srcs = [os.path.join(HERE, f) for f in ("ahf_oracle_mesh.c", "ahf_oracle_halo.c", "ahf_oracle.h")]
+    if (not force and os.path.exists(LIB_PATH)
+            and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
+        return
+    subprocess.check_call(["make", "-s", "-C", HERE, "libahf_oracle.so"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        L.orc_hilbert_key.restype = C.c_uint64
+        L.orc_hilbert_key.argtypes = [C.c_double, C.c_double, C.c_double, C.c_uint]
+        L.orc_hilbert_key_grid.restype = C.c_uint64
+        L.orc_hilbert_key_grid.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint]
+        L.orc_hilbert_keys.argtypes = [C.c_void_p, C.c_int64, C.c_uint, C.c_void_p]
+        L.orc_hilbert_coords.argtypes = [C.c_uint64, C.c_uint, C.c_void_p]
+        L.orc_argsort_keys.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        L.orc_hier_build.restype = C.c_void_p
+        L.orc_hier_build.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_double]
+        L.orc_hier_nlevels.argtypes = [C.c_void_p]
+        L.orc_hier_level_header.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_hier_level_get.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 11
+        L.orc_hier_free.argtypes = [C.c_void_p]
+        if hasattr(L, "orc_halo_construct"):
+            L.orc_halo_construct.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+            L.orc_halo_result_free.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+# ------------------------------------------------------------------------------------------------
+def hilbert_keys(pos: np.ndarray, bits: int = 21) -> np.ndarray:
+    pos = np.ascontiguousarray(pos, dtype=np.float32)
+    keys = np.empty(pos.shape[0], dtype=np.uint64)
+    lib().orc_hilbert_keys(_p(pos), pos.shape[0], bits, _p(keys))
+    return keys
+
+
+def argsort_keys(keys: np.ndarray) -> np.ndarray:
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    order = np.empty(keys.shape[0], dtype=np.int64)
+    lib().orc_argsort_keys(_p(keys), keys.shape[0], _p(order))
+    return order
+
+
+@dataclass
+class Level:
+    l1dim: int
+    ncell: int
+    critdens: float
+    masstopartdens: float
+    x: np.ndarray
+    y: np.ndarray
+    z: np.ndarray
+    dens: np.ndarray
+    runflags: np.ndarray
+    cnt_flag: np.ndarray
+    plist_flag: np.ndarray
+    interior: np.ndarray | None = None
+    mark: np.ndarray | None = None
+    cnt_final: np.ndarray | None = None
+    plist_final: np.ndarray | None = None
+
+    def lin(self) -> np.ndarray:
+        L = np.int64(self.l1dim)
+        return (self.z.astype(np.int64) * L + self.y.astype(np.int64)) * L + self.x.astype(np.int64)
+
+
+def build_hierarchy(pos_sorted: np.ndarray, lgrid_dom: int, lgrid_max: int = 1 << 21, nth_dom: float = 2.0,
+                    nth_ref: float = 2.5) -> list[Level]:
+    pos_sorted = np.ascontiguousarray(pos_sorted, dtype=np.float32)
+    L = lib()
+    h = L.orc_hier_build(_p(pos_sorted), pos_sorted.shape[0], lgrid_dom, lgrid_max, nth_dom, nth_ref)
+    out = []
+    try:
+        for lev in range(L.orc_hier_nlevels(h)):
+            io = np.zeros(4, dtype=np.int64)
+            do = np.zeros(2, dtype=np.float64)
+            L.orc_hier_level_header(h, lev, _p(io), _p(do))
+            nc, nf, nfin = int(io[1]), int(io[2]), int(io[3])
+            x = np.empty(nc, np.int32); y = np.empty(nc, np.int32); z = np.empty(nc, np.int32)
+            dens = np.empty(nc, np.float32); rf = np.empty(nc, np.uint8); it = np.empty(nc, np.uint8)
+            mk = np.empty(nc, np.uint8); cf = np.empty(nc, np.int32); pf = np.empty(max(nf, 1), np.int64)
+            cfin = np.empty(nc, np.int32); pfin = np.empty(max(nfin, 1), np.int64)
+            L.orc_hier_level_get(h, lev, _p(x), _p(y), _p(z), _p(dens), _p(rf), _p(it), _p(mk), _p(cf), _p(pf),
+                                 _p(cfin), _p(pfin))
+            out.append(Level(int(io[0]), nc, float(do[0]), float(do[1]), x, y, z, dens, rf, cf, pf[:nf], it, mk,
+                             cfin, pfin[:nfin]))
+    finally:
+        L.orc_hier_free(h)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# readers for the reference dumps
+@dataclass
+class RefParticles:
+    n: int
+    boxsize: float
+    pmass: float
+    t_unit: float
+    a: float
+    omega0: float
+    lambda0: float
+    no_vpart: float
+    ids: np.ndarray
+    keys: np.ndarray
+    pos: np.ndarray
+    mom: np.ndarray
+    weight: np.ndarray | None = None
+    u: np.ndarray | None = None
+
+
+def read_particles(path: str, multimass: bool = False) -> RefParticles:
+    with open(path, "rb") as f:
+        n = int(np.fromfile(f, np.uint64, 1)[0])
+        sc = np.fromfile(f, np.float64, 8)
+        ids = np.fromfile(f, np.uint64, n)
+        keys = np.fromfile(f, np.uint64, n)
+        pos = np.fromfile(f, np.float32, 3 * n).reshape(n, 3)
+        mom = np.fromfile(f, np.float32, 3 * n).reshape(n, 3)
+        w = u = None
+        if multimass:
+            w = np.fromfile(f, np.float32, n)
+            u = np.fromfile(f, np.float32, n)
+    return RefParticles(n, sc[0], sc[1], sc[2], sc[3], sc[4], sc[5], sc[6], ids, keys, pos, mom, w, u)
+
+
+def read_level(path: str) -> Level:
+    with open(path, "rb") as f:
+        hdr = np.fromfile(f, np.int64, 4)
+        dh = np.fromfile(f, np.float64, 2)
+        nc, npart = int(hdr[1]), int(hdr[2])
+        x = np.fromfile(f, np.int32, nc); y = np.fromfile(f, np.int32, nc); z = np.fromfile(f, np.int32, nc)
+        dens = np.fromfile(f, np.float32, nc)
+        flg = np.fromfile(f, np.uint8, nc)
+        cnt = np.fromfile(f, np.int32, nc)
+        pl = np.fromfile(f, np.int64, npart)
+    return Level(int(hdr[0]), nc, float(dh[0]), float(dh[1]), x, y, z, dens, flg, cnt, pl)
+
+
+@dataclass
+class RefHalos:
+    n: int
+    glob: np.ndarray            # 16 doubles: r_fac x_fac v_fac m_fac rho_fac phi_fac Hubble ovlim rho_vir minpart vtune maxgather a
+    s: np.ndarray               # (n, 64) scalar slots, layout in oracle/ref_hooks.c dump_halos()
+    members: list = field(default_factory=list)
+    prof: list = field(default_factory=list)    # per halo (25, nbins) or None
+
+
+def read_halos(dump_dir: str) -> RefHalos:
+    with open(os.path.join(dump_dir, "halos.bin"), "rb") as f:
+        hdr = np.fromfile(f, np.int64, 2)
+        g = np.fromfile(f, np.float64, 16)
+        n, ns = int(hdr[0]), int(hdr[1])
+        s = np.fromfile(f, np.float64, n * ns).reshape(n, ns)
+    members, prof = [], []
+    with open(os.path.join(dump_dir, "halo_ipart.bin"), "rb") as f:
+        for _ in range(n):
+            m = int(np.fromfile(f, np.int64, 1)[0])
+            members.append(np.fromfile(f, np.int64, m))
+    with open(os.path.join(dump_dir, "halo_prof.bin"), "rb") as f:
+        for _ in range(n):
+            nb = int(np.fromfile(f, np.int64, 1)[0])
+            prof.append(np.fromfile(f, np.float64, 25 * nb).reshape(25, nb) if nb > 0 else None)
+    return RefHalos(n, g, s, members, prof)
+
+
+def run_reference(ahf_input: str, dump_dir: str | None = None, threads: int | None = None, multimass: bool = False,
+                  cwd: str | None = None) -> dict:
+    """Run the hooked, otherwise unmodified reference binary; returns the REFHOOK_TIMING fields."""
+    env = dict(os.environ)
+    if dump_dir is not None:
+        os.makedirs(dump_dir, exist_ok=True)
+        env["AHF_DUMP_DIR"] = dump_dir
+    else:
+        env.pop("AHF_DUMP_DIR", None)
+    if threads is not None:
+        env["OMP_NUM_THREADS"] = str(threads)
+    exe = REF_BIN_MM if multimass else REF_BIN
+    if not os.path.exists(exe):
+        raise FileNotFoundError(f"{exe} missing: run oracle/build_ref.sh where /root/reference exists")
+    pr = subprocess.run([exe, ahf_input], cwd=cwd or os.path.dirname(ahf_input), env=env, capture_output=True, text=True)
+    if pr.returncode != 0:
+        raise RuntimeError(f"reference failed ({pr.returncode}): {pr.stderr[-2000:]}")
+    out = {}
+    for line in pr.stderr.splitlines():
+        if line.startswith("REFHOOK_TIMING"):
+            for tok in line.split()[1:]:
+                k, v = tok.split("=")
+                out[k] = float(v)
+    return out
