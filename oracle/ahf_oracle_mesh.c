@@ -435,7 +435,7 @@ static void run_offsets(int wrapped, int64_t r0, int64_t r1, int64_t L, int *low
 
 static void level_mark_refinement(olevel *lv)
 {
-  int64_t  L = lv->L, c, nrow = 0, npl = 0, ir, ip;
+  int64_t  L = lv->L, c, nrow = 0, npl = 0, ir;
   orow    *rows;
   oplane  *pl;
   /* row / plane tables from the sorted cell list */

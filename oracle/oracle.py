@@ -219,3 +219,49 @@ def run_reference(ahf_input: str, dump_dir: str | None = None, threads: int | No
                 k, v = tok.split("=")
                 out[k] = float(v)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+class _HaloParams(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("r_fac", "x_fac", "v_fac", "m_fac", "rho_fac", "phi_fac", "Hubble", "ovlim",
+                                          "rho_vir", "vesc_tune")] + [("min_part", C.c_int)]
+
+
+class _HaloResult(C.Structure):
+    _fields_ = [("npart", C.c_int64), ("ipart", C.POINTER(C.c_int64)), ("n_gather", C.c_int64), ("n_rvir0", C.c_int64),
+                ("n_unbound", C.c_int64), ("n_rvir1", C.c_int64), ("s", C.c_double * 64), ("nbins", C.c_int),
+                ("prof", C.POINTER(C.c_double))]
+
+
+def params_from_glob(g: np.ndarray) -> dict:
+    """glob = the 16 doubles written by ref_hooks.c dump_halos()"""
+    return dict(r_fac=g[0], x_fac=g[1], v_fac=g[2], m_fac=g[3], rho_fac=g[4], phi_fac=g[5], Hubble=g[6], ovlim=g[7],
+                rho_vir=g[8], min_part=int(g[9]), vesc_tune=g[10])
+
+
+def construct_halos(keys, pos, mom, weight, u, par: dict, centres, gather_rad, seed_npart=None) -> list[dict]:
+    keys = np.ascontiguousarray(keys, np.uint64); pos = np.ascontiguousarray(pos, np.float32)
+    mom = np.ascontiguousarray(mom, np.float32)
+    weight = None if weight is None else np.ascontiguousarray(weight, np.float32)
+    u = None if u is None else np.ascontiguousarray(u, np.float32)
+    hp = _HaloParams(**{k: par[k] for k in ("r_fac", "x_fac", "v_fac", "m_fac", "rho_fac", "phi_fac", "Hubble", "ovlim",
+                                            "rho_vir", "vesc_tune")}, min_part=int(par["min_part"]))
+    L = lib()
+    out = []
+    for i in range(len(gather_rad)):
+        if seed_npart is not None and seed_npart[i] == 0:      # ahf_halos_sfc.c:122 -- nothing to construct
+            out.append(dict(npart=0, ipart=np.empty(0, np.int64), n_gather=0, n_rvir0=0, n_unbound=0, n_rvir1=0,
+                            s=np.zeros(64), prof=None, nbins=0))
+            continue
+        r = _HaloResult()
+        c = np.ascontiguousarray(centres[i], np.float64)
+        L.orc_halo_construct(_p(keys), _p(pos), _p(mom), _p(weight), _p(u), keys.shape[0], C.byref(hp), _p(c),
+                             float(gather_rad[i]), C.byref(r))
+        ip = np.ctypeslib.as_array(r.ipart, shape=(max(int(r.npart), 1),))[:int(r.npart)].copy() if r.npart > 0 else np.empty(0, np.int64)
+        pr = None
+        if r.nbins > 0:
+            pr = np.ctypeslib.as_array(r.prof, shape=(25 * r.nbins,)).copy().reshape(25, r.nbins)
+        out.append(dict(npart=int(r.npart), ipart=ip, n_gather=int(r.n_gather), n_rvir0=int(r.n_rvir0),
+                        n_unbound=int(r.n_unbound), n_rvir1=int(r.n_rvir1), s=np.array(r.s[:]), prof=pr, nbins=int(r.nbins)))
+        L.orc_halo_result_free(C.byref(r))
+    return out
