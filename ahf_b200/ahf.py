@@ -1,0 +1,283 @@
+"""Host-side view of libahfgpu.so (include/ahfgpu.h) for Python callers: tests, bench.py, smoke().
+
+The reference (NegriAndrea/AHF) is a C program; its own host code binds the same C-ABI directly
+(INTEGRATION.md).  This module mirrors the reference's call order for the path --
+
+    startrun -> [keys + sort, main.c:343-356] -> [gen_domgrids..gen_AMRhierarchy, main.c:616-648]
+             -> (ahf_gridinfo / tree, host C) -> [halo loop, ahf_halos.c:504-510]
+
+-- and keeps its names for parameters (AHF.input keys) and results (HALO / HALOPROFILE fields).
+There is no CPU fallback: every method raises if the CUDA library is missing or reports an error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libahfgpu.so")
+NSCAL = 64
+NPROFCOL = 25
+
+H0 = 100.0
+RHOC0 = 2.7755397e11
+GRAV = 4.3006485e-9
+
+
+class AhfGpuError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("device", C.c_int32), ("lgrid_dom", C.c_int32), ("lgrid_max", C.c_int32), ("min_part", C.c_int32),
+                ("nth_dom", C.c_double), ("nth_ref", C.c_double), ("vesc_tune", C.c_double),
+                ("r_fac", C.c_double), ("x_fac", C.c_double), ("v_fac", C.c_double), ("m_fac", C.c_double),
+                ("rho_fac", C.c_double), ("phi_fac", C.c_double), ("hubble", C.c_double), ("ovlim", C.c_double),
+                ("rho_vir", C.c_double)]
+
+
+def make_params(*, boxsize: float, pmass: float, lgrid_dom: int, device: int = 0, lgrid_max: int = 1 << 21,
+                nper_dom: float = 2.0, nper_ref: float = 2.5, vesc_tune: float = 1.5, nmin: int = 20,
+                a: float = 1.0, omega0: float = 0.3, lambda0: float = 0.7, dvir: float = 200.0) -> Params:
+    """AHF.input-example settings (RhoVir = 0: densities normalised to rho_crit; Dvir > 0 fixes ovlim) and the
+    unit factors of reference src/libahf/ahf_halos.c:199-221 for a snapshot at expansion factor `a`."""
+    t_unit = 1.0 / H0
+    ez2 = omega0 / a ** 3 + (1.0 - omega0 - lambda0) / a ** 2 + lambda0        # (H/H0)^2
+    hubble = H0 * np.sqrt(ez2)
+    rho_crit_a = RHOC0 * ez2                                                     # physical rho_crit(a)
+    return Params(device=device, lgrid_dom=lgrid_dom, lgrid_max=min(lgrid_max, 1 << 21), min_part=nmin,
+                  nth_dom=nper_dom, nth_ref=nper_ref, vesc_tune=vesc_tune,
+                  r_fac=boxsize * a, x_fac=boxsize, v_fac=boxsize / t_unit / a, m_fac=pmass,
+                  rho_fac=pmass / boxsize ** 3, phi_fac=GRAV * pmass / (boxsize * a), hubble=hubble, ovlim=dvir,
+                  rho_vir=a ** 3 * rho_crit_a)
+
+
+def params_from_reference(glob: np.ndarray, *, lgrid_dom: int, device: int = 0, nper_dom: float = 2.0,
+                          nper_ref: float = 2.5, lgrid_max: int = 1 << 21) -> Params:
+    """Params from the 16 doubles the hooked reference dumps (oracle/ref_hooks.c dump_halos)."""
+    return Params(device=device, lgrid_dom=lgrid_dom, lgrid_max=lgrid_max, min_part=int(glob[9]), nth_dom=nper_dom,
+                  nth_ref=nper_ref, vesc_tune=glob[10], r_fac=glob[0], x_fac=glob[1], v_fac=glob[2], m_fac=glob[3],
+                  rho_fac=glob[4], phi_fac=glob[5], hubble=glob[6], ovlim=glob[7], rho_vir=glob[8])
+
+
+_lib = None
+
+
+def build(force: bool = False) -> None:
+    """nvcc -gencode arch=compute_100a,code=sm_100a (cross-compiles without a GPU)."""
+    src = os.path.join(HERE, "csrc")
+    files = [os.path.join(src, f) for f in os.listdir(src) if f.endswith((".cu", ".cuh"))]
+    files.append(os.path.join(HERE, "..", "include", "ahfgpu.h"))
+    if (not force and os.path.exists(LIB_PATH)
+            and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(f) for f in files)):
+        return
+    subprocess.check_call(["make", "-s", "-C", src, "-j4"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise AhfGpuError(f"{LIB_PATH} not built (run __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.ahfgpu_last_error.restype = C.c_char_p
+        L.ahfgpu_init.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Params)]
+        L.ahfgpu_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
+        L.ahfgpu_finalize.argtypes = [C.c_void_p]
+        L.ahfgpu_sfc_sort_particles.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32] + [C.c_int32] * 6
+        L.ahfgpu_sfc_sort_soa.argtypes = [C.c_void_p] * 5 + [C.c_uint64, C.c_void_p, C.c_void_p]
+        L.ahfgpu_hilbert_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
+        L.ahfgpu_build_amr.argtypes = [C.c_void_p]
+        L.ahfgpu_amr_nlevels.argtypes = [C.c_void_p]
+        L.ahfgpu_amr_level_header.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        L.ahfgpu_amr_level_get.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 8
+        L.ahfgpu_amr_particle_levels.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+        L.ahfgpu_construct_halos.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ahfgpu_halo_sizes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ahfgpu_halo_fetch.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        L.ahfgpu_stage_ms.restype = C.c_double
+        L.ahfgpu_stage_ms.argtypes = [C.c_void_p, C.c_char_p]
+        L.ahfgpu_stage_count.restype = C.c_int64
+        L.ahfgpu_stage_count.argtypes = [C.c_void_p, C.c_char_p]
+        _lib = L
+    return _lib
+
+
+def exported_symbols() -> list[str]:
+    """Every entry point include/ahfgpu.h declares."""
+    hdr = open(os.path.join(HERE, "..", "include", "ahfgpu.h")).read()
+    import re
+    return sorted(set(re.findall(r"\b(ahfgpu_[a-z_0-9]+)\s*\(", hdr)))
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data if isinstance(a, np.ndarray) else int(a))
+
+
+@dataclass
+class GpuLevel:
+    l1dim: int
+    ncell: int
+    npart_dep: int
+    npart_final: int
+    critdens: float
+    masstopartdens: float
+    x: np.ndarray
+    y: np.ndarray
+    z: np.ndarray
+    dens: np.ndarray
+    runflags: np.ndarray
+    interior: np.ndarray
+    mark: np.ndarray
+    count: np.ndarray
+
+    def lin(self) -> np.ndarray:
+        L = np.int64(self.l1dim)
+        return (self.z.astype(np.int64) * L + self.y.astype(np.int64)) * L + self.x.astype(np.int64)
+
+
+class AhfGpu:
+    """One context = one device = one resident particle set."""
+
+    def __init__(self, params: Params):
+        self._L = lib()
+        self._h = C.c_void_p()
+        self.params = params
+        self._chk(self._L.ahfgpu_init(C.byref(self._h), C.byref(params)))
+        self.n = 0
+
+    def _chk(self, rc: int):
+        if rc != 0:
+            raise AhfGpuError(self._L.ahfgpu_last_error().decode())
+
+    def close(self):
+        if self._h:
+            self._L.ahfgpu_finalize(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_params(self, params: Params):
+        self.params = params
+        self._chk(self._L.ahfgpu_set_params(self._h, C.byref(params)))
+
+    # ---- K1 / K2 -------------------------------------------------------------------------------
+    def hilbert_keys(self, pos: np.ndarray, bits: int = 21) -> np.ndarray:
+        pos = np.ascontiguousarray(pos, np.float32)
+        keys = np.empty(pos.shape[0], np.uint64)
+        self._chk(self._L.ahfgpu_hilbert_keys(self._h, _p(pos), pos.shape[0], bits, _p(keys)))
+        return keys
+
+    def sfc_sort(self, pos, mom, weight=None, u=None, want_keys=True, want_order=True, keys_out=None, order_out=None):
+        """pos/mom: (N,3) float32 host arrays or raw host pointers (ints, e.g. pinned torch tensors' data_ptr)."""
+        if isinstance(pos, np.ndarray):
+            pos = np.ascontiguousarray(pos, np.float32); mom = np.ascontiguousarray(mom, np.float32)
+            n = pos.shape[0]
+        else:
+            raise TypeError("use sfc_sort_ptr for raw pointers")
+        weight = None if weight is None else np.ascontiguousarray(weight, np.float32)
+        u = None if u is None else np.ascontiguousarray(u, np.float32)
+        keys = keys_out if keys_out is not None else (np.empty(n, np.uint64) if want_keys else None)
+        order = order_out if order_out is not None else (np.empty(n, np.uint32) if want_order else None)
+        self._chk(self._L.ahfgpu_sfc_sort_soa(self._h, _p(pos), _p(mom), _p(weight), _p(u), n, _p(keys), _p(order)))
+        self.n = n
+        return keys, order
+
+    def sfc_sort_ptr(self, pos_ptr: int, mom_ptr: int, n: int, keys_ptr: int = 0, order_ptr: int = 0):
+        self._chk(self._L.ahfgpu_sfc_sort_soa(self._h, C.c_void_p(pos_ptr), C.c_void_p(mom_ptr), None, None, n,
+                                              C.c_void_p(keys_ptr) if keys_ptr else None,
+                                              C.c_void_p(order_ptr) if order_ptr else None))
+        self.n = n
+
+    def sfc_sort_particles(self, part: np.ndarray, off_pos: int, off_mom: int, off_key: int, off_id: int,
+                           off_weight: int = -1, off_u: int = -1):
+        """`part`: structured/byte array laid out like the reference's struct particle[] (sorted in place)."""
+        n, stride = part.shape[0], part.strides[0]
+        self._chk(self._L.ahfgpu_sfc_sort_particles(self._h, _p(part), n, stride, off_pos, off_mom, off_key, off_id,
+                                                    off_weight, off_u))
+        self.n = n
+
+    # ---- D / F / R / L -------------------------------------------------------------------------
+    def build_amr(self) -> int:
+        self._chk(self._L.ahfgpu_build_amr(self._h))
+        return self._L.ahfgpu_amr_nlevels(self._h)
+
+    def nlevels(self) -> int:
+        return self._L.ahfgpu_amr_nlevels(self._h)
+
+    def level_header(self, lev: int):
+        io = np.zeros(4, np.int64); do = np.zeros(2, np.float64)
+        self._chk(self._L.ahfgpu_amr_level_header(self._h, lev, _p(io), _p(do)))
+        return io, do
+
+    def level(self, lev: int, cells: bool = True) -> GpuLevel:
+        io, do = self.level_header(lev)
+        nc = int(io[1])
+        x = np.empty(nc, np.int32); y = np.empty(nc, np.int32); z = np.empty(nc, np.int32)
+        dens = np.empty(nc, np.float32); rf = np.empty(nc, np.uint8); it = np.empty(nc, np.uint8)
+        mk = np.empty(nc, np.uint8); cnt = np.empty(nc, np.int32)
+        if cells:
+            self._chk(self._L.ahfgpu_amr_level_get(self._h, lev, _p(x), _p(y), _p(z), _p(dens), _p(rf), _p(it), _p(mk), _p(cnt)))
+        else:
+            self._chk(self._L.ahfgpu_amr_level_get(self._h, lev, None, None, None, _p(dens), None, None, _p(mk), _p(cnt)))
+        return GpuLevel(int(io[0]), nc, int(io[2]), int(io[3]), float(do[0]), float(do[1]), x, y, z, dens, rf, it, mk, cnt)
+
+    def particle_levels(self, with_cells: bool = True):
+        nl = self.nlevels()
+        owner = np.empty(self.n, np.int8)
+        cells = np.empty((nl, self.n), np.int32) if with_cells else None
+        self._chk(self._L.ahfgpu_amr_particle_levels(self._h, _p(owner), _p(cells), nl))
+        return owner, cells
+
+    # ---- G / U / P -----------------------------------------------------------------------------
+    def construct_halos(self, centres: np.ndarray, gather_rad: np.ndarray, seed_npart: np.ndarray | None = None,
+                        fetch: bool = True):
+        centres = np.ascontiguousarray(centres, np.float64); gather_rad = np.ascontiguousarray(gather_rad, np.float64)
+        nh = gather_rad.shape[0]
+        seed = None if seed_npart is None else np.ascontiguousarray(seed_npart, np.int64)
+        self._chk(self._L.ahfgpu_construct_halos(self._h, nh, _p(centres), _p(gather_rad), _p(seed)))
+        if not fetch:
+            return None
+        return self.fetch_halos(nh)
+
+    def fetch_halos(self, nh: int, scal_only: bool = False):
+        tm = C.c_int64(); tb = C.c_int64()
+        self._chk(self._L.ahfgpu_halo_sizes(self._h, C.byref(tm), C.byref(tb)))
+        scal = np.empty((nh, NSCAL), np.float64)
+        if scal_only:
+            self._chk(self._L.ahfgpu_halo_fetch(self._h, _p(scal), None, None, None, None))
+            return dict(scal=scal)
+        moff = np.empty(nh + 1, np.int64); poff = np.empty(nh + 1, np.int64)
+        members = np.empty(max(tm.value, 1), np.int64); prof = np.empty(max(tb.value, 1) * NPROFCOL, np.float64)
+        self._chk(self._L.ahfgpu_halo_fetch(self._h, _p(scal), _p(moff), _p(members), _p(poff), _p(prof)))
+        return dict(scal=scal, member_offset=moff, members=members[:tm.value], prof_offset=poff, prof=prof[:tb.value * NPROFCOL])
+
+    @staticmethod
+    def halo_members(res: dict, i: int) -> np.ndarray:
+        return res["members"][res["member_offset"][i]:res["member_offset"][i + 1]]
+
+    @staticmethod
+    def halo_profile(res: dict, i: int):
+        a, b = res["prof_offset"][i], res["prof_offset"][i + 1]
+        nb = int(b - a)
+        if nb == 0:
+            return None
+        return res["prof"][a * NPROFCOL:b * NPROFCOL].reshape(NPROFCOL, nb)
+
+    # ---- measurement ---------------------------------------------------------------------------
+    def stage_ms(self, name: str) -> float:
+        return float(self._L.ahfgpu_stage_ms(self._h, name.encode()))
+
+    def stage_count(self, name: str) -> int:
+        return int(self._L.ahfgpu_stage_count(self._h, name.encode()))
+
+    def launches(self) -> int:
+        return self.stage_count("launches")

@@ -1,0 +1,223 @@
+// api.cu -- extern "C" entry points of libahfgpu.so (see include/ahfgpu.h) and context housekeeping.
+#include "common.cuh"
+
+namespace ahf {
+thread_local std::string g_last_error;
+
+void Level::free_all()
+{
+  cudaFree(ckey); cudaFree(xbreak); cudaFree(dens); cudaFree(interior); cudaFree(tn); cudaFree(mark); cudaFree(nbr);
+  cudaFree(crow); cudaFree(count); cudaFree(hkey); cudaFree(hval); cudaFree(rowkey); cudaFree(row_c0); cudaFree(row_tested);
+  cudaFree(plane_r0); cudaFree(rowplane); cudaFree(plist); cudaFree(pcell);
+  *this = Level();
+}
+}  // namespace ahf
+
+using namespace ahf;
+
+void ahfgpu_ctx::stage_reset()
+{
+  for (auto &s : stages) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+  stages.clear(); stage_ms.clear(); stage_cnt.clear(); stages_resolved = true;
+}
+void ahfgpu_ctx::stage_resolve()
+{
+  if (stages_resolved) return;
+  stage_ms.clear(); stage_cnt.clear();
+  for (auto &s : stages) {
+    float ms = 0.f;
+    cudaEventSynchronize(s.b);
+    cudaEventElapsedTime(&ms, s.a, s.b);
+    stage_ms[s.name] += ms; stage_cnt[s.name] += s.count;
+  }
+  stages_resolved = true;
+}
+void ahfgpu_ctx::free_particles()
+{
+  cudaFree(pos4); cudaFree(mom4); cudaFree(keys); cudaFree(order);
+  pos4 = mom4 = nullptr; keys = nullptr; order = nullptr; n = 0;
+}
+void ahfgpu_ctx::free_levels()
+{
+  for (auto &l : levels) l.free_all();
+  levels.clear();
+  cudaFree(owner_level); owner_level = nullptr;
+}
+void ahfgpu_ctx::free_halos()
+{
+  cudaFree(h_scal); cudaFree(h_moff); cudaFree(h_members); cudaFree(h_poff); cudaFree(h_prof);
+  h_scal = nullptr; h_moff = nullptr; h_members = nullptr; h_poff = nullptr; h_prof = nullptr;
+  nhalo = 0; h_total_members = h_total_bins = 0;
+}
+
+#define API_BEGIN try {
+#define API_END                                                                                         \
+  return 0; }                                                                                           \
+  catch (const ahf::Error &e) { ahf::g_last_error = e.msg; return -1; }                                  \
+  catch (const std::exception &e) { ahf::g_last_error = e.what(); return -2; }
+
+static void check_params(const ahfgpu_params *p)
+{
+  if (!p) AHF_FAIL("null params");
+  if (p->lgrid_dom < 4 || (p->lgrid_dom & (p->lgrid_dom - 1)) != 0) AHF_FAIL("lgrid_dom must be a power of two >= 4");
+  if (p->lgrid_dom > (1 << 21)) AHF_FAIL("lgrid_dom above 2^21");
+}
+
+extern "C" {
+
+const char *ahfgpu_last_error(void) { return ahf::g_last_error.c_str(); }
+
+int ahfgpu_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int ahfgpu_init(ahfgpu_ctx **out, const ahfgpu_params *par)
+{
+  API_BEGIN
+  if (!out) AHF_FAIL("null ctx pointer");
+  check_params(par);
+  int ndev = 0;
+  CUDA_CHECK(cudaGetDeviceCount(&ndev));
+  if (ndev <= 0) AHF_FAIL("no CUDA device: libahfgpu has no CPU fallback");
+  if (par->device < 0 || par->device >= ndev) AHF_FAIL("device ordinal out of range");
+  CUDA_CHECK(cudaSetDevice(par->device));
+  ahfgpu_ctx *c = new ahfgpu_ctx();
+  c->par = *par; c->dev = par->device;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  *out = c;
+  API_END
+}
+
+int ahfgpu_set_params(ahfgpu_ctx *c, const ahfgpu_params *par)
+{
+  API_BEGIN
+  if (!c) AHF_FAIL("null ctx");
+  check_params(par);
+  int dev = c->dev;
+  c->par = *par; c->par.device = dev;
+  API_END
+}
+
+int ahfgpu_finalize(ahfgpu_ctx *c)
+{
+  API_BEGIN
+  if (!c) return 0;
+  cudaSetDevice(c->dev);
+  cudaStreamSynchronize(c->stream);
+  c->stage_reset(); c->free_halos(); c->free_levels(); c->free_particles();
+  cudaStreamDestroy(c->stream);
+  delete c;
+  API_END
+}
+
+int ahfgpu_sfc_sort_particles(ahfgpu_ctx *c, void *part, uint64_t n, uint32_t stride, int32_t off_pos, int32_t off_mom,
+                              int32_t off_key, int32_t off_id, int32_t off_weight, int32_t off_u)
+{
+  API_BEGIN
+  if (!c || (!part && n)) AHF_FAIL("null argument");
+  CUDA_CHECK(cudaSetDevice(c->dev));
+  c->stage_reset();
+  sfc_sort_aos(c, part, n, stride, off_pos, off_mom, off_key, off_id, off_weight, off_u);
+  API_END
+}
+
+int ahfgpu_sfc_sort_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, const float *weight, const float *u, uint64_t n,
+                        uint64_t *keys_out, uint32_t *order_out)
+{
+  API_BEGIN
+  if (!c || ((!pos3 || !mom3) && n)) AHF_FAIL("null argument");
+  CUDA_CHECK(cudaSetDevice(c->dev));
+  c->stage_reset();
+  sfc_sort_soa(c, pos3, mom3, weight, u, n, keys_out, order_out);
+  API_END
+}
+
+int ahfgpu_hilbert_keys(ahfgpu_ctx *c, const float *pos3, uint64_t n, uint32_t bits, uint64_t *keys_out)
+{
+  API_BEGIN
+  if (!c || ((!pos3 || !keys_out) && n)) AHF_FAIL("null argument");
+  if (bits < 1 || bits > 21) AHF_FAIL("bits must be in 1..21");
+  CUDA_CHECK(cudaSetDevice(c->dev));
+  c->stage_reset();
+  sfc_keys_only(c, pos3, n, bits, keys_out);
+  API_END
+}
+
+int ahfgpu_build_amr(ahfgpu_ctx *c)
+{
+  API_BEGIN
+  if (!c) AHF_FAIL("null ctx");
+  if (!c->pos4) AHF_FAIL("no resident particles: call ahfgpu_sfc_sort_* first");
+  CUDA_CHECK(cudaSetDevice(c->dev));
+  c->stage_reset();
+  amr_build(c);
+  API_END
+}
+
+int ahfgpu_amr_nlevels(ahfgpu_ctx *c) { return c ? (int)c->levels.size() : -1; }
+
+int ahfgpu_amr_level_header(ahfgpu_ctx *c, int32_t lev, int64_t *iout, double *dout)
+{
+  API_BEGIN
+  if (!c || lev < 0 || lev >= (int)c->levels.size()) AHF_FAIL("bad level");
+  const Level &l = c->levels[lev];
+  if (iout) { iout[0] = l.L; iout[1] = l.ncell; iout[2] = l.npart_dep; iout[3] = l.npart_final; }
+  if (dout) { dout[0] = l.critdens; dout[1] = l.masstopartdens; }
+  API_END
+}
+
+int ahfgpu_halo_sizes(ahfgpu_ctx *c, int64_t *total_members, int64_t *total_bins)
+{
+  API_BEGIN
+  if (!c) AHF_FAIL("null ctx");
+  if (total_members) *total_members = c->h_total_members;
+  if (total_bins) *total_bins = c->h_total_bins;
+  API_END
+}
+
+int ahfgpu_construct_halos(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const double *gather_rad, const int64_t *seed)
+{
+  API_BEGIN
+  if (!c) AHF_FAIL("null ctx");
+  if (!c->pos4) AHF_FAIL("no resident particles: call ahfgpu_sfc_sort_* first");
+  if (nhalo && (!centre3 || !gather_rad)) AHF_FAIL("null argument");
+  CUDA_CHECK(cudaSetDevice(c->dev));
+  c->stage_reset();
+  halos_construct(c, nhalo, centre3, gather_rad, seed);
+  API_END
+}
+
+int ahfgpu_halo_fetch(ahfgpu_ctx *c, double *scal, int64_t *member_offset, int64_t *members, int64_t *prof_offset, double *prof)
+{
+  API_BEGIN
+  if (!c) AHF_FAIL("null ctx");
+  CUDA_CHECK(cudaSetDevice(c->dev));
+  if (scal && c->nhalo) CUDA_CHECK(cudaMemcpy(scal, c->h_scal, sizeof(double) * AHFGPU_NSCAL * c->nhalo, cudaMemcpyDeviceToHost));
+  if (member_offset) CUDA_CHECK(cudaMemcpy(member_offset, c->h_moff, sizeof(int64_t) * (c->nhalo + 1), cudaMemcpyDeviceToHost));
+  if (members && c->h_total_members) CUDA_CHECK(cudaMemcpy(members, c->h_members, sizeof(int64_t) * c->h_total_members, cudaMemcpyDeviceToHost));
+  if (prof_offset) CUDA_CHECK(cudaMemcpy(prof_offset, c->h_poff, sizeof(int64_t) * (c->nhalo + 1), cudaMemcpyDeviceToHost));
+  if (prof && c->h_total_bins) CUDA_CHECK(cudaMemcpy(prof, c->h_prof, sizeof(double) * AHFGPU_NPROFCOL * c->h_total_bins, cudaMemcpyDeviceToHost));
+  API_END
+}
+
+double ahfgpu_stage_ms(ahfgpu_ctx *c, const char *name)
+{
+  if (!c || !name) return -1.0;
+  c->stage_resolve();
+  auto it = c->stage_ms.find(name);
+  return it == c->stage_ms.end() ? -1.0 : it->second;
+}
+
+int64_t ahfgpu_stage_count(ahfgpu_ctx *c, const char *name)
+{
+  if (!c || !name) return -1;
+  if (!strcmp(name, "launches")) return c->n_launches;
+  c->stage_resolve();
+  auto it = c->stage_cnt.find(name);
+  return it == c->stage_cnt.end() ? -1 : it->second;
+}
+
+}  // extern "C"

@@ -1,0 +1,150 @@
+// common.cuh -- context, error handling, stage timers shared by the libahfgpu translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/ahfgpu.h"
+
+namespace ahf {
+
+extern thread_local std::string g_last_error;
+
+struct Error { std::string msg; };
+
+inline void fail(const char *file, int line, const std::string &what)
+{
+  char buf[64];
+  snprintf(buf, sizeof(buf), " (%s:%d)", file, line);
+  throw Error{what + buf};
+}
+#define AHF_FAIL(msg) ::ahf::fail(__FILE__, __LINE__, (msg))
+#define CUDA_CHECK(expr)                                                                                 \
+  do {                                                                                                   \
+    cudaError_t e__ = (expr);                                                                            \
+    if (e__ != cudaSuccess) ::ahf::fail(__FILE__, __LINE__, std::string(#expr ": ") + cudaGetErrorString(e__)); \
+  } while (0)
+
+// every kernel launch of the library goes through this macro so that launches can be counted (bench.py gpu_launches)
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                                                      \
+  do {                                                                                                   \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                                     \
+    (ctx)->n_launches++;                                                                                 \
+    CUDA_CHECK(cudaGetLastError());                                                                      \
+  } while (0)
+
+template <typename T> struct DevBuf {
+  T     *p   = nullptr;
+  size_t cap = 0;
+  void reserve(size_t n)
+  {
+    if (n <= cap) return;
+    if (p) CUDA_CHECK(cudaFree(p));
+    p = nullptr; cap = 0;
+    CUDA_CHECK(cudaMalloc(&p, (n ? n : 1) * sizeof(T)));
+    cap = n ? n : 1;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// one refinement level on the device (see DESIGN.md "data layout")
+struct Level {
+  int64_t  L = 0;           // l1dim
+  int64_t  ncell = 0;
+  bool     dense = false;   // domain level: cell index == (z*L+y)*L+x, no key list / hash
+  uint64_t *ckey = nullptr;     // [ncell] sorted linear keys (z*L+y)*L+x          (sparse levels)
+  uint8_t  *xbreak = nullptr;   // [ncell] reference nquad run ends after this cell (sparse levels)
+  float    *dens = nullptr;     // [ncell]
+  uint8_t  *interior = nullptr; // [ncell] (sparse levels; dense => all interior)
+  uint8_t  *tn = nullptr;       // [ncell] test_node()
+  uint8_t  *mark = nullptr;     // [ncell] 0 / 1 refined / 2 ghost
+  int32_t  *nbr = nullptr;      // [ncell*27] visible neighbour cell index or -1 (sparse levels)
+  int32_t  *crow = nullptr;     // [ncell] row index                             (sparse levels)
+  int32_t  *count = nullptr;    // [ncell] particles linked when deposited
+  uint64_t *hkey = nullptr; int32_t *hval = nullptr; uint64_t hmask = 0;   // open addressing hash
+  // rows / planes of sparse levels
+  int64_t  nrow = 0, nplane = 0;
+  uint64_t *rowkey = nullptr;   // [nrow] z*L+y
+  int32_t  *row_c0 = nullptr;   // [nrow+1]
+  uint8_t  *row_tested = nullptr;
+  int32_t  *plane_r0 = nullptr; // [nplane+1]
+  int32_t  *rowplane = nullptr; // [nrow]
+  double   critdens = 0, masstopartdens = 0;
+  int64_t  npart_dep = 0, npart_final = 0;
+  // particles that reached this level (ascending sorted offsets) and their cell on this level
+  uint32_t *plist = nullptr;    // [npart_dep]   (nullptr on the domain level = all particles)
+  int32_t  *pcell = nullptr;    // [npart_dep]
+  void free_all();
+};
+
+struct StageRec { std::string name; cudaEvent_t a, b; int64_t count; };
+
+}  // namespace ahf
+
+struct ahfgpu_ctx {
+  ahfgpu_params par{};
+  int           dev = 0;
+  cudaStream_t  stream = nullptr;
+  int64_t       n_launches = 0;
+  // resident sorted particles
+  uint64_t  n = 0;
+  float4   *pos4 = nullptr;     // x,y,z,weight
+  float4   *mom4 = nullptr;     // px,py,pz,u
+  uint64_t *keys = nullptr;
+  uint32_t *order = nullptr;    // input position of sorted particle i
+  bool      has_weight = false, has_u = false;
+  // hierarchy
+  std::vector<ahf::Level> levels;
+  int8_t   *owner_level = nullptr;   // [n]
+  // halo pass results
+  int64_t   nhalo = 0;
+  double   *h_scal = nullptr;        // device [nhalo*NSCAL]
+  int64_t  *h_moff = nullptr;        // device [nhalo+1]
+  int64_t  *h_members = nullptr;     // device
+  int64_t  *h_poff = nullptr;        // device [nhalo+1] (bins)
+  double   *h_prof = nullptr;        // device
+  int64_t   h_total_members = 0, h_total_bins = 0;
+  // stage timing
+  std::vector<ahf::StageRec> stages;
+  std::map<std::string, double>  stage_ms;
+  std::map<std::string, int64_t> stage_cnt;
+  bool stages_resolved = true;
+
+  void stage_reset();
+  void stage_resolve();
+  void free_particles();
+  void free_levels();
+  void free_halos();
+};
+
+namespace ahf {
+
+// RAII stage timer: CUDA events on the library's stream around a group of launches
+struct Stage {
+  ahfgpu_ctx *c; size_t idx;
+  Stage(ahfgpu_ctx *ctx, const char *name, int64_t count = 0) : c(ctx)
+  {
+    StageRec r; r.name = name; r.count = count;
+    CUDA_CHECK(cudaEventCreate(&r.a)); CUDA_CHECK(cudaEventCreate(&r.b));
+    CUDA_CHECK(cudaEventRecord(r.a, c->stream));
+    c->stages.push_back(r); idx = c->stages.size() - 1; c->stages_resolved = false;
+  }
+  ~Stage() { cudaEventRecord(c->stages[idx].b, c->stream); }
+};
+
+// entry points implemented in the .cu files
+void sfc_sort_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, const float *w, const float *u, uint64_t n,
+                  uint64_t *keys_out, uint32_t *order_out);
+void sfc_sort_aos(ahfgpu_ctx *c, void *part, uint64_t n, uint32_t stride, int off_pos, int off_mom, int off_key,
+                  int off_id, int off_w, int off_u);
+void sfc_keys_only(ahfgpu_ctx *c, const float *pos3, uint64_t n, uint32_t bits, uint64_t *keys_out);
+void radix_sort_pairs(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, uint64_t n,
+                      int key_bits, uint64_t **keys_sorted, uint32_t **vals_sorted);
+void amr_build(ahfgpu_ctx *c);
+void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const double *gather_rad, const int64_t *seed);
+
+}  // namespace ahf

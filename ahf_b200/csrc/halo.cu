@@ -1,0 +1,944 @@
+// halo.cu -- G/U/P: per-halo gather, radial sort, virial cut, unbinding, virial cut, profiles (sm_100a).
+//
+// Replaces the OpenMP loop over ahf_halos_sfc_constructHalo (src/libahf/ahf_halos.c:504-510) and its callees
+// gatherParts (ahf_halos_sfc.c:172-412), sort_halo_particles (ahf_halos.c:5786), rem_outsideRvir (:3687),
+// rem_unbound (:3292), HaloProfiles (:3961).  All halo arithmetic is double precision as in the reference.
+// One CTA per halo streams over the radius-sorted members in tiles; every "running" quantity of the
+// reference's inside-out loops is a block scan with a carry, the causal running-mean-velocity test of
+// rem_unbound is solved per tile as a fixed point (mask -> exclusive scan -> mask).  No tensor cores.
+#include "common.cuh"
+#include "hilbert.cuh"
+#include "scan.cuh"
+
+namespace ahf {
+
+constexpr int    HB = 256;                 // threads per halo CTA
+constexpr double MACHINE_ZERO = 5e-16;     // src/param.h:122
+constexpr double ZERO_F = 1e-6;            // src/param.h:121
+constexpr double PI_ = 3.14159265358979323846264338;
+constexpr double GRAV_ = 4.3006485e-9;
+constexpr double GATHERRAD_FAC = 1.001;
+constexpr int    NIGNORE = 5;
+constexpr int    MINPART_SHELL = 10;
+constexpr int    MAXBINS = 64;
+
+struct HP {   // parameters passed by value
+  double r_fac, x_fac, v_fac, m_fac, rho_fac, phi_fac, hubble, ovlim, rho_vir, vesc_tune;
+  int    min_part;
+};
+
+// ------------------------------------------------------------------------------------------------
+// block-wide helpers (HB threads)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_incl_scan(double v)
+{
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { double x = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += x; }
+  return v;
+}
+// inclusive scan over the block; *total = block sum.  sm: HB/32 doubles of shared scratch
+__device__ __forceinline__ double block_incl_scan(double v, double *sm, double *total)
+{
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double inc = warp_incl_scan(v);
+  __syncthreads();
+  if (lane == 31) sm[w] = inc;
+  __syncthreads();
+  double base = 0.0, tot = 0.0;
+#pragma unroll
+  for (int q = 0; q < HB / 32; q++) { double s = sm[q]; if (q < w) base += s; tot += s; }
+  *total = tot;
+  return base + inc;
+}
+__device__ __forceinline__ double block_sum(double v, double *sm)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int q = 0; q < HB / 32; q++) t += sm[q];
+  return t;
+}
+__device__ __forceinline__ int block_sum_i(int v, int *sm)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int t = 0;
+#pragma unroll
+  for (int q = 0; q < HB / 32; q++) t += sm[q];
+  return t;
+}
+__device__ __forceinline__ int block_excl_scan_i(int v, int *sm, int *total)
+{
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+  __syncthreads();
+  if (lane == 31) sm[w] = inc;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int q = 0; q < HB / 32; q++) { int s = sm[q]; if (q < w) base += s; tot += s; }
+  *total = tot;
+  return base + inc - v;
+}
+__device__ __forceinline__ long long block_min_ll(long long v, long long *sm)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { long long x = __shfl_xor_sync(0xffffffffu, v, o); v = x < v ? x : v; }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  long long t = sm[0];
+#pragma unroll
+  for (int q = 1; q < HB / 32; q++) t = sm[q] < t ? sm[q] : t;
+  return t;
+}
+
+// signed minimum-image separation (ahf_halos.c:5829-5841)
+__device__ __forceinline__ void sep3(const float4 &p, const double c[3], double d[3])
+{
+  d[0] = (double)p.x - c[0]; d[1] = (double)p.y - c[1]; d[2] = (double)p.z - c[2];
+#pragma unroll
+  for (int q = 0; q < 3; q++) { if (d[q] > 0.5) d[q] -= 1.0; if (d[q] < -0.5) d[q] += 1.0; }
+}
+__device__ __forceinline__ double dist3(const float4 &p, const double c[3])
+{
+  double d[3];
+  sep3(p, c, d);
+  return sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// G1: key ranges of the (at most 27) search cells of every halo (ahf_halos_sfc.c:172-300, :369-412)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t lower_bound_key(const uint64_t *__restrict__ keys, int64_t n, uint64_t k)
+{
+  int64_t lo = 0, hi = n;
+  while (lo < hi) { int64_t mid = lo + ((hi - lo) >> 1); if (keys[mid] < k) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+__global__ void k_gather_ranges(const uint64_t *__restrict__ keys, int64_t n, const double *__restrict__ centre, const double *__restrict__ grad,
+                                const int64_t *__restrict__ seed, int64_t nhalo, int64_t *__restrict__ rlo, int64_t *__restrict__ rhi,
+                                int64_t *__restrict__ cand)
+{
+  int64_t h = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (h >= nhalo) return;
+  int64_t tot = 0;
+  for (int q = 0; q < 27; q++) { rlo[h * 27 + q] = 0; rhi[h * 27 + q] = 0; }
+  if (seed && seed[h] == 0) { cand[h] = 0; return; }                     // ahf_halos_sfc.c:122
+  const double R = grad[h], cx = centre[3 * h], cy = centre[3 * h + 1], cz = centre[3 * h + 2];
+  unsigned bits = 1;
+  while ((GATHERRAD_FAC * R < 1. / (double)(1 << (bits + 1))) && ((bits + 1) <= 21)) bits++;     // :244-256
+  const unsigned sh = 3 * (21 - bits);
+  if (bits == 1) {
+    for (int q = 0; q < 8; q++) {                                        // :210-217 all octants
+      uint64_t kmin = (uint64_t)q << sh, kmax = kmin + ((1ull << sh) - 1);
+      int64_t  a = lower_bound_key(keys, n, kmin), b = lower_bound_key(keys, n, kmax + 1);
+      rlo[h * 27 + q] = a; rhi[h * 27 + q] = b; tot += b - a;
+    }
+  } else {
+    const uint64_t ckey = hilbert_key_posd(cx, cy, cz, bits);
+    uint32_t bx, by, bz;
+    hilbert_coords(ckey, bits, bx, by, bz);
+    const uint32_t L = 1u << bits;
+    const double   g = 1. / (double)(1ull << bits), big = 0.5 * sqrt(3.) * g;
+    int q = 0;
+    for (int i = -1; i <= 1; i++) for (int j = -1; j <= 1; j++) for (int k = -1; k <= 1; k++, q++) {    // hilbert_util.c:143-154
+      uint32_t x = (bx + L + i) % L, y = (by + L + j) % L, z = (bz + L + k) % L;
+      double dx = fabs((g * x + 0.5 * g) - cx), dy = fabs((g * y + 0.5 * g) - cy), dz = fabs((g * z + 0.5 * g) - cz);
+      if (dx > 0.5) dx = 1.0 - dx; if (dy > 0.5) dy = 1.0 - dy; if (dz > 0.5) dz = 1.0 - dz;
+      if (sqrt(dx * dx + dy * dy + dz * dz) > big + GATHERRAD_FAC * R) continue;                 // :294
+      uint64_t kc = hilbert_index(x, y, z, bits), kmin = kc << sh, kmax = kmin + ((1ull << sh) - 1);
+      int64_t  a = lower_bound_key(keys, n, kmin), b = lower_bound_key(keys, n, kmax + 1);
+      rlo[h * 27 + q] = a; rhi[h * 27 + q] = b; tot += b - a;
+    }
+  }
+  cand[h] = tot;
+}
+
+// G2: one CTA per halo; members = candidates with periodic d^2 <= R^2, appended range by range (ahf_halos_sfc.c:327-356)
+__global__ void __launch_bounds__(HB) k_gather_fill(const float4 *__restrict__ pos4, const double *__restrict__ centre, const double *__restrict__ grad,
+                                                   const int64_t *__restrict__ rlo, const int64_t *__restrict__ rhi, const int64_t *__restrict__ candoff,
+                                                   double *__restrict__ r2buf, uint32_t *__restrict__ idxbuf, int64_t *__restrict__ ngather)
+{
+  __shared__ int sm[HB / 32];
+  const int64_t h = blockIdx.x;
+  const double  c[3] = { centre[3 * h], centre[3 * h + 1], centre[3 * h + 2] };
+  const double  R2 = grad[h] * grad[h];
+  int64_t out = candoff[h];
+  for (int q = 0; q < 27; q++) {
+    const int64_t a = rlo[h * 27 + q], b = rhi[h * 27 + q];
+    for (int64_t base = a; base < b; base += HB) {
+      int64_t o = base + threadIdx.x;
+      bool    in = false;
+      double  r2 = 0.0;
+      if (o < b) {
+        float4 p = pos4[o];
+        double dx = fabs((double)p.x - c[0]), dy = fabs((double)p.y - c[1]), dz = fabs((double)p.z - c[2]);
+        if (dx > 0.5) dx = 1.0 - dx; if (dy > 0.5) dy = 1.0 - dy; if (dz > 0.5) dz = 1.0 - dz;
+        in = (dx * dx + dy * dy + dz * dz) <= R2;
+        if (in) { double d[3]; sep3(p, c, d); r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2]; }   // sort key (ahf_halos.c:5844)
+      }
+      int tot, pos = block_excl_scan_i(in ? 1 : 0, sm, &tot);
+      if (in) { r2buf[out + pos] = r2; idxbuf[out + pos] = (uint32_t)o; }
+      out += tot;
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) ngather[h] = out - candoff[h];
+}
+
+// ------------------------------------------------------------------------------------------------
+// U1: radial sort = LSD radix sort by r^2 bits, then stable sort by halo -> (halo, r^2, gather order)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_sort_setup(const int64_t *__restrict__ candoff, const int64_t *__restrict__ ngather, const int64_t *__restrict__ eoff, int64_t nhalo,
+                             int min_part, const double *__restrict__ r2buf, uint64_t *__restrict__ key, uint32_t *__restrict__ val,
+                             uint32_t *__restrict__ hid)
+{
+  const int64_t h = blockIdx.x;
+  if (h >= nhalo) return;
+  const int64_t ng = ngather[h];
+  if (ng < min_part) return;                                 // ahf_halos.c:5795: too small, left unsorted
+  const int64_t src = candoff[h], dst = eoff[h];
+  for (int64_t i = threadIdx.x; i < ng; i += blockDim.x) {
+    key[dst + i] = (uint64_t)__double_as_longlong(r2buf[src + i]);     // r^2 >= 0: the bit pattern orders like the value
+    val[dst + i] = (uint32_t)(dst + i);
+    hid[dst + i] = (uint32_t)h;
+  }
+}
+__global__ void k_hid_keys(const uint32_t *__restrict__ val, const uint32_t *__restrict__ hid, uint64_t ne, uint64_t *__restrict__ key2, uint32_t *__restrict__ val2)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= ne) return;
+  key2[i] = hid[val[i]];
+  val2[i] = val[i];
+}
+// element e of the packed (>= min_part) layout lives at candoff[h] + (e - eoff[h]) of the candidate buffers
+__global__ void k_apply_perm(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ hid, const int64_t *__restrict__ candoff,
+                             const int64_t *__restrict__ eoff, uint64_t ne, const uint32_t *__restrict__ idxbuf, uint32_t *__restrict__ sorted_idx)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= ne) return;
+  uint32_t e = perm[i], h = hid[e];
+  sorted_idx[i] = idxbuf[candoff[h] + ((int64_t)e - eoff[h])];
+}
+__global__ void k_scatter_sorted(const int64_t *__restrict__ eoff, const int64_t *__restrict__ moff0, const uint32_t *__restrict__ sorted, uint32_t *__restrict__ out)
+{
+  const int64_t h = blockIdx.x, ne = eoff[h + 1] - eoff[h];
+  for (int64_t i = threadIdx.x; i < ne; i += blockDim.x) out[moff0[h] + i] = sorted[eoff[h] + i];
+}
+__global__ void k_copy_unsorted(const int64_t *__restrict__ candoff, const int64_t *__restrict__ ngather, const int64_t *__restrict__ eoff2,
+                                int min_part, const uint32_t *__restrict__ idxbuf, uint32_t *__restrict__ out)
+{
+  const int64_t h = blockIdx.x, ng = ngather[h];
+  if (ng >= min_part) return;
+  for (int64_t i = threadIdx.x; i < ng; i += blockDim.x) out[eoff2[h] + i] = idxbuf[candoff[h] + i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// U2: rem_outsideRvir (ahf_halos.c:3811-3869): first member whose mean enclosed overdensity drops below ovlim, inclusive
+// ------------------------------------------------------------------------------------------------
+struct RvirOut { long long np; double M, R, ovd; };
+
+__device__ RvirOut rvir_cut(const float4 *__restrict__ pos4, const uint32_t *__restrict__ ip, long long np, const double c[3], const HP &P,
+                            double *smd, long long *sml)
+{
+  __shared__ RvirOut res;
+  double carryM = 0.0;
+  if (threadIdx.x == 0) { res.np = np; res.M = 0; res.R = -1.0; res.ovd = 2 * P.ovlim; }
+  __syncthreads();
+  for (long long base = 0; base < np; base += HB) {
+    long long j = base + threadIdx.x;
+    double w = 0.0, r = 0.0;
+    if (j < np) { float4 p = pos4[ip[j]]; w = (double)p.w; r = dist3(p, c); }
+    double tot, M = carryM + block_incl_scan(w, smd, &tot);
+    double od = 0.0;
+    bool   cross = false;
+    if (j < np) {
+      double V = 4. * PI_ / 3. * (r * r * r);
+      od = M / V * P.rho_fac / P.rho_vir;
+      cross = !(od >= P.ovlim);
+    }
+    long long first = block_min_ll(cross ? j : (long long)0x7fffffffffffffffll, sml);
+    if (first != 0x7fffffffffffffffll) {
+      if (j == first) { res.np = j + 1; res.M = M; res.R = r; res.ovd = od; }
+      __syncthreads();
+      return res;
+    }
+    if (j == np - 1) { res.np = np; res.M = M; res.R = r; res.ovd = od; }
+    carryM += tot;
+    __syncthreads();
+  }
+  __syncthreads();
+  return res;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage kernel 1: virial cut, unbinding, virial cut.  One CTA per halo; the member list is compacted in place.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HB) k_halo_unbind(const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, int has_u,
+                                                    const double *__restrict__ centre, const int64_t *__restrict__ moff0, const int64_t *__restrict__ ngather,
+                                                    uint32_t *__restrict__ members, HP P, double *__restrict__ scal, int64_t *__restrict__ npart_out,
+                                                    int64_t *__restrict__ iter_work)
+{
+  __shared__ double    smd[HB / 32];
+  __shared__ long long sml[HB / 32];
+  __shared__ int       smi[HB / 32];
+  __shared__ double    s_seed[4];
+  __shared__ int       s_changed;
+  const int64_t h = blockIdx.x;
+  uint32_t     *ip = members + moff0[h];
+  long long     np = ngather[h];
+  double       *S = scal + h * AHFGPU_NSCAL;
+  const double  c[3] = { centre[3 * h], centre[3 * h + 1], centre[3 * h + 2] };
+  if (threadIdx.x == 0) { S[5] = (double)np; S[6] = S[7] = S[8] = S[9] = (double)np; }
+  double M_vir = 0, R_vir = 0, ovd = 0, Phi0 = 0;
+  long long work = 0;
+  if (np >= P.min_part) {
+    RvirOut r = rvir_cut(pos4, ip, np, c, P, smd, sml);
+    np = r.np; M_vir = r.M; R_vir = r.R; ovd = r.ovd; Phi0 = 0.0;
+  }
+  if (threadIdx.x == 0) S[6] = S[7] = S[8] = S[9] = (double)np;
+  // ---- rem_unbound (ahf_halos.c:3292-3607)
+  if (np >= P.min_part) {
+    const double v2_tune = P.vesc_tune * P.vesc_tune;
+    long long nremove = 4;
+    int niter = 0;
+    while (nremove > 3) {
+      niter++;
+      work += np;
+      // pass A: Phi0 = sum of trapezoids of M(<r)/r^2 + M_tot/r_last (:3359-3426)
+      double carryM = 0.0, carryPhi = 0.0, prev_r = 0.0, prev_I = 0.0, lastM = 0.0, lastR = 0.0;
+      for (long long base = 0; base < np; base += HB) {
+        long long j = base + threadIdx.x;
+        double w = 0.0, r = 0.0;
+        if (j < np) { float4 p = pos4[ip[j]]; w = (double)p.w; r = dist3(p, c); }
+        double totM, M = carryM + block_incl_scan(w, smd, &totM);
+        double I = (j < np && r > MACHINE_ZERO) ? M / (r * r) : 0.0;
+        // neighbour values (j-1): shuffle within the warp, shared memory across warps, carry across tiles
+        __shared__ double nb_r[HB], nb_I[HB];
+        nb_r[threadIdx.x] = r; nb_I[threadIdx.x] = I;
+        __syncthreads();
+        double rp = threadIdx.x ? nb_r[threadIdx.x - 1] : prev_r, Ip = threadIdx.x ? nb_I[threadIdx.x - 1] : prev_I;
+        double term = (j < np && r > MACHINE_ZERO) ? ((I + Ip) / 2.) * (r - rp) : 0.0;
+        double totP; block_incl_scan(term, smd, &totP);
+        carryPhi += totP; carryM += totM;
+        long long lastj = (base + HB < np ? base + HB : np) - 1;
+        prev_r = nb_r[lastj - base]; prev_I = nb_I[lastj - base];
+        if (lastj == np - 1) { lastR = prev_r; lastM = carryM; }
+        __syncthreads();
+      }
+      Phi0 = carryPhi + lastM / lastR;
+      // seed of the running bulk velocity (:3441-3470)
+      if (threadIdx.x == 0) {
+        long long seed = 0;
+        if (niter == 1) {
+          int nv = P.min_part / 2;
+          float m2[64]; int id[64];
+          if (nv > 64) nv = 64;
+          for (int q = 0; q < nv; q++) { float4 m = mom4[ip[q]]; m2[q] = m.x * m.x + m.y * m.y + m.z * m.z; id[q] = q; }
+          for (int a = 1; a < nv; a++) { int t = id[a]; float v = m2[t]; int b = a - 1; while (b >= 0 && m2[id[b]] > v) { id[b + 1] = id[b]; b--; } id[b + 1] = t; }
+          seed = id[nv / 2 - 1];                                  // NR indexx is 1-based: idx[n/2] = (n/2)-th smallest
+        }
+        float4 p = pos4[ip[seed]], m = mom4[ip[seed]];
+        double w = (double)p.w;
+        s_seed[0] = w; s_seed[1] = w * m.x; s_seed[2] = w * m.y; s_seed[3] = w * m.z;
+      }
+      __syncthreads();
+      double Mvel = s_seed[0], Vx = s_seed[1], Vy = s_seed[2], Vz = s_seed[3];
+      // pass B (:3478-3583)
+      carryM = 0.0; carryPhi = 0.0; prev_r = 0.0; prev_I = 0.0;
+      long long nb = 0;
+      double Mv_acc = 0.0, Rv_last = 0.0;
+      nremove = 0;
+      for (long long base = 0; base < np; base += HB) {
+        long long j = base + threadIdx.x;
+        const bool act = j < np;
+        double w = 0.0, r = 0.0, d[3] = { 0, 0, 0 }, mx = 0, my = 0, mz = 0, uu = -1.0;
+        uint32_t pid = 0;
+        if (act) {
+          pid = ip[j];
+          float4 p = pos4[pid], m = mom4[pid];
+          w = (double)p.w; sep3(p, c, d); r = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+          mx = (double)m.x; my = (double)m.y; mz = (double)m.z; uu = (double)m.w;
+        }
+        double totM, M = carryM + block_incl_scan(w, smd, &totM);
+        double I = (act && r > MACHINE_ZERO) ? M / (r * r) : 0.0;
+        __shared__ double nb_r[HB], nb_I[HB];
+        nb_r[threadIdx.x] = r; nb_I[threadIdx.x] = I;
+        __syncthreads();
+        double rp = threadIdx.x ? nb_r[threadIdx.x - 1] : prev_r, Ip = threadIdx.x ? nb_I[threadIdx.x - 1] : prev_I;
+        double term = (act && r > MACHINE_ZERO) ? ((I + Ip) / 2.) * (r - rp) : 0.0;
+        double totP, Phi = carryPhi + block_incl_scan(term, smd, &totP);
+        double v_esc2 = (act && r > MACHINE_ZERO) ? (2 * fabs(Phi - Phi0) * P.phi_fac) : 1e30;
+        // fixed point of the causal bound mask inside the tile
+        bool bound = act;
+        for (int it = 0; it < HB + 2; it++) {
+          double bw = bound ? w : 0.0;
+          double t0, t1, t2, t3;
+          double eM = Mvel + block_incl_scan(bw, smd, &t0) - bw;
+          double eX = Vx + block_incl_scan(bw * mx, smd, &t1) - bw * mx;
+          double eY = Vy + block_incl_scan(bw * my, smd, &t2) - bw * my;
+          double eZ = Vz + block_incl_scan(bw * mz, smd, &t3) - bw * mz;
+          bool nbnd = false;
+          if (act) {
+            double dvx = (mx - eX / eM) * P.v_fac + P.hubble * d[0] * P.r_fac;
+            double dvy = (my - eY / eM) * P.v_fac + P.hubble * d[1] * P.r_fac;
+            double dvz = (mz - eZ / eM) * P.v_fac + P.hubble * d[2] * P.r_fac;
+            double vel2 = dvx * dvx + dvy * dvy + dvz * dvz;
+            if (has_u) vel2 += (uu < 0.0 ? 0.0 : 2 * uu);
+            nbnd = !(vel2 > v2_tune * v_esc2);
+          }
+          if (threadIdx.x == 0) s_changed = 0;
+          __syncthreads();
+          if (nbnd != bound) s_changed = 1;
+          bound = nbnd;
+          __syncthreads();
+          int ch = s_changed;
+          __syncthreads();
+          if (!ch) { Mvel += t0; Vx += t1; Vy += t2; Vz += t3; break; }
+        }
+        // append bound members (in place: nb <= base)
+        int totb, posb = block_excl_scan_i(bound ? 1 : 0, smi, &totb);
+        __syncthreads();
+        if (bound) ip[nb + posb] = pid;
+        // last bound member of the tile defines R_vir so far
+        long long lastb = block_min_ll(bound ? -(long long)j : 1, sml);       // max j among bound = -min(-j)
+        if (lastb <= 0 && totb > 0) Rv_last = nb_r[(-lastb) - base];
+        Mv_acc += block_sum(bound ? w : 0.0, smd);
+        nb += totb;
+        long long tile_n = (base + HB < np ? base + HB : np) - base;
+        nremove += tile_n - totb;
+        carryM += totM; carryPhi += totP;
+        prev_r = nb_r[tile_n - 1]; prev_I = nb_I[tile_n - 1];
+        __syncthreads();
+      }
+      np = nb; M_vir = Mv_acc; R_vir = Rv_last;
+      if ((double)np < (double)P.min_part) break;
+    }
+  }
+  if (threadIdx.x == 0) S[7] = S[8] = S[9] = (double)np;
+  if (np >= P.min_part) {
+    RvirOut r = rvir_cut(pos4, ip, np, c, P, smd, sml);
+    np = r.np; M_vir = r.M; R_vir = r.R; ovd = r.ovd;
+  }
+  if (threadIdx.x == 0) {
+    S[0] = c[0]; S[1] = c[1]; S[2] = c[2];
+    S[8] = S[9] = (double)np;
+    S[10] = M_vir; S[11] = R_vir; S[12] = ovd; S[13] = Phi0;
+    int nbins = 0;
+    if (np >= P.min_part) { nbins = (int)(6.2 * (log10((double)np)) - 3.5); if (nbins < 2) nbins = 2; if (nbins > MAXBINS) nbins = MAXBINS; }
+    S[57] = (double)nbins;
+    npart_out[h] = np;
+    iter_work[h] = work;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// P1 helpers: 3x3 Jacobi (general.c:1163-1240), get_axes (specific.c:135-178), calc_cNFW / R1 (specific.c:1972-2072)
+// ------------------------------------------------------------------------------------------------
+__device__ void jacobi3(double a[3][3], double d[3], double v[3][3])
+{
+  double b[3], z[3];
+  for (int ip = 0; ip < 3; ip++) { for (int iq = 0; iq < 3; iq++) v[ip][iq] = 0.0; v[ip][ip] = 1.0; }
+  for (int ip = 0; ip < 3; ip++) { b[ip] = d[ip] = a[ip][ip]; z[ip] = 0.0; }
+  for (int i = 1; i <= 50; i++) {
+    double sm = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+    if (sm == 0.0) return;
+    double tresh = (i < 4) ? 0.2 * sm / 9 : 0.0;
+    for (int ip = 0; ip < 2; ip++) for (int iq = ip + 1; iq < 3; iq++) {
+      double g = 100.0 * fabs(a[ip][iq]);
+      if (i > 4 && (fabs(d[ip]) + g) == fabs(d[ip]) && (fabs(d[iq]) + g) == fabs(d[iq])) a[ip][iq] = 0.0;
+      else if (fabs(a[ip][iq]) > tresh) {
+        double hh = d[iq] - d[ip], t;
+        if ((fabs(hh) + g) == fabs(hh)) t = (a[ip][iq]) / hh;
+        else {
+          double theta = 0.5 * hh / (a[ip][iq]);
+          t = 1.0 / (fabs(theta) + sqrt(1.0 + theta * theta));
+          if (theta < 0.0) t = -t;
+        }
+        double cc = 1.0 / sqrt(1 + t * t), s = t * cc, tau = s / (1.0 + cc);
+        hh = t * a[ip][iq];
+        z[ip] -= hh; z[iq] += hh; d[ip] -= hh; d[iq] += hh; a[ip][iq] = 0.0;
+#define ROT(Mx, i1, j1, k1, l1) { double g1 = Mx[i1][j1], h1 = Mx[k1][l1]; Mx[i1][j1] = g1 - s * (h1 + g1 * tau); Mx[k1][l1] = h1 + s * (g1 - h1 * tau); }
+        for (int j = 0; j <= ip - 1; j++) ROT(a, j, ip, j, iq)
+        for (int j = ip + 1; j <= iq - 1; j++) ROT(a, ip, j, j, iq)
+        for (int j = iq + 1; j < 3; j++) ROT(a, ip, j, iq, j)
+        for (int j = 0; j < 3; j++) ROT(v, j, ip, j, iq)
+#undef ROT
+      }
+    }
+    for (int ip = 0; ip < 3; ip++) { b[ip] += z[ip]; d[ip] = b[ip]; z[ip] = 0.0; }
+  }
+}
+__device__ void get_axes(double it[3][3], double &ax1, double &ax2, double &ax3)
+{
+  double a[3][3], d[3], v[3][3];
+  int    idx[3] = { 0, 1, 2 };
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) a[i][j] = it[i][j];
+  jacobi3(a, d, v);
+  for (int j = 1; j < 3; j++) { int t = idx[j]; double av = d[t]; int i = j - 1; for (; i >= 0; i--) { if (d[idx[i]] <= av) break; idx[i + 1] = idx[i]; } idx[i + 1] = t; }
+  ax1 = d[idx[2]]; ax2 = d[idx[1]]; ax3 = d[idx[0]];
+  for (int i = 0; i < 3; i++) { it[i][0] = v[i][idx[2]]; it[i][1] = v[i][idx[1]]; it[i][2] = v[i][idx[0]]; }
+}
+__device__ double cnfw_root(double c, double r) { return 0.216 * c / (log(1 + c) - c / (1 + c)) - r; }
+__device__ double calc_cNFW(double V2_max, double V2_vir)
+{
+  double r = V2_max / V2_vir, a = 2.2, b = 100, c;
+  if (r <= 1 || r > 5.9) return -1;
+  while (b - a > 1e-3) { c = (a + b) / 2; if (cnfw_root(a, r) * cnfw_root(c, r) > 0) a = c; else b = c; }
+  return (a + b) / 2.0;
+}
+__device__ double cr1_root(double c, double R1) { return (c - 2.0 * log(1.0 + c) + c / (1.0 + c)) / (c * (log(1.0 + c) - c / (1.0 + c))) - R1; }
+
+// ------------------------------------------------------------------------------------------------
+// stage kernel 2: HaloProfiles (ahf_halos.c:3961-5018).  One CTA per halo.
+//   per member prefix quantities (M, P, Phi) are block scans with carries; everything that is only sampled at bin
+//   edges (CoM, inertia tensor, L, Ekin, Epot ...) is reduced per (tile, bin) in a fixed order and prefix-summed over bins.
+// ------------------------------------------------------------------------------------------------
+constexpr int NACC = 18;   // CoM3, a11 a22 a33 a12 a13 a23, L3, Ekin, Epot, Mhires, Mlores, M, npart
+
+__global__ void __launch_bounds__(HB) k_halo_profiles(const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, int has_w, int has_u,
+                                                      const double *__restrict__ centre, const int64_t *__restrict__ moff0,
+                                                      const uint32_t *__restrict__ members, const int64_t *__restrict__ npart_in, HP P,
+                                                      double *__restrict__ scal, const int64_t *__restrict__ poff, double *__restrict__ prof,
+                                                      const int64_t *__restrict__ soff, double *__restrict__ scratch)
+{
+  __shared__ double smd[HB / 32];
+  __shared__ double edge[MAXBINS];
+  __shared__ double acc[MAXBINS][NACC];
+  __shared__ double vesc_bin[MAXBINS], Vc_bin[MAXBINS][3];
+  __shared__ double nb_r[HB], nb_I[HB];
+  __shared__ double s_dmin, s_dmax;
+  __shared__ double s_emin[HB / 32]; __shared__ long long s_eidx[HB / 32];
+  const int64_t h = blockIdx.x;
+  const long long np = npart_in[h];
+  double *S = scal + h * AHFGPU_NSCAL;
+  if (np < P.min_part) return;
+  const uint32_t *ip = members + moff0[h];
+  const double    c[3] = { centre[3 * h], centre[3 * h + 1], centre[3 * h + 2] };
+  const int       nbins = (int)S[57];
+  const double    Phi0 = S[13], R_vir = S[11];
+  double *pr = prof + poff[h] * AHFGPU_NPROFCOL;
+  // per-member work arrays: r, y (value), t (smoothing ping-pong)
+  double *w_r = scratch + soff[h] * 3, *w_y = w_r + np, *w_t = w_y + np;
+  const double F43 = 4. * PI_ / 3.;
+  // binning_parameter (specific.c:259-322)
+  if (threadIdx.x == 0) {
+    long long k = (long long)floor(((double)P.min_part / 10.) + 0.5);
+    double dmin = -1.0;
+    while (k < np - 1 && dmin < MACHINE_ZERO) { dmin = dist3(pos4[ip[k]], c); k++; }
+    double dmax = dist3(pos4[ip[np - 1]], c);
+    if (dmin < MACHINE_ZERO) dmin = dmax / 2.;
+    s_dmin = dmin; s_dmax = dmax;
+    double ldmin = log10(dmin), ldmax = log10(dmax), ldr = (ldmax - ldmin) / (double)nbins;
+    for (int b = 0; b < nbins; b++) edge[b] = pow(10., ldmin + ((double)b + 1) * ldr);
+    edge[nbins - 1] = dmax + ZERO_F;                                       // :4226-4241
+  }
+  for (int i = threadIdx.x; i < MAXBINS * NACC; i += HB) (&acc[0][0])[i] = 0.0;
+  for (int i = threadIdx.x; i < MAXBINS; i += HB) { vesc_bin[i] = 0.0; Vc_bin[i][0] = Vc_bin[i][1] = Vc_bin[i][2] = 0.0; }
+  __syncthreads();
+  double carryM = 0.0, carryPhi = 0.0, cVx = 0.0, cVy = 0.0, cVz = 0.0, prev_r = 0.0, prev_I = 0.0, prev_rr = -1.0;
+  double best_e = 1e30; long long best_j = -1;
+  for (long long base = 0; base < np; base += HB) {
+    const long long j = base + threadIdx.x;
+    const bool act = j < np;
+    double w = 0.0, r = 0.0, d[3] = { 0, 0, 0 }, mx = 0, my = 0, mz = 0, uu = -1.0;
+    if (act) {
+      uint32_t pid = ip[j];
+      float4 p = pos4[pid], m = mom4[pid];
+      w = (double)p.w; sep3(p, c, d); r = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+      mx = (double)m.x; my = (double)m.y; mz = (double)m.z; uu = (double)m.w;
+    }
+    double tM, t1, t2, t3, tP;
+    double M  = carryM + block_incl_scan(w, smd, &tM);
+    double Px = cVx + block_incl_scan(w * mx, smd, &t1);
+    double Py = cVy + block_incl_scan(w * my, smd, &t2);
+    double Pz = cVz + block_incl_scan(w * mz, smd, &t3);
+    double I = (act && r > MACHINE_ZERO) ? M / (r * r) : 0.0;
+    nb_r[threadIdx.x] = r; nb_I[threadIdx.x] = I;
+    __syncthreads();
+    double rp = threadIdx.x ? nb_r[threadIdx.x - 1] : prev_r, Ip = threadIdx.x ? nb_I[threadIdx.x - 1] : prev_I;
+    double rprev_bin = threadIdx.x ? nb_r[threadIdx.x - 1] : prev_rr;       // r_{j-1} with r_{-1} = -1 for the bin test
+    double term = (act && r > MACHINE_ZERO) ? ((I + Ip) / 2.) * (r - rp) : 0.0;
+    double Phi = carryPhi + block_incl_scan(term, smd, &tP);
+    int bin = 0;
+    double v[NACC];
+#pragma unroll
+    for (int q = 0; q < NACC; q++) v[q] = 0.0;
+    double Epart = 1e30, vesc2 = 0.0;
+    if (act) {
+      while (bin < nbins - 1 && !(rprev_bin < edge[bin])) bin++;            // member j falls into the first bin whose edge exceeds r_{j-1}
+      double dvx = mx - Px / M, dvy = my - Py / M, dvz = mz - Pz / M;       // :4363-4370 running mean INCLUDING j
+      v[9]  = w * (d[1] * dvz - d[2] * dvy);
+      v[10] = w * (d[2] * dvx - d[0] * dvz);
+      v[11] = w * (d[0] * dvy - d[1] * dvx);
+      dvx += P.hubble * d[0] * P.r_fac / P.v_fac; dvy += P.hubble * d[1] * P.r_fac / P.v_fac; dvz += P.hubble * d[2] * P.r_fac / P.v_fac;
+      double Tpart = w * (dvx * dvx + dvy * dvy + dvz * dvz);
+      double Upart = (Phi - Phi0) * w;
+      vesc2 = 2 * fabs(Upart) / w;
+      if (has_u && uu >= 0.0) Tpart += w * (2 * uu / (P.v_fac * P.v_fac));
+      Epart = 0.5 * Tpart + Upart;
+      v[0] = w * (c[0] + d[0]); v[1] = w * (c[1] + d[1]); v[2] = w * (c[2] + d[2]);
+      v[3] = w * d[0] * d[0]; v[4] = w * d[1] * d[1]; v[5] = w * d[2] * d[2];
+      v[6] = w * d[0] * d[1]; v[7] = w * d[0] * d[2]; v[8] = w * d[1] * d[2];
+      v[12] = Tpart; v[13] = Upart;
+      if (has_w) { if (fabs(w - 1.0) < ZERO_F) v[14] = w; else if (w > 1.0) v[15] = w; } else v[14] = w;
+      v[16] = w; v[17] = 1.0;
+      // per-member arrays for Rmax / r2 (:4598-4616)
+      w_r[j] = r;
+      // last member of a bin defines the bin's v_esc2 and cumulative momentum: written below by the owner
+    }
+    // per (tile, bin) reductions in a fixed order
+    __shared__ int s_binlo, s_binhi;
+    if (threadIdx.x == 0) s_binlo = bin;
+    long long tile_n = (base + HB < np ? base + HB : np) - base;
+    if (threadIdx.x == tile_n - 1) s_binhi = bin;
+    __syncthreads();
+    const int blo = s_binlo, bhi = s_binhi;
+    for (int b = blo; b <= bhi; b++) {
+#pragma unroll
+      for (int q = 0; q < NACC; q++) {
+        double s = block_sum((act && bin == b) ? v[q] : 0.0, smd);
+        if (threadIdx.x == 0) acc[b][q] += s;
+      }
+    }
+    // last member of each bin inside this tile: it owns v_esc2 and P(<=j) of the bin
+    if (act) {
+      bool lastofbin = (j == np - 1);
+      if (!lastofbin) {
+        // next member's bin: computed from r_j
+        int nbn = bin; while (nbn < nbins - 1 && !(r < edge[nbn])) nbn++;
+        lastofbin = nbn != bin;
+      }
+      if (lastofbin) { vesc_bin[bin] = vesc2; Vc_bin[bin][0] = Px; Vc_bin[bin][1] = Py; Vc_bin[bin][2] = Pz; }
+    }
+    // most bound member: minimum of Epart, first index on ties (:4590-4596)
+    {
+      double e = Epart; long long jj = act ? j : 0x7fffffffffffffffll;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        double e2 = __shfl_xor_sync(0xffffffffu, e, o); long long j2 = __shfl_xor_sync(0xffffffffu, jj, o);
+        if (e2 < e || (e2 == e && j2 < jj)) { e = e2; jj = j2; }
+      }
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) { s_emin[threadIdx.x >> 5] = e; s_eidx[threadIdx.x >> 5] = jj; }
+      __syncthreads();
+      for (int q = 0; q < HB / 32; q++) if (s_emin[q] < best_e) { best_e = s_emin[q]; best_j = s_eidx[q]; }
+    }
+    carryM += tM; cVx += t1; cVy += t2; cVz += t3; carryPhi += tP;
+    prev_r = nb_r[tile_n - 1]; prev_I = nb_I[tile_n - 1]; prev_rr = prev_r;
+    __syncthreads();
+  }
+  __syncthreads();
+  // ---- per-bin cumulative values, Jacobi, profile columns
+  if (threadIdx.x == 0) {
+    double cum[NACC];
+    for (int q = 0; q < NACC; q++) cum[q] = 0.0;
+    double M_prev = 0.0, V_prev = 0.0, vesc_run = 0.0, Pl[3] = { 0, 0, 0 };
+    for (int b = 0; b < nbins; b++) {
+      for (int q = 0; q < NACC; q++) cum[q] += acc[b][q];
+      if (acc[b][17] > 0.0) { vesc_run = vesc_bin[b]; Pl[0] = Vc_bin[b][0]; Pl[1] = Vc_bin[b][1]; Pl[2] = Vc_bin[b][2]; }
+      const double cur_rad = edge[b], M = cum[16], Volume = F43 * (cur_rad * cur_rad * cur_rad), dM = M - M_prev, dV = Volume - V_prev;
+      double it[3][3], ax1, ax2, ax3;
+      if (cum[17] > (double)MINPART_SHELL) {
+        it[0][0] = cum[3]; it[1][1] = cum[4]; it[2][2] = cum[5]; it[0][1] = it[1][0] = cum[6]; it[0][2] = it[2][0] = cum[7]; it[1][2] = it[2][1] = cum[8];
+        get_axes(it, ax1, ax2, ax3);
+      } else { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) it[i][j] = 0.0; ax1 = 1; ax2 = 0; ax3 = 0; }
+#define PR(col, bb) pr[(col) * nbins + (bb)]
+      PR(0, b) = cum[17]; PR(1, b) = cur_rad; PR(2, b) = M; PR(3, b) = M / Volume; PR(4, b) = (dV > 0) ? dM / dV : 0.0;
+      PR(5, b) = M / cur_rad; PR(6, b) = vesc_run; PR(7, b) = sqrt(cum[12] / M); PR(8, b) = 0.5 * cum[12]; PR(9, b) = 0.5 * cum[13];
+      PR(10, b) = cum[9]; PR(11, b) = cum[10]; PR(12, b) = cum[11];
+      PR(13, b) = 1.0; PR(14, b) = it[0][0]; PR(15, b) = it[1][0]; PR(16, b) = it[2][0];
+      PR(17, b) = (ax1 > 0.) ? sqrt(ax2 / ax1) : 0.0; PR(18, b) = it[0][1]; PR(19, b) = it[1][1]; PR(20, b) = it[2][1];
+      PR(21, b) = (ax1 > 0.) ? sqrt(ax3 / ax1) : 0.0; PR(22, b) = it[0][2]; PR(23, b) = it[1][2]; PR(24, b) = it[2][2];
+      M_prev = M; V_prev = Volume;
+    }
+    const double M = cum[16];
+    const int    lb = nbins - 1;
+    double CoM[3];
+    for (int q = 0; q < 3; q++) CoM[q] = fmod(cum[q] / M + 1., 1.);
+    double absL = sqrt(PR(10, lb) * PR(10, lb) + PR(11, lb) * PR(11, lb) + PR(12, lb) * PR(12, lb));
+    S[10] = M; S[14] = Pl[0] / M; S[15] = Pl[1] / M; S[16] = Pl[2] / M;
+    S[17] = PR(7, lb); S[18] = PR(6, lb); S[24] = PR(8, lb); S[25] = PR(9, lb);
+    if (absL > 0) {
+      S[38] = PR(10, lb) / absL; S[39] = PR(11, lb) / absL; S[40] = PR(12, lb) / absL;
+      double lam = absL / M / sqrt(2. * M * R_vir);
+      lam *= P.v_fac * sqrt(P.r_fac / (GRAV_ * P.m_fac));
+      S[22] = lam;
+      double t1 = sqrt(P.m_fac * M); t1 = t1 * t1 * t1;
+      double t2 = S[24] * P.m_fac * (P.v_fac * P.v_fac), t3 = S[25] * P.m_fac * P.phi_fac;
+      t2 = sqrt(fabs(t2 + t3)); t1 = t2 / t1; t2 = P.m_fac * P.r_fac * P.v_fac * absL; t2 = t2 / (P.m_fac * M);
+      S[23] = t1 * t2 / GRAV_;
+    } else { S[38] = S[39] = S[40] = 0.0; S[22] = S[23] = 0.0; }
+    S[41] = PR(13, lb); S[42] = PR(17, lb); S[43] = PR(21, lb);
+    S[44] = PR(14, lb); S[45] = PR(15, lb); S[46] = PR(16, lb); S[47] = PR(18, lb); S[48] = PR(19, lb); S[49] = PR(20, lb);
+    S[50] = PR(22, lb); S[51] = PR(23, lb); S[52] = PR(24, lb);
+    {
+      double R1 = (PR(1, 0) / 2.0) * (PR(1, 0) / 2.0) * (PR(1, 0) / 2.0) * PR(4, 0) * PR(1, 0);
+      for (int b = 1; b < nbins; b++) { double rmid = (PR(1, b) + PR(1, b - 1)) / 2.0, dr = PR(1, b) - PR(1, b - 1); R1 += (rmid * rmid * rmid) * PR(4, b) * dr; }
+      R1 = 4 * PI_ * R1 / M / R_vir;
+      S[56] = R1;
+      if (R1 <= 0.19 || 0.585 <= R1) S[55] = -1.0;
+      else { double a = 1.0, b2 = 500.0, cc; while (b2 - a > 1e-3) { cc = (a + b2) / 2; if (cr1_root(a, R1) * cr1_root(cc, R1) > 0) a = cc; else b2 = cc; } S[55] = (a + b2) / 2.0; }
+    }
+    {
+      double Ts = 2.0 * (PR(8, lb) - PR(8, lb - 1)), fr = fabs(PR(1, lb - 1) / PR(1, lb));
+      S[26] = -0.125 * ((1. + fr) * (1. + fr) * (1. + fr)) / (1. - (fr * fr * fr)) * Ts;
+    }
+    S[53] = (cum[14] > 0) ? cum[14] / (cum[14] + cum[15]) : 0.0;
+    if (best_j >= 0) {
+      float4 p = pos4[ip[best_j]], m = mom4[ip[best_j]];
+      double dx = fabs((double)p.x - c[0]), dy = fabs((double)p.y - c[1]), dz = fabs((double)p.z - c[2]);
+      if (dx > 0.5) dx -= 1.0; if (dy > 0.5) dy -= 1.0; if (dz > 0.5) dz -= 1.0;
+      S[37] = sqrt(dx * dx + dy * dy + dz * dz);
+      S[31] = p.x; S[32] = p.y; S[33] = p.z; S[34] = m.x; S[35] = m.y; S[36] = m.z;
+    } else S[37] = -1.0;
+    {
+      double dx = fabs(CoM[0] - c[0]), dy = fabs(CoM[1] - c[1]), dz = fabs(CoM[2] - c[2]);
+      if (dx > 0.5) dx -= 1.0; if (dy > 0.5) dy -= 1.0; if (dz > 0.5) dz -= 1.0;
+      S[30] = sqrt(dx * dx + dy * dy + dz * dz);
+      S[27] = CoM[0]; S[28] = CoM[1]; S[29] = CoM[2];
+    }
+#undef PR
+  }
+  __syncthreads();
+  // ---- R_max / r2 from per-member arrays (find_max, general.c:608-650; smooth3 :548-573)
+  // M(<=j): equal masses -> j+1; general -> recomputed by a scan while filling y
+  const long long nn = np - NIGNORE;          // arrays are offset by NIGNORE
+  double x_r2 = 0.0, x_rmax = 0.0;
+  for (int which = 0; which < 2; which++) {   // 0: dens_r2 (3 smoothing passes), 1: Vcirc2 (1 pass)
+    double cM = 0.0;
+    for (long long base = 0; base < np; base += HB) {
+      long long j = base + threadIdx.x;
+      double w = 0.0;
+      if (j < np) w = (double)pos4[ip[j]].w;
+      double tM, M = cM + block_incl_scan(w, smd, &tM);
+      if (j < np) {
+        double r = w_r[j], rpv = j ? w_r[j - 1] : 0.0;
+        if (which == 0) { double dV = F43 * ((r * r * r) - (rpv * rpv * rpv)); w_y[j] = w / dV * (((r + rpv) / 2.) * ((r + rpv) / 2.)); }
+        else w_y[j] = M / r;
+      }
+      cM += tM;
+    }
+    __syncthreads();
+    double *ya = w_y + NIGNORE, *yb = w_t + NIGNORE;
+    const int ns = which == 0 ? 3 : 1;
+    if (nn >= 3)
+      for (int s = 0; s < ns; s++) {
+        for (long long i = threadIdx.x; i < nn; i += HB) {
+          double t;
+          if (i == 0) t = (ya[0] + ya[1]) / 2.;
+          else if (i == nn - 1) t = (ya[nn - 1] + ya[nn - 2]) / 2.;
+          else t = (ya[i - 1] + ya[i] + ya[i + 1]) / 3.;
+          yb[i] = t;
+        }
+        __syncthreads();
+        double *tp = ya; ya = yb; yb = tp;
+      }
+    // first index of the maximum over [0, nn-2] with y > -10 (the right-to-left pass of find_max can never improve on it)
+    double bv = -10.0; long long bi = nn - 1;
+    for (long long i = threadIdx.x; i < nn - 1; i += HB) { double y = ya[i]; if (y > bv) { bv = y; bi = i; } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double v2 = __shfl_xor_sync(0xffffffffu, bv, o); long long i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+      bool has2 = v2 > -10.0, has1 = bv > -10.0;
+      if ((has2 && !has1) || (has2 && has1 && (v2 > bv || (v2 == bv && i2 < bi)))) { bv = v2; bi = i2; }
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { s_emin[threadIdx.x >> 5] = bv; s_eidx[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    bv = -10.0; bi = nn - 1;
+    for (int q = 0; q < HB / 32; q++) {
+      double v2 = s_emin[q]; long long i2 = s_eidx[q];
+      if (v2 > -10.0 && (!(bv > -10.0) || v2 > bv || (v2 == bv && i2 < bi))) { bv = v2; bi = i2; }
+    }
+    double xm = w_r[NIGNORE + bi];
+    if (which == 0) x_r2 = xm; else x_rmax = xm;
+    __syncthreads();
+  }
+  // V_max from the first member with r >= R_max (:4892-4901); M(<=j) by one more scan
+  {
+    __shared__ long long sml[HB / 32];
+    __shared__ double s_Mmax;
+    double cM = 0.0;
+    bool done = false;
+    for (long long base = 0; base < np && !done; base += HB) {
+      long long j = base + threadIdx.x;
+      double w = 0.0;
+      if (j < np) w = (double)pos4[ip[j]].w;
+      double tM, M = cM + block_incl_scan(w, smd, &tM);
+      bool hit = (j < np) && (!(w_r[j] < x_rmax) || j == np - 1);
+      long long first = block_min_ll(hit ? j : 0x7fffffffffffffffll, sml);
+      if (first != 0x7fffffffffffffffll) {
+        if (j == first) { double r = w_r[j]; double od = M / (F43 * (r * r * r)); s_Mmax = od * F43 * (r * r * r); }
+        done = true;
+      }
+      cM += tM;
+      __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double V_max = s_Mmax / x_rmax;
+      S[19] = V_max; S[20] = x_rmax; S[21] = x_r2;
+      S[54] = calc_cNFW(V_max, S[10] / R_vir);
+    }
+  }
+}
+
+__global__ void k_members_out(const int64_t *__restrict__ moff0, const int64_t *__restrict__ npart, const int64_t *__restrict__ moff, const uint32_t *__restrict__ members,
+                              int64_t *__restrict__ out)
+{
+  const int64_t h = blockIdx.x, np = npart[h];
+  for (int64_t i = threadIdx.x; i < np; i += blockDim.x) out[moff[h] + i] = (int64_t)members[moff0[h] + i];
+}
+
+// exclusive scan of int64 on the host (nhalo-sized arrays; halos are few compared with particles)
+static std::vector<int64_t> host_excl(const std::vector<int64_t> &v, int64_t *total)
+{
+  std::vector<int64_t> o(v.size() + 1, 0);
+  for (size_t i = 0; i < v.size(); i++) o[i + 1] = o[i] + v[i];
+  *total = o.back();
+  return o;
+}
+
+template <typename T> static T *dalloc(size_t n)
+{
+  T *p = nullptr;
+  CUDA_CHECK(cudaMalloc(&p, (n ? n : 1) * sizeof(T)));
+  return p;
+}
+static inline unsigned nblk(uint64_t n, int b) { return (unsigned)((n + b - 1) / b); }
+
+void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const double *gather_rad, const int64_t *seed)
+{
+  c->free_halos();
+  c->nhalo = nhalo;
+  const ahfgpu_params &par = c->par;
+  HP P; P.r_fac = par.r_fac; P.x_fac = par.x_fac; P.v_fac = par.v_fac; P.m_fac = par.m_fac; P.rho_fac = par.rho_fac; P.phi_fac = par.phi_fac;
+  P.hubble = par.hubble; P.ovlim = par.ovlim; P.rho_vir = par.rho_vir; P.vesc_tune = par.vesc_tune; P.min_part = par.min_part;
+  if (P.min_part < 2) AHF_FAIL("min_part must be >= 2");
+  c->h_scal = dalloc<double>((size_t)nhalo * AHFGPU_NSCAL);
+  c->h_moff = dalloc<int64_t>(nhalo + 1); c->h_poff = dalloc<int64_t>(nhalo + 1);
+  CUDA_CHECK(cudaMemsetAsync(c->h_scal, 0, sizeof(double) * AHFGPU_NSCAL * (size_t)nhalo, c->stream));
+  if (nhalo == 0) {
+    CUDA_CHECK(cudaMemsetAsync(c->h_moff, 0, sizeof(int64_t), c->stream)); CUDA_CHECK(cudaMemsetAsync(c->h_poff, 0, sizeof(int64_t), c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return;
+  }
+  const int64_t n = (int64_t)c->n;
+  double  *d_ctr = dalloc<double>(3 * nhalo), *d_rad = dalloc<double>(nhalo);
+  int64_t *d_seed = seed ? dalloc<int64_t>(nhalo) : nullptr;
+  int64_t *d_rlo = dalloc<int64_t>(27 * nhalo), *d_rhi = dalloc<int64_t>(27 * nhalo), *d_cand = dalloc<int64_t>(nhalo), *d_candoff = dalloc<int64_t>(nhalo + 1);
+  int64_t *d_ng = dalloc<int64_t>(nhalo);
+  CUDA_CHECK(cudaMemcpyAsync(d_ctr, centre3, sizeof(double) * 3 * nhalo, cudaMemcpyHostToDevice, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(d_rad, gather_rad, sizeof(double) * nhalo, cudaMemcpyHostToDevice, c->stream));
+  if (seed) CUDA_CHECK(cudaMemcpyAsync(d_seed, seed, sizeof(int64_t) * nhalo, cudaMemcpyHostToDevice, c->stream));
+  std::vector<int64_t> h_cand(nhalo), h_ng(nhalo), h_np(nhalo);
+  int64_t tot_cand = 0;
+  std::vector<int64_t> candoff;
+  double *d_r2 = nullptr; uint32_t *d_idx = nullptr;
+  {
+    Stage st(c, "halo_gather", 0);
+    LAUNCH(c, k_gather_ranges, nblk(nhalo, 128), 128, 0, c->keys, n, d_ctr, d_rad, d_seed, nhalo, d_rlo, d_rhi, d_cand);
+    CUDA_CHECK(cudaMemcpyAsync(h_cand.data(), d_cand, sizeof(int64_t) * nhalo, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    candoff = host_excl(h_cand, &tot_cand);
+    CUDA_CHECK(cudaMemcpyAsync(d_candoff, candoff.data(), sizeof(int64_t) * (nhalo + 1), cudaMemcpyHostToDevice, c->stream));
+    d_r2 = dalloc<double>(tot_cand); d_idx = dalloc<uint32_t>(tot_cand);
+    LAUNCH(c, k_gather_fill, (unsigned)nhalo, HB, 0, c->pos4, d_ctr, d_rad, d_rlo, d_rhi, d_candoff, d_r2, d_idx, d_ng);
+    CUDA_CHECK(cudaMemcpyAsync(h_ng.data(), d_ng, sizeof(int64_t) * nhalo, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  }
+  // packed layout of all gathered members (moff0) and of the ones that get sorted (eoff)
+  int64_t tot_g = 0, tot_e = 0;
+  std::vector<int64_t> moff0 = host_excl(h_ng, &tot_g);
+  std::vector<int64_t> h_ne(nhalo);
+  for (int64_t h = 0; h < nhalo; h++) h_ne[h] = h_ng[h] >= P.min_part ? h_ng[h] : 0;
+  std::vector<int64_t> eoff = host_excl(h_ne, &tot_e);
+  if (tot_e >= (1ll << 32)) AHF_FAIL("more than 2^32 gathered members in one call: split the halo list");
+  c->stage_cnt["halo_gathered"] = tot_g;
+  int64_t *d_moff0 = dalloc<int64_t>(nhalo + 1), *d_eoff = dalloc<int64_t>(nhalo + 1);
+  CUDA_CHECK(cudaMemcpyAsync(d_moff0, moff0.data(), sizeof(int64_t) * (nhalo + 1), cudaMemcpyHostToDevice, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(d_eoff, eoff.data(), sizeof(int64_t) * (nhalo + 1), cudaMemcpyHostToDevice, c->stream));
+  uint32_t *d_members = dalloc<uint32_t>(tot_g);
+  {
+    Stage st(c, "halo_sort", tot_e);
+    if (tot_e > 0) {
+      uint64_t *k0 = dalloc<uint64_t>(tot_e), *k1 = dalloc<uint64_t>(tot_e);
+      uint32_t *v0 = dalloc<uint32_t>(tot_e), *v1 = dalloc<uint32_t>(tot_e), *hid = dalloc<uint32_t>(tot_e);
+      LAUNCH(c, k_sort_setup, (unsigned)nhalo, 256, 0, d_candoff, d_ng, d_eoff, nhalo, P.min_part, d_r2, k0, v0, hid);
+      uint64_t *ks; uint32_t *vs;
+      radix_sort_pairs(c, k0, v0, k1, v1, (uint64_t)tot_e, 64, &ks, &vs);
+      // second, stable pass by halo index
+      uint64_t *k2 = (ks == k0) ? k1 : k0; uint32_t *v2 = (vs == v0) ? v1 : v0;
+      int hb = 1; while ((1ll << hb) < nhalo) hb++;
+      // keys for pass 2 overwrite the other buffer; values need a third buffer because ks/vs are still read
+      uint32_t *v3 = dalloc<uint32_t>(tot_e);
+      LAUNCH(c, k_hid_keys, nblk(tot_e, 256), 256, 0, vs, hid, (uint64_t)tot_e, k2, v3);
+      uint64_t *ks2; uint32_t *vs2;
+      radix_sort_pairs(c, k2, v3, ks, v2, (uint64_t)tot_e, hb, &ks2, &vs2);
+      // sorted members go to the positions eoff-packed; map back to the moff0-packed layout per halo
+      uint32_t *sorted = dalloc<uint32_t>(tot_e);
+      LAUNCH(c, k_apply_perm, nblk(tot_e, 256), 256, 0, vs2, hid, d_candoff, d_eoff, (uint64_t)tot_e, d_idx, sorted);
+      // scatter halo segments: eoff-layout -> moff0-layout
+      LAUNCH(c, k_scatter_sorted, (unsigned)nhalo, 256, 0, d_eoff, d_moff0, sorted, d_members);
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(hid); cudaFree(v3); cudaFree(sorted);
+    }
+    LAUNCH(c, k_copy_unsorted, (unsigned)nhalo, 64, 0, d_candoff, d_ng, d_moff0, P.min_part, d_idx, d_members);
+  }
+  cudaFree(d_r2);
+  int64_t *d_np = dalloc<int64_t>(nhalo), *d_work = dalloc<int64_t>(nhalo);
+  {
+    Stage st(c, "halo_unbind", tot_g);
+    LAUNCH(c, k_halo_unbind, (unsigned)nhalo, HB, 0, c->pos4, c->mom4, c->has_u ? 1 : 0, d_ctr, d_moff0, d_ng, d_members, P, c->h_scal, d_np, d_work);
+    CUDA_CHECK(cudaMemcpyAsync(h_np.data(), d_np, sizeof(int64_t) * nhalo, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  }
+  {
+    std::vector<int64_t> h_work(nhalo);
+    CUDA_CHECK(cudaMemcpy(h_work.data(), d_work, sizeof(int64_t) * nhalo, cudaMemcpyDeviceToHost));
+    int64_t tw = 0; for (auto w : h_work) tw += w;
+    c->stage_cnt["halo_unbind_iter_members"] = tw;
+  }
+  // offsets of the final member lists, profile bins and scratch
+  std::vector<int64_t> h_nb(nhalo), h_sc(nhalo);
+  for (int64_t h = 0; h < nhalo; h++) {
+    int nb = 0;
+    if (h_np[h] >= P.min_part) { nb = (int)(6.2 * (log10((double)h_np[h])) - 3.5); if (nb < 2) nb = 2; if (nb > MAXBINS) nb = MAXBINS; }
+    h_nb[h] = nb; h_sc[h] = h_np[h] >= P.min_part ? h_np[h] : 0;
+  }
+  int64_t tot_m = 0, tot_b = 0, tot_s = 0;
+  std::vector<int64_t> moff = host_excl(h_np, &tot_m), poff = host_excl(h_nb, &tot_b), soff = host_excl(h_sc, &tot_s);
+  c->h_total_members = tot_m; c->h_total_bins = tot_b;
+  c->stage_cnt["halo_final_members"] = tot_s;
+  CUDA_CHECK(cudaMemcpyAsync(c->h_moff, moff.data(), sizeof(int64_t) * (nhalo + 1), cudaMemcpyHostToDevice, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(c->h_poff, poff.data(), sizeof(int64_t) * (nhalo + 1), cudaMemcpyHostToDevice, c->stream));
+  int64_t *d_soff = dalloc<int64_t>(nhalo + 1);
+  CUDA_CHECK(cudaMemcpyAsync(d_soff, soff.data(), sizeof(int64_t) * (nhalo + 1), cudaMemcpyHostToDevice, c->stream));
+  c->h_prof = dalloc<double>((size_t)tot_b * AHFGPU_NPROFCOL);
+  c->h_members = dalloc<int64_t>(tot_m);
+  double *d_scratch = dalloc<double>((size_t)tot_s * 3);
+  {
+    Stage st(c, "halo_profiles", tot_s);
+    LAUNCH(c, k_halo_profiles, (unsigned)nhalo, HB, 0, c->pos4, c->mom4, c->has_weight ? 1 : 0, c->has_u ? 1 : 0, d_ctr, d_moff0, d_members, d_np, P,
+           c->h_scal, c->h_poff, c->h_prof, d_soff, d_scratch);
+    LAUNCH(c, k_members_out, (unsigned)nhalo, 256, 0, d_moff0, d_np, c->h_moff, d_members, c->h_members);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  }
+  cudaFree(d_ctr); cudaFree(d_rad); cudaFree(d_seed); cudaFree(d_rlo); cudaFree(d_rhi); cudaFree(d_cand); cudaFree(d_candoff); cudaFree(d_ng);
+  cudaFree(d_idx); cudaFree(d_moff0); cudaFree(d_eoff); cudaFree(d_members); cudaFree(d_np); cudaFree(d_work); cudaFree(d_soff); cudaFree(d_scratch);
+}
+
+}  // namespace ahf

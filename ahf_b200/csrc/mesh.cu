@@ -1,0 +1,784 @@
+// mesh.cu -- D/F/R/L: TSC number-density deposit, refinement flags, next-level construction, relink, level loop.
+//
+// Replaces gen_domgrids / ll / zero_dens / assign_npart / refine_grid / relink / gen_AMRhierarchy of the reference
+// (src/libamr_serial/*.c, called from src/main.c:616-648).  A level is the (z,y,x)-sorted list of its cell keys plus
+// one bit per cell (`xbreak`: the reference's x-run ends after this cell, refine_grid.c:231-250), an open-addressing
+// hash for coordinate lookup and a per-cell table of the 27 neighbours the reference's search would see
+// (get_nnodes.c:459-862).  The domain level is a dense periodic L^3 block addressed arithmetically.
+// HBM-bound integer/float scatter work: no tensor cores.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace ahf {
+
+constexpr int    MIN_NNODES = 125;     // src/param.h:54
+constexpr double CRITMULTI  = 8.0;     // src/param.h:118
+constexpr int    FX_SHIFT   = 40;      // global accumulators: u64 fixed point, 2^-40 per unit weight
+constexpr double FX_SCALE   = 1099511627776.0;   // 2^40
+
+// ------------------------------------------------------------------------------------------------
+// device view of a level
+// ------------------------------------------------------------------------------------------------
+struct LV {
+  long long       L;
+  int             ncell, dense, logL;
+  const uint64_t *ckey;
+  const uint8_t  *xbreak;
+  const uint64_t *hkey;
+  const int32_t  *hval;
+  uint64_t        hmask;
+};
+
+static LV view(const Level &l)
+{
+  LV v; v.L = l.L; v.ncell = (int)l.ncell; v.dense = l.dense ? 1 : 0;
+  v.logL = 0; while ((1ll << v.logL) < l.L) v.logL++;
+  v.ckey = l.ckey; v.xbreak = l.xbreak; v.hkey = l.hkey; v.hval = l.hval; v.hmask = l.hmask;
+  return v;
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t k)
+{
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return k;
+}
+__device__ __forceinline__ void lv_coords(const LV &v, int c, int &x, int &y, int &z)
+{
+  uint64_t k = v.dense ? (uint64_t)c : v.ckey[c];
+  x = (int)(k & (uint64_t)(v.L - 1)); y = (int)((k >> v.logL) & (uint64_t)(v.L - 1)); z = (int)(k >> (2 * v.logL));
+}
+__device__ __forceinline__ uint64_t lv_key(const LV &v, int x, int y, int z)
+{
+  return (((uint64_t)z << v.logL) | (uint64_t)y) << v.logL | (uint64_t)x;
+}
+// geometric lookup without periodic wrap: -1 when (x,y,z) is not a cell of the level
+__device__ __forceinline__ int lv_lookup(const LV &v, int x, int y, int z)
+{
+  if ((unsigned)x >= (unsigned)v.L || (unsigned)y >= (unsigned)v.L || (unsigned)z >= (unsigned)v.L) return -1;
+  uint64_t k = lv_key(v, x, y, z);
+  if (v.dense) return (int)k;
+  uint64_t s = mix64(k) & v.hmask;
+  for (;;) {
+    uint64_t hk = v.hkey[s];
+    if (hk == k) return v.hval[s];
+    if (hk == ~0ull) return -1;
+    s = (s + 1) & v.hmask;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// D2: ll() -- domain cell of every particle (lltools.c:59-66)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_domain_cells(const float4 *__restrict__ pos4, uint64_t n, int L, int logL, int32_t *__restrict__ pcell)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = pos4[i];
+  // (unsigned long)((double)L * pos): L is a power of two, the product is exact in float as well
+  long long cx = (long long)((double)L * (double)p.x), cy = (long long)((double)L * (double)p.y), cz = (long long)((double)L * (double)p.z);
+  if (cx > L - 1 || cx < 0) cx = 0;
+  if (cy > L - 1 || cy < 0) cy = 0;
+  if (cz > L - 1 || cz < 0) cz = 0;
+  pcell[i] = (int32_t)((((cz << logL) | cy) << logL) | cx);
+}
+
+// ------------------------------------------------------------------------------------------------
+// D4 generic deposit: one thread per particle, 27 u64 fixed-point global reductions, warp-aggregated when
+// several lanes of a warp sit in the same cell (sorted particles => clump cores collapse to one leader)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tsc_weights(double s, double w[3])
+{
+  w[0] = 0.5 * (0.5 - s) * (0.5 - s);     // density.c:357-359
+  w[1] = 0.75 - s * s;
+  w[2] = 0.5 * (0.5 + s) * (0.5 + s);
+}
+
+__device__ __forceinline__ double sep_cell(float pos, int i, double L)
+{
+  double s = (double)pos * L - ((double)i + 0.5);
+  if (fabs(s) > 0.5 * L) s -= copysign(L, s);   // density.c:347-354 periodic image
+  return s;
+}
+
+__global__ void __launch_bounds__(256) k_deposit_generic(const float4 *__restrict__ pos4, const uint32_t *__restrict__ plist,
+                                                         const int32_t *__restrict__ pcell, uint64_t np, LV v,
+                                                         const int32_t *__restrict__ nbr, unsigned long long *__restrict__ acc,
+                                                         int32_t *__restrict__ count)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const bool valid = i < np;
+  const int  lane = threadIdx.x & 31;
+  int    c = -1;
+  double wx[3], wy[3], wz[3];
+  int    cx = 0, cy = 0, cz = 0;
+  if (valid) {
+    uint64_t p = plist ? plist[i] : i;
+    float4   q = pos4[p];
+    c = pcell[i];
+    lv_coords(v, c, cx, cy, cz);
+    const double L = (double)v.L;
+    tsc_weights(sep_cell(q.x, cx, L), wx);
+    tsc_weights(sep_cell(q.y, cy, L), wy);
+    tsc_weights(sep_cell(q.z, cz, L), wz);
+  }
+  // lanes sharing a cell elect a leader; REDUX over the peer set sums their 27 fixed-point terms (two 20-bit limbs)
+  unsigned peers  = __match_any_sync(0xffffffffu, c);
+  int      leader = __ffs(peers) - 1;
+  const bool any_agg = __any_sync(0xffffffffu, valid && (__popc(peers) > 1));
+  if (valid && lane == leader) atomicAdd(&count[c], __popc(peers));
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        unsigned long long t = valid ? (unsigned long long)(wz[k] * wy[j] * wx[a] * FX_SCALE + 0.5) : 0ull;
+        if (any_agg) {
+          unsigned lo = (unsigned)(t & 0xfffffull), hi = (unsigned)(t >> 20);
+          lo = __reduce_add_sync(peers, lo);
+          hi = __reduce_add_sync(peers, hi);
+          t  = ((unsigned long long)hi << 20) + lo;
+        }
+        if (valid && lane == leader) {
+          int tgt;
+          if (v.dense) {
+            int x = (cx + a - 1) & (int)(v.L - 1), y = (cy + j - 1) & (int)(v.L - 1), z = (cz + k - 1) & (int)(v.L - 1);
+            tgt = (int)lv_key(v, x, y, z);
+          } else tgt = nbr[(size_t)c * 27 + (k * 9 + j * 3 + a)];
+          if (tgt >= 0) atomicAdd(&acc[tgt], t);
+        }
+      }
+}
+
+__global__ void k_finish_dens(const unsigned long long *__restrict__ acc, float *__restrict__ dens, int ncell, double m2d)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  dens[c] = (float)(m2d * ((double)acc[c] * (1.0 / FX_SCALE)) - 1.0);      // zero_dens: -mean_dens, density.c:480
+}
+
+// ------------------------------------------------------------------------------------------------
+// F1: test_node (refine_grid.c:113-138)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_test_node(LV v, const float *__restrict__ dens, const uint8_t *__restrict__ interior,
+                            const int32_t *__restrict__ nbr, double thr, uint8_t *__restrict__ tn)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= v.ncell) return;
+  bool hit = false;
+  if (v.dense) {
+    int x, y, z; lv_coords(v, c, x, y, z);
+    const int M = (int)(v.L - 1);
+#pragma unroll
+    for (int k = -1; k <= 1; k++)
+#pragma unroll
+      for (int j = -1; j <= 1; j++)
+#pragma unroll
+        for (int a = 0; a <= 1; a++) {
+          int t = (int)lv_key(v, (x + a) & M, (y + j) & M, (z + k) & M);
+          hit |= ((double)dens[t] >= thr);
+        }
+  } else if (interior[c]) {
+    const int32_t *nb = nbr + (size_t)c * 27;
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int a = 1; a < 3; a++) hit |= ((double)dens[nb[k * 9 + j * 3 + a]] >= thr);
+  }
+  tn[c] = hit ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// F2: which cells spawn children (ref_pquad / ref_cquad / ref_nquad)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_mark_dense(LV v, const uint8_t *__restrict__ tn, uint8_t *__restrict__ mark)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= v.ncell) return;
+  int x = c & (int)(v.L - 1);
+  uint8_t m = 0;
+  if (tn[c]) m = 1;
+  else if (x != v.L - 1) {                         // the run's last node never gets a ghost pair
+    int prev = (x == 0) ? c + (int)(v.L - 1) : c - 1;
+    if (tn[prev]) m = 2;
+  }
+  mark[c] = m;
+}
+
+__device__ __forceinline__ bool tested_idx(long long t, int low, int up, long long len, bool case2)
+{
+  long long last = (len - 1) + up;
+  if (t >= low && t < last) return true;
+  long long e = last > low ? last : low;
+  return case2 && t == e;
+}
+__device__ __forceinline__ void run_offsets(bool wrapped, long long r0, long long r1, long long L, int &low, int &up)
+{
+  low = 1; up = -1;
+  if (wrapped) {
+    if (r0 == 0 && r1 == L) { low = 0; up = 0; }
+    else if (r0 == 0) { low = 0; up = -1; }
+    else if (r1 == L) { low = 1; up = 0; }
+  }
+}
+
+// one thread per plane: y-run (cquad) bounds of every row of the plane, as row indices [q0,q1)
+__global__ void k_row_runs(const uint64_t *__restrict__ rowkey, const int32_t *__restrict__ plane_r0, int nplane,
+                           int32_t *__restrict__ rq0, int32_t *__restrict__ rq1)
+{
+  int P = blockIdx.x * blockDim.x + threadIdx.x;
+  if (P >= nplane) return;
+  int r0 = plane_r0[P], r1 = plane_r0[P + 1], start = r0;
+  for (int r = r0; r < r1; r++) {
+    if (r > r0 && rowkey[r] != rowkey[r - 1] + 1) start = r;
+    rq0[r] = start;
+  }
+  int end = r1;
+  for (int r = r1 - 1; r >= r0; r--) {
+    if (r < r1 - 1 && rowkey[r + 1] != rowkey[r] + 1) end = r + 1;
+    rq1[r] = end;
+  }
+}
+
+// single thread: z-run (pquad) bounds of every plane as plane indices [p0,p1)
+__global__ void k_plane_runs(const uint64_t *__restrict__ rowkey, const int32_t *__restrict__ plane_r0, int nplane, int logL,
+                             int32_t *__restrict__ pp0, int32_t *__restrict__ pp1)
+{
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  int start = 0;
+  for (int P = 0; P < nplane; P++) {
+    if (P > 0 && (rowkey[plane_r0[P]] >> logL) != (rowkey[plane_r0[P - 1]] >> logL) + 1) start = P;
+    pp0[P] = start;
+  }
+  int end = nplane;
+  for (int P = nplane - 1; P >= 0; P--) {
+    if (P < nplane - 1 && (rowkey[plane_r0[P + 1]] >> logL) != (rowkey[plane_r0[P]] >> logL) + 1) end = P + 1;
+    pp1[P] = end;
+  }
+}
+
+__global__ void k_row_tested(const uint64_t *__restrict__ rowkey, const int32_t *__restrict__ plane_r0, const int32_t *__restrict__ rowplane,
+                             const int32_t *__restrict__ rq0, const int32_t *__restrict__ rq1, const int32_t *__restrict__ pp0,
+                             const int32_t *__restrict__ pp1, int nrow, int nplane, long long L, int logL, uint8_t *__restrict__ row_tested)
+{
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrow) return;
+  const uint64_t M = (uint64_t)(L - 1);
+  int P = rowplane[r];
+  // z direction (refine_grid.c:645-703, :818)
+  int  a = pp0[P], b = pp1[P];
+  long long z0 = (long long)(rowkey[plane_r0[a]] >> logL), z1 = (long long)(rowkey[plane_r0[b - 1]] >> logL) + 1;
+  bool zwrapped = ((rowkey[plane_r0[0]] >> logL) == 0) && ((long long)(rowkey[plane_r0[nplane - 1]] >> logL) == L - 1);
+  int  low, up;
+  run_offsets(zwrapped, z0, z1, L, low, up);
+  bool tz = tested_idx(P - a, low, up, b - a, (b == nplane) && (z1 == L));
+  // y direction (refine_grid.c:346-405, :496); the wrap test looks at the FIRST plane of the z-run (:350)
+  int  fr0 = plane_r0[a], fr1 = plane_r0[a + 1];
+  bool ywrapped = ((rowkey[fr0] & M) == 0) && ((long long)(rowkey[fr1 - 1] & M) == L - 1);
+  int  q0 = rq0[r], q1 = rq1[r];
+  long long y0 = (long long)(rowkey[q0] & M), y1 = (long long)(rowkey[q1 - 1] & M) + 1;
+  run_offsets(ywrapped, y0, y1, L, low, up);
+  bool ty = tested_idx(r - q0, low, up, q1 - q0, (q1 == plane_r0[P + 1]) && (y1 == L));
+  row_tested[r] = (tz && ty) ? 1 : 0;
+}
+
+__global__ void k_mark_sparse(LV v, const uint8_t *__restrict__ tn, const uint8_t *__restrict__ interior, const int32_t *__restrict__ crow,
+                              const int32_t *__restrict__ row_c0, const uint8_t *__restrict__ row_tested, uint8_t *__restrict__ mark)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= v.ncell) return;
+  int r = crow[c];
+  uint8_t m = 0;
+  if (row_tested[r]) {
+    const int      c0 = row_c0[r], c1 = row_c0[r + 1];
+    const uint64_t M = (uint64_t)(v.L - 1);
+    const uint64_t k = v.ckey[c];
+    const long long x = (long long)(k & M);
+    const bool rowwrap = ((long long)(v.ckey[c1 - 1] & M) == v.L - 1);
+    const bool first = (c == c0) || (v.ckey[c - 1] + 1 != k) || v.xbreak[c - 1];
+    const bool last  = (c == c1 - 1) || (v.ckey[c + 1] != k + 1) || v.xbreak[c];
+    const bool inloop = !last && (!first || (x == 0 && rowwrap));
+    const bool case2  = last && (x == v.L - 1);
+    if ((inloop || case2) && tn[c]) m = 1;
+    else if (inloop && !tn[c] && interior[c]) {
+      bool state;
+      if (first) state = (x == 0 && rowwrap && tn[c1 - 1]);
+      else {
+        // c-1 belongs to the same run; it was part of the loop unless it is the run's untested first node
+        const uint64_t kp = v.ckey[c - 1];
+        const bool pfirst = (c - 1 == c0) || (v.ckey[c - 2] + 1 != kp) || v.xbreak[c - 2];
+        const bool pin    = !pfirst || (((long long)(kp & M) == 0) && rowwrap);
+        state = pin && tn[c - 1];
+      }
+      if (state) m = 2;
+    }
+  }
+  mark[c] = m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// next level: 2x2x2 children of every marked cell, written directly in (z,y,x) order
+//   idx = 8*MB(P) + k*4*MP(P) + 4*MBR(r) + j*2*MR(r) + 2*RR(c) + i        
+// ------------------------------------------------------------------------------------------------
+__global__ void k_make_children(LV v, const uint8_t *__restrict__ mark, const int *__restrict__ S, int Mtot,
+                                const int32_t *__restrict__ crow, const int32_t *__restrict__ row_c0, const int32_t *__restrict__ rowplane,
+                                const int32_t *__restrict__ plane_r0, int nrow, uint64_t *__restrict__ fkey, uint8_t *__restrict__ fbreak,
+                                int flogL)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= v.ncell || !mark[c]) return;
+  int r, rc0, rc1, pc0, pc1;
+  if (v.dense) {
+    r = c >> v.logL; rc0 = r << v.logL; rc1 = rc0 + (int)v.L;
+    int P = r >> v.logL; pc0 = P << (2 * v.logL); pc1 = pc0 + (1 << (2 * v.logL));
+  } else {
+    r = crow[c]; rc0 = row_c0[r]; rc1 = row_c0[r + 1];
+    int P = rowplane[r]; pc0 = row_c0[plane_r0[P]]; pc1 = row_c0[plane_r0[P + 1]];
+  }
+  (void)nrow;
+  auto Sat = [&](int i) { return i >= v.ncell ? Mtot : S[i]; };
+  const int Sp0 = Sat(pc0), Sp1 = Sat(pc1), Sr0 = Sat(rc0), Sr1 = Sat(rc1);
+  const int MB = Sp0, MP = Sp1 - Sp0, MBR = Sr0 - Sp0, MR = Sr1 - Sr0, RR = S[c] - Sr0;
+  int x, y, z; lv_coords(v, c, x, y, z);
+  const bool ghost = (mark[c] == 2);
+#pragma unroll
+  for (int k = 0; k < 2; k++)
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        long long idx = 8ll * MB + (long long)k * 4 * MP + 4ll * MBR + (long long)j * 2 * MR + 2ll * RR + i;
+        fkey[idx]   = ((((uint64_t)(2 * z + k)) << flogL | (uint64_t)(2 * y + j)) << flogL) | (uint64_t)(2 * x + i);
+        fbreak[idx] = (ghost && i == 1) ? 1 : 0;                 // the reference's run ends after a ghost pair
+      }
+}
+
+__global__ void k_hash_clear(uint64_t *__restrict__ hkey, uint64_t cap)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < cap) hkey[i] = ~0ull;
+}
+__global__ void k_hash_insert(const uint64_t *__restrict__ ckey, int ncell, uint64_t *__restrict__ hkey, int32_t *__restrict__ hval, uint64_t hmask)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  uint64_t k = ckey[c], s = mix64(k) & hmask;
+  for (;;) {
+    unsigned long long old = atomicCAS((unsigned long long *)&hkey[s], ~0ull, (unsigned long long)k);
+    if (old == ~0ull || old == k) { hval[s] = c; return; }
+    s = (s + 1) & hmask;
+  }
+}
+
+// row heads / plane heads
+__global__ void k_row_heads(const uint64_t *__restrict__ ckey, int ncell, int logL, uint8_t *__restrict__ head)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  head[c] = (c == 0 || (ckey[c] >> logL) != (ckey[c - 1] >> logL)) ? 1 : 0;
+}
+__global__ void k_row_fill(const uint64_t *__restrict__ ckey, int ncell, int logL, const uint8_t *__restrict__ head, const int *__restrict__ hs,
+                           int32_t *__restrict__ crow, uint64_t *__restrict__ rowkey, int32_t *__restrict__ row_c0, int nrow)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  int r = hs[c] + head[c] - 1;
+  crow[c] = r;
+  if (head[c]) { rowkey[r] = ckey[c] >> logL; row_c0[r] = c; }
+  if (c == ncell - 1) row_c0[nrow] = ncell;
+}
+__global__ void k_plane_heads(const uint64_t *__restrict__ rowkey, int nrow, int logL, uint8_t *__restrict__ head)
+{
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrow) return;
+  head[r] = (r == 0 || (rowkey[r] >> logL) != (rowkey[r - 1] >> logL)) ? 1 : 0;
+}
+__global__ void k_plane_fill(int nrow, const uint8_t *__restrict__ head, const int *__restrict__ hs, int32_t *__restrict__ rowplane,
+                             int32_t *__restrict__ plane_r0, int nplane)
+{
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrow) return;
+  int P = hs[r] + head[r] - 1;
+  rowplane[r] = P;
+  if (head[r]) plane_r0[P] = r;
+  if (r == nrow - 1) plane_r0[nplane] = nrow;
+}
+
+// D5: the 27 neighbours the reference's search sees from each cell + test_tsc (get_nnodes.c:41-51, :459-862)
+__global__ void k_neighbours(LV v, int32_t *__restrict__ nbr, uint8_t *__restrict__ interior)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= v.ncell) return;
+  int x, y, z; lv_coords(v, c, x, y, z);
+  const int L = (int)v.L;
+  bool all = true;
+  for (int k = 0; k < 3; k++) {
+    int zz = z + k - 1; if (zz < 0) zz = L - 1; else if (zz >= L) zz = 0;
+    int pm = (k == 1) ? c : lv_lookup(v, x, y, zz);
+    for (int j = 0; j < 3; j++) {
+      int yy = y + j - 1; if (yy < 0) yy = L - 1; else if (yy >= L) yy = 0;
+      int32_t *o = nbr + (size_t)c * 27 + k * 9 + j * 3;
+      int rm = -1;
+      if (pm >= 0) rm = (j == 1) ? pm : lv_lookup(v, x, yy, zz);
+      if (rm < 0) { o[0] = o[1] = o[2] = -1; all = false; continue; }
+      o[1] = rm;
+      const uint64_t kk = v.ckey[rm];
+      // x-1: same run, else the periodic image when on the face (get_nnodes.c:490-508)
+      int xm = -1;
+      if (rm > 0 && v.ckey[rm - 1] + 1 == kk && x > 0 && !v.xbreak[rm - 1]) xm = rm - 1;
+      else if (x == 0) xm = lv_lookup(v, L - 1, yy, zz);
+      // x+1 (get_nnodes.c:465-485)
+      int xp = -1;
+      if (!v.xbreak[rm] && rm + 1 < v.ncell && v.ckey[rm + 1] == kk + 1 && x < L - 1) xp = rm + 1;
+      else if (x == L - 1) xp = lv_lookup(v, 0, yy, zz);
+      o[0] = xm; o[2] = xp;
+      if (xm < 0 || xp < 0) all = false;
+    }
+  }
+  interior[c] = all ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// R1: relink (relink.c:31-288) -- per particle: first (z,y,x)-ordered interior child that contains it
+// ------------------------------------------------------------------------------------------------
+__global__ void k_relink(const float4 *__restrict__ pos4, const uint32_t *__restrict__ plist, const int32_t *__restrict__ pcell, uint64_t np,
+                         LV coa, const uint8_t *__restrict__ cmark, LV fin, const uint8_t *__restrict__ finterior,
+                         int32_t *__restrict__ newcell, uint8_t *__restrict__ moved)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= np) return;
+  int c = pcell[i], res = -1;
+  if (cmark[c]) {
+    uint64_t p = plist ? plist[i] : i;
+    float4   q = pos4[p];
+    int cx, cy, cz; lv_coords(coa, c, cx, cy, cz);
+    const double Lf = (double)fin.L;
+    const double t[3] = { (double)q.x * Lf, (double)q.y * Lf, (double)q.z * Lf };
+    const int    b[3] = { 2 * cx, 2 * cy, 2 * cz };
+    // child b+e (e = 0,1) contains the particle iff b+e <= t <= b+e+1 (inclusive on both faces, relink.c:153)
+    bool ok[3][2];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      ok[d][0] = (t[d] >= (double)b[d]) && (t[d] <= (double)(b[d] + 1));
+      ok[d][1] = (t[d] >= (double)(b[d] + 1)) && (t[d] <= (double)(b[d] + 2));
+    }
+    for (int k = 0; k < 2 && res < 0; k++) {
+      if (!ok[2][k]) continue;
+      for (int j = 0; j < 2 && res < 0; j++) {
+        if (!ok[1][j]) continue;
+        for (int e = 0; e < 2 && res < 0; e++) {
+          if (!ok[0][e]) continue;
+          int f = lv_lookup(fin, b[0] + e, b[1] + j, b[2] + k);
+          if (f >= 0 && finterior[f]) res = f;
+        }
+      }
+    }
+  }
+  newcell[i] = res;
+  moved[i]   = res >= 0 ? 1 : 0;
+}
+
+__global__ void k_compact_moved(const uint32_t *__restrict__ plist, const int32_t *__restrict__ newcell, const uint8_t *__restrict__ moved,
+                                const int *__restrict__ S, uint64_t np, uint32_t *__restrict__ plist_out, int32_t *__restrict__ pcell_out,
+                                int8_t *__restrict__ owner, int8_t newlevel)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= np || !moved[i]) return;
+  uint32_t p = plist ? plist[i] : (uint32_t)i;
+  plist_out[S[i]] = p; pcell_out[S[i]] = newcell[i];
+  owner[p] = newlevel;
+}
+
+__global__ void k_count_owner(const int8_t *__restrict__ owner, uint64_t n, unsigned long long *__restrict__ cnt)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int l = owner[i];
+  unsigned peers = __match_any_sync(__activemask(), l);
+  if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&cnt[l], (unsigned long long)__popc(peers));
+}
+
+__global__ void k_nonzero(const uint8_t *in, int n, uint8_t *out)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side of the level loop
+// ------------------------------------------------------------------------------------------------
+template <typename T> static T *dalloc(size_t n)
+{
+  T *p = nullptr;
+  CUDA_CHECK(cudaMalloc(&p, (n ? n : 1) * sizeof(T)));
+  return p;
+}
+static inline unsigned nblk(uint64_t n, int b) { return (unsigned)((n + b - 1) / b); }
+
+static void build_rows_planes(ahfgpu_ctx *c, Level &lv)
+{
+  LV v = view(lv);
+  const int nc = (int)lv.ncell;
+  DevBuf<uint8_t> head; DevBuf<int> hs;
+  head.reserve(nc); hs.reserve(nc);
+  LAUNCH(c, k_row_heads, nblk(nc, 256), 256, 0, lv.ckey, nc, v.logL, head.p);
+  lv.nrow = exclusive_scan<uint8_t>(c, head.p, hs.p, nc);
+  lv.crow = dalloc<int32_t>(nc); lv.rowkey = dalloc<uint64_t>(lv.nrow); lv.row_c0 = dalloc<int32_t>(lv.nrow + 1);
+  LAUNCH(c, k_row_fill, nblk(nc, 256), 256, 0, lv.ckey, nc, v.logL, head.p, hs.p, lv.crow, lv.rowkey, lv.row_c0, (int)lv.nrow);
+  head.reserve(lv.nrow); hs.reserve(lv.nrow);
+  LAUNCH(c, k_plane_heads, nblk(lv.nrow, 256), 256, 0, lv.rowkey, (int)lv.nrow, v.logL, head.p);
+  lv.nplane = exclusive_scan<uint8_t>(c, head.p, hs.p, lv.nrow);
+  int32_t *rowplane = dalloc<int32_t>(lv.nrow);
+  lv.plane_r0 = dalloc<int32_t>(lv.nplane + 1);
+  LAUNCH(c, k_plane_fill, nblk(lv.nrow, 256), 256, 0, (int)lv.nrow, head.p, hs.p, rowplane, lv.plane_r0, (int)lv.nplane);
+  // run bounds + tested rows
+  int32_t *rq0 = dalloc<int32_t>(lv.nrow), *rq1 = dalloc<int32_t>(lv.nrow), *pp0 = dalloc<int32_t>(lv.nplane), *pp1 = dalloc<int32_t>(lv.nplane);
+  LAUNCH(c, k_row_runs, nblk(lv.nplane, 128), 128, 0, lv.rowkey, lv.plane_r0, (int)lv.nplane, rq0, rq1);
+  LAUNCH(c, k_plane_runs, 1, 32, 0, lv.rowkey, lv.plane_r0, (int)lv.nplane, v.logL, pp0, pp1);
+  lv.row_tested = dalloc<uint8_t>(lv.nrow);
+  LAUNCH(c, k_row_tested, nblk(lv.nrow, 256), 256, 0, lv.rowkey, lv.plane_r0, rowplane, rq0, rq1, pp0, pp1, (int)lv.nrow, (int)lv.nplane,
+         (long long)lv.L, v.logL, lv.row_tested);
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  cudaFree(rq0); cudaFree(rq1); cudaFree(pp0); cudaFree(pp1);
+  head.release(); hs.release();
+  lv.rowplane = rowplane;
+}
+
+static void deposit_level(ahfgpu_ctx *c, Level &lv)
+{
+  Stage st(c, "deposit", lv.npart_dep);
+  LV v = view(lv);
+  const int nc = (int)lv.ncell;
+  DevBuf<unsigned long long> acc;
+  acc.reserve(nc);
+  CUDA_CHECK(cudaMemsetAsync(acc.p, 0, sizeof(unsigned long long) * nc, c->stream));
+  CUDA_CHECK(cudaMemsetAsync(lv.count, 0, sizeof(int32_t) * nc, c->stream));
+  if (lv.npart_dep > 0)
+    LAUNCH(c, k_deposit_generic, nblk(lv.npart_dep, 256), 256, 0, c->pos4, lv.plist, lv.pcell, (uint64_t)lv.npart_dep, v, lv.nbr, acc.p, lv.count);
+  LAUNCH(c, k_finish_dens, nblk(nc, 256), 256, 0, acc.p, lv.dens, nc, lv.masstopartdens);
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  acc.release();
+}
+
+static void alloc_cell_arrays(Level &lv)
+{
+  const size_t nc = (size_t)lv.ncell;
+  lv.dens = dalloc<float>(nc); lv.tn = dalloc<uint8_t>(nc); lv.mark = dalloc<uint8_t>(nc); lv.count = dalloc<int32_t>(nc);
+  CUDA_CHECK(cudaMemset(lv.mark, 0, nc));
+}
+
+void amr_build(ahfgpu_ctx *c)
+{
+  c->free_levels();
+  const uint64_t n = c->n;
+  const ahfgpu_params &par = c->par;
+  long long lmax = par.lgrid_max;
+  if (lmax > (1 << 21) || lmax <= 0) lmax = (1 << 21);
+  if (par.lgrid_dom > 1024) AHF_FAIL("dense domain grids above 1024^3 need 64-bit cell indices (not in this round)");
+  c->owner_level = dalloc<int8_t>(n);
+  CUDA_CHECK(cudaMemsetAsync(c->owner_level, 0, n, c->stream));
+
+  // ---- domain level (gen_domgrids, generate_grids.c:24-116)
+  {
+    Level d;
+    d.L = par.lgrid_dom; d.ncell = d.L * d.L * d.L; d.dense = true;
+    d.masstopartdens = ((double)d.L * (double)d.L * (double)d.L) / (double)n;
+    d.critdens = par.nth_dom * d.masstopartdens;
+    alloc_cell_arrays(d);
+    d.npart_dep = (int64_t)n;
+    d.pcell = dalloc<int32_t>(n);
+    {
+      Stage st(c, "ll", (int64_t)n);
+      LV v = view(d);
+      if (n) LAUNCH(c, k_domain_cells, nblk(n, 256), 256, 0, c->pos4, n, (int)d.L, v.logL, d.pcell);
+    }
+    c->levels.push_back(d);
+  }
+  for (;;) {
+    Level &cur = c->levels.back();
+    const int lev = (int)c->levels.size() - 1;
+    deposit_level(c, cur);
+    if (cur.L == lmax) break;                                          // generate_grids.c:307-308
+    LV cv = view(cur);
+    const int nc = (int)cur.ncell;
+    int M = 0;
+    DevBuf<int> S;
+    {
+      Stage st(c, "flag", nc);
+      LAUNCH(c, k_test_node, nblk(nc, 256), 256, 0, cv, cur.dens, cur.interior, cur.nbr, cur.critdens - 1.0, cur.tn);
+      if (cur.dense) LAUNCH(c, k_mark_dense, nblk(nc, 256), 256, 0, cv, cur.tn, cur.mark);
+      else LAUNCH(c, k_mark_sparse, nblk(nc, 256), 256, 0, cv, cur.tn, cur.interior, cur.crow, cur.row_c0, cur.row_tested, cur.mark);
+    }
+    {
+      Stage st(c, "refine", nc);
+      DevBuf<uint8_t> flag;
+      flag.reserve(nc); S.reserve(nc);
+      LAUNCH(c, k_nonzero, nblk(nc, 256), 256, 0, cur.mark, nc, flag.p);
+      M = exclusive_scan<uint8_t>(c, flag.p, S.p, nc);
+      flag.release();
+      if (M == 0) { S.release(); break; }                             // refine_grid returned FALSE
+      if ((long long)M * 8 > 2000000000ll) AHF_FAIL("refinement level exceeds 2^31 cells");
+      Level f;
+      f.L = cur.L * 2; f.ncell = (int64_t)M * 8; f.dense = false;
+      f.masstopartdens = cur.masstopartdens * CRITMULTI;               // generate_grids.c:164-170
+      f.critdens = par.nth_ref * f.masstopartdens;
+      f.ckey = dalloc<uint64_t>(f.ncell); f.xbreak = dalloc<uint8_t>(f.ncell);
+      int flogL = cv.logL + 1;
+      LAUNCH(c, k_make_children, nblk(nc, 256), 256, 0, cv, cur.mark, S.p, M, cur.crow, cur.row_c0, cur.dense ? nullptr : cur.rowplane,
+             cur.plane_r0, (int)cur.nrow, f.ckey, f.xbreak, flogL);
+      S.release();
+      // hash
+      uint64_t cap = 16; while (cap < (uint64_t)f.ncell * 2 + 2) cap <<= 1;
+      f.hmask = cap - 1; f.hkey = dalloc<uint64_t>(cap); f.hval = dalloc<int32_t>(cap);
+      LAUNCH(c, k_hash_clear, nblk(cap, 256), 256, 0, f.hkey, cap);
+      LAUNCH(c, k_hash_insert, nblk(f.ncell, 256), 256, 0, f.ckey, (int)f.ncell, f.hkey, f.hval, f.hmask);
+      alloc_cell_arrays(f);
+      f.interior = dalloc<uint8_t>(f.ncell); f.nbr = dalloc<int32_t>((size_t)f.ncell * 27);
+      LV fv = view(f);
+      LAUNCH(c, k_neighbours, nblk(f.ncell, 128), 128, 0, fv, f.nbr, f.interior);
+      build_rows_planes(c, f);
+      c->levels.push_back(f);
+    }
+    // ---- relink
+    {
+      Level &coa = c->levels[lev];
+      Level &fin = c->levels[lev + 1];
+      Stage st(c, "relink", coa.npart_dep);
+      const uint64_t np = (uint64_t)coa.npart_dep;
+      DevBuf<int32_t> newcell; DevBuf<uint8_t> moved; DevBuf<int> MS;
+      newcell.reserve(np); moved.reserve(np); MS.reserve(np);
+      int nmoved = 0;
+      if (np) {
+        LAUNCH(c, k_relink, nblk(np, 256), 256, 0, c->pos4, coa.plist, coa.pcell, np, view(coa), coa.mark, view(fin), fin.interior, newcell.p, moved.p);
+        nmoved = exclusive_scan<uint8_t>(c, moved.p, MS.p, np);
+      }
+      if (fin.ncell < MIN_NNODES) {                                   // generate_grids.c:231 / density.c:420: level rejected
+        fin.free_all();
+        c->levels.pop_back();
+        newcell.release(); moved.release(); MS.release();
+        break;
+      }
+      fin.npart_dep = nmoved;
+      fin.plist = dalloc<uint32_t>(nmoved); fin.pcell = dalloc<int32_t>(nmoved);
+      if (np) LAUNCH(c, k_compact_moved, nblk(np, 256), 256, 0, coa.plist, newcell.p, moved.p, MS.p, np, fin.plist, fin.pcell, c->owner_level, (int8_t)(lev + 1));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      newcell.release(); moved.release(); MS.release();
+    }
+    if (c->levels.size() >= 60) break;
+  }
+  // final ownership counts
+  {
+    DevBuf<unsigned long long> cnt;
+    cnt.reserve(64);
+    CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, 64 * sizeof(unsigned long long), c->stream));
+    if (n) LAUNCH(c, k_count_owner, nblk(n, 256), 256, 0, c->owner_level, n, cnt.p);
+    unsigned long long h[64];
+    CUDA_CHECK(cudaMemcpyAsync(h, cnt.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    for (size_t l = 0; l < c->levels.size(); l++) c->levels[l].npart_final = (int64_t)h[l];
+    cnt.release();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// queries
+// ------------------------------------------------------------------------------------------------
+__global__ void k_level_export(LV v, const int32_t *__restrict__ crow, const int32_t *__restrict__ row_c0, const uint64_t *__restrict__ rowkey,
+                               const int32_t *__restrict__ rowplane, const int32_t *__restrict__ plane_r0, int nrow, int nplane,
+                               int32_t *__restrict__ x, int32_t *__restrict__ y, int32_t *__restrict__ z, uint8_t *__restrict__ rf)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= v.ncell) return;
+  int X, Y, Z; lv_coords(v, c, X, Y, Z);
+  x[c] = X; y[c] = Y; z[c] = Z;
+  uint8_t f = 0;
+  const int L = (int)v.L;
+  if (v.dense) {
+    if (X == 0) f |= 1; if (X == L - 1) f |= 2; if (Y == 0) f |= 4; if (Y == L - 1) f |= 8; if (Z == 0) f |= 16; if (Z == L - 1) f |= 32;
+  } else {
+    int r = crow[c], c0 = row_c0[r], c1 = row_c0[r + 1];
+    uint64_t k = v.ckey[c];
+    if ((c == c0) || (v.ckey[c - 1] + 1 != k) || v.xbreak[c - 1]) f |= 1;
+    if ((c == c1 - 1) || (v.ckey[c + 1] != k + 1) || v.xbreak[c]) f |= 2;
+    int P = rowplane[r], r0 = plane_r0[P], r1 = plane_r0[P + 1];
+    if (r == r0 || rowkey[r - 1] + 1 != rowkey[r]) f |= 4;
+    if (r == r1 - 1 || rowkey[r + 1] != rowkey[r] + 1) f |= 8;
+    uint64_t zp = rowkey[r0] >> v.logL;
+    if (P == 0 || (rowkey[plane_r0[P - 1]] >> v.logL) + 1 != zp) f |= 16;
+    if (P == nplane - 1 || (rowkey[plane_r0[P + 1]] >> v.logL) != zp + 1) f |= 32;
+  }
+  (void)nrow;
+  rf[c] = f;
+}
+
+__global__ void k_fill_i32(int32_t *a, uint64_t n, int32_t v)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+__global__ void k_scatter_cells(const uint32_t *__restrict__ plist, const int32_t *__restrict__ pcell, uint64_t np, int32_t *__restrict__ out)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= np) return;
+  out[plist ? plist[i] : i] = pcell[i];
+}
+
+}  // namespace ahf
+
+using namespace ahf;
+
+extern "C" int ahfgpu_amr_level_get(ahfgpu_ctx *c, int32_t lev, int32_t *x, int32_t *y, int32_t *z, float *dens, uint8_t *runflags,
+                                    uint8_t *interior, uint8_t *mark, int32_t *count)
+{
+  try {
+    if (!c || lev < 0 || lev >= (int)c->levels.size()) AHF_FAIL("bad level");
+    CUDA_CHECK(cudaSetDevice(c->dev));
+    Level &l = c->levels[lev];
+    const size_t nc = (size_t)l.ncell;
+    if (x || y || z || runflags) {
+      DevBuf<int32_t> dx, dy, dz; DevBuf<uint8_t> rf;
+      dx.reserve(nc); dy.reserve(nc); dz.reserve(nc); rf.reserve(nc);
+      LAUNCH(c, k_level_export, nblk(nc, 256), 256, 0, view(l), l.crow, l.row_c0, l.rowkey, l.dense ? nullptr : l.rowplane, l.plane_r0,
+             (int)l.nrow, (int)l.nplane, dx.p, dy.p, dz.p, rf.p);
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      if (x) CUDA_CHECK(cudaMemcpy(x, dx.p, nc * 4, cudaMemcpyDeviceToHost));
+      if (y) CUDA_CHECK(cudaMemcpy(y, dy.p, nc * 4, cudaMemcpyDeviceToHost));
+      if (z) CUDA_CHECK(cudaMemcpy(z, dz.p, nc * 4, cudaMemcpyDeviceToHost));
+      if (runflags) CUDA_CHECK(cudaMemcpy(runflags, rf.p, nc, cudaMemcpyDeviceToHost));
+      dx.release(); dy.release(); dz.release(); rf.release();
+    }
+    if (dens) CUDA_CHECK(cudaMemcpy(dens, l.dens, nc * 4, cudaMemcpyDeviceToHost));
+    if (interior) {
+      if (l.dense) memset(interior, 1, nc);
+      else CUDA_CHECK(cudaMemcpy(interior, l.interior, nc, cudaMemcpyDeviceToHost));
+    }
+    if (mark) CUDA_CHECK(cudaMemcpy(mark, l.mark, nc, cudaMemcpyDeviceToHost));
+    if (count) CUDA_CHECK(cudaMemcpy(count, l.count, nc * 4, cudaMemcpyDeviceToHost));
+    return 0;
+  } catch (const ahf::Error &e) { ahf::g_last_error = e.msg; return -1; }
+}
+
+extern "C" int ahfgpu_amr_particle_levels(ahfgpu_ctx *c, int8_t *owner_level, int32_t *cell_of, int32_t nlev_cap)
+{
+  try {
+    if (!c || !c->owner_level) AHF_FAIL("no hierarchy");
+    CUDA_CHECK(cudaSetDevice(c->dev));
+    const uint64_t n = c->n;
+    if (owner_level) CUDA_CHECK(cudaMemcpy(owner_level, c->owner_level, n, cudaMemcpyDeviceToHost));
+    if (cell_of) {
+      DevBuf<int32_t> tmp;
+      tmp.reserve(n);
+      for (int l = 0; l < (int)c->levels.size() && l < nlev_cap; l++) {
+        Level &lv = c->levels[l];
+        LAUNCH(c, k_fill_i32, nblk(n, 256), 256, 0, tmp.p, n, -1);
+        if (lv.npart_dep) LAUNCH(c, k_scatter_cells, nblk(lv.npart_dep, 256), 256, 0, lv.plist, lv.pcell, (uint64_t)lv.npart_dep, tmp.p);
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        CUDA_CHECK(cudaMemcpy(cell_of + (size_t)l * n, tmp.p, n * 4, cudaMemcpyDeviceToHost));
+      }
+      tmp.release();
+    }
+    return 0;
+  } catch (const ahf::Error &e) { ahf::g_last_error = e.msg; return -1; }
+}

@@ -1,0 +1,112 @@
+// scan.cuh -- device-wide exclusive prefix sum (int32 output) over uint8 / int32 flags or counts.
+// Three-phase reduce / scan-of-block-sums / downsweep; the block-sum array is scanned recursively.
+#pragma once
+#include "common.cuh"
+
+namespace ahf {
+
+constexpr int SC_THREADS = 512;
+constexpr int SC_ITEMS   = 8;
+constexpr int SC_TILE    = SC_THREADS * SC_ITEMS;
+
+template <typename T> __device__ __forceinline__ int sc_load(const T *a, uint64_t i) { return (int)a[i]; }
+
+__device__ __forceinline__ int block_exclusive_scan(int v)
+{
+  __shared__ int wsum[SC_THREADS / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+  __syncthreads();
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int x = (lane < SC_THREADS / 32) ? wsum[lane] : 0, y = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int q = __shfl_up_sync(0xffffffffu, y, o); if (lane >= o) y += q; }
+    if (lane < SC_THREADS / 32) wsum[lane] = y - x;
+  }
+  __syncthreads();
+  return wsum[w] + inc - v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SC_THREADS) k_sc_reduce(const T *__restrict__ in, uint64_t n, int *__restrict__ bsum)
+{
+  __shared__ int red[SC_THREADS / 32];
+  uint64_t base = (uint64_t)blockIdx.x * SC_TILE + (uint64_t)threadIdx.x * SC_ITEMS;
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < SC_ITEMS; i++) if (base + i < n) s += sc_load(in, base + i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int v = threadIdx.x < SC_THREADS / 32 ? red[threadIdx.x] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = v;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SC_THREADS) k_sc_down(const T *__restrict__ in, uint64_t n, const int *__restrict__ boff,
+                                                        int *__restrict__ out)
+{
+  uint64_t base = (uint64_t)blockIdx.x * SC_TILE + (uint64_t)threadIdx.x * SC_ITEMS;
+  int v[SC_ITEMS], s = 0;
+#pragma unroll
+  for (int i = 0; i < SC_ITEMS; i++) { v[i] = (base + i < n) ? sc_load(in, base + i) : 0; s += v[i]; }
+  int ex = block_exclusive_scan(s) + boff[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SC_ITEMS; i++) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
+}
+
+// single CTA exclusive scan of a short int array in place; writes the total to *total
+static __global__ void __launch_bounds__(1024) k_sc_small(int *__restrict__ a, uint64_t m, int *__restrict__ total)
+{
+  __shared__ int wsum[32];
+  const int      t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const uint64_t per = (m + 1023) / 1024;
+  uint64_t       b = (uint64_t)t * per, e = b + per;
+  if (b > m) b = m;
+  if (e > m) e = m;
+  int s = 0;
+  for (uint64_t i = b; i < e; i++) s += a[i];
+  int v = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int x = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += x; }
+  if (lane == 31) wsum[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    int x = wsum[lane], y = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int q = __shfl_up_sync(0xffffffffu, y, o); if (lane >= o) y += q; }
+    wsum[lane] = y - x;
+    if (lane == 31 && total) *total = y;
+  }
+  __syncthreads();
+  int run = wsum[w] + (v - s);
+  for (uint64_t i = b; i < e; i++) { int x = a[i]; a[i] = run; run += x; }
+}
+
+// out[i] = sum_{j<i} in[j]; returns the total (synchronises the stream)
+template <typename T> int exclusive_scan(ahfgpu_ctx *c, const T *in, int *out, uint64_t n)
+{
+  if (n == 0) return 0;
+  const unsigned nblk = (unsigned)((n + SC_TILE - 1) / SC_TILE);
+  DevBuf<int> bs, tot;
+  bs.reserve(nblk); tot.reserve(1);
+  LAUNCH(c, (k_sc_reduce<T>), nblk, SC_THREADS, 0, in, n, bs.p);
+  LAUNCH(c, k_sc_small, 1, 1024, 0, bs.p, (uint64_t)nblk, tot.p);
+  LAUNCH(c, (k_sc_down<T>), nblk, SC_THREADS, 0, in, n, bs.p, out);
+  int h = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&h, tot.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  bs.release(); tot.release();
+  return h;
+}
+
+}  // namespace ahf

@@ -1,0 +1,313 @@
+// sfc.cu -- K1 Hilbert keys + K2 LSD radix sort + payload gather (sm_100a).
+//
+// Replaces the serial key loop and libc qsort of the reference (src/main.c:343-356): keys are the 63-bit
+// Hilbert index of (trunc(x*2^21), trunc(y*2^21), trunc(z*2^21)) (src/libsfc/hilbert_util.c:69-92,
+// hilbert.c:197-243).  HBM-bound integer work: no tensor cores.
+#include "common.cuh"
+#include "hilbert.cuh"
+
+namespace ahf {
+
+// ------------------------------------------------------------------------------------------------
+// K1
+// ------------------------------------------------------------------------------------------------
+__global__ void k_keys_soa(const float *__restrict__ pos3, uint64_t n, uint32_t bits, uint64_t *__restrict__ keys,
+                           uint32_t *__restrict__ idx)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float x = pos3[3 * i], y = pos3[3 * i + 1], z = pos3[3 * i + 2];
+  keys[i] = hilbert_key_pos(x, y, z, bits);
+  if (idx) idx[i] = (uint32_t)i;
+}
+
+// reference AoS record: positions at byte offset off_pos of a record of `stride` bytes
+__global__ void k_keys_aos(const unsigned char *__restrict__ rec, uint64_t n, uint32_t stride, int off_pos,
+                           uint64_t *__restrict__ keys, uint32_t *__restrict__ idx)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float *p = reinterpret_cast<const float *>(rec + i * stride + off_pos);
+  keys[i] = hilbert_key_pos(p[0], p[1], p[2], 21);
+  idx[i]  = (uint32_t)i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: LSD radix sort, 8-bit digits, (u64 key, u32 value) pairs, stable
+//   per pass: block histograms -> exclusive scan over [digit][block] -> ranked scatter
+// ------------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS   = 16;
+constexpr int RS_TILE    = RS_THREADS * RS_ITEMS;   // 4096 pairs per CTA
+constexpr int RS_WARPS   = RS_THREADS / 32;
+constexpr int RS_WCHUNK  = RS_TILE / RS_WARPS;      // 512 consecutive pairs per warp
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t *__restrict__ keys, uint64_t n, int shift,
+                                                        uint32_t *__restrict__ bhist, uint32_t nblk)
+{
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < RS_TILE; i += RS_THREADS) {
+    uint64_t j = base + i;
+    if (j < n) atomicAdd(&h[(uint32_t)(keys[j] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  bhist[(uint64_t)threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
+}
+
+// exclusive scan of m uint32 values in place, one CTA of 1024 threads
+__global__ void __launch_bounds__(1024) k_scan_u32(uint32_t *__restrict__ a, uint64_t m)
+{
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t carry_s;
+  const int      t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const uint64_t per = (m + 1023) / 1024;
+  uint64_t       b = (uint64_t)t * per, e = b + per;
+  if (b > m) b = m;
+  if (e > m) e = m;
+  uint32_t s = 0;
+  for (uint64_t i = b; i < e; i++) s += a[i];
+  uint32_t v = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t x = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += x; }
+  if (lane == 31) wsum[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t x = wsum[lane], y = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t q = __shfl_up_sync(0xffffffffu, y, o); if (lane >= o) y += q; }
+    wsum[lane] = y - x;
+  }
+  __syncthreads();
+  uint32_t run = wsum[w] + (v - s);
+  (void)carry_s;
+  for (uint64_t i = b; i < e; i++) { uint32_t x = a[i]; a[i] = run; run += x; }
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
+                                                           uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, uint64_t n,
+                                                           int shift, const uint32_t *__restrict__ bscan, uint32_t nblk)
+{
+  __shared__ uint32_t whist[RS_WARPS][256];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&whist[0][0])[i] = 0;
+  __syncthreads();
+  const uint64_t base = (uint64_t)blockIdx.x * RS_TILE + (uint64_t)w * RS_WCHUNK;
+  uint64_t k[RS_ITEMS];
+  uint32_t v[RS_ITEMS];
+  uint32_t rank[RS_ITEMS];
+#pragma unroll
+  for (int s = 0; s < RS_ITEMS; s++) {
+    uint64_t j = base + (uint64_t)s * 32 + lane;
+    bool     valid = j < n;
+    k[s] = valid ? kin[j] : ~0ull;
+    v[s] = valid ? vin[j] : 0u;
+  }
+#pragma unroll
+  for (int s = 0; s < RS_ITEMS; s++) {
+    uint64_t j = base + (uint64_t)s * 32 + lane;
+    bool     valid = j < n;
+    uint32_t d  = (uint32_t)(k[s] >> shift) & 255u;
+    uint32_t dd = valid ? d : (256u + lane);
+    uint32_t peers  = __match_any_sync(0xffffffffu, dd);
+    int      leader = __ffs(peers) - 1;
+    uint32_t r = __popc(peers & ((1u << lane) - 1u));
+    uint32_t bc = 0;
+    if (lane == leader && valid) { bc = whist[w][d]; whist[w][d] = bc + __popc(peers); }
+    bc = __shfl_sync(0xffffffffu, bc, leader);
+    rank[s] = bc + r;
+    __syncwarp();
+  }
+  __syncthreads();
+  {
+    const int t   = threadIdx.x;   // digit
+    uint32_t  run = bscan[(uint64_t)t * nblk + blockIdx.x];
+#pragma unroll
+    for (int q = 0; q < RS_WARPS; q++) { uint32_t c = whist[q][t]; whist[q][t] = run; run += c; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < RS_ITEMS; s++) {
+    uint64_t j = base + (uint64_t)s * 32 + lane;
+    if (j < n) {
+      uint32_t d = (uint32_t)(k[s] >> shift) & 255u;
+      uint32_t p = whist[w][d] + rank[s];
+      kout[p] = k[s];
+      vout[p] = v[s];
+    }
+  }
+}
+
+void radix_sort_pairs(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, uint64_t n,
+                      int key_bits, uint64_t **keys_sorted, uint32_t **vals_sorted)
+{
+  *keys_sorted = keys; *vals_sorted = vals;
+  if (n == 0) return;
+  const uint32_t nblk = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
+  DevBuf<uint32_t> bh;
+  bh.reserve((size_t)256 * nblk);
+  uint64_t *ki = keys, *ko = keys_tmp;
+  uint32_t *vi = vals, *vo = vals_tmp;
+  for (int shift = 0; shift < key_bits; shift += 8) {
+    LAUNCH(c, k_rs_hist, nblk, RS_THREADS, 0, ki, n, shift, bh.p, nblk);
+    LAUNCH(c, k_scan_u32, 1, 1024, 0, bh.p, (uint64_t)256 * nblk);
+    LAUNCH(c, k_rs_scatter, nblk, RS_THREADS, 0, ki, vi, ko, vo, n, shift, bh.p, nblk);
+    uint64_t *tk = ki; ki = ko; ko = tk;
+    uint32_t *tv = vi; vi = vo; vo = tv;
+  }
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  bh.release();
+  *keys_sorted = ki; *vals_sorted = vi;
+}
+
+// ------------------------------------------------------------------------------------------------
+// payload gather
+// ------------------------------------------------------------------------------------------------
+__global__ void k_gather_soa(const float *__restrict__ pos3, const float *__restrict__ mom3, const float *__restrict__ w,
+                             const float *__restrict__ u, const uint32_t *__restrict__ order, uint64_t n,
+                             float4 *__restrict__ pos4, float4 *__restrict__ mom4)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t o = order[i];
+  pos4[i] = make_float4(pos3[3 * o], pos3[3 * o + 1], pos3[3 * o + 2], w ? w[o] : 1.0f);
+  mom4[i] = make_float4(mom3[3 * o], mom3[3 * o + 1], mom3[3 * o + 2], u ? u[o] : -1.0f);
+}
+
+// sorted AoS: copy whole records in 8-byte words, then patch sfckey and clear the leading `ll` pointer
+__global__ void k_gather_aos(const unsigned char *__restrict__ in, unsigned char *__restrict__ out,
+                             const uint32_t *__restrict__ order, const uint64_t *__restrict__ keys, uint64_t n, uint32_t stride,
+                             int off_pos, int off_mom, int off_key, int off_w, int off_u, float4 *__restrict__ pos4,
+                             float4 *__restrict__ mom4)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t *src = reinterpret_cast<const uint64_t *>(in + (uint64_t)order[i] * stride);
+  uint64_t       *dst = reinterpret_cast<uint64_t *>(out + i * stride);
+  const int       nw  = stride / 8;
+  for (int q = 0; q < nw; q++) dst[q] = src[q];
+  dst[0] = 0;                                                      // part.ll: first member (tdef.h:38-42)
+  *reinterpret_cast<uint64_t *>(out + i * stride + off_key) = keys[i];
+  const float *p = reinterpret_cast<const float *>(out + i * stride + off_pos);
+  const float *m = reinterpret_cast<const float *>(out + i * stride + off_mom);
+  float ww = off_w >= 0 ? *reinterpret_cast<const float *>(out + i * stride + off_w) : 1.0f;
+  float uu = off_u >= 0 ? *reinterpret_cast<const float *>(out + i * stride + off_u) : -1.0f;
+  pos4[i] = make_float4(p[0], p[1], p[2], ww);
+  mom4[i] = make_float4(m[0], m[1], m[2], uu);
+}
+
+static void alloc_particles(ahfgpu_ctx *c, uint64_t n)
+{
+  c->free_particles();
+  c->free_levels();
+  c->free_halos();
+  c->n = n;
+  CUDA_CHECK(cudaMalloc(&c->pos4, (n ? n : 1) * sizeof(float4)));
+  CUDA_CHECK(cudaMalloc(&c->mom4, (n ? n : 1) * sizeof(float4)));
+}
+
+void sfc_keys_only(ahfgpu_ctx *c, const float *pos3, uint64_t n, uint32_t bits, uint64_t *keys_out)
+{
+  DevBuf<float>    dpos;
+  DevBuf<uint64_t> dk;
+  dpos.reserve(3 * n); dk.reserve(n);
+  CUDA_CHECK(cudaMemcpyAsync(dpos.p, pos3, 3 * n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  if (n) LAUNCH(c, k_keys_soa, (unsigned)((n + 255) / 256), 256, 0, dpos.p, n, bits, dk.p, (uint32_t *)nullptr);
+  CUDA_CHECK(cudaMemcpyAsync(keys_out, dk.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  dpos.release(); dk.release();
+}
+
+void sfc_sort_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, const float *w, const float *u, uint64_t n,
+                  uint64_t *keys_out, uint32_t *order_out)
+{
+  if (n >= (1ull << 32)) AHF_FAIL("more than 2^32-1 particles per device are not supported");
+  alloc_particles(c, n);
+  c->has_weight = (w != nullptr); c->has_u = (u != nullptr);
+  DevBuf<float>    dpos, dmom, dw, du;
+  DevBuf<uint64_t> k0, k1;
+  DevBuf<uint32_t> v0, v1;
+  dpos.reserve(3 * n); dmom.reserve(3 * n); k0.reserve(n); k1.reserve(n); v0.reserve(n); v1.reserve(n);
+  if (w) dw.reserve(n);
+  if (u) du.reserve(n);
+  {
+    Stage st(c, "h2d", (int64_t)(24 * n + (w ? 4 * n : 0) + (u ? 4 * n : 0)));
+    CUDA_CHECK(cudaMemcpyAsync(dpos.p, pos3, 3 * n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(dmom.p, mom3, 3 * n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (w) CUDA_CHECK(cudaMemcpyAsync(dw.p, w, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (u) CUDA_CHECK(cudaMemcpyAsync(du.p, u, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  }
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  {
+    Stage st(c, "keys", (int64_t)n);
+    if (n) LAUNCH(c, k_keys_soa, nb, 256, 0, dpos.p, n, 21u, k0.p, v0.p);
+  }
+  uint64_t *ks; uint32_t *vs;
+  {
+    Stage st(c, "sort", (int64_t)n);
+    radix_sort_pairs(c, k0.p, v0.p, k1.p, v1.p, n, 63, &ks, &vs);
+  }
+  {
+    Stage st(c, "gather", (int64_t)n);
+    if (n) LAUNCH(c, k_gather_soa, nb, 256, 0, dpos.p, dmom.p, w ? dw.p : nullptr, u ? du.p : nullptr, vs, n, c->pos4, c->mom4);
+  }
+  // keep sorted keys / order resident
+  CUDA_CHECK(cudaMalloc(&c->keys, (n ? n : 1) * sizeof(uint64_t)));
+  CUDA_CHECK(cudaMalloc(&c->order, (n ? n : 1) * sizeof(uint32_t)));
+  CUDA_CHECK(cudaMemcpyAsync(c->keys, ks, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(c->order, vs, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+  {
+    Stage st(c, "d2h", (int64_t)((keys_out ? 8 * n : 0) + (order_out ? 4 * n : 0)));
+    if (keys_out) CUDA_CHECK(cudaMemcpyAsync(keys_out, c->keys, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    if (order_out) CUDA_CHECK(cudaMemcpyAsync(order_out, c->order, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  dpos.release(); dmom.release(); dw.release(); du.release(); k0.release(); k1.release(); v0.release(); v1.release();
+}
+
+void sfc_sort_aos(ahfgpu_ctx *c, void *part, uint64_t n, uint32_t stride, int off_pos, int off_mom, int off_key, int off_id,
+                  int off_w, int off_u)
+{
+  (void)off_id;
+  if (n >= (1ull << 32)) AHF_FAIL("more than 2^32-1 particles per device are not supported");
+  if (stride % 8 != 0) AHF_FAIL("particle record stride must be a multiple of 8 bytes");
+  alloc_particles(c, n);
+  c->has_weight = off_w >= 0; c->has_u = off_u >= 0;
+  DevBuf<unsigned char> in, out;
+  DevBuf<uint64_t>      k0, k1;
+  DevBuf<uint32_t>      v0, v1;
+  in.reserve(n * stride); out.reserve(n * stride); k0.reserve(n); k1.reserve(n); v0.reserve(n); v1.reserve(n);
+  {
+    Stage st(c, "h2d", (int64_t)(n * stride));
+    CUDA_CHECK(cudaMemcpyAsync(in.p, part, n * stride, cudaMemcpyHostToDevice, c->stream));
+  }
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  {
+    Stage st(c, "keys", (int64_t)n);
+    if (n) LAUNCH(c, k_keys_aos, nb, 256, 0, in.p, n, stride, off_pos, k0.p, v0.p);
+  }
+  uint64_t *ks; uint32_t *vs;
+  {
+    Stage st(c, "sort", (int64_t)n);
+    radix_sort_pairs(c, k0.p, v0.p, k1.p, v1.p, n, 63, &ks, &vs);
+  }
+  {
+    Stage st(c, "gather", (int64_t)n);
+    if (n) LAUNCH(c, k_gather_aos, nb, 256, 0, in.p, out.p, vs, ks, n, stride, off_pos, off_mom, off_key, off_w, off_u, c->pos4, c->mom4);
+  }
+  CUDA_CHECK(cudaMalloc(&c->keys, (n ? n : 1) * sizeof(uint64_t)));
+  CUDA_CHECK(cudaMalloc(&c->order, (n ? n : 1) * sizeof(uint32_t)));
+  CUDA_CHECK(cudaMemcpyAsync(c->keys, ks, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(c->order, vs, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+  {
+    Stage st(c, "d2h", (int64_t)(n * stride));
+    CUDA_CHECK(cudaMemcpyAsync(part, out.p, n * stride, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  in.release(); out.release(); k0.release(); k1.release(); v0.release(); v1.release();
+}
+
+}  // namespace ahf

@@ -1,0 +1,125 @@
+/*
+ * ahfgpu.h -- C-ABI of libahfgpu.so: the B200 (sm_100a) implementation of AHF's particle hot path.
+ *
+ * Plain C, plain pointers and sizes, int status returns (0 = ok, <0 = error, text via ahfgpu_last_error()).
+ * The reference (NegriAndrea/AHF, C99) has no plugin/FFI layer; these entry points replace ordinary C calls
+ * inside its own translation units (INTEGRATION.md shows the call-site patch).  Each entry point names the
+ * reference interface it replaces (file:line relative to the reference tree).
+ *
+ * Ownership: every pointer passed in is HOST memory owned by the caller; outputs are written into caller
+ * buffers (query sizes first) -- nothing returned here has to be freed by the caller, and nothing the
+ * reference later free()s is allocated here.  All calls are made from one host thread (the reference's main
+ * thread); the library uses its own CUDA streams internally.
+ * Units: the reference's internal units (positions in box units [0,1), momenta a^2 dx/dt / (box/t_unit),
+ * masses in units of simu.pmass).
+ */
+#ifndef AHFGPU_H
+#define AHFGPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AHFGPU_NSCAL    64   /* scalar slots per halo, layout below */
+#define AHFGPU_NPROFCOL 25   /* profile columns per radial bin     */
+
+typedef struct ahfgpu_ctx ahfgpu_ctx;
+
+/* POD copy of the run parameters the path needs: simu.* (src/tdef.h:315-411, filled at src/startrun.c:465-713)
+ * and the unit factors / cosmology scalars of src/libahf/ahf_halos.c:199-221. */
+typedef struct {
+  int32_t device;          /* CUDA device ordinal                                                        */
+  int32_t lgrid_dom;       /* simu.NGRID_DOM  (AHF.input LgridDomain, power of two <= 2^21)               */
+  int32_t lgrid_max;       /* simu.NGRID_MAX  (AHF.input LgridMax; clipped to 2^21)                       */
+  int32_t min_part;        /* simu.AHF_MINPART (NminPerHalo)                                              */
+  double  nth_dom;         /* simu.Nth_dom    (NperDomCell)                                               */
+  double  nth_ref;         /* simu.Nth_ref    (NperRefCell)                                               */
+  double  vesc_tune;       /* simu.AHF_VTUNE  (VescTune)                                                  */
+  double  r_fac, x_fac, v_fac, m_fac, rho_fac, phi_fac;   /* ahf_halos.c:199-205                           */
+  double  hubble;          /* calc_Hubble(a)  ahf_halos.c:213                                             */
+  double  ovlim;           /* global.ovlim    ahf_halos.c:212,219                                         */
+  double  rho_vir;         /* global.rho_vir  ahf_halos.c:216,221                                         */
+} ahfgpu_params;
+
+const char *ahfgpu_last_error(void);
+int  ahfgpu_device_count(void);
+
+/* after startrun() (src/main.c:128) / before the final frees (src/main.c:671-707) */
+int  ahfgpu_init(ahfgpu_ctx **ctx, const ahfgpu_params *par);
+int  ahfgpu_set_params(ahfgpu_ctx *ctx, const ahfgpu_params *par);
+int  ahfgpu_finalize(ahfgpu_ctx *ctx);
+
+/* ---- K1 + K2 ----------------------------------------------------------------------------------------------
+ * Replaces the key loop + qsort of src/main.c:343-356 (sfc_curve_calcKey, src/libsfc/sfc_curve.c:87;
+ * cmp_sfckey_part, src/libutility/specific.c:1116).
+ *
+ * ahfgpu_sfc_sort_particles works on the reference's own AoS: `part` is `n` records of `stride` bytes
+ * (sizeof(struct particle), src/tdef.h:36-77; a multiple of 8); off_* are byte offsets of pos[3] (float),
+ * mom[3] (float), sfckey (uint64), id (uint64) and -- or -1 when the build has no such field -- weight
+ * (float) and u (float).  On return the HOST array is sorted ascending by key with sfckey filled (the first
+ * member `ll` is zeroed), exactly what ahf_halos.c:3361 / ahf_io.c:1136 index later, and the sorted particles
+ * stay resident on the device for the calls below.  Tie order between equal keys is by input position.
+ *
+ * ahfgpu_sfc_sort_soa is the same for separate arrays; keys_out (n) / order_out (n, input position of the
+ * particle now at sorted offset i) may be NULL.                                                            */
+int  ahfgpu_sfc_sort_particles(ahfgpu_ctx *ctx, void *part, uint64_t n, uint32_t stride, int32_t off_pos,
+                               int32_t off_mom, int32_t off_key, int32_t off_id, int32_t off_weight, int32_t off_u);
+int  ahfgpu_sfc_sort_soa(ahfgpu_ctx *ctx, const float *pos3, const float *mom3, const float *weight, const float *u,
+                         uint64_t n, uint64_t *keys_out, uint32_t *order_out);
+/* keys only (no sort, nothing stays resident): sfc_curve_calcKey(SFC_CURVE_HILBERT, x, y, z, bits) per particle */
+int  ahfgpu_hilbert_keys(ahfgpu_ctx *ctx, const float *pos3, uint64_t n, uint32_t bits, uint64_t *keys_out);
+
+/* ---- D / F / R / L ------------------------------------------------------------------------------------------
+ * Replaces gen_domgrids + ll + zero_dens + assign_npart + gen_AMRhierarchy (src/main.c:616-648;
+ * src/libamr_serial/generate_grids.c:24-432, lltools.c:32, density.c:238-492, refine_grid.c:903, relink.c:31)
+ * on the resident sorted particles.  The hierarchy stays on the device; the query calls copy it out.        */
+int  ahfgpu_build_amr(ahfgpu_ctx *ctx);
+int  ahfgpu_amr_nlevels(ahfgpu_ctx *ctx);
+/* iout[0]=l1dim [1]=ncell [2]=particles deposited on the level [3]=particles finally owned by it;
+ * dout[0]=critdens [1]=masstopartdens  (gridls fields, src/tdef.h:189-235) */
+int  ahfgpu_amr_level_header(ahfgpu_ctx *ctx, int32_t lev, int64_t *iout, double *dout);
+/* Cells in the reference's traversal order (z, y, x ascending).  Any pointer may be NULL.
+ *   dens     node.dens (float, number density contrast, src/libamr_serial/density.c:398,480)
+ *   runflags bit0/1 first/last node of its nquad, bit2/3 first/last row of its cquad, bit4/5 first/last plane
+ *            of its pquad -- enough to rebuild the pquad/cquad/nquad runs of src/tdef.h:143-183
+ *   interior test_tsc() of src/libamr_serial/get_nnodes.c:41-51
+ *   mark     0 untouched / 1 refined / 2 ghost pair (src/libamr_serial/refine_grid.c:231-250)
+ *   count    particles linked to the node when the level was deposited                                      */
+int  ahfgpu_amr_level_get(ahfgpu_ctx *ctx, int32_t lev, int32_t *x, int32_t *y, int32_t *z, float *dens,
+                          uint8_t *runflags, uint8_t *interior, uint8_t *mark, int32_t *count);
+/* per particle (sorted offset): deepest level that owns it (node.ll membership after all relinks) and its cell
+ * index on every level it reached: cell_of[lev*n + i] = index into the level's cell list or -1 */
+int  ahfgpu_amr_particle_levels(ahfgpu_ctx *ctx, int8_t *owner_level, int32_t *cell_of, int32_t nlev_cap);
+
+/* ---- G / U / P ----------------------------------------------------------------------------------------------
+ * Replaces the OpenMP loop over ahf_halos_sfc_constructHalo (src/libahf/ahf_halos.c:504-510;
+ * ahf_halos_sfc.c:118-169): gather, radial sort, virial cut, unbinding, virial cut, profiles.
+ * In: per halo centre[3] (HALO.pos), gather_rad (HALO.gatherRad), seed_npart (HALO.npart; 0 = skip,
+ * ahf_halos_sfc.c:122).  Results stay on the device until fetched:
+ *   scal     nhalo x AHFGPU_NSCAL doubles:
+ *              5 n_gathered, 6 n after 1st virial cut, 7 n after unbinding, 8 n after 2nd virial cut, 9 npart,
+ *              10 M_vir, 11 R_vir, 12 ovdens, 13 Phi0, 14-16 vel, 17 sigV, 18 v_esc2, 19 V2_max, 20 R_max, 21 r2,
+ *              22 lambda, 23 lambdaE, 24 Ekin, 25 Epot, 26 SurfP, 27-29 pos_com, 30 com_offset, 31-33 pos_mbp,
+ *              34-36 vel_mbp, 37 mbp_offset, 38-40 AngMom, 41-43 axis, 44-52 E1,E2,E3, 53 fMhires, 54 cNFW,
+ *              55 cR1, 56 R1, 57 nbins            (HALO fields, src/tdef.h:692-789)
+ *   members  radius-sorted offsets into the sorted particle array (HALO.ipart), CSR via member_offset
+ *   prof     per halo nbins x AHFGPU_NPROFCOL (column-major, col*nbins+bin): npart, r, nvpart, ovdens, dens,
+ *            v2_circ, v_esc2, sig_v, Ekin, Epot, Lx, Ly, Lz, axis1, E1x, E1y, E1z, axis2, E2x, E2y, E2z, axis3,
+ *            E3x, E3y, E3z   (HALOPROFILE, src/tdef.h:591-688), CSR via prof_offset (in bins)                 */
+int  ahfgpu_construct_halos(ahfgpu_ctx *ctx, int64_t nhalo, const double *centre3, const double *gather_rad,
+                            const int64_t *seed_npart);
+int  ahfgpu_halo_sizes(ahfgpu_ctx *ctx, int64_t *total_members, int64_t *total_bins);
+int  ahfgpu_halo_fetch(ahfgpu_ctx *ctx, double *scal, int64_t *member_offset, int64_t *members,
+                       int64_t *prof_offset, double *prof);
+
+/* ---- measurement hooks (bench.py): milliseconds of the last call, by stage, measured with CUDA events on
+ * the library's stream.  names: "h2d","keys","sort","gather","d2h","deposit","flag","refine","relink",
+ * "halo_gather","halo_sort","halo_unbind","halo_profiles", ... ; returns <0 for an unknown name.             */
+double  ahfgpu_stage_ms(ahfgpu_ctx *ctx, const char *name);
+int64_t ahfgpu_stage_count(ahfgpu_ctx *ctx, const char *name);   /* launches / items attributed to the stage */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

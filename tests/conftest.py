@@ -1,0 +1,60 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+GOLDEN_CASES = ["frag16", "edge32", "plain32"]
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+class Golden:
+    """One fixture written by tests/golden/make_golden.py from the unmodified reference."""
+
+    def __init__(self, name):
+        self.name = name
+        self.d = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        self.n1d = int(self.d["n1d"]); self.nlev = int(self.d["nlev"])
+        self.nper_dom = float(self.d["nper_dom"]); self.nper_ref = float(self.d["nper_ref"])
+        self.keys = self.d["keys"]; self.pos = self.d["pos"]; self.mom = self.d["mom"]; self.ids = self.d["ids"]
+        self.glob = self.d["halo_glob"]; self.hs = self.d["halo_s"]
+
+    def input_order(self):
+        """positions / momenta in snapshot-file order (ids are 0..N-1 in file order)"""
+        n = self.pos.shape[0]
+        pos = np.empty_like(self.pos); mom = np.empty_like(self.mom)
+        pos[self.ids] = self.pos; mom[self.ids] = self.mom
+        assert len(np.unique(self.ids)) == n
+        return pos, mom
+
+    def level(self, l):
+        p = "L%d_" % l
+        return {k: self.d[p + k] for k in ("l1dim", "critdens", "masstopartdens", "x", "y", "z", "dens", "runflags", "cnt",
+                                           "plist", "cnt_final", "plist_final")}
+
+    def members(self, i):
+        return self.d["halo_members"][self.d["halo_moff"][i]:self.d["halo_moff"][i + 1]].astype(np.int64)
+
+    def prof(self, i):
+        a, b = int(self.d["halo_poff"][i]), int(self.d["halo_poff"][i + 1])
+        if b == a:
+            return None
+        return self.d["halo_prof"][a * 25:b * 25].reshape(25, b - a)
+
+
+@pytest.fixture(scope="session", params=GOLDEN_CASES)
+def golden(request):
+    return Golden(request.param)
+
+
+def lin(x, y, z, L):
+    L = np.int64(L)
+    return (z.astype(np.int64) * L + y.astype(np.int64)) * L + x.astype(np.int64)

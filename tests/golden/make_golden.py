@@ -1,0 +1,63 @@
+"""Regenerates tests/golden/*.npz by running the UNMODIFIED reference (oracle/_ref/ahf_ref, built from
+/root/reference by oracle/build_ref.sh) on small synthetic boxes and collecting the hook dumps
+(oracle/ref_hooks.c).  Only runnable where the reference binary exists; the .npz files are committed.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
+sys.path.insert(0, ROOT)
+from ahf_b200 import synth          # noqa: E402
+from oracle import oracle as O      # noqa: E402
+
+CASES = {
+    # name: (n1d, seed, n_clumps, nper_dom, nper_ref, explicit clump centres (box units) or None)
+    "edge32": (32, 7, 8, 2.0, 2.5, [[0.0, 0.0, 0.0], [0.999, 0.5, 0.5], [0.5, 0.001, 0.999], [0.25, 0.999, 0.0005], [0.5, 0.5, 0.0]]),
+    "frag16": (16, 3, 4, 1.1, 1.3, [[0.02, 0.5, 0.97]]),
+    "plain32": (32, 42, 6, 2.0, 2.5, None),
+}
+
+
+def collect(name, n1d, seed, ncl, nper_dom, nper_ref, centres):
+    box = synth.make_box(n1d, seed=seed, n_clumps=ncl, centres_box=None if centres is None else np.array(centres))
+    work = tempfile.mkdtemp(prefix="ahf_golden_")
+    try:
+        inp = synth.write_reference_case(box, work, nper_dom=nper_dom, nper_ref=nper_ref)
+        O.run_reference(inp, dump_dir=os.path.join(work, "dump"), threads=1)
+        d = os.path.join(work, "dump")
+        P = O.read_particles(os.path.join(d, "particles.bin"))
+        out = dict(n1d=n1d, seed=seed, nper_dom=nper_dom, nper_ref=nper_ref, boxsize=P.boxsize, pmass=P.pmass,
+                   ids=P.ids.astype(np.uint32), keys=P.keys, pos=P.pos, mom=P.mom)   # key-sorted; input (file) order: x_in[ids] = x
+        nlev = 0
+        while os.path.exists(os.path.join(d, "flag_level_%02d.bin" % nlev)):
+            R = O.read_level(os.path.join(d, "flag_level_%02d.bin" % nlev))
+            F = O.read_level(os.path.join(d, "final_level_%02d.bin" % nlev))
+            p = "L%d_" % nlev
+            out[p + "l1dim"] = R.l1dim; out[p + "critdens"] = R.critdens; out[p + "masstopartdens"] = R.masstopartdens
+            out[p + "x"] = R.x; out[p + "y"] = R.y; out[p + "z"] = R.z; out[p + "dens"] = R.dens
+            out[p + "runflags"] = R.runflags; out[p + "cnt"] = R.cnt_flag; out[p + "plist"] = R.plist_flag.astype(np.int32)
+            out[p + "cnt_final"] = F.cnt_flag; out[p + "plist_final"] = F.plist_flag.astype(np.int32)
+            nlev += 1
+        out["nlev"] = nlev
+        H = O.read_halos(d)
+        out["halo_glob"] = H.glob; out["halo_s"] = H.s
+        out["halo_moff"] = np.concatenate([[0], np.cumsum([len(m) for m in H.members])]).astype(np.int64)
+        out["halo_members"] = np.concatenate(H.members).astype(np.int32) if H.n else np.zeros(0, np.int32)
+        nb = [0 if p is None else p.shape[1] for p in H.prof]
+        out["halo_poff"] = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
+        out["halo_prof"] = np.concatenate([p.reshape(-1) for p in H.prof if p is not None]) if sum(nb) else np.zeros(0)
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **out)
+        print(name, "levels", nlev, "halos", H.n, "bytes", os.path.getsize(os.path.join(ROOT, "tests", "golden", name + ".npz")))
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    for k, v in CASES.items():
+        collect(k, *v)

@@ -1,0 +1,55 @@
+"""CPU: the C restatement (oracle/) against the golden vectors produced by the unmodified reference.
+Integer / index results must be identical; the oracle reproduces the reference's summation order, so
+density and halo scalars are expected bit for bit (asserted to 1e-12 to stay robust to libm builds)."""
+import numpy as np
+
+from conftest import lin
+from oracle import oracle as O
+
+
+def test_keys_match_reference(golden):
+    k = O.hilbert_keys(golden.pos)
+    assert np.array_equal(k, golden.keys)
+    assert np.all(np.diff(golden.keys.astype(np.int64)) >= 0)
+    pos_in, _ = golden.input_order()
+    order = O.argsort_keys(O.hilbert_keys(pos_in))
+    assert np.array_equal(O.hilbert_keys(pos_in)[order], golden.keys)
+
+
+def test_key_prefix_property(golden):
+    # the halo gather relies on it (ahf_halos_sfc.c:370-412): the key at b bits is a prefix of the 21-bit key
+    for bits in (1, 2, 5, 11, 20):
+        kb = O.hilbert_keys(golden.pos[:2000], bits)
+        assert np.array_equal(kb, golden.keys[:2000] >> np.uint64(3 * (21 - bits)))
+
+
+def test_hierarchy_matches_reference(golden):
+    H = O.build_hierarchy(golden.pos, golden.n1d, nth_dom=golden.nper_dom, nth_ref=golden.nper_ref)
+    assert len(H) == golden.nlev
+    for l, M in enumerate(H):
+        R = golden.level(l)
+        assert M.l1dim == int(R["l1dim"]) and M.ncell == len(R["x"])
+        assert np.array_equal(M.lin(), lin(R["x"], R["y"], R["z"], R["l1dim"]))
+        assert np.array_equal(M.runflags, R["runflags"])
+        assert np.array_equal(M.cnt_flag, R["cnt"]) and np.array_equal(M.plist_flag, R["plist"])
+        assert np.array_equal(M.dens, R["dens"]), "density differs from the reference bit pattern"
+        assert abs(M.critdens - float(R["critdens"])) <= 1e-12 * abs(M.critdens)
+        assert np.array_equal(M.cnt_final, R["cnt_final"]) and np.array_equal(M.plist_final, R["plist_final"])
+
+
+def test_halo_pass_matches_reference(golden):
+    par = O.params_from_glob(golden.glob)
+    res = O.construct_halos(golden.keys, golden.pos, golden.mom, None, None, par, golden.hs[:, 0:3].copy(),
+                            golden.hs[:, 3].copy(), golden.hs[:, 4].copy())
+    slots = list(range(10, 58))
+    for i, r in enumerate(res):
+        ref = golden.hs[i]
+        if ref[4] == 0:
+            continue
+        assert [r["n_gather"], r["n_rvir0"], r["n_unbound"], r["n_rvir1"], r["npart"]] == [int(v) for v in ref[5:10]]
+        assert np.array_equal(r["ipart"], golden.members(i))
+        if r["npart"] < par["min_part"]:
+            continue
+        a, b = ref[slots], r["s"][slots]
+        assert np.allclose(a, b, rtol=1e-12, atol=0), (i, np.nonzero(~np.isclose(a, b, rtol=1e-12, atol=0)))
+        assert np.allclose(golden.prof(i), r["prof"], rtol=1e-12, atol=0)
