@@ -90,6 +90,12 @@ def lib():
         L.ahfgpu_finalize.argtypes = [C.c_void_p]
         L.ahfgpu_sfc_sort_particles.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32] + [C.c_int32] * 6
         L.ahfgpu_sfc_sort_soa.argtypes = [C.c_void_p] * 5 + [C.c_uint64, C.c_void_p, C.c_void_p]
+        L.ahfgpu_upload_soa.argtypes = [C.c_void_p] * 5 + [C.c_uint64]
+        L.ahfgpu_sfc_sort_resident.argtypes = [C.c_void_p]
+        L.ahfgpu_event_record.argtypes = [C.c_void_p, C.c_int32]
+        L.ahfgpu_event_elapsed_ms.restype = C.c_double
+        L.ahfgpu_event_elapsed_ms.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        L.ahfgpu_synchronize.argtypes = [C.c_void_p]
         L.ahfgpu_hilbert_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
         L.ahfgpu_build_amr.argtypes = [C.c_void_p]
         L.ahfgpu_amr_nlevels.argtypes = [C.c_void_p]
@@ -196,6 +202,25 @@ class AhfGpu:
                                               C.c_void_p(keys_ptr) if keys_ptr else None,
                                               C.c_void_p(order_ptr) if order_ptr else None))
         self.n = n
+
+    def upload(self, pos, mom, weight=None, u=None):
+        pos = np.ascontiguousarray(pos, np.float32); mom = np.ascontiguousarray(mom, np.float32)
+        weight = None if weight is None else np.ascontiguousarray(weight, np.float32)
+        u = None if u is None else np.ascontiguousarray(u, np.float32)
+        self._chk(self._L.ahfgpu_upload_soa(self._h, _p(pos), _p(mom), _p(weight), _p(u), pos.shape[0]))
+        self.n = pos.shape[0]
+
+    def sfc_sort_resident(self):
+        self._chk(self._L.ahfgpu_sfc_sort_resident(self._h))
+
+    def event_record(self, slot: int):
+        self._chk(self._L.ahfgpu_event_record(self._h, slot))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        return float(self._L.ahfgpu_event_elapsed_ms(self._h, a, b))
+
+    def synchronize(self):
+        self._chk(self._L.ahfgpu_synchronize(self._h))
 
     def sfc_sort_particles(self, part: np.ndarray, off_pos: int, off_mom: int, off_key: int, off_id: int,
                            off_weight: int = -1, off_u: int = -1):

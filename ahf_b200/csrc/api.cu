@@ -108,6 +108,8 @@ int ahfgpu_finalize(ahfgpu_ctx *c)
   cudaSetDevice(c->dev);
   cudaStreamSynchronize(c->stream);
   c->stage_reset(); c->free_halos(); c->free_levels(); c->free_particles();
+  cudaFree(c->in_pos); cudaFree(c->in_mom); cudaFree(c->in_w); cudaFree(c->in_u);
+  for (auto &e : c->ev) if (e) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;
   API_END
@@ -132,6 +134,55 @@ int ahfgpu_sfc_sort_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, con
   CUDA_CHECK(cudaSetDevice(c->dev));
   c->stage_reset();
   sfc_sort_soa(c, pos3, mom3, weight, u, n, keys_out, order_out);
+  API_END
+}
+
+int ahfgpu_upload_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, const float *weight, const float *u, uint64_t n)
+{
+  API_BEGIN
+  if (!c || ((!pos3 || !mom3) && n)) AHF_FAIL("null argument");
+  CUDA_CHECK(cudaSetDevice(c->dev));
+  c->stage_reset();
+  sfc_upload_soa(c, pos3, mom3, weight, u, n);
+  API_END
+}
+
+int ahfgpu_sfc_sort_resident(ahfgpu_ctx *c)
+{
+  API_BEGIN
+  if (!c) AHF_FAIL("null ctx");
+  CUDA_CHECK(cudaSetDevice(c->dev));
+  c->stage_reset();
+  sfc_sort_resident(c, nullptr, nullptr);
+  API_END
+}
+
+int ahfgpu_event_record(ahfgpu_ctx *c, int32_t slot)
+{
+  API_BEGIN
+  if (!c || slot < 0 || slot >= 16) AHF_FAIL("bad event slot");
+  CUDA_CHECK(cudaSetDevice(c->dev));
+  if (!c->ev[slot]) CUDA_CHECK(cudaEventCreate(&c->ev[slot]));
+  CUDA_CHECK(cudaEventRecord(c->ev[slot], c->stream));
+  API_END
+}
+
+double ahfgpu_event_elapsed_ms(ahfgpu_ctx *c, int32_t a, int32_t b)
+{
+  if (!c || a < 0 || b < 0 || a >= 16 || b >= 16 || !c->ev[a] || !c->ev[b]) return -1.0;
+  float ms = 0.f;
+  cudaSetDevice(c->dev);
+  if (cudaEventSynchronize(c->ev[b]) != cudaSuccess) return -1.0;
+  if (cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+
+int ahfgpu_synchronize(ahfgpu_ctx *c)
+{
+  API_BEGIN
+  if (!c) AHF_FAIL("null ctx");
+  CUDA_CHECK(cudaSetDevice(c->dev));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
   API_END
 }
 

@@ -97,6 +97,10 @@ struct ahfgpu_ctx {
   uint64_t *keys = nullptr;
   uint32_t *order = nullptr;    // input position of sorted particle i
   bool      has_weight = false, has_u = false;
+  // unsorted device copy kept by ahfgpu_upload_soa
+  float    *in_pos = nullptr, *in_mom = nullptr, *in_w = nullptr, *in_u = nullptr;
+  uint64_t  in_n = 0;
+  cudaEvent_t ev[16] = {};
   // hierarchy
   std::vector<ahf::Level> levels;
   int8_t   *owner_level = nullptr;   // [n]
@@ -141,6 +145,8 @@ void sfc_sort_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, const flo
                   uint64_t *keys_out, uint32_t *order_out);
 void sfc_sort_aos(ahfgpu_ctx *c, void *part, uint64_t n, uint32_t stride, int off_pos, int off_mom, int off_key,
                   int off_id, int off_w, int off_u);
+void sfc_upload_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, const float *w, const float *u, uint64_t n);
+void sfc_sort_resident(ahfgpu_ctx *c, uint64_t *keys_out, uint32_t *order_out);
 void sfc_keys_only(ahfgpu_ctx *c, const float *pos3, uint64_t n, uint32_t bits, uint64_t *keys_out);
 void radix_sort_pairs(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, uint64_t n,
                       int key_bits, uint64_t **keys_sorted, uint32_t **vals_sorted);

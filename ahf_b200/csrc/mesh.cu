@@ -555,8 +555,10 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
   acc.reserve(nc);
   CUDA_CHECK(cudaMemsetAsync(acc.p, 0, sizeof(unsigned long long) * nc, c->stream));
   CUDA_CHECK(cudaMemsetAsync(lv.count, 0, sizeof(int32_t) * nc, c->stream));
-  if (lv.npart_dep > 0)
+  if (lv.npart_dep > 0) {
+    Stage sk(c, lv.dense ? "deposit_dom_kernel" : "deposit_ref_kernel", lv.npart_dep);
     LAUNCH(c, k_deposit_generic, nblk(lv.npart_dep, 256), 256, 0, c->pos4, lv.plist, lv.pcell, (uint64_t)lv.npart_dep, v, lv.nbr, acc.p, lv.count);
+  }
   LAUNCH(c, k_finish_dens, nblk(nc, 256), 256, 0, acc.p, lv.dens, nc, lv.masstopartdens);
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
   acc.release();

@@ -221,29 +221,36 @@ void sfc_keys_only(ahfgpu_ctx *c, const float *pos3, uint64_t n, uint32_t bits, 
   dpos.release(); dk.release();
 }
 
-void sfc_sort_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, const float *w, const float *u, uint64_t n,
-                  uint64_t *keys_out, uint32_t *order_out)
+void sfc_upload_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, const float *w, const float *u, uint64_t n)
 {
   if (n >= (1ull << 32)) AHF_FAIL("more than 2^32-1 particles per device are not supported");
+  cudaFree(c->in_pos); cudaFree(c->in_mom); cudaFree(c->in_w); cudaFree(c->in_u);
+  c->in_pos = c->in_mom = c->in_w = c->in_u = nullptr; c->in_n = n;
+  CUDA_CHECK(cudaMalloc(&c->in_pos, (n ? n : 1) * 3 * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&c->in_mom, (n ? n : 1) * 3 * sizeof(float)));
+  if (w) CUDA_CHECK(cudaMalloc(&c->in_w, (n ? n : 1) * sizeof(float)));
+  if (u) CUDA_CHECK(cudaMalloc(&c->in_u, (n ? n : 1) * sizeof(float)));
+  Stage st(c, "h2d", (int64_t)(24 * n + (w ? 4 * n : 0) + (u ? 4 * n : 0)));
+  CUDA_CHECK(cudaMemcpyAsync(c->in_pos, pos3, 3 * n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(c->in_mom, mom3, 3 * n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  if (w) CUDA_CHECK(cudaMemcpyAsync(c->in_w, w, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  if (u) CUDA_CHECK(cudaMemcpyAsync(c->in_u, u, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+void sfc_sort_resident(ahfgpu_ctx *c, uint64_t *keys_out, uint32_t *order_out)
+{
+  if (!c->in_pos) AHF_FAIL("no uploaded particles: call ahfgpu_upload_soa first");
+  const uint64_t n = c->in_n;
   alloc_particles(c, n);
-  c->has_weight = (w != nullptr); c->has_u = (u != nullptr);
-  DevBuf<float>    dpos, dmom, dw, du;
+  c->has_weight = (c->in_w != nullptr); c->has_u = (c->in_u != nullptr);
   DevBuf<uint64_t> k0, k1;
   DevBuf<uint32_t> v0, v1;
-  dpos.reserve(3 * n); dmom.reserve(3 * n); k0.reserve(n); k1.reserve(n); v0.reserve(n); v1.reserve(n);
-  if (w) dw.reserve(n);
-  if (u) du.reserve(n);
-  {
-    Stage st(c, "h2d", (int64_t)(24 * n + (w ? 4 * n : 0) + (u ? 4 * n : 0)));
-    CUDA_CHECK(cudaMemcpyAsync(dpos.p, pos3, 3 * n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    CUDA_CHECK(cudaMemcpyAsync(dmom.p, mom3, 3 * n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    if (w) CUDA_CHECK(cudaMemcpyAsync(dw.p, w, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    if (u) CUDA_CHECK(cudaMemcpyAsync(du.p, u, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  }
+  k0.reserve(n); k1.reserve(n); v0.reserve(n); v1.reserve(n);
   const unsigned nb = (unsigned)((n + 255) / 256);
   {
     Stage st(c, "keys", (int64_t)n);
-    if (n) LAUNCH(c, k_keys_soa, nb, 256, 0, dpos.p, n, 21u, k0.p, v0.p);
+    if (n) LAUNCH(c, k_keys_soa, nb, 256, 0, c->in_pos, n, 21u, k0.p, v0.p);
   }
   uint64_t *ks; uint32_t *vs;
   {
@@ -252,20 +259,26 @@ void sfc_sort_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, const flo
   }
   {
     Stage st(c, "gather", (int64_t)n);
-    if (n) LAUNCH(c, k_gather_soa, nb, 256, 0, dpos.p, dmom.p, w ? dw.p : nullptr, u ? du.p : nullptr, vs, n, c->pos4, c->mom4);
+    if (n) LAUNCH(c, k_gather_soa, nb, 256, 0, c->in_pos, c->in_mom, c->in_w, c->in_u, vs, n, c->pos4, c->mom4);
   }
-  // keep sorted keys / order resident
   CUDA_CHECK(cudaMalloc(&c->keys, (n ? n : 1) * sizeof(uint64_t)));
   CUDA_CHECK(cudaMalloc(&c->order, (n ? n : 1) * sizeof(uint32_t)));
   CUDA_CHECK(cudaMemcpyAsync(c->keys, ks, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
   CUDA_CHECK(cudaMemcpyAsync(c->order, vs, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
-  {
+  if (keys_out || order_out) {
     Stage st(c, "d2h", (int64_t)((keys_out ? 8 * n : 0) + (order_out ? 4 * n : 0)));
     if (keys_out) CUDA_CHECK(cudaMemcpyAsync(keys_out, c->keys, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
     if (order_out) CUDA_CHECK(cudaMemcpyAsync(order_out, c->order, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   }
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  dpos.release(); dmom.release(); dw.release(); du.release(); k0.release(); k1.release(); v0.release(); v1.release();
+  k0.release(); k1.release(); v0.release(); v1.release();
+}
+
+void sfc_sort_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, const float *w, const float *u, uint64_t n,
+                  uint64_t *keys_out, uint32_t *order_out)
+{
+  sfc_upload_soa(c, pos3, mom3, w, u, n);
+  sfc_sort_resident(c, keys_out, order_out);
 }
 
 void sfc_sort_aos(ahfgpu_ctx *c, void *part, uint64_t n, uint32_t stride, int off_pos, int off_mom, int off_key, int off_id,

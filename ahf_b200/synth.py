@@ -183,3 +183,23 @@ def write_reference_case(box: Box, workdir: str, lgrid_domain: int | None = None
     inp = os.path.join(workdir, "AHF.input")
     write_ahf_input(inp, snap, os.path.join(workdir, "ref"), lgrid_domain or box.n1d, **kw)
     return inp
+
+
+def halo_seeds(box: Box, max_gather_rad_mpc: float = 3.0):
+    """Halo seeds (centre, gathering radius, seed particle count) for the per-halo pass, standing in for what the
+    reference's tree stage hands to ahf_halos_sfc_constructHalo: centres = the generator's clump centres,
+    gatherRad = half the periodic distance to the nearest clump with more particles, at most
+    min(MaxGatherRad/boxsize, 1/4); the richest clump gets the maximum (reference src/libahf/ahf_halos.c:2987-3051)."""
+    c = np.mod(box.clump_centres, 1.0)
+    npart = box.clump_npart.astype(np.int64)
+    nh = len(npart)
+    rmax = min(max_gather_rad_mpc / box.boxsize, 0.25)
+    order = np.argsort(-npart, kind="stable")
+    rad = np.full(nh, rmax)
+    cs = c[order]
+    for rank in range(1, nh):                      # clumps with more particles are the ones before `rank`
+        d = np.abs(cs[:rank] - cs[rank])
+        d = np.where(d > 0.5, 1.0 - d, d)
+        dist = np.sqrt((d * d).sum(axis=1)).min()
+        rad[order[rank]] = min(max(0.5 * dist, 4.0 * box.clump_scale[order[rank]]), rmax)
+    return c.astype(np.float64), rad.astype(np.float64), npart

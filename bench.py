@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py -- the AHF particle hot path on B200: Hilbert keys + sort, TSC deposit on the domain grid and every
+refinement level, refinement flags / next level / relink, per-halo gather + radial sort + unbinding + profiles.
+
+One "step" = one pass of the whole path over one synthetic box (BASELINE.json configs[1]: 256^3 particles,
+LgridDomain 256, AHF.input-example settings).  Prints ONE JSON line (rank 0).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--n1d 256] [--impl ours|reference]
+
+N > 1 (torchrun): the path is embarrassingly parallel over independent boxes; every rank processes its own box
+(different seed) on its own GPU, no data-path collective -> "scaling": "weak".
+--impl reference: the reference's own CPU implementation (oracle/_ref/ahf_ref = unmodified NegriAndrea/AHF with
+timing hooks) on a bounded sample (128^3 box of the same generator), all host threads, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particles/sec through the hot path (keys+sort, TSC deposit+flag+refine+relink on all levels, halo gather+sort+unbind+profiles)"
+UNIT = "particles/s"
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.sm_max = None
+        self._halt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0])); self.sm_max = float(out[1])
+                for nm, v in zip(names, out[2:6]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=5)
+        med = statistics.median(self.samples) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def run_reference_sample(n1d: int, seed: int, threads: int | None):
+    """Unmodified reference on a bounded sample; returns (pps, detail dict)."""
+    from ahf_b200 import synth
+    from oracle import oracle as O
+    box = synth.make_box(n1d, seed=seed)
+    work = tempfile.mkdtemp(prefix="ahf_refbench_")
+    try:
+        inp = synth.write_reference_case(box, work)
+        t0 = time.perf_counter()
+        t = O.run_reference(inp, dump_dir=None, threads=threads)
+        wall = time.perf_counter() - t0
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+    path_s = t["keys"] + t["sort"] + t["ll"] + t["deposit"] + t["refine"] + t["relink"] + t["halo_loop"]
+    return box.npart / path_s, dict(t, wall_s=wall, path_s=path_s, npart=box.npart)
+
+
+def run_port_sample(n1d: int, seed: int):
+    """CPU port (oracle/) on a bounded sample when the reference binary is not available."""
+    from ahf_b200 import synth, ahf
+    from oracle import oracle as O
+    box = synth.make_box(n1d, seed=seed)
+    t0 = time.perf_counter()
+    keys = O.hilbert_keys(box.pos); order = O.argsort_keys(keys)
+    pos = box.pos[order]; mom = box.mom[order]; keys = keys[order]
+    O.build_hierarchy(pos, n1d)
+    c, r, npart = synth.halo_seeds(box)
+    P = ahf.make_params(boxsize=box.boxsize, pmass=box.pmass, lgrid_dom=n1d)
+    par = dict(r_fac=P.r_fac, x_fac=P.x_fac, v_fac=P.v_fac, m_fac=P.m_fac, rho_fac=P.rho_fac, phi_fac=P.phi_fac,
+               Hubble=P.hubble, ovlim=P.ovlim, rho_vir=P.rho_vir, vesc_tune=P.vesc_tune, min_part=P.min_part)
+    O.construct_halos(keys, pos, mom, None, None, par, c, r, npart)
+    dt = time.perf_counter() - t0
+    return box.npart / dt, dict(path_s=dt, npart=box.npart)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--n1d", type=int, default=256)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-n1d", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="print the per-stage table to stderr")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": f"synthetic {args.n1d}^3-particle box (jittered lattice + Plummer clumps, seed 43+rank), LgridDomain {args.n1d}, "
+                          "AHF.input-example settings (NperDomCell 2.0, NperRefCell 2.5, VescTune 1.5, NminPerHalo 20, Dvir 200)",
+              "n_particles_per_gpu": args.n1d ** 3, "lgrid_domain": args.n1d,
+              "l2": "inputs (particle arrays 0.5 GB, domain grid 0.2 GB at 256^3) exceed the 126 MB L2; no explicit flush",
+              "parallelism": "one independent box per GPU, no collective" if world > 1 else "single GPU"}
+
+    # ------------------------------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        from oracle import oracle as O
+        nthreads = os.cpu_count() or 1
+        have_ref = os.path.exists(O.REF_BIN)
+        vals = []
+        detail = {}
+        for i in range(args.warmup + args.steps):
+            if have_ref:
+                v, detail = run_reference_sample(args.ref_n1d, 43, nthreads)
+            else:
+                v, detail = run_port_sample(min(args.ref_n1d, 64), 43)
+            if i >= args.warmup:
+                vals.append(v)
+        val = float(np.mean(vals))
+        sample = (f"{args.ref_n1d}^3 box of the same generator per step (bounded sample of the {args.n1d}^3 workload); "
+                  "time = keys+qsort+ll+deposit(all levels, as the reference does them: twice)+refine+relink+halo loop")
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * detail.get("path_s", 0.0), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32 particles / f64 halo arithmetic", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads if have_ref else 1,
+                                 "kind": "reference" if have_ref else "port", "sample": sample},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "detail": detail}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    from ahf_b200 import ahf, synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ahf.build()
+    box = synth.make_box(args.n1d, seed=43 + rank)
+    n = box.npart
+    centres, rad, seednp = synth.halo_seeds(box)
+    par = ahf.make_params(boxsize=box.boxsize, pmass=box.pmass, lgrid_dom=args.n1d, device=local_rank)
+    g = ahf.AhfGpu(par)
+    # pinned host buffers for the end-to-end leg
+    hpos = torch.empty((n, 3), dtype=torch.float32, pin_memory=True); hpos.numpy()[:] = box.pos
+    hmom = torch.empty((n, 3), dtype=torch.float32, pin_memory=True); hmom.numpy()[:] = box.mom
+
+    def barrier():
+        g.synchronize(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        g.sfc_sort_resident()
+        st = {k: g.stage_ms(k) for k in ("keys", "sort", "gather")}
+        g.build_amr()
+        st.update({k: g.stage_ms(k) for k in ("ll", "deposit", "deposit_dom_kernel", "flag", "refine", "relink")})
+        st["deposit_particles"] = g.stage_count("deposit")
+        g.construct_halos(centres, rad, seednp, fetch=False)
+        st.update({k: g.stage_ms(k) for k in ("halo_gather", "halo_sort", "halo_unbind", "halo_profiles")})
+        st["halo_gathered"] = g.stage_count("halo_gathered")
+        return st
+
+    def step_e2e():
+        g.sfc_sort_ptr(hpos.data_ptr(), hmom.data_ptr(), n)
+        g.build_amr()
+        g.construct_halos(centres, rad, seednp, fetch=False)
+        return g.fetch_halos(len(rad), scal_only=True)["scal"]
+
+    # ---- HBM-resident timing
+    g.upload(box.pos, box.mom)
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank); sampler.start()
+    barrier()
+    l0 = g.launches()
+    g.event_record(0)
+    stages = []
+    for _ in range(args.steps):
+        stages.append(step_resident())
+    g.event_record(1)
+    barrier()
+    ms_res = g.event_elapsed_ms(0, 1) / args.steps
+    launches = g.launches() - l0
+    # ---- end-to-end timing (pinned host -> device every step, results back every step)
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    g.event_record(2)
+    for _ in range(args.steps):
+        scal = step_e2e()
+    g.event_record(3)
+    barrier()
+    ms_e2e = g.event_elapsed_ms(2, 3) / args.steps
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms_res, ms_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_res, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    st = {k: float(np.mean([s[k] for s in stages])) for k in stages[0]}
+    nlev = g.nlevels()
+    hdr0, _ = g.level_header(0)
+    peak, peak_src = measured_peak_gbs()
+    C0 = args.n1d ** 3
+    dep_bytes = 16.0 * n + 4.0 * C0                       # B_dep,0 = 16 N_0 + 4 C_0
+    t_dep_kernel = st["deposit_dom_kernel"] * 1e-3
+    achieved = dep_bytes / t_dep_kernel / 1e9
+    nhalo_ok = int((scal[:, 9] >= par.min_part).sum())
+    line = {
+        "metric": METRIC, "value": world * n / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 particles, u32/u64 fixed-point deposit, f64 halo arithmetic", "data": "synthetic", "config": config,
+        "e2e": {"value": world * n / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": 24 * n + 32 * len(rad) + 8 * len(rad),
+                "d2h_bytes_per_step": int(scal.nbytes)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "TSC deposit, domain level (k_deposit_*)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes": dep_bytes, "kernel_ms": st["deposit_dom_kernel"]},
+        "stages_ms": {k: v for k, v in st.items() if k not in ("deposit_particles", "halo_gathered")},
+        "throughput": {"deposit_pps": st["deposit_particles"] / (st["deposit"] * 1e-3), "deposit_particles_all_levels": st["deposit_particles"],
+                       "unbind_pps": st["halo_gathered"] / ((st["halo_gather"] + st["halo_sort"] + st["halo_unbind"] + st["halo_profiles"]) * 1e-3),
+                       "halo_gathered_particles": st["halo_gathered"], "levels": nlev, "halos_in": len(rad), "halos_ge_minpart": nhalo_ok},
+    }
+    if not args.no_cpu_baseline:
+        from oracle import oracle as O
+        nthreads = os.cpu_count() or 1
+        if os.path.exists(O.REF_BIN):
+            v, d = run_reference_sample(args.ref_n1d, 43, nthreads)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": nthreads, "kind": "reference",
+                                    "sample": f"unmodified reference (oracle/_ref/ahf_ref) on a {args.ref_n1d}^3 box of the same generator, one run",
+                                    "detail": {k: d[k] for k in ("keys", "sort", "ll", "deposit", "refine", "relink", "halo_loop", "path_s")}}
+        else:
+            v, d = run_port_sample(64, 43)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": "oracle/ C port on a 64^3 box of the same generator"}
+    if args.breakdown:
+        for k, v in sorted(line["stages_ms"].items()):
+            print(f"  {k:22s} {v:10.3f} ms", file=sys.stderr)
+    print(json.dumps(line))
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

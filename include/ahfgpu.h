@@ -67,6 +67,11 @@ int  ahfgpu_sfc_sort_particles(ahfgpu_ctx *ctx, void *part, uint64_t n, uint32_t
                                int32_t off_mom, int32_t off_key, int32_t off_id, int32_t off_weight, int32_t off_u);
 int  ahfgpu_sfc_sort_soa(ahfgpu_ctx *ctx, const float *pos3, const float *mom3, const float *weight, const float *u,
                          uint64_t n, uint64_t *keys_out, uint32_t *order_out);
+/* Same as ahfgpu_sfc_sort_soa but split in two so that the sort can be timed with its input already in HBM:
+ * ahfgpu_upload_soa copies the unsorted arrays to the device, ahfgpu_sfc_sort_resident runs keys + sort + gather on
+ * them (repeatable: the unsorted copy is kept).                                                                */
+int  ahfgpu_upload_soa(ahfgpu_ctx *ctx, const float *pos3, const float *mom3, const float *weight, const float *u, uint64_t n);
+int  ahfgpu_sfc_sort_resident(ahfgpu_ctx *ctx);
 /* keys only (no sort, nothing stays resident): sfc_curve_calcKey(SFC_CURVE_HILBERT, x, y, z, bits) per particle */
 int  ahfgpu_hilbert_keys(ahfgpu_ctx *ctx, const float *pos3, uint64_t n, uint32_t bits, uint64_t *keys_out);
 
@@ -117,6 +122,10 @@ int  ahfgpu_halo_fetch(ahfgpu_ctx *ctx, double *scal, int64_t *member_offset, in
  * the library's stream.  names: "h2d","keys","sort","gather","d2h","deposit","flag","refine","relink",
  * "halo_gather","halo_sort","halo_unbind","halo_profiles", ... ; returns <0 for an unknown name.             */
 double  ahfgpu_stage_ms(ahfgpu_ctx *ctx, const char *name);
+/* CUDA events on the library's own stream (slot 0..15): record, then elapsed milliseconds between two slots */
+int     ahfgpu_event_record(ahfgpu_ctx *ctx, int32_t slot);
+double  ahfgpu_event_elapsed_ms(ahfgpu_ctx *ctx, int32_t slot_a, int32_t slot_b);
+int     ahfgpu_synchronize(ahfgpu_ctx *ctx);
 int64_t ahfgpu_stage_count(ahfgpu_ctx *ctx, const char *name);   /* launches / items attributed to the stage */
 
 #ifdef __cplusplus
