@@ -3,12 +3,13 @@
 
 namespace ahf {
 thread_local std::string g_last_error;
+thread_local cudaStream_t g_pool_stream = nullptr;
 
 void Level::free_all()
 {
-  cudaFree(ckey); cudaFree(xbreak); cudaFree(dens); cudaFree(interior); cudaFree(tn); cudaFree(mark); cudaFree(nbr);
-  cudaFree(crow); cudaFree(count); cudaFree(hkey); cudaFree(hval); cudaFree(rowkey); cudaFree(row_c0); cudaFree(row_tested);
-  cudaFree(plane_r0); cudaFree(rowplane); cudaFree(plist); cudaFree(pcell);
+  ahf::dfree(ckey); ahf::dfree(xbreak); ahf::dfree(dens); ahf::dfree(interior); ahf::dfree(tn); ahf::dfree(mark); ahf::dfree(nbr);
+  ahf::dfree(crow); ahf::dfree(count); ahf::dfree(hkey); ahf::dfree(hval); ahf::dfree(rowkey); ahf::dfree(row_c0); ahf::dfree(row_tested);
+  ahf::dfree(plane_r0); ahf::dfree(rowplane); ahf::dfree(plist); ahf::dfree(pcell);
   *this = Level();
 }
 }  // namespace ahf
@@ -18,7 +19,7 @@ using namespace ahf;
 void ahfgpu_ctx::stage_reset()
 {
   for (auto &s : stages) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
-  stages.clear(); stage_ms.clear(); stage_cnt.clear(); stages_resolved = true;
+  stages.clear(); stage_ms.clear(); stage_cnt.clear(); stage_cnt_extra.clear(); stages_resolved = true;
 }
 void ahfgpu_ctx::stage_resolve()
 {
@@ -34,18 +35,18 @@ void ahfgpu_ctx::stage_resolve()
 }
 void ahfgpu_ctx::free_particles()
 {
-  cudaFree(pos4); cudaFree(mom4); cudaFree(keys); cudaFree(order);
+  ahf::dfree(pos4); ahf::dfree(mom4); ahf::dfree(keys); ahf::dfree(order);
   pos4 = mom4 = nullptr; keys = nullptr; order = nullptr; n = 0;
 }
 void ahfgpu_ctx::free_levels()
 {
   for (auto &l : levels) l.free_all();
   levels.clear();
-  cudaFree(owner_level); owner_level = nullptr;
+  ahf::dfree(owner_level); owner_level = nullptr;
 }
 void ahfgpu_ctx::free_halos()
 {
-  cudaFree(h_scal); cudaFree(h_moff); cudaFree(h_members); cudaFree(h_poff); cudaFree(h_prof);
+  ahf::dfree(h_scal); ahf::dfree(h_moff); ahf::dfree(h_members); ahf::dfree(h_poff); ahf::dfree(h_prof);
   h_scal = nullptr; h_moff = nullptr; h_members = nullptr; h_poff = nullptr; h_prof = nullptr;
   nhalo = 0; h_total_members = h_total_bins = 0;
 }
@@ -87,6 +88,12 @@ int ahfgpu_init(ahfgpu_ctx **out, const ahfgpu_params *par)
   ahfgpu_ctx *c = new ahfgpu_ctx();
   c->par = *par; c->dev = par->device;
   CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {
+    cudaMemPool_t pool;
+    CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, par->device));
+    uint64_t keep = ~0ull;
+    CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   *out = c;
   API_END
 }
@@ -105,11 +112,12 @@ int ahfgpu_finalize(ahfgpu_ctx *c)
 {
   API_BEGIN
   if (!c) return 0;
-  cudaSetDevice(c->dev);
+  cudaSetDevice(c->dev); ahf::g_pool_stream = c->stream;
   cudaStreamSynchronize(c->stream);
   c->stage_reset(); c->free_halos(); c->free_levels(); c->free_particles();
-  cudaFree(c->in_pos); cudaFree(c->in_mom); cudaFree(c->in_w); cudaFree(c->in_u);
+  ahf::dfree(c->in_pos); ahf::dfree(c->in_mom); ahf::dfree(c->in_w); ahf::dfree(c->in_u);
   for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+  cudaStreamSynchronize(c->stream);
   cudaStreamDestroy(c->stream);
   delete c;
   API_END
@@ -120,7 +128,7 @@ int ahfgpu_sfc_sort_particles(ahfgpu_ctx *c, void *part, uint64_t n, uint32_t st
 {
   API_BEGIN
   if (!c || (!part && n)) AHF_FAIL("null argument");
-  CUDA_CHECK(cudaSetDevice(c->dev));
+  CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
   c->stage_reset();
   sfc_sort_aos(c, part, n, stride, off_pos, off_mom, off_key, off_id, off_weight, off_u);
   API_END
@@ -131,7 +139,7 @@ int ahfgpu_sfc_sort_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, con
 {
   API_BEGIN
   if (!c || ((!pos3 || !mom3) && n)) AHF_FAIL("null argument");
-  CUDA_CHECK(cudaSetDevice(c->dev));
+  CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
   c->stage_reset();
   sfc_sort_soa(c, pos3, mom3, weight, u, n, keys_out, order_out);
   API_END
@@ -141,7 +149,7 @@ int ahfgpu_upload_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, const
 {
   API_BEGIN
   if (!c || ((!pos3 || !mom3) && n)) AHF_FAIL("null argument");
-  CUDA_CHECK(cudaSetDevice(c->dev));
+  CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
   c->stage_reset();
   sfc_upload_soa(c, pos3, mom3, weight, u, n);
   API_END
@@ -151,7 +159,7 @@ int ahfgpu_sfc_sort_resident(ahfgpu_ctx *c)
 {
   API_BEGIN
   if (!c) AHF_FAIL("null ctx");
-  CUDA_CHECK(cudaSetDevice(c->dev));
+  CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
   c->stage_reset();
   sfc_sort_resident(c, nullptr, nullptr);
   API_END
@@ -161,7 +169,7 @@ int ahfgpu_event_record(ahfgpu_ctx *c, int32_t slot)
 {
   API_BEGIN
   if (!c || slot < 0 || slot >= 16) AHF_FAIL("bad event slot");
-  CUDA_CHECK(cudaSetDevice(c->dev));
+  CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
   if (!c->ev[slot]) CUDA_CHECK(cudaEventCreate(&c->ev[slot]));
   CUDA_CHECK(cudaEventRecord(c->ev[slot], c->stream));
   API_END
@@ -181,7 +189,7 @@ int ahfgpu_synchronize(ahfgpu_ctx *c)
 {
   API_BEGIN
   if (!c) AHF_FAIL("null ctx");
-  CUDA_CHECK(cudaSetDevice(c->dev));
+  CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
   API_END
 }
@@ -191,7 +199,7 @@ int ahfgpu_hilbert_keys(ahfgpu_ctx *c, const float *pos3, uint64_t n, uint32_t b
   API_BEGIN
   if (!c || ((!pos3 || !keys_out) && n)) AHF_FAIL("null argument");
   if (bits < 1 || bits > 21) AHF_FAIL("bits must be in 1..21");
-  CUDA_CHECK(cudaSetDevice(c->dev));
+  CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
   c->stage_reset();
   sfc_keys_only(c, pos3, n, bits, keys_out);
   API_END
@@ -202,7 +210,7 @@ int ahfgpu_build_amr(ahfgpu_ctx *c)
   API_BEGIN
   if (!c) AHF_FAIL("null ctx");
   if (!c->pos4) AHF_FAIL("no resident particles: call ahfgpu_sfc_sort_* first");
-  CUDA_CHECK(cudaSetDevice(c->dev));
+  CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
   c->stage_reset();
   amr_build(c);
   API_END
@@ -235,7 +243,7 @@ int ahfgpu_construct_halos(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, 
   if (!c) AHF_FAIL("null ctx");
   if (!c->pos4) AHF_FAIL("no resident particles: call ahfgpu_sfc_sort_* first");
   if (nhalo && (!centre3 || !gather_rad)) AHF_FAIL("null argument");
-  CUDA_CHECK(cudaSetDevice(c->dev));
+  CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
   c->stage_reset();
   halos_construct(c, nhalo, centre3, gather_rad, seed);
   API_END
@@ -245,7 +253,7 @@ int ahfgpu_halo_fetch(ahfgpu_ctx *c, double *scal, int64_t *member_offset, int64
 {
   API_BEGIN
   if (!c) AHF_FAIL("null ctx");
-  CUDA_CHECK(cudaSetDevice(c->dev));
+  CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
   if (scal && c->nhalo) CUDA_CHECK(cudaMemcpy(scal, c->h_scal, sizeof(double) * AHFGPU_NSCAL * c->nhalo, cudaMemcpyDeviceToHost));
   if (member_offset) CUDA_CHECK(cudaMemcpy(member_offset, c->h_moff, sizeof(int64_t) * (c->nhalo + 1), cudaMemcpyDeviceToHost));
   if (members && c->h_total_members) CUDA_CHECK(cudaMemcpy(members, c->h_members, sizeof(int64_t) * c->h_total_members, cudaMemcpyDeviceToHost));
@@ -267,6 +275,8 @@ int64_t ahfgpu_stage_count(ahfgpu_ctx *c, const char *name)
   if (!c || !name) return -1;
   if (!strcmp(name, "launches")) return c->n_launches;
   c->stage_resolve();
+  auto ie = c->stage_cnt_extra.find(name);
+  if (ie != c->stage_cnt_extra.end()) return ie->second;
   auto it = c->stage_cnt.find(name);
   return it == c->stage_cnt.end() ? -1 : it->second;
 }

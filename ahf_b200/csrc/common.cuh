@@ -37,18 +37,23 @@ inline void fail(const char *file, int line, const std::string &what)
     CUDA_CHECK(cudaGetLastError());                                                                      \
   } while (0)
 
+// stream-ordered allocation from the device's default memory pool (release threshold raised in ahfgpu_init so that
+// freed blocks are reused instead of being returned to the driver): every API entry sets g_pool_stream = ctx->stream
+extern thread_local cudaStream_t g_pool_stream;
+inline void dfree(void *p) { if (p) cudaFreeAsync(p, g_pool_stream); }
+
 template <typename T> struct DevBuf {
   T     *p   = nullptr;
   size_t cap = 0;
   void reserve(size_t n)
   {
     if (n <= cap) return;
-    if (p) CUDA_CHECK(cudaFree(p));
+    if (p) ahf::dfree(p);
     p = nullptr; cap = 0;
-    CUDA_CHECK(cudaMalloc(&p, (n ? n : 1) * sizeof(T)));
+    CUDA_CHECK(cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), ahf::g_pool_stream));
     cap = n ? n : 1;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  void release() { if (p) ahf::dfree(p); p = nullptr; cap = 0; }
 };
 
 // one refinement level on the device (see DESIGN.md "data layout")
@@ -116,6 +121,7 @@ struct ahfgpu_ctx {
   std::vector<ahf::StageRec> stages;
   std::map<std::string, double>  stage_ms;
   std::map<std::string, int64_t> stage_cnt;
+  std::map<std::string, int64_t> stage_cnt_extra;   // counters set directly by the stages (not event based)
   bool stages_resolved = true;
 
   void stage_reset();

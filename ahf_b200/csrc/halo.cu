@@ -815,7 +815,7 @@ static std::vector<int64_t> host_excl(const std::vector<int64_t> &v, int64_t *to
 template <typename T> static T *dalloc(size_t n)
 {
   T *p = nullptr;
-  CUDA_CHECK(cudaMalloc(&p, (n ? n : 1) * sizeof(T)));
+  CUDA_CHECK(cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), ahf::g_pool_stream));
   return p;
 }
 static inline unsigned nblk(uint64_t n, int b) { return (unsigned)((n + b - 1) / b); }
@@ -867,7 +867,7 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
   for (int64_t h = 0; h < nhalo; h++) h_ne[h] = h_ng[h] >= P.min_part ? h_ng[h] : 0;
   std::vector<int64_t> eoff = host_excl(h_ne, &tot_e);
   if (tot_e >= (1ll << 32)) AHF_FAIL("more than 2^32 gathered members in one call: split the halo list");
-  c->stage_cnt["halo_gathered"] = tot_g;
+  c->stage_cnt_extra["halo_gathered"] = tot_g;
   int64_t *d_moff0 = dalloc<int64_t>(nhalo + 1), *d_eoff = dalloc<int64_t>(nhalo + 1);
   CUDA_CHECK(cudaMemcpyAsync(d_moff0, moff0.data(), sizeof(int64_t) * (nhalo + 1), cudaMemcpyHostToDevice, c->stream));
   CUDA_CHECK(cudaMemcpyAsync(d_eoff, eoff.data(), sizeof(int64_t) * (nhalo + 1), cudaMemcpyHostToDevice, c->stream));
@@ -894,11 +894,11 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
       // scatter halo segments: eoff-layout -> moff0-layout
       LAUNCH(c, k_scatter_sorted, (unsigned)nhalo, 256, 0, d_eoff, d_moff0, sorted, d_members);
       CUDA_CHECK(cudaStreamSynchronize(c->stream));
-      cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(hid); cudaFree(v3); cudaFree(sorted);
+      ahf::dfree(k0); ahf::dfree(k1); ahf::dfree(v0); ahf::dfree(v1); ahf::dfree(hid); ahf::dfree(v3); ahf::dfree(sorted);
     }
     LAUNCH(c, k_copy_unsorted, (unsigned)nhalo, 64, 0, d_candoff, d_ng, d_moff0, P.min_part, d_idx, d_members);
   }
-  cudaFree(d_r2);
+  ahf::dfree(d_r2);
   int64_t *d_np = dalloc<int64_t>(nhalo), *d_work = dalloc<int64_t>(nhalo);
   {
     Stage st(c, "halo_unbind", tot_g);
@@ -910,7 +910,7 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
     std::vector<int64_t> h_work(nhalo);
     CUDA_CHECK(cudaMemcpy(h_work.data(), d_work, sizeof(int64_t) * nhalo, cudaMemcpyDeviceToHost));
     int64_t tw = 0; for (auto w : h_work) tw += w;
-    c->stage_cnt["halo_unbind_iter_members"] = tw;
+    c->stage_cnt_extra["halo_unbind_iter_members"] = tw;
   }
   // offsets of the final member lists, profile bins and scratch
   std::vector<int64_t> h_nb(nhalo), h_sc(nhalo);
@@ -922,7 +922,7 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
   int64_t tot_m = 0, tot_b = 0, tot_s = 0;
   std::vector<int64_t> moff = host_excl(h_np, &tot_m), poff = host_excl(h_nb, &tot_b), soff = host_excl(h_sc, &tot_s);
   c->h_total_members = tot_m; c->h_total_bins = tot_b;
-  c->stage_cnt["halo_final_members"] = tot_s;
+  c->stage_cnt_extra["halo_final_members"] = tot_s;
   CUDA_CHECK(cudaMemcpyAsync(c->h_moff, moff.data(), sizeof(int64_t) * (nhalo + 1), cudaMemcpyHostToDevice, c->stream));
   CUDA_CHECK(cudaMemcpyAsync(c->h_poff, poff.data(), sizeof(int64_t) * (nhalo + 1), cudaMemcpyHostToDevice, c->stream));
   int64_t *d_soff = dalloc<int64_t>(nhalo + 1);
@@ -937,8 +937,8 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
     LAUNCH(c, k_members_out, (unsigned)nhalo, 256, 0, d_moff0, d_np, c->h_moff, d_members, c->h_members);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
   }
-  cudaFree(d_ctr); cudaFree(d_rad); cudaFree(d_seed); cudaFree(d_rlo); cudaFree(d_rhi); cudaFree(d_cand); cudaFree(d_candoff); cudaFree(d_ng);
-  cudaFree(d_idx); cudaFree(d_moff0); cudaFree(d_eoff); cudaFree(d_members); cudaFree(d_np); cudaFree(d_work); cudaFree(d_soff); cudaFree(d_scratch);
+  ahf::dfree(d_ctr); ahf::dfree(d_rad); ahf::dfree(d_seed); ahf::dfree(d_rlo); ahf::dfree(d_rhi); ahf::dfree(d_cand); ahf::dfree(d_candoff); ahf::dfree(d_ng);
+  ahf::dfree(d_idx); ahf::dfree(d_moff0); ahf::dfree(d_eoff); ahf::dfree(d_members); ahf::dfree(d_np); ahf::dfree(d_work); ahf::dfree(d_soff); ahf::dfree(d_scratch);
 }
 
 }  // namespace ahf

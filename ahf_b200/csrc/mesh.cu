@@ -8,6 +8,7 @@
 // HBM-bound integer/float scatter work: no tensor cores.
 #include "common.cuh"
 #include "scan.cuh"
+#include "hilbert.cuh"
 
 namespace ahf {
 
@@ -102,8 +103,7 @@ __device__ __forceinline__ double sep_cell(float pos, int i, double L)
 
 __global__ void __launch_bounds__(256) k_deposit_generic(const float4 *__restrict__ pos4, const uint32_t *__restrict__ plist,
                                                          const int32_t *__restrict__ pcell, uint64_t np, LV v,
-                                                         const int32_t *__restrict__ nbr, unsigned long long *__restrict__ acc,
-                                                         int32_t *__restrict__ count)
+                                                         const int32_t *__restrict__ nbr, unsigned long long *__restrict__ acc)
 {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const bool valid = i < np;
@@ -125,7 +125,6 @@ __global__ void __launch_bounds__(256) k_deposit_generic(const float4 *__restric
   unsigned peers  = __match_any_sync(0xffffffffu, c);
   int      leader = __ffs(peers) - 1;
   const bool any_agg = __any_sync(0xffffffffu, valid && (__popc(peers) > 1));
-  if (valid && lane == leader) atomicAdd(&count[c], __popc(peers));
 #pragma unroll
   for (int k = 0; k < 3; k++)
 #pragma unroll
@@ -148,6 +147,173 @@ __global__ void __launch_bounds__(256) k_deposit_generic(const float4 *__restric
           if (tgt >= 0) atomicAdd(&acc[tgt], t);
         }
       }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// D4 domain level: shared-memory tile deposit.
+//   The particle array is Hilbert sorted, so the particles of every aligned T^3-cell cube ("tile") are one contiguous
+//   range.  A CTA takes one chunk (<= DT_CHUNK particles) of one tile: the chunk's float4 positions are staged into
+//   shared memory by the TMA (cp.async.bulk, mbarrier completion), the (T+2)^3 tile is accumulated with native u32
+//   shared-memory atomics in 2^-21 fixed point (ATOMS.ADD; float shared atomics would be CAS loops), and flushed as
+//   2^-40 fixed point u64 into the level accumulators: plain stores for the cells no other CTA can touch, REDG.ADD.64
+//   for the rest.  Integer accumulation makes the result independent of any ordering.
+// ------------------------------------------------------------------------------------------------
+constexpr int DT_T       = 16;
+constexpr int DT_H       = DT_T + 2;
+constexpr int DT_HH      = DT_H * DT_H * DT_H;
+constexpr int DT_CHUNK   = 4096;
+constexpr int DT_THREADS = 512;
+constexpr float DT_FX    = 2147483648.0f;         // 2^31 per unit weight; the 32-bit tile word wraps, carries are counted in a second word
+constexpr int DT_SMEM    = DT_CHUNK * 16 + 2 * DT_HH * 4 + 16;
+
+__global__ void k_tile_starts(const uint64_t *__restrict__ keys, int64_t n, int tbits, int ntile, int32_t *__restrict__ tstart)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > ntile) return;
+  if (t == ntile) { tstart[t] = (int32_t)n; return; }
+  const uint64_t kmin = (uint64_t)t << (3 * (21 - tbits));
+  int64_t lo = 0, hi = n;
+  while (lo < hi) { int64_t mid = lo + ((hi - lo) >> 1); if (keys[mid] < kmin) lo = mid + 1; else hi = mid; }
+  tstart[t] = (int32_t)lo;
+}
+__global__ void k_tile_nchunk(const int32_t *__restrict__ tstart, int ntile, int *__restrict__ nchunk)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntile) return;
+  nchunk[t] = (tstart[t + 1] - tstart[t] + DT_CHUNK - 1) / DT_CHUNK;
+}
+__global__ void k_tile_work(const int *__restrict__ nchunk, const int *__restrict__ woff, int ntile, int2 *__restrict__ work)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntile) return;
+  const int nc = nchunk[t], o = woff[t];
+  for (int q = 0; q < nc; q++) work[o + q] = make_int2(t, q | (nc == 1 ? 0x40000000 : 0));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(DT_THREADS, 2)
+k_deposit_tiles(const float4 *__restrict__ pos4, const int32_t *__restrict__ tstart, const int2 *__restrict__ work, int L, int logL, int tbits,
+                unsigned long long *__restrict__ acc)
+{
+  extern __shared__ __align__(16) unsigned char dsm[];
+  float4   *sp   = reinterpret_cast<float4 *>(dsm);
+  uint32_t *tile = reinterpret_cast<uint32_t *>(dsm + DT_CHUNK * 16);          // low 32 bits of the 2^-31 fixed-point sums
+  uint32_t *tcar = tile + DT_HH;                                               // number of wrap-arounds of the low word
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(dsm + DT_CHUNK * 16 + 2 * DT_HH * 4);
+  const int2 wk = work[blockIdx.x];
+  const int  t = wk.x, chunk = wk.y & 0x3fffffff;
+  const bool sole = (wk.y & 0x40000000) != 0;        // the tile's only chunk: its inner cells are touched by nobody else
+  const int  s0 = tstart[t] + chunk * DT_CHUNK;
+  int        np = tstart[t + 1] - s0;
+  if (np > DT_CHUNK) np = DT_CHUNK;
+  uint32_t tx, ty, tz;
+  hilbert_coords((uint64_t)t, (unsigned)tbits, tx, ty, tz);
+  const int x0 = (int)tx * DT_T, y0 = (int)ty * DT_T, z0 = (int)tz * DT_T;
+  const uint32_t bar = smem_u32(mbar), dst = smem_u32(sp);
+  const uint32_t bytes = (uint32_t)np * 16u;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(pos4 + s0), "r"(bytes), "r"(bar) : "memory");
+  }
+  for (int i = threadIdx.x; i < 2 * DT_HH; i += DT_THREADS) tile[i] = 0;  // overlaps the bulk copy
+  {
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                   : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+    }
+  }
+  __syncthreads();
+  const float fL = (float)L;
+  const int   M = L - 1;
+  const int   lane = threadIdx.x & 31;
+  for (int i0 = 0; i0 < np; i0 += DT_THREADS) {
+    const int  i = i0 + threadIdx.x;
+    const bool valid = i < np;
+    const float4 q = valid ? sp[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    // ll(): cell = (unsigned long)(L * pos), out-of-range -> 0 (lltools.c:59-66); exact in float for power-of-two L
+    const float fx = q.x * fL, fy = q.y * fL, fz = q.z * fL;
+    int cx = (int)fx, cy = (int)fy, cz = (int)fz;
+    float sx = fx - ((float)cx + 0.5f), sy = fy - ((float)cy + 0.5f), sz = fz - ((float)cz + 0.5f);
+    if (cx > M) { cx = 0; sx = fx - 0.5f - fL; }
+    if (cy > M) { cy = 0; sy = fy - 0.5f - fL; }
+    if (cz > M) { cz = 0; sz = fz - 0.5f - fL; }
+    float wx[3], wy[3], wz[3];
+    wx[0] = 0.5f * (0.5f - sx) * (0.5f - sx); wx[1] = 0.75f - sx * sx; wx[2] = 0.5f * (0.5f + sx) * (0.5f + sx);
+    wy[0] = 0.5f * (0.5f - sy) * (0.5f - sy); wy[1] = 0.75f - sy * sy; wy[2] = 0.5f * (0.5f + sy) * (0.5f + sy);
+    wz[0] = 0.5f * (0.5f - sz) * (0.5f - sz); wz[1] = 0.75f - sz * sz; wz[2] = 0.5f * (0.5f + sz) * (0.5f + sz);
+    const int lx = cx - x0, ly = cy - y0, lz = cz - z0;         // 0..T-1 inside the tile
+    const bool intile = (unsigned)lx < (unsigned)DT_T && (unsigned)ly < (unsigned)DT_T && (unsigned)lz < (unsigned)DT_T;
+    const int  cid = valid ? (intile ? ((lz * DT_T + ly) * DT_T + lx) : -2) : -1;
+    // clump cores: a whole warp in ONE cell -> sum the 27 terms across the warp (REDUX on two 16-bit limbs) and let
+    // one lane issue the shared-memory atomics instead of 32 lanes serialising on the same address
+    int allsame = 0;
+    __match_all_sync(0xffffffffu, cid, &allsame);
+    if (allsame && cid >= 0) {
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          const float wyz = wz[k] * wy[j] * DT_FX;
+          uint32_t *row = tile + ((lz + k) * DT_H + (ly + j)) * DT_H + lx;
+#pragma unroll
+          for (int a = 0; a < 3; a++) {
+            const uint32_t v = __float2uint_rn(wyz * wx[a]);
+            const uint32_t lo = __reduce_add_sync(0xffffffffu, v & 0xffffu), hi = __reduce_add_sync(0xffffffffu, v >> 16);
+            if (lane == 0) {
+              const unsigned long long tot = ((unsigned long long)hi << 16) + lo;
+              const uint32_t t32 = (uint32_t)tot, old = atomicAdd(row + a, t32);
+              const uint32_t cr = (uint32_t)(tot >> 32) + ((old + t32 < old) ? 1u : 0u);
+              if (cr) atomicAdd(row + a + DT_HH, cr);
+            }
+          }
+        }
+    } else if (valid && intile) {
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          const float wyz = wz[k] * wy[j] * DT_FX;
+          uint32_t *row = tile + ((lz + k) * DT_H + (ly + j)) * DT_H + lx;
+#pragma unroll
+          for (int a = 0; a < 3; a++) {
+            const uint32_t v = __float2uint_rn(wyz * wx[a]);
+            const uint32_t old = atomicAdd(row + a, v);
+            if (old + v < old) atomicAdd(row + a + DT_HH, 1u);                 // carry out of the low word
+          }
+        }
+    } else if (valid) {
+      // the particle's cell is not in this tile (coordinate clamp of ll()): straight to the global accumulators
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+          for (int a = 0; a < 3; a++) {
+            const int x = (cx + a - 1) & M, y = (cy + j - 1) & M, z = (cz + k - 1) & M;
+            atomicAdd(&acc[(((size_t)z << logL | y) << logL) | x], (unsigned long long)__float2uint_rn(wz[k] * wy[j] * DT_FX * wx[a]) << 9);
+          }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < DT_HH; i += DT_THREADS) {
+    const uint32_t v = tile[i], cr = tcar[i];
+    if ((v | cr) == 0) continue;
+    const int hx = i % DT_H, hy = (i / DT_H) % DT_H, hz = i / (DT_H * DT_H);
+    const int x = (x0 + hx - 1) & M, y = (y0 + hy - 1) & M, z = (z0 + hz - 1) & M;
+    unsigned long long *dstp = &acc[(((size_t)z << logL | y) << logL) | x];
+    const unsigned long long val = (((unsigned long long)cr << 32) | v) << 9;   // 2^-31 -> 2^-40
+    const bool inner = hx >= 2 && hx <= DT_T - 1 && hy >= 2 && hy <= DT_T - 1 && hz >= 2 && hz <= DT_T - 1;
+    if (sole && inner) *dstp = val; else atomicAdd(dstp, val);
+  }
 }
 
 __global__ void k_finish_dens(const unsigned long long *__restrict__ acc, float *__restrict__ dens, int ncell, double m2d)
@@ -512,7 +678,7 @@ __global__ void k_nonzero(const uint8_t *in, int n, uint8_t *out)
 template <typename T> static T *dalloc(size_t n)
 {
   T *p = nullptr;
-  CUDA_CHECK(cudaMalloc(&p, (n ? n : 1) * sizeof(T)));
+  CUDA_CHECK(cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), ahf::g_pool_stream));
   return p;
 }
 static inline unsigned nblk(uint64_t n, int b) { return (unsigned)((n + b - 1) / b); }
@@ -541,7 +707,7 @@ static void build_rows_planes(ahfgpu_ctx *c, Level &lv)
   LAUNCH(c, k_row_tested, nblk(lv.nrow, 256), 256, 0, lv.rowkey, lv.plane_r0, rowplane, rq0, rq1, pp0, pp1, (int)lv.nrow, (int)lv.nplane,
          (long long)lv.L, v.logL, lv.row_tested);
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  cudaFree(rq0); cudaFree(rq1); cudaFree(pp0); cudaFree(pp1);
+  ahf::dfree(rq0); ahf::dfree(rq1); ahf::dfree(pp0); ahf::dfree(pp1);
   head.release(); hs.release();
   lv.rowplane = rowplane;
 }
@@ -554,10 +720,31 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
   DevBuf<unsigned long long> acc;
   acc.reserve(nc);
   CUDA_CHECK(cudaMemsetAsync(acc.p, 0, sizeof(unsigned long long) * nc, c->stream));
-  CUDA_CHECK(cudaMemsetAsync(lv.count, 0, sizeof(int32_t) * nc, c->stream));
-  if (lv.npart_dep > 0) {
+  const bool tiles = lv.dense && lv.L >= 2 * DT_T && lv.npart_dep > 0 && !getenv("AHFGPU_GENERIC_DEPOSIT");
+  if (tiles) {
+    // tiles are Hilbert cells of (logL - 4) bits per dimension: contiguous particle ranges
+    const int tbits = v.logL - 4, ntile = 1 << (3 * tbits);
+    DevBuf<int32_t> tstart; DevBuf<int> nchunk, woff, bs, tot; DevBuf<int2> work;
+    tstart.reserve(ntile + 1); nchunk.reserve(ntile); woff.reserve(ntile); tot.reserve(1);
+    LAUNCH(c, k_tile_starts, nblk(ntile + 1, 256), 256, 0, c->keys, (int64_t)c->n, tbits, ntile, tstart.p);
+    LAUNCH(c, k_tile_nchunk, nblk(ntile, 256), 256, 0, tstart.p, ntile, nchunk.p);
+    exclusive_scan_async<int>(c, nchunk.p, woff.p, ntile, tot.p, bs);
+    int W = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&W, tot.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    work.reserve(W);
+    LAUNCH(c, k_tile_work, nblk(ntile, 256), 256, 0, nchunk.p, woff.p, ntile, work.p);
+    static bool attr_set = false;
+    if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(k_deposit_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM)); attr_set = true; }
+    {
+      Stage sk(c, "deposit_dom_kernel", lv.npart_dep);
+      LAUNCH(c, k_deposit_tiles, (unsigned)W, DT_THREADS, DT_SMEM, c->pos4, tstart.p, work.p, (int)lv.L, v.logL, tbits, acc.p);
+    }
+    c->stage_cnt_extra["deposit_dom_ctas"] = W;
+    tstart.release(); nchunk.release(); woff.release(); bs.release(); tot.release(); work.release();
+  } else if (lv.npart_dep > 0) {
     Stage sk(c, lv.dense ? "deposit_dom_kernel" : "deposit_ref_kernel", lv.npart_dep);
-    LAUNCH(c, k_deposit_generic, nblk(lv.npart_dep, 256), 256, 0, c->pos4, lv.plist, lv.pcell, (uint64_t)lv.npart_dep, v, lv.nbr, acc.p, lv.count);
+    LAUNCH(c, k_deposit_generic, nblk(lv.npart_dep, 256), 256, 0, c->pos4, lv.plist, lv.pcell, (uint64_t)lv.npart_dep, v, lv.nbr, acc.p);
   }
   LAUNCH(c, k_finish_dens, nblk(nc, 256), 256, 0, acc.p, lv.dens, nc, lv.masstopartdens);
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -715,6 +902,14 @@ __global__ void k_level_export(LV v, const int32_t *__restrict__ crow, const int
   rf[c] = f;
 }
 
+// particles per node when the level was deposited: computed on demand for the query API
+__global__ void k_count_cells(const int32_t *__restrict__ pcell, uint64_t np, int32_t *__restrict__ count)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const int c = i < np ? pcell[i] : -1;
+  unsigned peers = __match_any_sync(0xffffffffu, c);
+  if (c >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&count[c], __popc(peers));
+}
 __global__ void k_fill_i32(int32_t *a, uint64_t n, int32_t v)
 {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -736,7 +931,7 @@ extern "C" int ahfgpu_amr_level_get(ahfgpu_ctx *c, int32_t lev, int32_t *x, int3
 {
   try {
     if (!c || lev < 0 || lev >= (int)c->levels.size()) AHF_FAIL("bad level");
-    CUDA_CHECK(cudaSetDevice(c->dev));
+    CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
     Level &l = c->levels[lev];
     const size_t nc = (size_t)l.ncell;
     if (x || y || z || runflags) {
@@ -757,7 +952,12 @@ extern "C" int ahfgpu_amr_level_get(ahfgpu_ctx *c, int32_t lev, int32_t *x, int3
       else CUDA_CHECK(cudaMemcpy(interior, l.interior, nc, cudaMemcpyDeviceToHost));
     }
     if (mark) CUDA_CHECK(cudaMemcpy(mark, l.mark, nc, cudaMemcpyDeviceToHost));
-    if (count) CUDA_CHECK(cudaMemcpy(count, l.count, nc * 4, cudaMemcpyDeviceToHost));
+    if (count) {
+      CUDA_CHECK(cudaMemsetAsync(l.count, 0, nc * 4, c->stream));
+      if (l.npart_dep) LAUNCH(c, k_count_cells, nblk(l.npart_dep, 256), 256, 0, l.pcell, (uint64_t)l.npart_dep, l.count);
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      CUDA_CHECK(cudaMemcpy(count, l.count, nc * 4, cudaMemcpyDeviceToHost));
+    }
     return 0;
   } catch (const ahf::Error &e) { ahf::g_last_error = e.msg; return -1; }
 }
@@ -766,7 +966,7 @@ extern "C" int ahfgpu_amr_particle_levels(ahfgpu_ctx *c, int8_t *owner_level, in
 {
   try {
     if (!c || !c->owner_level) AHF_FAIL("no hierarchy");
-    CUDA_CHECK(cudaSetDevice(c->dev));
+    CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
     const uint64_t n = c->n;
     if (owner_level) CUDA_CHECK(cudaMemcpy(owner_level, c->owner_level, n, cudaMemcpyDeviceToHost));
     if (cell_of) {

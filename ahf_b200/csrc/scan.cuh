@@ -52,8 +52,8 @@ __global__ void __launch_bounds__(SC_THREADS) k_sc_reduce(const T *__restrict__ 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(SC_THREADS) k_sc_down(const T *__restrict__ in, uint64_t n, const int *__restrict__ boff,
-                                                        int *__restrict__ out)
+__global__ void __launch_bounds__(SC_THREADS) k_sc_down(const T *in, uint64_t n, const int *__restrict__ boff,
+                                                        int *out)
 {
   uint64_t base = (uint64_t)blockIdx.x * SC_TILE + (uint64_t)threadIdx.x * SC_ITEMS;
   int v[SC_ITEMS], s = 0;
@@ -92,16 +92,24 @@ static __global__ void __launch_bounds__(1024) k_sc_small(int *__restrict__ a, u
   for (uint64_t i = b; i < e; i++) { int x = a[i]; a[i] = run; run += x; }
 }
 
+// out[i] = sum_{j<i} in[j]; no host synchronisation; d_total (device, may be null) receives the sum
+template <typename T> void exclusive_scan_async(ahfgpu_ctx *c, const T *in, int *out, uint64_t n, int *d_total, DevBuf<int> &bs)
+{
+  if (n == 0) return;
+  const unsigned nblk = (unsigned)((n + SC_TILE - 1) / SC_TILE);
+  bs.reserve(nblk);
+  LAUNCH(c, (k_sc_reduce<T>), nblk, SC_THREADS, 0, in, n, bs.p);
+  LAUNCH(c, k_sc_small, 1, 1024, 0, bs.p, (uint64_t)nblk, d_total);
+  LAUNCH(c, (k_sc_down<T>), nblk, SC_THREADS, 0, in, n, bs.p, out);
+}
+
 // out[i] = sum_{j<i} in[j]; returns the total (synchronises the stream)
 template <typename T> int exclusive_scan(ahfgpu_ctx *c, const T *in, int *out, uint64_t n)
 {
   if (n == 0) return 0;
-  const unsigned nblk = (unsigned)((n + SC_TILE - 1) / SC_TILE);
   DevBuf<int> bs, tot;
-  bs.reserve(nblk); tot.reserve(1);
-  LAUNCH(c, (k_sc_reduce<T>), nblk, SC_THREADS, 0, in, n, bs.p);
-  LAUNCH(c, k_sc_small, 1, 1024, 0, bs.p, (uint64_t)nblk, tot.p);
-  LAUNCH(c, (k_sc_down<T>), nblk, SC_THREADS, 0, in, n, bs.p, out);
+  tot.reserve(1);
+  exclusive_scan_async<T>(c, in, out, n, tot.p, bs);
   int h = 0;
   CUDA_CHECK(cudaMemcpyAsync(&h, tot.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK(cudaStreamSynchronize(c->stream));

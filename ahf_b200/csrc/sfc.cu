@@ -5,6 +5,7 @@
 // hilbert.c:197-243).  HBM-bound integer work: no tensor cores.
 #include "common.cuh"
 #include "hilbert.cuh"
+#include "scan.cuh"
 
 namespace ahf {
 
@@ -148,18 +149,19 @@ void radix_sort_pairs(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t *k
   if (n == 0) return;
   const uint32_t nblk = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
   DevBuf<uint32_t> bh;
+  DevBuf<int>      bs;
   bh.reserve((size_t)256 * nblk);
   uint64_t *ki = keys, *ko = keys_tmp;
   uint32_t *vi = vals, *vo = vals_tmp;
   for (int shift = 0; shift < key_bits; shift += 8) {
     LAUNCH(c, k_rs_hist, nblk, RS_THREADS, 0, ki, n, shift, bh.p, nblk);
-    LAUNCH(c, k_scan_u32, 1, 1024, 0, bh.p, (uint64_t)256 * nblk);
+    exclusive_scan_async<int>(c, (const int *)bh.p, (int *)bh.p, (uint64_t)256 * nblk, nullptr, bs);   // in place: each tile is read before it is written
     LAUNCH(c, k_rs_scatter, nblk, RS_THREADS, 0, ki, vi, ko, vo, n, shift, bh.p, nblk);
     uint64_t *tk = ki; ki = ko; ko = tk;
     uint32_t *tv = vi; vi = vo; vo = tv;
   }
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  bh.release();
+  bh.release(); bs.release();
   *keys_sorted = ki; *vals_sorted = vi;
 }
 
@@ -205,8 +207,8 @@ static void alloc_particles(ahfgpu_ctx *c, uint64_t n)
   c->free_levels();
   c->free_halos();
   c->n = n;
-  CUDA_CHECK(cudaMalloc(&c->pos4, (n ? n : 1) * sizeof(float4)));
-  CUDA_CHECK(cudaMalloc(&c->mom4, (n ? n : 1) * sizeof(float4)));
+  CUDA_CHECK(cudaMallocAsync(&c->pos4, (n ? n : 1) * sizeof(float4), ahf::g_pool_stream));
+  CUDA_CHECK(cudaMallocAsync(&c->mom4, (n ? n : 1) * sizeof(float4), ahf::g_pool_stream));
 }
 
 void sfc_keys_only(ahfgpu_ctx *c, const float *pos3, uint64_t n, uint32_t bits, uint64_t *keys_out)
@@ -224,12 +226,12 @@ void sfc_keys_only(ahfgpu_ctx *c, const float *pos3, uint64_t n, uint32_t bits, 
 void sfc_upload_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, const float *w, const float *u, uint64_t n)
 {
   if (n >= (1ull << 32)) AHF_FAIL("more than 2^32-1 particles per device are not supported");
-  cudaFree(c->in_pos); cudaFree(c->in_mom); cudaFree(c->in_w); cudaFree(c->in_u);
+  ahf::dfree(c->in_pos); ahf::dfree(c->in_mom); ahf::dfree(c->in_w); ahf::dfree(c->in_u);
   c->in_pos = c->in_mom = c->in_w = c->in_u = nullptr; c->in_n = n;
-  CUDA_CHECK(cudaMalloc(&c->in_pos, (n ? n : 1) * 3 * sizeof(float)));
-  CUDA_CHECK(cudaMalloc(&c->in_mom, (n ? n : 1) * 3 * sizeof(float)));
-  if (w) CUDA_CHECK(cudaMalloc(&c->in_w, (n ? n : 1) * sizeof(float)));
-  if (u) CUDA_CHECK(cudaMalloc(&c->in_u, (n ? n : 1) * sizeof(float)));
+  CUDA_CHECK(cudaMallocAsync(&c->in_pos, (n ? n : 1) * 3 * sizeof(float), ahf::g_pool_stream));
+  CUDA_CHECK(cudaMallocAsync(&c->in_mom, (n ? n : 1) * 3 * sizeof(float), ahf::g_pool_stream));
+  if (w) CUDA_CHECK(cudaMallocAsync(&c->in_w, (n ? n : 1) * sizeof(float), ahf::g_pool_stream));
+  if (u) CUDA_CHECK(cudaMallocAsync(&c->in_u, (n ? n : 1) * sizeof(float), ahf::g_pool_stream));
   Stage st(c, "h2d", (int64_t)(24 * n + (w ? 4 * n : 0) + (u ? 4 * n : 0)));
   CUDA_CHECK(cudaMemcpyAsync(c->in_pos, pos3, 3 * n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   CUDA_CHECK(cudaMemcpyAsync(c->in_mom, mom3, 3 * n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
@@ -261,8 +263,8 @@ void sfc_sort_resident(ahfgpu_ctx *c, uint64_t *keys_out, uint32_t *order_out)
     Stage st(c, "gather", (int64_t)n);
     if (n) LAUNCH(c, k_gather_soa, nb, 256, 0, c->in_pos, c->in_mom, c->in_w, c->in_u, vs, n, c->pos4, c->mom4);
   }
-  CUDA_CHECK(cudaMalloc(&c->keys, (n ? n : 1) * sizeof(uint64_t)));
-  CUDA_CHECK(cudaMalloc(&c->order, (n ? n : 1) * sizeof(uint32_t)));
+  CUDA_CHECK(cudaMallocAsync(&c->keys, (n ? n : 1) * sizeof(uint64_t), ahf::g_pool_stream));
+  CUDA_CHECK(cudaMallocAsync(&c->order, (n ? n : 1) * sizeof(uint32_t), ahf::g_pool_stream));
   CUDA_CHECK(cudaMemcpyAsync(c->keys, ks, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
   CUDA_CHECK(cudaMemcpyAsync(c->order, vs, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
   if (keys_out || order_out) {
@@ -311,8 +313,8 @@ void sfc_sort_aos(ahfgpu_ctx *c, void *part, uint64_t n, uint32_t stride, int of
     Stage st(c, "gather", (int64_t)n);
     if (n) LAUNCH(c, k_gather_aos, nb, 256, 0, in.p, out.p, vs, ks, n, stride, off_pos, off_mom, off_key, off_w, off_u, c->pos4, c->mom4);
   }
-  CUDA_CHECK(cudaMalloc(&c->keys, (n ? n : 1) * sizeof(uint64_t)));
-  CUDA_CHECK(cudaMalloc(&c->order, (n ? n : 1) * sizeof(uint32_t)));
+  CUDA_CHECK(cudaMallocAsync(&c->keys, (n ? n : 1) * sizeof(uint64_t), ahf::g_pool_stream));
+  CUDA_CHECK(cudaMallocAsync(&c->order, (n ? n : 1) * sizeof(uint32_t), ahf::g_pool_stream));
   CUDA_CHECK(cudaMemcpyAsync(c->keys, ks, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
   CUDA_CHECK(cudaMemcpyAsync(c->order, vs, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
   {
