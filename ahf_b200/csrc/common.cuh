@@ -83,6 +83,7 @@ struct Level {
   // particles that reached this level (ascending sorted offsets) and their cell on this level
   uint32_t *plist = nullptr;    // [npart_dep]   (nullptr on the domain level = all particles)
   int32_t  *pcell = nullptr;    // [npart_dep]
+  float4   *lpos = nullptr;     // [npart_dep] positions of the level's particles, contiguous (refinement levels)
   void free_all();
 };
 

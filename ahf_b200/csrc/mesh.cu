@@ -14,8 +14,9 @@ namespace ahf {
 
 constexpr int    MIN_NNODES = 125;     // src/param.h:54
 constexpr double CRITMULTI  = 8.0;     // src/param.h:118
-constexpr int    FX_SHIFT   = 40;      // global accumulators: u64 fixed point, 2^-40 per unit weight
-constexpr double FX_SCALE   = 1099511627776.0;   // 2^40
+// Deposit accumulators are u64 fixed point with a per-level scale 2^S: S = min(31 + ceil(log2(masstopartdens)), 44), so that the
+// quantum seen by `dens` (masstopartdens * 2^-S) stays ~2^-31 on every level while a cell can still hold 2^20 particles.
+static int fx_shift_for(double m2d) { int e = 0; while ((double)(1ull << e) < m2d && e < 40) e++; int S = 31 + e; return S > 44 ? 44 : S; }
 
 // ------------------------------------------------------------------------------------------------
 // device view of a level
@@ -84,8 +85,7 @@ __global__ void k_domain_cells(const float4 *__restrict__ pos4, uint64_t n, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// D4 generic deposit: one thread per particle, 27 u64 fixed-point global reductions, warp-aggregated when
-// several lanes of a warp sit in the same cell (sorted particles => clump cores collapse to one leader)
+// D4 generic deposit (small levels): one thread per particle, 27 u64 fixed-point global reductions
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tsc_weights(double s, double w[3])
 {
@@ -103,11 +103,10 @@ __device__ __forceinline__ double sep_cell(float pos, int i, double L)
 
 __global__ void __launch_bounds__(256) k_deposit_generic(const float4 *__restrict__ pos4, const uint32_t *__restrict__ plist,
                                                          const int32_t *__restrict__ pcell, uint64_t np, LV v,
-                                                         const int32_t *__restrict__ nbr, unsigned long long *__restrict__ acc)
+                                                         const int32_t *__restrict__ nbr, unsigned long long *__restrict__ acc, double fxscale)
 {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const bool valid = i < np;
-  const int  lane = threadIdx.x & 31;
   int    c = -1;
   double wx[3], wy[3], wz[3];
   int    cx = 0, cy = 0, cz = 0;
@@ -121,34 +120,22 @@ __global__ void __launch_bounds__(256) k_deposit_generic(const float4 *__restric
     tsc_weights(sep_cell(q.y, cy, L), wy);
     tsc_weights(sep_cell(q.z, cz, L), wz);
   }
-  // lanes sharing a cell elect a leader; REDUX over the peer set sums their 27 fixed-point terms (two 20-bit limbs)
-  unsigned peers  = __match_any_sync(0xffffffffu, c);
-  int      leader = __ffs(peers) - 1;
-  const bool any_agg = __any_sync(0xffffffffu, valid && (__popc(peers) > 1));
+  if (!valid) return;
 #pragma unroll
   for (int k = 0; k < 3; k++)
 #pragma unroll
     for (int j = 0; j < 3; j++)
 #pragma unroll
       for (int a = 0; a < 3; a++) {
-        unsigned long long t = valid ? (unsigned long long)(wz[k] * wy[j] * wx[a] * FX_SCALE + 0.5) : 0ull;
-        if (any_agg) {
-          unsigned lo = (unsigned)(t & 0xfffffull), hi = (unsigned)(t >> 20);
-          lo = __reduce_add_sync(peers, lo);
-          hi = __reduce_add_sync(peers, hi);
-          t  = ((unsigned long long)hi << 20) + lo;
-        }
-        if (valid && lane == leader) {
-          int tgt;
-          if (v.dense) {
-            int x = (cx + a - 1) & (int)(v.L - 1), y = (cy + j - 1) & (int)(v.L - 1), z = (cz + k - 1) & (int)(v.L - 1);
-            tgt = (int)lv_key(v, x, y, z);
-          } else tgt = nbr[(size_t)c * 27 + (k * 9 + j * 3 + a)];
-          if (tgt >= 0) atomicAdd(&acc[tgt], t);
-        }
+        const unsigned long long t = (unsigned long long)(wz[k] * wy[j] * wx[a] * fxscale + 0.5);
+        int tgt;
+        if (v.dense) {
+          int x = (cx + a - 1) & (int)(v.L - 1), y = (cy + j - 1) & (int)(v.L - 1), z = (cz + k - 1) & (int)(v.L - 1);
+          tgt = (int)lv_key(v, x, y, z);
+        } else tgt = nbr[(size_t)c * 27 + (k * 9 + j * 3 + a)];
+        if (tgt >= 0) atomicAdd(&acc[tgt], t);
       }
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // D4 domain level: shared-memory tile deposit.
@@ -164,7 +151,6 @@ constexpr int DT_H       = DT_T + 2;
 constexpr int DT_HH      = DT_H * DT_H * DT_H;
 constexpr int DT_CHUNK   = 4096;
 constexpr int DT_THREADS = 512;
-constexpr float DT_FX    = 2147483648.0f;         // 2^31 per unit weight; the 32-bit tile word wraps, carries are counted in a second word
 constexpr int DT_SMEM    = DT_CHUNK * 16 + 2 * DT_HH * 4 + 16;
 
 __global__ void k_tile_starts(const uint64_t *__restrict__ keys, int64_t n, int tbits, int ntile, int32_t *__restrict__ tstart)
@@ -191,11 +177,29 @@ __global__ void k_tile_work(const int *__restrict__ nchunk, const int *__restric
   for (int q = 0; q < nc; q++) work[o + q] = make_int2(t, q | (nc == 1 ? 0x40000000 : 0));
 }
 
+// refinement levels: tile id (Hilbert prefix of the particle key) of every level particle, heads of equal-id runs
+__global__ void k_lvl_tile_heads(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ plist, uint64_t np, int sh, uint8_t *__restrict__ head)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= np) return;
+  head[i] = (i == 0 || (keys[plist[i]] >> sh) != (keys[plist[i - 1]] >> sh)) ? 1 : 0;
+}
+__global__ void k_lvl_tile_fill(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ plist, uint64_t np, int sh, const uint8_t *__restrict__ head,
+                                const int *__restrict__ hs, int ntile, uint32_t *__restrict__ tlist, int32_t *__restrict__ tstart)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= np) return;
+  if (head[i]) { tlist[hs[i]] = (uint32_t)(keys[plist[i]] >> sh); tstart[hs[i]] = (int32_t)i; }
+  if (i == np - 1) tstart[ntile] = (int32_t)np;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+template <bool SPARSE>
 __global__ void __launch_bounds__(DT_THREADS, 2)
 k_deposit_tiles(const float4 *__restrict__ pos4, const int32_t *__restrict__ tstart, const int2 *__restrict__ work, int L, int logL, int tbits,
-                unsigned long long *__restrict__ acc)
+                unsigned long long *__restrict__ acc, const uint32_t *__restrict__ tlist, const int32_t *__restrict__ pcell, LV lvw,
+                const int32_t *__restrict__ nbr, float fxs)
 {
   extern __shared__ __align__(16) unsigned char dsm[];
   float4   *sp   = reinterpret_cast<float4 *>(dsm);
@@ -209,7 +213,7 @@ k_deposit_tiles(const float4 *__restrict__ pos4, const int32_t *__restrict__ tst
   int        np = tstart[t + 1] - s0;
   if (np > DT_CHUNK) np = DT_CHUNK;
   uint32_t tx, ty, tz;
-  hilbert_coords((uint64_t)t, (unsigned)tbits, tx, ty, tz);
+  hilbert_coords(SPARSE ? (uint64_t)tlist[t] : (uint64_t)t, (unsigned)tbits, tx, ty, tz);
   const int x0 = (int)tx * DT_T, y0 = (int)ty * DT_T, z0 = (int)tz * DT_T;
   const uint32_t bar = smem_u32(mbar), dst = smem_u32(sp);
   const uint32_t bytes = (uint32_t)np * 16u;
@@ -241,11 +245,17 @@ k_deposit_tiles(const float4 *__restrict__ pos4, const int32_t *__restrict__ tst
     const float4 q = valid ? sp[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     // ll(): cell = (unsigned long)(L * pos), out-of-range -> 0 (lltools.c:59-66); exact in float for power-of-two L
     const float fx = q.x * fL, fy = q.y * fL, fz = q.z * fL;
-    int cx = (int)fx, cy = (int)fy, cz = (int)fz;
+    int cx, cy, cz, pc = 0;
+    if (SPARSE) {          // the node the particle is linked to (relink's inclusive faces: not always floor(L*x))
+      pc = valid ? pcell[s0 + i] : 0;
+      lv_coords(lvw, pc, cx, cy, cz);
+    } else { cx = (int)fx; cy = (int)fy; cz = (int)fz; }
     float sx = fx - ((float)cx + 0.5f), sy = fy - ((float)cy + 0.5f), sz = fz - ((float)cz + 0.5f);
-    if (cx > M) { cx = 0; sx = fx - 0.5f - fL; }
-    if (cy > M) { cy = 0; sy = fy - 0.5f - fL; }
-    if (cz > M) { cz = 0; sz = fz - 0.5f - fL; }
+    if (!SPARSE) {
+      if (cx > M) { cx = 0; sx = fx - 0.5f - fL; }
+      if (cy > M) { cy = 0; sy = fy - 0.5f - fL; }
+      if (cz > M) { cz = 0; sz = fz - 0.5f - fL; }
+    }
     float wx[3], wy[3], wz[3];
     wx[0] = 0.5f * (0.5f - sx) * (0.5f - sx); wx[1] = 0.75f - sx * sx; wx[2] = 0.5f * (0.5f + sx) * (0.5f + sx);
     wy[0] = 0.5f * (0.5f - sy) * (0.5f - sy); wy[1] = 0.75f - sy * sy; wy[2] = 0.5f * (0.5f + sy) * (0.5f + sy);
@@ -255,21 +265,22 @@ k_deposit_tiles(const float4 *__restrict__ pos4, const int32_t *__restrict__ tst
     const int  cid = valid ? (intile ? ((lz * DT_T + ly) * DT_T + lx) : -2) : -1;
     // clump cores: a whole warp in ONE cell -> sum the 27 terms across the warp (REDUX on two 16-bit limbs) and let
     // one lane issue the shared-memory atomics instead of 32 lanes serialising on the same address
-    int allsame = 0;
-    __match_all_sync(0xffffffffu, cid, &allsame);
+    const int  cid0 = __shfl_sync(0xffffffffu, cid, 0);
+    const bool allsame = __all_sync(0xffffffffu, cid == cid0);
     if (allsame && cid >= 0) {
 #pragma unroll
       for (int k = 0; k < 3; k++)
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-          const float wyz = wz[k] * wy[j] * DT_FX;
+          const float wyz = wz[k] * wy[j] * fxs;
           uint32_t *row = tile + ((lz + k) * DT_H + (ly + j)) * DT_H + lx;
 #pragma unroll
           for (int a = 0; a < 3; a++) {
-            const uint32_t v = __float2uint_rn(wyz * wx[a]);
-            const uint32_t lo = __reduce_add_sync(0xffffffffu, v & 0xffffu), hi = __reduce_add_sync(0xffffffffu, v >> 16);
+            const unsigned long long v = __float2ull_rn(wyz * wx[a]);          // < 2^43
+            const uint32_t l0 = __reduce_add_sync(0xffffffffu, (uint32_t)(v & 0xffffu)), l1 = __reduce_add_sync(0xffffffffu, (uint32_t)((v >> 16) & 0xffffu)),
+                           l2 = __reduce_add_sync(0xffffffffu, (uint32_t)(v >> 32));
             if (lane == 0) {
-              const unsigned long long tot = ((unsigned long long)hi << 16) + lo;
+              const unsigned long long tot = (unsigned long long)l0 + ((unsigned long long)l1 << 16) + ((unsigned long long)l2 << 32);
               const uint32_t t32 = (uint32_t)tot, old = atomicAdd(row + a, t32);
               const uint32_t cr = (uint32_t)(tot >> 32) + ((old + t32 < old) ? 1u : 0u);
               if (cr) atomicAdd(row + a + DT_HH, cr);
@@ -281,13 +292,25 @@ k_deposit_tiles(const float4 *__restrict__ pos4, const int32_t *__restrict__ tst
       for (int k = 0; k < 3; k++)
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-          const float wyz = wz[k] * wy[j] * DT_FX;
+          const float wyz = wz[k] * wy[j] * fxs;
           uint32_t *row = tile + ((lz + k) * DT_H + (ly + j)) * DT_H + lx;
+          if (fxs <= 4294967296.0f) {          // S <= 32 (domain and first level): every term fits the low word
+            const uint32_t v0 = __float2uint_rn(wyz * wx[0]), v1 = __float2uint_rn(wyz * wx[1]), v2 = __float2uint_rn(wyz * wx[2]);
+            const uint32_t o0 = atomicAdd(row, v0), o1 = atomicAdd(row + 1, v1), o2 = atomicAdd(row + 2, v2);
+            const bool c0 = o0 + v0 < o0, c1 = o1 + v1 < o1, c2 = o2 + v2 < o2;   // carries out of the low words (rare)
+            if (c0 | c1 | c2) {
+              if (c0) atomicAdd(row + DT_HH, 1u);
+              if (c1) atomicAdd(row + 1 + DT_HH, 1u);
+              if (c2) atomicAdd(row + 2 + DT_HH, 1u);
+            }
+          } else {
 #pragma unroll
-          for (int a = 0; a < 3; a++) {
-            const uint32_t v = __float2uint_rn(wyz * wx[a]);
-            const uint32_t old = atomicAdd(row + a, v);
-            if (old + v < old) atomicAdd(row + a + DT_HH, 1u);                 // carry out of the low word
+            for (int a = 0; a < 3; a++) {
+              const unsigned long long v = __float2ull_rn(wyz * wx[a]);
+              const uint32_t lo = (uint32_t)v, old = atomicAdd(row + a, lo);
+              const uint32_t hi = (uint32_t)(v >> 32) + ((old + lo < old) ? 1u : 0u);
+              if (hi) atomicAdd(row + a + DT_HH, hi);
+            }
           }
         }
     } else if (valid) {
@@ -298,8 +321,10 @@ k_deposit_tiles(const float4 *__restrict__ pos4, const int32_t *__restrict__ tst
         for (int j = 0; j < 3; j++)
 #pragma unroll
           for (int a = 0; a < 3; a++) {
-            const int x = (cx + a - 1) & M, y = (cy + j - 1) & M, z = (cz + k - 1) & M;
-            atomicAdd(&acc[(((size_t)z << logL | y) << logL) | x], (unsigned long long)__float2uint_rn(wz[k] * wy[j] * DT_FX * wx[a]) << 9);
+            long long tgt;
+            if (SPARSE) tgt = nbr[(size_t)pc * 27 + (k * 9 + j * 3 + a)];
+            else { const int x = (cx + a - 1) & M, y = (cy + j - 1) & M, z = (cz + k - 1) & M; tgt = (long long)((((size_t)z << logL | y) << logL) | x); }
+            if (tgt >= 0) atomicAdd(&acc[tgt], __float2ull_rn(wz[k] * wy[j] * fxs * wx[a]));
           }
     }
   }
@@ -309,18 +334,23 @@ k_deposit_tiles(const float4 *__restrict__ pos4, const int32_t *__restrict__ tst
     if ((v | cr) == 0) continue;
     const int hx = i % DT_H, hy = (i / DT_H) % DT_H, hz = i / (DT_H * DT_H);
     const int x = (x0 + hx - 1) & M, y = (y0 + hy - 1) & M, z = (z0 + hz - 1) & M;
-    unsigned long long *dstp = &acc[(((size_t)z << logL | y) << logL) | x];
-    const unsigned long long val = (((unsigned long long)cr << 32) | v) << 9;   // 2^-31 -> 2^-40
-    const bool inner = hx >= 2 && hx <= DT_T - 1 && hy >= 2 && hy <= DT_T - 1 && hz >= 2 && hz <= DT_T - 1;
-    if (sole && inner) *dstp = val; else atomicAdd(dstp, val);
+    const unsigned long long val = ((unsigned long long)cr << 32) | v;          // already in the level's 2^-S units
+    if (SPARSE) {
+      const int tgt = lv_lookup(lvw, x, y, z);         // particles sit on interior nodes: every touched cell exists
+      if (tgt >= 0) atomicAdd(&acc[tgt], val);
+    } else {
+      unsigned long long *dstp = &acc[(((size_t)z << logL | y) << logL) | x];
+      const bool inner = hx >= 2 && hx <= DT_T - 1 && hy >= 2 && hy <= DT_T - 1 && hz >= 2 && hz <= DT_T - 1;
+      if (sole && inner) *dstp = val; else atomicAdd(dstp, val);
+    }
   }
 }
 
-__global__ void k_finish_dens(const unsigned long long *__restrict__ acc, float *__restrict__ dens, int ncell, double m2d)
+__global__ void k_finish_dens(const unsigned long long *__restrict__ acc, float *__restrict__ dens, int ncell, double m2d_over_scale)
 {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncell) return;
-  dens[c] = (float)(m2d * ((double)acc[c] * (1.0 / FX_SCALE)) - 1.0);      // zero_dens: -mean_dens, density.c:480
+  dens[c] = (float)(m2d_over_scale * (double)acc[c] - 1.0);      // zero_dens: -mean_dens, density.c:480
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -408,21 +438,20 @@ __global__ void k_row_runs(const uint64_t *__restrict__ rowkey, const int32_t *_
   }
 }
 
-// single thread: z-run (pquad) bounds of every plane as plane indices [p0,p1)
-__global__ void k_plane_runs(const uint64_t *__restrict__ rowkey, const int32_t *__restrict__ plane_r0, int nplane, int logL,
-                             int32_t *__restrict__ pp0, int32_t *__restrict__ pp1)
+// z-run (pquad) bounds of every plane as plane indices [p0,p1): one thread per plane walks to the ends of its run
+__global__ void k_plane_z(const uint64_t *__restrict__ rowkey, const int32_t *__restrict__ plane_r0, int nplane, int logL, int32_t *__restrict__ pz)
 {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  int start = 0;
-  for (int P = 0; P < nplane; P++) {
-    if (P > 0 && (rowkey[plane_r0[P]] >> logL) != (rowkey[plane_r0[P - 1]] >> logL) + 1) start = P;
-    pp0[P] = start;
-  }
-  int end = nplane;
-  for (int P = nplane - 1; P >= 0; P--) {
-    if (P < nplane - 1 && (rowkey[plane_r0[P + 1]] >> logL) != (rowkey[plane_r0[P]] >> logL) + 1) end = P + 1;
-    pp1[P] = end;
-  }
+  int P = blockIdx.x * blockDim.x + threadIdx.x;
+  if (P < nplane) pz[P] = (int32_t)(rowkey[plane_r0[P]] >> logL);
+}
+__global__ void k_plane_runs(const int32_t *__restrict__ pz, int nplane, int32_t *__restrict__ pp0, int32_t *__restrict__ pp1)
+{
+  int P = blockIdx.x * blockDim.x + threadIdx.x;
+  if (P >= nplane) return;
+  int a = P, b = P + 1;
+  while (a > 0 && pz[a - 1] + 1 == pz[a]) a--;
+  while (b < nplane && pz[b] == pz[b - 1] + 1) b++;
+  pp0[P] = a; pp1[P] = b;
 }
 
 __global__ void k_row_tested(const uint64_t *__restrict__ rowkey, const int32_t *__restrict__ plane_r0, const int32_t *__restrict__ rowplane,
@@ -648,12 +677,13 @@ __global__ void k_relink(const float4 *__restrict__ pos4, const uint32_t *__rest
 
 __global__ void k_compact_moved(const uint32_t *__restrict__ plist, const int32_t *__restrict__ newcell, const uint8_t *__restrict__ moved,
                                 const int *__restrict__ S, uint64_t np, uint32_t *__restrict__ plist_out, int32_t *__restrict__ pcell_out,
-                                int8_t *__restrict__ owner, int8_t newlevel)
+                                int8_t *__restrict__ owner, int8_t newlevel, const float4 *__restrict__ pos4, float4 *__restrict__ lpos_out)
 {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= np || !moved[i]) return;
   uint32_t p = plist ? plist[i] : (uint32_t)i;
   plist_out[S[i]] = p; pcell_out[S[i]] = newcell[i];
+  lpos_out[S[i]] = pos4[p];                 // level-local contiguous copy: TMA-stageable, no index indirection in the deposit
   owner[p] = newlevel;
 }
 
@@ -702,12 +732,14 @@ static void build_rows_planes(ahfgpu_ctx *c, Level &lv)
   // run bounds + tested rows
   int32_t *rq0 = dalloc<int32_t>(lv.nrow), *rq1 = dalloc<int32_t>(lv.nrow), *pp0 = dalloc<int32_t>(lv.nplane), *pp1 = dalloc<int32_t>(lv.nplane);
   LAUNCH(c, k_row_runs, nblk(lv.nplane, 128), 128, 0, lv.rowkey, lv.plane_r0, (int)lv.nplane, rq0, rq1);
-  LAUNCH(c, k_plane_runs, 1, 32, 0, lv.rowkey, lv.plane_r0, (int)lv.nplane, v.logL, pp0, pp1);
+  int32_t *pz = dalloc<int32_t>(lv.nplane);
+  LAUNCH(c, k_plane_z, nblk(lv.nplane, 128), 128, 0, lv.rowkey, lv.plane_r0, (int)lv.nplane, v.logL, pz);
+  LAUNCH(c, k_plane_runs, nblk(lv.nplane, 128), 128, 0, pz, (int)lv.nplane, pp0, pp1);
   lv.row_tested = dalloc<uint8_t>(lv.nrow);
   LAUNCH(c, k_row_tested, nblk(lv.nrow, 256), 256, 0, lv.rowkey, lv.plane_r0, rowplane, rq0, rq1, pp0, pp1, (int)lv.nrow, (int)lv.nplane,
          (long long)lv.L, v.logL, lv.row_tested);
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  ahf::dfree(rq0); ahf::dfree(rq1); ahf::dfree(pp0); ahf::dfree(pp1);
+  ahf::dfree(rq0); ahf::dfree(rq1); ahf::dfree(pp0); ahf::dfree(pp1); ahf::dfree(pz);
   head.release(); hs.release();
   lv.rowplane = rowplane;
 }
@@ -720,13 +752,37 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
   DevBuf<unsigned long long> acc;
   acc.reserve(nc);
   CUDA_CHECK(cudaMemsetAsync(acc.p, 0, sizeof(unsigned long long) * nc, c->stream));
-  const bool tiles = lv.dense && lv.L >= 2 * DT_T && lv.npart_dep > 0 && !getenv("AHFGPU_GENERIC_DEPOSIT");
-  if (tiles) {
-    // tiles are Hilbert cells of (logL - 4) bits per dimension: contiguous particle ranges
-    const int tbits = v.logL - 4, ntile = 1 << (3 * tbits);
-    DevBuf<int32_t> tstart; DevBuf<int> nchunk, woff, bs, tot; DevBuf<int2> work;
-    tstart.reserve(ntile + 1); nchunk.reserve(ntile); woff.reserve(ntile); tot.reserve(1);
-    LAUNCH(c, k_tile_starts, nblk(ntile + 1, 256), 256, 0, c->keys, (int64_t)c->n, tbits, ntile, tstart.p);
+  const int    S = fx_shift_for(lv.masstopartdens);
+  const double fxscale = (double)(1ull << S);
+  const bool generic_only = getenv("AHFGPU_GENERIC_DEPOSIT") != nullptr;
+  const bool tiles_dense  = lv.dense && lv.L >= 2 * DT_T && lv.npart_dep > 0 && !generic_only;
+  const bool tiles_sparse = !lv.dense && lv.lpos && lv.npart_dep >= 2048 && v.logL - 4 <= 20 && !generic_only;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(k_deposit_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_deposit_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
+    attr_set = true;
+  }
+  if (tiles_dense || tiles_sparse) {
+    // tiles are Hilbert cells of (logL - 4) bits per dimension: contiguous ranges of the (level's) particle list
+    const int tbits = v.logL - 4;
+    int ntile = 0;
+    DevBuf<int32_t> tstart; DevBuf<int> nchunk, woff, bs, tot, hs; DevBuf<int2> work; DevBuf<uint32_t> tlist; DevBuf<uint8_t> head;
+    tot.reserve(1);
+    if (tiles_dense) {
+      ntile = 1 << (3 * tbits);
+      tstart.reserve(ntile + 1);
+      LAUNCH(c, k_tile_starts, nblk(ntile + 1, 256), 256, 0, c->keys, (int64_t)c->n, tbits, ntile, tstart.p);
+    } else {
+      const uint64_t np = (uint64_t)lv.npart_dep;
+      const int sh = 3 * (21 - tbits);
+      head.reserve(np); hs.reserve(np);
+      LAUNCH(c, k_lvl_tile_heads, nblk(np, 256), 256, 0, c->keys, lv.plist, np, sh, head.p);
+      ntile = exclusive_scan<uint8_t>(c, head.p, hs.p, np);
+      tlist.reserve(ntile); tstart.reserve(ntile + 1);
+      LAUNCH(c, k_lvl_tile_fill, nblk(np, 256), 256, 0, c->keys, lv.plist, np, sh, head.p, hs.p, ntile, tlist.p, tstart.p);
+    }
+    nchunk.reserve(ntile); woff.reserve(ntile);
     LAUNCH(c, k_tile_nchunk, nblk(ntile, 256), 256, 0, tstart.p, ntile, nchunk.p);
     exclusive_scan_async<int>(c, nchunk.p, woff.p, ntile, tot.p, bs);
     int W = 0;
@@ -734,19 +790,22 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     work.reserve(W);
     LAUNCH(c, k_tile_work, nblk(ntile, 256), 256, 0, nchunk.p, woff.p, ntile, work.p);
-    static bool attr_set = false;
-    if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(k_deposit_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM)); attr_set = true; }
     {
-      Stage sk(c, "deposit_dom_kernel", lv.npart_dep);
-      LAUNCH(c, k_deposit_tiles, (unsigned)W, DT_THREADS, DT_SMEM, c->pos4, tstart.p, work.p, (int)lv.L, v.logL, tbits, acc.p);
+      Stage sk(c, lv.dense ? "deposit_dom_kernel" : "deposit_ref_kernel", lv.npart_dep);
+      if (tiles_dense)
+        LAUNCH(c, k_deposit_tiles<false>, (unsigned)W, DT_THREADS, DT_SMEM, c->pos4, tstart.p, work.p, (int)lv.L, v.logL, tbits, acc.p,
+               (const uint32_t *)nullptr, (const int32_t *)nullptr, v, (const int32_t *)nullptr, (float)fxscale);
+      else
+        LAUNCH(c, k_deposit_tiles<true>, (unsigned)W, DT_THREADS, DT_SMEM, lv.lpos, tstart.p, work.p, (int)lv.L, v.logL, tbits, acc.p,
+               tlist.p, lv.pcell, v, lv.nbr, (float)fxscale);
     }
-    c->stage_cnt_extra["deposit_dom_ctas"] = W;
-    tstart.release(); nchunk.release(); woff.release(); bs.release(); tot.release(); work.release();
+    if (lv.dense) c->stage_cnt_extra["deposit_dom_ctas"] = W;
+    tstart.release(); nchunk.release(); woff.release(); bs.release(); tot.release(); work.release(); tlist.release(); head.release(); hs.release();
   } else if (lv.npart_dep > 0) {
     Stage sk(c, lv.dense ? "deposit_dom_kernel" : "deposit_ref_kernel", lv.npart_dep);
-    LAUNCH(c, k_deposit_generic, nblk(lv.npart_dep, 256), 256, 0, c->pos4, lv.plist, lv.pcell, (uint64_t)lv.npart_dep, v, lv.nbr, acc.p);
+    LAUNCH(c, k_deposit_generic, nblk(lv.npart_dep, 256), 256, 0, c->pos4, lv.plist, lv.pcell, (uint64_t)lv.npart_dep, v, lv.nbr, acc.p, fxscale);
   }
-  LAUNCH(c, k_finish_dens, nblk(nc, 256), 256, 0, acc.p, lv.dens, nc, lv.masstopartdens);
+  LAUNCH(c, k_finish_dens, nblk(nc, 256), 256, 0, acc.p, lv.dens, nc, lv.masstopartdens / fxscale);
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
   acc.release();
 }
@@ -850,8 +909,8 @@ void amr_build(ahfgpu_ctx *c)
         break;
       }
       fin.npart_dep = nmoved;
-      fin.plist = dalloc<uint32_t>(nmoved); fin.pcell = dalloc<int32_t>(nmoved);
-      if (np) LAUNCH(c, k_compact_moved, nblk(np, 256), 256, 0, coa.plist, newcell.p, moved.p, MS.p, np, fin.plist, fin.pcell, c->owner_level, (int8_t)(lev + 1));
+      fin.plist = dalloc<uint32_t>(nmoved); fin.pcell = dalloc<int32_t>(nmoved); fin.lpos = dalloc<float4>(nmoved);
+      if (np) LAUNCH(c, k_compact_moved, nblk(np, 256), 256, 0, coa.plist, newcell.p, moved.p, MS.p, np, fin.plist, fin.pcell, c->owner_level, (int8_t)(lev + 1), c->pos4, fin.lpos);
       CUDA_CHECK(cudaStreamSynchronize(c->stream));
       newcell.release(); moved.release(); MS.release();
     }

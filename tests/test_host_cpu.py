@@ -1,0 +1,116 @@
+"""CPU-only: host-side logic, the C-ABI surface, the synthetic generator, multi-rank partitioning (gloo)."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_library_exports_every_declared_symbol():
+    from ahf_b200 import ahf
+    ahf.build()
+    L = C.CDLL(ahf.LIB_PATH)
+    names = ahf.exported_symbols()
+    assert len(names) >= 20
+    for s in names:
+        assert hasattr(L, s), s
+
+
+def test_no_cpu_fallback_without_device():
+    from ahf_b200 import ahf
+    L = ahf.lib()
+    if L.ahfgpu_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    par = ahf.make_params(boxsize=64.0, pmass=1e10, lgrid_dom=64)
+    with pytest.raises(ahf.AhfGpuError):
+        ahf.AhfGpu(par)
+
+
+def test_params_follow_reference_unit_factors(golden):
+    from ahf_b200 import ahf
+    g = golden.glob      # r_fac x_fac v_fac m_fac rho_fac phi_fac Hubble ovlim rho_vir minpart vtune maxgather a
+    p = ahf.make_params(boxsize=float(golden.d["boxsize"]), pmass=float(golden.d["pmass"]), lgrid_dom=golden.n1d)
+    mine = [p.r_fac, p.x_fac, p.v_fac, p.m_fac, p.rho_fac, p.phi_fac, p.hubble, p.ovlim, p.rho_vir, p.min_part, p.vesc_tune]
+    assert np.allclose(mine, g[:11], rtol=1e-6), (mine, g[:11])
+
+
+def test_synth_box_and_gadget_roundtrip(tmp_path):
+    from ahf_b200 import synth
+    b = synth.make_box(16, seed=1, n_clumps=3)
+    assert b.pos.shape == (4096, 3) and b.pos.dtype == np.float32
+    assert b.pos.min() >= 0.0 and b.pos.max() < 1.0
+    inp = synth.write_reference_case(b, str(tmp_path))
+    raw = open(os.path.join(tmp_path, "snap.gadget"), "rb").read()
+    assert int.from_bytes(raw[:4], "little") == 256
+    npart = np.frombuffer(raw[4:4 + 24], "<i4")
+    assert npart[1] == 4096 and npart.sum() == 4096
+    x = np.frombuffer(raw[4 + 256 + 4 + 4:4 + 256 + 4 + 4 + 4096 * 12], "<f4").reshape(-1, 3)
+    assert np.array_equal((x * np.float32(1.0 / b.boxsize)).astype(np.float32), b.pos)      # exact: box is 2^k
+    assert "LgridDomain       = 16" in open(inp).read()
+    c, r, n = synth.halo_seeds(b)
+    assert len(r) == 3 and r.max() <= 0.25 and (n >= 30).all()
+
+
+def test_lpt_partition_properties():
+    from ahf_b200 import parallel as P
+    rng = np.random.default_rng(0)
+    w = rng.pareto(1.2, 500) * 100 + 20
+    a = P.assign_halos_lpt(w, 8)
+    loads = np.bincount(a, weights=w, minlength=8)
+    assert set(a.tolist()) <= set(range(8))
+    assert loads.max() <= loads.mean() + w.max()            # LPT bound
+    assert np.array_equal(a, P.assign_halos_lpt(w, 8))      # deterministic
+    b = P.slab_bounds(1000003, 8)
+    assert b[0] == 0 and b[-1] == 1000003 and np.all(np.diff(b) >= 125000)
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+from ahf_b200 import parallel as P, synth
+from oracle import oracle as O
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+box = synth.make_box(16, seed=9, n_clumps=4)
+keys = O.hilbert_keys(box.pos); order = O.argsort_keys(keys); keys = keys[order]
+b = P.slab_bounds(len(keys), 2)
+mine = np.arange(b[rank], b[rank + 1])
+# every rank owns a contiguous SFC slab; together they cover the box exactly once
+cnt = torch.tensor([len(mine)]); dist.all_reduce(cnt); assert int(cnt) == len(keys)
+lo = torch.tensor([int(keys[mine[0]] >> np.uint64(1))]); hi = torch.tensor([int(keys[mine[-1]] >> np.uint64(1))])
+los = [torch.zeros(1, dtype=torch.int64) for _ in range(2)]; his = [torch.zeros(1, dtype=torch.int64) for _ in range(2)]
+dist.all_gather(los, lo); dist.all_gather(his, hi)
+assert int(his[0]) <= int(los[1])
+# haloes: same LPT assignment on every rank, each halo constructed by exactly one rank, results identical to a serial run
+c, r, n = synth.halo_seeds(box)
+a = P.assign_halos_lpt(n, 2)
+par = dict(r_fac=box.boxsize, x_fac=box.boxsize, v_fac=box.boxsize*100, m_fac=box.pmass, rho_fac=box.pmass/box.boxsize**3,
+           phi_fac=4.3006485e-9*box.pmass/box.boxsize, Hubble=100.0, ovlim=200.0, rho_vir=2.7755397e11, vesc_tune=1.5, min_part=20)
+pos = box.pos[order]; mom = box.mom[order]
+sel = np.nonzero(a == rank)[0]
+res = O.construct_halos(keys, pos, mom, None, None, par, c[sel], r[sel], n[sel])
+np_local = torch.zeros(len(r), dtype=torch.int64)
+for k, h in enumerate(sel): np_local[h] = res[k]["npart"]
+dist.all_reduce(np_local)
+serial = O.construct_halos(keys, pos, mom, None, None, par, c, r, n)
+assert [int(v) for v in np_local] == [s["npart"] for s in serial]
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_two_rank_partition_gloo(tmp_path):
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % dict(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o
