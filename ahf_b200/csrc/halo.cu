@@ -245,11 +245,123 @@ __global__ void k_copy_unsorted(const int64_t *__restrict__ candoff, const int64
   for (int64_t i = threadIdx.x; i < ng; i += blockDim.x) out[eoff2[h] + i] = idxbuf[candoff[h] + i];
 }
 
+struct RvirOut { long long np; double M, R, ovd; };
+
+constexpr int HI = 4;            // members per thread and tile (blocked: thread t owns HI consecutive members)
+constexpr int HT = HB * HI;      // members per tile
+
+// exclusive block scan of NC doubles per thread at once; tot[] = block totals.  sm: (HB/32)*NC doubles
+template <int NC> __device__ __forceinline__ void block_excl_scan_n(const double (&v)[NC], double (&ex)[NC], double (&tot)[NC], double *sm)
+{
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double inc[NC];
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    inc[c] = v[c];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { double x = __shfl_up_sync(0xffffffffu, inc[c], o); if (lane >= o) inc[c] += x; }
+  }
+  __syncthreads();
+  if (lane == 31) {
+#pragma unroll
+    for (int c = 0; c < NC; c++) sm[w * NC + c] = inc[c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    double base = 0.0, t = 0.0;
+#pragma unroll
+    for (int q = 0; q < HB / 32; q++) { double s = sm[q * NC + c]; if (q < w) base += s; t += s; }
+    ex[c] = base + inc[c] - v[c]; tot[c] = t;
+  }
+}
+template <int NC> __device__ __forceinline__ void block_sum_n(double (&v)[NC], double *sm)
+{
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[c] += __shfl_xor_sync(0xffffffffu, v[c], o);
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int c = 0; c < NC; c++) sm[(threadIdx.x >> 5) * NC + c] = v[c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < NC; c++) { double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < HB / 32; q++) t += sm[q * NC + c];
+    v[c] = t; }
+}
+
+// one tile of radius-sorted members in registers
+struct TileMembers {
+  uint32_t pid[HI];
+  double   w[HI], r[HI], d[HI][3];
+  bool     act[HI];
+};
+__device__ __forceinline__ void load_tile(TileMembers &T, const float4 *__restrict__ pos4, const uint32_t *__restrict__ ip, long long base, long long np,
+                                          const double c[3])
+{
+#pragma unroll
+  for (int i = 0; i < HI; i++) {
+    long long j = base + (long long)threadIdx.x * HI + i;
+    T.act[i] = j < np; T.pid[i] = 0; T.w[i] = 0.0; T.r[i] = 0.0; T.d[i][0] = T.d[i][1] = T.d[i][2] = 0.0;
+    if (T.act[i]) {
+      T.pid[i] = ip[j];
+      float4 p = pos4[T.pid[i]];
+      T.w[i] = (double)p.w; sep3(p, c, T.d[i]);
+      T.r[i] = sqrt(T.d[i][0] * T.d[i][0] + T.d[i][1] * T.d[i][1] + T.d[i][2] * T.d[i][2]);
+    }
+  }
+}
+// M(<=j) for the tile's members: thread-local running sum + one block scan.  Returns the tile total.
+__device__ __forceinline__ double tile_mass(const TileMembers &T, double carryM, double (&M)[HI], double *smd)
+{
+  double loc[1] = { 0.0 }, ex[1], tot[1];
+#pragma unroll
+  for (int i = 0; i < HI; i++) loc[0] += T.w[i];
+  block_excl_scan_n<1>(loc, ex, tot, smd);
+  double run = carryM + ex[0];
+#pragma unroll
+  for (int i = 0; i < HI; i++) { run += T.w[i]; M[i] = run; }
+  return tot[0];
+}
+// Phi(r_j) = trapezoid sum of M(<r)/r^2 (ahf_halos.c:3398-3410, :3514-3526): needs (r, I) of member j-1
+__device__ __forceinline__ double tile_phi(const TileMembers &T, const double (&M)[HI], double carryPhi, double &prev_r, double &prev_I,
+                                           double (&Phi)[HI], double *nb_r, double *nb_I, double *smd, long long tile_n)
+{
+  double I[HI];
+#pragma unroll
+  for (int i = 0; i < HI; i++) I[i] = (T.act[i] && T.r[i] > MACHINE_ZERO) ? M[i] / (T.r[i] * T.r[i]) : 0.0;
+  __syncthreads();
+  nb_r[threadIdx.x] = T.r[HI - 1]; nb_I[threadIdx.x] = I[HI - 1];
+  __syncthreads();
+  double rp = threadIdx.x ? nb_r[threadIdx.x - 1] : prev_r, Ip = threadIdx.x ? nb_I[threadIdx.x - 1] : prev_I;
+  double term[HI], loc[1] = { 0.0 }, ex[1], tot[1];
+#pragma unroll
+  for (int i = 0; i < HI; i++) {
+    term[i] = (T.act[i] && T.r[i] > MACHINE_ZERO) ? ((I[i] + Ip) / 2.) * (T.r[i] - rp) : 0.0;
+    loc[0] += term[i];
+    rp = T.r[i]; Ip = I[i];
+  }
+  block_excl_scan_n<1>(loc, ex, tot, smd);
+  double run = carryPhi + ex[0];
+#pragma unroll
+  for (int i = 0; i < HI; i++) { run += term[i]; Phi[i] = run; }
+  // (r, I) of the tile's last member -> carry for the next tile
+  const long long lt = (tile_n - 1) / HI; const int li = (int)((tile_n - 1) % HI);
+  __syncthreads();
+  if (threadIdx.x == lt) { nb_r[HB] = T.r[li]; nb_I[HB] = I[li]; }
+  __syncthreads();
+  prev_r = nb_r[HB]; prev_I = nb_I[HB];
+  return tot[0];
+}
+
 // ------------------------------------------------------------------------------------------------
 // U2: rem_outsideRvir (ahf_halos.c:3811-3869): first member whose mean enclosed overdensity drops below ovlim, inclusive
 // ------------------------------------------------------------------------------------------------
-struct RvirOut { long long np; double M, R, ovd; };
-
 __device__ RvirOut rvir_cut(const float4 *__restrict__ pos4, const uint32_t *__restrict__ ip, long long np, const double c[3], const HP &P,
                             double *smd, long long *sml)
 {
@@ -257,26 +369,34 @@ __device__ RvirOut rvir_cut(const float4 *__restrict__ pos4, const uint32_t *__r
   double carryM = 0.0;
   if (threadIdx.x == 0) { res.np = np; res.M = 0; res.R = -1.0; res.ovd = 2 * P.ovlim; }
   __syncthreads();
-  for (long long base = 0; base < np; base += HB) {
-    long long j = base + threadIdx.x;
-    double w = 0.0, r = 0.0;
-    if (j < np) { float4 p = pos4[ip[j]]; w = (double)p.w; r = dist3(p, c); }
-    double tot, M = carryM + block_incl_scan(w, smd, &tot);
-    double od = 0.0;
-    bool   cross = false;
-    if (j < np) {
-      double V = 4. * PI_ / 3. * (r * r * r);
-      od = M / V * P.rho_fac / P.rho_vir;
-      cross = !(od >= P.ovlim);
+  for (long long base = 0; base < np; base += HT) {
+    TileMembers T;
+    load_tile(T, pos4, ip, base, np, c);
+    double M[HI];
+    double totM = tile_mass(T, carryM, M, smd);
+    long long mine = 0x7fffffffffffffffll;
+    double od[HI];
+#pragma unroll
+    for (int i = 0; i < HI; i++) {
+      od[i] = 0.0;
+      if (T.act[i]) {
+        double V = 4. * PI_ / 3. * (T.r[i] * T.r[i] * T.r[i]);
+        od[i] = M[i] / V * P.rho_fac / P.rho_vir;
+        if (!(od[i] >= P.ovlim) && mine == 0x7fffffffffffffffll) mine = base + (long long)threadIdx.x * HI + i;
+      }
     }
-    long long first = block_min_ll(cross ? j : (long long)0x7fffffffffffffffll, sml);
+    long long first = block_min_ll(mine, sml);
     if (first != 0x7fffffffffffffffll) {
-      if (j == first) { res.np = j + 1; res.M = M; res.R = r; res.ovd = od; }
+#pragma unroll
+      for (int i = 0; i < HI; i++)
+        if (base + (long long)threadIdx.x * HI + i == first) { res.np = first + 1; res.M = M[i]; res.R = T.r[i]; res.ovd = od[i]; }
       __syncthreads();
       return res;
     }
-    if (j == np - 1) { res.np = np; res.M = M; res.R = r; res.ovd = od; }
-    carryM += tot;
+#pragma unroll
+    for (int i = 0; i < HI; i++)
+      if (base + (long long)threadIdx.x * HI + i == np - 1) { res.np = np; res.M = M[i]; res.R = T.r[i]; res.ovd = od[i]; }
+    carryM += totM;
     __syncthreads();
   }
   __syncthreads();
@@ -291,11 +411,12 @@ __global__ void __launch_bounds__(HB) k_halo_unbind(const float4 *__restrict__ p
                                                     uint32_t *__restrict__ members, HP P, double *__restrict__ scal, int64_t *__restrict__ npart_out,
                                                     int64_t *__restrict__ iter_work)
 {
-  __shared__ double    smd[HB / 32];
+  __shared__ double    smd[(HB / 32) * 4];
   __shared__ long long sml[HB / 32];
   __shared__ int       smi[HB / 32];
+  __shared__ double    nb_r[HB + 1], nb_I[HB + 1];
   __shared__ double    s_seed[4];
-  __shared__ int       s_changed;
+  __shared__ double    s_R;
   const int64_t h = blockIdx.x;
   uint32_t     *ip = members + moff0[h];
   long long     np = ngather[h];
@@ -318,27 +439,16 @@ __global__ void __launch_bounds__(HB) k_halo_unbind(const float4 *__restrict__ p
       niter++;
       work += np;
       // pass A: Phi0 = sum of trapezoids of M(<r)/r^2 + M_tot/r_last (:3359-3426)
-      double carryM = 0.0, carryPhi = 0.0, prev_r = 0.0, prev_I = 0.0, lastM = 0.0, lastR = 0.0;
-      for (long long base = 0; base < np; base += HB) {
-        long long j = base + threadIdx.x;
-        double w = 0.0, r = 0.0;
-        if (j < np) { float4 p = pos4[ip[j]]; w = (double)p.w; r = dist3(p, c); }
-        double totM, M = carryM + block_incl_scan(w, smd, &totM);
-        double I = (j < np && r > MACHINE_ZERO) ? M / (r * r) : 0.0;
-        // neighbour values (j-1): shuffle within the warp, shared memory across warps, carry across tiles
-        __shared__ double nb_r[HB], nb_I[HB];
-        nb_r[threadIdx.x] = r; nb_I[threadIdx.x] = I;
-        __syncthreads();
-        double rp = threadIdx.x ? nb_r[threadIdx.x - 1] : prev_r, Ip = threadIdx.x ? nb_I[threadIdx.x - 1] : prev_I;
-        double term = (j < np && r > MACHINE_ZERO) ? ((I + Ip) / 2.) * (r - rp) : 0.0;
-        double totP; block_incl_scan(term, smd, &totP);
-        carryPhi += totP; carryM += totM;
-        long long lastj = (base + HB < np ? base + HB : np) - 1;
-        prev_r = nb_r[lastj - base]; prev_I = nb_I[lastj - base];
-        if (lastj == np - 1) { lastR = prev_r; lastM = carryM; }
-        __syncthreads();
+      double carryM = 0.0, carryPhi = 0.0, prev_r = 0.0, prev_I = 0.0;
+      for (long long base = 0; base < np; base += HT) {
+        TileMembers T;
+        load_tile(T, pos4, ip, base, np, c);
+        double M[HI], Phi[HI];
+        const long long tile_n = (base + HT < np ? base + HT : np) - base;
+        carryM += tile_mass(T, carryM, M, smd);
+        carryPhi += tile_phi(T, M, carryPhi, prev_r, prev_I, Phi, nb_r, nb_I, smd, tile_n);
       }
-      Phi0 = carryPhi + lastM / lastR;
+      Phi0 = carryPhi + carryM / prev_r;
       // seed of the running bulk velocity (:3441-3470)
       if (threadIdx.x == 0) {
         long long seed = 0;
@@ -355,72 +465,77 @@ __global__ void __launch_bounds__(HB) k_halo_unbind(const float4 *__restrict__ p
         s_seed[0] = w; s_seed[1] = w * m.x; s_seed[2] = w * m.y; s_seed[3] = w * m.z;
       }
       __syncthreads();
-      double Mvel = s_seed[0], Vx = s_seed[1], Vy = s_seed[2], Vz = s_seed[3];
+      double run0[4] = { s_seed[0], s_seed[1], s_seed[2], s_seed[3] };     // M_vel, V (bound so far, before this tile)
       // pass B (:3478-3583)
       carryM = 0.0; carryPhi = 0.0; prev_r = 0.0; prev_I = 0.0;
       long long nb = 0;
       double Mv_acc = 0.0, Rv_last = 0.0;
       nremove = 0;
-      for (long long base = 0; base < np; base += HB) {
-        long long j = base + threadIdx.x;
-        const bool act = j < np;
-        double w = 0.0, r = 0.0, d[3] = { 0, 0, 0 }, mx = 0, my = 0, mz = 0, uu = -1.0;
-        uint32_t pid = 0;
-        if (act) {
-          pid = ip[j];
-          float4 p = pos4[pid], m = mom4[pid];
-          w = (double)p.w; sep3(p, c, d); r = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-          mx = (double)m.x; my = (double)m.y; mz = (double)m.z; uu = (double)m.w;
+      for (long long base = 0; base < np; base += HT) {
+        TileMembers T;
+        load_tile(T, pos4, ip, base, np, c);
+        const long long tile_n = (base + HT < np ? base + HT : np) - base;
+        double M[HI], Phi[HI], mom[HI][3], uu[HI], vesc2[HI];
+#pragma unroll
+        for (int i = 0; i < HI; i++) {
+          mom[i][0] = mom[i][1] = mom[i][2] = 0.0; uu[i] = -1.0;
+          if (T.act[i]) { float4 m = mom4[T.pid[i]]; mom[i][0] = (double)m.x; mom[i][1] = (double)m.y; mom[i][2] = (double)m.z; uu[i] = (double)m.w; }
         }
-        double totM, M = carryM + block_incl_scan(w, smd, &totM);
-        double I = (act && r > MACHINE_ZERO) ? M / (r * r) : 0.0;
-        __shared__ double nb_r[HB], nb_I[HB];
-        nb_r[threadIdx.x] = r; nb_I[threadIdx.x] = I;
-        __syncthreads();
-        double rp = threadIdx.x ? nb_r[threadIdx.x - 1] : prev_r, Ip = threadIdx.x ? nb_I[threadIdx.x - 1] : prev_I;
-        double term = (act && r > MACHINE_ZERO) ? ((I + Ip) / 2.) * (r - rp) : 0.0;
-        double totP, Phi = carryPhi + block_incl_scan(term, smd, &totP);
-        double v_esc2 = (act && r > MACHINE_ZERO) ? (2 * fabs(Phi - Phi0) * P.phi_fac) : 1e30;
-        // fixed point of the causal bound mask inside the tile
-        bool bound = act;
+        carryM += tile_mass(T, carryM, M, smd);
+        carryPhi += tile_phi(T, M, carryPhi, prev_r, prev_I, Phi, nb_r, nb_I, smd, tile_n);
+#pragma unroll
+        for (int i = 0; i < HI; i++) vesc2[i] = (T.act[i] && T.r[i] > MACHINE_ZERO) ? (2 * fabs(Phi[i] - Phi0) * P.phi_fac) : 1e30;
+        // causal bound mask: inside a thread the members are tested sequentially; across threads the incoming prefix of
+        // (M_vel, V) is iterated to its fixed point (a thread's answer only depends on the threads before it)
+        bool bound[HI];
+#pragma unroll
+        for (int i = 0; i < HI; i++) bound[i] = T.act[i];
+        double tot[4];
         for (int it = 0; it < HB + 2; it++) {
-          double bw = bound ? w : 0.0;
-          double t0, t1, t2, t3;
-          double eM = Mvel + block_incl_scan(bw, smd, &t0) - bw;
-          double eX = Vx + block_incl_scan(bw * mx, smd, &t1) - bw * mx;
-          double eY = Vy + block_incl_scan(bw * my, smd, &t2) - bw * my;
-          double eZ = Vz + block_incl_scan(bw * mz, smd, &t3) - bw * mz;
-          bool nbnd = false;
-          if (act) {
-            double dvx = (mx - eX / eM) * P.v_fac + P.hubble * d[0] * P.r_fac;
-            double dvy = (my - eY / eM) * P.v_fac + P.hubble * d[1] * P.r_fac;
-            double dvz = (mz - eZ / eM) * P.v_fac + P.hubble * d[2] * P.r_fac;
-            double vel2 = dvx * dvx + dvy * dvy + dvz * dvz;
-            if (has_u) vel2 += (uu < 0.0 ? 0.0 : 2 * uu);
-            nbnd = !(vel2 > v2_tune * v_esc2);
+          double loc[4] = { 0, 0, 0, 0 }, ex[4];
+#pragma unroll
+          for (int i = 0; i < HI; i++)
+            if (bound[i]) { loc[0] += T.w[i]; loc[1] += T.w[i] * mom[i][0]; loc[2] += T.w[i] * mom[i][1]; loc[3] += T.w[i] * mom[i][2]; }
+          block_excl_scan_n<4>(loc, ex, tot, smd);
+          double m = run0[0] + ex[0], vx = run0[1] + ex[1], vy = run0[2] + ex[2], vz = run0[3] + ex[3];
+          bool changed = false;
+#pragma unroll
+          for (int i = 0; i < HI; i++) {
+            bool nbnd = false;
+            if (T.act[i]) {
+              double dvx = (mom[i][0] - vx / m) * P.v_fac + P.hubble * T.d[i][0] * P.r_fac;
+              double dvy = (mom[i][1] - vy / m) * P.v_fac + P.hubble * T.d[i][1] * P.r_fac;
+              double dvz = (mom[i][2] - vz / m) * P.v_fac + P.hubble * T.d[i][2] * P.r_fac;
+              double vel2 = dvx * dvx + dvy * dvy + dvz * dvz;
+              if (has_u) vel2 += (uu[i] < 0.0 ? 0.0 : 2 * uu[i]);
+              nbnd = !(vel2 > v2_tune * vesc2[i]);
+              if (nbnd) { m += T.w[i]; vx += T.w[i] * mom[i][0]; vy += T.w[i] * mom[i][1]; vz += T.w[i] * mom[i][2]; }
+            }
+            changed |= (nbnd != bound[i]);
+            bound[i] = nbnd;
           }
-          if (threadIdx.x == 0) s_changed = 0;
-          __syncthreads();
-          if (nbnd != bound) s_changed = 1;
-          bound = nbnd;
-          __syncthreads();
-          int ch = s_changed;
-          __syncthreads();
-          if (!ch) { Mvel += t0; Vx += t1; Vy += t2; Vz += t3; break; }
+          if (!__syncthreads_or(changed ? 1 : 0)) break;
         }
-        // append bound members (in place: nb <= base)
-        int totb, posb = block_excl_scan_i(bound ? 1 : 0, smi, &totb);
+        // `tot` was computed with the mask of the last (unchanged) evaluation
+        run0[0] += tot[0]; run0[1] += tot[1]; run0[2] += tot[2]; run0[3] += tot[3];
+        Mv_acc += tot[0];
+        // append bound members in place (nb <= base)
+        int cnt = 0;
+#pragma unroll
+        for (int i = 0; i < HI; i++) cnt += bound[i] ? 1 : 0;
+        int totb, posb = block_excl_scan_i(cnt, smi, &totb);
+        long long lastj = -1;
+#pragma unroll
+        for (int i = 0; i < HI; i++)
+          if (bound[i]) { ip[nb + posb] = T.pid[i]; posb++; lastj = base + (long long)threadIdx.x * HI + i; }
+        long long lb = block_min_ll(-lastj, sml);                     // -(largest bound index), 1 if none
+#pragma unroll
+        for (int i = 0; i < HI; i++)
+          if (bound[i] && base + (long long)threadIdx.x * HI + i == -lb) s_R = T.r[i];
         __syncthreads();
-        if (bound) ip[nb + posb] = pid;
-        // last bound member of the tile defines R_vir so far
-        long long lastb = block_min_ll(bound ? -(long long)j : 1, sml);       // max j among bound = -min(-j)
-        if (lastb <= 0 && totb > 0) Rv_last = nb_r[(-lastb) - base];
-        Mv_acc += block_sum(bound ? w : 0.0, smd);
+        if (totb > 0) Rv_last = s_R;
         nb += totb;
-        long long tile_n = (base + HB < np ? base + HB : np) - base;
         nremove += tile_n - totb;
-        carryM += totM; carryPhi += totP;
-        prev_r = nb_r[tile_n - 1]; prev_I = nb_I[tile_n - 1];
         __syncthreads();
       }
       np = nb; M_vir = Mv_acc; R_vir = Rv_last;

@@ -168,6 +168,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ahf.build()
     box = synth.make_box(args.n1d, seed=43 + rank)
