@@ -629,11 +629,11 @@ __global__ void __launch_bounds__(HB) k_halo_profiles(const float4 *__restrict__
                                                       double *__restrict__ scal, const int64_t *__restrict__ poff, double *__restrict__ prof,
                                                       const int64_t *__restrict__ soff, double *__restrict__ scratch)
 {
-  __shared__ double smd[HB / 32];
+  __shared__ double smd[(HB / 32) * NACC];
   __shared__ double edge[MAXBINS];
   __shared__ double acc[MAXBINS][NACC];
   __shared__ double vesc_bin[MAXBINS], Vc_bin[MAXBINS][3];
-  __shared__ double nb_r[HB], nb_I[HB];
+  __shared__ double nb_r[HB + 1], nb_I[HB + 1];
   __shared__ double s_dmin, s_dmax;
   __shared__ double s_emin[HB / 32]; __shared__ long long s_eidx[HB / 32];
   const int64_t h = blockIdx.x;
@@ -663,97 +663,117 @@ __global__ void __launch_bounds__(HB) k_halo_profiles(const float4 *__restrict__
   for (int i = threadIdx.x; i < MAXBINS * NACC; i += HB) (&acc[0][0])[i] = 0.0;
   for (int i = threadIdx.x; i < MAXBINS; i += HB) { vesc_bin[i] = 0.0; Vc_bin[i][0] = Vc_bin[i][1] = Vc_bin[i][2] = 0.0; }
   __syncthreads();
-  double carryM = 0.0, carryPhi = 0.0, cVx = 0.0, cVy = 0.0, cVz = 0.0, prev_r = 0.0, prev_I = 0.0, prev_rr = -1.0;
+  double carryM = 0.0, carryPhi = 0.0, cP[3] = { 0.0, 0.0, 0.0 }, prev_r = 0.0, prev_I = 0.0;
   double best_e = 1e30; long long best_j = -1;
-  for (long long base = 0; base < np; base += HB) {
-    const long long j = base + threadIdx.x;
-    const bool act = j < np;
-    double w = 0.0, r = 0.0, d[3] = { 0, 0, 0 }, mx = 0, my = 0, mz = 0, uu = -1.0;
-    if (act) {
-      uint32_t pid = ip[j];
-      float4 p = pos4[pid], m = mom4[pid];
-      w = (double)p.w; sep3(p, c, d); r = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-      mx = (double)m.x; my = (double)m.y; mz = (double)m.z; uu = (double)m.w;
-    }
-    double tM, t1, t2, t3, tP;
-    double M  = carryM + block_incl_scan(w, smd, &tM);
-    double Px = cVx + block_incl_scan(w * mx, smd, &t1);
-    double Py = cVy + block_incl_scan(w * my, smd, &t2);
-    double Pz = cVz + block_incl_scan(w * mz, smd, &t3);
-    double I = (act && r > MACHINE_ZERO) ? M / (r * r) : 0.0;
-    nb_r[threadIdx.x] = r; nb_I[threadIdx.x] = I;
-    __syncthreads();
-    double rp = threadIdx.x ? nb_r[threadIdx.x - 1] : prev_r, Ip = threadIdx.x ? nb_I[threadIdx.x - 1] : prev_I;
-    double rprev_bin = threadIdx.x ? nb_r[threadIdx.x - 1] : prev_rr;       // r_{j-1} with r_{-1} = -1 for the bin test
-    double term = (act && r > MACHINE_ZERO) ? ((I + Ip) / 2.) * (r - rp) : 0.0;
-    double Phi = carryPhi + block_incl_scan(term, smd, &tP);
-    int bin = 0;
-    double v[NACC];
+  __shared__ int s_binlo, s_binhi;
+  for (long long base = 0; base < np; base += HT) {
+    TileMembers T;
+    load_tile(T, pos4, ip, base, np, c);
+    const long long tile_n = (base + HT < np ? base + HT : np) - base;
+    double mom[HI][3], uu[HI], M[HI], Phi[HI], Pc[HI][3];
 #pragma unroll
-    for (int q = 0; q < NACC; q++) v[q] = 0.0;
-    double Epart = 1e30, vesc2 = 0.0;
-    if (act) {
-      while (bin < nbins - 1 && !(rprev_bin < edge[bin])) bin++;            // member j falls into the first bin whose edge exceeds r_{j-1}
-      double dvx = mx - Px / M, dvy = my - Py / M, dvz = mz - Pz / M;       // :4363-4370 running mean INCLUDING j
-      v[9]  = w * (d[1] * dvz - d[2] * dvy);
-      v[10] = w * (d[2] * dvx - d[0] * dvz);
-      v[11] = w * (d[0] * dvy - d[1] * dvx);
-      dvx += P.hubble * d[0] * P.r_fac / P.v_fac; dvy += P.hubble * d[1] * P.r_fac / P.v_fac; dvz += P.hubble * d[2] * P.r_fac / P.v_fac;
-      double Tpart = w * (dvx * dvx + dvy * dvy + dvz * dvz);
-      double Upart = (Phi - Phi0) * w;
-      vesc2 = 2 * fabs(Upart) / w;
-      if (has_u && uu >= 0.0) Tpart += w * (2 * uu / (P.v_fac * P.v_fac));
-      Epart = 0.5 * Tpart + Upart;
-      v[0] = w * (c[0] + d[0]); v[1] = w * (c[1] + d[1]); v[2] = w * (c[2] + d[2]);
-      v[3] = w * d[0] * d[0]; v[4] = w * d[1] * d[1]; v[5] = w * d[2] * d[2];
-      v[6] = w * d[0] * d[1]; v[7] = w * d[0] * d[2]; v[8] = w * d[1] * d[2];
-      v[12] = Tpart; v[13] = Upart;
-      if (has_w) { if (fabs(w - 1.0) < ZERO_F) v[14] = w; else if (w > 1.0) v[15] = w; } else v[14] = w;
-      v[16] = w; v[17] = 1.0;
-      // per-member arrays for Rmax / r2 (:4598-4616)
-      w_r[j] = r;
-      // last member of a bin defines the bin's v_esc2 and cumulative momentum: written below by the owner
+    for (int i = 0; i < HI; i++) {
+      mom[i][0] = mom[i][1] = mom[i][2] = 0.0; uu[i] = -1.0;
+      if (T.act[i]) { float4 m = mom4[T.pid[i]]; mom[i][0] = (double)m.x; mom[i][1] = (double)m.y; mom[i][2] = (double)m.z; uu[i] = (double)m.w; }
     }
-    // per (tile, bin) reductions in a fixed order
-    __shared__ int s_binlo, s_binhi;
-    if (threadIdx.x == 0) s_binlo = bin;
-    long long tile_n = (base + HB < np ? base + HB : np) - base;
-    if (threadIdx.x == tile_n - 1) s_binhi = bin;
+    carryM += tile_mass(T, carryM, M, smd);
+    {
+      double loc[3] = { 0, 0, 0 }, ex[3], tot[3];
+#pragma unroll
+      for (int i = 0; i < HI; i++) { loc[0] += T.w[i] * mom[i][0]; loc[1] += T.w[i] * mom[i][1]; loc[2] += T.w[i] * mom[i][2]; }
+      block_excl_scan_n<3>(loc, ex, tot, smd);
+      double run[3] = { cP[0] + ex[0], cP[1] + ex[1], cP[2] + ex[2] };
+#pragma unroll
+      for (int i = 0; i < HI; i++) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) { run[q] += T.w[i] * mom[i][q]; Pc[i][q] = run[q]; }
+      }
+      cP[0] += tot[0]; cP[1] += tot[1]; cP[2] += tot[2];
+    }
+    const double rr_in = (base == 0) ? -1.0 : prev_r;                 // r_{j-1} of the tile's first member (r_{-1} = -1)
+    carryPhi += tile_phi(T, M, carryPhi, prev_r, prev_I, Phi, nb_r, nb_I, smd, tile_n);
+    // bin of every member: the first bin whose edge exceeds r_{j-1} (ahf_halos.c:4283 `while (cur_dist < cur_rad)`)
+    int bin[HI];
+    {
+      double rp = threadIdx.x ? nb_r[threadIdx.x - 1] : rr_in;
+      int b = 0;
+#pragma unroll
+      for (int i = 0; i < HI; i++) {
+        while (b < nbins - 1 && !(rp < edge[b])) b++;
+        bin[i] = b;
+        rp = T.r[i];
+      }
+    }
+    if (threadIdx.x == 0) s_binlo = bin[0];
+    if (threadIdx.x == (tile_n - 1) / HI) s_binhi = bin[(tile_n - 1) % HI];
     __syncthreads();
     const int blo = s_binlo, bhi = s_binhi;
+    // per member energies (needed for the bin sums, v_esc and the most bound member)
+    double Tp[HI], Up[HI], Lm[HI][3];
+#pragma unroll
+    for (int i = 0; i < HI; i++) {
+      Tp[i] = Up[i] = 0.0; Lm[i][0] = Lm[i][1] = Lm[i][2] = 0.0;
+      if (T.act[i]) {
+        const double w = T.w[i];
+        double dvx = mom[i][0] - Pc[i][0] / M[i], dvy = mom[i][1] - Pc[i][1] / M[i], dvz = mom[i][2] - Pc[i][2] / M[i];   // :4363-4370 mean INCLUDING j
+        Lm[i][0] = w * (T.d[i][1] * dvz - T.d[i][2] * dvy);
+        Lm[i][1] = w * (T.d[i][2] * dvx - T.d[i][0] * dvz);
+        Lm[i][2] = w * (T.d[i][0] * dvy - T.d[i][1] * dvx);
+        dvx += P.hubble * T.d[i][0] * P.r_fac / P.v_fac; dvy += P.hubble * T.d[i][1] * P.r_fac / P.v_fac; dvz += P.hubble * T.d[i][2] * P.r_fac / P.v_fac;
+        Tp[i] = w * (dvx * dvx + dvy * dvy + dvz * dvz);
+        Up[i] = (Phi[i] - Phi0) * w;
+        const double vesc2 = 2 * fabs(Up[i]) / w;
+        if (has_u && uu[i] >= 0.0) Tp[i] += w * (2 * uu[i] / (P.v_fac * P.v_fac));
+        const long long j = base + (long long)threadIdx.x * HI + i;
+        w_r[j] = T.r[i];
+        // the last member of a bin owns the bin's v_esc2 and cumulative momentum
+        bool lastofbin = (j == np - 1);
+        if (!lastofbin) { int nbn = bin[i]; while (nbn < nbins - 1 && !(T.r[i] < edge[nbn])) nbn++; lastofbin = nbn != bin[i]; }
+        if (lastofbin) { vesc_bin[bin[i]] = vesc2; Vc_bin[bin[i]][0] = Pc[i][0]; Vc_bin[bin[i]][1] = Pc[i][1]; Vc_bin[bin[i]][2] = Pc[i][2]; }
+        const double Epart = 0.5 * Tp[i] + Up[i];
+        if (Epart < best_e) { best_e = Epart; best_j = j; }          // provisional: thread-local, merged below
+      }
+    }
+    // (tile, bin) reductions in a fixed order
     for (int b = blo; b <= bhi; b++) {
+      double s[NACC];
 #pragma unroll
-      for (int q = 0; q < NACC; q++) {
-        double s = block_sum((act && bin == b) ? v[q] : 0.0, smd);
-        if (threadIdx.x == 0) acc[b][q] += s;
-      }
-    }
-    // last member of each bin inside this tile: it owns v_esc2 and P(<=j) of the bin
-    if (act) {
-      bool lastofbin = (j == np - 1);
-      if (!lastofbin) {
-        // next member's bin: computed from r_j
-        int nbn = bin; while (nbn < nbins - 1 && !(r < edge[nbn])) nbn++;
-        lastofbin = nbn != bin;
-      }
-      if (lastofbin) { vesc_bin[bin] = vesc2; Vc_bin[bin][0] = Px; Vc_bin[bin][1] = Py; Vc_bin[bin][2] = Pz; }
-    }
-    // most bound member: minimum of Epart, first index on ties (:4590-4596)
-    {
-      double e = Epart; long long jj = act ? j : 0x7fffffffffffffffll;
+      for (int q = 0; q < NACC; q++) s[q] = 0.0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        double e2 = __shfl_xor_sync(0xffffffffu, e, o); long long j2 = __shfl_xor_sync(0xffffffffu, jj, o);
-        if (e2 < e || (e2 == e && j2 < jj)) { e = e2; jj = j2; }
+      for (int i = 0; i < HI; i++) {
+        if (T.act[i] && bin[i] == b) {
+          const double w = T.w[i];
+          s[0] += w * (c[0] + T.d[i][0]); s[1] += w * (c[1] + T.d[i][1]); s[2] += w * (c[2] + T.d[i][2]);
+          s[3] += w * T.d[i][0] * T.d[i][0]; s[4] += w * T.d[i][1] * T.d[i][1]; s[5] += w * T.d[i][2] * T.d[i][2];
+          s[6] += w * T.d[i][0] * T.d[i][1]; s[7] += w * T.d[i][0] * T.d[i][2]; s[8] += w * T.d[i][1] * T.d[i][2];
+          s[9] += Lm[i][0]; s[10] += Lm[i][1]; s[11] += Lm[i][2];
+          s[12] += Tp[i]; s[13] += Up[i];
+          if (has_w) { if (fabs(w - 1.0) < ZERO_F) s[14] += w; else if (w > 1.0) s[15] += w; } else s[14] += w;
+          s[16] += w; s[17] += 1.0;
+        }
       }
-      __syncthreads();
-      if ((threadIdx.x & 31) == 0) { s_emin[threadIdx.x >> 5] = e; s_eidx[threadIdx.x >> 5] = jj; }
-      __syncthreads();
-      for (int q = 0; q < HB / 32; q++) if (s_emin[q] < best_e) { best_e = s_emin[q]; best_j = s_eidx[q]; }
+      block_sum_n<NACC>(s, smd);
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < NACC; q++) acc[b][q] += s[q];
+      }
     }
-    carryM += tM; cVx += t1; cVy += t2; cVz += t3; carryPhi += tP;
-    prev_r = nb_r[tile_n - 1]; prev_I = nb_I[tile_n - 1]; prev_rr = prev_r;
     __syncthreads();
+  }
+  // most bound member: minimum of 0.5 T + U, first index on ties (:4590-4596); merge the thread-local candidates
+  {
+    double e = best_e; long long jj = best_j < 0 ? 0x7fffffffffffffffll : best_j;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double e2 = __shfl_xor_sync(0xffffffffu, e, o); long long j2 = __shfl_xor_sync(0xffffffffu, jj, o);
+      if (e2 < e || (e2 == e && j2 < jj)) { e = e2; jj = j2; }
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { s_emin[threadIdx.x >> 5] = e; s_eidx[threadIdx.x >> 5] = jj; }
+    __syncthreads();
+    best_e = 1e30; best_j = -1;
+    for (int q = 0; q < HB / 32; q++)
+      if (s_eidx[q] != 0x7fffffffffffffffll && (s_emin[q] < best_e || (s_emin[q] == best_e && s_eidx[q] < best_j) || best_j < 0)) { best_e = s_emin[q]; best_j = s_eidx[q]; }
   }
   __syncthreads();
   // ---- per-bin cumulative values, Jacobi, profile columns
@@ -833,6 +853,14 @@ __global__ void __launch_bounds__(HB) k_halo_profiles(const float4 *__restrict__
   const long long nn = np - NIGNORE;          // arrays are offset by NIGNORE
   double x_r2 = 0.0, x_rmax = 0.0;
   for (int which = 0; which < 2; which++) {   // 0: dens_r2 (3 smoothing passes), 1: Vcirc2 (1 pass)
+    if (!has_w) {
+      // equal masses: M(<=j) = j + 1 exactly, no scan needed
+      for (long long j = threadIdx.x; j < np; j += HB) {
+        double r = w_r[j], rpv = j ? w_r[j - 1] : 0.0;
+        if (which == 0) { double dV = F43 * ((r * r * r) - (rpv * rpv * rpv)); w_y[j] = 1.0 / dV * (((r + rpv) / 2.) * ((r + rpv) / 2.)); }
+        else w_y[j] = (double)(j + 1) / r;
+      }
+    } else {
     double cM = 0.0;
     for (long long base = 0; base < np; base += HB) {
       long long j = base + threadIdx.x;
@@ -845,6 +873,7 @@ __global__ void __launch_bounds__(HB) k_halo_profiles(const float4 *__restrict__
         else w_y[j] = M / r;
       }
       cM += tM;
+    }
     }
     __syncthreads();
     double *ya = w_y + NIGNORE, *yb = w_t + NIGNORE;
@@ -882,7 +911,17 @@ __global__ void __launch_bounds__(HB) k_halo_profiles(const float4 *__restrict__
     if (which == 0) x_r2 = xm; else x_rmax = xm;
     __syncthreads();
   }
-  // V_max from the first member with r >= R_max (:4892-4901); M(<=j) by one more scan
+  // V_max from the first member with r >= R_max (:4892-4901)
+  if (!has_w) {
+    if (threadIdx.x == 0) {
+      long long lo = 0, hi = np - 1;                       // radii ascend: first j with !(r_j < x_rmax), capped at np-1
+      while (lo < hi) { long long mid = lo + ((hi - lo) >> 1); if (w_r[mid] < x_rmax) lo = mid + 1; else hi = mid; }
+      const double r = w_r[lo], od = (double)(lo + 1) / (F43 * (r * r * r)), M_max = od * F43 * (r * r * r), V_max = M_max / x_rmax;
+      S[19] = V_max; S[20] = x_rmax; S[21] = x_r2;
+      S[54] = calc_cNFW(V_max, S[10] / R_vir);
+    }
+    return;
+  }
   {
     __shared__ long long sml[HB / 32];
     __shared__ double s_Mmax;
