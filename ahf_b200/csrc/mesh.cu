@@ -149,9 +149,10 @@ __global__ void __launch_bounds__(256) k_deposit_generic(const float4 *__restric
 constexpr int DT_T       = 16;
 constexpr int DT_H       = DT_T + 2;
 constexpr int DT_HH      = DT_H * DT_H * DT_H;
-constexpr int DT_CHUNK   = 4096;
+constexpr int DT_CHUNK   = 8192;         // particles per CTA (carry words make any count safe)
+constexpr int DT_SUB     = 512;          // particles per TMA stage = one per thread
 constexpr int DT_THREADS = 512;
-constexpr int DT_SMEM    = DT_CHUNK * 16 + 2 * DT_HH * 4 + 16;
+constexpr int DT_SMEM    = 2 * DT_SUB * 16 + 2 * DT_HH * 4 + 16;
 
 __global__ void k_tile_starts(const uint64_t *__restrict__ keys, int64_t n, int tbits, int ntile, int32_t *__restrict__ tstart)
 {
@@ -195,17 +196,35 @@ __global__ void k_lvl_tile_fill(const uint64_t *__restrict__ keys, const uint32_
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// tile word update: low word += v with a native shared atomic; the (rare) carry goes to the carry word through a
+// PREDICATED red.shared -- no branch, no convergence barrier in the hot loop
+__device__ __forceinline__ void tile_add32(uint32_t saddr, uint32_t v)
+{
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"(v) : "memory");
+  const uint32_t sum = old + v;
+  asm volatile("{\n .reg .pred p;\n setp.lt.u32 p, %0, %1;\n @p red.shared.add.u32 [%2], 1;\n}" ::"r"(sum), "r"(old), "r"(saddr + DT_HH * 4) : "memory");
+}
+__device__ __forceinline__ void tile_add64(uint32_t saddr, unsigned long long v)
+{
+  const uint32_t lo = (uint32_t)v;
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"(lo) : "memory");
+  const uint32_t hi = (uint32_t)(v >> 32) + ((old + lo < old) ? 1u : 0u);
+  asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %0, 0;\n @p red.shared.add.u32 [%1], %0;\n}" ::"r"(hi), "r"(saddr + DT_HH * 4) : "memory");
+}
+
 template <bool SPARSE>
-__global__ void __launch_bounds__(DT_THREADS, 2)
+__global__ void __launch_bounds__(DT_THREADS, 3)
 k_deposit_tiles(const float4 *__restrict__ pos4, const int32_t *__restrict__ tstart, const int2 *__restrict__ work, int L, int logL, int tbits,
                 unsigned long long *__restrict__ acc, const uint32_t *__restrict__ tlist, const int32_t *__restrict__ pcell, LV lvw,
                 const int32_t *__restrict__ nbr, float fxs)
 {
   extern __shared__ __align__(16) unsigned char dsm[];
-  float4   *sp   = reinterpret_cast<float4 *>(dsm);
-  uint32_t *tile = reinterpret_cast<uint32_t *>(dsm + DT_CHUNK * 16);          // low 32 bits of the 2^-31 fixed-point sums
+  float4   *sp   = reinterpret_cast<float4 *>(dsm);                            // two stages of DT_SUB positions
+  uint32_t *tile = reinterpret_cast<uint32_t *>(dsm + 2 * DT_SUB * 16);        // low 32 bits of the fixed-point sums
   uint32_t *tcar = tile + DT_HH;                                               // number of wrap-arounds of the low word
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(dsm + DT_CHUNK * 16 + 2 * DT_HH * 4);
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(dsm + 2 * DT_SUB * 16 + 2 * DT_HH * 4);   // two mbarriers
   const int2 wk = work[blockIdx.x];
   const int  t = wk.x, chunk = wk.y & 0x3fffffff;
   const bool sole = (wk.y & 0x40000000) != 0;        // the tile's only chunk: its inner cells are touched by nobody else
@@ -215,34 +234,41 @@ k_deposit_tiles(const float4 *__restrict__ pos4, const int32_t *__restrict__ tst
   uint32_t tx, ty, tz;
   hilbert_coords(SPARSE ? (uint64_t)tlist[t] : (uint64_t)t, (unsigned)tbits, tx, ty, tz);
   const int x0 = (int)tx * DT_T, y0 = (int)ty * DT_T, z0 = (int)tz * DT_T;
-  const uint32_t bar = smem_u32(mbar), dst = smem_u32(sp);
-  const uint32_t bytes = (uint32_t)np * 16u;
+  const uint32_t bar = smem_u32(mbar), dst = smem_u32(sp), tile_s = smem_u32(tile);
+  const int nsub = (np + DT_SUB - 1) / DT_SUB;
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar + 8));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  // TMA stage `sub` -> buffer sub&1 (cp.async.bulk global->shared, completion on the stage's mbarrier)
+  auto issue = [&](int sub) {
+    const int      cnt = min(DT_SUB, np - sub * DT_SUB);
+    const uint32_t bytes = (uint32_t)cnt * 16u, bb = bar + 8u * (sub & 1), dd = dst + (uint32_t)(sub & 1) * DT_SUB * 16u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bb), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(pos4 + s0), "r"(bytes), "r"(bar) : "memory");
-  }
-  for (int i = threadIdx.x; i < 2 * DT_HH; i += DT_THREADS) tile[i] = 0;  // overlaps the bulk copy
-  {
-    uint32_t done = 0;
-    while (!done) {
-      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                   : "=r"(done) : "r"(bar), "r"(0u) : "memory");
-    }
-  }
+                 ::"r"(dd), "l"(pos4 + s0 + (size_t)sub * DT_SUB), "r"(bytes), "r"(bb) : "memory");
+  };
+  if (threadIdx.x == 0) issue(0);
+  for (int i = threadIdx.x; i < 2 * DT_HH / 4; i += DT_THREADS) reinterpret_cast<uint4 *>(tile)[i] = make_uint4(0, 0, 0, 0);  // overlaps the first copy
   __syncthreads();
   const float fL = (float)L;
   const int   M = L - 1;
   const int   lane = threadIdx.x & 31;
-  for (int i0 = 0; i0 < np; i0 += DT_THREADS) {
-    const int  i = i0 + threadIdx.x;
+  for (int sub = 0; sub < nsub; sub++) {
+    if (threadIdx.x == 0 && sub + 1 < nsub) issue(sub + 1);                    // the other buffer was released by the barrier below
+    {
+      const uint32_t bb = bar + 8u * (sub & 1), parity = (uint32_t)(sub >> 1) & 1u;
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(bb), "r"(parity) : "memory");
+      }
+    }
+    const int  i = sub * DT_SUB + threadIdx.x;
     const bool valid = i < np;
-    const float4 q = valid ? sp[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 q = valid ? sp[(sub & 1) * DT_SUB + threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
     // ll(): cell = (unsigned long)(L * pos), out-of-range -> 0 (lltools.c:59-66); exact in float for power-of-two L
     const float fx = q.x * fL, fy = q.y * fL, fz = q.z * fL;
     int cx, cy, cz, pc = 0;
@@ -263,57 +289,51 @@ k_deposit_tiles(const float4 *__restrict__ pos4, const int32_t *__restrict__ tst
     const int lx = cx - x0, ly = cy - y0, lz = cz - z0;         // 0..T-1 inside the tile
     const bool intile = (unsigned)lx < (unsigned)DT_T && (unsigned)ly < (unsigned)DT_T && (unsigned)lz < (unsigned)DT_T;
     const int  cid = valid ? (intile ? ((lz * DT_T + ly) * DT_T + lx) : -2) : -1;
-    // clump cores: a whole warp in ONE cell -> sum the 27 terms across the warp (REDUX on two 16-bit limbs) and let
-    // one lane issue the shared-memory atomics instead of 32 lanes serialising on the same address
+    // clump cores: a whole warp in ONE cell -> sum the 27 terms across the warp (REDUX on three 16-bit limbs) and let one
+    // lane issue the shared-memory atomics instead of 32 lanes serialising on the same address.  (Grouping partial
+    // matches with match.any was measured: the MATCH + partial-mask REDUX cost more than the conflicts they remove.)
     const int  cid0 = __shfl_sync(0xffffffffu, cid, 0);
-    const bool allsame = __all_sync(0xffffffffu, cid == cid0);
-    if (allsame && cid >= 0) {
+    const bool grouped = __all_sync(0xffffffffu, cid == cid0) && cid0 >= 0;
+    const unsigned peers = 0xffffffffu;
+    const int      leader = 0;
+    const uint32_t cell0 = tile_s + 4u * (uint32_t)((lz * DT_H + ly) * DT_H + lx);     // shared address of the (k=0,j=0,a=0) word
+    if (grouped) {
 #pragma unroll
       for (int k = 0; k < 3; k++)
 #pragma unroll
         for (int j = 0; j < 3; j++) {
           const float wyz = wz[k] * wy[j] * fxs;
-          uint32_t *row = tile + ((lz + k) * DT_H + (ly + j)) * DT_H + lx;
 #pragma unroll
           for (int a = 0; a < 3; a++) {
             const unsigned long long v = __float2ull_rn(wyz * wx[a]);          // < 2^43
-            const uint32_t l0 = __reduce_add_sync(0xffffffffu, (uint32_t)(v & 0xffffu)), l1 = __reduce_add_sync(0xffffffffu, (uint32_t)((v >> 16) & 0xffffu)),
-                           l2 = __reduce_add_sync(0xffffffffu, (uint32_t)(v >> 32));
-            if (lane == 0) {
-              const unsigned long long tot = (unsigned long long)l0 + ((unsigned long long)l1 << 16) + ((unsigned long long)l2 << 32);
-              const uint32_t t32 = (uint32_t)tot, old = atomicAdd(row + a, t32);
-              const uint32_t cr = (uint32_t)(tot >> 32) + ((old + t32 < old) ? 1u : 0u);
-              if (cr) atomicAdd(row + a + DT_HH, cr);
-            }
+            const uint32_t l0 = __reduce_add_sync(peers, (uint32_t)(v & 0xffffu)), l1 = __reduce_add_sync(peers, (uint32_t)((v >> 16) & 0xffffu)),
+                           l2 = __reduce_add_sync(peers, (uint32_t)(v >> 32));
+            if (lane == leader && cid >= 0) tile_add64(cell0 + 4u * (uint32_t)((k * DT_H + j) * DT_H + a),
+                                      (unsigned long long)l0 + ((unsigned long long)l1 << 16) + ((unsigned long long)l2 << 32));
           }
         }
     } else if (valid && intile) {
+      if (!SPARSE || fxs <= 4294967296.0f) {         // S <= 32 (domain and first level): every term fits the low word
 #pragma unroll
-      for (int k = 0; k < 3; k++)
+        for (int k = 0; k < 3; k++)
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
-          const float wyz = wz[k] * wy[j] * fxs;
-          uint32_t *row = tile + ((lz + k) * DT_H + (ly + j)) * DT_H + lx;
-          if (fxs <= 4294967296.0f) {          // S <= 32 (domain and first level): every term fits the low word
-            const uint32_t v0 = __float2uint_rn(wyz * wx[0]), v1 = __float2uint_rn(wyz * wx[1]), v2 = __float2uint_rn(wyz * wx[2]);
-            const uint32_t o0 = atomicAdd(row, v0), o1 = atomicAdd(row + 1, v1), o2 = atomicAdd(row + 2, v2);
-            const bool c0 = o0 + v0 < o0, c1 = o1 + v1 < o1, c2 = o2 + v2 < o2;   // carries out of the low words (rare)
-            if (c0 | c1 | c2) {
-              if (c0) atomicAdd(row + DT_HH, 1u);
-              if (c1) atomicAdd(row + 1 + DT_HH, 1u);
-              if (c2) atomicAdd(row + 2 + DT_HH, 1u);
-            }
-          } else {
+          for (int j = 0; j < 3; j++) {
+            const float wyz = wz[k] * wy[j] * fxs;
 #pragma unroll
-            for (int a = 0; a < 3; a++) {
-              const unsigned long long v = __float2ull_rn(wyz * wx[a]);
-              const uint32_t lo = (uint32_t)v, old = atomicAdd(row + a, lo);
-              const uint32_t hi = (uint32_t)(v >> 32) + ((old + lo < old) ? 1u : 0u);
-              if (hi) atomicAdd(row + a + DT_HH, hi);
-            }
+            for (int a = 0; a < 3; a++) tile_add32(cell0 + 4u * (uint32_t)((k * DT_H + j) * DT_H + a), __float2uint_rn(wyz * wx[a]));
           }
-        }
-    } else if (valid) {
+      } else {
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+          for (int j = 0; j < 3; j++) {
+            const float wyz = wz[k] * wy[j] * fxs;
+#pragma unroll
+            for (int a = 0; a < 3; a++) tile_add64(cell0 + 4u * (uint32_t)((k * DT_H + j) * DT_H + a), __float2ull_rn(wyz * wx[a]));
+          }
+      }
+    }
+    if (valid && !intile) {
       // the particle's cell is not in this tile (coordinate clamp of ll()): straight to the global accumulators
 #pragma unroll
       for (int k = 0; k < 3; k++)
@@ -327,21 +347,27 @@ k_deposit_tiles(const float4 *__restrict__ pos4, const int32_t *__restrict__ tst
             if (tgt >= 0) atomicAdd(&acc[tgt], __float2ull_rn(wz[k] * wy[j] * fxs * wx[a]));
           }
     }
+    __syncthreads();                                   // everybody is done with this stage's buffer
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < DT_HH; i += DT_THREADS) {
-    const uint32_t v = tile[i], cr = tcar[i];
-    if ((v | cr) == 0) continue;
-    const int hx = i % DT_H, hy = (i / DT_H) % DT_H, hz = i / (DT_H * DT_H);
-    const int x = (x0 + hx - 1) & M, y = (y0 + hy - 1) & M, z = (z0 + hz - 1) & M;
-    const unsigned long long val = ((unsigned long long)cr << 32) | v;          // already in the level's 2^-S units
-    if (SPARSE) {
-      const int tgt = lv_lookup(lvw, x, y, z);         // particles sit on interior nodes: every touched cell exists
-      if (tgt >= 0) atomicAdd(&acc[tgt], val);
-    } else {
-      unsigned long long *dstp = &acc[(((size_t)z << logL | y) << logL) | x];
-      const bool inner = hx >= 2 && hx <= DT_T - 1 && hy >= 2 && hy <= DT_T - 1 && hz >= 2 && hz <= DT_T - 1;
-      if (sole && inner) *dstp = val; else atomicAdd(dstp, val);
+  // flush: thread = one (hx,hy) column of the tile, marching in z (no div/mod, constant strides)
+  if (threadIdx.x < DT_H * DT_H) {
+    const int hx = threadIdx.x % DT_H, hy = threadIdx.x / DT_H;
+    const int x = (x0 + hx - 1) & M, y = (y0 + hy - 1) & M;
+    const bool inxy = hx >= 2 && hx <= DT_T - 1 && hy >= 2 && hy <= DT_T - 1;
+#pragma unroll 2
+    for (int hz = 0; hz < DT_H; hz++) {
+      const int i = (hz * DT_H + hy) * DT_H + hx;
+      const uint32_t v = tile[i], cr = tcar[i];
+      if ((v | cr) == 0) continue;
+      const int z = (z0 + hz - 1) & M;
+      const unsigned long long val = ((unsigned long long)cr << 32) | v;          // already in the level's 2^-S units
+      if (SPARSE) {
+        const int tgt = lv_lookup(lvw, x, y, z);         // particles sit on interior nodes: every touched cell exists
+        if (tgt >= 0) atomicAdd(&acc[tgt], val);
+      } else {
+        unsigned long long *dstp = &acc[(((size_t)z << logL | y) << logL) | x];
+        if (sole && inxy && hz >= 2 && hz <= DT_T - 1) *dstp = val; else atomicAdd(dstp, val);
+      }
     }
   }
 }
