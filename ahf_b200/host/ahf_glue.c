@@ -1,0 +1,179 @@
+/*
+ * ahf_glue.c -- host side of the drop-in, in the reference's own language (C99).
+ *
+ * Compiled TOGETHER WITH the unmodified reference sources (NegriAndrea/AHF) by build_dropin.sh; nothing of the
+ * reference is copied or edited: the reference translation units that contain the path's call sites are compiled with
+ * `-Dcallee=ahfb200_callee`, which lands the calls in this file, and this file calls libahfgpu.so (include/ahfgpu.h).
+ *
+ *   src/main.c:343-356        key loop + qsort            -> ahfb200_calcKey (stub) + ahfb200_qsort  -> ahfgpu_sfc_sort_particles
+ *   src/libahf/ahf_halos.c:504-510   OpenMP halo loop     -> ahfb200_constructHalo (collects the HALO pointers)
+ *                                                            + ahfb200_fprintf (first serial statement after the loop)
+ *                                                            -> ahfgpu_construct_halos / ahfgpu_halo_fetch -> HALO, c_profile arrays
+ * The mesh stage (src/main.c:616-648) still runs the reference's CPU code in this build (the device hierarchy is checked
+ * against it level by level in tests/); everything else -- readers, ahf_gridinfo, tree, subhalo re-hash, writers -- is the
+ * reference, so the catalogues come out in AHF's own formats.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <stdarg.h>
+#include <stddef.h>
+#include <string.h>
+#include <omp.h>
+
+#include "common.h"
+#include "param.h"
+#include "tdef.h"
+#include "libutility/utility.h"
+#include "ahfgpu.h"
+
+extern double r_fac, x_fac, v_fac, m_fac, rho_fac, phi_fac, Hubble;      /* src/libahf/ahf_halos.c:163 */
+
+static ahfgpu_ctx *G = NULL;
+
+static void die(const char *what)
+{
+  fprintf(stderr, "ahf_glue: %s: %s\n", what, ahfgpu_last_error());
+  common_terminate(EXIT_FAILURE);
+}
+
+static void fill_params(ahfgpu_params *p)
+{
+  memset(p, 0, sizeof(*p));
+  p->device = 0;
+  p->lgrid_dom = simu.NGRID_DOM; p->lgrid_max = simu.NGRID_MAX > (1 << 21) ? (1 << 21) : simu.NGRID_MAX;
+  p->nth_dom = simu.Nth_dom; p->nth_ref = simu.Nth_ref; p->min_part = simu.AHF_MINPART; p->vesc_tune = simu.AHF_VTUNE;
+  p->r_fac = r_fac; p->x_fac = x_fac; p->v_fac = v_fac; p->m_fac = m_fac; p->rho_fac = rho_fac; p->phi_fac = phi_fac;
+  p->hubble = Hubble; p->ovlim = global.ovlim; p->rho_vir = global.rho_vir;
+}
+
+static void ensure_ctx(void)
+{
+  ahfgpu_params p;
+  if (G) return;
+  fill_params(&p);
+  if (ahfgpu_init(&G, &p)) die("ahfgpu_init");
+}
+
+/* ---- K: src/main.c:343-356 ------------------------------------------------------------------------------- */
+sfc_key_t ahfb200_calcKey(sfc_curve_t ctype, double x, double y, double z, uint32_t bits)
+{
+  (void)ctype; (void)x; (void)y; (void)z; (void)bits;
+  return 0;                                   /* keys are produced by the device sort below */
+}
+
+void ahfb200_qsort(void *base, size_t n, size_t sz, int (*cmp)(const void *, const void *))
+{
+  if (base == (void *)global_info.fst_part && sz == sizeof(part)) {
+    ensure_ctx();
+    if (ahfgpu_sfc_sort_particles(G, base, (uint64_t)n, (uint32_t)sizeof(part), (int32_t)offsetof(part, pos), (int32_t)offsetof(part, mom),
+                                  (int32_t)offsetof(part, sfckey), (int32_t)offsetof(part, id),
+#ifdef MULTIMASS
+                                  (int32_t)offsetof(part, weight),
+#else
+                                  -1,
+#endif
+#ifdef GAS_PARTICLES
+                                  (int32_t)offsetof(part, u)
+#else
+                                  -1
+#endif
+                                  )) die("ahfgpu_sfc_sort_particles");
+    return;
+  }
+  qsort(base, n, sz, cmp);
+}
+
+/* ---- H: src/libahf/ahf_halos.c:504-510 ------------------------------------------------------------------- */
+static HALO **pend = NULL;
+static long   npend = 0, cappend = 0;
+
+void ahfb200_constructHalo(HALO *h)
+{
+#pragma omp critical(ahfb200_pend)
+  {
+    if (npend == cappend) { cappend = cappend ? 2 * cappend : 1024; pend = realloc(pend, cappend * sizeof(HALO *)); }
+    pend[npend++] = h;
+  }
+}
+
+static int cmp_ptr(const void *a, const void *b)
+{
+  const HALO *x = *(HALO *const *)a, *y = *(HALO *const *)b;
+  return (x < y) ? -1 : (x > y);
+}
+
+static void flush_halos(void)
+{
+  long          i, k, nh = npend;
+  double       *ctr, *rad, *scal, *prof;
+  int64_t      *seed, *moff, *mem, *poff, nmem = 0, nbin = 0;
+  ahfgpu_params p;
+  if (nh == 0) return;
+  npend = 0;
+  if (getenv("AHFB200_VERBOSE")) fprintf(stderr, "ahf_glue: constructing %ld haloes on the device\n", nh);
+  qsort(pend, nh, sizeof(HALO *), cmp_ptr);           /* halos[] index order */
+  ensure_ctx();
+  fill_params(&p);
+  if (ahfgpu_set_params(G, &p)) die("ahfgpu_set_params");
+  ctr = malloc(3 * nh * sizeof(double)); rad = malloc(nh * sizeof(double)); seed = malloc(nh * sizeof(int64_t));
+  for (i = 0; i < nh; i++) {
+    ctr[3 * i] = pend[i]->pos.x; ctr[3 * i + 1] = pend[i]->pos.y; ctr[3 * i + 2] = pend[i]->pos.z;
+    rad[i] = pend[i]->gatherRad; seed[i] = (int64_t)pend[i]->npart;
+  }
+  if (ahfgpu_construct_halos(G, nh, ctr, rad, seed)) die("ahfgpu_construct_halos");
+  if (ahfgpu_halo_sizes(G, &nmem, &nbin)) die("ahfgpu_halo_sizes");
+  scal = malloc(nh * AHFGPU_NSCAL * sizeof(double)); moff = malloc((nh + 1) * sizeof(int64_t)); poff = malloc((nh + 1) * sizeof(int64_t));
+  mem = malloc((nmem > 0 ? nmem : 1) * sizeof(int64_t)); prof = malloc((nbin > 0 ? nbin : 1) * AHFGPU_NPROFCOL * sizeof(double));
+  if (ahfgpu_halo_fetch(G, scal, moff, mem, poff, prof)) die("ahfgpu_halo_fetch");
+  for (i = 0; i < nh; i++) {
+    HALO   *h = pend[i];
+    double *s = scal + (size_t)AHFGPU_NSCAL * i;
+    if (seed[i] == 0) continue;                        /* ahf_halos_sfc.c:122 */
+    h->nll = 0; h->ll = NULL;
+    h->npart = (unsigned long)s[9];
+    h->ipart = (h->npart > 0) ? malloc(h->npart * sizeof(unsigned long)) : NULL;     /* freed with free(), ahf_halos.c:897 */
+    for (k = 0; k < (long)h->npart; k++) h->ipart[k] = (unsigned long)mem[moff[i] + k];
+    if ((long)s[5] >= simu.AHF_MINPART) {              /* rem_outsideRvir ran at least once (ahf_halos.c:3696) */
+      h->M_vir = s[10]; h->R_vir = s[11]; h->ovdens = s[12]; h->Phi0 = s[13];
+    }
+    if ((long)h->npart >= simu.AHF_MINPART) {
+      int     nb = (int)s[57], b;
+      double *pr = prof + (size_t)AHFGPU_NPROFCOL * poff[i];
+      c_profile(h, nb);                                /* alloc_struct.c:614; freed by dest_profile */
+      h->vel.x = s[14]; h->vel.y = s[15]; h->vel.z = s[16]; h->sigV = s[17]; h->v_esc2 = s[18]; h->V2_max = s[19];
+      h->R_max = s[20]; h->r2 = s[21]; h->lambda = s[22]; h->lambdaE = s[23]; h->Ekin = s[24]; h->Epot = s[25]; h->SurfP = s[26];
+      h->pos_com.x = s[27]; h->pos_com.y = s[28]; h->pos_com.z = s[29]; h->com_offset = s[30];
+      h->pos_mbp.x = s[31]; h->pos_mbp.y = s[32]; h->pos_mbp.z = s[33]; h->vel_mbp.x = s[34]; h->vel_mbp.y = s[35]; h->vel_mbp.z = s[36];
+      h->mbp_offset = s[37]; h->AngMom.x = s[38]; h->AngMom.y = s[39]; h->AngMom.z = s[40];
+      h->axis.x = s[41]; h->axis.y = s[42]; h->axis.z = s[43];
+      h->E1.x = s[44]; h->E1.y = s[45]; h->E1.z = s[46]; h->E2.x = s[47]; h->E2.y = s[48]; h->E2.z = s[49];
+      h->E3.x = s[50]; h->E3.y = s[51]; h->E3.z = s[52];
+      h->fMhires = s[53]; h->cNFW = s[54]; h->cR1 = s[55]; h->R1 = s[56];
+      for (b = 0; b < nb; b++) {
+#define PR(col) pr[(col) * nb + b]
+        h->prof.npart[b] = (unsigned long)PR(0); h->prof.r[b] = PR(1); h->prof.nvpart[b] = PR(2); h->prof.ovdens[b] = PR(3);
+        h->prof.dens[b] = PR(4); h->prof.v2_circ[b] = PR(5); h->prof.v_esc2[b] = PR(6); h->prof.sig_v[b] = PR(7);
+        h->prof.Ekin[b] = PR(8); h->prof.Epot[b] = PR(9); h->prof.Lx[b] = PR(10); h->prof.Ly[b] = PR(11); h->prof.Lz[b] = PR(12);
+        h->prof.axis1[b] = PR(13); h->prof.E1x[b] = PR(14); h->prof.E1y[b] = PR(15); h->prof.E1z[b] = PR(16);
+        h->prof.axis2[b] = PR(17); h->prof.E2x[b] = PR(18); h->prof.E2y[b] = PR(19); h->prof.E2z[b] = PR(20);
+        h->prof.axis3[b] = PR(21); h->prof.E3x[b] = PR(22); h->prof.E3y[b] = PR(23); h->prof.E3z[b] = PR(24);
+#undef PR
+      }
+    }
+  }
+  if (getenv("AHFB200_VERBOSE")) { long ok = 0; for (i = 0; i < nh; i++) ok += ((long)pend[i]->npart >= simu.AHF_MINPART); fprintf(stderr, "ahf_glue: %ld haloes with npart >= %d\n", ok, simu.AHF_MINPART); }
+  free(ctr); free(rad); free(seed); free(scal); free(moff); free(poff); free(mem); free(prof);
+}
+
+/* every fprintf of ahf_halos.c passes through here; the first one issued from serial code after the halo loop
+ * (ahf_halos.c:540, VERBOSE is on in define.h:20) triggers the batched device pass */
+int ahfb200_fprintf(FILE *f, const char *fmt, ...)
+{
+  va_list ap;
+  int     r;
+  if (npend > 0 && !omp_in_parallel()) flush_halos();
+  va_start(ap, fmt);
+  r = vfprintf(f, fmt, ap);
+  va_end(ap);
+  return r;
+}

@@ -1,0 +1,32 @@
+#!/bin/bash
+# Builds ahf_b200/host/_build/AHF-b200: the reference's own main() / startrun / readers / tree / writers (compiled from the
+# sources where they lie, unmodified, same flags as the reference's "Standard OpenMP" SYSTEM) with the hot-path call sites
+# redirected to libahfgpu.so through ahf_glue.c.  Only possible where the reference sources exist (not on the GPU box; the
+# binary travels with the repo snapshot).
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REPO="$(cd "$HERE/../.." && pwd)"
+REF="${AHF_REFERENCE_SRC:-/root/reference/src}"
+OUT="$HERE/_build"
+[ -d "$REF" ] || { echo "build_dropin.sh: $REF not present - keeping prebuilt $OUT" >&2; exit 0; }
+mkdir -p "$OUT/obj"
+CC="gcc -fopenmp -std=c99 -O2 -DWITH_OPENMP -DAHF -w -I$REF -I$REPO/include"
+pids=()
+for f in "$REF"/*.c "$REF"/lib*/*.c; do
+  base="$(basename "$(dirname "$f")")_$(basename "$f" .c)"
+  extra=""
+  case "$base" in
+    src_main)         extra="-Dsfc_curve_calcKey=ahfb200_calcKey -Dqsort=ahfb200_qsort" ;;
+    libahf_ahf_halos) extra="-U_FORTIFY_SOURCE -D_FORTIFY_SOURCE=0 -Dahf_halos_sfc_constructHalo=ahfb200_constructHalo -Dfprintf=ahfb200_fprintf" ;;   # fortify would turn fprintf into an inline wrapper
+  esac
+  $CC $extra -c "$f" -o "$OUT/obj/$base.o" &
+  pids+=($!)
+  if [ ${#pids[@]} -ge 8 ]; then wait "${pids[0]}"; pids=("${pids[@]:1}"); fi
+done
+wait
+$CC -c "$HERE/ahf_glue.c" -o "$OUT/ahf_glue.o"
+mv "$OUT/obj/src_main.o" "$OUT/"
+ar rcs "$OUT/libref.a" "$OUT"/obj/*.o
+gcc -fopenmp -o "$OUT/AHF-b200" "$OUT/src_main.o" "$OUT/ahf_glue.o" "$OUT/libref.a" -L"$REPO/ahf_b200" -lahfgpu -Wl,-rpath,'$ORIGIN/../..' -lm
+rm -rf "$OUT/obj" "$OUT/src_main.o" "$OUT/ahf_glue.o" "$OUT/libref.a"
+ls -la "$OUT"

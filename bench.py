@@ -43,7 +43,9 @@ def measured_peak_gbs():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock and throttle reasons during the timed region, sampled in-process through NVML (nvidia_ml_py) -- the same
+    counters `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` prints (B200_PROFILING.md), without
+    forking nvidia-smi five times a second next to the measurement."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
@@ -52,28 +54,38 @@ class ClockSampler(threading.Thread):
         self.reasons = set()
         self.sm_max = None
         self._halt = threading.Event()
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        if self.h is None:
+            return
+        nv = self.nv
+        masks = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0])); self.sm_max = float(out[1])
-                for nm, v in zip(names, out[2:6]):
-                    if "Active" in v and "Not" not in v:
-                        self.reasons.add(nm)
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, m in masks.items():
+                    if r & m:
+                        self.reasons.add(k)
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.05)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=5)
         med = statistics.median(self.samples) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        return {"sm_mhz": med, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(self.samples), "source": "nvml"}
 
 
 def run_reference_sample(n1d: int, seed: int, threads: int | None):
