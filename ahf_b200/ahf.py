@@ -96,6 +96,12 @@ def lib():
         L.ahfgpu_event_elapsed_ms.restype = C.c_double
         L.ahfgpu_event_elapsed_ms.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         L.ahfgpu_synchronize.argtypes = [C.c_void_p]
+        L.ahfgpu_device_ptr.restype = C.c_void_p
+        L.ahfgpu_device_ptr.argtypes = [C.c_void_p, C.c_char_p]
+        L.ahfgpu_set_global_count.argtypes = [C.c_void_p, C.c_uint64]
+        L.ahfgpu_set_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ahfgpu_adopt_sorted.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_int32]
+        L.ahfgpu_sfc_sort_device4.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_int32]
         L.ahfgpu_hilbert_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
         L.ahfgpu_build_amr.argtypes = [C.c_void_p]
         L.ahfgpu_amr_nlevels.argtypes = [C.c_void_p]

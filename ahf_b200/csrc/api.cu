@@ -35,6 +35,7 @@ void ahfgpu_ctx::stage_resolve()
 }
 void ahfgpu_ctx::free_particles()
 {
+  if (adopted) { pos4 = mom4 = nullptr; keys = nullptr; adopted = false; }
   ahf::dfree(pos4); ahf::dfree(mom4); ahf::dfree(keys); ahf::dfree(order);
   pos4 = mom4 = nullptr; keys = nullptr; order = nullptr; n = 0;
 }
@@ -163,6 +164,52 @@ int ahfgpu_sfc_sort_resident(ahfgpu_ctx *c)
   c->stage_reset();
   sfc_sort_resident(c, nullptr, nullptr);
   API_END
+}
+
+int ahfgpu_sfc_sort_device4(ahfgpu_ctx *c, const void *pos4_dev, const void *mom4_dev, uint64_t n, int32_t has_weight, int32_t has_u)
+{
+  API_BEGIN
+  if (!c || ((!pos4_dev || !mom4_dev) && n)) AHF_FAIL("null argument");
+  CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
+  c->stage_reset();
+  sfc_sort_device4(c, pos4_dev, mom4_dev, n, has_weight != 0, has_u != 0);
+  API_END
+}
+
+int ahfgpu_set_global_count(ahfgpu_ctx *c, uint64_t n_total)
+{
+  API_BEGIN
+  if (!c) AHF_FAIL("null ctx");
+  c->n_total = n_total;
+  API_END
+}
+
+int ahfgpu_set_allreduce(ahfgpu_ctx *c, ahfgpu_allreduce_fn fn, void *user)
+{
+  API_BEGIN
+  if (!c) AHF_FAIL("null ctx");
+  c->allreduce = fn; c->allreduce_user = user;
+  API_END
+}
+
+int ahfgpu_adopt_sorted(ahfgpu_ctx *c, const void *pos4_dev, const void *mom4_dev, const void *keys_dev, uint64_t n, int32_t has_weight, int32_t has_u)
+{
+  API_BEGIN
+  if (!c || ((!pos4_dev || !mom4_dev || !keys_dev) && n)) AHF_FAIL("null argument");
+  CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
+  c->free_halos(); c->free_levels(); c->free_particles();
+  c->pos4 = (float4 *)pos4_dev; c->mom4 = (float4 *)mom4_dev; c->keys = (uint64_t *)keys_dev; c->order = nullptr;
+  c->n = n; c->adopted = true; c->has_weight = has_weight != 0; c->has_u = has_u != 0;
+  API_END
+}
+
+void *ahfgpu_device_ptr(ahfgpu_ctx *c, const char *name)
+{
+  if (!c || !name) return nullptr;
+  if (!strcmp(name, "pos4")) return c->pos4;
+  if (!strcmp(name, "mom4")) return c->mom4;
+  if (!strcmp(name, "keys")) return c->keys;
+  return nullptr;
 }
 
 int ahfgpu_event_record(ahfgpu_ctx *c, int32_t slot)

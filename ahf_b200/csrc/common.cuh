@@ -103,6 +103,9 @@ struct ahfgpu_ctx {
   uint64_t *keys = nullptr;
   uint32_t *order = nullptr;    // input position of sorted particle i
   bool      has_weight = false, has_u = false;
+  bool      adopted = false;          // pos4/mom4/keys belong to the caller (ahfgpu_adopt_sorted)
+  uint64_t  n_total = 0;              // particles of the whole box when the box is split over several contexts (0: n)
+  ahfgpu_allreduce_fn allreduce = nullptr; void *allreduce_user = nullptr;
   // unsorted device copy kept by ahfgpu_upload_soa
   float    *in_pos = nullptr, *in_mom = nullptr, *in_w = nullptr, *in_u = nullptr;
   uint64_t  in_n = 0;
@@ -154,6 +157,7 @@ void sfc_sort_aos(ahfgpu_ctx *c, void *part, uint64_t n, uint32_t stride, int of
                   int off_id, int off_w, int off_u);
 void sfc_upload_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, const float *w, const float *u, uint64_t n);
 void sfc_sort_resident(ahfgpu_ctx *c, uint64_t *keys_out, uint32_t *order_out);
+void sfc_sort_device4(ahfgpu_ctx *c, const void *pos4_dev, const void *mom4_dev, uint64_t n, bool has_w, bool has_u);
 void sfc_keys_only(ahfgpu_ctx *c, const float *pos3, uint64_t n, uint32_t bits, uint64_t *keys_out);
 void radix_sort_pairs(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, uint64_t n,
                       int key_bits, uint64_t **keys_sorted, uint32_t **vals_sorted);

@@ -831,6 +831,12 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
     Stage sk(c, lv.dense ? "deposit_dom_kernel" : "deposit_ref_kernel", lv.npart_dep);
     LAUNCH(c, k_deposit_generic, nblk(lv.npart_dep, 256), 256, 0, c->pos4, lv.plist, lv.pcell, (uint64_t)lv.npart_dep, v, lv.nbr, acc.p, fxscale);
   }
+  if (c->allreduce) {
+    // several contexts share one box: sum the level's accumulators over all of them (exact: integers)
+    Stage sa(c, "allreduce", (int64_t)nc * 8);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (c->allreduce(c->allreduce_user, acc.p, (int64_t)nc) != 0) AHF_FAIL("all-reduce callback failed");
+  }
   LAUNCH(c, k_finish_dens, nblk(nc, 256), 256, 0, acc.p, lv.dens, nc, lv.masstopartdens / fxscale);
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
   acc.release();
@@ -858,7 +864,7 @@ void amr_build(ahfgpu_ctx *c)
   {
     Level d;
     d.L = par.lgrid_dom; d.ncell = d.L * d.L * d.L; d.dense = true;
-    d.masstopartdens = ((double)d.L * (double)d.L * (double)d.L) / (double)n;
+    d.masstopartdens = ((double)d.L * (double)d.L * (double)d.L) / (double)(c->n_total ? c->n_total : n);
     d.critdens = par.nth_dom * d.masstopartdens;
     alloc_cell_arrays(d);
     d.npart_dep = (int64_t)n;

@@ -283,6 +283,53 @@ void sfc_sort_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, const flo
   sfc_sort_resident(c, keys_out, order_out);
 }
 
+__global__ void k_keys_pos4(const float4 *__restrict__ pos4, uint64_t n, uint64_t *__restrict__ keys, uint32_t *__restrict__ idx)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = pos4[i];
+  keys[i] = hilbert_key_pos(p.x, p.y, p.z, 21);
+  idx[i]  = (uint32_t)i;
+}
+__global__ void k_gather4(const float4 *__restrict__ pin, const float4 *__restrict__ min_, const uint32_t *__restrict__ order, uint64_t n,
+                          float4 *__restrict__ pos4, float4 *__restrict__ mom4)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t o = order[i];
+  pos4[i] = pin[o]; mom4[i] = min_[o];
+}
+
+void sfc_sort_device4(ahfgpu_ctx *c, const void *pos4_dev, const void *mom4_dev, uint64_t n, bool has_w, bool has_u)
+{
+  if (n >= (1ull << 32)) AHF_FAIL("more than 2^32-1 particles per device are not supported");
+  alloc_particles(c, n);
+  c->has_weight = has_w; c->has_u = has_u;
+  DevBuf<uint64_t> k0, k1;
+  DevBuf<uint32_t> v0, v1;
+  k0.reserve(n); k1.reserve(n); v0.reserve(n); v1.reserve(n);
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  {
+    Stage st(c, "keys", (int64_t)n);
+    if (n) LAUNCH(c, k_keys_pos4, nb, 256, 0, (const float4 *)pos4_dev, n, k0.p, v0.p);
+  }
+  uint64_t *ks; uint32_t *vs;
+  {
+    Stage st(c, "sort", (int64_t)n);
+    radix_sort_pairs(c, k0.p, v0.p, k1.p, v1.p, n, 63, &ks, &vs);
+  }
+  {
+    Stage st(c, "gather", (int64_t)n);
+    if (n) LAUNCH(c, k_gather4, nb, 256, 0, (const float4 *)pos4_dev, (const float4 *)mom4_dev, vs, n, c->pos4, c->mom4);
+  }
+  CUDA_CHECK(cudaMallocAsync(&c->keys, (n ? n : 1) * sizeof(uint64_t), ahf::g_pool_stream));
+  CUDA_CHECK(cudaMallocAsync(&c->order, (n ? n : 1) * sizeof(uint32_t), ahf::g_pool_stream));
+  CUDA_CHECK(cudaMemcpyAsync(c->keys, ks, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(c->order, vs, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  k0.release(); k1.release(); v0.release(); v1.release();
+}
+
 void sfc_sort_aos(ahfgpu_ctx *c, void *part, uint64_t n, uint32_t stride, int off_pos, int off_mom, int off_key, int off_id,
                   int off_w, int off_u)
 {

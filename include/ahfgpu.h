@@ -118,6 +118,26 @@ int  ahfgpu_halo_sizes(ahfgpu_ctx *ctx, int64_t *total_members, int64_t *total_b
 int  ahfgpu_halo_fetch(ahfgpu_ctx *ctx, double *scal, int64_t *member_offset, int64_t *members,
                        int64_t *prof_offset, double *prof);
 
+/* ---- several GPUs working on ONE box: particles are split into SFC slabs, one per process/GPU; every process
+ * holds the full (small) cell structure of every level, deposits its own particles and the level accumulators are summed
+ * over the processes through a caller-supplied all-reduce (NCCL via torch.distributed in ahf_b200/multigpu.py) -- the
+ * ghost-cell exchange of the reference's MPI mode (src/comm.c:324ff duplicates boundary PARTICLES instead) generalised to
+ * a sum of the u64 fixed-point accumulators, which is exact and order independent.
+ *   ahfgpu_set_global_count : N of the whole box (masstopartdens = L^3 / N, generate_grids.c:66-69)
+ *   ahfgpu_set_allreduce    : fn(user, device pointer, number of uint64) must sum the buffer over all processes in place
+ *   ahfgpu_adopt_sorted     : make caller-owned DEVICE arrays (float4 pos+weight, float4 mom+u, u64 keys; key sorted) the
+ *                             resident particle set, e.g. the all-gathered box for the halo pass (not freed by the library)
+ *   ahfgpu_device_ptr       : device pointers of the resident sorted set ("pos4","mom4","keys") for the exchange         */
+/*   ahfgpu_sfc_sort_device4 : keys + sort + gather of particles that already sit on the device as float4 (x,y,z,weight) /
+ *                             float4 (px,py,pz,u) arrays, e.g. what a rank received in the slab exchange               */
+typedef int (*ahfgpu_allreduce_fn)(void *user, void *dev_u64, int64_t count);
+int  ahfgpu_sfc_sort_device4(ahfgpu_ctx *ctx, const void *pos4_dev, const void *mom4_dev, uint64_t n, int32_t has_weight, int32_t has_u);
+int  ahfgpu_set_global_count(ahfgpu_ctx *ctx, uint64_t n_total);
+int  ahfgpu_set_allreduce(ahfgpu_ctx *ctx, ahfgpu_allreduce_fn fn, void *user);
+int  ahfgpu_adopt_sorted(ahfgpu_ctx *ctx, const void *pos4_dev, const void *mom4_dev, const void *keys_dev, uint64_t n,
+                         int32_t has_weight, int32_t has_u);
+void *ahfgpu_device_ptr(ahfgpu_ctx *ctx, const char *name);
+
 /* ---- measurement hooks (bench.py): milliseconds of the last call, by stage, measured with CUDA events on
  * the library's stream.  names: "h2d","keys","sort","gather","d2h","deposit","flag","refine","relink",
  * "halo_gather","halo_sort","halo_unbind","halo_profiles", ... ; returns <0 for an unknown name.             */
