@@ -65,11 +65,12 @@ class SlabBox:
         pos4 = dev_tensor(L.ahfgpu_device_ptr(g._h, b"pos4"), (n_local, 4), "<f4", dev)
         mom4 = dev_tensor(L.ahfgpu_device_ptr(g._h, b"mom4"), (n_local, 4), "<f4", dev)
         keys = dev_tensor(L.ahfgpu_device_ptr(g._h, b"keys"), (n_local,), "<i8", dev)       # 63-bit keys: non-negative as int64
+        if self.world == 1:
+            self.n_total = n_local
+            return
         tot = torch.tensor([n_local], device=dev, dtype=torch.int64)
         dist.all_reduce(tot)
         self.n_total = int(tot.item())
-        if self.world == 1:
-            return
         # splitters from regular samples of every rank's sorted keys
         ns = 4096
         idx = torch.linspace(0, max(n_local - 1, 0), ns, device=dev).long()

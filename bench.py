@@ -34,6 +34,29 @@ METRIC = "particles/sec through the hot path (keys+sort, TSC deposit+flag+refine
 UNIT = "particles/s"
 
 
+def ncu_traffic_bytes(n1d: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the domain deposit kernel, from the committed
+    `ncu --set full` summary (profiles/); only valid for the configuration that was profiled (256^3)."""
+    if n1d != 256:
+        return None
+    import glob, re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_deposit_tiles_ncu_full.txt")))
+    if not files:
+        return None
+    rd = wr = None
+    for line in open(files[-1]):
+        if line.startswith("## launch id") and rd is not None:
+            break
+        m = re.match(r"\s+dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", line)
+        if m:
+            v = float(m.group(2)) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[m.group(3)]
+            if m.group(1) == "read":
+                rd = v
+            else:
+                wr = v
+    return None if rd is None or wr is None else rd + wr
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -123,6 +146,55 @@ def run_port_sample(n1d: int, seed: int):
     return box.npart / dt, dict(path_s=dt, npart=box.npart)
 
 
+def bench_slab(args, rank, world, local_rank, config):
+    """ONE box over all ranks (strong scaling): time = exchange + sort, mesh with all-reduce, all-gather + halo pass."""
+    import torch
+    import torch.distributed as dist
+    from ahf_b200 import ahf, multigpu, synth
+    box = synth.make_box(args.n1d, seed=43)
+    n = box.npart
+    b = (np.arange(world + 1) * n) // world
+    pos_l, mom_l = np.ascontiguousarray(box.pos[b[rank]:b[rank + 1]]), np.ascontiguousarray(box.mom[b[rank]:b[rank + 1]])
+    c, r, seed = synth.halo_seeds(box)
+    par = ahf.make_params(boxsize=box.boxsize, pmass=box.pmass, lgrid_dom=args.n1d, device=local_rank)
+    sb = multigpu.SlabBox(par, rank, world, local_rank)
+
+    def step():
+        sb.distribute(pos_l, mom_l)
+        sb.build_amr()
+        sb.gather_box()
+        return sb.construct_halos(c, r, seed)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(args.steps):
+        scal = step()
+    sb.g.synchronize(); sb.gh.synchronize(); torch.cuda.synchronize(); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    if rank == 0:
+        config = dict(config, workload=config["workload"].replace("seed 43+rank", "seed 43"), n_particles_total=n,
+                      parallelism=f"one box, {world} SFC slabs: all-to-all exchange, NCCL all-reduce of level accumulators, all-gather for the halo pass")
+        config.pop("n_particles_per_gpu", None)
+        print(json.dumps({"metric": METRIC, "value": n / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "f32 particles, u32/u64 fixed-point deposit, f64 halo arithmetic", "data": "synthetic", "config": config,
+                          "mode": "slab", "note": "host->device upload of the rank's file-order slice is inside the timed step",
+                          "levels": sb.g.nlevels(), "halos_ge_minpart": int((scal[:, 9] >= par.min_part).sum())}))
+    sb.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -133,6 +205,9 @@ def main():
     ap.add_argument("--ref-n1d", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print the per-stage table to stderr")
+    ap.add_argument("--mode", default="boxes", choices=["boxes", "slab"],
+                    help="N>1: 'boxes' = one independent box per GPU (weak, no collective; default); 'slab' = ONE box of --n1d^3 particles split "
+                         "into SFC slabs over the GPUs (all-to-all exchange, NCCL all-reduce of the level accumulators, all-gather for the halo pass)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -184,6 +259,8 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ahf.build()
+    if args.mode == "slab":
+        return bench_slab(args, rank, world, local_rank, config)
     box = synth.make_box(args.n1d, seed=43 + rank)
     n = box.npart
     centres, rad, seednp = synth.halo_seeds(box)
@@ -269,7 +346,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"kernel": "TSC deposit, domain level (k_deposit_*)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": ncu_traffic_bytes(args.n1d), "peak_source": peak_src,
                      "algorithmic_bytes": dep_bytes, "kernel_ms": st["deposit_dom_kernel"]},
         "stages_ms": {k: v for k, v in st.items() if k not in ("deposit_particles", "halo_gathered")},
         "throughput": {"deposit_pps": st["deposit_particles"] / (st["deposit"] * 1e-3), "deposit_particles_all_levels": st["deposit_particles"],
