@@ -9,9 +9,11 @@
  *   src/libahf/ahf_halos.c:504-510   OpenMP halo loop     -> ahfb200_constructHalo (collects the HALO pointers)
  *                                                            + ahfb200_fprintf (first serial statement after the loop)
  *                                                            -> ahfgpu_construct_halos / ahfgpu_halo_fetch -> HALO, c_profile arrays
- * The mesh stage (src/main.c:616-648) still runs the reference's CPU code in this build (the device hierarchy is checked
- * against it level by level in tests/); everything else -- readers, ahf_gridinfo, tree, subhalo re-hash, writers -- is the
- * reference, so the catalogues come out in AHF's own formats.
+ *   src/main.c:616-648        gen_domgrids / ll / zero_dens / assign_npart / gen_AMRhierarchy
+ *                                                         -> ahfb200_gen_domgrids -> ahfgpu_build_amr + rebuild of the reference's quads
+ *                                                            (only in the AHF-b200 build; AHF-b200-kh keeps the CPU mesh)
+ * Everything else -- readers, ahf_gridinfo, tree, subhalo re-hash, writers -- is the reference, so the catalogues come out in
+ * AHF's own formats.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -24,6 +26,7 @@
 #include "param.h"
 #include "tdef.h"
 #include "libutility/utility.h"
+#include "libamr_serial/amr_serial.h"
 #include "ahfgpu.h"
 
 extern double r_fac, x_fac, v_fac, m_fac, rho_fac, phi_fac, Hubble;      /* src/libahf/ahf_halos.c:163 */
@@ -82,6 +85,135 @@ void ahfb200_qsort(void *base, size_t n, size_t sz, int (*cmp)(const void *, con
   }
   qsort(base, n, sz, cmp);
 }
+
+/* ---- M: src/main.c:616-648 ------------------------------------------------------------------------------
+ * gen_domgrids + ll + zero_dens + assign_npart + gen_AMRhierarchy  ->  ahfgpu_build_amr, then the device hierarchy is
+ * rebuilt as the reference's own gridls / pquad / cquad / nquad / node structures (tdef.h:110-235) for the host code that
+ * still consumes them (ahf_gridinfo, RefCentre ...).  The per-level cell list with run flags (ahfgpu_amr_level_get) carries
+ * exactly the information of the quads; node particle lists are rebuilt in the reference's order (head insertion: a node of
+ * an even level lists its particles by descending offset, of an odd level by ascending offset -- what ll()/relink() leave).
+ * Everything is allocated with the reference's c_* allocators so that free_grid() (ahf_halos.c:483) works.             */
+static void build_level_quads(gridls *g, int64_t nc, const int32_t *x, const int32_t *y, const int32_t *z, const float *dens,
+                              const uint8_t *rf, nptr *nodeptr)
+{
+  int64_t c = 0;
+  pqptr   pq = NULL, pq_tail = NULL;
+  long    npq = 0;
+  while (c < nc) {
+    /* one z-run (pquad): planes until a "last plane" flag */
+    int64_t c_run = c, nplanes = 0, cc = c;
+    pqptr   newpq = c_pquad(1);
+    /* count planes of the run */
+    while (cc < nc) {
+      int32_t zz = z[cc];
+      int     lastplane = (rf[cc] & 32) != 0;
+      while (cc < nc && z[cc] == zz) cc++;
+      nplanes++;
+      if (lastplane) break;
+    }
+    newpq->z = z[c_run]; newpq->length = (int)nplanes; newpq->loc = c_cquad(nplanes); newpq->next = NULL;
+    if (pq_tail) pq_tail->next = newpq; else pq = newpq;
+    pq_tail = newpq; npq++;
+    for (int64_t ip = 0; ip < nplanes; ip++) {
+      /* plane: cells [c, cend) */
+      int64_t cend = c;
+      cqptr   cq = newpq->loc + ip;
+      int     first_yrun = 1;
+      while (cend < nc && z[cend] == z[c]) cend++;
+      while (c < cend) {
+        /* one y-run (cquad): rows until a "last row" flag */
+        int64_t r = c, nrows = 0;
+        while (r < cend) {
+          int32_t yy = y[r];
+          int     lastrow = (rf[r] & 8) != 0;
+          while (r < cend && y[r] == yy) r++;
+          nrows++;
+          if (lastrow) break;
+        }
+        if (!first_yrun) { cq->next = c_cquad(1); cq = cq->next; }
+        first_yrun = 0;
+        cq->y = y[c]; cq->length = (int)nrows; cq->loc = c_nquad(nrows); cq->next = NULL;
+        for (int64_t ir = 0; ir < nrows; ir++) {
+          int64_t rend = c;
+          nqptr   nq = cq->loc + ir;
+          int     first_xrun = 1;
+          while (rend < cend && y[rend] == y[c]) rend++;
+          while (c < rend) {
+            /* one x-run (nquad): nodes until a "last node" flag */
+            int64_t e = c;
+            while (e < rend && !(rf[e] & 2)) e++;
+            e++;                                            /* include the flagged last node */
+            if (!first_xrun) { nq->next = c_nquad(1); nq = nq->next; }
+            first_xrun = 0;
+            nq->x = x[c]; nq->length = (int)(e - c); nq->loc = c_node(e - c); nq->next = NULL;
+            for (int64_t k = c; k < e; k++) { nq->loc[k - c].dens = dens[k]; nq->loc[k - c].ll = NULL; nodeptr[k] = nq->loc + (k - c); }
+            c = e;
+          }
+        }
+      }
+    }
+  }
+  g->pquad = pq;
+  g->no_pquad = npq;
+  g->pquad_array = (pqptr *)calloc(npq > 0 ? npq : 1, sizeof(pqptr));
+  { long i = 0; for (pqptr q = pq; q != NULL; q = q->next) g->pquad_array[i++] = q; }
+}
+
+gridls *ahfb200_gen_domgrids(int *no_grids)
+{
+  ahfgpu_params p;
+  gridls       *gl;
+  int           nlev, l;
+  uint64_t      n = global_info.no_part, i;
+  int8_t       *owner;
+  int32_t      *cell_of;
+  nptr        **nodeptr;
+  if (simu.NGRID_MIN != simu.NGRID_DOM) { fprintf(stderr, "ahf_glue: NGRID_MIN != NGRID_DOM is not supported\n"); common_terminate(EXIT_FAILURE); }
+  ensure_ctx();
+  fill_params(&p);
+  if (ahfgpu_set_params(G, &p)) die("ahfgpu_set_params");
+  if (ahfgpu_build_amr(G)) die("ahfgpu_build_amr");
+  nlev = ahfgpu_amr_nlevels(G);
+  gl = (gridls *)calloc(nlev, sizeof(gridls));
+  nodeptr = (nptr **)calloc(nlev, sizeof(nptr *));
+  for (l = 0; l < nlev; l++) {
+    int64_t  io[4]; double dd[2];
+    int32_t *x, *y, *z; float *dens; uint8_t *rf;
+    gridls  *g = gl + l;
+    if (ahfgpu_amr_level_header(G, l, io, dd)) die("ahfgpu_amr_level_header");
+    x = malloc(io[1] * 4); y = malloc(io[1] * 4); z = malloc(io[1] * 4); dens = malloc(io[1] * 4); rf = malloc(io[1]);
+    nodeptr[l] = malloc(io[1] * sizeof(nptr));
+    if (ahfgpu_amr_level_get(G, l, x, y, z, dens, rf, NULL, NULL, NULL)) die("ahfgpu_amr_level_get");
+    g->l1dim = (long unsigned)io[0]; g->spacing = 1.0 / (double)io[0]; g->spacing2 = g->spacing * g->spacing;
+    g->critdens = dd[0]; g->masstopartdens = dd[1];
+    g->masstodens = dd[1] * (double)simu.no_part / simu.no_vpart;          /* generate_grids.c:66-69 */
+    g->size.no_part = (long unsigned)io[2]; g->size.no_nodes = (long unsigned)io[1];
+    g->timecounter = global.super_t; g->next = (l < nlev - 1) ? TRUE : FALSE;
+    build_level_quads(g, io[1], x, y, z, dens, rf, nodeptr[l]);
+    free(x); free(y); free(z); free(dens); free(rf);
+  }
+  /* node particle lists */
+  owner = malloc(n); cell_of = malloc((size_t)nlev * n * sizeof(int32_t));
+  if (ahfgpu_amr_particle_levels(G, owner, cell_of, nlev)) die("ahfgpu_amr_particle_levels");
+  for (i = 0; i < n; i++) global_info.fst_part[i].ll = NULL;
+  for (l = 0; l < nlev; l++) {
+    if ((l & 1) == 0) {           /* descending list: head-insert in ascending order */
+      for (i = 0; i < n; i++) if (owner[i] == l) { nptr nd = nodeptr[l][cell_of[(size_t)l * n + i]]; partptr q = global_info.fst_part + i; q->ll = nd->ll; nd->ll = q; }
+    } else {                      /* ascending list: head-insert in descending order */
+      for (i = n; i-- > 0;) if (owner[i] == l) { nptr nd = nodeptr[l][cell_of[(size_t)l * n + i]]; partptr q = global_info.fst_part + i; q->ll = nd->ll; nd->ll = q; }
+    }
+  }
+  for (l = 0; l < nlev; l++) free(nodeptr[l]);
+  free(nodeptr); free(owner); free(cell_of);
+  global.dom_grid = gl; global.domgrid_no = 0;
+  *no_grids = nlev;
+  return gl;
+}
+
+void    ahfb200_ll(long unsigned npart, partptr fst_part, gridls *cur_grid) { (void)npart; (void)fst_part; (void)cur_grid; }
+void    ahfb200_zero_dens(gridls *g) { (void)g; }
+boolean ahfb200_assign_npart(gridls *g) { (void)g; return TRUE; }
+boolean ahfb200_gen_AMRhierarchy(gridls **grid_list, int *no_grids) { (void)grid_list; (void)no_grids; return FALSE; }
 
 /* ---- H: src/libahf/ahf_halos.c:504-510 ------------------------------------------------------------------- */
 static HALO **pend = NULL;

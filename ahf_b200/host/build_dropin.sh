@@ -9,6 +9,8 @@ REPO="$(cd "$HERE/../.." && pwd)"
 REF="${AHF_REFERENCE_SRC:-/root/reference/src}"
 OUT="$HERE/_build"
 [ -d "$REF" ] || { echo "build_dropin.sh: $REF not present - keeping prebuilt $OUT" >&2; exit 0; }
+build_one() {
+name="$1"; mainflags="$2"
 mkdir -p "$OUT/obj"
 CC="gcc -fopenmp -std=c99 -O2 -DWITH_OPENMP -DAHF -w -I$REF -I$REPO/include"
 pids=()
@@ -16,7 +18,7 @@ for f in "$REF"/*.c "$REF"/lib*/*.c; do
   base="$(basename "$(dirname "$f")")_$(basename "$f" .c)"
   extra=""
   case "$base" in
-    src_main)         extra="-Dsfc_curve_calcKey=ahfb200_calcKey -Dqsort=ahfb200_qsort" ;;
+    src_main)         extra="-Dsfc_curve_calcKey=ahfb200_calcKey -Dqsort=ahfb200_qsort $mainflags" ;;
     libahf_ahf_halos) extra="-U_FORTIFY_SOURCE -D_FORTIFY_SOURCE=0 -Dahf_halos_sfc_constructHalo=ahfb200_constructHalo -Dfprintf=ahfb200_fprintf" ;;   # fortify would turn fprintf into an inline wrapper
   esac
   $CC $extra -c "$f" -o "$OUT/obj/$base.o" &
@@ -27,6 +29,11 @@ wait
 $CC -c "$HERE/ahf_glue.c" -o "$OUT/ahf_glue.o"
 mv "$OUT/obj/src_main.o" "$OUT/"
 ar rcs "$OUT/libref.a" "$OUT"/obj/*.o
-gcc -fopenmp -o "$OUT/AHF-b200" "$OUT/src_main.o" "$OUT/ahf_glue.o" "$OUT/libref.a" -L"$REPO/ahf_b200" -lahfgpu -Wl,-rpath,'$ORIGIN/../..' -lm
+gcc -fopenmp -o "$OUT/$name" "$OUT/src_main.o" "$OUT/ahf_glue.o" "$OUT/libref.a" -L"$REPO/ahf_b200" -lahfgpu -Wl,-rpath,'$ORIGIN/../..' -lm
 rm -rf "$OUT/obj" "$OUT/src_main.o" "$OUT/ahf_glue.o" "$OUT/libref.a"
+}
+# AHF-b200    : key/sort, mesh and halo loop on the GPU
+# AHF-b200-kh : key/sort and halo loop on the GPU, mesh on the CPU (reference code)
+build_one AHF-b200 "-Dgen_domgrids=ahfb200_gen_domgrids -Dll=ahfb200_ll -Dzero_dens=ahfb200_zero_dens -Dassign_npart=ahfb200_assign_npart -Dgen_AMRhierarchy=ahfb200_gen_AMRhierarchy"
+build_one AHF-b200-kh ""
 ls -la "$OUT"

@@ -13,7 +13,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
-DROPIN = os.path.join(ROOT, "ahf_b200", "host", "_build", "AHF-b200")
+DROPIN_DIR = os.path.join(ROOT, "ahf_b200", "host", "_build")
 
 
 def _num_table(path):
@@ -25,8 +25,10 @@ def _num_table(path):
     return rows
 
 
+@pytest.mark.parametrize("variant", ["AHF-b200", "AHF-b200-kh"])      # full path on the GPU / CPU mesh + GPU sort & haloes
 @pytest.mark.parametrize("n1d,seed,ncl", [(32, 21, 6), (64, 12, 14)])
-def test_catalogues_equal_reference(n1d, seed, ncl):
+def test_catalogues_equal_reference(n1d, seed, ncl, variant):
+    DROPIN = os.path.join(DROPIN_DIR, variant)
     from ahf_b200 import synth
     from oracle import oracle as O
     if not (os.path.exists(DROPIN) and os.path.exists(O.REF_BIN)):
