@@ -73,7 +73,7 @@ class SlabBox:
         self.n_total = int(tot.item())
         # splitters from regular samples of every rank's sorted keys
         ns = 4096
-        idx = torch.linspace(0, max(n_local - 1, 0), ns, device=dev).long()
+        idx = (torch.arange(ns, device=dev, dtype=torch.int64) * max(n_local - 1, 0)) // (ns - 1)     # integer arithmetic: float32 linspace overflows 2^24
         samp = keys[idx] if n_local else torch.zeros(ns, dtype=torch.int64, device=dev)
         allsamp = [torch.empty_like(samp) for _ in range(self.world)]
         dist.all_gather(allsamp, samp)

@@ -203,3 +203,55 @@ def halo_seeds(box: Box, max_gather_rad_mpc: float = 3.0):
         dist = np.sqrt((d * d).sum(axis=1)).min()
         rad[order[rank]] = min(max(0.5 * dist, 4.0 * box.clump_scale[order[rank]]), rmax)
     return c.astype(np.float64), rad.astype(np.float64), npart
+
+
+def make_box_slice(n1d: int, rank: int, world: int, seed: int = 42, clump_frac: float = 0.3, n_clumps: int | None = None,
+                   boxsize: float | None = None, omega0: float = 0.3, sigma_cell: float = 0.3, mass_decades: float = 3.0):
+    """The share of rank `rank` (of `world`) of a box of about n1d^3 particles, generated independently per rank so that very
+    large boxes (512^3, 1024^3) never exist in one process: a contiguous z-slab of the jittered lattice (thinned by
+    1 - clump_frac) plus every `world`-th Plummer clump.  Same statistics as make_box, not the same realisation.
+    Returns (pos float32 (n,3) box units, mom float32 (n,3), clump centres/scale/npart of ALL clumps, boxsize, pmass)."""
+    box = default_boxsize(n1d) if boxsize is None else float(boxsize)
+    ntot = n1d ** 3
+    if n_clumps is None:
+        n_clumps = max(1, int(round(20 * (n1d / 128.0) ** 3)))
+    pmass = omega0 * RHOC0 * box ** 3 / ntot
+    rng0 = np.random.default_rng(seed)                      # global quantities: identical on every rank
+    w = 10.0 ** (rng0.uniform(0.0, mass_decades, size=n_clumps))
+    cn = np.maximum(30, np.floor(w / w.sum() * int(clump_frac * ntot))).astype(np.int64)
+    centres = rng0.uniform(0.0, box, size=(n_clumps, 3))
+    mass = cn * pmass
+    a_pl = np.clip(0.1 * (mass / 1e14) ** (1.0 / 3.0), 0.05, 0.15)
+    keep = 1.0 - cn.sum() / ntot
+    rng = np.random.default_rng([seed, 1000 + rank])
+    z0, z1 = (rank * n1d) // world, ((rank + 1) * n1d) // world
+    cell = box / n1d
+    parts_x, parts_v = [], []
+    for iz in range(z0, z1):                                # plane by plane keeps the temporaries small
+        m = rng.random(n1d * n1d) < keep
+        idx = np.nonzero(m)[0]
+        lat = np.empty((len(idx), 3))
+        lat[:, 0] = (idx % n1d + 0.5) * cell; lat[:, 1] = (idx // n1d + 0.5) * cell; lat[:, 2] = (iz + 0.5) * cell
+        lat += rng.normal(0.0, sigma_cell * cell, size=lat.shape)
+        parts_x.append(lat.astype(np.float32)); parts_v.append(rng.normal(0.0, 50.0, size=lat.shape).astype(np.float32))
+    for c in range(rank, n_clumps, world):
+        mcl = int(cn[c])
+        u = rng.uniform(1e-9, 1.0 - 1e-6, size=mcl)
+        r = np.minimum(a_pl[c] / np.sqrt(u ** (-2.0 / 3.0) - 1.0), 20.0 * a_pl[c])
+        d = rng.normal(size=(mcl, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+        sig2 = GRAV * mass[c] / (6.0 * a_pl[c]) / np.sqrt(1.0 + (r / a_pl[c]) ** 2)
+        parts_x.append((centres[c] + d * r[:, None]).astype(np.float32))
+        parts_v.append((rng.normal(0.0, 200.0, size=3) + rng.normal(size=(mcl, 3)) * np.sqrt(sig2)[:, None]).astype(np.float32))
+    x = np.mod(np.concatenate(parts_x), np.float32(box)).astype(np.float32)
+    x = np.where(x >= np.float32(box), np.nextafter(np.float32(box), np.float32(0.0)), x).astype(np.float32)
+    v = np.concatenate(parts_v)
+    pos = (x * np.float32(1.0 / box)).astype(np.float32)
+    mom = (v * np.float32(1.0 / (box * 100.0))).astype(np.float32)
+    return pos, mom, dict(centres=centres / box, npart=cn, scale=a_pl / box), box, pmass
+
+
+def halo_seeds_from(centres_box, npart, scale_box, boxsize, max_gather_rad_mpc: float = 3.0):
+    b = Box(n1d=0, boxsize=boxsize, omega0=0.3, lambda0=0.7, pmass=0.0, pos=np.zeros((0, 3), np.float32), mom=np.zeros((0, 3), np.float32),
+            ids=np.zeros(0, np.uint64), vel_kms=np.zeros((0, 3), np.float32), clump_centres=np.asarray(centres_box), clump_npart=np.asarray(npart),
+            clump_scale=np.asarray(scale_box))
+    return halo_seeds(b, max_gather_rad_mpc)

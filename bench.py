@@ -151,12 +151,15 @@ def bench_slab(args, rank, world, local_rank, config):
     import torch
     import torch.distributed as dist
     from ahf_b200 import ahf, multigpu, synth
-    box = synth.make_box(args.n1d, seed=43)
-    n = box.npart
-    b = (np.arange(world + 1) * n) // world
-    pos_l, mom_l = np.ascontiguousarray(box.pos[b[rank]:b[rank + 1]]), np.ascontiguousarray(box.mom[b[rank]:b[rank + 1]])
-    c, r, seed = synth.halo_seeds(box)
-    par = ahf.make_params(boxsize=box.boxsize, pmass=box.pmass, lgrid_dom=args.n1d, device=local_rank)
+    # every rank generates only its own share of the box (a z-slab of the lattice + every world-th clump)
+    pos_l, mom_l, cl, boxsize, pmass = synth.make_box_slice(args.n1d, rank, world, seed=43)
+    c, r, seed = synth.halo_seeds_from(cl["centres"], cl["npart"], cl["scale"], boxsize)
+    nl = torch.tensor([pos_l.shape[0]], device="cuda", dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(nl)
+    n = int(nl.item())
+    pmass = 0.3 * synth.RHOC0 * boxsize ** 3 / n
+    par = ahf.make_params(boxsize=boxsize, pmass=pmass, lgrid_dom=args.n1d, device=local_rank)
     sb = multigpu.SlabBox(par, rank, world, local_rank)
 
     def step():
@@ -170,6 +173,16 @@ def bench_slab(args, rank, world, local_rank, config):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    tphase = {}
+    def timed(name, fn):
+        t0 = time.perf_counter(); out = fn(); sb.g.synchronize(); sb.gh.synchronize(); torch.cuda.synchronize()
+        tphase[name] = tphase.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+        return out
+    def step():           # noqa: F811 -- same sequence with per-phase wall clocks
+        timed("exchange+sort", lambda: sb.distribute(pos_l, mom_l))
+        timed("mesh", sb.build_amr)
+        timed("allgather", sb.gather_box)
+        return timed("halos", lambda: sb.construct_halos(c, r, seed))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); e0.record()
     for _ in range(args.steps):
@@ -188,7 +201,9 @@ def bench_slab(args, rank, world, local_rank, config):
                           "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                           "dtype": "f32 particles, u32/u64 fixed-point deposit, f64 halo arithmetic", "data": "synthetic", "config": config,
                           "mode": "slab", "note": "host->device upload of the rank's file-order slice is inside the timed step",
-                          "levels": sb.g.nlevels(), "halos_ge_minpart": int((scal[:, 9] >= par.min_part).sum())}))
+                          "levels": sb.g.nlevels(), "halos_ge_minpart": int((scal[:, 9] >= par.min_part).sum()),
+                          "phases_ms_rank0": {k: v / args.steps for k, v in tphase.items()},
+                          "mesh_stages_ms_rank0": {k: sb.g.stage_ms(k) for k in ("deposit", "deposit_dom_kernel", "allreduce", "flag", "refine", "relink")}}))
     sb.close()
     if world > 1:
         dist.destroy_process_group()
