@@ -178,6 +178,18 @@ __global__ void k_tile_work(const int *__restrict__ nchunk, const int *__restric
   for (int q = 0; q < nc; q++) work[o + q] = make_int2(t, q | (nc == 1 ? 0x40000000 : 0));
 }
 
+// dense domain level: self-contained work items {first particle, count, tile origin (10 bits per axis), flags}
+__global__ void k_tile_work4(const int32_t *__restrict__ tstart, const int *__restrict__ nchunk, const int *__restrict__ woff, int ntile, int tbits,
+                             int4 *__restrict__ work)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntile) return;
+  const int nc = nchunk[t], o = woff[t], a = tstart[t], b = tstart[t + 1];
+  uint32_t tx, ty, tz;
+  hilbert_coords((uint64_t)t, (unsigned)tbits, tx, ty, tz);
+  for (int q = 0; q < nc; q++) work[o + q] = make_int4(a + q * DT_CHUNK, min(DT_CHUNK, b - a - q * DT_CHUNK), (int)(tx | (ty << 10) | (tz << 20)), nc == 1 ? 1 : 0);
+}
+
 // refinement levels: tile id (Hilbert prefix of the particle key) of every level particle, heads of equal-id runs
 __global__ void k_lvl_tile_heads(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ plist, uint64_t np, int sh, uint8_t *__restrict__ head)
 {
@@ -369,6 +381,227 @@ k_deposit_tiles(const float4 *__restrict__ pos4, const int32_t *__restrict__ tst
         if (sole && inxy && hz >= 2 && hz <= DT_T - 1) *dstp = val; else atomicAdd(dstp, val);
       }
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// D4 domain level, integer formulation (k_deposit_dom).
+//   Positions are float32 in [0,1): u = trunc(x * 2^32) is exact (x >= 2^-8) and cell = u >> (32 - logL) equals the
+//   reference's (unsigned long)(L * x) (lltools.c:59).  The in-cell fraction f = (u << logL) / 2^32 gives the TSC weights
+//   (density.c:357-359 with s = f - 1/2) in 2^-32 fixed point:  W0 = (1-f)^2/2, W2 = f^2/2, W1 = 1 - W0 - W2.  Products use
+//   IMAD.HI and the middle weight of every triple is the complement, so each particle deposits EXACTLY 2^32 units: the
+//   level total is N * 2^32 whatever the order (a checksum the tests use).  No float->int conversion in the 27-term loop.
+//   Two copies of the tile low words (even / odd lanes, 16 banks apart) halve the same-address serialisation of the
+//   shared-memory atomics that Hilbert-adjacent particles of one cell cause.
+// ------------------------------------------------------------------------------------------------
+constexpr int DD_CO   = DT_HH + 8;                                   // word offset of copy B: == 16 (mod 32 banks)
+constexpr int DD_CAR  = 2 * DD_CO;                                   // word offset of the carry counters
+constexpr int DD_NS   = 4;                                           // TMA stages of DT_SUB particles (ring)
+constexpr int DD_SMEM = DD_NS * DT_SUB * 16 + (DD_CAR + DT_HH) * 4 + 8 * DD_NS * (DT_THREADS / 32);   // DT_SUB*16 = 16 warps x 512 B per ring slot
+
+__device__ __forceinline__ uint32_t pos_q32(float x) { return x >= 1.0f ? 0u : __float2uint_rz(x * 4294967296.0f); }   // x == 1 -> cell 0 (lltools.c:61-64)
+__device__ __forceinline__ void tsc_q32(uint32_t t32, uint32_t (&w)[3])
+{
+  const uint32_t t31 = t32 >> 1, a31 = 0x80000000u - t31;
+  w[0] = (uint32_t)(((unsigned long long)a31 * a31) >> 31);
+  w[2] = (uint32_t)(((unsigned long long)t31 * t31) >> 31);
+  w[1] = 0u - w[0] - w[2];
+}
+// low word += v (native ATOMS.ADD, old value returned).  Whether the low word wrapped is the carry-out of old + v; dom_carry
+// shifts it into a per-thread bit mask (IADD3 with carry-out + IADD3.X: two instructions, no predicate, no branch).  The
+// atomics of a plane are all issued before the first result is used; the few set bits are replayed onto the carry counters
+// after the 27 terms.
+__device__ __forceinline__ uint32_t dom_atom(uint32_t lo_addr, uint32_t v)
+{
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(lo_addr), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void dom_carry(uint32_t &mask, uint32_t old, uint32_t v)
+{
+  asm volatile("{\n .reg .u32 s;\n add.cc.u32 s, %1, %2;\n addc.u32 %0, %0, %0;\n}" : "+r"(mask) : "r"(old), "r"(v));
+}
+__constant__ uint16_t c_dom_off[27];     // byte offset of term (k,j,a) inside the (T+2)^3 tile, indexed k*9+j*3+a
+
+template <int VAR>      // 0 = product; 1..4 = timing experiments (AHFGPU_DOM_VARIANT): 1 no return/carry, 2 no atomics, 3 no flush, 4 one copy
+__global__ void __launch_bounds__(DT_THREADS, 2)
+k_deposit_dom(const float4 *__restrict__ pos4, const int4 *__restrict__ work, int W, int L, int logL,
+              unsigned long long *__restrict__ acc, const uint32_t one /* == 1, a run-time value on purpose: see dom_carry */)
+{
+  extern __shared__ __align__(16) unsigned char dsm[];
+  float4   *sp   = reinterpret_cast<float4 *>(dsm);
+  uint32_t *tile = reinterpret_cast<uint32_t *>(dsm + DD_NS * DT_SUB * 16);        // copy A | copy B | carry counters
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(dsm + DD_NS * DT_SUB * 16 + (DD_CAR + DT_HH) * 4);
+  // Persistent CTA: work items blockIdx.x, +gridDim.x, ...  Every warp streams its own 32-particle slices (slice w, w+16, ...
+  // of each item) through a private DD_NS-deep TMA ring with private mbarriers.  The ring runs ahead ACROSS items, so the
+  // loads of the next tile are in flight while this one is flushed; block-wide barriers only bracket the flush.
+  constexpr int NW = DT_THREADS / 32;
+  const int      lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const uint32_t tile_s = smem_u32(tile);
+  const uint32_t bar = smem_u32(mbar) + 8u * (uint32_t)(wrp * DD_NS), dst = smem_u32(sp) + 512u * (uint32_t)(wrp * DD_NS);
+  const int      M = L - 1, sh = 32 - logL;
+  const uint32_t copy_off = (VAR != 4 && (lane & 1)) ? 4u * DD_CO : 0u;
+  // producer state (warp-uniform): next slice to request
+  int  p_item = blockIdx.x, p_k = 0, p_s0 = 0, p_np = 0, p_n = 0;
+  uint32_t gi = 0, g = 0;                                       // slices requested / consumed by this warp so far
+  if (p_item < W) { const int4 w4 = work[p_item]; p_s0 = w4.x; p_np = w4.y; const int nsl = (p_np + 31) >> 5; p_n = nsl > wrp ? (nsl - wrp + NW - 1) / NW : 0; }
+  auto produce = [&]() {
+    while (p_item < W && p_k >= p_n) {
+      p_item += gridDim.x; p_k = 0;
+      if (p_item < W) { const int4 w4 = work[p_item]; p_s0 = w4.x; p_np = w4.y; const int nsl = (p_np + 31) >> 5; p_n = nsl > wrp ? (nsl - wrp + NW - 1) / NW : 0; }
+    }
+    if (p_item >= W) return;
+    if (lane == 0) {
+      const int      first = (wrp + p_k * NW) << 5, cnt = min(32, p_np - first);
+      const uint32_t bytes = (uint32_t)cnt * 16u, bb = bar + 8u * (gi % DD_NS), dd = dst + 512u * (gi % DD_NS);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bb), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dd), "l"(pos4 + p_s0 + first), "r"(bytes), "r"(bb) : "memory");
+    }
+    gi++; p_k++;
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < DD_NS; q++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar + 8u * q));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < DD_NS - 1; q++) produce();
+  for (int i = threadIdx.x; i < (DD_CAR + DT_HH) / 4; i += DT_THREADS) reinterpret_cast<uint4 *>(tile)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  for (int item = blockIdx.x; item < W; item += gridDim.x) {
+  const int4 wk = work[item];
+  const int  np = wk.y;
+  const bool sole = wk.w != 0;
+  const int  x0 = (wk.z & 1023) * DT_T, y0 = ((wk.z >> 10) & 1023) * DT_T, z0 = ((wk.z >> 20) & 1023) * DT_T;
+  const int  nsl = (np + 31) >> 5;
+  const int  nmine = nsl > wrp ? (nsl - wrp + NW - 1) / NW : 0;
+  for (int k = 0; k < nmine; k++) {
+    produce();                                  // refills the slot read in the previous iteration (ordered by the __syncwarp below)
+    {
+      const uint32_t bb = bar + 8u * (g % DD_NS), parity = (g / DD_NS) & 1u;
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(bb), "r"(parity) : "memory");
+      }
+    }
+    const int  i = ((wrp + k * NW) << 5) + lane;
+    const bool valid = i < np;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "r"(dst + 512u * (g % DD_NS) + 16u * lane) : "memory");
+    __syncwarp();
+    g++;
+    const uint32_t ux = pos_q32(q.x), uy = pos_q32(q.y), uz = pos_q32(q.z);
+    const int cx = (int)(ux >> sh), cy = (int)(uy >> sh), cz = (int)(uz >> sh);
+    const int lx = cx - x0, ly = cy - y0, lz = cz - z0;
+    const bool intile = (unsigned)(lx | ly | lz) < (unsigned)DT_T;
+    const int  widx = (lz * DT_H + ly) * DT_H + lx;
+    const int  cid = valid ? (intile ? widx : -2) : -1;
+    uint32_t wx[3], wy[3], wz[3], wyz[9];
+    tsc_q32(ux << logL, wx); tsc_q32(uy << logL, wy); tsc_q32(uz << logL, wz);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      wyz[k * 3 + 0] = __umulhi(wy[0], wz[k]); wyz[k * 3 + 2] = __umulhi(wy[2], wz[k]);
+      wyz[k * 3 + 1] = wz[k] - wyz[k * 3 + 0] - wyz[k * 3 + 2];
+    }
+    const int  cid0 = __shfl_sync(0xffffffffu, cid, 0);
+    const bool grouped = __all_sync(0xffffffffu, cid == cid0) && cid0 >= 0;
+    if (grouped) {
+      // clump cores: the whole warp sits in ONE cell -> sum the 27 terms across the warp (two 16-bit limbs through REDUX);
+      // lane 0 issues a plane's 9 low-word atomics back to back, then adds (high part + carry-out) to the carry counters
+      const uint32_t lo0 = tile_s + 4u * (uint32_t)widx, ca0 = lo0 + 4u * DD_CAR;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        uint32_t tl[9], th[9], old[9];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          const uint32_t w = wyz[k * 3 + j];
+          const uint32_t v0 = __umulhi(wx[0], w), v2 = __umulhi(wx[2], w), v1 = w - v0 - v2;
+          const uint32_t vv[3] = { v0, v1, v2 };
+#pragma unroll
+          for (int a = 0; a < 3; a++) {
+            const uint32_t l0 = __reduce_add_sync(0xffffffffu, vv[a] & 0xffffu), l1 = __reduce_add_sync(0xffffffffu, vv[a] >> 16);
+            const unsigned long long tot = (unsigned long long)l0 + ((unsigned long long)l1 << 16);
+            tl[j * 3 + a] = (uint32_t)tot; th[j * 3 + a] = (uint32_t)(tot >> 32);
+          }
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int q = 0; q < 9; q++) old[q] = dom_atom(lo0 + 4u * (uint32_t)((k * DT_H + q / 3) * DT_H + q % 3), tl[q]);
+#pragma unroll
+          for (int q = 0; q < 9; q++) {
+            const uint32_t hi = th[q] + ((old[q] + tl[q] < old[q]) ? 1u : 0u);
+            if (hi) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(ca0 + 4u * (uint32_t)((k * DT_H + q / 3) * DT_H + q % 3)), "r"(hi) : "memory");
+          }
+        }
+      }
+    } else if (intile && valid) {
+      const uint32_t lo0 = tile_s + 4u * (uint32_t)widx + copy_off, ca0 = tile_s + 4u * (uint32_t)(widx + DD_CAR);
+      uint32_t cmask = 0;                                   // bit 26-i: term i wrapped its low word
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        uint32_t v[9], old[9];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          const uint32_t w = wyz[k * 3 + j];
+          v[j * 3 + 0] = __umulhi(wx[0], w); v[j * 3 + 2] = __umulhi(wx[2], w); v[j * 3 + 1] = w - v[j * 3 + 0] - v[j * 3 + 2];
+        }
+        if (VAR == 1) {
+#pragma unroll
+          for (int q = 0; q < 9; q++) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(lo0 + 4u * (uint32_t)((k * DT_H + q / 3) * DT_H + q % 3)), "r"(v[q]) : "memory");
+          continue;
+        }
+        if (VAR == 2) {
+#pragma unroll
+          for (int q = 0; q < 9; q++) cmask ^= v[q];
+          continue;
+        }
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+          for (int a = 0; a < 3; a++) old[j * 3 + a] = dom_atom(lo0 + 4u * (uint32_t)((k * DT_H + j) * DT_H + a), v[j * 3 + a]);
+#pragma unroll
+        for (int q = 0; q < 9; q++) dom_carry(cmask, old[q], v[q]);
+      }
+      if (VAR == 2) { if (cmask == 0x12345u) tile[DD_CAR + widx] = 1; cmask = 0; }
+      while (cmask) {
+        const int b = 31 - __clz(cmask);
+        cmask ^= 1u << b;
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(ca0 + (uint32_t)c_dom_off[26 - b]), "r"(one) : "memory");
+      }
+    } else if (valid) {
+      // ll()'s coordinate clamp put the particle into a cell outside this tile: straight to the global accumulators
+#pragma unroll
+      for (int r = 0; r < 9; r++) {
+        const uint32_t v0 = __umulhi(wx[0], wyz[r]), v2 = __umulhi(wx[2], wyz[r]), v1 = wyz[r] - v0 - v2;
+        const uint32_t vv[3] = { v0, v1, v2 };
+        const int y = (cy + (r % 3) - 1) & M, z = (cz + (r / 3) - 1) & M;
+#pragma unroll
+        for (int a = 0; a < 3; a++) atomicAdd(&acc[(((size_t)z << logL | y) << logL) | (size_t)((cx + a - 1) & M)], (unsigned long long)vv[a]);
+      }
+    }
+  }
+  __syncthreads();
+  // flush + re-zero: thread = one (hx,hy) column of the tile, marching in z (no div/mod, constant strides)
+  if (threadIdx.x < DT_H * DT_H) {
+    const int hx = threadIdx.x % DT_H, hy = threadIdx.x / DT_H;
+    const int x = (x0 + hx - 1) & M, y = (y0 + hy - 1) & M;
+    const bool inxy = hx >= 2 && hx <= DT_T - 1 && hy >= 2 && hy <= DT_T - 1;
+#pragma unroll 2
+    for (int hz = 0; hz < DT_H; hz++) {
+      const int i = (hz * DT_H + hy) * DT_H + hx;
+      const unsigned long long val = ((unsigned long long)tile[DD_CAR + i] << 32) + (unsigned long long)tile[i] + (unsigned long long)tile[DD_CO + i];
+      if (val == 0) continue;
+      tile[i] = 0; tile[DD_CO + i] = 0; tile[DD_CAR + i] = 0;
+      if (VAR == 3) continue;
+      const int z = (z0 + hz - 1) & M;
+      unsigned long long *dstp = &acc[(((size_t)z << logL | y) << logL) | x];
+      if (sole && inxy && hz >= 2 && hz <= DT_T - 1) *dstp = val; else atomicAdd(dstp, val);
+    }
+  }
+  __syncthreads();
   }
 }
 
@@ -770,30 +1003,43 @@ static void build_rows_planes(ahfgpu_ctx *c, Level &lv)
   lv.rowplane = rowplane;
 }
 
+static std::string lvl_name(const char *base, int lev) { char b[48]; snprintf(b, sizeof(b), "%s_L%d", base, lev); return b; }
+
 static void deposit_level(ahfgpu_ctx *c, Level &lv)
 {
+  const int lev_id = (int)c->levels.size() - 1;
   Stage st(c, "deposit", lv.npart_dep);
+  Stage stl(c, lvl_name("deposit", lev_id).c_str(), lv.npart_dep);
   LV v = view(lv);
   const int nc = (int)lv.ncell;
   DevBuf<unsigned long long> acc;
   acc.reserve(nc);
   CUDA_CHECK(cudaMemsetAsync(acc.p, 0, sizeof(unsigned long long) * nc, c->stream));
-  const int    S = fx_shift_for(lv.masstopartdens);
-  const double fxscale = (double)(1ull << S);
   const bool generic_only = getenv("AHFGPU_GENERIC_DEPOSIT") != nullptr;
+  const bool dom_v1       = getenv("AHFGPU_DEPOSIT_V1") != nullptr;           // previous float-weight domain kernel (A/B timing)
   const bool tiles_dense  = lv.dense && lv.L >= 2 * DT_T && lv.npart_dep > 0 && !generic_only;
+  const int    S = (tiles_dense && !dom_v1) ? 32 : fx_shift_for(lv.masstopartdens);    // k_deposit_dom works in 2^-32 units
+  const double fxscale = (double)(1ull << S);
   const bool tiles_sparse = !lv.dense && lv.lpos && lv.npart_dep >= 2048 && v.logL - 4 <= 20 && !generic_only;
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_CHECK(cudaFuncSetAttribute(k_deposit_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_deposit_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
+    uint16_t off[27];
+    for (int k = 0; k < 3; k++) for (int j = 0; j < 3; j++) for (int a = 0; a < 3; a++) off[k * 9 + j * 3 + a] = (uint16_t)(4 * ((k * DT_H + j) * DT_H + a));
+    CUDA_CHECK(cudaMemcpyToSymbol(c_dom_off, off, sizeof(off)));
     attr_set = true;
   }
   if (tiles_dense || tiles_sparse) {
     // tiles are Hilbert cells of (logL - 4) bits per dimension: contiguous ranges of the (level's) particle list
     const int tbits = v.logL - 4;
     int ntile = 0;
-    DevBuf<int32_t> tstart; DevBuf<int> nchunk, woff, bs, tot, hs; DevBuf<int2> work; DevBuf<uint32_t> tlist; DevBuf<uint8_t> head;
+    DevBuf<int32_t> tstart; DevBuf<int> nchunk, woff, bs, tot, hs; DevBuf<int2> work; DevBuf<int4> work4; DevBuf<uint32_t> tlist; DevBuf<uint8_t> head;
     tot.reserve(1);
     if (tiles_dense) {
       ntile = 1 << (3 * tbits);
@@ -818,7 +1064,22 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
     LAUNCH(c, k_tile_work, nblk(ntile, 256), 256, 0, nchunk.p, woff.p, ntile, work.p);
     {
       Stage sk(c, lv.dense ? "deposit_dom_kernel" : "deposit_ref_kernel", lv.npart_dep);
-      if (tiles_dense)
+      Stage skl(c, lvl_name("depk", lev_id).c_str(), W);
+      if (tiles_dense && !dom_v1) {
+        const char *ev = getenv("AHFGPU_DOM_VARIANT");
+        const int var = ev ? atoi(ev) : 0;
+        work4.reserve(W);
+        LAUNCH(c, k_tile_work4, nblk(ntile, 256), 256, 0, tstart.p, nchunk.p, woff.p, ntile, tbits, work4.p);
+        int nsm = 0;
+        CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->dev));
+        // AHFGPU_DOM_PERSIST=1: two persistent CTAs per SM striding over the items (measured slower: static striding loses the
+        // hardware's dynamic balance between light and heavy tiles); default: one CTA per item
+        const unsigned grid = getenv("AHFGPU_DOM_PERSIST") ? (unsigned)std::min(W, 2 * nsm) : (unsigned)W;
+#define DOM_LAUNCH(V) LAUNCH(c, k_deposit_dom<V>, grid, DT_THREADS, DD_SMEM, c->pos4, work4.p, W, (int)lv.L, v.logL, acc.p, 1u)
+        if (var == 1) DOM_LAUNCH(1); else if (var == 2) DOM_LAUNCH(2); else if (var == 3) DOM_LAUNCH(3); else if (var == 4) DOM_LAUNCH(4); else DOM_LAUNCH(0);
+#undef DOM_LAUNCH
+      }
+      else if (tiles_dense)
         LAUNCH(c, k_deposit_tiles<false>, (unsigned)W, DT_THREADS, DT_SMEM, c->pos4, tstart.p, work.p, (int)lv.L, v.logL, tbits, acc.p,
                (const uint32_t *)nullptr, (const int32_t *)nullptr, v, (const int32_t *)nullptr, (float)fxscale);
       else
@@ -826,7 +1087,7 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
                tlist.p, lv.pcell, v, lv.nbr, (float)fxscale);
     }
     if (lv.dense) c->stage_cnt_extra["deposit_dom_ctas"] = W;
-    tstart.release(); nchunk.release(); woff.release(); bs.release(); tot.release(); work.release(); tlist.release(); head.release(); hs.release();
+    tstart.release(); nchunk.release(); woff.release(); bs.release(); tot.release(); work.release(); work4.release(); tlist.release(); head.release(); hs.release();
   } else if (lv.npart_dep > 0) {
     Stage sk(c, lv.dense ? "deposit_dom_kernel" : "deposit_ref_kernel", lv.npart_dep);
     LAUNCH(c, k_deposit_generic, nblk(lv.npart_dep, 256), 256, 0, c->pos4, lv.plist, lv.pcell, (uint64_t)lv.npart_dep, v, lv.nbr, acc.p, fxscale);
@@ -887,12 +1148,14 @@ void amr_build(ahfgpu_ctx *c)
     DevBuf<int> S;
     {
       Stage st(c, "flag", nc);
+      Stage stl(c, lvl_name("flag", lev).c_str(), nc);
       LAUNCH(c, k_test_node, nblk(nc, 256), 256, 0, cv, cur.dens, cur.interior, cur.nbr, cur.critdens - 1.0, cur.tn);
       if (cur.dense) LAUNCH(c, k_mark_dense, nblk(nc, 256), 256, 0, cv, cur.tn, cur.mark);
       else LAUNCH(c, k_mark_sparse, nblk(nc, 256), 256, 0, cv, cur.tn, cur.interior, cur.crow, cur.row_c0, cur.row_tested, cur.mark);
     }
     {
       Stage st(c, "refine", nc);
+      Stage stl(c, lvl_name("refine", lev).c_str(), nc);
       DevBuf<uint8_t> flag;
       flag.reserve(nc); S.reserve(nc);
       LAUNCH(c, k_nonzero, nblk(nc, 256), 256, 0, cur.mark, nc, flag.p);
@@ -926,6 +1189,7 @@ void amr_build(ahfgpu_ctx *c)
       Level &coa = c->levels[lev];
       Level &fin = c->levels[lev + 1];
       Stage st(c, "relink", coa.npart_dep);
+      Stage stl(c, lvl_name("relink", lev).c_str(), coa.npart_dep);
       const uint64_t np = (uint64_t)coa.npart_dep;
       DevBuf<int32_t> newcell; DevBuf<uint8_t> moved; DevBuf<int> MS;
       newcell.reserve(np); moved.reserve(np); MS.reserve(np);
