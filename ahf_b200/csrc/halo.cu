@@ -560,6 +560,382 @@ __global__ void __launch_bounds__(HB) k_halo_unbind(const float4 *__restrict__ p
 }
 
 // ------------------------------------------------------------------------------------------------
+// U2/U3, cooperative multi-block form (default).  Every halo is cut into tiles of HT radius-sorted members and ALL tiles
+// of ALL active haloes run in one grid, so a 10^7-particle host spreads over the whole GPU and the step time no longer
+// depends on the largest halo.  Each running quantity of the reference's inside-out loops is a segmented scan in three
+// steps: tile totals (k_g_*_a) -> per-halo exclusive scan of the tile totals (k_g_scan, fixed order) -> tile-local scan plus
+// carry (k_g_*_c).  The causal bound test of rem_unbound (mask_j depends on the running mean velocity of the BOUND members
+// before j, ahf_halos.c:3538-3569) is solved as a fixed point over the whole halo: mask -> prefix sums -> mask, repeated
+// until no member changes; because mask_j only depends on mask_<j the fixed point is unique and equals the sequential
+// answer.  Deterministic: no floating-point atomics anywhere.
+// ------------------------------------------------------------------------------------------------
+constexpr int GNC = 5;      // scan components of the mask iteration: M_vel, P(3), bound count
+
+struct GH {                 // per-halo device state of the cooperative pass (arrays indexed by halo)
+  int64_t       *np;        // current member count
+  double        *Mvir, *Rvir, *ovd, *Phi0, *seed;   // seed: 4 per halo
+  unsigned long long *first;                         // rvir: first index below the overdensity limit
+  int32_t       *tile0, *ntile;                      // tiles of the halo in the current tile list
+  int64_t       *nb, *nremove;                       // result of an unbinding iteration
+};
+
+template <int NC>
+__global__ void __launch_bounds__(HB) k_g_scan(const int32_t *__restrict__ act, const int32_t *__restrict__ tile0, const int32_t *__restrict__ ntile,
+                                               const double *__restrict__ tt, double *__restrict__ tc, double *__restrict__ htot)
+{
+  __shared__ double smd[(HB / 32) * NC];
+  const int h = act[blockIdx.x], t0 = tile0[h], nt = ntile[h];
+  double carry[NC];
+#pragma unroll
+  for (int q = 0; q < NC; q++) carry[q] = 0.0;
+  for (int b = 0; b < nt; b += HB) {
+    const int t = b + threadIdx.x;
+    double v[NC], ex[NC], tot[NC];
+#pragma unroll
+    for (int q = 0; q < NC; q++) v[q] = t < nt ? tt[(size_t)(t0 + t) * NC + q] : 0.0;
+    block_excl_scan_n<NC>(v, ex, tot, smd);
+    if (t < nt) {
+#pragma unroll
+      for (int q = 0; q < NC; q++) tc[(size_t)(t0 + t) * NC + q] = carry[q] + ex[q];
+    }
+#pragma unroll
+    for (int q = 0; q < NC; q++) carry[q] += tot[q];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < NC; q++) htot[(size_t)h * NC + q] = carry[q];
+  }
+}
+
+// cumulative mass of the tile's members: equal masses -> index + 1 exactly; otherwise the stored prefix
+__device__ __forceinline__ void g_tile_M(const TileMembers &T, const double *__restrict__ Mpre, long long base, double (&M)[HI])
+{
+#pragma unroll
+  for (int i = 0; i < HI; i++) {
+    const long long j = base + (long long)threadIdx.x * HI + i;
+    M[i] = Mpre ? (T.act[i] ? Mpre[j] : 0.0) : (double)(j + 1);
+  }
+}
+
+// multimass only: tile totals of w, then M(<=j) per member
+__global__ void __launch_bounds__(HB) k_g_mass_a(const float4 *__restrict__ pos4, const double *__restrict__ centre, const int64_t *__restrict__ moff0,
+                                                 const uint32_t *__restrict__ members, GH G, const int2 *__restrict__ tiles, double *__restrict__ tt)
+{
+  __shared__ double smd[HB / 32];
+  const int2 tl = tiles[blockIdx.x];
+  const int  h = tl.x; const long long base = (long long)tl.y * HT, np = G.np[h];
+  const uint32_t *ip = members + moff0[h];
+  double loc = 0.0;
+#pragma unroll
+  for (int i = 0; i < HI; i++) { long long j = base + (long long)threadIdx.x * HI + i; if (j < np) loc += (double)pos4[ip[j]].w; }
+  loc = block_sum(loc, smd);
+  if (threadIdx.x == 0) tt[blockIdx.x] = loc;
+}
+__global__ void __launch_bounds__(HB) k_g_mass_c(const float4 *__restrict__ pos4, const int64_t *__restrict__ moff0, const uint32_t *__restrict__ members, GH G,
+                                                 const int2 *__restrict__ tiles, const double *__restrict__ tc, double *__restrict__ Mpre)
+{
+  __shared__ double smd[HB / 32];
+  const int2 tl = tiles[blockIdx.x];
+  const int  h = tl.x; const long long base = (long long)tl.y * HT, np = G.np[h];
+  const uint32_t *ip = members + moff0[h];
+  double w[HI], loc[1] = { 0.0 }, ex[1], tot[1];
+#pragma unroll
+  for (int i = 0; i < HI; i++) { long long j = base + (long long)threadIdx.x * HI + i; w[i] = j < np ? (double)pos4[ip[j]].w : 0.0; loc[0] += w[i]; }
+  block_excl_scan_n<1>(loc, ex, tot, smd);
+  double run = tc[blockIdx.x] + ex[0];
+#pragma unroll
+  for (int i = 0; i < HI; i++) { long long j = base + (long long)threadIdx.x * HI + i; run += w[i]; if (j < np) Mpre[moff0[h] + j] = run; }
+}
+
+// rem_outsideRvir (ahf_halos.c:3811-3869): first member whose mean enclosed overdensity drops below ovlim
+__global__ void __launch_bounds__(HB) k_g_rvir_find(const float4 *__restrict__ pos4, const double *__restrict__ centre, const int64_t *__restrict__ moff0,
+                                                    const uint32_t *__restrict__ members, GH G, const int2 *__restrict__ tiles, const double *__restrict__ Mpre, HP P)
+{
+  __shared__ long long sml[HB / 32];
+  const int2 tl = tiles[blockIdx.x];
+  const int  h = tl.x; const long long base = (long long)tl.y * HT, np = G.np[h];
+  const double c[3] = { centre[3 * h], centre[3 * h + 1], centre[3 * h + 2] };
+  TileMembers T;
+  load_tile(T, pos4, members + moff0[h], base, np, c);
+  double M[HI];
+  g_tile_M(T, Mpre ? Mpre + moff0[h] : nullptr, base, M);
+  long long mine = 0x7fffffffffffffffll;
+#pragma unroll
+  for (int i = 0; i < HI; i++)
+    if (T.act[i]) {
+      const double V = 4. * PI_ / 3. * (T.r[i] * T.r[i] * T.r[i]), od = M[i] / V * P.rho_fac / P.rho_vir;
+      if (!(od >= P.ovlim) && mine == 0x7fffffffffffffffll) mine = base + (long long)threadIdx.x * HI + i;
+    }
+  const long long first = block_min_ll(mine, sml);
+  if (threadIdx.x == 0 && first != 0x7fffffffffffffffll) atomicMin(&G.first[h], (unsigned long long)first);
+}
+__global__ void k_g_rvir_apply(const float4 *__restrict__ pos4, const double *__restrict__ centre, const int64_t *__restrict__ moff0,
+                               const uint32_t *__restrict__ members, GH G, const int32_t *__restrict__ act, int nact, const double *__restrict__ Mpre, HP P)
+{
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nact) return;
+  const int h = act[a];
+  const long long np = G.np[h];
+  const unsigned long long f = G.first[h];
+  const long long js = (f == ~0ull) ? np - 1 : (long long)f;
+  const double c[3] = { centre[3 * h], centre[3 * h + 1], centre[3 * h + 2] };
+  const double r = dist3(pos4[members[moff0[h] + js]], c), M = Mpre ? Mpre[moff0[h] + js] : (double)(js + 1);
+  const double V = 4. * PI_ / 3. * (r * r * r);
+  G.np[h] = js + 1; G.Mvir[h] = M; G.Rvir[h] = r; G.ovd[h] = M / V * P.rho_fac / P.rho_vir;
+  G.first[h] = ~0ull;
+}
+
+// trapezoid terms of Phi for one tile (ahf_halos.c:3398-3410): (r, I) of the member before the tile come from that member itself
+__device__ __forceinline__ double g_tile_phi(const TileMembers &T, const double (&M)[HI], double prev_r, double prev_I, double (&term)[HI],
+                                             double *nb_r, double *nb_I)
+{
+  double I[HI];
+#pragma unroll
+  for (int i = 0; i < HI; i++) I[i] = (T.act[i] && T.r[i] > MACHINE_ZERO) ? M[i] / (T.r[i] * T.r[i]) : 0.0;
+  nb_r[threadIdx.x] = T.r[HI - 1]; nb_I[threadIdx.x] = I[HI - 1];
+  __syncthreads();
+  double rp = threadIdx.x ? nb_r[threadIdx.x - 1] : prev_r, Ip = threadIdx.x ? nb_I[threadIdx.x - 1] : prev_I;
+  double loc = 0.0;
+#pragma unroll
+  for (int i = 0; i < HI; i++) {
+    term[i] = (T.act[i] && T.r[i] > MACHINE_ZERO) ? ((I[i] + Ip) / 2.) * (T.r[i] - rp) : 0.0;
+    loc += term[i];
+    rp = T.r[i]; Ip = I[i];
+  }
+  return loc;
+}
+__device__ __forceinline__ void g_prev_member(const float4 *__restrict__ pos4, const uint32_t *__restrict__ ip, const double *__restrict__ Mpre,
+                                              long long base, const double c[3], double &prev_r, double &prev_I)
+{
+  prev_r = 0.0; prev_I = 0.0;
+  if (base > 0) {
+    prev_r = dist3(pos4[ip[base - 1]], c);
+    const double Mp = Mpre ? Mpre[base - 1] : (double)base;
+    prev_I = prev_r > MACHINE_ZERO ? Mp / (prev_r * prev_r) : 0.0;
+  }
+}
+__global__ void __launch_bounds__(HB) k_g_phi_a(const float4 *__restrict__ pos4, const double *__restrict__ centre, const int64_t *__restrict__ moff0,
+                                                const uint32_t *__restrict__ members, GH G, const int2 *__restrict__ tiles, const double *__restrict__ Mpre,
+                                                double *__restrict__ tt)
+{
+  __shared__ double smd[HB / 32];
+  __shared__ double nb_r[HB], nb_I[HB];
+  const int2 tl = tiles[blockIdx.x];
+  const int  h = tl.x; const long long base = (long long)tl.y * HT, np = G.np[h];
+  const double c[3] = { centre[3 * h], centre[3 * h + 1], centre[3 * h + 2] };
+  const uint32_t *ip = members + moff0[h];
+  const double   *Mp = Mpre ? Mpre + moff0[h] : nullptr;
+  TileMembers T;
+  load_tile(T, pos4, ip, base, np, c);
+  double M[HI], term[HI], prev_r, prev_I;
+  g_tile_M(T, Mp, base, M);
+  g_prev_member(pos4, ip, Mp, base, c, prev_r, prev_I);
+  double loc = g_tile_phi(T, M, prev_r, prev_I, term, nb_r, nb_I);
+  loc = block_sum(loc, smd);
+  if (threadIdx.x == 0) tt[blockIdx.x] = loc;
+}
+// Phi0 = sum of all trapezoids + M_tot / r_last (:3423-3426)
+__global__ void k_g_phi0(const float4 *__restrict__ pos4, const double *__restrict__ centre, const int64_t *__restrict__ moff0, const uint32_t *__restrict__ members,
+                         GH G, const int32_t *__restrict__ act, int nact, const double *__restrict__ Mpre, const double *__restrict__ htot)
+{
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nact) return;
+  const int h = act[a];
+  const long long np = G.np[h];
+  const double c[3] = { centre[3 * h], centre[3 * h + 1], centre[3 * h + 2] };
+  const double r = dist3(pos4[members[moff0[h] + np - 1]], c), M = Mpre ? Mpre[moff0[h] + np - 1] : (double)np;
+  G.Phi0[h] = htot[h] + M / r;
+}
+__global__ void __launch_bounds__(HB) k_g_phi_c(const float4 *__restrict__ pos4, const double *__restrict__ centre, const int64_t *__restrict__ moff0,
+                                                const uint32_t *__restrict__ members, GH G, const int2 *__restrict__ tiles, const double *__restrict__ Mpre,
+                                                const double *__restrict__ tc, HP P, double *__restrict__ vesc2)
+{
+  __shared__ double smd[HB / 32];
+  __shared__ double nb_r[HB], nb_I[HB];
+  const int2 tl = tiles[blockIdx.x];
+  const int  h = tl.x; const long long base = (long long)tl.y * HT, np = G.np[h];
+  const double c[3] = { centre[3 * h], centre[3 * h + 1], centre[3 * h + 2] };
+  const uint32_t *ip = members + moff0[h];
+  const double   *Mp = Mpre ? Mpre + moff0[h] : nullptr;
+  TileMembers T;
+  load_tile(T, pos4, ip, base, np, c);
+  double M[HI], term[HI], prev_r, prev_I;
+  g_tile_M(T, Mp, base, M);
+  g_prev_member(pos4, ip, Mp, base, c, prev_r, prev_I);
+  double loc[1], ex[1], tot[1];
+  loc[0] = g_tile_phi(T, M, prev_r, prev_I, term, nb_r, nb_I);
+  block_excl_scan_n<1>(loc, ex, tot, smd);
+  double run = tc[blockIdx.x] + ex[0];
+  const double Phi0 = G.Phi0[h];
+#pragma unroll
+  for (int i = 0; i < HI; i++) {
+    run += term[i];
+    const long long j = base + (long long)threadIdx.x * HI + i;
+    if (T.act[i]) vesc2[moff0[h] + j] = T.r[i] > MACHINE_ZERO ? (2 * fabs(run - Phi0) * P.phi_fac) : 1e30;      // :3514-3530
+  }
+}
+// seed of the running bulk velocity (:3441-3470)
+__global__ void k_g_seed(const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, const int64_t *__restrict__ moff0, const uint32_t *__restrict__ members,
+                         GH G, const int32_t *__restrict__ act, int nact, int first_iter, int min_part)
+{
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nact) return;
+  const int h = act[a];
+  const uint32_t *ip = members + moff0[h];
+  long long seed = 0;
+  if (first_iter) {
+    int nv = min_part / 2;
+    float m2[64]; int id[64];
+    if (nv > 64) nv = 64;
+    for (int q = 0; q < nv; q++) { float4 m = mom4[ip[q]]; m2[q] = m.x * m.x + m.y * m.y + m.z * m.z; id[q] = q; }
+    for (int x = 1; x < nv; x++) { int t = id[x]; float v = m2[t]; int b = x - 1; while (b >= 0 && m2[id[b]] > v) { id[b + 1] = id[b]; b--; } id[b + 1] = t; }
+    seed = id[nv / 2 - 1];                                  // NR indexx is 1-based: idx[n/2] = (n/2)-th smallest
+  }
+  const float4 p = pos4[ip[seed]], m = mom4[ip[seed]];
+  const double w = (double)p.w;
+  G.seed[4 * h] = w; G.seed[4 * h + 1] = w * m.x; G.seed[4 * h + 2] = w * m.y; G.seed[4 * h + 3] = w * m.z;
+}
+// one sweep of the mask fixed point.  FIRST: masks start as "all bound", only the tile totals are produced.
+// Otherwise: prefix of the bound (M_vel, P) from the previous masks -> new masks (iterated inside the tile until stable for the
+// given carry-in) -> their tile totals for the next sweep; *changed is raised when any mask differs from the one it replaces.
+template <bool FIRST>
+__global__ void __launch_bounds__(HB) k_g_mask(const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, int has_u, const double *__restrict__ centre,
+                                               const int64_t *__restrict__ moff0, const uint32_t *__restrict__ members, GH G, const int2 *__restrict__ tiles,
+                                               const double *__restrict__ vesc2, const double *__restrict__ tc, HP P, uint8_t *__restrict__ mask,
+                                               double *__restrict__ tt, int *__restrict__ changed)
+{
+  __shared__ double smd[(HB / 32) * GNC];
+  const int2 tl = tiles[blockIdx.x];
+  const int  h = tl.x; const long long base = (long long)tl.y * HT, np = G.np[h];
+  const double c[3] = { centre[3 * h], centre[3 * h + 1], centre[3 * h + 2] };
+  const uint32_t *ip = members + moff0[h];
+  TileMembers T;
+  load_tile(T, pos4, ip, base, np, c);
+  double mom[HI][3], uu[HI];
+#pragma unroll
+  for (int i = 0; i < HI; i++) {
+    mom[i][0] = mom[i][1] = mom[i][2] = 0.0; uu[i] = -1.0;
+    if (T.act[i]) { float4 m = mom4[T.pid[i]]; mom[i][0] = (double)m.x; mom[i][1] = (double)m.y; mom[i][2] = (double)m.z; uu[i] = (double)m.w; }
+  }
+  bool bound[HI], was[HI];
+#pragma unroll
+  for (int i = 0; i < HI; i++) {
+    const long long j = base + (long long)threadIdx.x * HI + i;
+    bound[i] = T.act[i] && (FIRST ? true : mask[moff0[h] + j] != 0);
+    was[i] = bound[i];
+  }
+  double tot[GNC];
+  if (!FIRST) {
+    const double v2_tune = P.vesc_tune * P.vesc_tune;
+    double ve[HI];
+#pragma unroll
+    for (int i = 0; i < HI; i++) { const long long j = base + (long long)threadIdx.x * HI + i; ve[i] = T.act[i] ? vesc2[moff0[h] + j] : 1e30; }
+    double run0[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) run0[q] = G.seed[4 * h + q] + tc[(size_t)blockIdx.x * GNC + q];
+    for (int it = 0; it < HB + 2; it++) {
+      double loc[4] = { 0, 0, 0, 0 }, ex[4], t4[4];
+#pragma unroll
+      for (int i = 0; i < HI; i++)
+        if (bound[i]) { loc[0] += T.w[i]; loc[1] += T.w[i] * mom[i][0]; loc[2] += T.w[i] * mom[i][1]; loc[3] += T.w[i] * mom[i][2]; }
+      block_excl_scan_n<4>(loc, ex, t4, smd);
+      double m = run0[0] + ex[0], vx = run0[1] + ex[1], vy = run0[2] + ex[2], vz = run0[3] + ex[3];
+      bool chg = false;
+#pragma unroll
+      for (int i = 0; i < HI; i++) {
+        bool nbnd = false;
+        if (T.act[i]) {
+          double dvx = (mom[i][0] - vx / m) * P.v_fac + P.hubble * T.d[i][0] * P.r_fac;
+          double dvy = (mom[i][1] - vy / m) * P.v_fac + P.hubble * T.d[i][1] * P.r_fac;
+          double dvz = (mom[i][2] - vz / m) * P.v_fac + P.hubble * T.d[i][2] * P.r_fac;
+          double vel2 = dvx * dvx + dvy * dvy + dvz * dvz;
+          if (has_u) vel2 += (uu[i] < 0.0 ? 0.0 : 2 * uu[i]);
+          nbnd = !(vel2 > v2_tune * ve[i]);
+          if (nbnd) { m += T.w[i]; vx += T.w[i] * mom[i][0]; vy += T.w[i] * mom[i][1]; vz += T.w[i] * mom[i][2]; }
+        }
+        chg |= (nbnd != bound[i]);
+        bound[i] = nbnd;
+      }
+      if (!__syncthreads_or(chg ? 1 : 0)) break;
+    }
+    bool diff = false;
+#pragma unroll
+    for (int i = 0; i < HI; i++) {
+      diff |= (bound[i] != was[i]);
+      const long long j = base + (long long)threadIdx.x * HI + i;
+      if (T.act[i] && bound[i] != was[i]) mask[moff0[h] + j] = bound[i] ? 1 : 0;
+    }
+    if (__syncthreads_or(diff ? 1 : 0) && threadIdx.x == 0) atomicOr(changed, 1);
+  }
+  double loc[GNC] = { 0, 0, 0, 0, 0 };
+#pragma unroll
+  for (int i = 0; i < HI; i++)
+    if (bound[i]) { loc[0] += T.w[i]; loc[1] += T.w[i] * mom[i][0]; loc[2] += T.w[i] * mom[i][1]; loc[3] += T.w[i] * mom[i][2]; loc[4] += 1.0; }
+  block_sum_n<GNC>(loc, smd);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < GNC; q++) tt[(size_t)blockIdx.x * GNC + q] = loc[q];
+  }
+  (void)tot;
+}
+// compaction of the bound members (tc[.][4] = bound members of the halo before this tile) into a scratch list
+__global__ void __launch_bounds__(HB) k_g_compact(const int64_t *__restrict__ moff0, const uint32_t *__restrict__ members, GH G, const int2 *__restrict__ tiles,
+                                                  const uint8_t *__restrict__ mask, const double *__restrict__ tc, uint32_t *__restrict__ out)
+{
+  __shared__ int smi[HB / 32];
+  const int2 tl = tiles[blockIdx.x];
+  const int  h = tl.x; const long long base = (long long)tl.y * HT, np = G.np[h];
+  uint32_t pid[HI]; bool b[HI]; int cnt = 0;
+#pragma unroll
+  for (int i = 0; i < HI; i++) {
+    const long long j = base + (long long)threadIdx.x * HI + i;
+    b[i] = j < np && mask[moff0[h] + j] != 0; pid[i] = b[i] ? members[moff0[h] + j] : 0u; cnt += b[i] ? 1 : 0;
+  }
+  int tot, pos = block_excl_scan_i(cnt, smi, &tot);
+  const long long o = moff0[h] + (long long)tc[(size_t)blockIdx.x * GNC + 4];
+#pragma unroll
+  for (int i = 0; i < HI; i++) if (b[i]) { out[o + pos] = pid[i]; pos++; }
+}
+__global__ void __launch_bounds__(HB) k_g_copyback(const int64_t *__restrict__ moff0, GH G, const int2 *__restrict__ tiles, const double *__restrict__ htot,
+                                                   const uint32_t *__restrict__ in, uint32_t *__restrict__ members)
+{
+  const int2 tl = tiles[blockIdx.x];
+  const int  h = tl.x; const long long base = (long long)tl.y * HT, nb = (long long)htot[(size_t)h * GNC + 4];
+#pragma unroll
+  for (int i = 0; i < HI; i++) { const long long j = base + (long long)threadIdx.x + (long long)i * HB; if (j < nb) members[moff0[h] + j] = in[moff0[h] + j]; }
+}
+// end of an unbinding iteration (:3583-3599): npart, M_vir, R_vir of the bound set; Phi0 stays the one of this iteration
+__global__ void k_g_iter_finish(const float4 *__restrict__ pos4, const double *__restrict__ centre, const int64_t *__restrict__ moff0,
+                                const uint32_t *__restrict__ members, GH G, const int32_t *__restrict__ act, int nact, const double *__restrict__ htot)
+{
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nact) return;
+  const int h = act[a];
+  const long long np = G.np[h], nb = (long long)htot[(size_t)h * GNC + 4];
+  const double c[3] = { centre[3 * h], centre[3 * h + 1], centre[3 * h + 2] };
+  G.nb[h] = nb; G.nremove[h] = np - nb;
+  G.Mvir[h] = htot[(size_t)h * GNC + 0];
+  G.Rvir[h] = nb > 0 ? dist3(pos4[members[moff0[h] + nb - 1]], c) : 0.0;
+  G.np[h] = nb;
+}
+__global__ void k_g_write_scal(GH G, const double *__restrict__ centre, const int64_t *__restrict__ ngather, const int64_t *__restrict__ n6, const int64_t *__restrict__ n7,
+                               int64_t nhalo, int min_part, double *__restrict__ scal, int64_t *__restrict__ npart_out)
+{
+  const int64_t h = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (h >= nhalo) return;
+  double *S = scal + h * AHFGPU_NSCAL;
+  const long long np = G.np[h];
+  S[0] = centre[3 * h]; S[1] = centre[3 * h + 1]; S[2] = centre[3 * h + 2];
+  S[5] = (double)ngather[h]; S[6] = (double)n6[h]; S[7] = (double)n7[h]; S[8] = S[9] = (double)np;
+  S[10] = G.Mvir[h]; S[11] = G.Rvir[h]; S[12] = G.ovd[h]; S[13] = G.Phi0[h];
+  int nbins = 0;
+  if (np >= min_part) { nbins = (int)(6.2 * (log10((double)np)) - 3.5); if (nbins < 2) nbins = 2; if (nbins > MAXBINS) nbins = MAXBINS; }
+  S[57] = (double)nbins;
+  npart_out[h] = np;
+}
+
+// ------------------------------------------------------------------------------------------------
 // P1 helpers: 3x3 Jacobi (general.c:1163-1240), get_axes (specific.c:135-178), calc_cNFW / R1 (specific.c:1972-2072)
 // ------------------------------------------------------------------------------------------------
 __device__ void jacobi3(double a[3][3], double d[3], double v[3][3])
@@ -974,6 +1350,123 @@ template <typename T> static T *dalloc(size_t n)
 }
 static inline unsigned nblk(uint64_t n, int b) { return (unsigned)((n + b - 1) / b); }
 
+// host side of the cooperative U2/U3 pass: tile lists per phase, kernel sequences, the few per-halo read-backs
+static void unbind_cooperative(ahfgpu_ctx *c, int64_t nhalo, const HP &P, const double *d_ctr, const int64_t *d_moff0, const std::vector<int64_t> &moff0,
+                               const int64_t *d_ng, const std::vector<int64_t> &h_ng, uint32_t *d_members, int64_t tot_g, int64_t *d_np_out,
+                               std::vector<int64_t> &h_np, int64_t *iter_members)
+{
+  const bool has_w = c->has_weight;
+  const int  has_u = c->has_u ? 1 : 0;
+  GH G;
+  G.np = dalloc<int64_t>(nhalo); G.nb = dalloc<int64_t>(nhalo); G.nremove = dalloc<int64_t>(nhalo);
+  G.Mvir = dalloc<double>(nhalo); G.Rvir = dalloc<double>(nhalo); G.ovd = dalloc<double>(nhalo); G.Phi0 = dalloc<double>(nhalo); G.seed = dalloc<double>(4 * nhalo);
+  G.first = dalloc<unsigned long long>(nhalo); G.tile0 = dalloc<int32_t>(nhalo); G.ntile = dalloc<int32_t>(nhalo);
+  int64_t *d_n6 = dalloc<int64_t>(nhalo), *d_n7 = dalloc<int64_t>(nhalo);
+  CUDA_CHECK(cudaMemcpyAsync(G.np, d_ng, sizeof(int64_t) * nhalo, cudaMemcpyDeviceToDevice, c->stream));
+  for (double *q : { G.Mvir, G.Rvir, G.ovd, G.Phi0 }) CUDA_CHECK(cudaMemsetAsync(q, 0, sizeof(double) * nhalo, c->stream));
+  CUDA_CHECK(cudaMemsetAsync(G.first, 0xff, sizeof(unsigned long long) * nhalo, c->stream));
+  int64_t max_tiles = 0;
+  for (int64_t h = 0; h < nhalo; h++) max_tiles += (h_ng[h] + HT - 1) / HT;
+  if (max_tiles >= (1ll << 31)) AHF_FAIL("too many member tiles in one call");
+  int2    *d_tiles = dalloc<int2>(max_tiles);
+  int32_t *d_act = dalloc<int32_t>(nhalo);
+  double  *d_tt = dalloc<double>((size_t)max_tiles * GNC), *d_tc = dalloc<double>((size_t)max_tiles * GNC);
+  double  *d_htot1 = dalloc<double>(nhalo), *d_htot5 = dalloc<double>((size_t)nhalo * GNC);
+  double  *d_vesc2 = dalloc<double>(tot_g), *d_Mpre = has_w ? dalloc<double>(tot_g) : nullptr;
+  uint8_t *d_mask = dalloc<uint8_t>(tot_g);
+  uint32_t *d_tmp = dalloc<uint32_t>(tot_g);
+  int     *d_changed = dalloc<int>(4);
+  h_np = h_ng;
+  std::vector<int32_t> act, tile0(nhalo), ntile(nhalo);
+  std::vector<int2>    tiles;
+  int nact = 0, nt = 0;
+  // tile list of the haloes selected by `sel`
+  auto build = [&](const std::vector<char> &sel) {
+    act.clear(); tiles.clear();
+    for (int64_t h = 0; h < nhalo; h++) {
+      tile0[h] = 0; ntile[h] = 0;
+      if (!sel[h]) continue;
+      act.push_back((int32_t)h);
+      tile0[h] = (int32_t)tiles.size(); ntile[h] = (int32_t)((h_np[h] + HT - 1) / HT);
+      for (int t = 0; t < ntile[h]; t++) tiles.push_back(make_int2((int)h, t));
+    }
+    nact = (int)act.size(); nt = (int)tiles.size();
+    if (!nact) return;
+    CUDA_CHECK(cudaMemcpyAsync(d_act, act.data(), sizeof(int32_t) * nact, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(G.tile0, tile0.data(), sizeof(int32_t) * nhalo, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(G.ntile, ntile.data(), sizeof(int32_t) * nhalo, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(int2) * nt, cudaMemcpyHostToDevice, c->stream));
+  };
+  auto mass_prefix = [&]() {
+    if (!has_w) return;
+    LAUNCH(c, k_g_mass_a, (unsigned)nt, HB, 0, c->pos4, d_ctr, d_moff0, d_members, G, d_tiles, d_tt);
+    LAUNCH(c, k_g_scan<1>, (unsigned)nact, HB, 0, d_act, G.tile0, G.ntile, d_tt, d_tc, d_htot1);
+    LAUNCH(c, k_g_mass_c, (unsigned)nt, HB, 0, c->pos4, d_moff0, d_members, G, d_tiles, d_tc, d_Mpre);
+  };
+  auto fetch_np = [&]() {
+    CUDA_CHECK(cudaMemcpyAsync(h_np.data(), G.np, sizeof(int64_t) * nhalo, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  };
+  auto rvir = [&]() {
+    std::vector<char> sel(nhalo);
+    for (int64_t h = 0; h < nhalo; h++) sel[h] = h_np[h] >= P.min_part;
+    build(sel);
+    if (!nact) return;
+    mass_prefix();
+    LAUNCH(c, k_g_rvir_find, (unsigned)nt, HB, 0, c->pos4, d_ctr, d_moff0, d_members, G, d_tiles, d_Mpre, P);
+    LAUNCH(c, k_g_rvir_apply, nblk(nact, 128), 128, 0, c->pos4, d_ctr, d_moff0, d_members, G, d_act, nact, d_Mpre, P);
+    fetch_np();
+  };
+  // ---- rem_outsideRvir, call 0
+  rvir();
+  CUDA_CHECK(cudaMemcpyAsync(d_n6, G.np, sizeof(int64_t) * nhalo, cudaMemcpyDeviceToDevice, c->stream));
+  // ---- rem_unbound (ahf_halos.c:3292-3607): all haloes iterate together, a halo leaves when nremove <= 3 or npart < min_part
+  std::vector<char> active(nhalo);
+  std::vector<int64_t> h_nrem(nhalo);
+  int64_t work = 0;
+  for (int64_t h = 0; h < nhalo; h++) active[h] = h_np[h] >= P.min_part;
+  for (int iter = 1;; iter++) {
+    build(active);
+    if (!nact) break;
+    for (int h : act) work += h_np[h];
+    mass_prefix();
+    LAUNCH(c, k_g_phi_a, (unsigned)nt, HB, 0, c->pos4, d_ctr, d_moff0, d_members, G, d_tiles, d_Mpre, d_tt);
+    LAUNCH(c, k_g_scan<1>, (unsigned)nact, HB, 0, d_act, G.tile0, G.ntile, d_tt, d_tc, d_htot1);
+    LAUNCH(c, k_g_phi0, nblk(nact, 128), 128, 0, c->pos4, d_ctr, d_moff0, d_members, G, d_act, nact, d_Mpre, d_htot1);
+    LAUNCH(c, k_g_phi_c, (unsigned)nt, HB, 0, c->pos4, d_ctr, d_moff0, d_members, G, d_tiles, d_Mpre, d_tc, P, d_vesc2);
+    LAUNCH(c, k_g_seed, nblk(nact, 64), 64, 0, c->pos4, c->mom4, d_moff0, d_members, G, d_act, nact, iter == 1 ? 1 : 0, P.min_part);
+    CUDA_CHECK(cudaMemsetAsync(d_mask, 1, (size_t)tot_g, c->stream));
+    LAUNCH(c, k_g_mask<true>, (unsigned)nt, HB, 0, c->pos4, c->mom4, has_u, d_ctr, d_moff0, d_members, G, d_tiles, d_vesc2, d_tc, P, d_mask, d_tt, d_changed);
+    for (;;) {              // fixed point: two sweeps per read-back; converged when the last sweep changed nothing
+      CUDA_CHECK(cudaMemsetAsync(d_changed, 0, sizeof(int) * 2, c->stream));
+      for (int q = 0; q < 2; q++) {
+        LAUNCH(c, k_g_scan<GNC>, (unsigned)nact, HB, 0, d_act, G.tile0, G.ntile, d_tt, d_tc, d_htot5);
+        LAUNCH(c, k_g_mask<false>, (unsigned)nt, HB, 0, c->pos4, c->mom4, has_u, d_ctr, d_moff0, d_members, G, d_tiles, d_vesc2, d_tc, P, d_mask, d_tt, d_changed + q);
+      }
+      int chg[2];
+      CUDA_CHECK(cudaMemcpyAsync(chg, d_changed, sizeof(int) * 2, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      if (!chg[1]) break;
+    }
+    LAUNCH(c, k_g_compact, (unsigned)nt, HB, 0, d_moff0, d_members, G, d_tiles, d_mask, d_tc, d_tmp);
+    LAUNCH(c, k_g_copyback, (unsigned)nt, HB, 0, d_moff0, G, d_tiles, d_htot5, d_tmp, d_members);
+    LAUNCH(c, k_g_iter_finish, nblk(nact, 128), 128, 0, c->pos4, d_ctr, d_moff0, d_members, G, d_act, nact, d_htot5);
+    CUDA_CHECK(cudaMemcpyAsync(h_nrem.data(), G.nremove, sizeof(int64_t) * nhalo, cudaMemcpyDeviceToHost, c->stream));
+    fetch_np();
+    for (int h : act) active[h] = h_nrem[h] > 3 && h_np[h] >= P.min_part;
+  }
+  CUDA_CHECK(cudaMemcpyAsync(d_n7, G.np, sizeof(int64_t) * nhalo, cudaMemcpyDeviceToDevice, c->stream));
+  // ---- rem_outsideRvir, call 1
+  rvir();
+  LAUNCH(c, k_g_write_scal, nblk(nhalo, 128), 128, 0, G, d_ctr, d_ng, d_n6, d_n7, nhalo, P.min_part, c->h_scal, d_np_out);
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  *iter_members = work;
+  for (void *q : { (void *)G.np, (void *)G.nb, (void *)G.nremove, (void *)G.Mvir, (void *)G.Rvir, (void *)G.ovd, (void *)G.Phi0, (void *)G.seed, (void *)G.first,
+                   (void *)G.tile0, (void *)G.ntile, (void *)d_n6, (void *)d_n7, (void *)d_tiles, (void *)d_act, (void *)d_tt, (void *)d_tc, (void *)d_htot1,
+                   (void *)d_htot5, (void *)d_vesc2, (void *)d_Mpre, (void *)d_mask, (void *)d_tmp, (void *)d_changed })
+    ahf::dfree(q);
+}
+
 void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const double *gather_rad, const int64_t *seed)
 {
   c->free_halos();
@@ -1054,16 +1547,21 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
   }
   ahf::dfree(d_r2);
   int64_t *d_np = dalloc<int64_t>(nhalo), *d_work = dalloc<int64_t>(nhalo);
-  {
-    Stage st(c, "halo_unbind", tot_g);
-    LAUNCH(c, k_halo_unbind, (unsigned)nhalo, HB, 0, c->pos4, c->mom4, c->has_u ? 1 : 0, d_ctr, d_moff0, d_ng, d_members, P, c->h_scal, d_np, d_work);
-    CUDA_CHECK(cudaMemcpyAsync(h_np.data(), d_np, sizeof(int64_t) * nhalo, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  }
-  {
+  if (getenv("AHFGPU_UNBIND_V1")) {           // previous form: one CTA per halo (kept for A/B timing)
+    {
+      Stage st(c, "halo_unbind", tot_g);
+      LAUNCH(c, k_halo_unbind, (unsigned)nhalo, HB, 0, c->pos4, c->mom4, c->has_u ? 1 : 0, d_ctr, d_moff0, d_ng, d_members, P, c->h_scal, d_np, d_work);
+      CUDA_CHECK(cudaMemcpyAsync(h_np.data(), d_np, sizeof(int64_t) * nhalo, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
     std::vector<int64_t> h_work(nhalo);
     CUDA_CHECK(cudaMemcpy(h_work.data(), d_work, sizeof(int64_t) * nhalo, cudaMemcpyDeviceToHost));
     int64_t tw = 0; for (auto w : h_work) tw += w;
+    c->stage_cnt_extra["halo_unbind_iter_members"] = tw;
+  } else {
+    Stage st(c, "halo_unbind", tot_g);
+    int64_t tw = 0;
+    unbind_cooperative(c, nhalo, P, d_ctr, d_moff0, moff0, d_ng, h_ng, d_members, tot_g, d_np, h_np, &tw);
     c->stage_cnt_extra["halo_unbind_iter_members"] = tw;
   }
   // offsets of the final member lists, profile bins and scratch
