@@ -999,6 +999,83 @@ __device__ double cr1_root(double c, double R1) { return (c - 2.0 * log(1.0 + c)
 // ------------------------------------------------------------------------------------------------
 constexpr int NACC = 18;   // CoM3, a11 a22 a33 a12 a13 a23, L3, Ekin, Epot, Mhires, Mlores, M, npart
 
+// per-bin cumulative values, Jacobi, profile columns and the integral properties (ahf_halos.c:4632-4710, :4870-5018); one thread
+__device__ void prof_finalize(const int nbins, const double (*acc)[NACC], const double *edge, const double *vesc_bin, const double (*Vc_bin)[3],
+                              double *pr, double *S, const double R_vir, const HP &P, const long long best_j, const float4 *__restrict__ pos4,
+                              const float4 *__restrict__ mom4, const uint32_t *__restrict__ ip, const double c[3])
+{
+  const double F43 = 4. * PI_ / 3.;
+    double cum[NACC];
+    for (int q = 0; q < NACC; q++) cum[q] = 0.0;
+    double M_prev = 0.0, V_prev = 0.0, vesc_run = 0.0, Pl[3] = { 0, 0, 0 };
+    for (int b = 0; b < nbins; b++) {
+      for (int q = 0; q < NACC; q++) cum[q] += acc[b][q];
+      if (acc[b][17] > 0.0) { vesc_run = vesc_bin[b]; Pl[0] = Vc_bin[b][0]; Pl[1] = Vc_bin[b][1]; Pl[2] = Vc_bin[b][2]; }
+      const double cur_rad = edge[b], M = cum[16], Volume = F43 * (cur_rad * cur_rad * cur_rad), dM = M - M_prev, dV = Volume - V_prev;
+      double it[3][3], ax1, ax2, ax3;
+      if (cum[17] > (double)MINPART_SHELL) {
+        it[0][0] = cum[3]; it[1][1] = cum[4]; it[2][2] = cum[5]; it[0][1] = it[1][0] = cum[6]; it[0][2] = it[2][0] = cum[7]; it[1][2] = it[2][1] = cum[8];
+        get_axes(it, ax1, ax2, ax3);
+      } else { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) it[i][j] = 0.0; ax1 = 1; ax2 = 0; ax3 = 0; }
+#define PR(col, bb) pr[(col) * nbins + (bb)]
+      PR(0, b) = cum[17]; PR(1, b) = cur_rad; PR(2, b) = M; PR(3, b) = M / Volume; PR(4, b) = (dV > 0) ? dM / dV : 0.0;
+      PR(5, b) = M / cur_rad; PR(6, b) = vesc_run; PR(7, b) = sqrt(cum[12] / M); PR(8, b) = 0.5 * cum[12]; PR(9, b) = 0.5 * cum[13];
+      PR(10, b) = cum[9]; PR(11, b) = cum[10]; PR(12, b) = cum[11];
+      PR(13, b) = 1.0; PR(14, b) = it[0][0]; PR(15, b) = it[1][0]; PR(16, b) = it[2][0];
+      PR(17, b) = (ax1 > 0.) ? sqrt(ax2 / ax1) : 0.0; PR(18, b) = it[0][1]; PR(19, b) = it[1][1]; PR(20, b) = it[2][1];
+      PR(21, b) = (ax1 > 0.) ? sqrt(ax3 / ax1) : 0.0; PR(22, b) = it[0][2]; PR(23, b) = it[1][2]; PR(24, b) = it[2][2];
+      M_prev = M; V_prev = Volume;
+    }
+    const double M = cum[16];
+    const int    lb = nbins - 1;
+    double CoM[3];
+    for (int q = 0; q < 3; q++) CoM[q] = fmod(cum[q] / M + 1., 1.);
+    double absL = sqrt(PR(10, lb) * PR(10, lb) + PR(11, lb) * PR(11, lb) + PR(12, lb) * PR(12, lb));
+    S[10] = M; S[14] = Pl[0] / M; S[15] = Pl[1] / M; S[16] = Pl[2] / M;
+    S[17] = PR(7, lb); S[18] = PR(6, lb); S[24] = PR(8, lb); S[25] = PR(9, lb);
+    if (absL > 0) {
+      S[38] = PR(10, lb) / absL; S[39] = PR(11, lb) / absL; S[40] = PR(12, lb) / absL;
+      double lam = absL / M / sqrt(2. * M * R_vir);
+      lam *= P.v_fac * sqrt(P.r_fac / (GRAV_ * P.m_fac));
+      S[22] = lam;
+      double t1 = sqrt(P.m_fac * M); t1 = t1 * t1 * t1;
+      double t2 = S[24] * P.m_fac * (P.v_fac * P.v_fac), t3 = S[25] * P.m_fac * P.phi_fac;
+      t2 = sqrt(fabs(t2 + t3)); t1 = t2 / t1; t2 = P.m_fac * P.r_fac * P.v_fac * absL; t2 = t2 / (P.m_fac * M);
+      S[23] = t1 * t2 / GRAV_;
+    } else { S[38] = S[39] = S[40] = 0.0; S[22] = S[23] = 0.0; }
+    S[41] = PR(13, lb); S[42] = PR(17, lb); S[43] = PR(21, lb);
+    S[44] = PR(14, lb); S[45] = PR(15, lb); S[46] = PR(16, lb); S[47] = PR(18, lb); S[48] = PR(19, lb); S[49] = PR(20, lb);
+    S[50] = PR(22, lb); S[51] = PR(23, lb); S[52] = PR(24, lb);
+    {
+      double R1 = (PR(1, 0) / 2.0) * (PR(1, 0) / 2.0) * (PR(1, 0) / 2.0) * PR(4, 0) * PR(1, 0);
+      for (int b = 1; b < nbins; b++) { double rmid = (PR(1, b) + PR(1, b - 1)) / 2.0, dr = PR(1, b) - PR(1, b - 1); R1 += (rmid * rmid * rmid) * PR(4, b) * dr; }
+      R1 = 4 * PI_ * R1 / M / R_vir;
+      S[56] = R1;
+      if (R1 <= 0.19 || 0.585 <= R1) S[55] = -1.0;
+      else { double a = 1.0, b2 = 500.0, cc; while (b2 - a > 1e-3) { cc = (a + b2) / 2; if (cr1_root(a, R1) * cr1_root(cc, R1) > 0) a = cc; else b2 = cc; } S[55] = (a + b2) / 2.0; }
+    }
+    {
+      double Ts = 2.0 * (PR(8, lb) - PR(8, lb - 1)), fr = fabs(PR(1, lb - 1) / PR(1, lb));
+      S[26] = -0.125 * ((1. + fr) * (1. + fr) * (1. + fr)) / (1. - (fr * fr * fr)) * Ts;
+    }
+    S[53] = (cum[14] > 0) ? cum[14] / (cum[14] + cum[15]) : 0.0;
+    if (best_j >= 0) {
+      float4 p = pos4[ip[best_j]], m = mom4[ip[best_j]];
+      double dx = fabs((double)p.x - c[0]), dy = fabs((double)p.y - c[1]), dz = fabs((double)p.z - c[2]);
+      if (dx > 0.5) dx -= 1.0; if (dy > 0.5) dy -= 1.0; if (dz > 0.5) dz -= 1.0;
+      S[37] = sqrt(dx * dx + dy * dy + dz * dz);
+      S[31] = p.x; S[32] = p.y; S[33] = p.z; S[34] = m.x; S[35] = m.y; S[36] = m.z;
+    } else S[37] = -1.0;
+    {
+      double dx = fabs(CoM[0] - c[0]), dy = fabs(CoM[1] - c[1]), dz = fabs(CoM[2] - c[2]);
+      if (dx > 0.5) dx -= 1.0; if (dy > 0.5) dy -= 1.0; if (dz > 0.5) dz -= 1.0;
+      S[30] = sqrt(dx * dx + dy * dy + dz * dz);
+      S[27] = CoM[0]; S[28] = CoM[1]; S[29] = CoM[2];
+    }
+#undef PR
+}
+
+
 __global__ void __launch_bounds__(HB) k_halo_profiles(const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, int has_w, int has_u,
                                                       const double *__restrict__ centre, const int64_t *__restrict__ moff0,
                                                       const uint32_t *__restrict__ members, const int64_t *__restrict__ npart_in, HP P,
@@ -1153,76 +1230,7 @@ __global__ void __launch_bounds__(HB) k_halo_profiles(const float4 *__restrict__
   }
   __syncthreads();
   // ---- per-bin cumulative values, Jacobi, profile columns
-  if (threadIdx.x == 0) {
-    double cum[NACC];
-    for (int q = 0; q < NACC; q++) cum[q] = 0.0;
-    double M_prev = 0.0, V_prev = 0.0, vesc_run = 0.0, Pl[3] = { 0, 0, 0 };
-    for (int b = 0; b < nbins; b++) {
-      for (int q = 0; q < NACC; q++) cum[q] += acc[b][q];
-      if (acc[b][17] > 0.0) { vesc_run = vesc_bin[b]; Pl[0] = Vc_bin[b][0]; Pl[1] = Vc_bin[b][1]; Pl[2] = Vc_bin[b][2]; }
-      const double cur_rad = edge[b], M = cum[16], Volume = F43 * (cur_rad * cur_rad * cur_rad), dM = M - M_prev, dV = Volume - V_prev;
-      double it[3][3], ax1, ax2, ax3;
-      if (cum[17] > (double)MINPART_SHELL) {
-        it[0][0] = cum[3]; it[1][1] = cum[4]; it[2][2] = cum[5]; it[0][1] = it[1][0] = cum[6]; it[0][2] = it[2][0] = cum[7]; it[1][2] = it[2][1] = cum[8];
-        get_axes(it, ax1, ax2, ax3);
-      } else { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) it[i][j] = 0.0; ax1 = 1; ax2 = 0; ax3 = 0; }
-#define PR(col, bb) pr[(col) * nbins + (bb)]
-      PR(0, b) = cum[17]; PR(1, b) = cur_rad; PR(2, b) = M; PR(3, b) = M / Volume; PR(4, b) = (dV > 0) ? dM / dV : 0.0;
-      PR(5, b) = M / cur_rad; PR(6, b) = vesc_run; PR(7, b) = sqrt(cum[12] / M); PR(8, b) = 0.5 * cum[12]; PR(9, b) = 0.5 * cum[13];
-      PR(10, b) = cum[9]; PR(11, b) = cum[10]; PR(12, b) = cum[11];
-      PR(13, b) = 1.0; PR(14, b) = it[0][0]; PR(15, b) = it[1][0]; PR(16, b) = it[2][0];
-      PR(17, b) = (ax1 > 0.) ? sqrt(ax2 / ax1) : 0.0; PR(18, b) = it[0][1]; PR(19, b) = it[1][1]; PR(20, b) = it[2][1];
-      PR(21, b) = (ax1 > 0.) ? sqrt(ax3 / ax1) : 0.0; PR(22, b) = it[0][2]; PR(23, b) = it[1][2]; PR(24, b) = it[2][2];
-      M_prev = M; V_prev = Volume;
-    }
-    const double M = cum[16];
-    const int    lb = nbins - 1;
-    double CoM[3];
-    for (int q = 0; q < 3; q++) CoM[q] = fmod(cum[q] / M + 1., 1.);
-    double absL = sqrt(PR(10, lb) * PR(10, lb) + PR(11, lb) * PR(11, lb) + PR(12, lb) * PR(12, lb));
-    S[10] = M; S[14] = Pl[0] / M; S[15] = Pl[1] / M; S[16] = Pl[2] / M;
-    S[17] = PR(7, lb); S[18] = PR(6, lb); S[24] = PR(8, lb); S[25] = PR(9, lb);
-    if (absL > 0) {
-      S[38] = PR(10, lb) / absL; S[39] = PR(11, lb) / absL; S[40] = PR(12, lb) / absL;
-      double lam = absL / M / sqrt(2. * M * R_vir);
-      lam *= P.v_fac * sqrt(P.r_fac / (GRAV_ * P.m_fac));
-      S[22] = lam;
-      double t1 = sqrt(P.m_fac * M); t1 = t1 * t1 * t1;
-      double t2 = S[24] * P.m_fac * (P.v_fac * P.v_fac), t3 = S[25] * P.m_fac * P.phi_fac;
-      t2 = sqrt(fabs(t2 + t3)); t1 = t2 / t1; t2 = P.m_fac * P.r_fac * P.v_fac * absL; t2 = t2 / (P.m_fac * M);
-      S[23] = t1 * t2 / GRAV_;
-    } else { S[38] = S[39] = S[40] = 0.0; S[22] = S[23] = 0.0; }
-    S[41] = PR(13, lb); S[42] = PR(17, lb); S[43] = PR(21, lb);
-    S[44] = PR(14, lb); S[45] = PR(15, lb); S[46] = PR(16, lb); S[47] = PR(18, lb); S[48] = PR(19, lb); S[49] = PR(20, lb);
-    S[50] = PR(22, lb); S[51] = PR(23, lb); S[52] = PR(24, lb);
-    {
-      double R1 = (PR(1, 0) / 2.0) * (PR(1, 0) / 2.0) * (PR(1, 0) / 2.0) * PR(4, 0) * PR(1, 0);
-      for (int b = 1; b < nbins; b++) { double rmid = (PR(1, b) + PR(1, b - 1)) / 2.0, dr = PR(1, b) - PR(1, b - 1); R1 += (rmid * rmid * rmid) * PR(4, b) * dr; }
-      R1 = 4 * PI_ * R1 / M / R_vir;
-      S[56] = R1;
-      if (R1 <= 0.19 || 0.585 <= R1) S[55] = -1.0;
-      else { double a = 1.0, b2 = 500.0, cc; while (b2 - a > 1e-3) { cc = (a + b2) / 2; if (cr1_root(a, R1) * cr1_root(cc, R1) > 0) a = cc; else b2 = cc; } S[55] = (a + b2) / 2.0; }
-    }
-    {
-      double Ts = 2.0 * (PR(8, lb) - PR(8, lb - 1)), fr = fabs(PR(1, lb - 1) / PR(1, lb));
-      S[26] = -0.125 * ((1. + fr) * (1. + fr) * (1. + fr)) / (1. - (fr * fr * fr)) * Ts;
-    }
-    S[53] = (cum[14] > 0) ? cum[14] / (cum[14] + cum[15]) : 0.0;
-    if (best_j >= 0) {
-      float4 p = pos4[ip[best_j]], m = mom4[ip[best_j]];
-      double dx = fabs((double)p.x - c[0]), dy = fabs((double)p.y - c[1]), dz = fabs((double)p.z - c[2]);
-      if (dx > 0.5) dx -= 1.0; if (dy > 0.5) dy -= 1.0; if (dz > 0.5) dz -= 1.0;
-      S[37] = sqrt(dx * dx + dy * dy + dz * dz);
-      S[31] = p.x; S[32] = p.y; S[33] = p.z; S[34] = m.x; S[35] = m.y; S[36] = m.z;
-    } else S[37] = -1.0;
-    {
-      double dx = fabs(CoM[0] - c[0]), dy = fabs(CoM[1] - c[1]), dz = fabs(CoM[2] - c[2]);
-      if (dx > 0.5) dx -= 1.0; if (dy > 0.5) dy -= 1.0; if (dz > 0.5) dz -= 1.0;
-      S[30] = sqrt(dx * dx + dy * dy + dz * dz);
-      S[27] = CoM[0]; S[28] = CoM[1]; S[29] = CoM[2];
-    }
-#undef PR
-  }
+  if (threadIdx.x == 0) prof_finalize(nbins, acc, edge, vesc_bin, Vc_bin, pr, S, R_vir, P, best_j, pos4, mom4, ip, c);
   __syncthreads();
   // ---- R_max / r2 from per-member arrays (find_max, general.c:608-650; smooth3 :548-573)
   // M(<=j): equal masses -> j+1; general -> recomputed by a scan while filling y
@@ -1324,6 +1332,387 @@ __global__ void __launch_bounds__(HB) k_halo_profiles(const float4 *__restrict__
       S[54] = calc_cNFW(V_max, S[10] / R_vir);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// P1, cooperative multi-block form (default): the tiles of all haloes in one grid, like the unbinding pass.
+//   k_p_bins    per halo: binning_parameter
+//   k_p_sum     per tile: totals of (w, w*mom) and the first / last radial bin the tile touches
+//   k_g_scan<4> per halo: carries of M and P
+//   k_p_phi     per tile: trapezoid total of Phi (needs M carry)            -> k_g_scan<1>
+//   k_p_main    per tile: every per-member quantity; per (tile, bin) sums of the NACC accumulators in a fixed order
+//   k_p_finish  per halo: sums the (tile, bin) partials in tile order, then prof_finalize
+//   k_p_smooth / k_p_argmax / k_p_vmax: find_max of rho r^2 (3 smoothing passes) and v_circ^2 (1 pass), V_max
+// ------------------------------------------------------------------------------------------------
+struct PG {
+  const int64_t *np;        // final member count per halo
+  const int32_t *tile0, *ntile;
+  double  *edge;            // [nhalo][MAXBINS]
+  double  *vesc_bin;        // [nhalo][MAXBINS]
+  double  *Vc_bin;          // [nhalo][MAXBINS][3]
+  int32_t *tile_blo, *tile_ns;      // per tile: first bin, number of bins touched
+  const int32_t *slot_off;          // per tile: offset into the partial sums
+  double  *partial;         // [slots][NACC]
+  double  *tbest_e; long long *tbest_j;   // per tile: most bound member
+  double  *w_r, *y0a, *y0b, *y1a, *y1b, *Mpre;   // per member (moff0 layout); Mpre only with weights
+};
+
+__device__ __forceinline__ int bin_of(double rp, const double *__restrict__ edge, int nbins, int b)
+{
+  while (b < nbins - 1 && !(rp < edge[b])) b++;
+  return b;
+}
+
+__global__ void k_p_bins(const float4 *__restrict__ pos4, const double *__restrict__ centre, const int64_t *__restrict__ moff0, const uint32_t *__restrict__ members,
+                         PG G, const int32_t *__restrict__ act, int nact, const double *__restrict__ scal, HP P)
+{
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nact) return;
+  const int h = act[a];
+  const long long np = G.np[h];
+  const uint32_t *ip = members + moff0[h];
+  const double c[3] = { centre[3 * h], centre[3 * h + 1], centre[3 * h + 2] };
+  const int nbins = (int)scal[(size_t)h * AHFGPU_NSCAL + 57];
+  double *edge = G.edge + (size_t)h * MAXBINS;
+  long long k = (long long)floor(((double)P.min_part / 10.) + 0.5);          // binning_parameter (specific.c:259-322)
+  double dmin = -1.0;
+  while (k < np - 1 && dmin < MACHINE_ZERO) { dmin = dist3(pos4[ip[k]], c); k++; }
+  const double dmax = dist3(pos4[ip[np - 1]], c);
+  if (dmin < MACHINE_ZERO) dmin = dmax / 2.;
+  const double ldmin = log10(dmin), ldmax = log10(dmax), ldr = (ldmax - ldmin) / (double)nbins;
+  for (int b = 0; b < nbins; b++) edge[b] = pow(10., ldmin + ((double)b + 1) * ldr);
+  edge[nbins - 1] = dmax + ZERO_F;                                           // ahf_halos.c:4226-4241
+}
+
+__global__ void __launch_bounds__(HB) k_p_sum(const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, const double *__restrict__ centre,
+                                              const int64_t *__restrict__ moff0, const uint32_t *__restrict__ members, PG G, const int2 *__restrict__ tiles,
+                                              const double *__restrict__ scal, double *__restrict__ tt)
+{
+  __shared__ double smd[(HB / 32) * 4];
+  const int2 tl = tiles[blockIdx.x];
+  const int  h = tl.x; const long long base = (long long)tl.y * HT, np = G.np[h];
+  const uint32_t *ip = members + moff0[h];
+  double loc[4] = { 0, 0, 0, 0 };
+#pragma unroll
+  for (int i = 0; i < HI; i++) {
+    const long long j = base + (long long)threadIdx.x * HI + i;
+    if (j < np) { const uint32_t pid = ip[j]; const double w = (double)pos4[pid].w; const float4 m = mom4[pid]; loc[0] += w; loc[1] += w * m.x; loc[2] += w * m.y; loc[3] += w * m.z; }
+  }
+  block_sum_n<4>(loc, smd);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) tt[(size_t)blockIdx.x * 4 + q] = loc[q];
+    // bins of the tile's first and last member: the first bin whose edge exceeds the radius of the member BEFORE (ahf_halos.c:4283)
+    const double c[3] = { centre[3 * h], centre[3 * h + 1], centre[3 * h + 2] };
+    const int nbins = (int)scal[(size_t)h * AHFGPU_NSCAL + 57];
+    const double *edge = G.edge + (size_t)h * MAXBINS;
+    const long long last = (base + HT < np ? base + HT : np) - 1;
+    const double rp0 = base ? dist3(pos4[ip[base - 1]], c) : -1.0, rp1 = last ? dist3(pos4[ip[last - 1]], c) : -1.0;
+    const int blo = bin_of(rp0, edge, nbins, 0), bhi = bin_of(rp1, edge, nbins, blo);
+    G.tile_blo[blockIdx.x] = blo; G.tile_ns[blockIdx.x] = bhi - blo + 1;
+  }
+}
+
+// M(<=j), tile-local scan + carry (weights) or index + 1 (equal masses)
+__device__ __forceinline__ void p_tile_M(const TileMembers &T, int has_w, double carryM, long long base, double (&M)[HI], double *smd)
+{
+  if (!has_w) {
+#pragma unroll
+    for (int i = 0; i < HI; i++) M[i] = (double)(base + (long long)threadIdx.x * HI + i + 1);
+    return;
+  }
+  double loc[1] = { 0.0 }, ex[1], tot[1];
+#pragma unroll
+  for (int i = 0; i < HI; i++) loc[0] += T.w[i];
+  block_excl_scan_n<1>(loc, ex, tot, smd);
+  double run = carryM + ex[0];
+#pragma unroll
+  for (int i = 0; i < HI; i++) { run += T.w[i]; M[i] = run; }
+  __syncthreads();
+}
+__device__ __forceinline__ void p_prev_member(const float4 *__restrict__ pos4, const uint32_t *__restrict__ ip, int has_w, double carryM, long long base,
+                                              const double c[3], double &prev_r, double &prev_I)
+{
+  prev_r = 0.0; prev_I = 0.0;
+  if (base > 0) {
+    prev_r = dist3(pos4[ip[base - 1]], c);
+    const double Mp = has_w ? carryM : (double)base;          // M(<= base-1) = carry of the tile
+    prev_I = prev_r > MACHINE_ZERO ? Mp / (prev_r * prev_r) : 0.0;
+  }
+}
+__global__ void __launch_bounds__(HB) k_p_phi(const float4 *__restrict__ pos4, int has_w, const double *__restrict__ centre, const int64_t *__restrict__ moff0,
+                                              const uint32_t *__restrict__ members, PG G, const int2 *__restrict__ tiles, const double *__restrict__ tc4,
+                                              double *__restrict__ tt)
+{
+  __shared__ double smd[HB / 32];
+  __shared__ double nb_r[HB], nb_I[HB];
+  const int2 tl = tiles[blockIdx.x];
+  const int  h = tl.x; const long long base = (long long)tl.y * HT, np = G.np[h];
+  const double c[3] = { centre[3 * h], centre[3 * h + 1], centre[3 * h + 2] };
+  const uint32_t *ip = members + moff0[h];
+  TileMembers T;
+  load_tile(T, pos4, ip, base, np, c);
+  const double carryM = tc4[(size_t)blockIdx.x * 4];
+  double M[HI], term[HI], prev_r, prev_I;
+  p_tile_M(T, has_w, carryM, base, M, smd);
+  p_prev_member(pos4, ip, has_w, carryM, base, c, prev_r, prev_I);
+  double loc = g_tile_phi(T, M, prev_r, prev_I, term, nb_r, nb_I);
+  loc = block_sum(loc, smd);
+  if (threadIdx.x == 0) tt[blockIdx.x] = loc;
+}
+
+__global__ void __launch_bounds__(HB) k_p_main(const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, int has_w, int has_u, const double *__restrict__ centre,
+                                               const int64_t *__restrict__ moff0, const uint32_t *__restrict__ members, PG G, const int2 *__restrict__ tiles,
+                                               const double *__restrict__ tc4, const double *__restrict__ tcphi, const double *__restrict__ scal, HP P)
+{
+  __shared__ double smd[(HB / 32) * NACC];
+  __shared__ double edge[MAXBINS];
+  __shared__ double nb_r[HB], nb_I[HB];
+  __shared__ double s_emin[HB / 32]; __shared__ long long s_eidx[HB / 32];
+  const int2 tl = tiles[blockIdx.x];
+  const int  h = tl.x; const long long base = (long long)tl.y * HT, np = G.np[h];
+  const double c[3] = { centre[3 * h], centre[3 * h + 1], centre[3 * h + 2] };
+  const uint32_t *ip = members + moff0[h];
+  const double *S = scal + (size_t)h * AHFGPU_NSCAL;
+  const int    nbins = (int)S[57];
+  const double Phi0 = S[13];
+  const double F43 = 4. * PI_ / 3.;
+  for (int i = threadIdx.x; i < nbins; i += HB) edge[i] = G.edge[(size_t)h * MAXBINS + i];
+  TileMembers T;
+  load_tile(T, pos4, ip, base, np, c);
+  double mom[HI][3], uu[HI], M[HI], Phi[HI], Pc[HI][3];
+#pragma unroll
+  for (int i = 0; i < HI; i++) {
+    mom[i][0] = mom[i][1] = mom[i][2] = 0.0; uu[i] = -1.0;
+    if (T.act[i]) { float4 m = mom4[T.pid[i]]; mom[i][0] = (double)m.x; mom[i][1] = (double)m.y; mom[i][2] = (double)m.z; uu[i] = (double)m.w; }
+  }
+  __syncthreads();
+  const double carryM = tc4[(size_t)blockIdx.x * 4];
+  p_tile_M(T, has_w, carryM, base, M, smd);
+  {
+    double loc[3] = { 0, 0, 0 }, ex[3], tot[3];
+#pragma unroll
+    for (int i = 0; i < HI; i++) { loc[0] += T.w[i] * mom[i][0]; loc[1] += T.w[i] * mom[i][1]; loc[2] += T.w[i] * mom[i][2]; }
+    block_excl_scan_n<3>(loc, ex, tot, smd);
+    double run[3] = { tc4[(size_t)blockIdx.x * 4 + 1] + ex[0], tc4[(size_t)blockIdx.x * 4 + 2] + ex[1], tc4[(size_t)blockIdx.x * 4 + 3] + ex[2] };
+#pragma unroll
+    for (int i = 0; i < HI; i++) {
+#pragma unroll
+      for (int q = 0; q < 3; q++) { run[q] += T.w[i] * mom[i][q]; Pc[i][q] = run[q]; }
+    }
+    __syncthreads();
+  }
+  double prev_r, prev_I;
+  p_prev_member(pos4, ip, has_w, carryM, base, c, prev_r, prev_I);
+  {
+    double term[HI], loc[1], ex[1], tot[1];
+    loc[0] = g_tile_phi(T, M, prev_r, prev_I, term, nb_r, nb_I);
+    block_excl_scan_n<1>(loc, ex, tot, smd);
+    double run = tcphi[blockIdx.x] + ex[0];
+#pragma unroll
+    for (int i = 0; i < HI; i++) { run += term[i]; Phi[i] = run; }
+  }
+  // radius of the member before each of the thread's members (r_{-1}: -1 for binning, 0 for the per-member arrays)
+  const double rr_in = (base == 0) ? -1.0 : prev_r;
+  int bin[HI];
+  double rprev[HI];
+  {
+    double rp = threadIdx.x ? nb_r[threadIdx.x - 1] : rr_in;
+    int b = 0;
+#pragma unroll
+    for (int i = 0; i < HI; i++) { b = bin_of(rp, edge, nbins, b); bin[i] = b; rprev[i] = rp; rp = T.r[i]; }
+  }
+  const int blo = G.tile_blo[blockIdx.x], bhi = blo + G.tile_ns[blockIdx.x] - 1;
+  double Tp[HI], Up[HI], Lm[HI][3];
+  double best_e = 1e30; long long best_j = 0x7fffffffffffffffll;
+#pragma unroll
+  for (int i = 0; i < HI; i++) {
+    Tp[i] = Up[i] = 0.0; Lm[i][0] = Lm[i][1] = Lm[i][2] = 0.0;
+    if (T.act[i]) {
+      const double w = T.w[i];
+      double dvx = mom[i][0] - Pc[i][0] / M[i], dvy = mom[i][1] - Pc[i][1] / M[i], dvz = mom[i][2] - Pc[i][2] / M[i];   // :4363-4370 mean INCLUDING j
+      Lm[i][0] = w * (T.d[i][1] * dvz - T.d[i][2] * dvy);
+      Lm[i][1] = w * (T.d[i][2] * dvx - T.d[i][0] * dvz);
+      Lm[i][2] = w * (T.d[i][0] * dvy - T.d[i][1] * dvx);
+      dvx += P.hubble * T.d[i][0] * P.r_fac / P.v_fac; dvy += P.hubble * T.d[i][1] * P.r_fac / P.v_fac; dvz += P.hubble * T.d[i][2] * P.r_fac / P.v_fac;
+      Tp[i] = w * (dvx * dvx + dvy * dvy + dvz * dvz);
+      Up[i] = (Phi[i] - Phi0) * w;
+      const double vesc2 = 2 * fabs(Up[i]) / w;
+      if (has_u && uu[i] >= 0.0) Tp[i] += w * (2 * uu[i] / (P.v_fac * P.v_fac));
+      const long long j = base + (long long)threadIdx.x * HI + i;
+      const long long e = moff0[h] + j;
+      // per-member arrays of find_max (ahf_halos.c:4598-4616): r, rho r^2, v_circ^2
+      const double r = T.r[i], rpv = j ? rprev[i] : 0.0, dV = F43 * ((r * r * r) - (rpv * rpv * rpv));
+      G.w_r[e] = r; G.y0a[e] = w / dV * (((r + rpv) / 2.) * ((r + rpv) / 2.)); G.y1a[e] = M[i] / r;
+      if (has_w) G.Mpre[e] = M[i];
+      // the last member of a bin owns the bin's v_esc2 and cumulative momentum
+      bool lastofbin = (j == np - 1);
+      if (!lastofbin) lastofbin = bin_of(r, edge, nbins, bin[i]) != bin[i];
+      if (lastofbin) {
+        G.vesc_bin[(size_t)h * MAXBINS + bin[i]] = vesc2;
+        double *vc = G.Vc_bin + ((size_t)h * MAXBINS + bin[i]) * 3; vc[0] = Pc[i][0]; vc[1] = Pc[i][1]; vc[2] = Pc[i][2];
+      }
+      const double Epart = 0.5 * Tp[i] + Up[i];
+      if (Epart < best_e) { best_e = Epart; best_j = j; }
+    }
+  }
+  for (int b = blo; b <= bhi; b++) {
+    double s[NACC];
+#pragma unroll
+    for (int q = 0; q < NACC; q++) s[q] = 0.0;
+#pragma unroll
+    for (int i = 0; i < HI; i++) {
+      if (T.act[i] && bin[i] == b) {
+        const double w = T.w[i];
+        s[0] += w * (c[0] + T.d[i][0]); s[1] += w * (c[1] + T.d[i][1]); s[2] += w * (c[2] + T.d[i][2]);
+        s[3] += w * T.d[i][0] * T.d[i][0]; s[4] += w * T.d[i][1] * T.d[i][1]; s[5] += w * T.d[i][2] * T.d[i][2];
+        s[6] += w * T.d[i][0] * T.d[i][1]; s[7] += w * T.d[i][0] * T.d[i][2]; s[8] += w * T.d[i][1] * T.d[i][2];
+        s[9] += Lm[i][0]; s[10] += Lm[i][1]; s[11] += Lm[i][2];
+        s[12] += Tp[i]; s[13] += Up[i];
+        if (has_w) { if (fabs(w - 1.0) < ZERO_F) s[14] += w; else if (w > 1.0) s[15] += w; } else s[14] += w;
+        s[16] += w; s[17] += 1.0;
+      }
+    }
+    block_sum_n<NACC>(s, smd);
+    if (threadIdx.x == 0) {
+      double *dst = G.partial + ((size_t)G.slot_off[blockIdx.x] + (b - blo)) * NACC;
+#pragma unroll
+      for (int q = 0; q < NACC; q++) dst[q] = s[q];
+    }
+  }
+  // most bound member of the tile: minimum of 0.5 T + U, first index on ties (:4590-4596)
+  {
+    double e = best_e; long long jj = best_j;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double e2 = __shfl_xor_sync(0xffffffffu, e, o); long long j2 = __shfl_xor_sync(0xffffffffu, jj, o);
+      if (e2 < e || (e2 == e && j2 < jj)) { e = e2; jj = j2; }
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { s_emin[threadIdx.x >> 5] = e; s_eidx[threadIdx.x >> 5] = jj; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      e = s_emin[0]; jj = s_eidx[0];
+      for (int q = 1; q < HB / 32; q++) if (s_emin[q] < e || (s_emin[q] == e && s_eidx[q] < jj)) { e = s_emin[q]; jj = s_eidx[q]; }
+      G.tbest_e[blockIdx.x] = e; G.tbest_j[blockIdx.x] = jj;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(HB) k_p_finish(const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, const double *__restrict__ centre,
+                                                 const int64_t *__restrict__ moff0, const uint32_t *__restrict__ members, PG G, const int32_t *__restrict__ act,
+                                                 double *__restrict__ scal, const int64_t *__restrict__ poff, double *__restrict__ prof, HP P)
+{
+  __shared__ double acc[MAXBINS][NACC];
+  __shared__ double edge[MAXBINS], vesc_bin[MAXBINS], Vc_bin[MAXBINS][3];
+  const int h = act[blockIdx.x];
+  double *S = scal + (size_t)h * AHFGPU_NSCAL;
+  const int nbins = (int)S[57], t0 = G.tile0[h], nt = G.ntile[h];
+  for (int idx = threadIdx.x; idx < nbins * NACC; idx += HB) {       // (bin, component): partials summed in tile order
+    const int b = idx / NACC, q = idx - b * NACC;
+    double a = 0.0;
+    for (int t = t0; t < t0 + nt; t++) {
+      const int blo = G.tile_blo[t];
+      if (b >= blo && b < blo + G.tile_ns[t]) a += G.partial[((size_t)G.slot_off[t] + (b - blo)) * NACC + q];
+    }
+    acc[b][q] = a;
+  }
+  for (int i = threadIdx.x; i < nbins; i += HB) {
+    edge[i] = G.edge[(size_t)h * MAXBINS + i]; vesc_bin[i] = G.vesc_bin[(size_t)h * MAXBINS + i];
+    for (int q = 0; q < 3; q++) Vc_bin[i][q] = G.Vc_bin[((size_t)h * MAXBINS + i) * 3 + q];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double e = 1e30; long long bj = -1;
+    for (int t = t0; t < t0 + nt; t++) {
+      const long long jj = G.tbest_j[t];
+      if (jj != 0x7fffffffffffffffll && (G.tbest_e[t] < e || bj < 0)) { e = G.tbest_e[t]; bj = jj; }
+    }
+    const double c[3] = { centre[3 * h], centre[3 * h + 1], centre[3 * h + 2] };
+    prof_finalize(nbins, acc, edge, vesc_bin, Vc_bin, prof + poff[h] * AHFGPU_NPROFCOL, S, S[11], P, bj, pos4, mom4, members + moff0[h], c);
+  }
+}
+
+// smooth3 (general.c:548-573) of both per-member arrays, offset by NIGNORE; `both` = 0 smooths only rho r^2
+__global__ void __launch_bounds__(HB) k_p_smooth(const int64_t *__restrict__ moff0, PG G, const int2 *__restrict__ tiles, const double *__restrict__ a0,
+                                                 double *__restrict__ b0, const double *__restrict__ a1, double *__restrict__ b1, int both)
+{
+  const int2 tl = tiles[blockIdx.x];
+  const int  h = tl.x; const long long base = (long long)tl.y * HT, np = G.np[h], nn = np - NIGNORE, o = moff0[h] + NIGNORE;
+#pragma unroll
+  for (int k = 0; k < HI; k++) {
+    const long long i = base + threadIdx.x + (long long)k * HB - NIGNORE;
+    if (i < 0 || i >= nn) continue;
+    for (int w = 0; w < (both ? 2 : 1); w++) {
+      const double *ya = (w ? a1 : a0) + o; double *yb = (w ? b1 : b0) + o;
+      double t;
+      if (nn < 3) t = ya[i];
+      else if (i == 0) t = (ya[0] + ya[1]) / 2.;
+      else if (i == nn - 1) t = (ya[nn - 1] + ya[nn - 2]) / 2.;
+      else t = (ya[i - 1] + ya[i] + ya[i + 1]) / 3.;
+      yb[i] = t;
+    }
+  }
+}
+// first index of the maximum over [0, nn-2] with y > -10, per tile (find_max, general.c:608-650: the right-to-left pass can never improve on it)
+__global__ void __launch_bounds__(HB) k_p_argmax(const int64_t *__restrict__ moff0, PG G, const int2 *__restrict__ tiles, const double *__restrict__ y0,
+                                                 const double *__restrict__ y1, double *__restrict__ tval, long long *__restrict__ tidx)
+{
+  __shared__ double s_v[HB / 32]; __shared__ long long s_i[HB / 32];
+  const int2 tl = tiles[blockIdx.x];
+  const int  h = tl.x; const long long base = (long long)tl.y * HT, np = G.np[h], nn = np - NIGNORE, o = moff0[h] + NIGNORE;
+  for (int w = 0; w < 2; w++) {
+    const double *y = (w ? y1 : y0) + o;
+    double bv = -10.0; long long bi = 0x7fffffffffffffffll;
+#pragma unroll
+    for (int k = 0; k < HI; k++) {
+      const long long i = base + threadIdx.x + (long long)k * HB - NIGNORE;
+      if (i >= 0 && i < nn - 1) { const double v = y[i]; if (v > bv) { bv = v; bi = i; } }
+    }
+#pragma unroll
+    for (int q = 16; q > 0; q >>= 1) {
+      double v2 = __shfl_xor_sync(0xffffffffu, bv, q); long long i2 = __shfl_xor_sync(0xffffffffu, bi, q);
+      if (v2 > bv || (v2 == bv && i2 < bi)) { bv = v2; bi = i2; }
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = bv; s_i[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      bv = s_v[0]; bi = s_i[0];
+      for (int q = 1; q < HB / 32; q++) if (s_v[q] > bv || (s_v[q] == bv && s_i[q] < bi)) { bv = s_v[q]; bi = s_i[q]; }
+      tval[(size_t)blockIdx.x * 2 + w] = bv; tidx[(size_t)blockIdx.x * 2 + w] = bi;
+    }
+  }
+}
+// R_max, r2, V_max (:4875-4901), cNFW
+__global__ void k_p_vmax(const int64_t *__restrict__ moff0, PG G, const int32_t *__restrict__ act, int nact, int has_w, const double *__restrict__ tval,
+                         const long long *__restrict__ tidx, double *__restrict__ scal)
+{
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nact) return;
+  const int h = act[a];
+  const long long np = G.np[h], nn = np - NIGNORE;
+  const int t0 = G.tile0[h], nt = G.ntile[h];
+  const double *w_r = G.w_r + moff0[h];
+  double *S = scal + (size_t)h * AHFGPU_NSCAL;
+  const double F43 = 4. * PI_ / 3.;
+  double xm[2];
+  for (int w = 0; w < 2; w++) {
+    double bv = -10.0; long long bi = nn - 1;
+    for (int t = t0; t < t0 + nt; t++) {
+      const double v = tval[(size_t)t * 2 + w]; const long long i = tidx[(size_t)t * 2 + w];
+      if (i != 0x7fffffffffffffffll && v > bv) { bv = v; bi = i; }
+    }
+    long long k = NIGNORE + bi; if (k < 0) k = 0;
+    xm[w] = w_r[k];
+  }
+  const double x_r2 = xm[0], x_rmax = xm[1];
+  long long lo = 0, hi = np - 1;                       // radii ascend: first j with !(r_j < x_rmax), capped at np-1
+  while (lo < hi) { long long mid = lo + ((hi - lo) >> 1); if (w_r[mid] < x_rmax) lo = mid + 1; else hi = mid; }
+  const double r = w_r[lo], Mlo = has_w ? G.Mpre[moff0[h] + lo] : (double)(lo + 1);
+  const double od = Mlo / (F43 * (r * r * r)), M_max = od * F43 * (r * r * r), V_max = M_max / x_rmax;
+  S[19] = V_max; S[20] = x_rmax; S[21] = x_r2;
+  S[54] = calc_cNFW(V_max, S[10] / S[11]);
 }
 
 __global__ void k_members_out(const int64_t *__restrict__ moff0, const int64_t *__restrict__ npart, const int64_t *__restrict__ moff, const uint32_t *__restrict__ members,
@@ -1467,6 +1856,61 @@ static void unbind_cooperative(ahfgpu_ctx *c, int64_t nhalo, const HP &P, const 
     ahf::dfree(q);
 }
 
+// host side of the cooperative P1 pass
+static void profiles_cooperative(ahfgpu_ctx *c, int64_t nhalo, const HP &P, const double *d_ctr, const int64_t *d_moff0, const uint32_t *d_members,
+                                 int64_t tot_g, const int64_t *d_np, const std::vector<int64_t> &h_np)
+{
+  const int has_w = c->has_weight ? 1 : 0, has_u = c->has_u ? 1 : 0;
+  std::vector<int32_t> act, tile0(nhalo, 0), ntile(nhalo, 0);
+  std::vector<int2>    tiles;
+  for (int64_t h = 0; h < nhalo; h++) {
+    if (h_np[h] < P.min_part) continue;
+    act.push_back((int32_t)h);
+    tile0[h] = (int32_t)tiles.size(); ntile[h] = (int32_t)((h_np[h] + HT - 1) / HT);
+    for (int t = 0; t < ntile[h]; t++) tiles.push_back(make_int2((int)h, t));
+  }
+  const int nact = (int)act.size(), nt = (int)tiles.size();
+  if (!nact) return;
+  int32_t *d_act = dalloc<int32_t>(nact), *d_tile0 = dalloc<int32_t>(nhalo), *d_ntile = dalloc<int32_t>(nhalo);
+  int2    *d_tiles = dalloc<int2>(nt);
+  CUDA_CHECK(cudaMemcpyAsync(d_act, act.data(), sizeof(int32_t) * nact, cudaMemcpyHostToDevice, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(d_tile0, tile0.data(), sizeof(int32_t) * nhalo, cudaMemcpyHostToDevice, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(d_ntile, ntile.data(), sizeof(int32_t) * nhalo, cudaMemcpyHostToDevice, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(int2) * nt, cudaMemcpyHostToDevice, c->stream));
+  PG G;
+  G.np = d_np; G.tile0 = d_tile0; G.ntile = d_ntile;
+  G.edge = dalloc<double>((size_t)nhalo * MAXBINS); G.vesc_bin = dalloc<double>((size_t)nhalo * MAXBINS); G.Vc_bin = dalloc<double>((size_t)nhalo * MAXBINS * 3);
+  CUDA_CHECK(cudaMemsetAsync(G.vesc_bin, 0, sizeof(double) * nhalo * MAXBINS, c->stream));
+  CUDA_CHECK(cudaMemsetAsync(G.Vc_bin, 0, sizeof(double) * nhalo * MAXBINS * 3, c->stream));
+  G.tile_blo = dalloc<int32_t>(nt); G.tile_ns = dalloc<int32_t>(nt);
+  int32_t *d_slot = dalloc<int32_t>(nt);
+  G.slot_off = d_slot;
+  G.tbest_e = dalloc<double>(nt); G.tbest_j = dalloc<long long>(nt);
+  G.w_r = dalloc<double>(tot_g); G.y0a = dalloc<double>(tot_g); G.y0b = dalloc<double>(tot_g); G.y1a = dalloc<double>(tot_g); G.y1b = dalloc<double>(tot_g);
+  G.Mpre = has_w ? dalloc<double>(tot_g) : nullptr;
+  double *d_tt4 = dalloc<double>((size_t)nt * 4), *d_tc4 = dalloc<double>((size_t)nt * 4), *d_ht4 = dalloc<double>((size_t)nhalo * 4);
+  double *d_tt1 = dalloc<double>(nt), *d_tc1 = dalloc<double>(nt), *d_ht1 = dalloc<double>(nhalo);
+  double *d_tval = dalloc<double>((size_t)nt * 2); long long *d_tidx = dalloc<long long>((size_t)nt * 2);
+  LAUNCH(c, k_p_bins, nblk(nact, 64), 64, 0, c->pos4, d_ctr, d_moff0, d_members, G, d_act, nact, c->h_scal, P);
+  LAUNCH(c, k_p_sum, (unsigned)nt, HB, 0, c->pos4, c->mom4, d_ctr, d_moff0, d_members, G, d_tiles, c->h_scal, d_tt4);
+  LAUNCH(c, k_g_scan<4>, (unsigned)nact, HB, 0, d_act, d_tile0, d_ntile, d_tt4, d_tc4, d_ht4);
+  LAUNCH(c, k_p_phi, (unsigned)nt, HB, 0, c->pos4, has_w, d_ctr, d_moff0, d_members, G, d_tiles, d_tc4, d_tt1);
+  LAUNCH(c, k_g_scan<1>, (unsigned)nact, HB, 0, d_act, d_tile0, d_ntile, d_tt1, d_tc1, d_ht1);
+  const int nslot = exclusive_scan<int32_t>(c, G.tile_ns, d_slot, (uint64_t)nt);
+  G.partial = dalloc<double>((size_t)nslot * NACC);
+  LAUNCH(c, k_p_main, (unsigned)nt, HB, 0, c->pos4, c->mom4, has_w, has_u, d_ctr, d_moff0, d_members, G, d_tiles, d_tc4, d_tc1, c->h_scal, P);
+  LAUNCH(c, k_p_finish, (unsigned)nact, HB, 0, c->pos4, c->mom4, d_ctr, d_moff0, d_members, G, d_act, c->h_scal, c->h_poff, c->h_prof, P);
+  LAUNCH(c, k_p_smooth, (unsigned)nt, HB, 0, d_moff0, G, d_tiles, G.y0a, G.y0b, G.y1a, G.y1b, 1);
+  LAUNCH(c, k_p_smooth, (unsigned)nt, HB, 0, d_moff0, G, d_tiles, G.y0b, G.y0a, G.y1a, G.y1b, 0);
+  LAUNCH(c, k_p_smooth, (unsigned)nt, HB, 0, d_moff0, G, d_tiles, G.y0a, G.y0b, G.y1a, G.y1b, 0);
+  LAUNCH(c, k_p_argmax, (unsigned)nt, HB, 0, d_moff0, G, d_tiles, G.y0b, G.y1b, d_tval, d_tidx);
+  LAUNCH(c, k_p_vmax, nblk(nact, 64), 64, 0, d_moff0, G, d_act, nact, has_w, d_tval, d_tidx, c->h_scal);
+  for (void *q : { (void *)d_act, (void *)d_tile0, (void *)d_ntile, (void *)d_tiles, (void *)G.edge, (void *)G.vesc_bin, (void *)G.Vc_bin, (void *)G.tile_blo,
+                   (void *)G.tile_ns, (void *)d_slot, (void *)G.tbest_e, (void *)G.tbest_j, (void *)G.w_r, (void *)G.y0a, (void *)G.y0b, (void *)G.y1a, (void *)G.y1b,
+                   (void *)G.Mpre, (void *)d_tt4, (void *)d_tc4, (void *)d_ht4, (void *)d_tt1, (void *)d_tc1, (void *)d_ht1, (void *)d_tval, (void *)d_tidx, (void *)G.partial })
+    ahf::dfree(q);
+}
+
 void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const double *gather_rad, const int64_t *seed)
 {
   c->free_halos();
@@ -1581,11 +2025,15 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
   CUDA_CHECK(cudaMemcpyAsync(d_soff, soff.data(), sizeof(int64_t) * (nhalo + 1), cudaMemcpyHostToDevice, c->stream));
   c->h_prof = dalloc<double>((size_t)tot_b * AHFGPU_NPROFCOL);
   c->h_members = dalloc<int64_t>(tot_m);
-  double *d_scratch = dalloc<double>((size_t)tot_s * 3);
+  const bool prof_v1 = getenv("AHFGPU_PROFILES_V1") != nullptr;      // previous form: one CTA per halo (kept for A/B timing)
+  double *d_scratch = prof_v1 ? dalloc<double>((size_t)tot_s * 3) : nullptr;
   {
     Stage st(c, "halo_profiles", tot_s);
-    LAUNCH(c, k_halo_profiles, (unsigned)nhalo, HB, 0, c->pos4, c->mom4, c->has_weight ? 1 : 0, c->has_u ? 1 : 0, d_ctr, d_moff0, d_members, d_np, P,
-           c->h_scal, c->h_poff, c->h_prof, d_soff, d_scratch);
+    if (prof_v1)
+      LAUNCH(c, k_halo_profiles, (unsigned)nhalo, HB, 0, c->pos4, c->mom4, c->has_weight ? 1 : 0, c->has_u ? 1 : 0, d_ctr, d_moff0, d_members, d_np, P,
+             c->h_scal, c->h_poff, c->h_prof, d_soff, d_scratch);
+    else
+      profiles_cooperative(c, nhalo, P, d_ctr, d_moff0, d_members, tot_g, d_np, h_np);
     LAUNCH(c, k_members_out, (unsigned)nhalo, 256, 0, d_moff0, d_np, c->h_moff, d_members, c->h_members);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
   }
