@@ -127,43 +127,47 @@ __device__ __forceinline__ int64_t lower_bound_key(const uint64_t *__restrict__ 
   return lo;
 }
 
+// one warp per halo, one lane per search cell
 __global__ void k_gather_ranges(const uint64_t *__restrict__ keys, int64_t n, const double *__restrict__ centre, const double *__restrict__ grad,
                                 const int64_t *__restrict__ seed, int64_t nhalo, int64_t *__restrict__ rlo, int64_t *__restrict__ rhi,
                                 int64_t *__restrict__ cand)
 {
-  int64_t h = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t h = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int     q = threadIdx.x & 31;
   if (h >= nhalo) return;
-  int64_t tot = 0;
-  for (int q = 0; q < 27; q++) { rlo[h * 27 + q] = 0; rhi[h * 27 + q] = 0; }
-  if (seed && seed[h] == 0) { cand[h] = 0; return; }                     // ahf_halos_sfc.c:122
-  const double R = grad[h], cx = centre[3 * h], cy = centre[3 * h + 1], cz = centre[3 * h + 2];
-  unsigned bits = 1;
-  while ((GATHERRAD_FAC * R < 1. / (double)(1 << (bits + 1))) && ((bits + 1) <= 21)) bits++;     // :244-256
-  const unsigned sh = 3 * (21 - bits);
-  if (bits == 1) {
-    for (int q = 0; q < 8; q++) {                                        // :210-217 all octants
-      uint64_t kmin = (uint64_t)q << sh, kmax = kmin + ((1ull << sh) - 1);
-      int64_t  a = lower_bound_key(keys, n, kmin), b = lower_bound_key(keys, n, kmax + 1);
-      rlo[h * 27 + q] = a; rhi[h * 27 + q] = b; tot += b - a;
-    }
-  } else {
-    const uint64_t ckey = hilbert_key_posd(cx, cy, cz, bits);
-    uint32_t bx, by, bz;
-    hilbert_coords(ckey, bits, bx, by, bz);
-    const uint32_t L = 1u << bits;
-    const double   g = 1. / (double)(1ull << bits), big = 0.5 * sqrt(3.) * g;
-    int q = 0;
-    for (int i = -1; i <= 1; i++) for (int j = -1; j <= 1; j++) for (int k = -1; k <= 1; k++, q++) {    // hilbert_util.c:143-154
+  int64_t a = 0, b = 0;
+  const bool skip = seed && seed[h] == 0;                                  // ahf_halos_sfc.c:122
+  if (!skip && q < 27) {
+    const double R = grad[h], cx = centre[3 * h], cy = centre[3 * h + 1], cz = centre[3 * h + 2];
+    unsigned bits = 1;
+    while ((GATHERRAD_FAC * R < 1. / (double)(1 << (bits + 1))) && ((bits + 1) <= 21)) bits++;     // :244-256
+    const unsigned sh = 3 * (21 - bits);
+    if (bits == 1) {
+      if (q < 8) {                                                         // :210-217 all octants
+        uint64_t kmin = (uint64_t)q << sh, kmax = kmin + ((1ull << sh) - 1);
+        a = lower_bound_key(keys, n, kmin); b = lower_bound_key(keys, n, kmax + 1);
+      }
+    } else {
+      const uint64_t ckey = hilbert_key_posd(cx, cy, cz, bits);
+      uint32_t bx, by, bz;
+      hilbert_coords(ckey, bits, bx, by, bz);
+      const uint32_t L = 1u << bits;
+      const double   g = 1. / (double)(1ull << bits), big = 0.5 * sqrt(3.) * g;
+      const int i = q / 9 - 1, j = (q / 3) % 3 - 1, k = q % 3 - 1;          // hilbert_util.c:143-154: q = (i+1)*9 + (j+1)*3 + (k+1)
       uint32_t x = (bx + L + i) % L, y = (by + L + j) % L, z = (bz + L + k) % L;
       double dx = fabs((g * x + 0.5 * g) - cx), dy = fabs((g * y + 0.5 * g) - cy), dz = fabs((g * z + 0.5 * g) - cz);
       if (dx > 0.5) dx = 1.0 - dx; if (dy > 0.5) dy = 1.0 - dy; if (dz > 0.5) dz = 1.0 - dz;
-      if (sqrt(dx * dx + dy * dy + dz * dz) > big + GATHERRAD_FAC * R) continue;                 // :294
-      uint64_t kc = hilbert_index(x, y, z, bits), kmin = kc << sh, kmax = kmin + ((1ull << sh) - 1);
-      int64_t  a = lower_bound_key(keys, n, kmin), b = lower_bound_key(keys, n, kmax + 1);
-      rlo[h * 27 + q] = a; rhi[h * 27 + q] = b; tot += b - a;
+      if (!(sqrt(dx * dx + dy * dy + dz * dz) > big + GATHERRAD_FAC * R)) {                 // :294
+        uint64_t kc = hilbert_index(x, y, z, bits), kmin = kc << sh, kmax = kmin + ((1ull << sh) - 1);
+        a = lower_bound_key(keys, n, kmin); b = lower_bound_key(keys, n, kmax + 1);
+      }
     }
   }
-  cand[h] = tot;
+  if (q < 27) { rlo[h * 27 + q] = a; rhi[h * 27 + q] = b; }
+  long long tot = b - a;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+  if (q == 0) cand[h] = tot;
 }
 
 // G2: one CTA per halo; members = candidates with periodic d^2 <= R^2, appended range by range (ahf_halos_sfc.c:327-356)
@@ -606,6 +610,45 @@ __global__ void __launch_bounds__(HB) k_g_scan(const int32_t *__restrict__ act, 
 #pragma unroll
     for (int q = 0; q < NC; q++) htot[(size_t)h * NC + q] = carry[q];
   }
+}
+
+// G2, tile-parallel: tile = up to HT consecutive candidates of one search cell of one halo.  COUNT pass -> k_g_scan<1> -> FILL pass;
+// members are appended range by range in key order, as the reference does (ahf_halos_sfc.c:327-356)
+template <bool FILL>
+__global__ void __launch_bounds__(HB) k_gather_tiles(const float4 *__restrict__ pos4, const double *__restrict__ centre, const double *__restrict__ grad,
+                                                     const int4 *__restrict__ tiles, const int64_t *__restrict__ candoff, const double *__restrict__ tc,
+                                                     double *__restrict__ tt, double *__restrict__ r2buf, uint32_t *__restrict__ idxbuf)
+{
+  __shared__ int smi[HB / 32];
+  const int4 tl = tiles[blockIdx.x];
+  const int  h = tl.x, cnt = tl.w;
+  const uint32_t start = (uint32_t)tl.z;
+  const double c[3] = { centre[3 * h], centre[3 * h + 1], centre[3 * h + 2] };
+  const double R2 = grad[h] * grad[h];
+  bool in[HI]; double r2[HI]; int mine = 0;
+#pragma unroll
+  for (int i = 0; i < HI; i++) {
+    const int t = threadIdx.x * HI + i;
+    in[i] = false; r2[i] = 0.0;
+    if (t < cnt) {
+      const float4 p = pos4[start + (uint32_t)t];
+      double dx = fabs((double)p.x - c[0]), dy = fabs((double)p.y - c[1]), dz = fabs((double)p.z - c[2]);
+      if (dx > 0.5) dx = 1.0 - dx; if (dy > 0.5) dy = 1.0 - dy; if (dz > 0.5) dz = 1.0 - dz;
+      in[i] = (dx * dx + dy * dy + dz * dz) <= R2;
+      if (FILL && in[i]) { double d[3]; sep3(p, c, d); r2[i] = d[0] * d[0] + d[1] * d[1] + d[2] * d[2]; }   // sort key (ahf_halos.c:5844)
+      mine += in[i] ? 1 : 0;
+    }
+  }
+  int tot, pos = block_excl_scan_i(mine, smi, &tot);
+  if (!FILL) { if (threadIdx.x == 0) tt[blockIdx.x] = (double)tot; return; }
+  int64_t out = candoff[h] + (int64_t)tc[blockIdx.x] + pos;
+#pragma unroll
+  for (int i = 0; i < HI; i++) if (in[i]) { r2buf[out] = r2[i]; idxbuf[out] = start + (uint32_t)(threadIdx.x * HI + i); out++; }
+}
+__global__ void k_gather_counts(const double *__restrict__ htot, int64_t nhalo, int64_t *__restrict__ ngather)
+{
+  const int64_t h = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (h < nhalo) ngather[h] = (int64_t)htot[h];
 }
 
 // cumulative mass of the tile's members: equal masses -> index + 1 exactly; otherwise the stored prefix
@@ -1941,13 +1984,42 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
   double *d_r2 = nullptr; uint32_t *d_idx = nullptr;
   {
     Stage st(c, "halo_gather", 0);
-    LAUNCH(c, k_gather_ranges, nblk(nhalo, 128), 128, 0, c->keys, n, d_ctr, d_rad, d_seed, nhalo, d_rlo, d_rhi, d_cand);
+    LAUNCH(c, k_gather_ranges, nblk(nhalo * 32, 128), 128, 0, c->keys, n, d_ctr, d_rad, d_seed, nhalo, d_rlo, d_rhi, d_cand);
     CUDA_CHECK(cudaMemcpyAsync(h_cand.data(), d_cand, sizeof(int64_t) * nhalo, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     candoff = host_excl(h_cand, &tot_cand);
     CUDA_CHECK(cudaMemcpyAsync(d_candoff, candoff.data(), sizeof(int64_t) * (nhalo + 1), cudaMemcpyHostToDevice, c->stream));
     d_r2 = dalloc<double>(tot_cand); d_idx = dalloc<uint32_t>(tot_cand);
-    LAUNCH(c, k_gather_fill, (unsigned)nhalo, HB, 0, c->pos4, d_ctr, d_rad, d_rlo, d_rhi, d_candoff, d_r2, d_idx, d_ng);
+    if (getenv("AHFGPU_GATHER_V1")) {
+      LAUNCH(c, k_gather_fill, (unsigned)nhalo, HB, 0, c->pos4, d_ctr, d_rad, d_rlo, d_rhi, d_candoff, d_r2, d_idx, d_ng);
+    } else {
+      // tile list: chunks of HT candidates of every (halo, search cell) range, in the reference's append order
+      std::vector<int64_t> h_rlo(27 * nhalo), h_rhi(27 * nhalo);
+      CUDA_CHECK(cudaMemcpyAsync(h_rlo.data(), d_rlo, sizeof(int64_t) * 27 * nhalo, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_CHECK(cudaMemcpyAsync(h_rhi.data(), d_rhi, sizeof(int64_t) * 27 * nhalo, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      std::vector<int4> tiles; std::vector<int32_t> act, tile0(nhalo, 0), ntile(nhalo, 0);
+      for (int64_t h = 0; h < nhalo; h++) {
+        act.push_back((int32_t)h);
+        tile0[h] = (int32_t)tiles.size();
+        for (int q = 0; q < 27; q++)
+          for (int64_t a = h_rlo[h * 27 + q]; a < h_rhi[h * 27 + q]; a += HT)
+            tiles.push_back(make_int4((int)h, q, (int)(uint32_t)a, (int)std::min<int64_t>(HT, h_rhi[h * 27 + q] - a)));
+        ntile[h] = (int32_t)tiles.size() - tile0[h];
+      }
+      const int nt = (int)tiles.size();
+      int4 *d_gt = dalloc<int4>(nt); int32_t *d_act = dalloc<int32_t>(nhalo), *d_t0 = dalloc<int32_t>(nhalo), *d_ntl = dalloc<int32_t>(nhalo);
+      double *d_tt = dalloc<double>(nt), *d_tc = dalloc<double>(nt), *d_ht = dalloc<double>(nhalo);
+      CUDA_CHECK(cudaMemcpyAsync(d_gt, tiles.data(), sizeof(int4) * nt, cudaMemcpyHostToDevice, c->stream));
+      CUDA_CHECK(cudaMemcpyAsync(d_act, act.data(), sizeof(int32_t) * nhalo, cudaMemcpyHostToDevice, c->stream));
+      CUDA_CHECK(cudaMemcpyAsync(d_t0, tile0.data(), sizeof(int32_t) * nhalo, cudaMemcpyHostToDevice, c->stream));
+      CUDA_CHECK(cudaMemcpyAsync(d_ntl, ntile.data(), sizeof(int32_t) * nhalo, cudaMemcpyHostToDevice, c->stream));
+      if (nt) LAUNCH(c, k_gather_tiles<false>, (unsigned)nt, HB, 0, c->pos4, d_ctr, d_rad, d_gt, d_candoff, d_tc, d_tt, d_r2, d_idx);
+      LAUNCH(c, k_g_scan<1>, (unsigned)nhalo, HB, 0, d_act, d_t0, d_ntl, d_tt, d_tc, d_ht);
+      if (nt) LAUNCH(c, k_gather_tiles<true>, (unsigned)nt, HB, 0, c->pos4, d_ctr, d_rad, d_gt, d_candoff, d_tc, d_tt, d_r2, d_idx);
+      LAUNCH(c, k_gather_counts, nblk(nhalo, 128), 128, 0, d_ht, nhalo, d_ng);
+      ahf::dfree(d_gt); ahf::dfree(d_act); ahf::dfree(d_t0); ahf::dfree(d_ntl); ahf::dfree(d_tt); ahf::dfree(d_tc); ahf::dfree(d_ht);
+    }
     CUDA_CHECK(cudaMemcpyAsync(h_ng.data(), d_ng, sizeof(int64_t) * nhalo, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
   }

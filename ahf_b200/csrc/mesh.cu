@@ -53,16 +53,19 @@ __device__ __forceinline__ uint64_t lv_key(const LV &v, int x, int y, int z)
 {
   return (((uint64_t)z << v.logL) | (uint64_t)y) << v.logL | (uint64_t)x;
 }
-// geometric lookup without periodic wrap: -1 when (x,y,z) is not a cell of the level
+// geometric lookup without periodic wrap: -1 when (x,y,z) is not a cell of the level.
+// The hash is keyed on blocks of 8 x-consecutive cells (key >> 3): one 8-byte key and eight 4-byte cell indices per slot, so that
+// the lookups of a warp walking along a row share a few 32-byte sectors instead of touching 32 random ones.
 __device__ __forceinline__ int lv_lookup(const LV &v, int x, int y, int z)
 {
   if ((unsigned)x >= (unsigned)v.L || (unsigned)y >= (unsigned)v.L || (unsigned)z >= (unsigned)v.L) return -1;
   uint64_t k = lv_key(v, x, y, z);
   if (v.dense) return (int)k;
-  uint64_t s = mix64(k) & v.hmask;
+  const uint64_t kb = k >> 3;
+  uint64_t s = mix64(kb) & v.hmask;
   for (;;) {
     uint64_t hk = v.hkey[s];
-    if (hk == k) return v.hval[s];
+    if (hk == kb) return v.hval[s * 8 + (k & 7)];
     if (hk == ~0ull) return -1;
     s = (s + 1) & v.hmask;
   }
@@ -809,24 +812,23 @@ __global__ void k_make_children(LV v, const uint8_t *__restrict__ mark, const in
       }
 }
 
-__global__ void k_hash_clear(uint64_t *__restrict__ hkey, uint64_t cap)
+__global__ void k_hash_clear(uint64_t *__restrict__ hkey, int4 *__restrict__ hval8, uint64_t cap)
 {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i < cap) hkey[i] = ~0ull;
+  if (i < cap) { hkey[i] = ~0ull; hval8[2 * i] = make_int4(-1, -1, -1, -1); hval8[2 * i + 1] = make_int4(-1, -1, -1, -1); }
 }
 __global__ void k_hash_insert(const uint64_t *__restrict__ ckey, int ncell, uint64_t *__restrict__ hkey, int32_t *__restrict__ hval, uint64_t hmask)
 {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncell) return;
-  uint64_t k = ckey[c], s = mix64(k) & hmask;
+  const uint64_t k = ckey[c], kb = k >> 3;
+  uint64_t s = mix64(kb) & hmask;
   for (;;) {
-    unsigned long long old = atomicCAS((unsigned long long *)&hkey[s], ~0ull, (unsigned long long)k);
-    if (old == ~0ull || old == k) { hval[s] = c; return; }
+    unsigned long long old = atomicCAS((unsigned long long *)&hkey[s], ~0ull, (unsigned long long)kb);
+    if (old == ~0ull || old == kb) { hval[s * 8 + (k & 7)] = c; return; }
     s = (s + 1) & hmask;
   }
 }
-
-// row heads / plane heads
 __global__ void k_row_heads(const uint64_t *__restrict__ ckey, int ncell, int logL, uint8_t *__restrict__ head)
 {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -934,6 +936,13 @@ __global__ void k_relink(const float4 *__restrict__ pos4, const uint32_t *__rest
   moved[i]   = res >= 0 ? 1 : 0;
 }
 
+__global__ void k_dbg_compare(const int32_t *__restrict__ a, const int32_t *__restrict__ b, uint64_t n, unsigned long long *__restrict__ out)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (a[i] >= 0) atomicAdd(&out[1], 1ull);
+  if (a[i] != b[i]) { atomicAdd(&out[0], 1ull); atomicMin(&out[2], (unsigned long long)i); }
+}
 __global__ void k_compact_moved(const uint32_t *__restrict__ plist, const int32_t *__restrict__ newcell, const uint8_t *__restrict__ moved,
                                 const int *__restrict__ S, uint64_t np, uint32_t *__restrict__ plist_out, int32_t *__restrict__ pcell_out,
                                 int8_t *__restrict__ owner, int8_t newlevel, const float4 *__restrict__ pos4, float4 *__restrict__ lpos_out)
@@ -948,13 +957,17 @@ __global__ void k_compact_moved(const uint32_t *__restrict__ plist, const int32_
 
 __global__ void k_count_owner(const int8_t *__restrict__ owner, uint64_t n, unsigned long long *__restrict__ cnt)
 {
-  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int l = owner[i];
-  unsigned peers = __match_any_sync(__activemask(), l);
-  if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&cnt[l], (unsigned long long)__popc(peers));
+  __shared__ unsigned int h[64];
+  if (threadIdx.x < 64) h[threadIdx.x] = 0;
+  __syncthreads();
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const int l = owner[i];
+    const unsigned peers = __match_any_sync(__activemask(), l);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&h[l & 63], (unsigned)__popc(peers));
+  }
+  __syncthreads();
+  if (threadIdx.x < 64 && h[threadIdx.x]) atomicAdd(&cnt[threadIdx.x], (unsigned long long)h[threadIdx.x]);
 }
-
 __global__ void k_nonzero(const uint8_t *in, int n, uint8_t *out)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1107,7 +1120,7 @@ static void alloc_cell_arrays(Level &lv)
 {
   const size_t nc = (size_t)lv.ncell;
   lv.dens = dalloc<float>(nc); lv.tn = dalloc<uint8_t>(nc); lv.mark = dalloc<uint8_t>(nc); lv.count = dalloc<int32_t>(nc);
-  CUDA_CHECK(cudaMemset(lv.mark, 0, nc));
+  CUDA_CHECK(cudaMemsetAsync(lv.mark, 0, nc, ahf::g_pool_stream));      // stream ordered: the block may be recycled memory that queued kernels still read
 }
 
 void amr_build(ahfgpu_ctx *c)
@@ -1173,14 +1186,31 @@ void amr_build(ahfgpu_ctx *c)
              cur.plane_r0, (int)cur.nrow, f.ckey, f.xbreak, flogL);
       S.release();
       // hash
-      uint64_t cap = 16; while (cap < (uint64_t)f.ncell * 2 + 2) cap <<= 1;
-      f.hmask = cap - 1; f.hkey = dalloc<uint64_t>(cap); f.hval = dalloc<int32_t>(cap);
-      LAUNCH(c, k_hash_clear, nblk(cap, 256), 256, 0, f.hkey, cap);
+      // slots hold 8 x-consecutive cells; children come in x-pairs, so there are at most ncell/2 occupied slots
+      uint64_t cap = 16; while (cap < (uint64_t)f.ncell + 2) cap <<= 1;
+      f.hmask = cap - 1; f.hkey = dalloc<uint64_t>(cap); f.hval = dalloc<int32_t>(cap * 8);
+      LAUNCH(c, k_hash_clear, nblk(cap, 256), 256, 0, f.hkey, reinterpret_cast<int4 *>(f.hval), cap);
       LAUNCH(c, k_hash_insert, nblk(f.ncell, 256), 256, 0, f.ckey, (int)f.ncell, f.hkey, f.hval, f.hmask);
       alloc_cell_arrays(f);
       f.interior = dalloc<uint8_t>(f.ncell); f.nbr = dalloc<int32_t>((size_t)f.ncell * 27);
       LV fv = view(f);
       LAUNCH(c, k_neighbours, nblk(f.ncell, 128), 128, 0, fv, f.nbr, f.interior);
+      if (getenv("AHFGPU_DEBUG_RELINK")) {
+        DevBuf<int32_t> nb2; DevBuf<uint8_t> in2; DevBuf<unsigned long long> out;
+        nb2.reserve((size_t)f.ncell * 27); in2.reserve(f.ncell); out.reserve(3);
+        unsigned long long h0[3] = { 0, 0, ~0ull }, h[3];
+        CUDA_CHECK(cudaMemcpyAsync(out.p, h0, sizeof(h0), cudaMemcpyHostToDevice, c->stream));
+        LAUNCH(c, k_neighbours, nblk(f.ncell, 128), 128, 0, fv, nb2.p, in2.p);
+        LAUNCH(c, k_dbg_compare, nblk((uint64_t)f.ncell * 27, 256), 256, 0, f.nbr, nb2.p, (uint64_t)f.ncell * 27, out.p);
+        CUDA_CHECK(cudaMemcpyAsync(h, out.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        static std::map<int, unsigned long long> refcnt;
+        if (h[0]) fprintf(stderr, "[nbr dbg] level %d: %llu neighbour entries differ between two runs (first at %llu)\n", lev + 1, h[0], h[2]);
+        if (refcnt.count(lev + 1) && refcnt[lev + 1] != h[1])
+          fprintf(stderr, "[nbr dbg] level %d: %llu existing neighbour entries, %llu in the first build\n", lev + 1, h[1], refcnt[lev + 1]);
+        if (!refcnt.count(lev + 1)) refcnt[lev + 1] = h[1];
+        nb2.release(); in2.release(); out.release();
+      }
       build_rows_planes(c, f);
       c->levels.push_back(f);
     }
@@ -1197,6 +1227,20 @@ void amr_build(ahfgpu_ctx *c)
       if (np) {
         LAUNCH(c, k_relink, nblk(np, 256), 256, 0, c->pos4, coa.plist, coa.pcell, np, view(coa), coa.mark, view(fin), fin.interior, newcell.p, moved.p);
         nmoved = exclusive_scan<uint8_t>(c, moved.p, MS.p, np);
+        if (getenv("AHFGPU_DEBUG_RELINK")) {
+          DevBuf<int32_t> nc2; DevBuf<uint8_t> mv2; DevBuf<unsigned long long> out;
+          nc2.reserve(np); mv2.reserve(np); out.reserve(3);
+          unsigned long long h0[3] = { 0, 0, ~0ull }, h[3];
+          CUDA_CHECK(cudaMemcpyAsync(out.p, h0, sizeof(h0), cudaMemcpyHostToDevice, c->stream));
+          LAUNCH(c, k_relink, nblk(np, 256), 256, 0, c->pos4, coa.plist, coa.pcell, np, view(coa), coa.mark, view(fin), fin.interior, nc2.p, mv2.p);
+          LAUNCH(c, k_dbg_compare, nblk(np, 256), 256, 0, newcell.p, nc2.p, np, out.p);
+          CUDA_CHECK(cudaMemcpyAsync(h, out.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+          CUDA_CHECK(cudaStreamSynchronize(c->stream));
+          if (h[0] || (long long)h[1] != nmoved)
+            fprintf(stderr, "[relink dbg] level %d -> %d: %llu of %llu newcell differ between two runs (first at %llu); count(res>=0) %llu, scan total %d\n",
+                    lev, lev + 1, h[0], (unsigned long long)np, h[2], h[1], nmoved);
+          nc2.release(); mv2.release(); out.release();
+        }
       }
       if (fin.ncell < MIN_NNODES) {                                   // generate_grids.c:231 / density.c:420: level rejected
         fin.free_all();
@@ -1217,7 +1261,7 @@ void amr_build(ahfgpu_ctx *c)
     DevBuf<unsigned long long> cnt;
     cnt.reserve(64);
     CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, 64 * sizeof(unsigned long long), c->stream));
-    if (n) LAUNCH(c, k_count_owner, nblk(n, 256), 256, 0, c->owner_level, n, cnt.p);
+    if (n) LAUNCH(c, k_count_owner, std::min(nblk(n, 256), 2368u), 256, 0, c->owner_level, n, cnt.p);
     unsigned long long h[64];
     CUDA_CHECK(cudaMemcpyAsync(h, cnt.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));

@@ -6,10 +6,37 @@
 namespace ahf {
 
 constexpr int SC_THREADS = 512;
-constexpr int SC_ITEMS   = 8;
+constexpr int SC_ITEMS   = 8;      // sc_load_items is written for 8
 constexpr int SC_TILE    = SC_THREADS * SC_ITEMS;
 
 template <typename T> __device__ __forceinline__ int sc_load(const T *a, uint64_t i) { return (int)a[i]; }
+// SC_ITEMS consecutive inputs of one thread with vector loads when the thread's slice is whole and the array is aligned
+__device__ __forceinline__ void sc_load_items(const uint8_t *a, uint64_t base, uint64_t n, int (&v)[8])
+{
+  if (base + 8 <= n && (reinterpret_cast<uintptr_t>(a) & 7) == 0) {
+    const uint2 q = *reinterpret_cast<const uint2 *>(a + base);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { v[i] = (int)((q.x >> (8 * i)) & 255u); v[4 + i] = (int)((q.y >> (8 * i)) & 255u); }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = (base + i < n) ? (int)a[base + i] : 0;
+  }
+}
+__device__ __forceinline__ void sc_load_items(const int *a, uint64_t base, uint64_t n, int (&v)[8])
+{
+  if (base + 8 <= n && (reinterpret_cast<uintptr_t>(a) & 15) == 0) {
+    const int4 q0 = *reinterpret_cast<const int4 *>(a + base), q1 = *reinterpret_cast<const int4 *>(a + base + 4);
+    v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = (base + i < n) ? a[base + i] : 0;
+  }
+}
+template <typename T> __device__ __forceinline__ void sc_load_items(const T *a, uint64_t base, uint64_t n, int (&v)[8])
+{
+#pragma unroll
+  for (int i = 0; i < 8; i++) v[i] = (base + i < n) ? (int)a[base + i] : 0;
+}
 
 __device__ __forceinline__ int block_exclusive_scan(int v)
 {
@@ -36,9 +63,10 @@ __global__ void __launch_bounds__(SC_THREADS) k_sc_reduce(const T *__restrict__ 
 {
   __shared__ int red[SC_THREADS / 32];
   uint64_t base = (uint64_t)blockIdx.x * SC_TILE + (uint64_t)threadIdx.x * SC_ITEMS;
-  int s = 0;
+  int s = 0, vv[SC_ITEMS];
+  sc_load_items(in, base, n, vv);
 #pragma unroll
-  for (int i = 0; i < SC_ITEMS; i++) if (base + i < n) s += sc_load(in, base + i);
+  for (int i = 0; i < SC_ITEMS; i++) s += vv[i];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -57,11 +85,20 @@ __global__ void __launch_bounds__(SC_THREADS) k_sc_down(const T *in, uint64_t n,
 {
   uint64_t base = (uint64_t)blockIdx.x * SC_TILE + (uint64_t)threadIdx.x * SC_ITEMS;
   int v[SC_ITEMS], s = 0;
+  sc_load_items(in, base, n, v);
 #pragma unroll
-  for (int i = 0; i < SC_ITEMS; i++) { v[i] = (base + i < n) ? sc_load(in, base + i) : 0; s += v[i]; }
+  for (int i = 0; i < SC_ITEMS; i++) s += v[i];
   int ex = block_exclusive_scan(s) + boff[blockIdx.x];
+  if (base + SC_ITEMS <= n && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    int o[SC_ITEMS];
 #pragma unroll
-  for (int i = 0; i < SC_ITEMS; i++) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
+    for (int i = 0; i < SC_ITEMS; i++) { o[i] = ex; ex += v[i]; }
+    *reinterpret_cast<int4 *>(out + base) = make_int4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<int4 *>(out + base + 4) = make_int4(o[4], o[5], o[6], o[7]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; i++) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
+  }
 }
 
 // single CTA exclusive scan of a short int array in place; writes the total to *total

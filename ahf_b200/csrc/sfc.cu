@@ -38,7 +38,7 @@ __global__ void k_keys_aos(const unsigned char *__restrict__ rec, uint64_t n, ui
 //   per pass: block histograms -> exclusive scan over [digit][block] -> ranked scatter
 // ------------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS   = 16;
+constexpr int RS_ITEMS   = 8;
 constexpr int RS_TILE    = RS_THREADS * RS_ITEMS;   // 4096 pairs per CTA
 constexpr int RS_WARPS   = RS_THREADS / 32;
 constexpr int RS_WCHUNK  = RS_TILE / RS_WARPS;      // 512 consecutive pairs per warp
@@ -88,15 +88,23 @@ __global__ void __launch_bounds__(1024) k_scan_u32(uint32_t *__restrict__ a, uin
   for (uint64_t i = b; i < e; i++) { uint32_t x = a[i]; a[i] = run; run += x; }
 }
 
+// ranked scatter.  The tile is first sorted by digit in shared memory (stable), then written out digit run by digit run so that
+// consecutive threads store consecutive addresses (a direct scatter writes 12 useful bytes per pair of 32-byte sectors).
+constexpr int RS_SMEM = RS_TILE * 12 + RS_WARPS * 256 * 4 + 2 * 256 * 4 + 64;
 __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
                                                            uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, uint64_t n,
                                                            int shift, const uint32_t *__restrict__ bscan, uint32_t nblk)
 {
-  __shared__ uint32_t whist[RS_WARPS][256];
+  extern __shared__ __align__(16) unsigned char rsm[];
+  uint64_t *sk = reinterpret_cast<uint64_t *>(rsm);                                  // [RS_TILE]
+  uint32_t *sv = reinterpret_cast<uint32_t *>(rsm + RS_TILE * 8);                    // [RS_TILE]
+  uint32_t (*whist)[256] = reinterpret_cast<uint32_t (*)[256]>(rsm + RS_TILE * 12);  // [RS_WARPS][256]
+  uint32_t *gbase = reinterpret_cast<uint32_t *>(rsm + RS_TILE * 12 + RS_WARPS * 256 * 4);   // [256] global address of tile slot 0 of the digit's run
+  uint32_t *wtot  = gbase + 256;                                                     // [RS_WARPS] scratch of the digit scan
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&whist[0][0])[i] = 0;
   __syncthreads();
-  const uint64_t base = (uint64_t)blockIdx.x * RS_TILE + (uint64_t)w * RS_WCHUNK;
+  const uint64_t tile0 = (uint64_t)blockIdx.x * RS_TILE, base = tile0 + (uint64_t)w * RS_WCHUNK;
   uint64_t k[RS_ITEMS];
   uint32_t v[RS_ITEMS];
   uint32_t rank[RS_ITEMS];
@@ -124,10 +132,23 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t *__res
   }
   __syncthreads();
   {
-    const int t   = threadIdx.x;   // digit
-    uint32_t  run = bscan[(uint64_t)t * nblk + blockIdx.x];
+    const int t = threadIdx.x;   // digit: counts of the warps -> exclusive offsets inside the digit, tile count of the digit
+    uint32_t  run = 0;
 #pragma unroll
     for (int q = 0; q < RS_WARPS; q++) { uint32_t c = whist[q][t]; whist[q][t] = run; run += c; }
+    // exclusive scan of the 256 digit counts: where the digit's run starts inside the tile
+    uint32_t inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+    if (lane == 31) wtot[w] = inc;
+    __syncthreads();
+    uint32_t wb = 0;
+#pragma unroll
+    for (int q = 0; q < RS_WARPS; q++) if (q < w) wb += wtot[q];
+    const uint32_t dstart = wb + inc - run;
+#pragma unroll
+    for (int q = 0; q < RS_WARPS; q++) whist[q][t] += dstart;
+    gbase[t] = bscan[(uint64_t)t * nblk + blockIdx.x] - dstart;
   }
   __syncthreads();
 #pragma unroll
@@ -135,10 +156,17 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t *__res
     uint64_t j = base + (uint64_t)s * 32 + lane;
     if (j < n) {
       uint32_t d = (uint32_t)(k[s] >> shift) & 255u;
-      uint32_t p = whist[w][d] + rank[s];
-      kout[p] = k[s];
-      vout[p] = v[s];
+      uint32_t lp = whist[w][d] + rank[s];
+      sk[lp] = k[s]; sv[lp] = v[s];
     }
+  }
+  __syncthreads();
+  const int nv = (int)((n - tile0) < (uint64_t)RS_TILE ? (n - tile0) : (uint64_t)RS_TILE);
+#pragma unroll 4
+  for (int i = threadIdx.x; i < nv; i += RS_THREADS) {
+    const uint64_t kk = sk[i];
+    const uint32_t p = gbase[(uint32_t)(kk >> shift) & 255u] + (uint32_t)i;
+    kout[p] = kk; vout[p] = sv[i];
   }
 }
 
@@ -150,13 +178,15 @@ void radix_sort_pairs(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t *k
   const uint32_t nblk = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
   DevBuf<uint32_t> bh;
   DevBuf<int>      bs;
+  static bool attr_set = false;
+  if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM)); attr_set = true; }
   bh.reserve((size_t)256 * nblk);
   uint64_t *ki = keys, *ko = keys_tmp;
   uint32_t *vi = vals, *vo = vals_tmp;
   for (int shift = 0; shift < key_bits; shift += 8) {
     LAUNCH(c, k_rs_hist, nblk, RS_THREADS, 0, ki, n, shift, bh.p, nblk);
     exclusive_scan_async<int>(c, (const int *)bh.p, (int *)bh.p, (uint64_t)256 * nblk, nullptr, bs);   // in place: each tile is read before it is written
-    LAUNCH(c, k_rs_scatter, nblk, RS_THREADS, 0, ki, vi, ko, vo, n, shift, bh.p, nblk);
+    LAUNCH(c, k_rs_scatter, nblk, RS_THREADS, RS_SMEM, ki, vi, ko, vo, n, shift, bh.p, nblk);
     uint64_t *tk = ki; ki = ko; ko = tk;
     uint32_t *tv = vi; vi = vo; vo = tv;
   }
