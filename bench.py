@@ -40,7 +40,7 @@ def ncu_traffic_bytes(n1d: int):
     if n1d != 256:
         return None
     import glob, re
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_deposit_tiles_ncu_full.txt")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_deposit_*_ncu_full.txt")))
     if not files:
         return None
     rd = wr = None
