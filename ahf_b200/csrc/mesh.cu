@@ -364,7 +364,37 @@ k_deposit_tiles(const float4 *__restrict__ pos4, const int32_t *__restrict__ tst
     }
     __syncthreads();                                   // everybody is done with this stage's buffer
   }
-  // flush: thread = one (hx,hy) column of the tile, marching in z (no div/mod, constant strides)
+  if (SPARSE) {
+    // flush of a refinement-level tile: the touched cells are first compacted into a list (the TMA stage buffers are free now),
+    // then ALL threads resolve them through the cell hash -- a thread sees a few independent lookups instead of marching
+    // through 18 dependent ones
+    __shared__ int s_nnz;
+    uint16_t *list = reinterpret_cast<uint16_t *>(dsm);                     // DT_HH entries fit the 16 KB of stage buffers
+    if (threadIdx.x == 0) s_nnz = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < DT_HH; i += DT_THREADS) {
+      const bool nz = (tile[i] | tcar[i]) != 0;
+      const unsigned bal = __ballot_sync(__activemask(), nz);
+      if (nz) {
+        const int leader = __ffs(bal) - 1;
+        int basep = 0;
+        if (lane == leader) basep = atomicAdd(&s_nnz, __popc(bal));
+        basep = __shfl_sync(bal, basep, leader);
+        list[basep + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
+      }
+    }
+    __syncthreads();
+    const int nnz = s_nnz;
+    for (int e = threadIdx.x; e < nnz; e += DT_THREADS) {
+      const int i = list[e];
+      const int hz = i / (DT_H * DT_H), r = i - hz * (DT_H * DT_H), hy = r / DT_H, hx = r - hy * DT_H;
+      const unsigned long long val = ((unsigned long long)tcar[i] << 32) | tile[i];      // already in the level's 2^-S units
+      const int tgt = lv_lookup(lvw, (x0 + hx - 1) & M, (y0 + hy - 1) & M, (z0 + hz - 1) & M);   // particles sit on interior nodes: every touched cell exists
+      if (tgt >= 0) atomicAdd(&acc[tgt], val);
+    }
+    return;
+  }
+  // flush (dense): thread = one (hx,hy) column of the tile, marching in z (no div/mod, constant strides)
   if (threadIdx.x < DT_H * DT_H) {
     const int hx = threadIdx.x % DT_H, hy = threadIdx.x / DT_H;
     const int x = (x0 + hx - 1) & M, y = (y0 + hy - 1) & M;
@@ -376,13 +406,8 @@ k_deposit_tiles(const float4 *__restrict__ pos4, const int32_t *__restrict__ tst
       if ((v | cr) == 0) continue;
       const int z = (z0 + hz - 1) & M;
       const unsigned long long val = ((unsigned long long)cr << 32) | v;          // already in the level's 2^-S units
-      if (SPARSE) {
-        const int tgt = lv_lookup(lvw, x, y, z);         // particles sit on interior nodes: every touched cell exists
-        if (tgt >= 0) atomicAdd(&acc[tgt], val);
-      } else {
-        unsigned long long *dstp = &acc[(((size_t)z << logL | y) << logL) | x];
-        if (sole && inxy && hz >= 2 && hz <= DT_T - 1) *dstp = val; else atomicAdd(dstp, val);
-      }
+      unsigned long long *dstp = &acc[(((size_t)z << logL | y) << logL) | x];
+      if (sole && inxy && hz >= 2 && hz <= DT_T - 1) *dstp = val; else atomicAdd(dstp, val);
     }
   }
 }
@@ -429,7 +454,7 @@ __constant__ uint16_t c_dom_off[27];     // byte offset of term (k,j,a) inside t
 template <int VAR>      // 0 = product; 1..4 = timing experiments (AHFGPU_DOM_VARIANT): 1 no return/carry, 2 no atomics, 3 no flush, 4 one copy
 __global__ void __launch_bounds__(DT_THREADS, 2)
 k_deposit_dom(const float4 *__restrict__ pos4, const int4 *__restrict__ work, int W, int L, int logL,
-              unsigned long long *__restrict__ acc, const uint32_t one /* == 1, a run-time value on purpose: see dom_carry */)
+              unsigned long long *__restrict__ acc, const uint32_t one /* == 1, a run-time value on purpose: see dom_carry */, const int rmax)
 {
   extern __shared__ __align__(16) unsigned char dsm[];
   float4   *sp   = reinterpret_cast<float4 *>(dsm);
@@ -509,11 +534,17 @@ k_deposit_dom(const float4 *__restrict__ pos4, const int4 *__restrict__ work, in
       wyz[k * 3 + 0] = __umulhi(wy[0], wz[k]); wyz[k * 3 + 2] = __umulhi(wy[2], wz[k]);
       wyz[k * 3 + 1] = wz[k] - wyz[k * 3 + 0] - wyz[k * 3 + 2];
     }
-    const int  cid0 = __shfl_sync(0xffffffffu, cid, 0);
-    const bool grouped = __all_sync(0xffffffffu, cid == cid0) && cid0 >= 0;
+    // dense slices (clump cores): the particles of one cell are adjacent lanes (Hilbert order).  When the 32 lanes hold at most
+    // `rmax` distinct cells, every run of equal cells sums its 27 terms with REDUX over the run's lane mask (two 16-bit limbs)
+    // and only the run's first lane touches shared memory: no same-address serialisation of the atomics.
+    const int      cprev = __shfl_up_sync(0xffffffffu, cid, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || cid != cprev);
+    const bool grouped = __popc(heads) <= rmax && __all_sync(0xffffffffu, cid >= 0);
     if (grouped) {
-      // clump cores: the whole warp sits in ONE cell -> sum the 27 terms across the warp (two 16-bit limbs through REDUX);
-      // lane 0 issues a plane's 9 low-word atomics back to back, then adds (high part + carry-out) to the carry counters
+      const unsigned upto = (2u << lane) - 1u;                                    // lanes 0..lane (lane 31: all)
+      const int      rlo = 31 - __clz(heads & upto);
+      const unsigned above = heads & ~upto;
+      const unsigned rmask = (above ? ((1u << (__ffs(above) - 1)) - 1u) : 0xffffffffu) & ~((1u << rlo) - 1u);
       const uint32_t lo0 = tile_s + 4u * (uint32_t)widx, ca0 = lo0 + 4u * DD_CAR;
 #pragma unroll
       for (int k = 0; k < 3; k++) {
@@ -525,12 +556,12 @@ k_deposit_dom(const float4 *__restrict__ pos4, const int4 *__restrict__ work, in
           const uint32_t vv[3] = { v0, v1, v2 };
 #pragma unroll
           for (int a = 0; a < 3; a++) {
-            const uint32_t l0 = __reduce_add_sync(0xffffffffu, vv[a] & 0xffffu), l1 = __reduce_add_sync(0xffffffffu, vv[a] >> 16);
+            const uint32_t l0 = __reduce_add_sync(rmask, vv[a] & 0xffffu), l1 = __reduce_add_sync(rmask, vv[a] >> 16);
             const unsigned long long tot = (unsigned long long)l0 + ((unsigned long long)l1 << 16);
             tl[j * 3 + a] = (uint32_t)tot; th[j * 3 + a] = (uint32_t)(tot >> 32);
           }
         }
-        if (lane == 0) {
+        if (lane == rlo) {
 #pragma unroll
           for (int q = 0; q < 9; q++) old[q] = dom_atom(lo0 + 4u * (uint32_t)((k * DT_H + q / 3) * DT_H + q % 3), tl[q]);
 #pragma unroll
@@ -869,15 +900,39 @@ __global__ void k_neighbours(LV v, int32_t *__restrict__ nbr, uint8_t *__restric
   if (c >= v.ncell) return;
   int x, y, z; lv_coords(v, c, x, y, z);
   const int L = (int)v.L;
+  // the 8 rows around the cell's own: all hash probes are issued together (independent loads in flight), resolved afterwards
+  int      rowc[9];
+  uint64_t kq[9], sq[9], hq[9];
+#pragma unroll
+  for (int q = 0; q < 9; q++) {
+    const int k = q / 3, j = q % 3;
+    int zz = z + k - 1; if (zz < 0) zz = L - 1; else if (zz >= L) zz = 0;
+    int yy = y + j - 1; if (yy < 0) yy = L - 1; else if (yy >= L) yy = 0;
+    kq[q] = lv_key(v, x, yy, zz);
+    sq[q] = mix64(kq[q] >> 3) & v.hmask;
+  }
+#pragma unroll
+  for (int q = 0; q < 9; q++) hq[q] = (q == 4) ? 0 : v.hkey[sq[q]];
+#pragma unroll
+  for (int q = 0; q < 9; q++) {
+    if (q == 4) { rowc[q] = c; continue; }
+    const uint64_t kb = kq[q] >> 3;
+    uint64_t s = sq[q], hk = hq[q];
+    while (hk != kb && hk != ~0ull) { s = (s + 1) & v.hmask; hk = v.hkey[s]; }
+    sq[q] = s; hq[q] = hk;
+  }
+#pragma unroll
+  for (int q = 0; q < 9; q++) if (q != 4) rowc[q] = (hq[q] == (kq[q] >> 3)) ? v.hval[sq[q] * 8 + (kq[q] & 7)] : -1;
   bool all = true;
+#pragma unroll
   for (int k = 0; k < 3; k++) {
     int zz = z + k - 1; if (zz < 0) zz = L - 1; else if (zz >= L) zz = 0;
-    int pm = (k == 1) ? c : lv_lookup(v, x, y, zz);
+    const int pm = rowc[k * 3 + 1];                               // the plane is found through its (x, y) node (get_nnodes.c:514-651)
+#pragma unroll
     for (int j = 0; j < 3; j++) {
       int yy = y + j - 1; if (yy < 0) yy = L - 1; else if (yy >= L) yy = 0;
       int32_t *o = nbr + (size_t)c * 27 + k * 9 + j * 3;
-      int rm = -1;
-      if (pm >= 0) rm = (j == 1) ? pm : lv_lookup(v, x, yy, zz);
+      const int rm = (pm >= 0) ? rowc[k * 3 + j] : -1;
       if (rm < 0) { o[0] = o[1] = o[2] = -1; all = false; continue; }
       o[1] = rm;
       const uint64_t kk = v.ckey[rm];
@@ -1081,6 +1136,8 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
       if (tiles_dense && !dom_v1) {
         const char *ev = getenv("AHFGPU_DOM_VARIANT");
         const int var = ev ? atoi(ev) : 0;
+        const char *er = getenv("AHFGPU_DOM_RMAX");
+        const int rmax = er ? atoi(er) : 1;           // slices with at most this many distinct cells take the run-reduction path (measured: 1 = whole warp in one cell is best; partial-mask REDUX costs more than the conflicts it removes)
         work4.reserve(W);
         LAUNCH(c, k_tile_work4, nblk(ntile, 256), 256, 0, tstart.p, nchunk.p, woff.p, ntile, tbits, work4.p);
         int nsm = 0;
@@ -1088,7 +1145,7 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
         // AHFGPU_DOM_PERSIST=1: two persistent CTAs per SM striding over the items (measured slower: static striding loses the
         // hardware's dynamic balance between light and heavy tiles); default: one CTA per item
         const unsigned grid = getenv("AHFGPU_DOM_PERSIST") ? (unsigned)std::min(W, 2 * nsm) : (unsigned)W;
-#define DOM_LAUNCH(V) LAUNCH(c, k_deposit_dom<V>, grid, DT_THREADS, DD_SMEM, c->pos4, work4.p, W, (int)lv.L, v.logL, acc.p, 1u)
+#define DOM_LAUNCH(V) LAUNCH(c, k_deposit_dom<V>, grid, DT_THREADS, DD_SMEM, c->pos4, work4.p, W, (int)lv.L, v.logL, acc.p, 1u, rmax)
         if (var == 1) DOM_LAUNCH(1); else if (var == 2) DOM_LAUNCH(2); else if (var == 3) DOM_LAUNCH(3); else if (var == 4) DOM_LAUNCH(4); else DOM_LAUNCH(0);
 #undef DOM_LAUNCH
       }
