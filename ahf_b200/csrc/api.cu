@@ -1,9 +1,69 @@
 // api.cu -- extern "C" entry points of libahfgpu.so (see include/ahfgpu.h) and context housekeeping.
 #include "common.cuh"
+#include <mutex>
+#include <unordered_map>
 
 namespace ahf {
 thread_local std::string g_last_error;
 thread_local cudaStream_t g_pool_stream = nullptr;
+
+// ---- size-class block cache (see common.cuh)
+namespace {
+struct CacheKey { cudaStream_t st; size_t cls; bool operator<(const CacheKey &o) const { return st != o.st ? st < o.st : cls < o.cls; } };
+struct CacheMeta { cudaStream_t st; size_t cls; };
+std::mutex g_cache_mu;
+std::map<CacheKey, std::vector<void *>> g_cache_free;
+std::unordered_map<void *, CacheMeta>   g_cache_live;
+// below 1 MiB: powers of two from 512 B; above: eight classes per octave (at most 12.5 % slack)
+size_t cache_class(size_t bytes)
+{
+  if (bytes <= 512) return 512;
+  size_t p2 = 512;
+  while (p2 < bytes) p2 <<= 1;
+  if (p2 <= (1u << 20)) return p2;
+  const size_t step = p2 >> 4;                       // p2/2 .. p2 in eight steps
+  return ((bytes + step - 1) / step) * step;
+}
+}  // namespace
+void *cache_alloc(size_t bytes)
+{
+  const size_t cls = cache_class(bytes);
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    auto it = g_cache_free.find(CacheKey{ g_pool_stream, cls });
+    if (it != g_cache_free.end() && !it->second.empty()) {
+      void *p = it->second.back(); it->second.pop_back();
+      g_cache_live[p] = CacheMeta{ g_pool_stream, cls };
+      return p;
+    }
+  }
+  void *p = nullptr;
+  cudaError_t e = cudaMallocAsync(&p, cls, g_pool_stream);
+  if (e != cudaSuccess) {                            // out of memory: drop the cache and retry once
+    cudaGetLastError();
+    cache_release_all();
+    cudaStreamSynchronize(g_pool_stream);
+    CUDA_CHECK(cudaMallocAsync(&p, cls, g_pool_stream));
+  }
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  g_cache_live[p] = CacheMeta{ g_pool_stream, cls };
+  return p;
+}
+void cache_free(void *p)
+{
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  auto it = g_cache_live.find(p);
+  if (it == g_cache_live.end()) { cudaFreeAsync(p, g_pool_stream); return; }     // not ours (should not happen)
+  g_cache_free[CacheKey{ it->second.st, it->second.cls }].push_back(p);
+  g_cache_live.erase(it);
+}
+void cache_release_all()
+{
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  for (auto &kv : g_cache_free) for (void *p : kv.second) cudaFreeAsync(p, kv.first.st);
+  g_cache_free.clear();
+}
 
 void Level::free_all()
 {
@@ -19,7 +79,7 @@ using namespace ahf;
 void ahfgpu_ctx::stage_reset()
 {
   for (auto &s : stages) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
-  stages.clear(); stage_ms.clear(); stage_cnt.clear(); stage_cnt_extra.clear(); stages_resolved = true;
+  stages.clear(); stage_ms.clear(); stage_cnt.clear(); stage_cnt_extra.clear(); stage_wall.clear(); stages_resolved = true;
 }
 void ahfgpu_ctx::stage_resolve()
 {
@@ -118,6 +178,13 @@ int ahfgpu_finalize(ahfgpu_ctx *c)
   c->stage_reset(); c->free_halos(); c->free_levels(); c->free_particles();
   ahf::dfree(c->in_pos); ahf::dfree(c->in_mom); ahf::dfree(c->in_w); ahf::dfree(c->in_u);
   for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+  {                                                   // blocks cached for this context's stream go back to the driver pool
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (auto it = g_cache_free.begin(); it != g_cache_free.end();) {
+      if (it->first.st == c->stream) { for (void *p : it->second) cudaFreeAsync(p, c->stream); it = g_cache_free.erase(it); }
+      else ++it;
+    }
+  }
   cudaStreamSynchronize(c->stream);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -313,6 +380,11 @@ double ahfgpu_stage_ms(ahfgpu_ctx *c, const char *name)
 {
   if (!c || !name) return -1.0;
   c->stage_resolve();
+  const std::string nm(name);
+  if (nm.size() > 5 && nm.compare(nm.size() - 5, 5, "@wall") == 0) {
+    auto iw = c->stage_wall.find(nm.substr(0, nm.size() - 5));
+    return iw == c->stage_wall.end() ? -1.0 : iw->second;
+  }
   auto it = c->stage_ms.find(name);
   return it == c->stage_ms.end() ? -1.0 : it->second;
 }

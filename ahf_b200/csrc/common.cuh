@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <chrono>
 #include "../../include/ahfgpu.h"
 
 namespace ahf {
@@ -40,7 +41,14 @@ inline void fail(const char *file, int line, const std::string &what)
 // stream-ordered allocation from the device's default memory pool (release threshold raised in ahfgpu_init so that
 // freed blocks are reused instead of being returned to the driver): every API entry sets g_pool_stream = ctx->stream
 extern thread_local cudaStream_t g_pool_stream;
-inline void dfree(void *p) { if (p) cudaFreeAsync(p, g_pool_stream); }
+// Size-class cache in front of cudaMallocAsync (api.cu).  A pass of the path allocates the same few hundred blocks every time
+// (level arrays, sort and halo scratch, several GB at 512^3); handing a freed block of the same size class straight back costs
+// nothing, whereas the driver pool may have to re-map physical memory when its free space is fragmented (measured: hundreds of
+// ms per pass at 512^3).  Blocks are cached per stream, so reuse is ordered like any other work on that stream.
+void *cache_alloc(size_t bytes);
+void  cache_free(void *p);
+void  cache_release_all();      // give everything cached back to the driver pool
+inline void dfree(void *p) { if (p) cache_free(p); }
 
 template <typename T> struct DevBuf {
   T     *p   = nullptr;
@@ -50,7 +58,7 @@ template <typename T> struct DevBuf {
     if (n <= cap) return;
     if (p) ahf::dfree(p);
     p = nullptr; cap = 0;
-    CUDA_CHECK(cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), ahf::g_pool_stream));
+    p = static_cast<T *>(ahf::cache_alloc((n ? n : 1) * sizeof(T)));
     cap = n ? n : 1;
   }
   void release() { if (p) ahf::dfree(p); p = nullptr; cap = 0; }
@@ -126,6 +134,7 @@ struct ahfgpu_ctx {
   std::map<std::string, double>  stage_ms;
   std::map<std::string, int64_t> stage_cnt;
   std::map<std::string, int64_t> stage_cnt_extra;   // counters set directly by the stages (not event based)
+  std::map<std::string, double>  stage_wall;        // host wall clock spent inside the stage scopes (ms); query "<name>@wall"
   bool stages_resolved = true;
 
   void stage_reset();
@@ -140,6 +149,7 @@ namespace ahf {
 // RAII stage timer: CUDA events on the library's stream around a group of launches
 struct Stage {
   ahfgpu_ctx *c; size_t idx;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
   Stage(ahfgpu_ctx *ctx, const char *name, int64_t count = 0) : c(ctx)
   {
     StageRec r; r.name = name; r.count = count;
@@ -147,7 +157,11 @@ struct Stage {
     CUDA_CHECK(cudaEventRecord(r.a, c->stream));
     c->stages.push_back(r); idx = c->stages.size() - 1; c->stages_resolved = false;
   }
-  ~Stage() { cudaEventRecord(c->stages[idx].b, c->stream); }
+  ~Stage()
+  {
+    cudaEventRecord(c->stages[idx].b, c->stream);
+    c->stage_wall[c->stages[idx].name] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
 };
 
 // entry points implemented in the .cu files

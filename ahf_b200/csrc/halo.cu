@@ -1777,7 +1777,7 @@ static std::vector<int64_t> host_excl(const std::vector<int64_t> &v, int64_t *to
 template <typename T> static T *dalloc(size_t n)
 {
   T *p = nullptr;
-  CUDA_CHECK(cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), ahf::g_pool_stream));
+  p = static_cast<T *>(ahf::cache_alloc((n ? n : 1) * sizeof(T)));
   return p;
 }
 static inline unsigned nblk(uint64_t n, int b) { return (unsigned)((n + b - 1) / b); }

@@ -1035,7 +1035,7 @@ __global__ void k_nonzero(const uint8_t *in, int n, uint8_t *out)
 template <typename T> static T *dalloc(size_t n)
 {
   T *p = nullptr;
-  CUDA_CHECK(cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), ahf::g_pool_stream));
+  p = static_cast<T *>(ahf::cache_alloc((n ? n : 1) * sizeof(T)));
   return p;
 }
 static inline unsigned nblk(uint64_t n, int b) { return (unsigned)((n + b - 1) / b); }
@@ -1182,6 +1182,7 @@ static void alloc_cell_arrays(Level &lv)
 
 void amr_build(ahfgpu_ctx *c)
 {
+  Stage sall(c, "amr_total", (int64_t)c->n);
   c->free_levels();
   const uint64_t n = c->n;
   const ahfgpu_params &par = c->par;

@@ -237,8 +237,8 @@ static void alloc_particles(ahfgpu_ctx *c, uint64_t n)
   c->free_levels();
   c->free_halos();
   c->n = n;
-  CUDA_CHECK(cudaMallocAsync(&c->pos4, (n ? n : 1) * sizeof(float4), ahf::g_pool_stream));
-  CUDA_CHECK(cudaMallocAsync(&c->mom4, (n ? n : 1) * sizeof(float4), ahf::g_pool_stream));
+  c->pos4 = static_cast<decltype(c->pos4)>(ahf::cache_alloc((n ? n : 1) * sizeof(float4)));
+  c->mom4 = static_cast<decltype(c->mom4)>(ahf::cache_alloc((n ? n : 1) * sizeof(float4)));
 }
 
 void sfc_keys_only(ahfgpu_ctx *c, const float *pos3, uint64_t n, uint32_t bits, uint64_t *keys_out)
@@ -258,10 +258,10 @@ void sfc_upload_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, const f
   if (n >= (1ull << 32)) AHF_FAIL("more than 2^32-1 particles per device are not supported");
   ahf::dfree(c->in_pos); ahf::dfree(c->in_mom); ahf::dfree(c->in_w); ahf::dfree(c->in_u);
   c->in_pos = c->in_mom = c->in_w = c->in_u = nullptr; c->in_n = n;
-  CUDA_CHECK(cudaMallocAsync(&c->in_pos, (n ? n : 1) * 3 * sizeof(float), ahf::g_pool_stream));
-  CUDA_CHECK(cudaMallocAsync(&c->in_mom, (n ? n : 1) * 3 * sizeof(float), ahf::g_pool_stream));
-  if (w) CUDA_CHECK(cudaMallocAsync(&c->in_w, (n ? n : 1) * sizeof(float), ahf::g_pool_stream));
-  if (u) CUDA_CHECK(cudaMallocAsync(&c->in_u, (n ? n : 1) * sizeof(float), ahf::g_pool_stream));
+  c->in_pos = static_cast<decltype(c->in_pos)>(ahf::cache_alloc((n ? n : 1) * 3 * sizeof(float)));
+  c->in_mom = static_cast<decltype(c->in_mom)>(ahf::cache_alloc((n ? n : 1) * 3 * sizeof(float)));
+  if (w) c->in_w = static_cast<decltype(c->in_w)>(ahf::cache_alloc((n ? n : 1) * sizeof(float)));
+  if (u) c->in_u = static_cast<decltype(c->in_u)>(ahf::cache_alloc((n ? n : 1) * sizeof(float)));
   Stage st(c, "h2d", (int64_t)(24 * n + (w ? 4 * n : 0) + (u ? 4 * n : 0)));
   CUDA_CHECK(cudaMemcpyAsync(c->in_pos, pos3, 3 * n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   CUDA_CHECK(cudaMemcpyAsync(c->in_mom, mom3, 3 * n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
@@ -293,8 +293,8 @@ void sfc_sort_resident(ahfgpu_ctx *c, uint64_t *keys_out, uint32_t *order_out)
     Stage st(c, "gather", (int64_t)n);
     if (n) LAUNCH(c, k_gather_soa, nb, 256, 0, c->in_pos, c->in_mom, c->in_w, c->in_u, vs, n, c->pos4, c->mom4);
   }
-  CUDA_CHECK(cudaMallocAsync(&c->keys, (n ? n : 1) * sizeof(uint64_t), ahf::g_pool_stream));
-  CUDA_CHECK(cudaMallocAsync(&c->order, (n ? n : 1) * sizeof(uint32_t), ahf::g_pool_stream));
+  c->keys = static_cast<decltype(c->keys)>(ahf::cache_alloc((n ? n : 1) * sizeof(uint64_t)));
+  c->order = static_cast<decltype(c->order)>(ahf::cache_alloc((n ? n : 1) * sizeof(uint32_t)));
   CUDA_CHECK(cudaMemcpyAsync(c->keys, ks, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
   CUDA_CHECK(cudaMemcpyAsync(c->order, vs, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
   if (keys_out || order_out) {
@@ -352,8 +352,8 @@ void sfc_sort_device4(ahfgpu_ctx *c, const void *pos4_dev, const void *mom4_dev,
     Stage st(c, "gather", (int64_t)n);
     if (n) LAUNCH(c, k_gather4, nb, 256, 0, (const float4 *)pos4_dev, (const float4 *)mom4_dev, vs, n, c->pos4, c->mom4);
   }
-  CUDA_CHECK(cudaMallocAsync(&c->keys, (n ? n : 1) * sizeof(uint64_t), ahf::g_pool_stream));
-  CUDA_CHECK(cudaMallocAsync(&c->order, (n ? n : 1) * sizeof(uint32_t), ahf::g_pool_stream));
+  c->keys = static_cast<decltype(c->keys)>(ahf::cache_alloc((n ? n : 1) * sizeof(uint64_t)));
+  c->order = static_cast<decltype(c->order)>(ahf::cache_alloc((n ? n : 1) * sizeof(uint32_t)));
   CUDA_CHECK(cudaMemcpyAsync(c->keys, ks, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
   CUDA_CHECK(cudaMemcpyAsync(c->order, vs, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -390,8 +390,8 @@ void sfc_sort_aos(ahfgpu_ctx *c, void *part, uint64_t n, uint32_t stride, int of
     Stage st(c, "gather", (int64_t)n);
     if (n) LAUNCH(c, k_gather_aos, nb, 256, 0, in.p, out.p, vs, ks, n, stride, off_pos, off_mom, off_key, off_w, off_u, c->pos4, c->mom4);
   }
-  CUDA_CHECK(cudaMallocAsync(&c->keys, (n ? n : 1) * sizeof(uint64_t), ahf::g_pool_stream));
-  CUDA_CHECK(cudaMallocAsync(&c->order, (n ? n : 1) * sizeof(uint32_t), ahf::g_pool_stream));
+  c->keys = static_cast<decltype(c->keys)>(ahf::cache_alloc((n ? n : 1) * sizeof(uint64_t)));
+  c->order = static_cast<decltype(c->order)>(ahf::cache_alloc((n ? n : 1) * sizeof(uint32_t)));
   CUDA_CHECK(cudaMemcpyAsync(c->keys, ks, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
   CUDA_CHECK(cudaMemcpyAsync(c->order, vs, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
   {

@@ -61,7 +61,10 @@ class SlabBox:
         key sorted, resident in the mesh context."""
         g, L, dev = self.g, ahf.lib(), self.device
         n_local = int(pos_local.shape[0])
-        g.sfc_sort(pos_local, mom_local, want_keys=False, want_order=False)
+        if isinstance(pos_local, torch.Tensor):     # (pinned) host tensors: no staging copy inside the driver
+            g.sfc_sort_ptr(pos_local.data_ptr(), mom_local.data_ptr(), n_local)
+        else:
+            g.sfc_sort(pos_local, mom_local, want_keys=False, want_order=False)
         pos4 = dev_tensor(L.ahfgpu_device_ptr(g._h, b"pos4"), (n_local, 4), "<f4", dev)
         mom4 = dev_tensor(L.ahfgpu_device_ptr(g._h, b"mom4"), (n_local, 4), "<f4", dev)
         keys = dev_tensor(L.ahfgpu_device_ptr(g._h, b"keys"), (n_local,), "<i8", dev)       # 63-bit keys: non-negative as int64

@@ -152,8 +152,12 @@ def bench_slab(args, rank, world, local_rank, config):
     import torch.distributed as dist
     from ahf_b200 import ahf, multigpu, synth
     # every rank generates only its own share of the box (a z-slab of the lattice + every world-th clump)
-    pos_l, mom_l, cl, boxsize, pmass = synth.make_box_slice(args.n1d, rank, world, seed=43)
+    pos_np, mom_np, cl, boxsize, pmass = synth.make_box_slice(args.n1d, rank, world, seed=43)
     c, r, seed = synth.halo_seeds_from(cl["centres"], cl["npart"], cl["scale"], boxsize)
+    # pinned host buffers: what a reader would fill; the upload is part of every step
+    pos_l = torch.empty(pos_np.shape, dtype=torch.float32, pin_memory=True); pos_l.numpy()[:] = pos_np
+    mom_l = torch.empty(mom_np.shape, dtype=torch.float32, pin_memory=True); mom_l.numpy()[:] = mom_np
+    del pos_np, mom_np
     nl = torch.tensor([pos_l.shape[0]], device="cuda", dtype=torch.int64)
     if world > 1:
         dist.all_reduce(nl)
@@ -203,7 +207,8 @@ def bench_slab(args, rank, world, local_rank, config):
                           "mode": "slab", "note": "host->device upload of the rank's file-order slice is inside the timed step",
                           "levels": sb.g.nlevels(), "halos_ge_minpart": int((scal[:, 9] >= par.min_part).sum()),
                           "phases_ms_rank0": {k: v / args.steps for k, v in tphase.items()},
-                          "mesh_stages_ms_rank0": {k: sb.g.stage_ms(k) for k in ("deposit", "deposit_dom_kernel", "allreduce", "flag", "refine", "relink")}}))
+                          "mesh_stages_ms_rank0": {k: sb.g.stage_ms(k) for k in ("amr_total", "ll", "deposit", "deposit_dom_kernel", "allreduce", "flag", "refine", "relink")},
+                          "mesh_stages_host_wall_ms_rank0": {k: sb.g.stage_ms(k + "@wall") for k in ("amr_total", "deposit", "allreduce", "flag", "refine", "relink")}}))
     sb.close()
     if world > 1:
         dist.destroy_process_group()
