@@ -1651,13 +1651,23 @@ __global__ void __launch_bounds__(HB) k_p_finish(const float4 *__restrict__ pos4
   const int h = act[blockIdx.x];
   double *S = scal + (size_t)h * AHFGPU_NSCAL;
   const int nbins = (int)S[57], t0 = G.tile0[h], nt = G.ntile[h];
-  for (int idx = threadIdx.x; idx < nbins * NACC; idx += HB) {       // (bin, component): partials summed in tile order
+  // tiles touching bin b form one contiguous range (first and last bin of a tile both grow with the tile number): two binary
+  // searches per bin, then the partials are summed in tile order -- a 10^7-particle host has 10^4 tiles
+  __shared__ int s_tlo[MAXBINS], s_thi[MAXBINS];
+  for (int b = threadIdx.x; b < nbins; b += HB) {
+    int lo = t0, hi = t0 + nt;                                        // first tile whose last bin >= b
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (G.tile_blo[mid] + G.tile_ns[mid] - 1 < b) lo = mid + 1; else hi = mid; }
+    s_tlo[b] = lo;
+    hi = t0 + nt;                                                     // first tile whose first bin > b
+    int l2 = lo;
+    while (l2 < hi) { const int mid = (l2 + hi) >> 1; if (G.tile_blo[mid] <= b) l2 = mid + 1; else hi = mid; }
+    s_thi[b] = l2;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < nbins * NACC; idx += HB) {       // (bin, component)
     const int b = idx / NACC, q = idx - b * NACC;
     double a = 0.0;
-    for (int t = t0; t < t0 + nt; t++) {
-      const int blo = G.tile_blo[t];
-      if (b >= blo && b < blo + G.tile_ns[t]) a += G.partial[((size_t)G.slot_off[t] + (b - blo)) * NACC + q];
-    }
+    for (int t = s_tlo[b]; t < s_thi[b]; t++) a += G.partial[((size_t)G.slot_off[t] + (b - G.tile_blo[t])) * NACC + q];
     acc[b][q] = a;
   }
   for (int i = threadIdx.x; i < nbins; i += HB) {
@@ -1855,12 +1865,13 @@ static void unbind_cooperative(ahfgpu_ctx *c, int64_t nhalo, const HP &P, const 
   // ---- rem_unbound (ahf_halos.c:3292-3607): all haloes iterate together, a halo leaves when nremove <= 3 or npart < min_part
   std::vector<char> active(nhalo);
   std::vector<int64_t> h_nrem(nhalo);
-  int64_t work = 0;
+  int64_t work = 0, n_iter = 0, n_sweep = 0;
   for (int64_t h = 0; h < nhalo; h++) active[h] = h_np[h] >= P.min_part;
   for (int iter = 1;; iter++) {
     build(active);
     if (!nact) break;
     for (int h : act) work += h_np[h];
+    n_iter++;
     mass_prefix();
     LAUNCH(c, k_g_phi_a, (unsigned)nt, HB, 0, c->pos4, d_ctr, d_moff0, d_members, G, d_tiles, d_Mpre, d_tt);
     LAUNCH(c, k_g_scan<1>, (unsigned)nact, HB, 0, d_act, G.tile0, G.ntile, d_tt, d_tc, d_htot1);
@@ -1871,6 +1882,7 @@ static void unbind_cooperative(ahfgpu_ctx *c, int64_t nhalo, const HP &P, const 
     LAUNCH(c, k_g_mask<true>, (unsigned)nt, HB, 0, c->pos4, c->mom4, has_u, d_ctr, d_moff0, d_members, G, d_tiles, d_vesc2, d_tc, P, d_mask, d_tt, d_changed);
     for (;;) {              // fixed point: two sweeps per read-back; converged when the last sweep changed nothing
       CUDA_CHECK(cudaMemsetAsync(d_changed, 0, sizeof(int) * 2, c->stream));
+      n_sweep += 2;
       for (int q = 0; q < 2; q++) {
         LAUNCH(c, k_g_scan<GNC>, (unsigned)nact, HB, 0, d_act, G.tile0, G.ntile, d_tt, d_tc, d_htot5);
         LAUNCH(c, k_g_mask<false>, (unsigned)nt, HB, 0, c->pos4, c->mom4, has_u, d_ctr, d_moff0, d_members, G, d_tiles, d_vesc2, d_tc, P, d_mask, d_tt, d_changed + q);
@@ -1893,6 +1905,8 @@ static void unbind_cooperative(ahfgpu_ctx *c, int64_t nhalo, const HP &P, const 
   LAUNCH(c, k_g_write_scal, nblk(nhalo, 128), 128, 0, G, d_ctr, d_ng, d_n6, d_n7, nhalo, P.min_part, c->h_scal, d_np_out);
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
   *iter_members = work;
+  c->stage_cnt_extra["halo_unbind_iterations"] = n_iter;
+  c->stage_cnt_extra["halo_unbind_mask_sweeps"] = n_sweep;
   for (void *q : { (void *)G.np, (void *)G.nb, (void *)G.nremove, (void *)G.Mvir, (void *)G.Rvir, (void *)G.ovd, (void *)G.Phi0, (void *)G.seed, (void *)G.first,
                    (void *)G.tile0, (void *)G.ntile, (void *)d_n6, (void *)d_n7, (void *)d_tiles, (void *)d_act, (void *)d_tt, (void *)d_tc, (void *)d_htot1,
                    (void *)d_htot5, (void *)d_vesc2, (void *)d_Mpre, (void *)d_mask, (void *)d_tmp, (void *)d_changed })

@@ -255,3 +255,43 @@ def halo_seeds_from(centres_box, npart, scale_box, boxsize, max_gather_rad_mpc: 
             ids=np.zeros(0, np.uint64), vel_kms=np.zeros((0, 3), np.float32), clump_centres=np.asarray(centres_box), clump_npart=np.asarray(npart),
             clump_scale=np.asarray(scale_box))
     return halo_seeds(b, max_gather_rad_mpc)
+
+
+def make_host_box(n_host: int, n_sub: int = 40, n1d_bg: int = 64, seed: int = 47, boxsize: float = 64.0, omega0: float = 0.3,
+                  lambda0: float = 0.7) -> Box:
+    """BASELINE.json configs[4] stand-in for the cooperative unbinding path: ONE Plummer host of `n_host` particles with `n_sub`
+    smaller Plummer subclumps inside it, on a sparse jittered-lattice background (equal-mass dark matter).  The host is far
+    larger than anything one thread block should walk alone."""
+    rng = np.random.default_rng(seed)
+    box = float(boxsize)
+    sub_n = np.maximum(200, (n_host * 10.0 ** rng.uniform(-4.0, -2.0, size=n_sub)).astype(np.int64))
+    n_bg = n1d_bg ** 3
+    ntot = int(n_host + sub_n.sum() + n_bg)
+    pmass = omega0 * RHOC0 * box ** 3 / ntot
+    cn = np.concatenate([[n_host], sub_n]).astype(np.int64)
+    mass = cn * pmass
+    a_pl = np.clip(0.1 * (mass / 1e14) ** (1.0 / 3.0), 0.02, 0.15)
+    centres = np.empty((n_sub + 1, 3))
+    centres[0] = 0.5 * box + rng.uniform(-1.0, 1.0, size=3)
+    d = rng.normal(size=(n_sub, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    centres[1:] = centres[0] + d * (a_pl[0] * rng.uniform(1.5, 12.0, size=n_sub))[:, None]
+    xs, vs = [], []
+    cell = box / n1d_bg
+    g = (np.arange(n1d_bg) + 0.5) * cell
+    lat = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(-1, 3) + rng.normal(0.0, 0.3 * cell, size=(n_bg, 3))
+    xs.append(lat.astype(np.float32)); vs.append(rng.normal(0.0, 50.0, size=(n_bg, 3)).astype(np.float32))
+    for c in range(n_sub + 1):
+        m = int(cn[c])
+        u = rng.uniform(1e-9, 1.0 - 1e-6, size=m)
+        r = np.minimum(a_pl[c] / np.sqrt(u ** (-2.0 / 3.0) - 1.0), 20.0 * a_pl[c])
+        dd = rng.normal(size=(m, 3)); dd /= np.linalg.norm(dd, axis=1, keepdims=True)
+        sig2 = GRAV * mass[c] / (6.0 * a_pl[c]) / np.sqrt(1.0 + (r / a_pl[c]) ** 2)
+        xs.append((centres[c] + dd * r[:, None]).astype(np.float32))
+        vs.append((rng.normal(0.0, 200.0, size=3) + rng.normal(size=(m, 3)) * np.sqrt(sig2)[:, None]).astype(np.float32))
+    x = np.mod(np.concatenate(xs), np.float32(box)).astype(np.float32)
+    x = np.where(x >= np.float32(box), np.nextafter(np.float32(box), np.float32(0.0)), x).astype(np.float32)
+    v = np.concatenate(vs)
+    pos = (x * np.float32(1.0 / box)).astype(np.float32)
+    mom = (v * np.float32(1.0 / (box * 100.0))).astype(np.float32)
+    return Box(n1d=n1d_bg, boxsize=box, omega0=omega0, lambda0=lambda0, pmass=pmass, pos=pos, mom=mom, ids=np.arange(ntot, dtype=np.uint64),
+               vel_kms=v, clump_centres=centres / box, clump_npart=cn, clump_scale=a_pl / box)

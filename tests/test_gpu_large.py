@@ -170,3 +170,31 @@ def test_domain_deposit_conserves_mass_exactly(A):
         g.sfc_sort(box.pos[perm], box.mom[perm])
         g.build_amr()
         assert np.array_equal(g.level(0, cells=False).dens.astype(np.float64), d)
+
+
+def test_cooperative_halo_pass_equals_one_cta_per_halo(A):
+    """one large host (4e5 members) with subclumps: the cooperative multi-block kernels (default) and the one-CTA-per-halo kernels
+    give identical member lists and scalars / profiles equal to rounding (different but fixed summation trees)"""
+    from ahf_b200 import synth
+    box = synth.make_host_box(400_000, n_sub=12, n1d_bg=32)
+    c, r, npart = synth.halo_seeds(box)
+    par = A.make_params(boxsize=box.boxsize, pmass=box.pmass, lgrid_dom=64)
+    out = {}
+    try:
+        for variant in ("coop", "v1"):
+            for k in ("AHFGPU_UNBIND_V1", "AHFGPU_PROFILES_V1", "AHFGPU_GATHER_V1"):
+                if variant == "v1":
+                    os.environ[k] = "1"
+                else:
+                    os.environ.pop(k, None)
+            with A.AhfGpu(par) as g:
+                g.sfc_sort(box.pos, box.mom)
+                out[variant] = g.construct_halos(c, r, npart)
+    finally:
+        for k in ("AHFGPU_UNBIND_V1", "AHFGPU_PROFILES_V1", "AHFGPU_GATHER_V1"):
+            os.environ.pop(k, None)
+    a, b = out["coop"], out["v1"]
+    assert int(a["scal"][0, 9]) > 300_000
+    assert np.array_equal(a["members"], b["members"]) and np.array_equal(a["member_offset"], b["member_offset"])
+    assert np.allclose(a["scal"], b["scal"], rtol=1e-10, atol=1e-300, equal_nan=True)
+    assert np.allclose(a["prof"], b["prof"], rtol=1e-9, atol=1e-300, equal_nan=True)
