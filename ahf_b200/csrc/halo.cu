@@ -1400,6 +1400,10 @@ struct PG {
   double  *w_r, *y0a, *y0b, *y1a, *y1b, *Mpre;   // per member (moff0 layout); Mpre only with weights
 };
 
+constexpr int PNC = 5;     // scan components of the profile pass: M, P(3), baryon mass (gas + stars; GAS_PARTICLES build)
+// species of a particle from `u` (param.h:26-28; ahf_halos.c:4424, :4470): gas u >= PGAS (0), stars u == PSTAR (-4)
+__device__ __forceinline__ bool is_baryon(double u) { return u >= 0.0 || fabs(u + 4.0) < ZERO_F; }
+
 __device__ __forceinline__ int bin_of(double rp, const double *__restrict__ edge, int nbins, int b)
 {
   while (b < nbins - 1 && !(rp < edge[b])) b++;
@@ -1429,22 +1433,26 @@ __global__ void k_p_bins(const float4 *__restrict__ pos4, const double *__restri
 
 __global__ void __launch_bounds__(HB) k_p_sum(const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, const double *__restrict__ centre,
                                               const int64_t *__restrict__ moff0, const uint32_t *__restrict__ members, PG G, const int2 *__restrict__ tiles,
-                                              const double *__restrict__ scal, double *__restrict__ tt)
+                                              const double *__restrict__ scal, int has_u, double *__restrict__ tt)
 {
-  __shared__ double smd[(HB / 32) * 4];
+  __shared__ double smd[(HB / 32) * PNC];
   const int2 tl = tiles[blockIdx.x];
   const int  h = tl.x; const long long base = (long long)tl.y * HT, np = G.np[h];
   const uint32_t *ip = members + moff0[h];
-  double loc[4] = { 0, 0, 0, 0 };
+  double loc[PNC] = { 0, 0, 0, 0, 0 };
 #pragma unroll
   for (int i = 0; i < HI; i++) {
     const long long j = base + (long long)threadIdx.x * HI + i;
-    if (j < np) { const uint32_t pid = ip[j]; const double w = (double)pos4[pid].w; const float4 m = mom4[pid]; loc[0] += w; loc[1] += w * m.x; loc[2] += w * m.y; loc[3] += w * m.z; }
+    if (j < np) {
+      const uint32_t pid = ip[j]; const double w = (double)pos4[pid].w; const float4 m = mom4[pid];
+      loc[0] += w; loc[1] += w * m.x; loc[2] += w * m.y; loc[3] += w * m.z;
+      if (has_u && is_baryon((double)m.w)) loc[4] += w;
+    }
   }
-  block_sum_n<4>(loc, smd);
+  block_sum_n<PNC>(loc, smd);
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int q = 0; q < 4; q++) tt[(size_t)blockIdx.x * 4 + q] = loc[q];
+    for (int q = 0; q < PNC; q++) tt[(size_t)blockIdx.x * PNC + q] = loc[q];
     // bins of the tile's first and last member: the first bin whose edge exceeds the radius of the member BEFORE (ahf_halos.c:4283)
     const double c[3] = { centre[3 * h], centre[3 * h + 1], centre[3 * h + 2] };
     const int nbins = (int)scal[(size_t)h * AHFGPU_NSCAL + 57];
@@ -1495,7 +1503,7 @@ __global__ void __launch_bounds__(HB) k_p_phi(const float4 *__restrict__ pos4, i
   const uint32_t *ip = members + moff0[h];
   TileMembers T;
   load_tile(T, pos4, ip, base, np, c);
-  const double carryM = tc4[(size_t)blockIdx.x * 4];
+  const double carryM = tc4[(size_t)blockIdx.x * PNC];
   double M[HI], term[HI], prev_r, prev_I;
   p_tile_M(T, has_w, carryM, base, M, smd);
   p_prev_member(pos4, ip, has_w, carryM, base, c, prev_r, prev_I);
@@ -1530,14 +1538,28 @@ __global__ void __launch_bounds__(HB) k_p_main(const float4 *__restrict__ pos4, 
     if (T.act[i]) { float4 m = mom4[T.pid[i]]; mom[i][0] = (double)m.x; mom[i][1] = (double)m.y; mom[i][2] = (double)m.z; uu[i] = (double)m.w; }
   }
   __syncthreads();
-  const double carryM = tc4[(size_t)blockIdx.x * 4];
+  const double carryM = tc4[(size_t)blockIdx.x * PNC];
   p_tile_M(T, has_w, carryM, base, M, smd);
+  // GAS_PARTICLES build: R_max and r2 come from the dark matter alone (AHFdmonly_Rmax_r2, ahf_halos.c:4603-4611) -> cumulative baryon mass
+  double Mb[HI];
+#pragma unroll
+  for (int i = 0; i < HI; i++) Mb[i] = 0.0;
+  if (has_u) {
+    double loc[1] = { 0.0 }, ex[1], tot[1];
+#pragma unroll
+    for (int i = 0; i < HI; i++) if (T.act[i] && is_baryon(uu[i])) loc[0] += T.w[i];
+    block_excl_scan_n<1>(loc, ex, tot, smd);
+    double run = tc4[(size_t)blockIdx.x * PNC + 4] + ex[0];
+#pragma unroll
+    for (int i = 0; i < HI; i++) { if (T.act[i] && is_baryon(uu[i])) run += T.w[i]; Mb[i] = run; }
+    __syncthreads();
+  }
   {
     double loc[3] = { 0, 0, 0 }, ex[3], tot[3];
 #pragma unroll
     for (int i = 0; i < HI; i++) { loc[0] += T.w[i] * mom[i][0]; loc[1] += T.w[i] * mom[i][1]; loc[2] += T.w[i] * mom[i][2]; }
     block_excl_scan_n<3>(loc, ex, tot, smd);
-    double run[3] = { tc4[(size_t)blockIdx.x * 4 + 1] + ex[0], tc4[(size_t)blockIdx.x * 4 + 2] + ex[1], tc4[(size_t)blockIdx.x * 4 + 3] + ex[2] };
+    double run[3] = { tc4[(size_t)blockIdx.x * PNC + 1] + ex[0], tc4[(size_t)blockIdx.x * PNC + 2] + ex[1], tc4[(size_t)blockIdx.x * PNC + 3] + ex[2] };
 #pragma unroll
     for (int i = 0; i < HI; i++) {
 #pragma unroll
@@ -1586,7 +1608,8 @@ __global__ void __launch_bounds__(HB) k_p_main(const float4 *__restrict__ pos4, 
       const long long e = moff0[h] + j;
       // per-member arrays of find_max (ahf_halos.c:4598-4616): r, rho r^2, v_circ^2
       const double r = T.r[i], rpv = j ? rprev[i] : 0.0, dV = F43 * ((r * r * r) - (rpv * rpv * rpv));
-      G.w_r[e] = r; G.y0a[e] = w / dV * (((r + rpv) / 2.) * ((r + rpv) / 2.)); G.y1a[e] = M[i] / r;
+      const double w_dm = (has_u && is_baryon(uu[i])) ? 0.0 : w;
+      G.w_r[e] = r; G.y0a[e] = w_dm / dV * (((r + rpv) / 2.) * ((r + rpv) / 2.)); G.y1a[e] = (M[i] - Mb[i]) / r;
       if (has_w) G.Mpre[e] = M[i];
       // the last member of a bin owns the bin's v_esc2 and cumulative momentum
       bool lastofbin = (j == np - 1);
@@ -1945,12 +1968,12 @@ static void profiles_cooperative(ahfgpu_ctx *c, int64_t nhalo, const HP &P, cons
   G.tbest_e = dalloc<double>(nt); G.tbest_j = dalloc<long long>(nt);
   G.w_r = dalloc<double>(tot_g); G.y0a = dalloc<double>(tot_g); G.y0b = dalloc<double>(tot_g); G.y1a = dalloc<double>(tot_g); G.y1b = dalloc<double>(tot_g);
   G.Mpre = has_w ? dalloc<double>(tot_g) : nullptr;
-  double *d_tt4 = dalloc<double>((size_t)nt * 4), *d_tc4 = dalloc<double>((size_t)nt * 4), *d_ht4 = dalloc<double>((size_t)nhalo * 4);
+  double *d_tt4 = dalloc<double>((size_t)nt * PNC), *d_tc4 = dalloc<double>((size_t)nt * PNC), *d_ht4 = dalloc<double>((size_t)nhalo * PNC);
   double *d_tt1 = dalloc<double>(nt), *d_tc1 = dalloc<double>(nt), *d_ht1 = dalloc<double>(nhalo);
   double *d_tval = dalloc<double>((size_t)nt * 2); long long *d_tidx = dalloc<long long>((size_t)nt * 2);
   LAUNCH(c, k_p_bins, nblk(nact, 64), 64, 0, c->pos4, d_ctr, d_moff0, d_members, G, d_act, nact, c->h_scal, P);
-  LAUNCH(c, k_p_sum, (unsigned)nt, HB, 0, c->pos4, c->mom4, d_ctr, d_moff0, d_members, G, d_tiles, c->h_scal, d_tt4);
-  LAUNCH(c, k_g_scan<4>, (unsigned)nact, HB, 0, d_act, d_tile0, d_ntile, d_tt4, d_tc4, d_ht4);
+  LAUNCH(c, k_p_sum, (unsigned)nt, HB, 0, c->pos4, c->mom4, d_ctr, d_moff0, d_members, G, d_tiles, c->h_scal, has_u, d_tt4);
+  LAUNCH(c, k_g_scan<PNC>, (unsigned)nact, HB, 0, d_act, d_tile0, d_ntile, d_tt4, d_tc4, d_ht4);
   LAUNCH(c, k_p_phi, (unsigned)nt, HB, 0, c->pos4, has_w, d_ctr, d_moff0, d_members, G, d_tiles, d_tc4, d_tt1);
   LAUNCH(c, k_g_scan<1>, (unsigned)nact, HB, 0, d_act, d_tile0, d_ntile, d_tt1, d_tc1, d_ht1);
   const int nslot = exclusive_scan<int32_t>(c, G.tile_ns, d_slot, (uint64_t)nt);

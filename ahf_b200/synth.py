@@ -295,3 +295,78 @@ def make_host_box(n_host: int, n_sub: int = 40, n1d_bg: int = 64, seed: int = 47
     mom = (v * np.float32(1.0 / (box * 100.0))).astype(np.float32)
     return Box(n1d=n1d_bg, boxsize=box, omega0=omega0, lambda0=lambda0, pmass=pmass, pos=pos, mom=mom, ids=np.arange(ntot, dtype=np.uint64),
                vel_kms=v, clump_centres=centres / box, clump_npart=cn, clump_scale=a_pl / box)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# multi-species boxes (dark matter + gas + stars) for the -DMULTIMASS -DGAS_PARTICLES build of the reference
+# ---------------------------------------------------------------------------------------------------------------------
+PGAS, PDM, PSTAR = 0.0, -1.0, -4.0       # reference src/param.h:26-28: what `u` holds for non-gas particles
+
+
+@dataclass
+class SpeciesBox:
+    box: Box                 # particles regrouped by GADGET type: gas (0), dark matter (1), stars (4)
+    ngas: int
+    ndm: int
+    nstar: int
+    mass: np.ndarray         # (N,) float32 Msun/h
+    weight: np.ndarray       # (N,) float32 mass / dark-matter particle mass (io_gadget.c:1595-1599)
+    u: np.ndarray            # (N,) float32: thermal energy (km/s)^2 for gas, -type for the others (io_gadget.c:1943-1958)
+
+
+def make_species_box(n1d: int, seed: int = 42, gas_frac: float = 0.15, star_frac: float = 0.05, gas_mass: float = 0.2, star_mass: float = 0.1,
+                     **kw) -> SpeciesBox:
+    """make_box() with a random subset of particles turned into lighter gas / star particles."""
+    b = make_box(n1d, seed=seed, **kw)
+    rng = np.random.default_rng([seed, 77])
+    n = b.npart
+    t = rng.random(n)
+    typ = np.where(t < gas_frac, 0, np.where(t < gas_frac + star_frac, 4, 1))
+    order = np.argsort(typ, kind="stable")
+    typ = typ[order]
+    ngas, ndm, nstar = int((typ == 0).sum()), int((typ == 1).sum()), int((typ == 4).sum())
+    w = np.where(typ == 0, gas_mass, np.where(typ == 4, star_mass, 1.0)).astype(np.float32)
+    u = np.where(typ == 0, rng.uniform(1e3, 2e5, size=n), np.where(typ == 4, PSTAR, PDM)).astype(np.float32)
+    nb = Box(n1d=b.n1d, boxsize=b.boxsize, omega0=b.omega0, lambda0=b.lambda0, pmass=b.pmass, pos=b.pos[order], mom=b.mom[order],
+             ids=np.arange(n, dtype=np.uint64), vel_kms=b.vel_kms[order], clump_centres=b.clump_centres, clump_npart=b.clump_npart,
+             clump_scale=b.clump_scale)
+    return SpeciesBox(box=nb, ngas=ngas, ndm=ndm, nstar=nstar, mass=(w * np.float32(b.pmass)).astype(np.float32), weight=w, u=u)
+
+
+def write_gadget1_species(sb: SpeciesBox, path: str) -> None:
+    """GADGET-1 with types 0/1/4: massarr[1] > 0, a MASS block for gas and stars (the reference's GADGET-1 reader skips exactly four
+    blocks POS, VEL, ID, MASS before U, io_gadget.c:1850-1853) and a U block for the gas."""
+    b = sb.box
+    n = b.npart
+    hdr = bytearray(256)
+    np_ = [sb.ngas, sb.ndm, 0, 0, sb.nstar, 0]
+    massarr = [0.0, b.pmass / 1e10, 0.0, 0.0, 0.0, 0.0]
+    struct.pack_into("<6i", hdr, 0, *np_)
+    struct.pack_into("<6d", hdr, 24, *massarr)
+    struct.pack_into("<2d", hdr, 72, 1.0, 0.0)
+    struct.pack_into("<2i", hdr, 88, 0, 0)
+    struct.pack_into("<6I", hdr, 96, *np_)
+    struct.pack_into("<2i", hdr, 120, 0, 1)
+    struct.pack_into("<4d", hdr, 128, b.boxsize, b.omega0, b.lambda0, 0.7)
+
+    def block(f, payload: bytes):
+        f.write(struct.pack("<I", len(payload))); f.write(payload); f.write(struct.pack("<I", len(payload)))
+
+    x = (b.pos.astype(np.float32) * np.float32(b.boxsize)).astype("<f4")
+    m = (sb.mass.astype(np.float64) / 1e10).astype("<f4")
+    with open(path, "wb") as f:
+        block(f, bytes(hdr))
+        block(f, x.tobytes())
+        block(f, b.vel_kms.astype("<f4").tobytes())
+        block(f, b.ids.astype("<u4").tobytes())
+        block(f, np.concatenate([m[:sb.ngas], m[sb.ngas + sb.ndm:]]).tobytes())          # types with massarr == 0, in type order
+        block(f, sb.u[:sb.ngas].astype("<f4").tobytes())
+
+
+def write_reference_case_species(sb: SpeciesBox, workdir: str, lgrid_domain: int | None = None, **kw) -> str:
+    os.makedirs(workdir, exist_ok=True)
+    snap = os.path.join(workdir, "snap.gadget")
+    write_gadget1_species(sb, snap)
+    inp = os.path.join(workdir, "AHF.input")
+    write_ahf_input(inp, snap, os.path.join(workdir, "ref"), lgrid_domain or sb.box.n1d, **kw)
+    return inp

@@ -333,6 +333,7 @@ static void profiles(const float *pos, const float *mom, const float *wgt, const
   double  M_sph_prev = 0.0, prev_dist = 0.0, M = 0.0, Vc[3] = { 0, 0, 0 }, a11 = 0, a22 = 0, a33 = 0, a12 = 0, a13 = 0, a23 = 0;
   double  sig_v = 0, Lv[3] = { 0, 0, 0 }, CoM[3] = { 0, 0, 0 }, Epot = 0, Ekin = 0, Emin = 1e30, M_hires = 0, M_lores = 0;
   double  cur_dist = -1.0, v_esc2 = 0.0, F43 = 4. * PI_ / 3.;
+  double  M_gas = 0.0, M_star = 0.0;     /* GAS_PARTICLES build: cumulative gas / star mass (ahf_halos.c:4424-4484) */
   double *Vcirc2, *dens_r2, *ovd, *rad, *pr, x_max, r2, R_max, V_max, M_max, absL;
   double *s = out->s;
   if (nbins < 2) nbins = 2;
@@ -387,9 +388,12 @@ static void profiles(const float *pos, const float *mom, const float *wgt, const
       rad[jp] = cur_dist;
       ovd[jp] = M / (F43 * (cur_dist * cur_dist * cur_dist));
       dVv     = F43 * ((cur_dist * cur_dist * cur_dist) - (prev_dist * prev_dist * prev_dist));
-      dMm     = M - M_sph_prev;
-      Vcirc2[jp] = M / cur_dist;
-      M_sph_prev = M;
+      /* AHFdmonly_Rmax_r2 && GAS_PARTICLES (define.h:66, ahf_halos.c:4603-4611): R_max and r2 from the dark matter alone;
+         gas: u >= PGAS (0), stars: |u - PSTAR| < ZERO with PSTAR = -4 (param.h:26-28) */
+      if (u) { if (u[p] >= 0.0f) M_gas += w; if (fabs((double)u[p] - (-4.0)) < ZERO_F) M_star += w; }
+      dMm     = (M - M_gas - M_star) - M_sph_prev;
+      Vcirc2[jp] = (M - M_gas - M_star) / cur_dist;
+      M_sph_prev = M - M_gas - M_star;
       dens_r2[jp] = dMm / dVv * (((cur_dist + prev_dist) / 2.) * ((cur_dist + prev_dist) / 2.));
       prev_dist = cur_dist;
       jp++;

@@ -9,7 +9,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = ["frag16", "edge32", "plain32"]
+GOLDEN_CASES = ["frag16", "edge32", "plain32", "species32"]
 
 
 def pytest_configure(config):
@@ -26,6 +26,9 @@ class Golden:
         self.nper_dom = float(self.d["nper_dom"]); self.nper_ref = float(self.d["nper_ref"])
         self.keys = self.d["keys"]; self.pos = self.d["pos"]; self.mom = self.d["mom"]; self.ids = self.d["ids"]
         self.glob = self.d["halo_glob"]; self.hs = self.d["halo_s"]
+        # multi-species fixtures (the reference's -DMULTIMASS -DGAS_PARTICLES build) carry weights and thermal energies
+        self.weight = self.d["weight"] if "weight" in self.d.files else None
+        self.u = self.d["u"] if "u" in self.d.files else None
 
     def input_order(self):
         """positions / momenta in snapshot-file order (ids are 0..N-1 in file order)"""

@@ -24,16 +24,28 @@ CASES = {
 }
 
 
-def collect(name, n1d, seed, ncl, nper_dom, nper_ref, centres):
-    box = synth.make_box(n1d, seed=seed, n_clumps=ncl, centres_box=None if centres is None else np.array(centres))
+# multi-species cases run the -DMULTIMASS -DGAS_PARTICLES build (oracle/_ref/ahf_ref_mm): gas + dark matter + stars
+CASES_MM = {
+    "species32": (32, 11, 6, 2.0, 2.5, None),
+}
+
+
+def collect(name, n1d, seed, ncl, nper_dom, nper_ref, centres, species=False):
     work = tempfile.mkdtemp(prefix="ahf_golden_")
     try:
-        inp = synth.write_reference_case(box, work, nper_dom=nper_dom, nper_ref=nper_ref)
-        O.run_reference(inp, dump_dir=os.path.join(work, "dump"), threads=1)
+        if species:
+            sb = synth.make_species_box(n1d, seed=seed, n_clumps=ncl, centres_box=None if centres is None else np.array(centres))
+            inp = synth.write_reference_case_species(sb, work, nper_dom=nper_dom, nper_ref=nper_ref)
+        else:
+            box = synth.make_box(n1d, seed=seed, n_clumps=ncl, centres_box=None if centres is None else np.array(centres))
+            inp = synth.write_reference_case(box, work, nper_dom=nper_dom, nper_ref=nper_ref)
+        O.run_reference(inp, dump_dir=os.path.join(work, "dump"), threads=1, multimass=species)
         d = os.path.join(work, "dump")
-        P = O.read_particles(os.path.join(d, "particles.bin"))
+        P = O.read_particles(os.path.join(d, "particles.bin"), multimass=species)
         out = dict(n1d=n1d, seed=seed, nper_dom=nper_dom, nper_ref=nper_ref, boxsize=P.boxsize, pmass=P.pmass,
                    ids=P.ids.astype(np.uint32), keys=P.keys, pos=P.pos, mom=P.mom)   # key-sorted; input (file) order: x_in[ids] = x
+        if species:
+            out["weight"] = P.weight; out["u"] = P.u
         nlev = 0
         while os.path.exists(os.path.join(d, "flag_level_%02d.bin" % nlev)):
             R = O.read_level(os.path.join(d, "flag_level_%02d.bin" % nlev))
@@ -59,5 +71,10 @@ def collect(name, n1d, seed, ncl, nper_dom, nper_ref, centres):
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
     for k, v in CASES.items():
-        collect(k, *v)
+        if not only or k in only:
+            collect(k, *v)
+    for k, v in CASES_MM.items():
+        if not only or k in only:
+            collect(k, *v, species=True)

@@ -81,7 +81,7 @@ def _check_levels(g, golden):
 
 def test_amr_matches_reference(A, golden):
     with _ctx(A, golden) as g:
-        g.sfc_sort(golden.pos, golden.mom)       # already key-sorted: the stable sort keeps the order
+        g.sfc_sort(golden.pos, golden.mom, golden.weight, golden.u)       # already key-sorted: the stable sort keeps the order
         worst = _check_levels(g, golden)
         print("max density error", worst)
 
@@ -117,16 +117,22 @@ def _check_halos(g, golden, rtol=1e-9):
 
 
 def test_halo_pass_matches_reference(A, golden):
+    """species32: the -DMULTIMASS -DGAS_PARTICLES build (weights in M_vir / potential / profiles, thermal energy in the bound test
+    and Ekin, R_max and r2 from the dark matter alone)"""
     with _ctx(A, golden) as g:
-        g.sfc_sort(golden.pos, golden.mom)
+        g.sfc_sort(golden.pos, golden.mom, golden.weight, golden.u)
         _check_halos(g, golden)
 
 
 def test_end_to_end_from_file_order(A, golden):
     """sort + mesh + halo pass from the snapshot's own particle order (what main.c hands over)"""
     pos_in, mom_in = golden.input_order()
+    w_in = u_in = None
+    if golden.weight is not None:
+        w_in = np.empty_like(golden.weight); u_in = np.empty_like(golden.u)
+        w_in[golden.ids] = golden.weight; u_in[golden.ids] = golden.u
     with _ctx(A, golden) as g:
-        keys, order = g.sfc_sort(pos_in, mom_in)
+        keys, order = g.sfc_sort(pos_in, mom_in, w_in, u_in)
         if np.all(keys[1:] != keys[:-1]):
             _check_levels(g, golden)
             _check_halos(g, golden)

@@ -39,7 +39,7 @@ def test_hierarchy_matches_reference(golden):
 
 def test_halo_pass_matches_reference(golden):
     par = O.params_from_glob(golden.glob)
-    res = O.construct_halos(golden.keys, golden.pos, golden.mom, None, None, par, golden.hs[:, 0:3].copy(),
+    res = O.construct_halos(golden.keys, golden.pos, golden.mom, golden.weight, golden.u, par, golden.hs[:, 0:3].copy(),
                             golden.hs[:, 3].copy(), golden.hs[:, 4].copy())
     slots = list(range(10, 58))
     for i, r in enumerate(res):
