@@ -58,6 +58,10 @@ typedef struct {
   double   s[ORC_NSCAL];      /* scalars, slots 10.. as in ref_hooks.c                              */
   int      nbins;
   double  *prof;              /* malloc'd, ORC_NPROFCOL x nbins, column-major (col*nbins + bin)      */
+  /* GAS_PARTICLES build only (u != NULL): gas_only at 0, stars_only at 32 (SPECIESPROP, src/tdef.h:560-587):
+     npart, Mass, pos_com(3), pos_mbp(3), vel(3), lambda, lambdaE, AngMom(3), axis(3), E1(3), E2(3), E3(3), Ekin, Epot */
+  double   species[64];
+  double  *prof_species;      /* malloc'd, 3 x nbins: M_gas, M_star (cumulative), u_gas (per shell) */
 } orc_halo_result;
 
 /* particle arrays in key-sorted order; weight/u may be NULL (equal-mass DM, default reference build) */

@@ -334,6 +334,10 @@ static void profiles(const float *pos, const float *mom, const float *wgt, const
   double  sig_v = 0, Lv[3] = { 0, 0, 0 }, CoM[3] = { 0, 0, 0 }, Epot = 0, Ekin = 0, Emin = 1e30, M_hires = 0, M_lores = 0;
   double  cur_dist = -1.0, v_esc2 = 0.0, F43 = 4. * PI_ / 3.;
   double  M_gas = 0.0, M_star = 0.0;     /* GAS_PARTICLES build: cumulative gas / star mass (ahf_halos.c:4424-4484) */
+  /* per species (0 gas, 1 stars): n, M, com(3), V(3), L(3), a11 a22 a33 a12 a13 a23, Epot, Ekin ; most bound ; u of the shell */
+  double  sp[2][19], sp_emin[2] = { 1e30, 1e30 }, u_shell_gas = 0.0;
+  int64_t sp_mb[2] = { -1, -1 };
+  const double u_fac = (P->x_fac / 0.01) * (P->x_fac / 0.01);          /* (box / t_unit)^2, t_unit = 1/H0 (ahf_halos.c:205, startrun.c:547) */
   double *Vcirc2, *dens_r2, *ovd, *rad, *pr, x_max, r2, R_max, V_max, M_max, absL;
   double *s = out->s;
   if (nbins < 2) nbins = 2;
@@ -349,11 +353,14 @@ static void profiles(const float *pos, const float *mom, const float *wgt, const
 #define PR(col, b) pr[(col) * nbins + (b)]
   Vcirc2 = calloc((size_t)np, sizeof(double)); dens_r2 = calloc((size_t)np, sizeof(double));
   ovd = calloc((size_t)np, sizeof(double)); rad = calloc((size_t)np, sizeof(double));
+  memset(sp, 0, sizeof(sp));
+  if (u) out->prof_species = calloc((size_t)(3 * nbins), sizeof(double));
   rad_prev = dist_min;
   jp = 0;
   for (ibin = 0; ibin < nbins; ibin++) {
     double cur_rad = pow(10., ldmin + ((double)ibin + 1) * ldr), Volume, dM, dV, it[3][3], ax1, ax2, ax3;
     if (ibin == nbins - 1) cur_rad = dist_max + ZERO_F;
+    u_shell_gas = 0.0;                                      /* :4274 */
     while (cur_dist < cur_rad && jp < np) {
       int64_t p = ip[jp];
       double  w = wgt ? (double)wgt[p] : 1.0, d[3], dv[3], Tpart, Upart, Epart, dVv, dMm;
@@ -384,6 +391,26 @@ static void profiles(const float *pos, const float *mom, const float *wgt, const
       sig_v += Tpart; Ekin += Tpart;
       Epart  = (0.5 * Tpart + Upart);
       if (Epart < Emin) { Emin = Epart; mb = p; }
+      if (u) {                                              /* species sums (:4420-4582) */
+        const int isg = (u[p] >= 0.0f), iss = (fabs((double)u[p] - (-4.0)) < ZERO_F);
+        int t;
+        for (t = 0; t < 2; t++) {
+          if (!(t == 0 ? isg : iss)) continue;
+          double *a = sp[t];
+          const double *dvr = dv;                           /* the reference's dVX at this point already carries the Hubble term (:4376-4378); d x d = 0 up to rounding */
+          a[0] += 1.0; a[1] += w;
+          for (q = 0; q < 3; q++) a[2 + q] += w * (ctr[q] + d[q]);
+          for (q = 0; q < 3; q++) a[5 + q] += w * mom[3 * p + q];
+          a[8]  += w * (d[1] * dvr[2] - d[2] * dvr[1]);
+          a[9]  += w * (d[2] * dvr[0] - d[0] * dvr[2]);
+          a[10] += w * (d[0] * dvr[1] - d[1] * dvr[0]);
+          a[11] += w * d[0] * d[0]; a[12] += w * d[1] * d[1]; a[13] += w * d[2] * d[2];
+          a[14] += w * d[0] * d[1]; a[15] += w * d[0] * d[2]; a[16] += w * d[1] * d[2];
+          a[17] += Upart; a[18] += Tpart;
+          if (Epart < sp_emin[t]) { sp_emin[t] = Epart; sp_mb[t] = p; }
+        }
+        if (isg) u_shell_gas += w * (double)u[p] / u_fac;
+      }
       /* AHFparticle_Rmax_r2 per-member arrays (:4598-4616) */
       rad[jp] = cur_dist;
       ovd[jp] = M / (F43 * (cur_dist * cur_dist * cur_dist));
@@ -411,6 +438,7 @@ static void profiles(const float *pos, const float *mom, const float *wgt, const
     PR(13, ibin) = 1.0; PR(14, ibin) = it[0][0]; PR(15, ibin) = it[1][0]; PR(16, ibin) = it[2][0];
     PR(17, ibin) = (ax1 > 0.) ? sqrt(ax2 / ax1) : 0.0; PR(18, ibin) = it[0][1]; PR(19, ibin) = it[1][1]; PR(20, ibin) = it[2][1];
     PR(21, ibin) = (ax1 > 0.) ? sqrt(ax3 / ax1) : 0.0; PR(22, ibin) = it[0][2]; PR(23, ibin) = it[1][2]; PR(24, ibin) = it[2][2];
+    if (u) { out->prof_species[0 * nbins + ibin] = sp[0][1]; out->prof_species[1 * nbins + ibin] = sp[1][1]; out->prof_species[2 * nbins + ibin] = u_shell_gas; }
     M_prev = M; V_prev = Volume; rad_prev = cur_rad;
   }
   (void)rad_prev;
@@ -474,6 +502,29 @@ static void profiles(const float *pos, const float *mom, const float *wgt, const
     s[27] = CoM[0]; s[28] = CoM[1]; s[29] = CoM[2];
   }
   s[57] = (double)nbins;
+  if (u) {                                                  /* gas_only / stars_only (:5020-5181) */
+    int t;
+    for (t = 0; t < 2; t++) {
+      double *a = sp[t], *o = out->species + 32 * t;
+      if (a[0] <= 0.0) continue;                            /* reset_SPECIESPROP: all zero */
+      o[0] = a[0]; o[1] = a[1];
+      for (q = 0; q < 3; q++) { o[2 + q] = fmod(a[2 + q] / a[1] + 1.0, 1.0); o[8 + q] = a[5 + q] / a[1]; }
+      o[28] = 0.5 * a[18]; o[29] = 0.5 * a[17];
+      if (a[0] > 10.0) {                                    /* AHF_MINPART_GAS / AHF_MINPART_STARS (param.h:14-15) */
+        double aL = sqrt(a[8] * a[8] + a[9] * a[9] + a[10] * a[10]), it[3][3], ax1, ax2, ax3;
+        o[13] = a[8] / aL; o[14] = a[9] / aL; o[15] = a[10] / aL;
+        o[11] = aL / a[1] / sqrt(2. * M * R_vir_in);
+        o[11] *= P->v_fac * sqrt(P->r_fac / (GRAV_ * P->m_fac));
+        o[12] = calc_lambdaE(P, aL, M, a[1], o[28], o[29]);
+        it[0][0] = a[11]; it[1][1] = a[12]; it[2][2] = a[13]; it[0][1] = it[1][0] = a[14]; it[0][2] = it[2][0] = a[15]; it[1][2] = it[2][1] = a[16];
+        get_axes(it, &ax1, &ax2, &ax3);
+        o[16] = 1.0; o[17] = (ax1 > 0.) ? sqrt(ax2 / ax1) : 0.0; o[18] = (ax1 > 0.) ? sqrt(ax3 / ax1) : 0.0;
+        o[19] = it[0][0]; o[20] = it[1][0]; o[21] = it[2][0]; o[22] = it[0][1]; o[23] = it[1][1]; o[24] = it[2][1];
+        o[25] = it[0][2]; o[26] = it[1][2]; o[27] = it[2][2];
+      }
+      if (sp_mb[t] >= 0) { o[5] = pos[3 * sp_mb[t]]; o[6] = pos[3 * sp_mb[t] + 1]; o[7] = pos[3 * sp_mb[t] + 2]; }
+    }
+  }
 #undef PR
 }
 
@@ -516,6 +567,6 @@ void orc_halo_construct(const uint64_t *keys, const float *pos, const float *mom
 
 void orc_halo_result_free(orc_halo_result *r)
 {
-  free(r->ipart); free(r->prof);
-  r->ipart = NULL; r->prof = NULL;
+  free(r->ipart); free(r->prof); free(r->prof_species);
+  r->ipart = NULL; r->prof = NULL; r->prof_species = NULL;
 }

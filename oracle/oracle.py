@@ -175,6 +175,8 @@ class RefHalos:
     s: np.ndarray               # (n, 64) scalar slots, layout in oracle/ref_hooks.c dump_halos()
     members: list = field(default_factory=list)
     prof: list = field(default_factory=list)    # per halo (25, nbins) or None
+    species: np.ndarray | None = None           # (n, 64): gas_only at 0, stars_only at 32 (GAS_PARTICLES build)
+    prof_species: list | None = None            # per halo (3, nbins): M_gas, M_star, u_gas
 
 
 def read_halos(dump_dir: str) -> RefHalos:
@@ -192,7 +194,16 @@ def read_halos(dump_dir: str) -> RefHalos:
         for _ in range(n):
             nb = int(np.fromfile(f, np.int64, 1)[0])
             prof.append(np.fromfile(f, np.float64, 25 * nb).reshape(25, nb) if nb > 0 else None)
-    return RefHalos(n, g, s, members, prof)
+    rh = RefHalos(n, g, s, members, prof)
+    sp_path = os.path.join(dump_dir, "halo_species.bin")
+    if os.path.exists(sp_path):                     # GAS_PARTICLES build: gas_only / stars_only blocks and the M_gas, M_star, u_gas profile columns
+        rh.species = np.fromfile(sp_path, np.float64).reshape(n, 64)
+        rh.prof_species = []
+        with open(os.path.join(dump_dir, "halo_prof_species.bin"), "rb") as f:
+            for _ in range(n):
+                nb = int(np.fromfile(f, np.int64, 1)[0])
+                rh.prof_species.append(np.fromfile(f, np.float64, 3 * nb).reshape(3, nb) if nb > 0 else None)
+    return rh
 
 
 def run_reference(ahf_input: str, dump_dir: str | None = None, threads: int | None = None, multimass: bool = False,
@@ -230,7 +241,7 @@ class _HaloParams(C.Structure):
 class _HaloResult(C.Structure):
     _fields_ = [("npart", C.c_int64), ("ipart", C.POINTER(C.c_int64)), ("n_gather", C.c_int64), ("n_rvir0", C.c_int64),
                 ("n_unbound", C.c_int64), ("n_rvir1", C.c_int64), ("s", C.c_double * 64), ("nbins", C.c_int),
-                ("prof", C.POINTER(C.c_double))]
+                ("prof", C.POINTER(C.c_double)), ("species", C.c_double * 64), ("prof_species", C.POINTER(C.c_double))]
 
 
 def params_from_glob(g: np.ndarray) -> dict:
@@ -261,7 +272,11 @@ def construct_halos(keys, pos, mom, weight, u, par: dict, centres, gather_rad, s
         pr = None
         if r.nbins > 0:
             pr = np.ctypeslib.as_array(r.prof, shape=(25 * r.nbins,)).copy().reshape(25, r.nbins)
+        ps = None
+        if r.nbins > 0 and u is not None and bool(r.prof_species):
+            ps = np.ctypeslib.as_array(r.prof_species, shape=(3 * r.nbins,)).copy().reshape(3, r.nbins)
         out.append(dict(npart=int(r.npart), ipart=ip, n_gather=int(r.n_gather), n_rvir0=int(r.n_rvir0),
-                        n_unbound=int(r.n_unbound), n_rvir1=int(r.n_rvir1), s=np.array(r.s[:]), prof=pr, nbins=int(r.nbins)))
+                        n_unbound=int(r.n_unbound), n_rvir1=int(r.n_rvir1), s=np.array(r.s[:]), prof=pr, nbins=int(r.nbins),
+                        species=np.array(r.species[:]), prof_species=ps))
         L.orc_halo_result_free(C.byref(r))
     return out

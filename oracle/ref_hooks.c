@@ -298,6 +298,9 @@ static void dump_halos(void)
   f  = dump_open("halos.bin");
   fi = dump_open("halo_ipart.bin");
   fp = dump_open("halo_prof.bin");
+#ifdef GAS_PARTICLES
+  FILE *fs = dump_open("halo_species.bin"), *fps = dump_open("halo_prof_species.bin");
+#endif
   {
     int64_t hdr[2] = { g_numHalos, NSCAL };
     double  g[16];
@@ -355,8 +358,33 @@ static void dump_halos(void)
       for (b = 0; b < nb; b++) { double v = (double)h->prof.npart[b]; fwrite(&v, sizeof(double), 1, fp); }
       for (k = 0; k < 24; k++) fwrite(cols[k], sizeof(double), nb, fp);
     }
+#ifdef GAS_PARTICLES
+    {
+      /* gas_only at 0, stars_only at 32: npart, Mass, pos_com(3), pos_mbp(3), vel(3), lambda, lambdaE, AngMom(3), axis(3), E1, E2, E3, Ekin, Epot */
+      double sp[64];
+      int    q;
+      memset(sp, 0, sizeof(sp));
+      if (np >= simu.AHF_MINPART)
+        for (q = 0; q < 2; q++) {
+          SPECIESPROP *t = q ? &h->stars_only : &h->gas_only;
+          double *o = sp + 32 * q;
+          o[0] = (double)t->npart; o[1] = t->Mass; o[2] = t->pos_com.x; o[3] = t->pos_com.y; o[4] = t->pos_com.z;
+          o[5] = t->pos_mbp.x; o[6] = t->pos_mbp.y; o[7] = t->pos_mbp.z; o[8] = t->vel.x; o[9] = t->vel.y; o[10] = t->vel.z;
+          o[11] = t->lambda; o[12] = t->lambdaE; o[13] = t->AngMom.x; o[14] = t->AngMom.y; o[15] = t->AngMom.z;
+          o[16] = t->axis.x; o[17] = t->axis.y; o[18] = t->axis.z;
+          o[19] = t->E1.x; o[20] = t->E1.y; o[21] = t->E1.z; o[22] = t->E2.x; o[23] = t->E2.y; o[24] = t->E2.z;
+          o[25] = t->E3.x; o[26] = t->E3.y; o[27] = t->E3.z; o[28] = t->Ekin; o[29] = t->Epot;
+        }
+      fwrite(sp, sizeof(double), 64, fs);
+      fwrite(&nb, sizeof(int64_t), 1, fps);
+      if (nb > 0) { fwrite(h->prof.M_gas, sizeof(double), nb, fps); fwrite(h->prof.M_star, sizeof(double), nb, fps); fwrite(h->prof.u_gas, sizeof(double), nb, fps); }
+    }
+#endif
   }
   fclose(f); fclose(fi); fclose(fp);
+#ifdef GAS_PARTICLES
+  fclose(fs); fclose(fps);
+#endif
 }
 
 /* ahf_halos.c:824 -- first writer call; halos[] is complete (incl. the subhalo re-hash) and still alive */

@@ -46,6 +46,15 @@ class Golden:
     def members(self, i):
         return self.d["halo_members"][self.d["halo_moff"][i]:self.d["halo_moff"][i + 1]].astype(np.int64)
 
+    def species(self, i):
+        return self.d["halo_species"][i] if "halo_species" in self.d.files else None
+
+    def prof_species(self, i):
+        a, b = int(self.d["halo_poff"][i]), int(self.d["halo_poff"][i + 1])
+        if b == a or "halo_prof_species" not in self.d.files:
+            return None
+        return self.d["halo_prof_species"][a * 3:b * 3].reshape(3, b - a)
+
     def prof(self, i):
         a, b = int(self.d["halo_poff"][i]), int(self.d["halo_poff"][i + 1])
         if b == a:

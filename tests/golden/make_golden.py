@@ -64,6 +64,9 @@ def collect(name, n1d, seed, ncl, nper_dom, nper_ref, centres, species=False):
         nb = [0 if p is None else p.shape[1] for p in H.prof]
         out["halo_poff"] = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
         out["halo_prof"] = np.concatenate([p.reshape(-1) for p in H.prof if p is not None]) if sum(nb) else np.zeros(0)
+        if H.species is not None:
+            out["halo_species"] = H.species
+            out["halo_prof_species"] = np.concatenate([p.reshape(-1) for p in H.prof_species if p is not None]) if sum(nb) else np.zeros(0)
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **out)
         print(name, "levels", nlev, "halos", H.n, "bytes", os.path.getsize(os.path.join(ROOT, "tests", "golden", name + ".npz")))
     finally:

@@ -53,3 +53,7 @@ def test_halo_pass_matches_reference(golden):
         a, b = ref[slots], r["s"][slots]
         assert np.allclose(a, b, rtol=1e-12, atol=0), (i, np.nonzero(~np.isclose(a, b, rtol=1e-12, atol=0)))
         assert np.allclose(golden.prof(i), r["prof"], rtol=1e-12, atol=0)
+        if golden.species(i) is not None:          # GAS_PARTICLES build: gas_only / stars_only and the species profile columns
+            assert golden.species(i)[0] + golden.species(i)[32] > 0
+            assert np.allclose(golden.species(i), r["species"], rtol=1e-12, atol=0), (i, np.nonzero(~np.isclose(golden.species(i), r["species"], rtol=1e-12, atol=0)))
+            assert np.allclose(golden.prof_species(i), r["prof_species"], rtol=1e-12, atol=0)
