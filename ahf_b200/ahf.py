@@ -289,7 +289,20 @@ class AhfGpu:
         moff = np.empty(nh + 1, np.int64); poff = np.empty(nh + 1, np.int64)
         members = np.empty(max(tm.value, 1), np.int64); prof = np.empty(max(tb.value, 1) * NPROFCOL, np.float64)
         self._chk(self._L.ahfgpu_halo_fetch(self._h, _p(scal), _p(moff), _p(members), _p(poff), _p(prof)))
-        return dict(scal=scal, member_offset=moff, members=members[:tm.value], prof_offset=poff, prof=prof[:tb.value * NPROFCOL])
+        res = dict(scal=scal, member_offset=moff, members=members[:tm.value], prof_offset=poff, prof=prof[:tb.value * NPROFCOL])
+        # GAS_PARTICLES build (particles carry u): HALO.gas_only / HALO.stars_only and the M_gas, M_star, u_gas profile columns
+        species = np.empty((nh, 64), np.float64); psp = np.empty(max(tb.value, 1) * 3, np.float64)
+        if self._L.ahfgpu_halo_fetch_species(self._h, _p(species), _p(psp)) == 0:
+            res["species"] = species; res["prof_species"] = psp[:tb.value * 3]
+        return res
+
+    @staticmethod
+    def halo_profile_species(res: dict, i: int):
+        a, b = res["prof_offset"][i], res["prof_offset"][i + 1]
+        nb = int(b - a)
+        if nb == 0 or "prof_species" not in res:
+            return None
+        return res["prof_species"][a * 3:b * 3].reshape(3, nb)
 
     @staticmethod
     def halo_members(res: dict, i: int) -> np.ndarray:

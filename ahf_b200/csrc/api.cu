@@ -108,6 +108,7 @@ void ahfgpu_ctx::free_levels()
 void ahfgpu_ctx::free_halos()
 {
   ahf::dfree(h_scal); ahf::dfree(h_moff); ahf::dfree(h_members); ahf::dfree(h_poff); ahf::dfree(h_prof);
+  ahf::dfree(h_species); ahf::dfree(h_prof_species); h_species = nullptr; h_prof_species = nullptr;
   h_scal = nullptr; h_moff = nullptr; h_members = nullptr; h_poff = nullptr; h_prof = nullptr;
   nhalo = 0; h_total_members = h_total_bins = 0;
 }
@@ -373,6 +374,18 @@ int ahfgpu_halo_fetch(ahfgpu_ctx *c, double *scal, int64_t *member_offset, int64
   if (members && c->h_total_members) CUDA_CHECK(cudaMemcpy(members, c->h_members, sizeof(int64_t) * c->h_total_members, cudaMemcpyDeviceToHost));
   if (prof_offset) CUDA_CHECK(cudaMemcpy(prof_offset, c->h_poff, sizeof(int64_t) * (c->nhalo + 1), cudaMemcpyDeviceToHost));
   if (prof && c->h_total_bins) CUDA_CHECK(cudaMemcpy(prof, c->h_prof, sizeof(double) * AHFGPU_NPROFCOL * c->h_total_bins, cudaMemcpyDeviceToHost));
+  API_END
+}
+
+int ahfgpu_halo_fetch_species(ahfgpu_ctx *c, double *species, double *prof_species)
+{
+  API_BEGIN
+  if (!c) AHF_FAIL("null ctx");
+  if (!c->h_species) AHF_FAIL("no per-species results: the particles carry no thermal energy / type information (u)");
+  CUDA_CHECK(cudaSetDevice(c->dev));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (species && c->nhalo) CUDA_CHECK(cudaMemcpy(species, c->h_species, sizeof(double) * 64 * c->nhalo, cudaMemcpyDeviceToHost));
+  if (prof_species && c->h_total_bins) CUDA_CHECK(cudaMemcpy(prof_species, c->h_prof_species, sizeof(double) * 3 * c->h_total_bins, cudaMemcpyDeviceToHost));
   API_END
 }
 

@@ -128,6 +128,8 @@ struct ahfgpu_ctx {
   int64_t  *h_members = nullptr;     // device
   int64_t  *h_poff = nullptr;        // device [nhalo+1] (bins)
   double   *h_prof = nullptr;        // device
+  double   *h_species = nullptr;     // device [nhalo*64]      (GAS_PARTICLES build: gas_only at 0, stars_only at 32)
+  double   *h_prof_species = nullptr;// device [total bins*3]  (M_gas, M_star, u_gas)
   int64_t   h_total_members = 0, h_total_bins = 0;
   // stage timing
   std::vector<ahf::StageRec> stages;

@@ -1040,12 +1040,13 @@ __device__ double cr1_root(double c, double R1) { return (c - 2.0 * log(1.0 + c)
 //   per member prefix quantities (M, P, Phi) are block scans with carries; everything that is only sampled at bin
 //   edges (CoM, inertia tensor, L, Ekin, Epot ...) is reduced per (tile, bin) in a fixed order and prefix-summed over bins.
 // ------------------------------------------------------------------------------------------------
-constexpr int NACC = 18;   // CoM3, a11 a22 a33 a12 a13 a23, L3, Ekin, Epot, Mhires, Mlores, M, npart
+constexpr int NACC = 21;   // CoM3, a11 a22 a33 a12 a13 a23, L3, Ekin, Epot, Mhires, Mlores, M, npart, M_gas, M_star, u_gas (GAS_PARTICLES build)
+constexpr int NSPC = 19;   // per species: n, M, com(3), P(3), L(3), a11 a22 a33 a12 a13 a23, Epot, Ekin
 
 // per-bin cumulative values, Jacobi, profile columns and the integral properties (ahf_halos.c:4632-4710, :4870-5018); one thread
 __device__ void prof_finalize(const int nbins, const double (*acc)[NACC], const double *edge, const double *vesc_bin, const double (*Vc_bin)[3],
                               double *pr, double *S, const double R_vir, const HP &P, const long long best_j, const float4 *__restrict__ pos4,
-                              const float4 *__restrict__ mom4, const uint32_t *__restrict__ ip, const double c[3])
+                              const float4 *__restrict__ mom4, const uint32_t *__restrict__ ip, const double c[3], double *prsp = nullptr)
 {
   const double F43 = 4. * PI_ / 3.;
     double cum[NACC];
@@ -1067,6 +1068,7 @@ __device__ void prof_finalize(const int nbins, const double (*acc)[NACC], const 
       PR(13, b) = 1.0; PR(14, b) = it[0][0]; PR(15, b) = it[1][0]; PR(16, b) = it[2][0];
       PR(17, b) = (ax1 > 0.) ? sqrt(ax2 / ax1) : 0.0; PR(18, b) = it[0][1]; PR(19, b) = it[1][1]; PR(20, b) = it[2][1];
       PR(21, b) = (ax1 > 0.) ? sqrt(ax3 / ax1) : 0.0; PR(22, b) = it[0][2]; PR(23, b) = it[1][2]; PR(24, b) = it[2][2];
+      if (prsp) { prsp[0 * nbins + b] = cum[18]; prsp[1 * nbins + b] = cum[19]; prsp[2 * nbins + b] = acc[b][20]; }   // M_gas, M_star cumulative; u_gas of the shell (:4713-4715)
       M_prev = M; V_prev = Volume;
     }
     const double M = cum[16];
@@ -1397,6 +1399,8 @@ struct PG {
   const int32_t *slot_off;          // per tile: offset into the partial sums
   double  *partial;         // [slots][NACC]
   double  *tbest_e; long long *tbest_j;   // per tile: most bound member
+  double  *sp_part; double *sp_be; long long *sp_bj;   // GAS_PARTICLES build: per tile and species NSPC sums, most bound member
+  double  *species, *prof_species;        // outputs: [nhalo][64], [total bins][3]
   double  *w_r, *y0a, *y0b, *y1a, *y1b, *Mpre;   // per member (moff0 layout); Mpre only with weights
 };
 
@@ -1528,6 +1532,7 @@ __global__ void __launch_bounds__(HB) k_p_main(const float4 *__restrict__ pos4, 
   const int    nbins = (int)S[57];
   const double Phi0 = S[13];
   const double F43 = 4. * PI_ / 3.;
+  const double u_fac = (P.x_fac * 100.0) * (P.x_fac * 100.0);      // (box / t_unit)^2 with t_unit = 1/H0 (ahf_halos.c:205, startrun.c:547)
   for (int i = threadIdx.x; i < nbins; i += HB) edge[i] = G.edge[(size_t)h * MAXBINS + i];
   TileMembers T;
   load_tile(T, pos4, ip, base, np, c);
@@ -1637,6 +1642,10 @@ __global__ void __launch_bounds__(HB) k_p_main(const float4 *__restrict__ pos4, 
         s[12] += Tp[i]; s[13] += Up[i];
         if (has_w) { if (fabs(w - 1.0) < ZERO_F) s[14] += w; else if (w > 1.0) s[15] += w; } else s[14] += w;
         s[16] += w; s[17] += 1.0;
+        if (has_u) {
+          if (uu[i] >= 0.0) { s[18] += w; s[20] += w * uu[i] / u_fac; }          // gas (:4424-4474)
+          if (fabs(uu[i] + 4.0) < ZERO_F) s[19] += w;                            // stars (:4484)
+        }
       }
     }
     block_sum_n<NACC>(s, smd);
@@ -1644,6 +1653,50 @@ __global__ void __launch_bounds__(HB) k_p_main(const float4 *__restrict__ pos4, 
       double *dst = G.partial + ((size_t)G.slot_off[blockIdx.x] + (b - blo)) * NACC;
 #pragma unroll
       for (int q = 0; q < NACC; q++) dst[q] = s[q];
+    }
+  }
+  // GAS_PARTICLES build: gas_only / stars_only sums of the tile (:4420-4530) and the most bound member of each species
+  if (has_u) {
+    for (int t = 0; t < 2; t++) {
+      double s[NSPC];
+#pragma unroll
+      for (int q = 0; q < NSPC; q++) s[q] = 0.0;
+      double se = 1e30; long long sj = 0x7fffffffffffffffll;
+#pragma unroll
+      for (int i = 0; i < HI; i++) {
+        const bool in = T.act[i] && (t == 0 ? (uu[i] >= 0.0) : (fabs(uu[i] + 4.0) < ZERO_F));
+        if (in) {
+          const double w = T.w[i];
+          s[0] += 1.0; s[1] += w;
+          s[2] += w * (c[0] + T.d[i][0]); s[3] += w * (c[1] + T.d[i][1]); s[4] += w * (c[2] + T.d[i][2]);
+          s[5] += w * mom[i][0]; s[6] += w * mom[i][1]; s[7] += w * mom[i][2];
+          s[8] += Lm[i][0]; s[9] += Lm[i][1]; s[10] += Lm[i][2];                 // d x (H d) = 0: the Hubble term of the reference's dV drops out
+          s[11] += w * T.d[i][0] * T.d[i][0]; s[12] += w * T.d[i][1] * T.d[i][1]; s[13] += w * T.d[i][2] * T.d[i][2];
+          s[14] += w * T.d[i][0] * T.d[i][1]; s[15] += w * T.d[i][0] * T.d[i][2]; s[16] += w * T.d[i][1] * T.d[i][2];
+          s[17] += Up[i]; s[18] += Tp[i];
+          const double Epart = 0.5 * Tp[i] + Up[i];
+          const long long j = base + (long long)threadIdx.x * HI + i;
+          if (Epart < se) { se = Epart; sj = j; }
+        }
+      }
+      block_sum_n<NSPC>(s, smd);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        double e2 = __shfl_xor_sync(0xffffffffu, se, o); long long j2 = __shfl_xor_sync(0xffffffffu, sj, o);
+        if (e2 < se || (e2 == se && j2 < sj)) { se = e2; sj = j2; }
+      }
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) { s_emin[threadIdx.x >> 5] = se; s_eidx[threadIdx.x >> 5] = sj; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        se = s_emin[0]; sj = s_eidx[0];
+        for (int q = 1; q < HB / 32; q++) if (s_emin[q] < se || (s_emin[q] == se && s_eidx[q] < sj)) { se = s_emin[q]; sj = s_eidx[q]; }
+        double *dst = G.sp_part + ((size_t)blockIdx.x * 2 + t) * NSPC;
+#pragma unroll
+        for (int q = 0; q < NSPC; q++) dst[q] = s[q];
+        G.sp_be[(size_t)blockIdx.x * 2 + t] = se; G.sp_bj[(size_t)blockIdx.x * 2 + t] = sj;
+      }
+      __syncthreads();
     }
   }
   // most bound member of the tile: minimum of 0.5 T + U, first index on ties (:4590-4596)
@@ -1705,7 +1758,45 @@ __global__ void __launch_bounds__(HB) k_p_finish(const float4 *__restrict__ pos4
       if (jj != 0x7fffffffffffffffll && (G.tbest_e[t] < e || bj < 0)) { e = G.tbest_e[t]; bj = jj; }
     }
     const double c[3] = { centre[3 * h], centre[3 * h + 1], centre[3 * h + 2] };
-    prof_finalize(nbins, acc, edge, vesc_bin, Vc_bin, prof + poff[h] * AHFGPU_NPROFCOL, S, S[11], P, bj, pos4, mom4, members + moff0[h], c);
+    prof_finalize(nbins, acc, edge, vesc_bin, Vc_bin, prof + poff[h] * AHFGPU_NPROFCOL, S, S[11], P, bj, pos4, mom4, members + moff0[h], c,
+                  G.prof_species ? G.prof_species + poff[h] * 3 : nullptr);
+    if (G.species) {                       // gas_only / stars_only (ahf_halos.c:5020-5181): tile sums in tile order
+      const double M = S[10], R_vir = S[11];
+      for (int t = 0; t < 2; t++) {
+        double a[NSPC], se = 1e30; long long sj = -1;
+        for (int q = 0; q < NSPC; q++) a[q] = 0.0;
+        for (int tl = t0; tl < t0 + nt; tl++) {
+          const double *src = G.sp_part + ((size_t)tl * 2 + t) * NSPC;
+          for (int q = 0; q < NSPC; q++) a[q] += src[q];
+          const long long jj = G.sp_bj[(size_t)tl * 2 + t];
+          if (jj != 0x7fffffffffffffffll && (G.sp_be[(size_t)tl * 2 + t] < se || sj < 0)) { se = G.sp_be[(size_t)tl * 2 + t]; sj = jj; }
+        }
+        double *o = G.species + (size_t)h * 64 + 32 * t;
+        for (int q = 0; q < 32; q++) o[q] = 0.0;
+        if (a[0] <= 0.0) continue;                                       // reset_SPECIESPROP
+        o[0] = a[0]; o[1] = a[1];
+        for (int q = 0; q < 3; q++) { o[2 + q] = fmod(a[2 + q] / a[1] + 1.0, 1.0); o[8 + q] = a[5 + q] / a[1]; }
+        o[28] = 0.5 * a[18]; o[29] = 0.5 * a[17];
+        if (a[0] > 10.0) {                                               // AHF_MINPART_GAS / AHF_MINPART_STARS (param.h:14-15)
+          const double aL = sqrt(a[8] * a[8] + a[9] * a[9] + a[10] * a[10]);
+          o[13] = a[8] / aL; o[14] = a[9] / aL; o[15] = a[10] / aL;
+          double lam = aL / a[1] / sqrt(2. * M * R_vir);
+          lam *= P.v_fac * sqrt(P.r_fac / (GRAV_ * P.m_fac));
+          o[11] = lam;
+          double t1 = sqrt(P.m_fac * M); t1 = t1 * t1 * t1;                  // calc_lambdaE (:3937)
+          double t2 = o[28] * P.m_fac * (P.v_fac * P.v_fac), t3 = o[29] * P.m_fac * P.phi_fac;
+          t2 = sqrt(fabs(t2 + t3)); t1 = t2 / t1; t2 = P.m_fac * P.r_fac * P.v_fac * aL; t2 = t2 / (P.m_fac * a[1]);
+          o[12] = t1 * t2 / GRAV_;
+          double it[3][3], ax1, ax2, ax3;
+          it[0][0] = a[11]; it[1][1] = a[12]; it[2][2] = a[13]; it[0][1] = it[1][0] = a[14]; it[0][2] = it[2][0] = a[15]; it[1][2] = it[2][1] = a[16];
+          get_axes(it, ax1, ax2, ax3);
+          o[16] = 1.0; o[17] = (ax1 > 0.) ? sqrt(ax2 / ax1) : 0.0; o[18] = (ax1 > 0.) ? sqrt(ax3 / ax1) : 0.0;
+          o[19] = it[0][0]; o[20] = it[1][0]; o[21] = it[2][0]; o[22] = it[0][1]; o[23] = it[1][1]; o[24] = it[2][1];
+          o[25] = it[0][2]; o[26] = it[1][2]; o[27] = it[2][2];
+        }
+        if (sj >= 0) { const float4 pp = pos4[members[moff0[h] + sj]]; o[5] = pp.x; o[6] = pp.y; o[7] = pp.z; }
+      }
+    }
   }
 }
 
@@ -1968,6 +2059,13 @@ static void profiles_cooperative(ahfgpu_ctx *c, int64_t nhalo, const HP &P, cons
   G.tbest_e = dalloc<double>(nt); G.tbest_j = dalloc<long long>(nt);
   G.w_r = dalloc<double>(tot_g); G.y0a = dalloc<double>(tot_g); G.y0b = dalloc<double>(tot_g); G.y1a = dalloc<double>(tot_g); G.y1b = dalloc<double>(tot_g);
   G.Mpre = has_w ? dalloc<double>(tot_g) : nullptr;
+  G.sp_part = nullptr; G.sp_be = nullptr; G.sp_bj = nullptr; G.species = nullptr; G.prof_species = nullptr;
+  if (has_u) {                                                 // GAS_PARTICLES build: per-species blocks
+    G.sp_part = dalloc<double>((size_t)nt * 2 * NSPC); G.sp_be = dalloc<double>((size_t)nt * 2); G.sp_bj = dalloc<long long>((size_t)nt * 2);
+    c->h_species = dalloc<double>((size_t)nhalo * 64); c->h_prof_species = dalloc<double>((size_t)c->h_total_bins * 3);
+    CUDA_CHECK(cudaMemsetAsync(c->h_species, 0, sizeof(double) * 64 * (size_t)nhalo, c->stream));
+    G.species = c->h_species; G.prof_species = c->h_prof_species;
+  }
   double *d_tt4 = dalloc<double>((size_t)nt * PNC), *d_tc4 = dalloc<double>((size_t)nt * PNC), *d_ht4 = dalloc<double>((size_t)nhalo * PNC);
   double *d_tt1 = dalloc<double>(nt), *d_tc1 = dalloc<double>(nt), *d_ht1 = dalloc<double>(nhalo);
   double *d_tval = dalloc<double>((size_t)nt * 2); long long *d_tidx = dalloc<long long>((size_t)nt * 2);
@@ -1987,7 +2085,7 @@ static void profiles_cooperative(ahfgpu_ctx *c, int64_t nhalo, const HP &P, cons
   LAUNCH(c, k_p_vmax, nblk(nact, 64), 64, 0, d_moff0, G, d_act, nact, has_w, d_tval, d_tidx, c->h_scal);
   for (void *q : { (void *)d_act, (void *)d_tile0, (void *)d_ntile, (void *)d_tiles, (void *)G.edge, (void *)G.vesc_bin, (void *)G.Vc_bin, (void *)G.tile_blo,
                    (void *)G.tile_ns, (void *)d_slot, (void *)G.tbest_e, (void *)G.tbest_j, (void *)G.w_r, (void *)G.y0a, (void *)G.y0b, (void *)G.y1a, (void *)G.y1b,
-                   (void *)G.Mpre, (void *)d_tt4, (void *)d_tc4, (void *)d_ht4, (void *)d_tt1, (void *)d_tc1, (void *)d_ht1, (void *)d_tval, (void *)d_tidx, (void *)G.partial })
+                   (void *)G.Mpre, (void *)G.sp_part, (void *)G.sp_be, (void *)G.sp_bj, (void *)d_tt4, (void *)d_tc4, (void *)d_ht4, (void *)d_tt1, (void *)d_tc1, (void *)d_ht1, (void *)d_tval, (void *)d_tidx, (void *)G.partial })
     ahf::dfree(q);
 }
 

@@ -117,6 +117,13 @@ int  ahfgpu_construct_halos(ahfgpu_ctx *ctx, int64_t nhalo, const double *centre
 int  ahfgpu_halo_sizes(ahfgpu_ctx *ctx, int64_t *total_members, int64_t *total_bins);
 int  ahfgpu_halo_fetch(ahfgpu_ctx *ctx, double *scal, int64_t *member_offset, int64_t *members,
                        int64_t *prof_offset, double *prof);
+/* -DGAS_PARTICLES build of the reference (particles carry `u`): the per-species blocks of HaloProfiles
+ * (src/libahf/ahf_halos.c:4420-4582, :4712-4715, :5020-5181).
+ *   species       nhalo x 64 doubles: HALO.gas_only at 0, HALO.stars_only at 32 (SPECIESPROP, src/tdef.h:560-587):
+ *                 0 npart, 1 Mass, 2-4 pos_com, 5-7 pos_mbp, 8-10 vel, 11 lambda, 12 lambdaE, 13-15 AngMom, 16-18 axis,
+ *                 19-27 E1 E2 E3, 28 Ekin, 29 Epot
+ *   prof_species  per halo nbins x 3 (column-major, CSR via prof_offset): HALOPROFILE.M_gas, .M_star, .u_gas        */
+int  ahfgpu_halo_fetch_species(ahfgpu_ctx *ctx, double *species, double *prof_species);
 
 /* ---- several GPUs working on ONE box: particles are split into SFC slabs, one per process/GPU; every process
  * holds the full (small) cell structure of every level, deposits its own particles and the level accumulators are summed

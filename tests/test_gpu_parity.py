@@ -114,6 +114,16 @@ def _check_halos(g, golden, rtol=1e-9):
         cols = [c for c in range(25) if c not in (14, 15, 16, 18, 19, 20, 22, 23, 24)]
         okp = np.isclose(pr[cols], pg[cols], rtol=1e-8, atol=1e-300)
         assert okp.all(), (i, np.argwhere(~okp)[:5])
+        if golden.species(i) is not None:       # GAS_PARTICLES build: gas_only / stars_only blocks, M_gas / M_star / u_gas columns
+            sr, sg = golden.species(i), res["species"][i]
+            sl = [q + 32 * t for t in (0, 1) for q in list(range(0, 19)) + [28, 29]]
+            oks = np.isclose(sr[sl], sg[sl], rtol=rtol, atol=1e-300)
+            assert oks.all(), (i, [(sl[k], sr[sl[k]], sg[sl[k]]) for k in np.nonzero(~oks)[0]])
+            for t in (0, 1):
+                for k0 in (19, 22, 25):        # eigenvectors up to sign
+                    va, vb = sr[32 * t + k0:32 * t + k0 + 3], sg[32 * t + k0:32 * t + k0 + 3]
+                    assert np.allclose(va, vb, rtol=1e-6, atol=1e-9) or np.allclose(va, -vb, rtol=1e-6, atol=1e-9), (i, t, k0, va, vb)
+            assert np.allclose(golden.prof_species(i), g.halo_profile_species(res, i), rtol=1e-8, atol=1e-300)
 
 
 def test_halo_pass_matches_reference(A, golden):
