@@ -257,6 +257,10 @@ static void flush_halos(void)
   scal = malloc(nh * AHFGPU_NSCAL * sizeof(double)); moff = malloc((nh + 1) * sizeof(int64_t)); poff = malloc((nh + 1) * sizeof(int64_t));
   mem = malloc((nmem > 0 ? nmem : 1) * sizeof(int64_t)); prof = malloc((nbin > 0 ? nbin : 1) * AHFGPU_NPROFCOL * sizeof(double));
   if (ahfgpu_halo_fetch(G, scal, moff, mem, poff, prof)) die("ahfgpu_halo_fetch");
+#ifdef GAS_PARTICLES
+  double *spc = malloc(nh * 64 * sizeof(double)), *psp = malloc((nbin > 0 ? nbin : 1) * 3 * sizeof(double));
+  if (ahfgpu_halo_fetch_species(G, spc, psp)) die("ahfgpu_halo_fetch_species");
+#endif
   for (i = 0; i < nh; i++) {
     HALO   *h = pend[i];
     double *s = scal + (size_t)AHFGPU_NSCAL * i;
@@ -291,8 +295,29 @@ static void flush_halos(void)
         h->prof.axis3[b] = PR(21); h->prof.E3x[b] = PR(22); h->prof.E3y[b] = PR(23); h->prof.E3z[b] = PR(24);
 #undef PR
       }
+#ifdef GAS_PARTICLES
+      {                                               /* HaloProfiles' per-species blocks (ahf_halos.c:4712-4715, :5020-5181) */
+        int q;
+        for (b = 0; b < nb; b++) {
+          h->prof.M_gas[b] = psp[3 * poff[i] + 0 * nb + b]; h->prof.M_star[b] = psp[3 * poff[i] + 1 * nb + b]; h->prof.u_gas[b] = psp[3 * poff[i] + 2 * nb + b];
+        }
+        for (q = 0; q < 2; q++) {
+          SPECIESPROP *t = q ? &h->stars_only : &h->gas_only;
+          const double *o = spc + 64 * (size_t)i + 32 * q;
+          t->npart = (long unsigned)o[0]; t->Mass = o[1]; t->pos_com.x = o[2]; t->pos_com.y = o[3]; t->pos_com.z = o[4];
+          t->pos_mbp.x = o[5]; t->pos_mbp.y = o[6]; t->pos_mbp.z = o[7]; t->vel.x = o[8]; t->vel.y = o[9]; t->vel.z = o[10];
+          t->lambda = o[11]; t->lambdaE = o[12]; t->AngMom.x = o[13]; t->AngMom.y = o[14]; t->AngMom.z = o[15];
+          t->axis.x = o[16]; t->axis.y = o[17]; t->axis.z = o[18];
+          t->E1.x = o[19]; t->E1.y = o[20]; t->E1.z = o[21]; t->E2.x = o[22]; t->E2.y = o[23]; t->E2.z = o[24];
+          t->E3.x = o[25]; t->E3.y = o[26]; t->E3.z = o[27]; t->Ekin = o[28]; t->Epot = o[29];
+        }
+      }
+#endif
     }
   }
+#ifdef GAS_PARTICLES
+  free(spc); free(psp);
+#endif
   if (getenv("AHFB200_VERBOSE")) { long ok = 0; for (i = 0; i < nh; i++) ok += ((long)pend[i]->npart >= simu.AHF_MINPART); fprintf(stderr, "ahf_glue: %ld haloes with npart >= %d\n", ok, simu.AHF_MINPART); }
   free(ctr); free(rad); free(seed); free(scal); free(moff); free(poff); free(mem); free(prof);
 }

@@ -10,9 +10,9 @@ REF="${AHF_REFERENCE_SRC:-/root/reference/src}"
 OUT="$HERE/_build"
 [ -d "$REF" ] || { echo "build_dropin.sh: $REF not present - keeping prebuilt $OUT" >&2; exit 0; }
 build_one() {
-name="$1"; mainflags="$2"
+name="$1"; mainflags="$2"; defs="$3"
 mkdir -p "$OUT/obj"
-CC="gcc -fopenmp -std=c99 -O2 -DWITH_OPENMP -DAHF -w -I$REF -I$REPO/include"
+CC="gcc -fopenmp -std=c99 -O2 -DWITH_OPENMP -DAHF $defs -w -I$REF -I$REPO/include"
 pids=()
 for f in "$REF"/*.c "$REF"/lib*/*.c; do
   base="$(basename "$(dirname "$f")")_$(basename "$f" .c)"
@@ -36,4 +36,6 @@ rm -rf "$OUT/obj" "$OUT/src_main.o" "$OUT/ahf_glue.o" "$OUT/libref.a"
 # AHF-b200-kh : key/sort and halo loop on the GPU, mesh on the CPU (reference code)
 build_one AHF-b200 "-Dgen_domgrids=ahfb200_gen_domgrids -Dll=ahfb200_ll -Dzero_dens=ahfb200_zero_dens -Dassign_npart=ahfb200_assign_npart -Dgen_AMRhierarchy=ahfb200_gen_AMRhierarchy"
 build_one AHF-b200-kh ""
+# AHF-b200-mm : the multi-species build (-DMULTIMASS -DGAS_PARTICLES), everything on the GPU
+build_one AHF-b200-mm "-Dgen_domgrids=ahfb200_gen_domgrids -Dll=ahfb200_ll -Dzero_dens=ahfb200_zero_dens -Dassign_npart=ahfb200_assign_npart -Dgen_AMRhierarchy=ahfb200_gen_AMRhierarchy" "-DMULTIMASS -DGAS_PARTICLES"
 ls -la "$OUT"

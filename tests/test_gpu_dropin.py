@@ -62,3 +62,44 @@ def test_catalogues_equal_reference(n1d, seed, ncl, variant):
             assert np.allclose(np.array(a)[cols], np.array(b)[cols], rtol=2e-5, atol=1e-4)
     finally:
         shutil.rmtree(work, ignore_errors=True)
+
+
+@pytest.mark.parametrize("n1d,seed,ncl", [(32, 11, 6), (64, 5, 10)])
+def test_species_catalogues_equal_reference(n1d, seed, ncl):
+    """the multi-species build (-DMULTIMASS -DGAS_PARTICLES: gas + dark matter + stars): AHF-b200-mm against the reference's own
+    multi-species binary -- the _halos file then carries the gas_only / stars_only columns, _profiles the M_gas / M_star / u_gas ones"""
+    DROPIN = os.path.join(DROPIN_DIR, "AHF-b200-mm")
+    from ahf_b200 import synth
+    from oracle import oracle as O
+    if not (os.path.exists(DROPIN) and os.path.exists(O.REF_BIN_MM)):
+        pytest.skip("drop-in / reference binaries not built (need /root/reference at build time)")
+    sb = synth.make_species_box(n1d, seed=seed, n_clumps=ncl)
+    work = tempfile.mkdtemp(prefix="ahf_dropin_mm_")
+    try:
+        out = {}
+        for tag, exe in (("ref", O.REF_BIN_MM), ("gpu", DROPIN)):
+            d = os.path.join(work, tag)
+            inp = synth.write_reference_case_species(sb, d)
+            env = dict(os.environ); env.pop("AHF_DUMP_DIR", None)
+            pr = subprocess.run([exe, inp], cwd=d, env=env, capture_output=True, text=True)
+            assert pr.returncode == 0, pr.stderr[-3000:]
+            out[tag] = d
+        pre = "ref.z0.000.AHF_"
+        hr, hg = _num_table(os.path.join(out["ref"], pre + "halos")), _num_table(os.path.join(out["gpu"], pre + "halos"))
+        assert len(hr) == len(hg) and len(hr) >= 3 and len(hr[0]) > 43          # species columns present
+        assert any(a[43] > 0 for a in hr)                                        # n_gas of some halo
+        eig = set(range(26, 35)) | set(range(52, 61)) | set(range(72, 81))      # eigenvector columns (total, gas, stars): sign convention free
+        for a, b in zip(hr, hg):
+            assert a[:3] == b[:3] and a[4] == b[4]
+            cols = [i for i in range(len(a)) if i not in eig]
+            assert np.allclose(np.array(a)[cols], np.array(b)[cols], rtol=2e-5, atol=1e-4), [(i, a[i], b[i]) for i in cols if not np.isclose(a[i], b[i], rtol=2e-5, atol=1e-4)]
+        assert open(os.path.join(out["ref"], pre + "particles")).read() == open(os.path.join(out["gpu"], pre + "particles")).read()
+        assert open(os.path.join(out["ref"], pre + "substructure")).read() == open(os.path.join(out["gpu"], pre + "substructure")).read()
+        pr_, pg_ = _num_table(os.path.join(out["ref"], pre + "profiles")), _num_table(os.path.join(out["gpu"], pre + "profiles"))
+        assert len(pr_) == len(pg_)
+        for a, b in zip(pr_, pg_):
+            assert a[1] == b[1]
+            cols = [i for i in range(len(a)) if i not in range(16, 25)]
+            assert np.allclose(np.array(a)[cols], np.array(b)[cols], rtol=2e-5, atol=1e-4), [(i, a[i], b[i]) for i in cols if not np.isclose(a[i], b[i], rtol=2e-5, atol=1e-4)]
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
