@@ -91,6 +91,7 @@ def lib():
         L.ahfgpu_sfc_sort_particles.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32] + [C.c_int32] * 6
         L.ahfgpu_sfc_sort_soa.argtypes = [C.c_void_p] * 5 + [C.c_uint64, C.c_void_p, C.c_void_p]
         L.ahfgpu_upload_soa.argtypes = [C.c_void_p] * 5 + [C.c_uint64]
+        L.ahfgpu_sfc_sort_soa_async.argtypes = [C.c_void_p] * 5 + [C.c_uint64]
         L.ahfgpu_sfc_sort_resident.argtypes = [C.c_void_p]
         L.ahfgpu_event_record.argtypes = [C.c_void_p, C.c_int32]
         L.ahfgpu_event_elapsed_ms.restype = C.c_double
@@ -207,6 +208,14 @@ class AhfGpu:
         self._chk(self._L.ahfgpu_sfc_sort_soa(self._h, C.c_void_p(pos_ptr), C.c_void_p(mom_ptr), None, None, n,
                                               C.c_void_p(keys_ptr) if keys_ptr else None,
                                               C.c_void_p(order_ptr) if order_ptr else None))
+        self.n = n
+
+    def sfc_sort_async_ptr(self, pos_ptr: int, mom_ptr: int, n: int, weight_ptr: int = 0, u_ptr: int = 0):
+        """Overlapped variant (ahfgpu_sfc_sort_soa_async): the momenta are still in flight on return; the host buffers behind
+        mom_ptr / u_ptr must stay untouched until construct_halos() or synchronize() has returned."""
+        self._chk(self._L.ahfgpu_sfc_sort_soa_async(self._h, C.c_void_p(pos_ptr), C.c_void_p(mom_ptr),
+                                                    C.c_void_p(weight_ptr) if weight_ptr else None,
+                                                    C.c_void_p(u_ptr) if u_ptr else None, n))
         self.n = n
 
     def upload(self, pos, mom, weight=None, u=None):

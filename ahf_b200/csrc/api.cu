@@ -93,8 +93,16 @@ void ahfgpu_ctx::stage_resolve()
   }
   stages_resolved = true;
 }
+void ahfgpu_ctx::wait_mom(bool host)
+{
+  if (!mom_pending) return;
+  if (host) cudaEventSynchronize(ev_mom);
+  cudaStreamWaitEvent(stream, ev_mom, 0);
+  mom_pending = false;
+}
 void ahfgpu_ctx::free_particles()
 {
+  wait_mom(false);
   if (adopted) { pos4 = mom4 = nullptr; keys = nullptr; adopted = false; }
   ahf::dfree(pos4); ahf::dfree(mom4); ahf::dfree(keys); ahf::dfree(order);
   pos4 = mom4 = nullptr; keys = nullptr; order = nullptr; n = 0;
@@ -175,6 +183,8 @@ int ahfgpu_finalize(ahfgpu_ctx *c)
   API_BEGIN
   if (!c) return 0;
   cudaSetDevice(c->dev); ahf::g_pool_stream = c->stream;
+  c->wait_mom(true);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   cudaStreamSynchronize(c->stream);
   c->stage_reset(); c->free_halos(); c->free_levels(); c->free_particles();
   ahf::dfree(c->in_pos); ahf::dfree(c->in_mom); ahf::dfree(c->in_w); ahf::dfree(c->in_u);
@@ -188,6 +198,11 @@ int ahfgpu_finalize(ahfgpu_ctx *c)
   }
   cudaStreamSynchronize(c->stream);
   cudaStreamDestroy(c->stream);
+  if (c->copy_stream) {
+    cudaStreamDestroy(c->copy_stream);
+    for (auto &e : c->ev_copy) if (e) cudaEventDestroy(e);
+    cudaEventDestroy(c->ev_main); cudaEventDestroy(c->ev_mom);
+  }
   delete c;
   API_END
 }
@@ -211,6 +226,16 @@ int ahfgpu_sfc_sort_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, con
   CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
   c->stage_reset();
   sfc_sort_soa(c, pos3, mom3, weight, u, n, keys_out, order_out);
+  API_END
+}
+
+int ahfgpu_sfc_sort_soa_async(ahfgpu_ctx *c, const float *pos3, const float *mom3, const float *weight, const float *u, uint64_t n)
+{
+  API_BEGIN
+  if (!c || ((!pos3 || !mom3) && n)) AHF_FAIL("null argument");
+  CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
+  c->stage_reset();
+  sfc_sort_soa_async(c, pos3, mom3, weight, u, n);
   API_END
 }
 
@@ -275,7 +300,7 @@ void *ahfgpu_device_ptr(ahfgpu_ctx *c, const char *name)
 {
   if (!c || !name) return nullptr;
   if (!strcmp(name, "pos4")) return c->pos4;
-  if (!strcmp(name, "mom4")) return c->mom4;
+  if (!strcmp(name, "mom4")) { c->wait_mom(true); return c->mom4; }
   if (!strcmp(name, "keys")) return c->keys;
   return nullptr;
 }
@@ -305,6 +330,7 @@ int ahfgpu_synchronize(ahfgpu_ctx *c)
   API_BEGIN
   if (!c) AHF_FAIL("null ctx");
   CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
+  c->wait_mom(true);
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
   API_END
 }
@@ -360,6 +386,7 @@ int ahfgpu_construct_halos(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, 
   if (nhalo && (!centre3 || !gather_rad)) AHF_FAIL("null argument");
   CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
   c->stage_reset();
+  c->wait_mom(false);                                  // momenta of ahfgpu_sfc_sort_soa_async: device-side wait, the host does not block
   halos_construct(c, nhalo, centre3, gather_rad, seed);
   API_END
 }

@@ -118,6 +118,12 @@ struct ahfgpu_ctx {
   float    *in_pos = nullptr, *in_mom = nullptr, *in_w = nullptr, *in_u = nullptr;
   uint64_t  in_n = 0;
   cudaEvent_t ev[16] = {};
+  // second stream of ahfgpu_sfc_sort_soa_async: host->device copies and the momentum gather run here, so the momenta travel
+  // while the main stream sorts and builds the hierarchy.  mom_pending: mom4 is complete only after ev_mom.
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t  ev_copy[8] = {}, ev_main = nullptr, ev_mom = nullptr;
+  bool         mom_pending = false;
+  void wait_mom(bool host);     // order the main stream (host: the calling thread as well) after the momentum gather
   // hierarchy
   std::vector<ahf::Level> levels;
   int8_t   *owner_level = nullptr;   // [n]
@@ -173,6 +179,7 @@ void sfc_sort_aos(ahfgpu_ctx *c, void *part, uint64_t n, uint32_t stride, int of
                   int off_id, int off_w, int off_u);
 void sfc_upload_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, const float *w, const float *u, uint64_t n);
 void sfc_sort_resident(ahfgpu_ctx *c, uint64_t *keys_out, uint32_t *order_out);
+void sfc_sort_soa_async(ahfgpu_ctx *c, const float *pos3, const float *mom3, const float *w, const float *u, uint64_t n);
 void sfc_sort_device4(ahfgpu_ctx *c, const void *pos4_dev, const void *mom4_dev, uint64_t n, bool has_w, bool has_u);
 void sfc_keys_only(ahfgpu_ctx *c, const float *pos3, uint64_t n, uint32_t bits, uint64_t *keys_out);
 void radix_sort_pairs(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, uint64_t n,

@@ -256,6 +256,7 @@ void sfc_keys_only(ahfgpu_ctx *c, const float *pos3, uint64_t n, uint32_t bits, 
 void sfc_upload_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, const float *w, const float *u, uint64_t n)
 {
   if (n >= (1ull << 32)) AHF_FAIL("more than 2^32-1 particles per device are not supported");
+  c->wait_mom(false);
   ahf::dfree(c->in_pos); ahf::dfree(c->in_mom); ahf::dfree(c->in_w); ahf::dfree(c->in_u);
   c->in_pos = c->in_mom = c->in_w = c->in_u = nullptr; c->in_n = n;
   c->in_pos = static_cast<decltype(c->in_pos)>(ahf::cache_alloc((n ? n : 1) * 3 * sizeof(float)));
@@ -311,6 +312,101 @@ void sfc_sort_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, const flo
 {
   sfc_upload_soa(c, pos3, mom3, w, u, n);
   sfc_sort_resident(c, keys_out, order_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Overlapped host->device path (ahfgpu_sfc_sort_soa_async).  All copies go through ctx->copy_stream in the order
+// pos (four chunks), weight, mom, u; the main stream computes the keys of a chunk as soon as it has landed, sorts, and
+// gathers pos4 -- everything ahfgpu_build_amr needs -- while the momenta are still on the bus.  The momentum gather runs on
+// the copy stream behind its copy and signals ev_mom, which the halo pass waits for on the device.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_keys_soa_chunk(const float *__restrict__ pos3, uint64_t i0, uint64_t i1, uint64_t *__restrict__ keys, uint32_t *__restrict__ idx)
+{
+  uint64_t i = i0 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= i1) return;
+  keys[i] = hilbert_key_pos(pos3[3 * i], pos3[3 * i + 1], pos3[3 * i + 2], 21);
+  idx[i]  = (uint32_t)i;
+}
+__global__ void k_gather_pos(const float *__restrict__ pos3, const float *__restrict__ w, const uint32_t *__restrict__ order, uint64_t n,
+                             float4 *__restrict__ pos4)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t o = order[i];
+  pos4[i] = make_float4(pos3[3 * o], pos3[3 * o + 1], pos3[3 * o + 2], w ? w[o] : 1.0f);
+}
+__global__ void k_gather_mom(const float *__restrict__ mom3, const float *__restrict__ u, const uint32_t *__restrict__ order, uint64_t n,
+                             float4 *__restrict__ mom4)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t o = order[i];
+  mom4[i] = make_float4(mom3[3 * o], mom3[3 * o + 1], mom3[3 * o + 2], u ? u[o] : -1.0f);
+}
+
+void sfc_sort_soa_async(ahfgpu_ctx *c, const float *pos3, const float *mom3, const float *w, const float *u, uint64_t n)
+{
+  if (n >= (1ull << 32)) AHF_FAIL("more than 2^32-1 particles per device are not supported");
+  c->wait_mom(false);
+  if (!c->copy_stream) {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (auto &e : c->ev_copy) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_mom, cudaEventDisableTiming));
+  }
+  ahf::dfree(c->in_pos); ahf::dfree(c->in_mom); ahf::dfree(c->in_w); ahf::dfree(c->in_u);
+  c->in_pos = c->in_mom = c->in_w = c->in_u = nullptr; c->in_n = n;
+  c->in_pos = static_cast<decltype(c->in_pos)>(ahf::cache_alloc((n ? n : 1) * 3 * sizeof(float)));
+  c->in_mom = static_cast<decltype(c->in_mom)>(ahf::cache_alloc((n ? n : 1) * 3 * sizeof(float)));
+  if (w) c->in_w = static_cast<decltype(c->in_w)>(ahf::cache_alloc((n ? n : 1) * sizeof(float)));
+  if (u) c->in_u = static_cast<decltype(c->in_u)>(ahf::cache_alloc((n ? n : 1) * sizeof(float)));
+  alloc_particles(c, n);
+  c->has_weight = (w != nullptr); c->has_u = (u != nullptr);
+  c->keys = static_cast<decltype(c->keys)>(ahf::cache_alloc((n ? n : 1) * sizeof(uint64_t)));
+  c->order = static_cast<decltype(c->order)>(ahf::cache_alloc((n ? n : 1) * sizeof(uint32_t)));
+  DevBuf<uint64_t> k0, k1;
+  DevBuf<uint32_t> v0, v1;
+  k0.reserve(n); k1.reserve(n); v0.reserve(n); v1.reserve(n);
+  // the blocks above are ordered on the main stream (they may be recycled): the copy stream starts behind this point
+  CUDA_CHECK(cudaEventRecord(c->ev_main, c->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
+  constexpr int NCH = 4;
+  const uint64_t per = ((n + NCH - 1) / NCH + 255) & ~255ull;
+  {
+    Stage st(c, "keys", (int64_t)n);
+    for (int q = 0; q < NCH; q++) {
+      const uint64_t i0 = std::min(n, per * q), i1 = std::min(n, per * (q + 1));
+      if (i1 > i0) CUDA_CHECK(cudaMemcpyAsync(c->in_pos + 3 * i0, pos3 + 3 * i0, 3 * (i1 - i0) * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+      CUDA_CHECK(cudaEventRecord(c->ev_copy[q], c->copy_stream));
+      CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_copy[q], 0));
+      if (i1 > i0) LAUNCH(c, k_keys_soa_chunk, (unsigned)((i1 - i0 + 255) / 256), 256, 0, c->in_pos, i0, i1, k0.p, v0.p);
+    }
+  }
+  if (w) CUDA_CHECK(cudaMemcpyAsync(c->in_w, w, n * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+  CUDA_CHECK(cudaEventRecord(c->ev_copy[NCH], c->copy_stream));
+  CUDA_CHECK(cudaMemcpyAsync(c->in_mom, mom3, 3 * n * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+  if (u) CUDA_CHECK(cudaMemcpyAsync(c->in_u, u, n * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+  uint64_t *ks; uint32_t *vs;
+  {
+    Stage st(c, "sort", (int64_t)n);
+    radix_sort_pairs(c, k0.p, v0.p, k1.p, v1.p, n, 63, &ks, &vs);
+  }
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  {
+    Stage st(c, "gather", (int64_t)n);
+    CUDA_CHECK(cudaMemcpyAsync(c->keys, ks, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(c->order, vs, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_copy[NCH], 0));                 // weights
+    if (n) LAUNCH(c, k_gather_pos, nb, 256, 0, c->in_pos, c->in_w, c->order, n, c->pos4);
+  }
+  // momentum gather on the copy stream, behind its copy and behind the sorted order
+  CUDA_CHECK(cudaEventRecord(c->ev_main, c->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
+  if (n) { k_gather_mom<<<nb, 256, 0, c->copy_stream>>>(c->in_mom, c->in_u, c->order, n, c->mom4); c->n_launches++; CUDA_CHECK(cudaGetLastError()); }
+  CUDA_CHECK(cudaEventRecord(c->ev_mom, c->copy_stream));
+  c->mom_pending = true;
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  k0.release(); k1.release(); v0.release(); v1.release();
 }
 
 __global__ void k_keys_pos4(const float4 *__restrict__ pos4, uint64_t n, uint64_t *__restrict__ keys, uint32_t *__restrict__ idx)

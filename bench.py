@@ -308,7 +308,7 @@ def main():
         return st
 
     def step_e2e():
-        g.sfc_sort_ptr(hpos.data_ptr(), hmom.data_ptr(), n)
+        g.sfc_sort_async_ptr(hpos.data_ptr(), hmom.data_ptr(), n)      # momenta travel behind the sort and the hierarchy build
         g.build_amr()
         g.construct_halos(centres, rad, seednp, fetch=False)
         return g.fetch_halos(len(rad), scal_only=True)["scal"]

@@ -67,6 +67,13 @@ int  ahfgpu_sfc_sort_particles(ahfgpu_ctx *ctx, void *part, uint64_t n, uint32_t
                                int32_t off_mom, int32_t off_key, int32_t off_id, int32_t off_weight, int32_t off_u);
 int  ahfgpu_sfc_sort_soa(ahfgpu_ctx *ctx, const float *pos3, const float *mom3, const float *weight, const float *u,
                          uint64_t n, uint64_t *keys_out, uint32_t *order_out);
+/* ahfgpu_sfc_sort_soa_async: same result as ahfgpu_sfc_sort_soa, but the host->device copies run on a second stream and
+ * overlap the work: keys are computed chunk by chunk as the positions land, and the momenta (and u) travel while the sort
+ * and ahfgpu_build_amr run -- only ahfgpu_construct_halos needs them and waits for them on the device.  The call returns
+ * when the sorted positions and keys are resident.  CONTRACT: mom3 and u must stay valid and unchanged until the next
+ * ahfgpu_construct_halos, ahfgpu_synchronize or ahfgpu_finalize on this context has returned (pos3 and weight are free on
+ * return); pinned host memory is needed for the copies to overlap at all.                                             */
+int  ahfgpu_sfc_sort_soa_async(ahfgpu_ctx *ctx, const float *pos3, const float *mom3, const float *weight, const float *u, uint64_t n);
 /* Same as ahfgpu_sfc_sort_soa but split in two so that the sort can be timed with its input already in HBM:
  * ahfgpu_upload_soa copies the unsorted arrays to the device, ahfgpu_sfc_sort_resident runs keys + sort + gather on
  * them (repeatable: the unsorted copy is kept).                                                                */

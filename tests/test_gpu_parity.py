@@ -148,3 +148,21 @@ def test_end_to_end_from_file_order(A, golden):
             _check_halos(g, golden)
         else:   # duplicate keys: tie order may differ from libc qsort, offsets are not comparable one to one
             assert g.build_amr() == golden.nlev
+
+
+def test_overlapped_upload_gives_the_same_results(A, golden):
+    """ahfgpu_sfc_sort_soa_async (momenta copied behind the sort and the hierarchy build, pinned host buffers) against the
+    golden vectors, twice on one context so that the second call recycles buffers the copy stream used."""
+    import torch
+    hp = torch.from_numpy(np.ascontiguousarray(golden.pos, np.float32)).pin_memory()
+    hm = torch.from_numpy(np.ascontiguousarray(golden.mom, np.float32)).pin_memory()
+    hw = hu = None
+    if golden.weight is not None:
+        hw = torch.from_numpy(np.ascontiguousarray(golden.weight, np.float32)).pin_memory()
+        hu = torch.from_numpy(np.ascontiguousarray(golden.u, np.float32)).pin_memory()
+    with _ctx(A, golden) as g:
+        for _ in range(2):
+            g.sfc_sort_async_ptr(hp.data_ptr(), hm.data_ptr(), hp.shape[0], hw.data_ptr() if hw is not None else 0,
+                                 hu.data_ptr() if hu is not None else 0)
+            _check_levels(g, golden)
+            _check_halos(g, golden)
