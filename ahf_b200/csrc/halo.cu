@@ -2191,7 +2191,6 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
       LAUNCH(c, k_apply_perm, nblk(tot_e, 256), 256, 0, vs2, hid, d_candoff, d_eoff, (uint64_t)tot_e, d_idx, sorted);
       // scatter halo segments: eoff-layout -> moff0-layout
       LAUNCH(c, k_scatter_sorted, (unsigned)nhalo, 256, 0, d_eoff, d_moff0, sorted, d_members);
-      CUDA_CHECK(cudaStreamSynchronize(c->stream));
       ahf::dfree(k0); ahf::dfree(k1); ahf::dfree(v0); ahf::dfree(v1); ahf::dfree(hid); ahf::dfree(v3); ahf::dfree(sorted);
     }
     LAUNCH(c, k_copy_unsorted, (unsigned)nhalo, 64, 0, d_candoff, d_ng, d_moff0, P.min_part, d_idx, d_members);

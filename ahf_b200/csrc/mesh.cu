@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) k_deposit_generic(const float4 *__restric
         if (v.dense) {
           int x = (cx + a - 1) & (int)(v.L - 1), y = (cy + j - 1) & (int)(v.L - 1), z = (cz + k - 1) & (int)(v.L - 1);
           tgt = (int)lv_key(v, x, y, z);
-        } else tgt = nbr[(size_t)c * 27 + (k * 9 + j * 3 + a)];
+        } else tgt = nbr[(size_t)(k * 9 + j * 3 + a) * (size_t)v.ncell + (size_t)c];
         if (tgt >= 0) atomicAdd(&acc[tgt], t);
       }
 }
@@ -286,11 +286,11 @@ k_deposit_tiles(const float4 *__restrict__ pos4, const int32_t *__restrict__ tst
     const float4 q = valid ? sp[(sub & 1) * DT_SUB + threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
     // ll(): cell = (unsigned long)(L * pos), out-of-range -> 0 (lltools.c:59-66); exact in float for power-of-two L
     const float fx = q.x * fL, fy = q.y * fL, fz = q.z * fL;
-    int cx, cy, cz, pc = 0;
-    if (SPARSE) {          // the node the particle is linked to (relink's inclusive faces: not always floor(L*x))
-      pc = valid ? pcell[s0 + i] : 0;
-      lv_coords(lvw, pc, cx, cy, cz);
-    } else { cx = (int)fx; cy = (int)fy; cz = (int)fz; }
+    int cx = (int)fx, cy = (int)fy, cz = (int)fz;
+    if (SPARSE) {          // the node the particle is linked to (relink's inclusive faces: floor(L*x) - face bit, carried in .w)
+      const int fb = __float_as_int(q.w);
+      cx -= fb & 1; cy -= (fb >> 1) & 1; cz -= (fb >> 2) & 1;
+    }
     float sx = fx - ((float)cx + 0.5f), sy = fy - ((float)cy + 0.5f), sz = fz - ((float)cz + 0.5f);
     if (!SPARSE) {
       if (cx > M) { cx = 0; sx = fx - 0.5f - fL; }
@@ -357,7 +357,7 @@ k_deposit_tiles(const float4 *__restrict__ pos4, const int32_t *__restrict__ tst
 #pragma unroll
           for (int a = 0; a < 3; a++) {
             long long tgt;
-            if (SPARSE) tgt = nbr[(size_t)pc * 27 + (k * 9 + j * 3 + a)];
+            if (SPARSE) tgt = nbr[(size_t)(k * 9 + j * 3 + a) * (size_t)lvw.ncell + (size_t)pcell[s0 + i]];
             else { const int x = (cx + a - 1) & M, y = (cy + j - 1) & M, z = (cz + k - 1) & M; tgt = (long long)((((size_t)z << logL | y) << logL) | x); }
             if (tgt >= 0) atomicAdd(&acc[tgt], __float2ull_rn(wz[k] * wy[j] * fxs * wx[a]));
           }
@@ -385,12 +385,32 @@ k_deposit_tiles(const float4 *__restrict__ pos4, const int32_t *__restrict__ tst
     }
     __syncthreads();
     const int nnz = s_nnz;
-    for (int e = threadIdx.x; e < nnz; e += DT_THREADS) {
-      const int i = list[e];
-      const int hz = i / (DT_H * DT_H), r = i - hz * (DT_H * DT_H), hy = r / DT_H, hx = r - hy * DT_H;
-      const unsigned long long val = ((unsigned long long)tcar[i] << 32) | tile[i];      // already in the level's 2^-S units
-      const int tgt = lv_lookup(lvw, (x0 + hx - 1) & M, (y0 + hy - 1) & M, (z0 + hz - 1) & M);   // particles sit on interior nodes: every touched cell exists
-      if (tgt >= 0) atomicAdd(&acc[tgt], val);
+    // four independent hash probes in flight per thread (the walk is latency bound: key slot -> value -> reduction)
+    for (int e0 = threadIdx.x; e0 < nnz; e0 += 4 * DT_THREADS) {
+      uint64_t kq[4], sq[4], hq[4];
+      int      iq[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int e = e0 + q * DT_THREADS;
+        iq[q] = e < nnz ? (int)list[e] : -1;
+        const int i = iq[q] < 0 ? 0 : iq[q];
+        const int hz = i / (DT_H * DT_H), r = i - hz * (DT_H * DT_H), hy = r / DT_H, hx = r - hy * DT_H;
+        kq[q] = lv_key(lvw, (x0 + hx - 1) & M, (y0 + hy - 1) & M, (z0 + hz - 1) & M);
+        sq[q] = mix64(kq[q] >> 3) & lvw.hmask;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) hq[q] = iq[q] >= 0 ? lvw.hkey[sq[q]] : ~0ull;
+      int tg[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const uint64_t kb = kq[q] >> 3;
+        uint64_t s = sq[q], hk = hq[q];
+        while (hk != kb && hk != ~0ull) { s = (s + 1) & lvw.hmask; hk = lvw.hkey[s]; }
+        tg[q] = (iq[q] >= 0 && hk == kb) ? lvw.hval[s * 8 + (kq[q] & 7)] : -1;    // particles sit on interior nodes: every touched cell exists
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if (tg[q] >= 0) atomicAdd(&acc[tg[q]], ((unsigned long long)tcar[iq[q]] << 32) | tile[iq[q]]);      // already in the level's 2^-S units
     }
     return;
   }
@@ -668,13 +688,16 @@ __global__ void k_test_node(LV v, const float *__restrict__ dens, const uint8_t 
           hit |= ((double)dens[t] >= thr);
         }
   } else if (interior[c]) {
-    const int32_t *nb = nbr + (size_t)c * 27;
+    // nbr is stored term-major ([27][ncell]): the loads of a warp are coalesced
+    int t18[18];
 #pragma unroll
     for (int k = 0; k < 3; k++)
 #pragma unroll
       for (int j = 0; j < 3; j++)
 #pragma unroll
-        for (int a = 1; a < 3; a++) hit |= ((double)dens[nb[k * 9 + j * 3 + a]] >= thr);
+        for (int a = 1; a < 3; a++) t18[k * 6 + j * 2 + a - 1] = nbr[(size_t)(k * 9 + j * 3 + a) * (size_t)v.ncell + (size_t)c];
+#pragma unroll
+    for (int q = 0; q < 18; q++) hit |= ((double)dens[t18[q]] >= thr);
   }
   tn[c] = hit ? 1 : 0;
 }
@@ -931,10 +954,11 @@ __global__ void k_neighbours(LV v, int32_t *__restrict__ nbr, uint8_t *__restric
 #pragma unroll
     for (int j = 0; j < 3; j++) {
       int yy = y + j - 1; if (yy < 0) yy = L - 1; else if (yy >= L) yy = 0;
-      int32_t *o = nbr + (size_t)c * 27 + k * 9 + j * 3;
+      int32_t *o = nbr + (size_t)(k * 9 + j * 3) * (size_t)v.ncell + (size_t)c;      // term-major table: o[t * ncell]
+      const size_t os = (size_t)v.ncell;
       const int rm = (pm >= 0) ? rowc[k * 3 + j] : -1;
-      if (rm < 0) { o[0] = o[1] = o[2] = -1; all = false; continue; }
-      o[1] = rm;
+      if (rm < 0) { o[0] = o[os] = o[2 * os] = -1; all = false; continue; }
+      o[os] = rm;
       const uint64_t kk = v.ckey[rm];
       // x-1: same run, else the periodic image when on the face (get_nnodes.c:490-508)
       int xm = -1;
@@ -944,7 +968,7 @@ __global__ void k_neighbours(LV v, int32_t *__restrict__ nbr, uint8_t *__restric
       int xp = -1;
       if (!v.xbreak[rm] && rm + 1 < v.ncell && v.ckey[rm + 1] == kk + 1 && x < L - 1) xp = rm + 1;
       else if (x == L - 1) xp = lv_lookup(v, 0, yy, zz);
-      o[0] = xm; o[2] = xp;
+      o[0] = xm; o[2 * os] = xp;
       if (xm < 0 || xp < 0) all = false;
     }
   }
@@ -956,11 +980,12 @@ __global__ void k_neighbours(LV v, int32_t *__restrict__ nbr, uint8_t *__restric
 // ------------------------------------------------------------------------------------------------
 __global__ void k_relink(const float4 *__restrict__ pos4, const uint32_t *__restrict__ plist, const int32_t *__restrict__ pcell, uint64_t np,
                          LV coa, const uint8_t *__restrict__ cmark, LV fin, const uint8_t *__restrict__ finterior,
-                         int32_t *__restrict__ newcell, uint8_t *__restrict__ moved)
+                         int32_t *__restrict__ newcell, uint8_t *__restrict__ moved, uint8_t *__restrict__ dlt)
 {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= np) return;
   int c = pcell[i], res = -1;
+  uint8_t dl = 0;                            // bit d: the child's coordinate d is floor(L*x_d) - 1 (particle exactly on the upper face)
   if (cmark[c]) {
     uint64_t p = plist ? plist[i] : i;
     float4   q = pos4[p];
@@ -982,13 +1007,17 @@ __global__ void k_relink(const float4 *__restrict__ pos4, const uint32_t *__rest
         for (int e = 0; e < 2 && res < 0; e++) {
           if (!ok[0][e]) continue;
           int f = lv_lookup(fin, b[0] + e, b[1] + j, b[2] + k);
-          if (f >= 0 && finterior[f]) res = f;
+          if (f >= 0 && finterior[f]) {
+            res = f;
+            dl = (uint8_t)(((int)t[0] != b[0] + e ? 1 : 0) | ((int)t[1] != b[1] + j ? 2 : 0) | ((int)t[2] != b[2] + k ? 4 : 0));
+          }
         }
       }
     }
   }
   newcell[i] = res;
   moved[i]   = res >= 0 ? 1 : 0;
+  dlt[i]     = dl;
 }
 
 __global__ void k_dbg_compare(const int32_t *__restrict__ a, const int32_t *__restrict__ b, uint64_t n, unsigned long long *__restrict__ out)
@@ -1000,13 +1029,17 @@ __global__ void k_dbg_compare(const int32_t *__restrict__ a, const int32_t *__re
 }
 __global__ void k_compact_moved(const uint32_t *__restrict__ plist, const int32_t *__restrict__ newcell, const uint8_t *__restrict__ moved,
                                 const int *__restrict__ S, uint64_t np, uint32_t *__restrict__ plist_out, int32_t *__restrict__ pcell_out,
-                                int8_t *__restrict__ owner, int8_t newlevel, const float4 *__restrict__ pos4, float4 *__restrict__ lpos_out)
+                                int8_t *__restrict__ owner, int8_t newlevel, const float4 *__restrict__ pos4, float4 *__restrict__ lpos_out,
+                                const uint8_t *__restrict__ dlt)
 {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= np || !moved[i]) return;
   uint32_t p = plist ? plist[i] : (uint32_t)i;
   plist_out[S[i]] = p; pcell_out[S[i]] = newcell[i];
-  lpos_out[S[i]] = pos4[p];                 // level-local contiguous copy: TMA-stageable, no index indirection in the deposit
+  // level-local contiguous copy: TMA-stageable, no index indirection in the deposit.  The number-density deposit has no use for
+  // the weight, so .w carries relink's face bits (cell coordinate = floor(L*x) - bit) and the deposit needs no cell-key gather.
+  float4 q = pos4[p]; q.w = __int_as_float((int)dlt[i]);
+  lpos_out[S[i]] = q;
   owner[p] = newlevel;
 }
 
@@ -1169,8 +1202,7 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
     if (c->allreduce(c->allreduce_user, acc.p, (int64_t)nc) != 0) AHF_FAIL("all-reduce callback failed");
   }
   LAUNCH(c, k_finish_dens, nblk(nc, 256), 256, 0, acc.p, lv.dens, nc, lv.masstopartdens / fxscale);
-  CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  acc.release();
+  acc.release();                                    // stream-ordered block cache: no host sync needed
 }
 
 static void alloc_cell_arrays(Level &lv)
@@ -1279,38 +1311,37 @@ void amr_build(ahfgpu_ctx *c)
       Stage st(c, "relink", coa.npart_dep);
       Stage stl(c, lvl_name("relink", lev).c_str(), coa.npart_dep);
       const uint64_t np = (uint64_t)coa.npart_dep;
-      DevBuf<int32_t> newcell; DevBuf<uint8_t> moved; DevBuf<int> MS;
-      newcell.reserve(np); moved.reserve(np); MS.reserve(np);
+      DevBuf<int32_t> newcell; DevBuf<uint8_t> moved, dlt; DevBuf<int> MS;
+      newcell.reserve(np); moved.reserve(np); dlt.reserve(np); MS.reserve(np);
       int nmoved = 0;
       if (np) {
-        LAUNCH(c, k_relink, nblk(np, 256), 256, 0, c->pos4, coa.plist, coa.pcell, np, view(coa), coa.mark, view(fin), fin.interior, newcell.p, moved.p);
+        LAUNCH(c, k_relink, nblk(np, 256), 256, 0, c->pos4, coa.plist, coa.pcell, np, view(coa), coa.mark, view(fin), fin.interior, newcell.p, moved.p, dlt.p);
         nmoved = exclusive_scan<uint8_t>(c, moved.p, MS.p, np);
         if (getenv("AHFGPU_DEBUG_RELINK")) {
-          DevBuf<int32_t> nc2; DevBuf<uint8_t> mv2; DevBuf<unsigned long long> out;
-          nc2.reserve(np); mv2.reserve(np); out.reserve(3);
+          DevBuf<int32_t> nc2; DevBuf<uint8_t> mv2, dl2; DevBuf<unsigned long long> out;
+          nc2.reserve(np); mv2.reserve(np); dl2.reserve(np); out.reserve(3);
           unsigned long long h0[3] = { 0, 0, ~0ull }, h[3];
           CUDA_CHECK(cudaMemcpyAsync(out.p, h0, sizeof(h0), cudaMemcpyHostToDevice, c->stream));
-          LAUNCH(c, k_relink, nblk(np, 256), 256, 0, c->pos4, coa.plist, coa.pcell, np, view(coa), coa.mark, view(fin), fin.interior, nc2.p, mv2.p);
+          LAUNCH(c, k_relink, nblk(np, 256), 256, 0, c->pos4, coa.plist, coa.pcell, np, view(coa), coa.mark, view(fin), fin.interior, nc2.p, mv2.p, dl2.p);
           LAUNCH(c, k_dbg_compare, nblk(np, 256), 256, 0, newcell.p, nc2.p, np, out.p);
           CUDA_CHECK(cudaMemcpyAsync(h, out.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
           CUDA_CHECK(cudaStreamSynchronize(c->stream));
           if (h[0] || (long long)h[1] != nmoved)
             fprintf(stderr, "[relink dbg] level %d -> %d: %llu of %llu newcell differ between two runs (first at %llu); count(res>=0) %llu, scan total %d\n",
                     lev, lev + 1, h[0], (unsigned long long)np, h[2], h[1], nmoved);
-          nc2.release(); mv2.release(); out.release();
+          nc2.release(); mv2.release(); dl2.release(); out.release();
         }
       }
       if (fin.ncell < MIN_NNODES) {                                   // generate_grids.c:231 / density.c:420: level rejected
         fin.free_all();
         c->levels.pop_back();
-        newcell.release(); moved.release(); MS.release();
+        newcell.release(); moved.release(); dlt.release(); MS.release();
         break;
       }
       fin.npart_dep = nmoved;
       fin.plist = dalloc<uint32_t>(nmoved); fin.pcell = dalloc<int32_t>(nmoved); fin.lpos = dalloc<float4>(nmoved);
-      if (np) LAUNCH(c, k_compact_moved, nblk(np, 256), 256, 0, coa.plist, newcell.p, moved.p, MS.p, np, fin.plist, fin.pcell, c->owner_level, (int8_t)(lev + 1), c->pos4, fin.lpos);
-      CUDA_CHECK(cudaStreamSynchronize(c->stream));
-      newcell.release(); moved.release(); MS.release();
+      if (np) LAUNCH(c, k_compact_moved, nblk(np, 256), 256, 0, coa.plist, newcell.p, moved.p, MS.p, np, fin.plist, fin.pcell, c->owner_level, (int8_t)(lev + 1), c->pos4, fin.lpos, dlt.p);
+      newcell.release(); moved.release(); dlt.release(); MS.release();      // stream-ordered block cache: no host sync needed
     }
     if (c->levels.size() >= 60) break;
   }

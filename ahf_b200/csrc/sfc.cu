@@ -190,8 +190,7 @@ void radix_sort_pairs(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t *k
     uint64_t *tk = ki; ki = ko; ko = tk;
     uint32_t *tv = vi; vi = vo; vo = tv;
   }
-  CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  bh.release(); bs.release();
+  bh.release(); bs.release();                       // stream-ordered block cache: no host sync needed
   *keys_sorted = ki; *vals_sorted = vi;
 }
 
