@@ -79,6 +79,10 @@ struct Level {
   int32_t  *crow = nullptr;     // [ncell] row index                             (sparse levels)
   int32_t  *count = nullptr;    // [ncell] particles linked when deposited
   uint64_t *hkey = nullptr; int32_t *hval = nullptr; uint64_t hmask = 0;   // open addressing hash
+  // parent/child links between consecutive levels: cells of the next level are found through them, not through the hash
+  int32_t  *parent = nullptr;   // [ncell] cell of the coarser level this cell is a child of      (sparse levels)
+  int32_t  *cidx = nullptr;     // [ncell] -1: no children; else slot in cbase | 0x40000000 when the children are a ghost pair
+  int4     *cbase = nullptr;    // [marked cells] index on the next level of child (i=0, j, k): .x (0,0) .y (j=1,k=0) .z (0,1) .w (1,1)
   // rows / planes of sparse levels
   int64_t  nrow = 0, nplane = 0;
   uint64_t *rowkey = nullptr;   // [nrow] z*L+y

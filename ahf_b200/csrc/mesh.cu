@@ -433,6 +433,168 @@ k_deposit_tiles(const float4 *__restrict__ pos4, const int32_t *__restrict__ tst
 }
 
 // ------------------------------------------------------------------------------------------------
+// D4 refinement levels, run aggregation (k_deposit_runs).
+//   On a refinement level the particles are concentrated: several (in clump cores hundreds) per cell, and since the level's
+//   particle list is Hilbert sorted the particles of one cell are CONSECUTIVE.  Lane-per-particle shared atomics then serialise
+//   on the same address (ncu, level 4 of the bench box: 20 wavefronts per ATOMS).  Here every thread walks DR_K consecutive
+//   particles and keeps the 27 fixed-point terms of the current cell in registers; they go to the shared-memory tile only when
+//   the cell changes.  The lanes of a warp sit DR_K particles apart, so their flushes mostly hit different cells.  The per-term
+//   integers are the ones k_deposit_tiles<true> produces (same float expression, same rounding), so the level sums are
+//   bit-identical to it whatever the grouping.
+// ------------------------------------------------------------------------------------------------
+constexpr int DR_THREADS = 256;
+constexpr int DR_K       = 8;                                   // consecutive particles per thread = one 128-byte line of lpos
+constexpr int DR_SMEM    = 2 * DT_HH * 4 + DT_HH * 2 + 16;       // low words | carry words | compaction list of the flush
+
+__global__ void __launch_bounds__(DR_THREADS, 2)
+k_deposit_runs(const float4 *__restrict__ lpos, const int32_t *__restrict__ tstart, const int2 *__restrict__ work, int L, int logL, int tbits,
+               unsigned long long *__restrict__ acc, const uint32_t *__restrict__ tlist, const int32_t *__restrict__ pcell, LV lvw,
+               const int32_t *__restrict__ nbr, float fxs)
+{
+  extern __shared__ __align__(16) unsigned char dsm[];
+  uint32_t *tile = reinterpret_cast<uint32_t *>(dsm);
+  uint32_t *tcar = tile + DT_HH;
+  uint16_t *list = reinterpret_cast<uint16_t *>(dsm + 2 * DT_HH * 4);
+  __shared__ int s_nnz;
+  const int2 wk = work[blockIdx.x];
+  const int  t = wk.x, chunk = wk.y & 0x3fffffff;
+  const int  s0 = tstart[t] + chunk * DT_CHUNK;
+  int        np = tstart[t + 1] - s0;
+  if (np > DT_CHUNK) np = DT_CHUNK;
+  uint32_t tx, ty, tz;
+  hilbert_coords((uint64_t)tlist[t], (unsigned)tbits, tx, ty, tz);
+  const int x0 = (int)tx * DT_T, y0 = (int)ty * DT_T, z0 = (int)tz * DT_T;
+  const uint32_t tile_s = smem_u32(tile);
+  for (int i = threadIdx.x; i < 2 * DT_HH / 4; i += DR_THREADS) reinterpret_cast<uint4 *>(tile)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) s_nnz = 0;
+  __syncthreads();
+  const float fL = (float)L;
+  const int   M = L - 1;
+  const int   lane = threadIdx.x & 31;
+  // segment length: DR_K when the chunk is full, shorter for the thin tiles of deep levels so that all threads have work
+  const int kk = min(DR_K, max(1, (np + DR_THREADS - 1) / DR_THREADS));
+  for (int base = threadIdx.x * kk; base < np + (31 * kk); base += DR_THREADS * kk) {           // whole warps stay in the loop (REDUX below)
+    if ((base - lane * kk) >= np) break;                                                        // the warp's first segment is past the end
+    unsigned long long a27[27];
+#pragma unroll
+    for (int q = 0; q < 27; q++) a27[q] = 0ull;
+    int cur = -1;                                    // tile word index of the cell the registers belong to
+    auto flush = [&](int widx) {
+      const uint32_t cell0 = tile_s + 4u * (uint32_t)widx;
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+          for (int a = 0; a < 3; a++) tile_add64(cell0 + 4u * (uint32_t)((k * DT_H + j) * DT_H + a), a27[k * 9 + j * 3 + a]);
+    };
+    const int nmine = min(kk, np - base);            // <= 0: nothing (the thread only takes part in the warp votes)
+    float4 qn = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nmine > 0) qn = lpos[s0 + base];
+    for (int i = 0; i < nmine; i++) {
+      const float4 q = qn;
+      if (i + 1 < nmine) qn = lpos[s0 + base + i + 1];
+      const float fx = q.x * fL, fy = q.y * fL, fz = q.z * fL;
+      const int   fb = __float_as_int(q.w);          // relink's face bits: cell coordinate = floor(L*x) - bit
+      const int   cx = (int)fx - (fb & 1), cy = (int)fy - ((fb >> 1) & 1), cz = (int)fz - ((fb >> 2) & 1);
+      const float sx = fx - ((float)cx + 0.5f), sy = fy - ((float)cy + 0.5f), sz = fz - ((float)cz + 0.5f);
+      float wx[3], wy[3], wz[3];
+      wx[0] = 0.5f * (0.5f - sx) * (0.5f - sx); wx[1] = 0.75f - sx * sx; wx[2] = 0.5f * (0.5f + sx) * (0.5f + sx);
+      wy[0] = 0.5f * (0.5f - sy) * (0.5f - sy); wy[1] = 0.75f - sy * sy; wy[2] = 0.5f * (0.5f + sy) * (0.5f + sy);
+      wz[0] = 0.5f * (0.5f - sz) * (0.5f - sz); wz[1] = 0.75f - sz * sz; wz[2] = 0.5f * (0.5f + sz) * (0.5f + sz);
+      const int lx = cx - x0, ly = cy - y0, lz = cz - z0;
+      const bool intile = (unsigned)lx < (unsigned)DT_T && (unsigned)ly < (unsigned)DT_T && (unsigned)lz < (unsigned)DT_T;
+      if (!intile) {
+        // the particle's node is not in this tile (face case of relink): straight to the global accumulators
+        const size_t pc = (size_t)pcell[s0 + base + i];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+          for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+              const int tgt = nbr[(size_t)(k * 9 + j * 3 + a) * (size_t)lvw.ncell + pc];
+              if (tgt >= 0) atomicAdd(&acc[tgt], __float2ull_rn(wz[k] * wy[j] * fxs * wx[a]));
+            }
+        continue;
+      }
+      const int widx = (lz * DT_H + ly) * DT_H + lx;
+      if (widx != cur) {
+        if (cur >= 0) {
+          flush(cur);
+#pragma unroll
+          for (int q = 0; q < 27; q++) a27[q] = 0ull;
+        }
+        cur = widx;
+      }
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          const float wyz = wz[k] * wy[j] * fxs;
+#pragma unroll
+          for (int a = 0; a < 3; a++) a27[k * 9 + j * 3 + a] += __float2ull_rn(wyz * wx[a]);
+        }
+    }
+    // last run of the segment.  Clump cores: when the whole warp ends in ONE cell the 27 sums are added across the warp first
+    // (REDUX on three limbs, values < 2^48) and one lane touches shared memory.
+    const int  cur0 = __shfl_sync(0xffffffffu, cur, 0);
+    const bool same = __all_sync(0xffffffffu, cur == cur0) && cur0 >= 0;
+    if (same) {
+#pragma unroll
+      for (int q = 0; q < 27; q++) {
+        const unsigned long long v = a27[q];
+        const uint32_t l0 = __reduce_add_sync(0xffffffffu, (uint32_t)(v & 0xffffu)), l1 = __reduce_add_sync(0xffffffffu, (uint32_t)((v >> 16) & 0xffffu)),
+                       l2 = __reduce_add_sync(0xffffffffu, (uint32_t)(v >> 32));
+        a27[q] = (unsigned long long)l0 + ((unsigned long long)l1 << 16) + ((unsigned long long)l2 << 32);
+      }
+      if (lane == 0) flush(cur0);
+    } else if (cur >= 0) flush(cur);
+  }
+  __syncthreads();
+  // flush of the tile: touched cells compacted into a list, then resolved through the cell hash with four probes in flight
+  for (int i = threadIdx.x; i < DT_HH; i += DR_THREADS) {
+    const bool nz = (tile[i] | tcar[i]) != 0;
+    const unsigned bal = __ballot_sync(__activemask(), nz);
+    if (nz) {
+      const int leader = __ffs(bal) - 1;
+      int basep = 0;
+      if (lane == leader) basep = atomicAdd(&s_nnz, __popc(bal));
+      basep = __shfl_sync(bal, basep, leader);
+      list[basep + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
+    }
+  }
+  __syncthreads();
+  const int nnz = s_nnz;
+  for (int e0 = threadIdx.x; e0 < nnz; e0 += 4 * DR_THREADS) {
+    uint64_t kq[4], sq[4], hq[4];
+    int      iq[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int e = e0 + q * DR_THREADS;
+      iq[q] = e < nnz ? (int)list[e] : -1;
+      const int i = iq[q] < 0 ? 0 : iq[q];
+      const int hz = i / (DT_H * DT_H), r = i - hz * (DT_H * DT_H), hy = r / DT_H, hx = r - hy * DT_H;
+      kq[q] = lv_key(lvw, (x0 + hx - 1) & M, (y0 + hy - 1) & M, (z0 + hz - 1) & M);
+      sq[q] = mix64(kq[q] >> 3) & lvw.hmask;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) hq[q] = iq[q] >= 0 ? lvw.hkey[sq[q]] : ~0ull;
+    int tg[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const uint64_t kb = kq[q] >> 3;
+      uint64_t s = sq[q], hk = hq[q];
+      while (hk != kb && hk != ~0ull) { s = (s + 1) & lvw.hmask; hk = lvw.hkey[s]; }
+      tg[q] = (iq[q] >= 0 && hk == kb) ? lvw.hval[s * 8 + (kq[q] & 7)] : -1;      // particles sit on interior nodes: every touched cell exists
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      if (tg[q] >= 0) atomicAdd(&acc[tg[q]], ((unsigned long long)tcar[iq[q]] << 32) | tile[iq[q]]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // D4 domain level, integer formulation (k_deposit_dom).
 //   Positions are float32 in [0,1): u = trunc(x * 2^32) is exact (x >= 2^-8) and cell = u >> (32 - logL) equals the
 //   reference's (unsigned long)(L * x) (lltools.c:59).  The in-cell fraction f = (u << logL) / 2^32 gives the TSC weights
@@ -836,10 +998,11 @@ __global__ void k_mark_sparse(LV v, const uint8_t *__restrict__ tn, const uint8_
 __global__ void k_make_children(LV v, const uint8_t *__restrict__ mark, const int *__restrict__ S, int Mtot,
                                 const int32_t *__restrict__ crow, const int32_t *__restrict__ row_c0, const int32_t *__restrict__ rowplane,
                                 const int32_t *__restrict__ plane_r0, int nrow, uint64_t *__restrict__ fkey, uint8_t *__restrict__ fbreak,
-                                int flogL)
+                                int flogL, int32_t *__restrict__ fparent, int32_t *__restrict__ cidx, int4 *__restrict__ cbase)
 {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= v.ncell || !mark[c]) return;
+  if (c >= v.ncell) return;
+  if (!mark[c]) { cidx[c] = -1; return; }
   int r, rc0, rc1, pc0, pc1;
   if (v.dense) {
     r = c >> v.logL; rc0 = r << v.logL; rc1 = rc0 + (int)v.L;
@@ -854,16 +1017,22 @@ __global__ void k_make_children(LV v, const uint8_t *__restrict__ mark, const in
   const int MB = Sp0, MP = Sp1 - Sp0, MBR = Sr0 - Sp0, MR = Sr1 - Sr0, RR = S[c] - Sr0;
   int x, y, z; lv_coords(v, c, x, y, z);
   const bool ghost = (mark[c] == 2);
+  int cb[4];
 #pragma unroll
   for (int k = 0; k < 2; k++)
 #pragma unroll
-    for (int j = 0; j < 2; j++)
+    for (int j = 0; j < 2; j++) {
+      cb[k * 2 + j] = (int)(8ll * MB + (long long)k * 4 * MP + 4ll * MBR + (long long)j * 2 * MR + 2ll * RR);
 #pragma unroll
       for (int i = 0; i < 2; i++) {
         long long idx = 8ll * MB + (long long)k * 4 * MP + 4ll * MBR + (long long)j * 2 * MR + 2ll * RR + i;
         fkey[idx]   = ((((uint64_t)(2 * z + k)) << flogL | (uint64_t)(2 * y + j)) << flogL) | (uint64_t)(2 * x + i);
         fbreak[idx] = (ghost && i == 1) ? 1 : 0;                 // the reference's run ends after a ghost pair
+        fparent[idx] = c;
       }
+    }
+  cidx[c] = S[c] | (ghost ? 0x40000000 : 0);
+  cbase[S[c]] = make_int4(cb[0], cb[1], cb[2], cb[3]);
 }
 
 __global__ void k_hash_clear(uint64_t *__restrict__ hkey, int4 *__restrict__ hval8, uint64_t cap)
@@ -975,11 +1144,80 @@ __global__ void k_neighbours(LV v, int32_t *__restrict__ nbr, uint8_t *__restric
   interior[c] = all ? 1 : 0;
 }
 
+// Same table as k_neighbours, built WITHOUT hash probes.  A cell (x,y,z) = child (i,j,k) of coarse cell p; its neighbour
+// (x+a, y+b, z+c) is child ((i+a)&1, (j+b)&1, (k+c)&1) of the coarse neighbour at offset ((i+a)>>1, (j+b)>>1, (k+c)>>1).  Every
+// parent is interior on its own level (it passed test_node, or is the interior cell behind a ghost pair, refine_grid.c:231),
+// so all 27 coarse neighbours exist in the coarse table (arithmetic on the dense domain level, periodic wrap included), and the
+// children of a coarse cell are found through cidx/cbase.  "x-break" (the run ends after a ghost pair) is a property of the
+// parent: the i=1 child of a ghost parent.  The visibility rules are those of k_neighbours (get_nnodes.c:459-862).
+__global__ void __launch_bounds__(128) k_neighbours_pc(LV v, const int32_t *__restrict__ parent, LV cv, const int32_t *__restrict__ cnbr,
+                                                       const int32_t *__restrict__ cidx, const int4 *__restrict__ cbase,
+                                                       int32_t *__restrict__ nbr, uint8_t *__restrict__ interior)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= v.ncell) return;
+  int x, y, z; lv_coords(v, c, x, y, z);
+  const int L = (int)v.L;
+  const int p = parent[c];
+  const int bi = x & 1, bj = y & 1, bk = z & 1;
+  // the 2x2x2 coarse cells the 27 neighbours live in: per dimension the offsets (b-1, b)
+  int4 cbq[8];
+  bool ghq[8];
+  int  px = 0, py = 0, pz = 0;
+  const int CM = (int)(cv.L - 1);
+  if (cv.dense) lv_coords(cv, p, px, py, pz);
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const int da = (q & 1) + bi - 1, db = ((q >> 1) & 1) + bj - 1, dc = ((q >> 2) & 1) + bk - 1;
+    int qc;
+    if (cv.dense) qc = (int)lv_key(cv, (px + da) & CM, (py + db) & CM, (pz + dc) & CM);
+    else qc = (da == 0 && db == 0 && dc == 0) ? p : cnbr[(size_t)((dc + 1) * 9 + (db + 1) * 3 + (da + 1)) * (size_t)cv.ncell + (size_t)p];
+    const int ci = qc >= 0 ? cidx[qc] : -1;
+    ghq[q] = ci >= 0 && (ci & 0x40000000);
+    cbq[q] = ci >= 0 ? cbase[ci & 0x3fffffff] : make_int4(-1, -1, -1, -1);
+  }
+  // geometric neighbour (a,b,cc in -1..1) and whether the run ends after it
+  auto geo = [&](int a, int b, int cc, bool &brk) -> int {
+    const int tx = bi + a, ty = bj + b, tz = bk + cc;                       // -1..2
+    const int q = ((tx >> 1) - (bi - 1)) | (((ty >> 1) - (bj - 1)) << 1) | (((tz >> 1) - (bk - 1)) << 2);
+    const int4 cb = cbq[q];
+    const int  jk = (tz & 1) * 2 + (ty & 1);
+    const int  b0 = jk == 0 ? cb.x : jk == 1 ? cb.y : jk == 2 ? cb.z : cb.w;
+    brk = ghq[q] && (tx & 1);
+    return b0 < 0 ? -1 : b0 + (tx & 1);
+  };
+  bool all = true;
+  const size_t os = (size_t)v.ncell;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    bool dummy;
+    const int pm = (k == 1) ? c : geo(0, 0, k - 1, dummy);               // the plane is found through its (x, y) node (get_nnodes.c:514-651)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      int32_t *o = nbr + (size_t)(k * 9 + j * 3) * os + (size_t)c;
+      bool brk_rm = false;
+      const int rm = (pm >= 0) ? ((k == 1 && j == 1) ? c : geo(0, j - 1, k - 1, brk_rm)) : -1;
+      if (k == 1 && j == 1) brk_rm = ghq[(1 - bi) | ((1 - bj) << 1) | ((1 - bk) << 2)] && bi;      // own parent is slot (1-bi, 1-bj, 1-bk)
+      if (rm < 0) { o[0] = o[os] = o[2 * os] = -1; all = false; continue; }
+      o[os] = rm;
+      bool brk_m = false, brk_p = false;
+      const int gm = geo(-1, j - 1, k - 1, brk_m), gp = geo(1, j - 1, k - 1, brk_p);
+      // x-1: same run, else the periodic image when on the face (get_nnodes.c:490-508); x+1 (get_nnodes.c:465-485)
+      const int xm = (x > 0) ? ((gm >= 0 && !brk_m) ? gm : -1) : gm;
+      const int xp = (x < L - 1) ? ((gp >= 0 && !brk_rm) ? gp : -1) : gp;
+      o[0] = xm; o[2 * os] = xp;
+      if (xm < 0 || xp < 0) all = false;
+    }
+  }
+  interior[c] = all ? 1 : 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // R1: relink (relink.c:31-288) -- per particle: first (z,y,x)-ordered interior child that contains it
 // ------------------------------------------------------------------------------------------------
 __global__ void k_relink(const float4 *__restrict__ pos4, const uint32_t *__restrict__ plist, const int32_t *__restrict__ pcell, uint64_t np,
-                         LV coa, const uint8_t *__restrict__ cmark, LV fin, const uint8_t *__restrict__ finterior,
+                         LV coa, const uint8_t *__restrict__ cmark, const int32_t *__restrict__ cidx, const int4 *__restrict__ cbase,
+                         LV fin, const uint8_t *__restrict__ finterior,
                          int32_t *__restrict__ newcell, uint8_t *__restrict__ moved, uint8_t *__restrict__ dlt)
 {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -994,6 +1232,7 @@ __global__ void k_relink(const float4 *__restrict__ pos4, const uint32_t *__rest
     const double t[3] = { (double)q.x * Lf, (double)q.y * Lf, (double)q.z * Lf };
     const int    b[3] = { 2 * cx, 2 * cy, 2 * cz };
     // child b+e (e = 0,1) contains the particle iff b+e <= t <= b+e+1 (inclusive on both faces, relink.c:153)
+    const int4 cb = cbase[cidx[c] & 0x3fffffff];        // the cell's children on the fine level (k_make_children): no hash probe
     bool ok[3][2];
 #pragma unroll
     for (int d = 0; d < 3; d++) {
@@ -1006,8 +1245,9 @@ __global__ void k_relink(const float4 *__restrict__ pos4, const uint32_t *__rest
         if (!ok[1][j]) continue;
         for (int e = 0; e < 2 && res < 0; e++) {
           if (!ok[0][e]) continue;
-          int f = lv_lookup(fin, b[0] + e, b[1] + j, b[2] + k);
-          if (f >= 0 && finterior[f]) {
+          const int jk = k * 2 + j;
+          const int f = (jk == 0 ? cb.x : jk == 1 ? cb.y : jk == 2 ? cb.z : cb.w) + e;
+          if (finterior[f]) {
             res = f;
             dl = (uint8_t)(((int)t[0] != b[0] + e ? 1 : 0) | ((int)t[1] != b[1] + j ? 2 : 0) | ((int)t[2] != b[2] + k ? 4 : 0));
           }
@@ -1126,6 +1366,7 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
   if (!attr_set) {
     CUDA_CHECK(cudaFuncSetAttribute(k_deposit_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_deposit_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_deposit_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, DR_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
@@ -1185,8 +1426,13 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
       else if (tiles_dense)
         LAUNCH(c, k_deposit_tiles<false>, (unsigned)W, DT_THREADS, DT_SMEM, c->pos4, tstart.p, work.p, (int)lv.L, v.logL, tbits, acc.p,
                (const uint32_t *)nullptr, (const int32_t *)nullptr, v, (const int32_t *)nullptr, (float)fxscale);
-      else
+      else if (getenv("AHFGPU_SPARSE_V1") || (!getenv("AHFGPU_SPARSE_V2") && (double)lv.npart_dep < 0.75 * (double)lv.ncell))
+        // lane per particle: the thin tiles of the deepest levels (well under one particle per cell, a few hundred particles per
+        // tile) have no runs to aggregate and want the larger CTA for the tile flush (measured: 0.23 vs 0.31 ms on level 6)
         LAUNCH(c, k_deposit_tiles<true>, (unsigned)W, DT_THREADS, DT_SMEM, lv.lpos, tstart.p, work.p, (int)lv.L, v.logL, tbits, acc.p,
+               tlist.p, lv.pcell, v, lv.nbr, (float)fxscale);
+      else
+        LAUNCH(c, k_deposit_runs, (unsigned)W, DR_THREADS, DR_SMEM, lv.lpos, tstart.p, work.p, (int)lv.L, v.logL, tbits, acc.p,
                tlist.p, lv.pcell, v, lv.nbr, (float)fxscale);
     }
     if (lv.dense) c->stage_cnt_extra["deposit_dom_ctas"] = W;
@@ -1272,8 +1518,9 @@ void amr_build(ahfgpu_ctx *c)
       f.critdens = par.nth_ref * f.masstopartdens;
       f.ckey = dalloc<uint64_t>(f.ncell); f.xbreak = dalloc<uint8_t>(f.ncell);
       int flogL = cv.logL + 1;
+      f.parent = dalloc<int32_t>(f.ncell); cur.cidx = dalloc<int32_t>(nc); cur.cbase = dalloc<int4>(M);
       LAUNCH(c, k_make_children, nblk(nc, 256), 256, 0, cv, cur.mark, S.p, M, cur.crow, cur.row_c0, cur.dense ? nullptr : cur.rowplane,
-             cur.plane_r0, (int)cur.nrow, f.ckey, f.xbreak, flogL);
+             cur.plane_r0, (int)cur.nrow, f.ckey, f.xbreak, flogL, f.parent, cur.cidx, cur.cbase);
       S.release();
       // hash
       // slots hold 8 x-consecutive cells; children come in x-pairs, so there are at most ncell/2 occupied slots
@@ -1284,7 +1531,21 @@ void amr_build(ahfgpu_ctx *c)
       alloc_cell_arrays(f);
       f.interior = dalloc<uint8_t>(f.ncell); f.nbr = dalloc<int32_t>((size_t)f.ncell * 27);
       LV fv = view(f);
-      LAUNCH(c, k_neighbours, nblk(f.ncell, 128), 128, 0, fv, f.nbr, f.interior);
+      if (getenv("AHFGPU_NBR_V1")) LAUNCH(c, k_neighbours, nblk(f.ncell, 128), 128, 0, fv, f.nbr, f.interior);      // hash probes (A/B timing)
+      else LAUNCH(c, k_neighbours_pc, nblk(f.ncell, 128), 128, 0, fv, f.parent, cv, cur.nbr, cur.cidx, cur.cbase, f.nbr, f.interior);
+      if (getenv("AHFGPU_DEBUG_NBR")) {                 // both constructions must give the same table
+        DevBuf<int32_t> nb2; DevBuf<uint8_t> in2; DevBuf<unsigned long long> out;
+        nb2.reserve((size_t)f.ncell * 27); in2.reserve(f.ncell); out.reserve(3);
+        unsigned long long h0[3] = { 0, 0, ~0ull }, h[3];
+        CUDA_CHECK(cudaMemcpyAsync(out.p, h0, sizeof(h0), cudaMemcpyHostToDevice, c->stream));
+        LAUNCH(c, k_neighbours, nblk(f.ncell, 128), 128, 0, fv, nb2.p, in2.p);
+        LAUNCH(c, k_dbg_compare, nblk((uint64_t)f.ncell * 27, 256), 256, 0, f.nbr, nb2.p, (uint64_t)f.ncell * 27, out.p);
+        CUDA_CHECK(cudaMemcpyAsync(h, out.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        fprintf(stderr, "[nbr dbg] level %d: %llu of %llu neighbour entries differ between the parent/child and the hash construction (first at %llu)\n",
+                lev + 1, h[0], (unsigned long long)f.ncell * 27, h[2]);
+        nb2.release(); in2.release(); out.release();
+      }
       if (getenv("AHFGPU_DEBUG_RELINK")) {
         DevBuf<int32_t> nb2; DevBuf<uint8_t> in2; DevBuf<unsigned long long> out;
         nb2.reserve((size_t)f.ncell * 27); in2.reserve(f.ncell); out.reserve(3);
@@ -1315,14 +1576,14 @@ void amr_build(ahfgpu_ctx *c)
       newcell.reserve(np); moved.reserve(np); dlt.reserve(np); MS.reserve(np);
       int nmoved = 0;
       if (np) {
-        LAUNCH(c, k_relink, nblk(np, 256), 256, 0, c->pos4, coa.plist, coa.pcell, np, view(coa), coa.mark, view(fin), fin.interior, newcell.p, moved.p, dlt.p);
+        LAUNCH(c, k_relink, nblk(np, 256), 256, 0, c->pos4, coa.plist, coa.pcell, np, view(coa), coa.mark, coa.cidx, coa.cbase, view(fin), fin.interior, newcell.p, moved.p, dlt.p);
         nmoved = exclusive_scan<uint8_t>(c, moved.p, MS.p, np);
         if (getenv("AHFGPU_DEBUG_RELINK")) {
           DevBuf<int32_t> nc2; DevBuf<uint8_t> mv2, dl2; DevBuf<unsigned long long> out;
           nc2.reserve(np); mv2.reserve(np); dl2.reserve(np); out.reserve(3);
           unsigned long long h0[3] = { 0, 0, ~0ull }, h[3];
           CUDA_CHECK(cudaMemcpyAsync(out.p, h0, sizeof(h0), cudaMemcpyHostToDevice, c->stream));
-          LAUNCH(c, k_relink, nblk(np, 256), 256, 0, c->pos4, coa.plist, coa.pcell, np, view(coa), coa.mark, view(fin), fin.interior, nc2.p, mv2.p, dl2.p);
+          LAUNCH(c, k_relink, nblk(np, 256), 256, 0, c->pos4, coa.plist, coa.pcell, np, view(coa), coa.mark, coa.cidx, coa.cbase, view(fin), fin.interior, nc2.p, mv2.p, dl2.p);
           LAUNCH(c, k_dbg_compare, nblk(np, 256), 256, 0, newcell.p, nc2.p, np, out.p);
           CUDA_CHECK(cudaMemcpyAsync(h, out.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
           CUDA_CHECK(cudaStreamSynchronize(c->stream));
