@@ -38,11 +38,13 @@ __global__ void k_keys_aos(const unsigned char *__restrict__ rec, uint64_t n, ui
 //   per pass: block histograms -> exclusive scan over [digit][block] -> ranked scatter
 // ------------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS   = 8;
-constexpr int RS_TILE    = RS_THREADS * RS_ITEMS;   // 4096 pairs per CTA
 constexpr int RS_WARPS   = RS_THREADS / 32;
-constexpr int RS_WCHUNK  = RS_TILE / RS_WARPS;      // 512 consecutive pairs per warp
+// pairs per thread: 8 (tile 2048, 3 CTAs/SM) or 16 (tile 4096: digit runs twice as long, so the run-by-run output fills its
+// sectors better; 128 registers, 2 CTAs/SM).  Chosen at run time in radix_sort_pairs (AHFGPU_RS_ITEMS).
+#define RS_TILE   (RS_THREADS * RS_ITEMS)
+#define RS_WCHUNK (RS_TILE / RS_WARPS)
 
+template <int RS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t *__restrict__ keys, uint64_t n, int shift,
                                                         uint32_t *__restrict__ bhist, uint32_t nblk)
 {
@@ -90,7 +92,8 @@ __global__ void __launch_bounds__(1024) k_scan_u32(uint32_t *__restrict__ a, uin
 
 // ranked scatter.  The tile is first sorted by digit in shared memory (stable), then written out digit run by digit run so that
 // consecutive threads store consecutive addresses (a direct scatter writes 12 useful bytes per pair of 32-byte sectors).
-constexpr int RS_SMEM = RS_TILE * 12 + RS_WARPS * 256 * 4 + 2 * 256 * 4 + 64;
+#define RS_SMEM (RS_TILE * 12 + RS_WARPS * 256 * 4 + 2 * 256 * 4 + 64)
+template <int RS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
                                                            uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, uint64_t n,
                                                            int shift, const uint32_t *__restrict__ bscan, uint32_t nblk)
@@ -170,28 +173,37 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t *__res
   }
 }
 
-void radix_sort_pairs(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, uint64_t n,
-                      int key_bits, uint64_t **keys_sorted, uint32_t **vals_sorted)
+template <int RS_ITEMS>
+static void radix_sort_pairs_t(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, uint64_t n,
+                               int key_bits, uint64_t **keys_sorted, uint32_t **vals_sorted)
 {
-  *keys_sorted = keys; *vals_sorted = vals;
-  if (n == 0) return;
   const uint32_t nblk = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
   DevBuf<uint32_t> bh;
   DevBuf<int>      bs;
   static bool attr_set = false;
-  if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM)); attr_set = true; }
+  if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(k_rs_scatter<RS_ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM)); attr_set = true; }
   bh.reserve((size_t)256 * nblk);
   uint64_t *ki = keys, *ko = keys_tmp;
   uint32_t *vi = vals, *vo = vals_tmp;
   for (int shift = 0; shift < key_bits; shift += 8) {
-    LAUNCH(c, k_rs_hist, nblk, RS_THREADS, 0, ki, n, shift, bh.p, nblk);
+    LAUNCH(c, k_rs_hist<RS_ITEMS>, nblk, RS_THREADS, 0, ki, n, shift, bh.p, nblk);
     exclusive_scan_async<int>(c, (const int *)bh.p, (int *)bh.p, (uint64_t)256 * nblk, nullptr, bs);   // in place: each tile is read before it is written
-    LAUNCH(c, k_rs_scatter, nblk, RS_THREADS, RS_SMEM, ki, vi, ko, vo, n, shift, bh.p, nblk);
+    LAUNCH(c, k_rs_scatter<RS_ITEMS>, nblk, RS_THREADS, RS_SMEM, ki, vi, ko, vo, n, shift, bh.p, nblk);
     uint64_t *tk = ki; ki = ko; ko = tk;
     uint32_t *tv = vi; vi = vo; vo = tv;
   }
   bh.release(); bs.release();                       // stream-ordered block cache: no host sync needed
   *keys_sorted = ki; *vals_sorted = vi;
+}
+
+void radix_sort_pairs(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, uint64_t n,
+                      int key_bits, uint64_t **keys_sorted, uint32_t **vals_sorted)
+{
+  *keys_sorted = keys; *vals_sorted = vals;
+  if (n == 0) return;
+  static const int items = getenv("AHFGPU_RS_ITEMS") ? atoi(getenv("AHFGPU_RS_ITEMS")) : 8;      // measured at 256^3: 1.81 ms (8) vs 2.68 ms (16): the ranking loop is latency bound, occupancy wins
+  if (items == 8) radix_sort_pairs_t<8>(c, keys, vals, keys_tmp, vals_tmp, n, key_bits, keys_sorted, vals_sorted);
+  else radix_sort_pairs_t<16>(c, keys, vals, keys_tmp, vals_tmp, n, key_bits, keys_sorted, vals_sorted);
 }
 
 // ------------------------------------------------------------------------------------------------
