@@ -446,7 +446,7 @@ constexpr int DR_THREADS = 256;
 constexpr int DR_K       = 8;                                   // consecutive particles per thread = one 128-byte line of lpos
 constexpr int DR_SMEM    = 2 * DT_HH * 4 + DT_HH * 2 + 16;       // low words | carry words | compaction list of the flush
 
-__global__ void __launch_bounds__(DR_THREADS, 2)
+__global__ void __launch_bounds__(DR_THREADS, 3)
 k_deposit_runs(const float4 *__restrict__ lpos, const int32_t *__restrict__ tstart, const int2 *__restrict__ work, int L, int logL, int tbits,
                unsigned long long *__restrict__ acc, const uint32_t *__restrict__ tlist, const int32_t *__restrict__ pcell, LV lvw,
                const int32_t *__restrict__ nbr, float fxs)
@@ -1215,7 +1215,7 @@ __global__ void __launch_bounds__(128) k_neighbours_pc(LV v, const int32_t *__re
 // ------------------------------------------------------------------------------------------------
 // R1: relink (relink.c:31-288) -- per particle: first (z,y,x)-ordered interior child that contains it
 // ------------------------------------------------------------------------------------------------
-__global__ void k_relink(const float4 *__restrict__ pos4, const uint32_t *__restrict__ plist, const int32_t *__restrict__ pcell, uint64_t np,
+__global__ void k_relink(const float4 *__restrict__ pos4, const float4 *__restrict__ lpos, const uint32_t *__restrict__ plist, const int32_t *__restrict__ pcell, uint64_t np,
                          LV coa, const uint8_t *__restrict__ cmark, const int32_t *__restrict__ cidx, const int4 *__restrict__ cbase,
                          LV fin, const uint8_t *__restrict__ finterior,
                          int32_t *__restrict__ newcell, uint8_t *__restrict__ moved, uint8_t *__restrict__ dlt)
@@ -1225,8 +1225,7 @@ __global__ void k_relink(const float4 *__restrict__ pos4, const uint32_t *__rest
   int c = pcell[i], res = -1;
   uint8_t dl = 0;                            // bit d: the child's coordinate d is floor(L*x_d) - 1 (particle exactly on the upper face)
   if (cmark[c]) {
-    uint64_t p = plist ? plist[i] : i;
-    float4   q = pos4[p];
+    const float4 q = lpos ? lpos[i] : pos4[plist ? plist[i] : i];      // refinement levels: the level's contiguous copy (coalesced)
     int cx, cy, cz; lv_coords(coa, c, cx, cy, cz);
     const double Lf = (double)fin.L;
     const double t[3] = { (double)q.x * Lf, (double)q.y * Lf, (double)q.z * Lf };
@@ -1269,8 +1268,8 @@ __global__ void k_dbg_compare(const int32_t *__restrict__ a, const int32_t *__re
 }
 __global__ void k_compact_moved(const uint32_t *__restrict__ plist, const int32_t *__restrict__ newcell, const uint8_t *__restrict__ moved,
                                 const int *__restrict__ S, uint64_t np, uint32_t *__restrict__ plist_out, int32_t *__restrict__ pcell_out,
-                                int8_t *__restrict__ owner, int8_t newlevel, const float4 *__restrict__ pos4, float4 *__restrict__ lpos_out,
-                                const uint8_t *__restrict__ dlt)
+                                int8_t *__restrict__ owner, int8_t newlevel, const float4 *__restrict__ pos4, const float4 *__restrict__ lpos_in,
+                                float4 *__restrict__ lpos_out, const uint8_t *__restrict__ dlt)
 {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= np || !moved[i]) return;
@@ -1278,7 +1277,7 @@ __global__ void k_compact_moved(const uint32_t *__restrict__ plist, const int32_
   plist_out[S[i]] = p; pcell_out[S[i]] = newcell[i];
   // level-local contiguous copy: TMA-stageable, no index indirection in the deposit.  The number-density deposit has no use for
   // the weight, so .w carries relink's face bits (cell coordinate = floor(L*x) - bit) and the deposit needs no cell-key gather.
-  float4 q = pos4[p]; q.w = __int_as_float((int)dlt[i]);
+  float4 q = lpos_in ? lpos_in[i] : pos4[p]; q.w = __int_as_float((int)dlt[i]);
   lpos_out[S[i]] = q;
   owner[p] = newlevel;
 }
@@ -1576,14 +1575,14 @@ void amr_build(ahfgpu_ctx *c)
       newcell.reserve(np); moved.reserve(np); dlt.reserve(np); MS.reserve(np);
       int nmoved = 0;
       if (np) {
-        LAUNCH(c, k_relink, nblk(np, 256), 256, 0, c->pos4, coa.plist, coa.pcell, np, view(coa), coa.mark, coa.cidx, coa.cbase, view(fin), fin.interior, newcell.p, moved.p, dlt.p);
+        LAUNCH(c, k_relink, nblk(np, 256), 256, 0, c->pos4, coa.lpos, coa.plist, coa.pcell, np, view(coa), coa.mark, coa.cidx, coa.cbase, view(fin), fin.interior, newcell.p, moved.p, dlt.p);
         nmoved = exclusive_scan<uint8_t>(c, moved.p, MS.p, np);
         if (getenv("AHFGPU_DEBUG_RELINK")) {
           DevBuf<int32_t> nc2; DevBuf<uint8_t> mv2, dl2; DevBuf<unsigned long long> out;
           nc2.reserve(np); mv2.reserve(np); dl2.reserve(np); out.reserve(3);
           unsigned long long h0[3] = { 0, 0, ~0ull }, h[3];
           CUDA_CHECK(cudaMemcpyAsync(out.p, h0, sizeof(h0), cudaMemcpyHostToDevice, c->stream));
-          LAUNCH(c, k_relink, nblk(np, 256), 256, 0, c->pos4, coa.plist, coa.pcell, np, view(coa), coa.mark, coa.cidx, coa.cbase, view(fin), fin.interior, nc2.p, mv2.p, dl2.p);
+          LAUNCH(c, k_relink, nblk(np, 256), 256, 0, c->pos4, coa.lpos, coa.plist, coa.pcell, np, view(coa), coa.mark, coa.cidx, coa.cbase, view(fin), fin.interior, nc2.p, mv2.p, dl2.p);
           LAUNCH(c, k_dbg_compare, nblk(np, 256), 256, 0, newcell.p, nc2.p, np, out.p);
           CUDA_CHECK(cudaMemcpyAsync(h, out.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
           CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -1601,7 +1600,7 @@ void amr_build(ahfgpu_ctx *c)
       }
       fin.npart_dep = nmoved;
       fin.plist = dalloc<uint32_t>(nmoved); fin.pcell = dalloc<int32_t>(nmoved); fin.lpos = dalloc<float4>(nmoved);
-      if (np) LAUNCH(c, k_compact_moved, nblk(np, 256), 256, 0, coa.plist, newcell.p, moved.p, MS.p, np, fin.plist, fin.pcell, c->owner_level, (int8_t)(lev + 1), c->pos4, fin.lpos, dlt.p);
+      if (np) LAUNCH(c, k_compact_moved, nblk(np, 256), 256, 0, coa.plist, newcell.p, moved.p, MS.p, np, fin.plist, fin.pcell, c->owner_level, (int8_t)(lev + 1), c->pos4, coa.lpos, fin.lpos, dlt.p);
       newcell.release(); moved.release(); dlt.release(); MS.release();      // stream-ordered block cache: no host sync needed
     }
     if (c->levels.size() >= 60) break;
