@@ -825,7 +825,8 @@ __global__ void k_finish_dens(const unsigned long long *__restrict__ acc, float 
 {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncell) return;
-  dens[c] = (float)(m2d_over_scale * (double)acc[c] - 1.0);      // zero_dens: -mean_dens, density.c:480
+  const unsigned long long a = acc[c];
+  dens[c] = a ? (float)(m2d_over_scale * (double)a - 1.0) : -1.0f;      // zero_dens: -mean_dens, density.c:480 (an empty box has an infinite scale)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1490,6 +1491,7 @@ void amr_build(ahfgpu_ctx *c)
     const int lev = (int)c->levels.size() - 1;
     deposit_level(c, cur);
     if (cur.L == lmax) break;                                          // generate_grids.c:307-308
+    if ((c->n_total ? c->n_total : n) == 0) break;                     // empty box: the domain grid alone, nothing to flag
     LV cv = view(cur);
     const int nc = (int)cur.ncell;
     int M = 0;
