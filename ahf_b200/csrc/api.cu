@@ -189,6 +189,7 @@ int ahfgpu_finalize(ahfgpu_ctx *c)
   cudaStreamSynchronize(c->stream);
   c->stage_reset(); c->free_halos(); c->free_levels(); c->free_particles();
   ahf::dfree(c->in_pos); ahf::dfree(c->in_mom); ahf::dfree(c->in_w); ahf::dfree(c->in_u);
+  ahf::dfree(c->scan_state); c->scan_state = nullptr; c->scan_cap = 0;
   for (auto &e : c->ev) if (e) cudaEventDestroy(e);
   {                                                   // blocks cached for this context's stream go back to the driver pool
     std::lock_guard<std::mutex> lk(g_cache_mu);

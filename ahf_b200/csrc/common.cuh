@@ -122,6 +122,7 @@ struct ahfgpu_ctx {
   float    *in_pos = nullptr, *in_mom = nullptr, *in_w = nullptr, *in_u = nullptr;
   uint64_t  in_n = 0;
   cudaEvent_t ev[16] = {};
+  unsigned long long *scan_state = nullptr; size_t scan_cap = 0;      // look-back state of the single-pass scan (scan.cuh), kept zeroed
   // second stream of ahfgpu_sfc_sort_soa_async: host->device copies and the momentum gather run here, so the momenta travel
   // while the main stream sorts and builds the hierarchy.  mom_pending: mom4 is complete only after ev_mom.
   cudaStream_t copy_stream = nullptr;

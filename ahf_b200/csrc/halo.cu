@@ -1883,10 +1883,25 @@ __global__ void k_p_vmax(const int64_t *__restrict__ moff0, PG G, const int32_t 
 }
 
 __global__ void k_members_out(const int64_t *__restrict__ moff0, const int64_t *__restrict__ npart, const int64_t *__restrict__ moff, const uint32_t *__restrict__ members,
-                              int64_t *__restrict__ out)
+                              const uint32_t *__restrict__ gid, int64_t *__restrict__ out)
 {
   const int64_t h = blockIdx.x, np = npart[h];
-  for (int64_t i = threadIdx.x; i < np; i += blockDim.x) out[moff[h] + i] = (int64_t)members[moff0[h] + i];
+  for (int64_t i = threadIdx.x; i < np; i += blockDim.x) { const uint32_t m = members[moff0[h] + i]; out[moff[h] + i] = (int64_t)(gid ? gid[m] : m); }
+}
+
+// Halo-local particle copies.  After the radial sort the members of a halo are in radius order, i.e. scattered over the key-sorted
+// particle arrays, and every sweep of the unbinding / profile kernels would gather pos4/mom4 through them (32 random bytes per
+// member per sweep, ten to twenty sweeps).  The gathered members are copied ONCE into arrays in member order and the member lists
+// are renumbered to positions in those arrays (gid keeps the particle offsets for the output): the kernels are unchanged -- they
+// still index pos[members[j]] -- but consecutive members are now consecutive addresses, also after unbound members are removed
+// (the survivors stay in increasing order).
+__global__ void k_localize_members(const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, uint32_t *__restrict__ members, uint64_t tot,
+                                   float4 *__restrict__ hpos, float4 *__restrict__ hmom, uint32_t *__restrict__ gid)
+{
+  const uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (j >= tot) return;
+  const uint32_t p = members[j];
+  hpos[j] = pos4[p]; hmom[j] = mom4[p]; gid[j] = p; members[j] = (uint32_t)j;
 }
 
 // exclusive scan of int64 on the host (nhalo-sized arrays; halos are few compared with particles)
@@ -2196,6 +2211,15 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
     LAUNCH(c, k_copy_unsorted, (unsigned)nhalo, 64, 0, d_candoff, d_ng, d_moff0, P.min_part, d_idx, d_members);
   }
   ahf::dfree(d_r2);
+  // halo-local copies (k_localize_members); the context's particle pointers are swapped for the rest of the pass
+  float4 *hpos = nullptr, *hmom = nullptr; uint32_t *d_gid = nullptr;
+  struct Swap { ahfgpu_ctx *c; float4 *p, *m; ~Swap() { c->pos4 = p; c->mom4 = m; } } swap_back{ c, c->pos4, c->mom4 };
+  if (tot_g > 0 && !getenv("AHFGPU_HALO_GLOBAL")) {
+    Stage st(c, "halo_localize", tot_g);
+    hpos = dalloc<float4>(tot_g); hmom = dalloc<float4>(tot_g); d_gid = dalloc<uint32_t>(tot_g);
+    LAUNCH(c, k_localize_members, nblk(tot_g, 256), 256, 0, c->pos4, c->mom4, d_members, (uint64_t)tot_g, hpos, hmom, d_gid);
+    c->pos4 = hpos; c->mom4 = hmom;
+  }
   int64_t *d_np = dalloc<int64_t>(nhalo), *d_work = dalloc<int64_t>(nhalo);
   if (getenv("AHFGPU_UNBIND_V1")) {           // previous form: one CTA per halo (kept for A/B timing)
     {
@@ -2240,11 +2264,12 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
              c->h_scal, c->h_poff, c->h_prof, d_soff, d_scratch);
     else
       profiles_cooperative(c, nhalo, P, d_ctr, d_moff0, d_members, tot_g, d_np, h_np);
-    LAUNCH(c, k_members_out, (unsigned)nhalo, 256, 0, d_moff0, d_np, c->h_moff, d_members, c->h_members);
+    LAUNCH(c, k_members_out, (unsigned)nhalo, 256, 0, d_moff0, d_np, c->h_moff, d_members, d_gid, c->h_members);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
   }
   ahf::dfree(d_ctr); ahf::dfree(d_rad); ahf::dfree(d_seed); ahf::dfree(d_rlo); ahf::dfree(d_rhi); ahf::dfree(d_cand); ahf::dfree(d_candoff); ahf::dfree(d_ng);
   ahf::dfree(d_idx); ahf::dfree(d_moff0); ahf::dfree(d_eoff); ahf::dfree(d_members); ahf::dfree(d_np); ahf::dfree(d_work); ahf::dfree(d_soff); ahf::dfree(d_scratch);
+  ahf::dfree(hpos); ahf::dfree(hmom); ahf::dfree(d_gid);
 }
 
 }  // namespace ahf

@@ -1313,19 +1313,41 @@ template <typename T> static T *dalloc(size_t n)
 }
 static inline unsigned nblk(uint64_t n, int b) { return (unsigned)((n + b - 1) / b); }
 
+// rows / planes of a level that hold at least one marked cell (S = exclusive prefix sum over the marks, *Mtot its total)
+__global__ void k_count_marked(LV v, const int *__restrict__ S, const int *__restrict__ Mtot, const int32_t *__restrict__ row_c0,
+                               const int32_t *__restrict__ plane_r0, int nrow, int nplane, int *__restrict__ out)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int M = *Mtot;
+  auto Sat = [&](long long i) { return i >= v.ncell ? M : S[i]; };
+  bool rm = false, pm = false;
+  if (r < nrow) {
+    const long long c0 = v.dense ? ((long long)r << v.logL) : row_c0[r], c1 = v.dense ? c0 + v.L : row_c0[r + 1];
+    rm = Sat(c1) > Sat(c0);
+  }
+  if (r < nplane) {
+    const long long c0 = v.dense ? ((long long)r << (2 * v.logL)) : row_c0[plane_r0[r]], c1 = v.dense ? c0 + v.L * v.L : row_c0[plane_r0[r + 1]];
+    pm = Sat(c1) > Sat(c0);
+  }
+  const unsigned br = __ballot_sync(0xffffffffu, rm), bp = __ballot_sync(0xffffffffu, pm);
+  if ((threadIdx.x & 31) == 0) { if (br) atomicAdd(&out[0], __popc(br)); if (bp) atomicAdd(&out[1], __popc(bp)); }
+}
+
+// lv.nrow / lv.nplane are known before the level exists (4 rows per marked coarse row, 2 planes per marked coarse plane: counted
+// next to the prefix sum over the marks and read back with it), so nothing here waits for the device
 static void build_rows_planes(ahfgpu_ctx *c, Level &lv)
 {
   LV v = view(lv);
   const int nc = (int)lv.ncell;
-  DevBuf<uint8_t> head; DevBuf<int> hs;
+  DevBuf<uint8_t> head; DevBuf<int> hs, bs;
   head.reserve(nc); hs.reserve(nc);
   LAUNCH(c, k_row_heads, nblk(nc, 256), 256, 0, lv.ckey, nc, v.logL, head.p);
-  lv.nrow = exclusive_scan<uint8_t>(c, head.p, hs.p, nc);
+  exclusive_scan_async<uint8_t>(c, head.p, hs.p, nc, nullptr, bs);
   lv.crow = dalloc<int32_t>(nc); lv.rowkey = dalloc<uint64_t>(lv.nrow); lv.row_c0 = dalloc<int32_t>(lv.nrow + 1);
   LAUNCH(c, k_row_fill, nblk(nc, 256), 256, 0, lv.ckey, nc, v.logL, head.p, hs.p, lv.crow, lv.rowkey, lv.row_c0, (int)lv.nrow);
   head.reserve(lv.nrow); hs.reserve(lv.nrow);
   LAUNCH(c, k_plane_heads, nblk(lv.nrow, 256), 256, 0, lv.rowkey, (int)lv.nrow, v.logL, head.p);
-  lv.nplane = exclusive_scan<uint8_t>(c, head.p, hs.p, lv.nrow);
+  exclusive_scan_async<uint8_t>(c, head.p, hs.p, lv.nrow, nullptr, bs);
   int32_t *rowplane = dalloc<int32_t>(lv.nrow);
   lv.plane_r0 = dalloc<int32_t>(lv.nplane + 1);
   LAUNCH(c, k_plane_fill, nblk(lv.nrow, 256), 256, 0, (int)lv.nrow, head.p, hs.p, rowplane, lv.plane_r0, (int)lv.nplane);
@@ -1338,9 +1360,8 @@ static void build_rows_planes(ahfgpu_ctx *c, Level &lv)
   lv.row_tested = dalloc<uint8_t>(lv.nrow);
   LAUNCH(c, k_row_tested, nblk(lv.nrow, 256), 256, 0, lv.rowkey, lv.plane_r0, rowplane, rq0, rq1, pp0, pp1, (int)lv.nrow, (int)lv.nplane,
          (long long)lv.L, v.logL, lv.row_tested);
-  CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  ahf::dfree(rq0); ahf::dfree(rq1); ahf::dfree(pp0); ahf::dfree(pp1); ahf::dfree(pz);
-  head.release(); hs.release();
+  ahf::dfree(rq0); ahf::dfree(rq1); ahf::dfree(pp0); ahf::dfree(pp1); ahf::dfree(pz);      // stream-ordered block cache: no host sync needed
+  head.release(); hs.release(); bs.release();
   lv.rowplane = rowplane;
 }
 
@@ -1509,7 +1530,19 @@ void amr_build(ahfgpu_ctx *c)
       DevBuf<uint8_t> flag;
       flag.reserve(nc); S.reserve(nc);
       LAUNCH(c, k_nonzero, nblk(nc, 256), 256, 0, cur.mark, nc, flag.p);
-      M = exclusive_scan<uint8_t>(c, flag.p, S.p, nc);
+      int h3[3] = { 0, 0, 0 };
+      {
+        DevBuf<int> t3, bs;
+        t3.reserve(4);
+        CUDA_CHECK(cudaMemsetAsync(t3.p, 0, 4 * sizeof(int), c->stream));
+        exclusive_scan_async<uint8_t>(c, flag.p, S.p, nc, t3.p, bs);
+        const int cnrow = cur.dense ? (int)(cur.L * cur.L) : (int)cur.nrow, cnplane = cur.dense ? (int)cur.L : (int)cur.nplane;
+        LAUNCH(c, k_count_marked, nblk(cnrow, 256), 256, 0, cv, S.p, t3.p, cur.row_c0, cur.plane_r0, cnrow, cnplane, t3.p + 1);
+        CUDA_CHECK(cudaMemcpyAsync(h3, t3.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        t3.release(); bs.release();
+      }
+      M = h3[0];
       flag.release();
       if (M == 0) { S.release(); break; }                             // refine_grid returned FALSE
       if ((long long)M * 8 > 2000000000ll) AHF_FAIL("refinement level exceeds 2^31 cells");
@@ -1563,6 +1596,7 @@ void amr_build(ahfgpu_ctx *c)
         if (!refcnt.count(lev + 1)) refcnt[lev + 1] = h[1];
         nb2.release(); in2.release(); out.release();
       }
+      f.nrow = 4ll * h3[1]; f.nplane = 2ll * h3[2];               // every marked coarse cell spawns 2x2x2 children
       build_rows_planes(c, f);
       c->levels.push_back(f);
     }

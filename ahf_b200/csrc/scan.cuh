@@ -129,15 +129,98 @@ static __global__ void __launch_bounds__(1024) k_sc_small(int *__restrict__ a, u
   for (uint64_t i = b; i < e; i++) { int x = a[i]; a[i] = run; run += x; }
 }
 
+// Single-pass scan (chained scan with decoupled look-back): one launch instead of reduce + scan of block sums + downsweep.  The path
+// runs ~50 device-wide scans per pass, most of them over short arrays where launch latency is the cost.  Tiles are handed out by
+// an atomic ticket, so a tile only ever waits for tiles that already run; per-tile state = (flag << 32 | value) in one 64-bit word
+// (1: aggregate of the tile, 2: inclusive prefix up to and including the tile).  The state array lives in the context, starts
+// zeroed and is zeroed again by the last tile to finish, so no memset precedes the launch.  In-place use (in == out) is fine: a
+// tile reads its inputs before it writes its outputs and touches no other tile's data.
+template <typename T>
+__global__ void __launch_bounds__(SC_THREADS) k_sc_lookback(const T *in, uint64_t n, int *out, unsigned long long *__restrict__ state,
+                                                            unsigned *__restrict__ ctr, unsigned nblk, int *__restrict__ total)
+{
+  __shared__ unsigned s_bid;
+  __shared__ int      s_prefix, s_agg, s_last;
+  if (threadIdx.x == 0) s_bid = atomicAdd(&ctr[0], 1u);
+  __syncthreads();
+  const unsigned bid = s_bid;
+  const uint64_t base = (uint64_t)bid * SC_TILE + (uint64_t)threadIdx.x * SC_ITEMS;
+  int v[SC_ITEMS], s = 0;
+  sc_load_items(in, base, n, v);
+#pragma unroll
+  for (int i = 0; i < SC_ITEMS; i++) s += v[i];
+  int ex = block_exclusive_scan(s);
+  if (threadIdx.x == SC_THREADS - 1) s_agg = ex + s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int agg = s_agg;
+    int prefix = 0;
+    if (bid == 0) {
+      if (threadIdx.x == 0) atomicExch(&state[0], (2ull << 32) | (unsigned)agg);
+    } else {
+      if (threadIdx.x == 0) atomicExch(&state[bid], (1ull << 32) | (unsigned)agg);
+      long long j0 = (long long)bid - 1;                      // window [j0-31, j0], lane q looks at j0 - q
+      for (;;) {
+        const long long j = j0 - (long long)threadIdx.x;
+        unsigned long long st = 2ull << 32;                   // before tile 0: prefix 0
+        if (j >= 0) { do { st = *reinterpret_cast<volatile unsigned long long *>(&state[j]); } while ((st >> 32) == 0); }
+        const unsigned isp = __ballot_sync(0xffffffffu, (st >> 32) == 2);
+        const int      first = isp ? __ffs(isp) - 1 : 32;      // nearest predecessor that already has its inclusive prefix
+        int add = ((int)threadIdx.x <= first) ? (int)(unsigned)st : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
+        prefix += add;
+        if (isp) break;
+        j0 -= 32;
+      }
+      if (threadIdx.x == 0) atomicExch(&state[bid], (2ull << 32) | (unsigned)(prefix + agg));
+    }
+    if (threadIdx.x == 0) { s_prefix = prefix; if (bid == nblk - 1 && total) *total = prefix + agg; }
+  }
+  __syncthreads();
+  ex += s_prefix;
+  if (base + SC_ITEMS <= n && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    int o[SC_ITEMS];
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; i++) { o[i] = ex; ex += v[i]; }
+    *reinterpret_cast<int4 *>(out + base) = make_int4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<int4 *>(out + base + 4) = make_int4(o[4], o[5], o[6], o[7]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; i++) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
+  }
+  // the last tile to finish leaves the state zeroed for the next scan
+  if (threadIdx.x == 0) { __threadfence(); s_last = (atomicAdd(&ctr[1], 1u) == nblk - 1) ? 1 : 0; }
+  __syncthreads();
+  if (s_last) {
+    for (unsigned i = threadIdx.x; i < nblk; i += SC_THREADS) state[i] = 0ull;
+    if (threadIdx.x == 0) { ctr[0] = 0u; ctr[1] = 0u; }
+  }
+}
+
 // out[i] = sum_{j<i} in[j]; no host synchronisation; d_total (device, may be null) receives the sum
 template <typename T> void exclusive_scan_async(ahfgpu_ctx *c, const T *in, int *out, uint64_t n, int *d_total, DevBuf<int> &bs)
 {
   if (n == 0) return;
   const unsigned nblk = (unsigned)((n + SC_TILE - 1) / SC_TILE);
-  bs.reserve(nblk);
-  LAUNCH(c, (k_sc_reduce<T>), nblk, SC_THREADS, 0, in, n, bs.p);
-  LAUNCH(c, k_sc_small, 1, 1024, 0, bs.p, (uint64_t)nblk, d_total);
-  LAUNCH(c, (k_sc_down<T>), nblk, SC_THREADS, 0, in, n, bs.p, out);
+  static const bool three_phase = getenv("AHFGPU_SCAN_V1") != nullptr;       // previous form (A/B timing)
+  if (three_phase) {
+    bs.reserve(nblk);
+    LAUNCH(c, (k_sc_reduce<T>), nblk, SC_THREADS, 0, in, n, bs.p);
+    LAUNCH(c, k_sc_small, 1, 1024, 0, bs.p, (uint64_t)nblk, d_total);
+    LAUNCH(c, (k_sc_down<T>), nblk, SC_THREADS, 0, in, n, bs.p, out);
+    return;
+  }
+  if ((size_t)nblk + 2 > c->scan_cap) {                                       // grow the (zeroed) look-back state
+    if (c->scan_state) ahf::dfree(c->scan_state);
+    size_t cap = 4096; while (cap < (size_t)nblk + 2) cap <<= 1;
+    c->scan_state = static_cast<unsigned long long *>(ahf::cache_alloc(cap * sizeof(unsigned long long)));
+    CUDA_CHECK(cudaMemsetAsync(c->scan_state, 0, cap * sizeof(unsigned long long), c->stream));
+    c->scan_cap = cap;
+  }
+  // the two counters sit in the last word of the state array
+  unsigned *ctr = reinterpret_cast<unsigned *>(c->scan_state + (c->scan_cap - 1));
+  LAUNCH(c, (k_sc_lookback<T>), nblk, SC_THREADS, 0, in, n, out, c->scan_state, ctr, nblk, d_total);
 }
 
 // out[i] = sum_{j<i} in[j]; returns the total (synchronises the stream)
