@@ -1892,9 +1892,11 @@ __global__ void k_members_out(const int64_t *__restrict__ moff0, const int64_t *
 // Halo-local particle copies.  After the radial sort the members of a halo are in radius order, i.e. scattered over the key-sorted
 // particle arrays, and every sweep of the unbinding / profile kernels would gather pos4/mom4 through them (32 random bytes per
 // member per sweep, ten to twenty sweeps).  The gathered members are copied ONCE into arrays in member order and the member lists
-// are renumbered to positions in those arrays (gid keeps the particle offsets for the output): the kernels are unchanged -- they
-// still index pos[members[j]] -- but consecutive members are now consecutive addresses, also after unbound members are removed
-// (the survivors stay in increasing order).
+// are renumbered to positions in those arrays (gid keeps the particle offsets): the kernels are unchanged -- they still index
+// pos[members[j]] -- but consecutive members are now consecutive addresses, also after unbound members are removed (the survivors
+// stay in increasing order).  Only the unbinding uses the copies (1.1e7-member host: 155 -> 135 ms); the profile pass reads every
+// member once and is faster on the shared particle arrays, which overlapping haloes keep in L2 (15.6 vs 20.5 ms), so the lists are
+// translated back before it.
 __global__ void k_localize_members(const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, uint32_t *__restrict__ members, uint64_t tot,
                                    float4 *__restrict__ hpos, float4 *__restrict__ hmom, uint32_t *__restrict__ gid)
 {
@@ -1902,6 +1904,11 @@ __global__ void k_localize_members(const float4 *__restrict__ pos4, const float4
   if (j >= tot) return;
   const uint32_t p = members[j];
   hpos[j] = pos4[p]; hmom[j] = mom4[p]; gid[j] = p; members[j] = (uint32_t)j;
+}
+__global__ void k_globalize_members(uint32_t *__restrict__ members, uint64_t tot, const uint32_t *__restrict__ gid)
+{
+  const uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (j < tot) members[j] = gid[members[j]];
 }
 
 // exclusive scan of int64 on the host (nhalo-sized arrays; halos are few compared with particles)
@@ -2237,6 +2244,11 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
     int64_t tw = 0;
     unbind_cooperative(c, nhalo, P, d_ctr, d_moff0, moff0, d_ng, h_ng, d_members, tot_g, d_np, h_np, &tw);
     c->stage_cnt_extra["halo_unbind_iter_members"] = tw;
+  }
+  if (d_gid) {                                          // back to particle offsets and the shared particle arrays
+    LAUNCH(c, k_globalize_members, nblk(tot_g, 256), 256, 0, d_members, (uint64_t)tot_g, d_gid);
+    c->pos4 = swap_back.p; c->mom4 = swap_back.m;
+    ahf::dfree(hpos); ahf::dfree(hmom); ahf::dfree(d_gid); hpos = hmom = nullptr; d_gid = nullptr;
   }
   // offsets of the final member lists, profile bins and scratch
   std::vector<int64_t> h_nb(nhalo), h_sc(nhalo);

@@ -68,6 +68,45 @@ AHF_HD uint64_t hilbert_index(uint32_t cx, uint32_t cy, uint32_t cz, unsigned bi
   return index;
 }
 
+// ---- table-driven form for bits == 21 (the particle keys): three levels per look-up.
+// The loop above is a finite automaton: state = (rot, flip) with flip in {0, 1<<prev_rot}: 12 states; input = the 3 transformed
+// bits of a level.  hil_tab3[state * 512 + 9 input bits] = 9 index bits | next state << 9 (built once on the host with the very
+// step code above, hilbert_build_tab3).  Seven look-ups replace 21 dependent steps.
+AHF_HD unsigned hil_state(unsigned rot, unsigned flip) { return rot * 4u + (flip == 4u ? 3u : flip); }
+inline void hilbert_build_tab3(uint16_t *tab /* [12 * 512] */)
+{
+  for (unsigned s = 0; s < 12; s++)
+    for (unsigned in = 0; in < 512; in++) {
+      unsigned rot = s >> 2, fc = s & 3u, flip = fc == 3u ? 4u : fc, out = 0;
+      for (int lv = 2; lv >= 0; lv--) {
+        unsigned g = (in >> (3 * lv)) & 7u;
+        g ^= flip;
+        g = ((g >> rot) | (g << (3 - rot))) & 7u;
+        out = (out << 3) | g;
+        flip = 1u << rot;
+        rot = hil_next_rot(rot, g);
+      }
+      tab[s * 512 + in] = (uint16_t)(out | (hil_state(rot, flip) << 9));
+    }
+}
+AHF_HD uint64_t hilbert_index21_tab(uint32_t cx, uint32_t cy, uint32_t cz, const uint16_t *tab)
+{
+  uint64_t inter = spread3(cx) | (spread3(cy) << 1) | (spread3(cz) << 2);
+  inter ^= inter >> 3;
+  uint64_t index = 0;
+  unsigned st = 0;
+#pragma unroll
+  for (int b = 54; b >= 0; b -= 9) {
+    const unsigned e = tab[st * 512u + ((unsigned)(inter >> b) & 511u)];
+    index = (index << 9) | (e & 511u);
+    st = e >> 9;
+  }
+  index ^= 0x4924924924924924ull & ((1ull << 60) - 1ull);
+#pragma unroll
+  for (unsigned j = 1; j < 63; j <<= 1) index ^= index >> j;
+  return index;
+}
+
 // inverse: integer cell of an index
 AHF_HD void hilbert_coords(uint64_t index, unsigned bits, uint32_t &cx, uint32_t &cy, uint32_t &cz)
 {
@@ -111,6 +150,16 @@ AHF_HD uint64_t hilbert_key_pos(float x, float y, float z, unsigned bits)
   if (c1 == top) c1 = top - 1;
   if (c2 == top) c2 = top - 1;
   return hilbert_index(c0, c1, c2, bits);
+}
+AHF_HD uint64_t hilbert_key_pos21_tab(float x, float y, float z, const uint16_t *tab)
+{
+  const float    mx = 2097152.0f;
+  const uint32_t top = 1u << 21;
+  uint32_t c0 = (uint32_t)(int32_t)(x * mx), c1 = (uint32_t)(int32_t)(y * mx), c2 = (uint32_t)(int32_t)(z * mx);
+  if (c0 == top) c0 = top - 1;
+  if (c1 == top) c1 = top - 1;
+  if (c2 == top) c2 = top - 1;
+  return hilbert_index21_tab(c0, c1, c2, tab);
 }
 
 }  // namespace ahf
