@@ -233,8 +233,9 @@ template <bool SPARSE>
 __global__ void __launch_bounds__(DT_THREADS, 3)
 k_deposit_tiles(const float4 *__restrict__ pos4, const int32_t *__restrict__ tstart, const int2 *__restrict__ work, int L, int logL, int tbits,
                 unsigned long long *__restrict__ acc, const uint32_t *__restrict__ tlist, const int32_t *__restrict__ pcell, LV lvw,
-                const int32_t *__restrict__ nbr, float fxs)
+                const int32_t *__restrict__ nbr, float fxs, const int *__restrict__ Wp)
 {
+  if ((int)blockIdx.x >= *Wp) return;                  // the grid is an upper bound of the work list (no host read-back of its length)
   extern __shared__ __align__(16) unsigned char dsm[];
   float4   *sp   = reinterpret_cast<float4 *>(dsm);                            // two stages of DT_SUB positions
   uint32_t *tile = reinterpret_cast<uint32_t *>(dsm + 2 * DT_SUB * 16);        // low 32 bits of the fixed-point sums
@@ -449,8 +450,9 @@ constexpr int DR_SMEM    = 2 * DT_HH * 4 + DT_HH * 2 + 16;       // low words | 
 __global__ void __launch_bounds__(DR_THREADS, 3)
 k_deposit_runs(const float4 *__restrict__ lpos, const int32_t *__restrict__ tstart, const int2 *__restrict__ work, int L, int logL, int tbits,
                unsigned long long *__restrict__ acc, const uint32_t *__restrict__ tlist, const int32_t *__restrict__ pcell, LV lvw,
-               const int32_t *__restrict__ nbr, float fxs)
+               const int32_t *__restrict__ nbr, float fxs, const int *__restrict__ Wp)
 {
+  if ((int)blockIdx.x >= *Wp) return;                  // the grid is an upper bound of the work list
   extern __shared__ __align__(16) unsigned char dsm[];
   uint32_t *tile = reinterpret_cast<uint32_t *>(dsm);
   uint32_t *tcar = tile + DT_HH;
@@ -635,9 +637,11 @@ __constant__ uint16_t c_dom_off[27];     // byte offset of term (k,j,a) inside t
 
 template <int VAR>      // 0 = product; 1..4 = timing experiments (AHFGPU_DOM_VARIANT): 1 no return/carry, 2 no atomics, 3 no flush, 4 one copy
 __global__ void __launch_bounds__(DT_THREADS, 2)
-k_deposit_dom(const float4 *__restrict__ pos4, const int4 *__restrict__ work, int W, int L, int logL,
+k_deposit_dom(const float4 *__restrict__ pos4, const int4 *__restrict__ work, const int *__restrict__ Wp, int L, int logL,
               unsigned long long *__restrict__ acc, const uint32_t one /* == 1, a run-time value on purpose: see dom_carry */, const int rmax)
 {
+  const int W = *Wp;                                   // the grid is an upper bound of the work list (no host read-back of its length)
+  if ((int)blockIdx.x >= W) return;
   extern __shared__ __align__(16) unsigned char dsm[];
   float4   *sp   = reinterpret_cast<float4 *>(dsm);
   uint32_t *tile = reinterpret_cast<uint32_t *>(dsm + DD_NS * DT_SUB * 16);        // copy A | copy B | carry counters
@@ -1420,9 +1424,9 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
     nchunk.reserve(ntile); woff.reserve(ntile);
     LAUNCH(c, k_tile_nchunk, nblk(ntile, 256), 256, 0, tstart.p, ntile, nchunk.p);
     exclusive_scan_async<int>(c, nchunk.p, woff.p, ntile, tot.p, bs);
-    int W = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&W, tot.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    // the work list has at most one entry per tile plus one per full chunk: launch that many CTAs, the kernels read the real
+    // length from the device (no host read-back)
+    const int W = ntile + (int)(lv.npart_dep / DT_CHUNK) + 1;
     work.reserve(W);
     LAUNCH(c, k_tile_work, nblk(ntile, 256), 256, 0, nchunk.p, woff.p, ntile, work.p);
     {
@@ -1440,21 +1444,21 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
         // AHFGPU_DOM_PERSIST=1: two persistent CTAs per SM striding over the items (measured slower: static striding loses the
         // hardware's dynamic balance between light and heavy tiles); default: one CTA per item
         const unsigned grid = getenv("AHFGPU_DOM_PERSIST") ? (unsigned)std::min(W, 2 * nsm) : (unsigned)W;
-#define DOM_LAUNCH(V) LAUNCH(c, k_deposit_dom<V>, grid, DT_THREADS, DD_SMEM, c->pos4, work4.p, W, (int)lv.L, v.logL, acc.p, 1u, rmax)
+#define DOM_LAUNCH(V) LAUNCH(c, k_deposit_dom<V>, grid, DT_THREADS, DD_SMEM, c->pos4, work4.p, tot.p, (int)lv.L, v.logL, acc.p, 1u, rmax)
         if (var == 1) DOM_LAUNCH(1); else if (var == 2) DOM_LAUNCH(2); else if (var == 3) DOM_LAUNCH(3); else if (var == 4) DOM_LAUNCH(4); else DOM_LAUNCH(0);
 #undef DOM_LAUNCH
       }
       else if (tiles_dense)
         LAUNCH(c, k_deposit_tiles<false>, (unsigned)W, DT_THREADS, DT_SMEM, c->pos4, tstart.p, work.p, (int)lv.L, v.logL, tbits, acc.p,
-               (const uint32_t *)nullptr, (const int32_t *)nullptr, v, (const int32_t *)nullptr, (float)fxscale);
+               (const uint32_t *)nullptr, (const int32_t *)nullptr, v, (const int32_t *)nullptr, (float)fxscale, tot.p);
       else if (getenv("AHFGPU_SPARSE_V1") || (!getenv("AHFGPU_SPARSE_V2") && (double)lv.npart_dep < 0.75 * (double)lv.ncell))
         // lane per particle: the thin tiles of the deepest levels (well under one particle per cell, a few hundred particles per
         // tile) have no runs to aggregate and want the larger CTA for the tile flush (measured: 0.23 vs 0.31 ms on level 6)
         LAUNCH(c, k_deposit_tiles<true>, (unsigned)W, DT_THREADS, DT_SMEM, lv.lpos, tstart.p, work.p, (int)lv.L, v.logL, tbits, acc.p,
-               tlist.p, lv.pcell, v, lv.nbr, (float)fxscale);
+               tlist.p, lv.pcell, v, lv.nbr, (float)fxscale, tot.p);
       else
         LAUNCH(c, k_deposit_runs, (unsigned)W, DR_THREADS, DR_SMEM, lv.lpos, tstart.p, work.p, (int)lv.L, v.logL, tbits, acc.p,
-               tlist.p, lv.pcell, v, lv.nbr, (float)fxscale);
+               tlist.p, lv.pcell, v, lv.nbr, (float)fxscale, tot.p);
     }
     if (lv.dense) c->stage_cnt_extra["deposit_dom_ctas"] = W;
     tstart.release(); nchunk.release(); woff.release(); bs.release(); tot.release(); work.release(); work4.release(); tlist.release(); head.release(); hs.release();
