@@ -78,7 +78,7 @@ struct Level {
   int32_t  *nbr = nullptr;      // [27][ncell] (term-major) visible neighbour cell index or -1 (sparse levels)
   int32_t  *crow = nullptr;     // [ncell] row index                             (sparse levels)
   int32_t  *count = nullptr;    // [ncell] particles linked when deposited
-  uint64_t *hkey = nullptr; int32_t *hval = nullptr; uint64_t hmask = 0;   // open addressing hash
+  uint64_t *hkey = nullptr; int32_t *hval = nullptr; uint64_t hmask = 0;   // open addressing hash: block key | (first cell, occupancy mask)
   // parent/child links between consecutive levels: cells of the next level are found through them, not through the hash
   int32_t  *parent = nullptr;   // [ncell] cell of the coarser level this cell is a child of      (sparse levels)
   int32_t  *cidx = nullptr;     // [ncell] -1: no children; else slot in cbase | 0x40000000 when the children are a ghost pair

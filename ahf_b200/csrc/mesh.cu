@@ -27,7 +27,7 @@ struct LV {
   const uint64_t *ckey;
   const uint8_t  *xbreak;
   const uint64_t *hkey;
-  const int32_t  *hval;
+  const uint2    *hval;          // per slot: index of the block's first existing cell, 8-bit occupancy mask
   uint64_t        hmask;
 };
 
@@ -35,7 +35,7 @@ static LV view(const Level &l)
 {
   LV v; v.L = l.L; v.ncell = (int)l.ncell; v.dense = l.dense ? 1 : 0;
   v.logL = 0; while ((1ll << v.logL) < l.L) v.logL++;
-  v.ckey = l.ckey; v.xbreak = l.xbreak; v.hkey = l.hkey; v.hval = l.hval; v.hmask = l.hmask;
+  v.ckey = l.ckey; v.xbreak = l.xbreak; v.hkey = l.hkey; v.hval = reinterpret_cast<const uint2 *>(l.hval); v.hmask = l.hmask;
   return v;
 }
 
@@ -54,8 +54,14 @@ __device__ __forceinline__ uint64_t lv_key(const LV &v, int x, int y, int z)
   return (((uint64_t)z << v.logL) | (uint64_t)y) << v.logL | (uint64_t)x;
 }
 // geometric lookup without periodic wrap: -1 when (x,y,z) is not a cell of the level.
-// The hash is keyed on blocks of 8 x-consecutive cells (key >> 3): one 8-byte key and eight 4-byte cell indices per slot, so that
-// the lookups of a warp walking along a row share a few 32-byte sectors instead of touching 32 random ones.
+// The hash is keyed on blocks of 8 x-consecutive cells (key >> 3), so that the lookups of a warp walking along a row share a few
+// sectors instead of touching 32 random ones.  The cells of a block sit in one row, i.e. they are consecutive in the sorted cell
+// array: a slot holds the block key (8 B), the index of the block's first existing cell and an occupancy mask (8 B) -- 16 bytes
+// per slot to clear and probe instead of 40 with eight explicit indices.
+__device__ __forceinline__ int slot_cell(const uint2 bm, unsigned b)
+{
+  return ((bm.y >> b) & 1u) ? (int)bm.x + __popc(bm.y & ((1u << b) - 1u)) : -1;
+}
 __device__ __forceinline__ int lv_lookup(const LV &v, int x, int y, int z)
 {
   if ((unsigned)x >= (unsigned)v.L || (unsigned)y >= (unsigned)v.L || (unsigned)z >= (unsigned)v.L) return -1;
@@ -65,7 +71,7 @@ __device__ __forceinline__ int lv_lookup(const LV &v, int x, int y, int z)
   uint64_t s = mix64(kb) & v.hmask;
   for (;;) {
     uint64_t hk = v.hkey[s];
-    if (hk == kb) return v.hval[s * 8 + (k & 7)];
+    if (hk == kb) return slot_cell(v.hval[s], (unsigned)(k & 7));
     if (hk == ~0ull) return -1;
     s = (s + 1) & v.hmask;
   }
@@ -407,7 +413,7 @@ k_deposit_tiles(const float4 *__restrict__ pos4, const int32_t *__restrict__ tst
         const uint64_t kb = kq[q] >> 3;
         uint64_t s = sq[q], hk = hq[q];
         while (hk != kb && hk != ~0ull) { s = (s + 1) & lvw.hmask; hk = lvw.hkey[s]; }
-        tg[q] = (iq[q] >= 0 && hk == kb) ? lvw.hval[s * 8 + (kq[q] & 7)] : -1;    // particles sit on interior nodes: every touched cell exists
+        tg[q] = (iq[q] >= 0 && hk == kb) ? slot_cell(lvw.hval[s], (unsigned)(kq[q] & 7)) : -1;    // particles sit on interior nodes: every touched cell exists
       }
 #pragma unroll
       for (int q = 0; q < 4; q++)
@@ -588,7 +594,7 @@ k_deposit_runs(const float4 *__restrict__ lpos, const int32_t *__restrict__ tsta
       const uint64_t kb = kq[q] >> 3;
       uint64_t s = sq[q], hk = hq[q];
       while (hk != kb && hk != ~0ull) { s = (s + 1) & lvw.hmask; hk = lvw.hkey[s]; }
-      tg[q] = (iq[q] >= 0 && hk == kb) ? lvw.hval[s * 8 + (kq[q] & 7)] : -1;      // particles sit on interior nodes: every touched cell exists
+      tg[q] = (iq[q] >= 0 && hk == kb) ? slot_cell(lvw.hval[s], (unsigned)(kq[q] & 7)) : -1;      // particles sit on interior nodes: every touched cell exists
     }
 #pragma unroll
     for (int q = 0; q < 4; q++)
@@ -1040,12 +1046,12 @@ __global__ void k_make_children(LV v, const uint8_t *__restrict__ mark, const in
   cbase[S[c]] = make_int4(cb[0], cb[1], cb[2], cb[3]);
 }
 
-__global__ void k_hash_clear(uint64_t *__restrict__ hkey, int4 *__restrict__ hval8, uint64_t cap)
+__global__ void k_hash_clear(uint64_t *__restrict__ hkey, uint2 *__restrict__ hval, uint64_t cap)
 {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i < cap) { hkey[i] = ~0ull; hval8[2 * i] = make_int4(-1, -1, -1, -1); hval8[2 * i + 1] = make_int4(-1, -1, -1, -1); }
+  if (i < cap) { hkey[i] = ~0ull; hval[i] = make_uint2(0x7fffffffu, 0u); }
 }
-__global__ void k_hash_insert(const uint64_t *__restrict__ ckey, int ncell, uint64_t *__restrict__ hkey, int32_t *__restrict__ hval, uint64_t hmask)
+__global__ void k_hash_insert(const uint64_t *__restrict__ ckey, int ncell, uint64_t *__restrict__ hkey, uint2 *__restrict__ hval, uint64_t hmask)
 {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncell) return;
@@ -1053,7 +1059,7 @@ __global__ void k_hash_insert(const uint64_t *__restrict__ ckey, int ncell, uint
   uint64_t s = mix64(kb) & hmask;
   for (;;) {
     unsigned long long old = atomicCAS((unsigned long long *)&hkey[s], ~0ull, (unsigned long long)kb);
-    if (old == ~0ull || old == kb) { hval[s * 8 + (k & 7)] = c; return; }
+    if (old == ~0ull || old == kb) { atomicMin(reinterpret_cast<int *>(&hval[s].x), c); atomicOr(&hval[s].y, 1u << (unsigned)(k & 7)); return; }
     s = (s + 1) & hmask;
   }
 }
@@ -1119,7 +1125,7 @@ __global__ void k_neighbours(LV v, int32_t *__restrict__ nbr, uint8_t *__restric
     sq[q] = s; hq[q] = hk;
   }
 #pragma unroll
-  for (int q = 0; q < 9; q++) if (q != 4) rowc[q] = (hq[q] == (kq[q] >> 3)) ? v.hval[sq[q] * 8 + (kq[q] & 7)] : -1;
+  for (int q = 0; q < 9; q++) if (q != 4) rowc[q] = (hq[q] == (kq[q] >> 3)) ? slot_cell(v.hval[sq[q]], (unsigned)(kq[q] & 7)) : -1;
   bool all = true;
 #pragma unroll
   for (int k = 0; k < 3; k++) {
@@ -1563,9 +1569,9 @@ void amr_build(ahfgpu_ctx *c)
       // hash
       // slots hold 8 x-consecutive cells; children come in x-pairs, so there are at most ncell/2 occupied slots
       uint64_t cap = 16; while (cap < (uint64_t)f.ncell + 2) cap <<= 1;
-      f.hmask = cap - 1; f.hkey = dalloc<uint64_t>(cap); f.hval = dalloc<int32_t>(cap * 8);
-      LAUNCH(c, k_hash_clear, nblk(cap, 256), 256, 0, f.hkey, reinterpret_cast<int4 *>(f.hval), cap);
-      LAUNCH(c, k_hash_insert, nblk(f.ncell, 256), 256, 0, f.ckey, (int)f.ncell, f.hkey, f.hval, f.hmask);
+      f.hmask = cap - 1; f.hkey = dalloc<uint64_t>(cap); f.hval = dalloc<int32_t>(cap * 2);
+      LAUNCH(c, k_hash_clear, nblk(cap, 256), 256, 0, f.hkey, reinterpret_cast<uint2 *>(f.hval), cap);
+      LAUNCH(c, k_hash_insert, nblk(f.ncell, 256), 256, 0, f.ckey, (int)f.ncell, f.hkey, reinterpret_cast<uint2 *>(f.hval), f.hmask);
       alloc_cell_arrays(f);
       f.interior = dalloc<uint8_t>(f.ncell); f.nbr = dalloc<int32_t>((size_t)f.ncell * 27);
       LV fv = view(f);

@@ -79,3 +79,45 @@ def swz(x, y, z, l, copies=1):
 
 wavefronts(lambda x, y, z, l: swz(x, y, z, l, 1), "4x4x4 block xor swizzle, one copy")
 wavefronts(lambda x, y, z, l: swz(x, y, z, l, 2), "4x4x4 block xor swizzle, lane-parity xor 16")
+
+
+# ---- model of a run-aggregating domain kernel: thread = K consecutive particles, registers flushed when the cell changes
+def runs_model(K, threads=512):
+    tot_iter = tot_flush_exec = tot_flush_lanes = tot_wf = 0
+    npart = 0
+    for t in sel:
+        s, e = starts[t], ends[t]
+        for c0 in range(s, e, 8192):
+            c1 = min(e, c0 + 8192)
+            n = c1 - c0
+            wid = ((lz[c0:c1] * H + ly[c0:c1]) * H + lx[c0:c1]).astype(np.int64)
+            npart += n
+            # segments of K per thread; warp = 32 consecutive threads
+            nseg = (n + K - 1) // K
+            pad = nseg * K - n
+            w = np.concatenate([wid, np.full(pad, -1)]).reshape(nseg, K)
+            nwarp = (nseg + 31) // 32
+            w = np.concatenate([w, np.full((nwarp * 32 - nseg, K), -1)]).reshape(nwarp, 32, K)
+            prev = np.full((nwarp, 32), -1)
+            for i in range(K + 1):
+                cur = w[:, :, i] if i < K else np.full((nwarp, 32), -1)
+                flush = (prev >= 0) & (cur != prev)                 # lanes that flush prev before taking particle i
+                anyf = flush.any(1)
+                tot_flush_exec += int(anyf.sum())
+                tot_flush_lanes += int(flush.sum())
+                # wavefronts of one of the 27 flush atomics (term 0,0,0): max lanes per bank among flushing lanes
+                if anyf.any():
+                    bank = np.where(flush, prev & 31, -1)
+                    cnt = np.zeros((nwarp, 33), dtype=np.int32)
+                    np.add.at(cnt, (np.arange(nwarp)[:, None].repeat(32, 1), bank + 1), 1)
+                    tot_wf += int(cnt[:, 1:].max(1).sum())
+                if i < K:
+                    tot_iter += int((cur >= 0).any(1).sum())
+                    prev = np.where(cur >= 0, cur, prev)
+    per32 = npart / 32.0
+    print(f"K={K}: per 32 particles: accumulate iterations {tot_iter / per32:.2f}, flush executions {tot_flush_exec / per32:.2f}, "
+          f"flushing lanes per execution {tot_flush_lanes / max(tot_flush_exec, 1):.1f}, wavefronts per flush atomic {tot_wf / max(tot_flush_exec, 1):.2f}")
+
+
+for K in (1, 4, 8, 16):
+    runs_model(K)
