@@ -188,7 +188,7 @@ void sfc_sort_soa_async(ahfgpu_ctx *c, const float *pos3, const float *mom3, con
 void sfc_sort_device4(ahfgpu_ctx *c, const void *pos4_dev, const void *mom4_dev, uint64_t n, bool has_w, bool has_u);
 void sfc_keys_only(ahfgpu_ctx *c, const float *pos3, uint64_t n, uint32_t bits, uint64_t *keys_out);
 void radix_sort_pairs(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, uint64_t n,
-                      int key_bits, uint64_t **keys_sorted, uint32_t **vals_sorted);
+                      int key_bits, uint64_t **keys_sorted, uint32_t **vals_sorted, int first_bit = 0);
 void amr_build(ahfgpu_ctx *c);
 void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const double *gather_rad, const int64_t *seed);
 

@@ -228,6 +228,34 @@ __global__ void k_hid_keys(const uint32_t *__restrict__ val, const uint32_t *__r
   val2[i] = val[i];
 }
 // element e of the packed (>= min_part) layout lives at candoff[h] + (e - eoff[h]) of the candidate buffers
+// The radial sort skips the lowest `skip` bits of the r^2 keys (three of its eight passes): members whose keys agree in all the
+// sorted bits are still in gather order.  One thread per such run (a few per 10^5 members: 28 mantissa bits are sorted) puts it
+// into the order the full stable sort gives: by the whole key, then by gather position.
+__global__ void k_fix_ties(uint32_t *__restrict__ perm, const uint32_t *__restrict__ hid, const int64_t *__restrict__ candoff, const int64_t *__restrict__ eoff,
+                           const double *__restrict__ r2buf, uint64_t ne, int skip)
+{
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= ne) return;
+  auto key = [&](uint32_t e) { const uint32_t h = hid[e]; return (uint64_t)__double_as_longlong(r2buf[candoff[h] + ((int64_t)e - eoff[h])]); };
+  const uint32_t e = perm[i], h = hid[e];
+  const uint64_t top = key(e) >> skip;
+  if (i > 0) { const uint32_t p = perm[i - 1]; if (hid[p] == h && (key(p) >> skip) == top) return; }       // not the head of its run
+  uint64_t j = i + 1;
+  while (j < ne) { const uint32_t q = perm[j]; if (hid[q] != h || (key(q) >> skip) != top) break; j++; }
+  if (j - i < 2) return;
+  for (uint64_t a = i + 1; a < j; a++) {                       // insertion sort by (key, gather position)
+    const uint32_t ea = perm[a];
+    const uint64_t ka = key(ea);
+    uint64_t b = a;
+    while (b > i) {
+      const uint32_t eb = perm[b - 1];
+      const uint64_t kb = key(eb);
+      if (kb < ka || (kb == ka && eb < ea)) break;
+      perm[b] = eb; b--;
+    }
+    perm[b] = ea;
+  }
+}
 __global__ void k_apply_perm(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ hid, const int64_t *__restrict__ candoff,
                              const int64_t *__restrict__ eoff, uint64_t ne, const uint32_t *__restrict__ idxbuf, uint32_t *__restrict__ sorted_idx)
 {
@@ -2199,7 +2227,8 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
       uint32_t *v0 = dalloc<uint32_t>(tot_e), *v1 = dalloc<uint32_t>(tot_e), *hid = dalloc<uint32_t>(tot_e);
       LAUNCH(c, k_sort_setup, (unsigned)nhalo, 256, 0, d_candoff, d_ng, d_eoff, nhalo, P.min_part, d_r2, k0, v0, hid);
       uint64_t *ks; uint32_t *vs;
-      radix_sort_pairs(c, k0, v0, k1, v1, (uint64_t)tot_e, 64, &ks, &vs);
+      static const int skip = getenv("AHFGPU_HALO_SORT_SKIP") ? atoi(getenv("AHFGPU_HALO_SORT_SKIP")) : 24;     // multiple of 8, < 64; ties: k_fix_ties
+      radix_sort_pairs(c, k0, v0, k1, v1, (uint64_t)tot_e, 64, &ks, &vs, skip);
       // second, stable pass by halo index
       uint64_t *k2 = (ks == k0) ? k1 : k0; uint32_t *v2 = (vs == v0) ? v1 : v0;
       int hb = 1; while ((1ll << hb) < nhalo) hb++;
@@ -2210,6 +2239,7 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
       radix_sort_pairs(c, k2, v3, ks, v2, (uint64_t)tot_e, hb, &ks2, &vs2);
       // sorted members go to the positions eoff-packed; map back to the moff0-packed layout per halo
       uint32_t *sorted = dalloc<uint32_t>(tot_e);
+      if (skip > 0) LAUNCH(c, k_fix_ties, nblk(tot_e, 256), 256, 0, vs2, hid, d_candoff, d_eoff, d_r2, (uint64_t)tot_e, skip);
       LAUNCH(c, k_apply_perm, nblk(tot_e, 256), 256, 0, vs2, hid, d_candoff, d_eoff, (uint64_t)tot_e, d_idx, sorted);
       // scatter halo segments: eoff-layout -> moff0-layout
       LAUNCH(c, k_scatter_sorted, (unsigned)nhalo, 256, 0, d_eoff, d_moff0, sorted, d_members);

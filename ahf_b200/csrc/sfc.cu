@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t *__res
 
 template <int RS_ITEMS>
 static void radix_sort_pairs_t(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, uint64_t n,
-                               int key_bits, uint64_t **keys_sorted, uint32_t **vals_sorted)
+                               int key_bits, uint64_t **keys_sorted, uint32_t **vals_sorted, int first_bit)
 {
   const uint32_t nblk = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
   DevBuf<uint32_t> bh;
@@ -214,7 +214,7 @@ static void radix_sort_pairs_t(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, ui
   bh.reserve((size_t)256 * nblk);
   uint64_t *ki = keys, *ko = keys_tmp;
   uint32_t *vi = vals, *vo = vals_tmp;
-  for (int shift = 0; shift < key_bits; shift += 8) {
+  for (int shift = first_bit; shift < key_bits; shift += 8) {          // bits below first_bit are left to the caller (ties)
     LAUNCH(c, k_rs_hist<RS_ITEMS>, nblk, RS_THREADS, 0, ki, n, shift, bh.p, nblk);
     exclusive_scan_async<int>(c, (const int *)bh.p, (int *)bh.p, (uint64_t)256 * nblk, nullptr, bs);   // in place: each tile is read before it is written
     LAUNCH(c, k_rs_scatter<RS_ITEMS>, nblk, RS_THREADS, RS_SMEM, ki, vi, ko, vo, n, shift, bh.p, nblk);
@@ -226,13 +226,13 @@ static void radix_sort_pairs_t(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, ui
 }
 
 void radix_sort_pairs(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, uint64_t n,
-                      int key_bits, uint64_t **keys_sorted, uint32_t **vals_sorted)
+                      int key_bits, uint64_t **keys_sorted, uint32_t **vals_sorted, int first_bit)
 {
   *keys_sorted = keys; *vals_sorted = vals;
   if (n == 0) return;
   static const int items = getenv("AHFGPU_RS_ITEMS") ? atoi(getenv("AHFGPU_RS_ITEMS")) : 8;      // measured at 256^3: 1.81 ms (8) vs 2.68 ms (16): the ranking loop is latency bound, occupancy wins
-  if (items == 8) radix_sort_pairs_t<8>(c, keys, vals, keys_tmp, vals_tmp, n, key_bits, keys_sorted, vals_sorted);
-  else radix_sort_pairs_t<16>(c, keys, vals, keys_tmp, vals_tmp, n, key_bits, keys_sorted, vals_sorted);
+  if (items == 8) radix_sort_pairs_t<8>(c, keys, vals, keys_tmp, vals_tmp, n, key_bits, keys_sorted, vals_sorted, first_bit);
+  else radix_sort_pairs_t<16>(c, keys, vals, keys_tmp, vals_tmp, n, key_bits, keys_sorted, vals_sorted, first_bit);
 }
 
 // ------------------------------------------------------------------------------------------------
