@@ -243,6 +243,24 @@ __global__ void k_fix_ties(uint32_t *__restrict__ perm, const uint32_t *__restri
   uint64_t j = i + 1;
   while (j < ne) { const uint32_t q = perm[j]; if (hid[q] != h || (key(q) >> skip) != top) break; j++; }
   if (j - i < 2) return;
+  auto less = [&](uint32_t ea, uint32_t eb) { const uint64_t ka = key(ea), kb = key(eb); return ka < kb || (ka == kb && ea < eb); };
+  if (j - i > 32) {                                            // long run (thin shells, huge haloes): heap sort, O(L log L)
+    uint32_t *a = perm + i;
+    const uint64_t L = j - i;
+    auto sift = [&](uint64_t root, uint64_t end) {
+      for (;;) {
+        uint64_t ch = 2 * root + 1;
+        if (ch >= end) return;
+        if (ch + 1 < end && less(a[ch], a[ch + 1])) ch++;
+        if (!less(a[root], a[ch])) return;
+        const uint32_t t = a[root]; a[root] = a[ch]; a[ch] = t;
+        root = ch;
+      }
+    };
+    for (uint64_t st = L / 2; st-- > 0;) sift(st, L);
+    for (uint64_t end = L - 1; end > 0; end--) { const uint32_t t = a[0]; a[0] = a[end]; a[end] = t; sift(0, end); }
+    return;
+  }
   for (uint64_t a = i + 1; a < j; a++) {                       // insertion sort by (key, gather position)
     const uint32_t ea = perm[a];
     const uint64_t ka = key(ea);
@@ -2227,7 +2245,13 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
       uint32_t *v0 = dalloc<uint32_t>(tot_e), *v1 = dalloc<uint32_t>(tot_e), *hid = dalloc<uint32_t>(tot_e);
       LAUNCH(c, k_sort_setup, (unsigned)nhalo, 256, 0, d_candoff, d_ng, d_eoff, nhalo, P.min_part, d_r2, k0, v0, hid);
       uint64_t *ks; uint32_t *vs;
-      static const int skip = getenv("AHFGPU_HALO_SORT_SKIP") ? atoi(getenv("AHFGPU_HALO_SORT_SKIP")) : 24;     // multiple of 8, < 64; ties: k_fix_ties
+      // bits skipped: neighbouring r^2 of a halo with n members differ by ~1/n relative, so 52 - skip mantissa bits must resolve
+      // well below that or the tie runs grow (measured: skip 32 costs 2.7 instead of 0.85 ms at 256^3, seconds on a 1e7 host)
+      int64_t nmax = 1;
+      for (int64_t h = 0; h < nhalo; h++) nmax = std::max(nmax, h_ng[h]);
+      int lg = 0; while ((1ll << lg) < nmax) lg++;
+      int skip = 8 * ((48 - lg) / 8); skip = skip < 0 ? 0 : skip > 24 ? 24 : skip;
+      if (getenv("AHFGPU_HALO_SORT_SKIP")) skip = atoi(getenv("AHFGPU_HALO_SORT_SKIP"));                       // multiple of 8, < 64
       radix_sort_pairs(c, k0, v0, k1, v1, (uint64_t)tot_e, 64, &ks, &vs, skip);
       // second, stable pass by halo index
       uint64_t *k2 = (ks == k0) ? k1 : k0; uint32_t *v2 = (vs == v0) ? v1 : v0;
