@@ -114,3 +114,33 @@ def test_two_rank_partition_gloo(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+def test_table_driven_hilbert_index_equals_the_step_form(tmp_path, golden):
+    """hilbert.cuh is host+device code: the three-levels-per-look-up form the key kernel uses (hilbert_index21_tab) against the
+    21-step form, compiled for the host, on random cells, the box corners and the golden particle keys of the reference."""
+    src = tmp_path / "hil.cpp"
+    src.write_text('''
+#include "ahf_b200/csrc/hilbert.cuh"
+#include <cstdio>
+#include <cstdlib>
+extern "C" int hil_check(const float *pos, const unsigned long long *keys, long n) {
+  static uint16_t tab[12 * 512];
+  ahf::hilbert_build_tab3(tab);
+  unsigned long long bad = 0;
+  srand(1);
+  for (int i = 0; i < 1000000; i++) {
+    uint32_t x = rand() & 0x1fffff, y = rand() & 0x1fffff, z = rand() & 0x1fffff;
+    if (i < 8) { x = (i & 1) ? 0x1fffff : 0; y = (i & 2) ? 0x1fffff : 0; z = (i & 4) ? 0x1fffff : 0; }
+    if (ahf::hilbert_index(x, y, z, 21) != ahf::hilbert_index21_tab(x, y, z, tab)) bad++;
+  }
+  for (long i = 0; i < n; i++) if (ahf::hilbert_key_pos21_tab(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], tab) != keys[i]) bad++;
+  return (int)(bad > 1000000 ? 1000000 : bad);
+}
+''')
+    so = tmp_path / "hil.so"
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", "-I", ROOT, "-o", str(so), str(src)])
+    L = C.CDLL(str(so))
+    L.hil_check.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
+    pos = np.ascontiguousarray(golden.pos, np.float32); keys = np.ascontiguousarray(golden.keys, np.uint64)
+    assert L.hil_check(pos.ctypes.data, keys.ctypes.data, len(keys)) == 0
