@@ -1051,15 +1051,27 @@ __global__ void k_hash_clear(uint64_t *__restrict__ hkey, uint2 *__restrict__ hv
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i < cap) { hkey[i] = ~0ull; hval[i] = make_uint2(0x7fffffffu, 0u); }
 }
+// one insertion per block of 8 x-consecutive cells: the block's cells are consecutive in the sorted cell array, so the thread of
+// the block's first existing cell collects the occupancy mask from its (at most 7) successors and claims the slot -- one CAS and
+// one 8-byte store per block instead of three atomics per cell
 __global__ void k_hash_insert(const uint64_t *__restrict__ ckey, int ncell, uint64_t *__restrict__ hkey, uint2 *__restrict__ hval, uint64_t hmask)
 {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncell) return;
   const uint64_t k = ckey[c], kb = k >> 3;
+  if (c > 0 && (ckey[c - 1] >> 3) == kb) return;
+  uint32_t mask = 1u << (unsigned)(k & 7);
+#pragma unroll
+  for (int j = 1; j < 8; j++) {
+    if (c + j >= ncell) break;
+    const uint64_t kj = ckey[c + j];
+    if ((kj >> 3) != kb) break;
+    mask |= 1u << (unsigned)(kj & 7);
+  }
   uint64_t s = mix64(kb) & hmask;
   for (;;) {
     unsigned long long old = atomicCAS((unsigned long long *)&hkey[s], ~0ull, (unsigned long long)kb);
-    if (old == ~0ull || old == kb) { atomicMin(reinterpret_cast<int *>(&hval[s].x), c); atomicOr(&hval[s].y, 1u << (unsigned)(k & 7)); return; }
+    if (old == ~0ull) { hval[s] = make_uint2((uint32_t)c, mask); return; }
     s = (s + 1) & hmask;
   }
 }
@@ -1570,7 +1582,7 @@ void amr_build(ahfgpu_ctx *c)
       // slots hold 8 x-consecutive cells; children come in x-pairs, so there are at most ncell/2 occupied slots
       uint64_t cap = 16; while (cap < (uint64_t)f.ncell + 2) cap <<= 1;
       f.hmask = cap - 1; f.hkey = dalloc<uint64_t>(cap); f.hval = dalloc<int32_t>(cap * 2);
-      LAUNCH(c, k_hash_clear, nblk(cap, 256), 256, 0, f.hkey, reinterpret_cast<uint2 *>(f.hval), cap);
+      CUDA_CHECK(cudaMemsetAsync(f.hkey, 0xff, cap * sizeof(uint64_t), c->stream));          // empty slots: key ~0 (values are only read behind a key match)
       LAUNCH(c, k_hash_insert, nblk(f.ncell, 256), 256, 0, f.ckey, (int)f.ncell, f.hkey, reinterpret_cast<uint2 *>(f.hval), f.hmask);
       alloc_cell_arrays(f);
       f.interior = dalloc<uint8_t>(f.ncell); f.nbr = dalloc<int32_t>((size_t)f.ncell * 27);
