@@ -909,22 +909,18 @@ __device__ __forceinline__ void run_offsets(bool wrapped, long long r0, long lon
   }
 }
 
-// one thread per plane: y-run (cquad) bounds of every row of the plane, as row indices [q0,q1)
-__global__ void k_row_runs(const uint64_t *__restrict__ rowkey, const int32_t *__restrict__ plane_r0, int nplane,
+// y-run (cquad) bounds of every row as row indices [q0,q1): one thread per row walks to both ends of its run inside its plane
+// (runs are a few tens of rows; one thread per PLANE walking all its rows left most of the GPU idle)
+__global__ void k_row_runs(const uint64_t *__restrict__ rowkey, const int32_t *__restrict__ plane_r0, const int32_t *__restrict__ rowplane, int nrow,
                            int32_t *__restrict__ rq0, int32_t *__restrict__ rq1)
 {
-  int P = blockIdx.x * blockDim.x + threadIdx.x;
-  if (P >= nplane) return;
-  int r0 = plane_r0[P], r1 = plane_r0[P + 1], start = r0;
-  for (int r = r0; r < r1; r++) {
-    if (r > r0 && rowkey[r] != rowkey[r - 1] + 1) start = r;
-    rq0[r] = start;
-  }
-  int end = r1;
-  for (int r = r1 - 1; r >= r0; r--) {
-    if (r < r1 - 1 && rowkey[r + 1] != rowkey[r] + 1) end = r + 1;
-    rq1[r] = end;
-  }
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrow) return;
+  const int P = rowplane[r], r0 = plane_r0[P], r1 = plane_r0[P + 1];
+  int a = r, b = r + 1;
+  while (a > r0 && rowkey[a - 1] + 1 == rowkey[a]) a--;
+  while (b < r1 && rowkey[b] == rowkey[b - 1] + 1) b++;
+  rq0[r] = a; rq1[r] = b;
 }
 
 // z-run (pquad) bounds of every plane as plane indices [p0,p1): one thread per plane walks to the ends of its run
@@ -1375,7 +1371,7 @@ static void build_rows_planes(ahfgpu_ctx *c, Level &lv)
   LAUNCH(c, k_plane_fill, nblk(lv.nrow, 256), 256, 0, (int)lv.nrow, head.p, hs.p, rowplane, lv.plane_r0, (int)lv.nplane);
   // run bounds + tested rows
   int32_t *rq0 = dalloc<int32_t>(lv.nrow), *rq1 = dalloc<int32_t>(lv.nrow), *pp0 = dalloc<int32_t>(lv.nplane), *pp1 = dalloc<int32_t>(lv.nplane);
-  LAUNCH(c, k_row_runs, nblk(lv.nplane, 128), 128, 0, lv.rowkey, lv.plane_r0, (int)lv.nplane, rq0, rq1);
+  LAUNCH(c, k_row_runs, nblk(lv.nrow, 256), 256, 0, lv.rowkey, lv.plane_r0, rowplane, (int)lv.nrow, rq0, rq1);
   int32_t *pz = dalloc<int32_t>(lv.nplane);
   LAUNCH(c, k_plane_z, nblk(lv.nplane, 128), 128, 0, lv.rowkey, lv.plane_r0, (int)lv.nplane, v.logL, pz);
   LAUNCH(c, k_plane_runs, nblk(lv.nplane, 128), 128, 0, pz, (int)lv.nplane, pp0, pp1);
