@@ -75,7 +75,7 @@ struct Level {
   uint8_t  *interior = nullptr; // [ncell] (sparse levels; dense => all interior)
   uint8_t  *tn = nullptr;       // [ncell] test_node()
   uint8_t  *mark = nullptr;     // [ncell] 0 / 1 refined / 2 ghost
-  int32_t  *nbr = nullptr;      // [27][ncell] (term-major) visible neighbour cell index or -1 (sparse levels)
+  int32_t  *nbr = nullptr;      // [10][ncell] (term-major) neighbour table: 9 row centres + visibility bits of their x-1 / x+1 cells (mesh.cu nb_get)
   int32_t  *crow = nullptr;     // [ncell] row index                             (sparse levels)
   int32_t  *count = nullptr;    // [ncell] particles linked when deposited
   uint64_t *hkey = nullptr; int32_t *hval = nullptr; uint64_t hmask = 0;   // open addressing hash: block key | (first cell, occupancy mask)

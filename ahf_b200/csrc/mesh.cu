@@ -29,13 +29,14 @@ struct LV {
   const uint64_t *hkey;
   const uint2    *hval;          // per slot: index of the block's first existing cell, 8-bit occupancy mask
   uint64_t        hmask;
+  const int32_t  *crow, *row_c0; // rows of the level (build_rows_planes); used to decode the neighbour table on the periodic faces
 };
 
 static LV view(const Level &l)
 {
   LV v; v.L = l.L; v.ncell = (int)l.ncell; v.dense = l.dense ? 1 : 0;
   v.logL = 0; while ((1ll << v.logL) < l.L) v.logL++;
-  v.ckey = l.ckey; v.xbreak = l.xbreak; v.hkey = l.hkey; v.hval = reinterpret_cast<const uint2 *>(l.hval); v.hmask = l.hmask;
+  v.ckey = l.ckey; v.xbreak = l.xbreak; v.hkey = l.hkey; v.hval = reinterpret_cast<const uint2 *>(l.hval); v.hmask = l.hmask; v.crow = l.crow; v.row_c0 = l.row_c0;
   return v;
 }
 
@@ -75,6 +76,20 @@ __device__ __forceinline__ int lv_lookup(const LV &v, int x, int y, int z)
     if (hk == ~0ull) return -1;
     s = (s + 1) & v.hmask;
   }
+}
+
+// Neighbour table of a sparse level, 10 words per cell, term-major [10][ncell]: words 0..8 = the (x, y+j-1, z+k-1) cell of row
+// q = 3k + j as the reference's search sees it (-1: not visible), word 9 = visibility bits of the x-1 (bit q) and x+1 (bit 9+q)
+// neighbours of those rows.  A visible x-1 / x+1 neighbour IS the array neighbour of the row's centre cell (same row, consecutive x)
+// -- except across the periodic faces, where it is the last / first cell of that row.  40 bytes per cell instead of 27 explicit
+// indices (108): the table is the largest array of a level and the cost of building it is the bytes it writes.
+__device__ __forceinline__ int nb_get(const LV &v, const int32_t *__restrict__ nbr, int c, int q, int a, int x)
+{
+  const int rm = nbr[(size_t)q * (size_t)v.ncell + (size_t)c];
+  if (a == 1 || rm < 0) return rm;
+  const uint32_t m = (uint32_t)nbr[(size_t)9 * (size_t)v.ncell + (size_t)c];
+  if (a == 0) return ((m >> q) & 1u) ? (x > 0 ? rm - 1 : v.row_c0[v.crow[rm] + 1] - 1) : -1;
+  return ((m >> (9 + q)) & 1u) ? (x < (int)v.L - 1 ? rm + 1 : v.row_c0[v.crow[rm]]) : -1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -141,7 +156,7 @@ __global__ void __launch_bounds__(256) k_deposit_generic(const float4 *__restric
         if (v.dense) {
           int x = (cx + a - 1) & (int)(v.L - 1), y = (cy + j - 1) & (int)(v.L - 1), z = (cz + k - 1) & (int)(v.L - 1);
           tgt = (int)lv_key(v, x, y, z);
-        } else tgt = nbr[(size_t)(k * 9 + j * 3 + a) * (size_t)v.ncell + (size_t)c];
+        } else tgt = nb_get(v, nbr, c, k * 3 + j, a, cx);
         if (tgt >= 0) atomicAdd(&acc[tgt], t);
       }
 }
@@ -364,7 +379,7 @@ k_deposit_tiles(const float4 *__restrict__ pos4, const int32_t *__restrict__ tst
 #pragma unroll
           for (int a = 0; a < 3; a++) {
             long long tgt;
-            if (SPARSE) tgt = nbr[(size_t)(k * 9 + j * 3 + a) * (size_t)lvw.ncell + (size_t)pcell[s0 + i]];
+            if (SPARSE) tgt = nb_get(lvw, nbr, pcell[s0 + i], k * 3 + j, a, cx);
             else { const int x = (cx + a - 1) & M, y = (cy + j - 1) & M, z = (cz + k - 1) & M; tgt = (long long)((((size_t)z << logL | y) << logL) | x); }
             if (tgt >= 0) atomicAdd(&acc[tgt], __float2ull_rn(wz[k] * wy[j] * fxs * wx[a]));
           }
@@ -521,7 +536,7 @@ k_deposit_runs(const float4 *__restrict__ lpos, const int32_t *__restrict__ tsta
           for (int j = 0; j < 3; j++)
 #pragma unroll
             for (int a = 0; a < 3; a++) {
-              const int tgt = nbr[(size_t)(k * 9 + j * 3 + a) * (size_t)lvw.ncell + pc];
+              const int tgt = nb_get(lvw, nbr, (int)pc, k * 3 + j, a, cx);
               if (tgt >= 0) atomicAdd(&acc[tgt], __float2ull_rn(wz[k] * wy[j] * fxs * wx[a]));
             }
         continue;
@@ -861,14 +876,16 @@ __global__ void k_test_node(LV v, const float *__restrict__ dens, const uint8_t 
           hit |= ((double)dens[t] >= thr);
         }
   } else if (interior[c]) {
-    // nbr is stored term-major ([27][ncell]): the loads of a warp are coalesced
+    // term-major table: the loads of a warp are coalesced.  An interior cell sees all 27 neighbours, so x+1 of row q is the array
+    // neighbour of the row's centre (the row's first cell across the periodic face)
+    const bool face = (int)(v.ckey[c] & (uint64_t)(v.L - 1)) == (int)v.L - 1;
     int t18[18];
 #pragma unroll
-    for (int k = 0; k < 3; k++)
-#pragma unroll
-      for (int j = 0; j < 3; j++)
-#pragma unroll
-        for (int a = 1; a < 3; a++) t18[k * 6 + j * 2 + a - 1] = nbr[(size_t)(k * 9 + j * 3 + a) * (size_t)v.ncell + (size_t)c];
+    for (int q = 0; q < 9; q++) {
+      const int rm = nbr[(size_t)q * (size_t)v.ncell + (size_t)c];
+      t18[2 * q] = rm;
+      t18[2 * q + 1] = face ? v.row_c0[v.crow[rm]] : rm + 1;
+    }
 #pragma unroll
     for (int q = 0; q < 18; q++) hit |= ((double)dens[t18[q]] >= thr);
   }
@@ -1135,6 +1152,7 @@ __global__ void k_neighbours(LV v, int32_t *__restrict__ nbr, uint8_t *__restric
 #pragma unroll
   for (int q = 0; q < 9; q++) if (q != 4) rowc[q] = (hq[q] == (kq[q] >> 3)) ? slot_cell(v.hval[sq[q]], (unsigned)(kq[q] & 7)) : -1;
   bool all = true;
+  uint32_t vis = 0;
 #pragma unroll
   for (int k = 0; k < 3; k++) {
     int zz = z + k - 1; if (zz < 0) zz = L - 1; else if (zz >= L) zz = 0;
@@ -1142,11 +1160,9 @@ __global__ void k_neighbours(LV v, int32_t *__restrict__ nbr, uint8_t *__restric
 #pragma unroll
     for (int j = 0; j < 3; j++) {
       int yy = y + j - 1; if (yy < 0) yy = L - 1; else if (yy >= L) yy = 0;
-      int32_t *o = nbr + (size_t)(k * 9 + j * 3) * (size_t)v.ncell + (size_t)c;      // term-major table: o[t * ncell]
-      const size_t os = (size_t)v.ncell;
       const int rm = (pm >= 0) ? rowc[k * 3 + j] : -1;
-      if (rm < 0) { o[0] = o[os] = o[2 * os] = -1; all = false; continue; }
-      o[os] = rm;
+      nbr[(size_t)(k * 3 + j) * (size_t)v.ncell + (size_t)c] = rm;
+      if (rm < 0) { all = false; continue; }
       const uint64_t kk = v.ckey[rm];
       // x-1: same run, else the periodic image when on the face (get_nnodes.c:490-508)
       int xm = -1;
@@ -1156,10 +1172,12 @@ __global__ void k_neighbours(LV v, int32_t *__restrict__ nbr, uint8_t *__restric
       int xp = -1;
       if (!v.xbreak[rm] && rm + 1 < v.ncell && v.ckey[rm + 1] == kk + 1 && x < L - 1) xp = rm + 1;
       else if (x == L - 1) xp = lv_lookup(v, 0, yy, zz);
-      o[0] = xm; o[2 * os] = xp;
+      if (xm >= 0) vis |= 1u << (k * 3 + j);
+      if (xp >= 0) vis |= 1u << (9 + k * 3 + j);
       if (xm < 0 || xp < 0) all = false;
     }
   }
+  nbr[(size_t)9 * (size_t)v.ncell + (size_t)c] = (int32_t)vis;
   interior[c] = all ? 1 : 0;
 }
 
@@ -1184,13 +1202,13 @@ __global__ void __launch_bounds__(128) k_neighbours_pc(LV v, const int32_t *__re
   bool ghq[8];
   int  px = 0, py = 0, pz = 0;
   const int CM = (int)(cv.L - 1);
-  if (cv.dense) lv_coords(cv, p, px, py, pz);
+  lv_coords(cv, p, px, py, pz);
 #pragma unroll
   for (int q = 0; q < 8; q++) {
     const int da = (q & 1) + bi - 1, db = ((q >> 1) & 1) + bj - 1, dc = ((q >> 2) & 1) + bk - 1;
     int qc;
     if (cv.dense) qc = (int)lv_key(cv, (px + da) & CM, (py + db) & CM, (pz + dc) & CM);
-    else qc = (da == 0 && db == 0 && dc == 0) ? p : cnbr[(size_t)((dc + 1) * 9 + (db + 1) * 3 + (da + 1)) * (size_t)cv.ncell + (size_t)p];
+    else qc = (da == 0 && db == 0 && dc == 0) ? p : nb_get(cv, cnbr, p, (dc + 1) * 3 + (db + 1), da + 1, px);
     const int ci = qc >= 0 ? cidx[qc] : -1;
     ghq[q] = ci >= 0 && (ci & 0x40000000);
     cbq[q] = ci >= 0 ? cbase[ci & 0x3fffffff] : make_int4(-1, -1, -1, -1);
@@ -1206,6 +1224,7 @@ __global__ void __launch_bounds__(128) k_neighbours_pc(LV v, const int32_t *__re
     return b0 < 0 ? -1 : b0 + (tx & 1);
   };
   bool all = true;
+  uint32_t vis = 0;
   const size_t os = (size_t)v.ncell;
 #pragma unroll
   for (int k = 0; k < 3; k++) {
@@ -1213,21 +1232,22 @@ __global__ void __launch_bounds__(128) k_neighbours_pc(LV v, const int32_t *__re
     const int pm = (k == 1) ? c : geo(0, 0, k - 1, dummy);               // the plane is found through its (x, y) node (get_nnodes.c:514-651)
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-      int32_t *o = nbr + (size_t)(k * 9 + j * 3) * os + (size_t)c;
       bool brk_rm = false;
       const int rm = (pm >= 0) ? ((k == 1 && j == 1) ? c : geo(0, j - 1, k - 1, brk_rm)) : -1;
       if (k == 1 && j == 1) brk_rm = ghq[(1 - bi) | ((1 - bj) << 1) | ((1 - bk) << 2)] && bi;      // own parent is slot (1-bi, 1-bj, 1-bk)
-      if (rm < 0) { o[0] = o[os] = o[2 * os] = -1; all = false; continue; }
-      o[os] = rm;
+      nbr[(size_t)(k * 3 + j) * os + (size_t)c] = rm;
+      if (rm < 0) { all = false; continue; }
       bool brk_m = false, brk_p = false;
       const int gm = geo(-1, j - 1, k - 1, brk_m), gp = geo(1, j - 1, k - 1, brk_p);
       // x-1: same run, else the periodic image when on the face (get_nnodes.c:490-508); x+1 (get_nnodes.c:465-485)
       const int xm = (x > 0) ? ((gm >= 0 && !brk_m) ? gm : -1) : gm;
       const int xp = (x < L - 1) ? ((gp >= 0 && !brk_rm) ? gp : -1) : gp;
-      o[0] = xm; o[2 * os] = xp;
+      if (xm >= 0) vis |= 1u << (k * 3 + j);
+      if (xp >= 0) vis |= 1u << (9 + k * 3 + j);
       if (xm < 0 || xp < 0) all = false;
     }
   }
+  nbr[(size_t)9 * os + (size_t)c] = (int32_t)vis;
   interior[c] = all ? 1 : 0;
 }
 
@@ -1581,30 +1601,30 @@ void amr_build(ahfgpu_ctx *c)
       CUDA_CHECK(cudaMemsetAsync(f.hkey, 0xff, cap * sizeof(uint64_t), c->stream));          // empty slots: key ~0 (values are only read behind a key match)
       LAUNCH(c, k_hash_insert, nblk(f.ncell, 256), 256, 0, f.ckey, (int)f.ncell, f.hkey, reinterpret_cast<uint2 *>(f.hval), f.hmask);
       alloc_cell_arrays(f);
-      f.interior = dalloc<uint8_t>(f.ncell); f.nbr = dalloc<int32_t>((size_t)f.ncell * 27);
+      f.interior = dalloc<uint8_t>(f.ncell); f.nbr = dalloc<int32_t>((size_t)f.ncell * 10);
       LV fv = view(f);
       if (getenv("AHFGPU_NBR_V1")) LAUNCH(c, k_neighbours, nblk(f.ncell, 128), 128, 0, fv, f.nbr, f.interior);      // hash probes (A/B timing)
       else LAUNCH(c, k_neighbours_pc, nblk(f.ncell, 128), 128, 0, fv, f.parent, cv, cur.nbr, cur.cidx, cur.cbase, f.nbr, f.interior);
       if (getenv("AHFGPU_DEBUG_NBR")) {                 // both constructions must give the same table
         DevBuf<int32_t> nb2; DevBuf<uint8_t> in2; DevBuf<unsigned long long> out;
-        nb2.reserve((size_t)f.ncell * 27); in2.reserve(f.ncell); out.reserve(3);
+        nb2.reserve((size_t)f.ncell * 10); in2.reserve(f.ncell); out.reserve(3);
         unsigned long long h0[3] = { 0, 0, ~0ull }, h[3];
         CUDA_CHECK(cudaMemcpyAsync(out.p, h0, sizeof(h0), cudaMemcpyHostToDevice, c->stream));
         LAUNCH(c, k_neighbours, nblk(f.ncell, 128), 128, 0, fv, nb2.p, in2.p);
-        LAUNCH(c, k_dbg_compare, nblk((uint64_t)f.ncell * 27, 256), 256, 0, f.nbr, nb2.p, (uint64_t)f.ncell * 27, out.p);
+        LAUNCH(c, k_dbg_compare, nblk((uint64_t)f.ncell * 10, 256), 256, 0, f.nbr, nb2.p, (uint64_t)f.ncell * 10, out.p);
         CUDA_CHECK(cudaMemcpyAsync(h, out.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
         fprintf(stderr, "[nbr dbg] level %d: %llu of %llu neighbour entries differ between the parent/child and the hash construction (first at %llu)\n",
-                lev + 1, h[0], (unsigned long long)f.ncell * 27, h[2]);
+                lev + 1, h[0], (unsigned long long)f.ncell * 10, h[2]);
         nb2.release(); in2.release(); out.release();
       }
       if (getenv("AHFGPU_DEBUG_RELINK")) {
         DevBuf<int32_t> nb2; DevBuf<uint8_t> in2; DevBuf<unsigned long long> out;
-        nb2.reserve((size_t)f.ncell * 27); in2.reserve(f.ncell); out.reserve(3);
+        nb2.reserve((size_t)f.ncell * 10); in2.reserve(f.ncell); out.reserve(3);
         unsigned long long h0[3] = { 0, 0, ~0ull }, h[3];
         CUDA_CHECK(cudaMemcpyAsync(out.p, h0, sizeof(h0), cudaMemcpyHostToDevice, c->stream));
         LAUNCH(c, k_neighbours, nblk(f.ncell, 128), 128, 0, fv, nb2.p, in2.p);
-        LAUNCH(c, k_dbg_compare, nblk((uint64_t)f.ncell * 27, 256), 256, 0, f.nbr, nb2.p, (uint64_t)f.ncell * 27, out.p);
+        LAUNCH(c, k_dbg_compare, nblk((uint64_t)f.ncell * 10, 256), 256, 0, f.nbr, nb2.p, (uint64_t)f.ncell * 10, out.p);
         CUDA_CHECK(cudaMemcpyAsync(h, out.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
         static std::map<int, unsigned long long> refcnt;
