@@ -889,7 +889,7 @@ __global__ void k_g_seed(const float4 *__restrict__ pos4, const float4 *__restri
 // Otherwise: prefix of the bound (M_vel, P) from the previous masks -> new masks (iterated inside the tile until stable for the
 // given carry-in) -> their tile totals for the next sweep; *changed is raised when any mask differs from the one it replaces.
 template <bool FIRST>
-__global__ void __launch_bounds__(HB) k_g_mask(const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, int has_u, const double *__restrict__ centre,
+__global__ void __launch_bounds__(HB, 2) k_g_mask(const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, int has_u, const double *__restrict__ centre,
                                                const int64_t *__restrict__ moff0, const uint32_t *__restrict__ members, GH G, const int2 *__restrict__ tiles,
                                                const double *__restrict__ vesc2, const double *__restrict__ tc, HP P, uint8_t *__restrict__ mask,
                                                double *__restrict__ tt, int *__restrict__ changed)
@@ -1562,7 +1562,7 @@ __global__ void __launch_bounds__(HB) k_p_phi(const float4 *__restrict__ pos4, i
   if (threadIdx.x == 0) tt[blockIdx.x] = loc;
 }
 
-__global__ void __launch_bounds__(HB) k_p_main(const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, int has_w, int has_u, const double *__restrict__ centre,
+__global__ void __launch_bounds__(HB, 2) k_p_main(const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, int has_w, int has_u, const double *__restrict__ centre,
                                                const int64_t *__restrict__ moff0, const uint32_t *__restrict__ members, PG G, const int2 *__restrict__ tiles,
                                                const double *__restrict__ tc4, const double *__restrict__ tcphi, const double *__restrict__ scal, HP P)
 {
