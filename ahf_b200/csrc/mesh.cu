@@ -1427,10 +1427,12 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
     CUDA_CHECK(cudaFuncSetAttribute(k_deposit_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_deposit_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, DR_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
+#ifdef AHFGPU_EXPERIMENTS      // timing-only variants of the domain kernel (wrong densities on purpose): never in the shipped library
     CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
+#endif
     uint16_t off[27];
     for (int k = 0; k < 3; k++) for (int j = 0; j < 3; j++) for (int a = 0; a < 3; a++) off[k * 9 + j * 3 + a] = (uint16_t)(4 * ((k * DT_H + j) * DT_H + a));
     CUDA_CHECK(cudaMemcpyToSymbol(c_dom_off, off, sizeof(off)));
@@ -1479,7 +1481,12 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
         // hardware's dynamic balance between light and heavy tiles); default: one CTA per item
         const unsigned grid = getenv("AHFGPU_DOM_PERSIST") ? (unsigned)std::min(W, 2 * nsm) : (unsigned)W;
 #define DOM_LAUNCH(V) LAUNCH(c, k_deposit_dom<V>, grid, DT_THREADS, DD_SMEM, c->pos4, work4.p, tot.p, (int)lv.L, v.logL, acc.p, 1u, rmax)
+#ifdef AHFGPU_EXPERIMENTS
         if (var == 1) DOM_LAUNCH(1); else if (var == 2) DOM_LAUNCH(2); else if (var == 3) DOM_LAUNCH(3); else if (var == 4) DOM_LAUNCH(4); else DOM_LAUNCH(0);
+#else
+        if (var != 0) AHF_FAIL("AHFGPU_DOM_VARIANT needs a library built with -DAHFGPU_EXPERIMENTS (timing-only kernels, wrong densities)");
+        DOM_LAUNCH(0);
+#endif
 #undef DOM_LAUNCH
       }
       else if (tiles_dense)

@@ -1,4 +1,5 @@
-"""Timing experiments on the domain deposit kernel (variants produce wrong densities on purpose; timing only)."""
+"""Timing experiments on the domain deposit kernel (variants produce wrong densities on purpose; timing only).
+Needs a library built with NVFLAGS+=-DAHFGPU_EXPERIMENTS (ahf_b200/csrc/Makefile); the shipped library refuses them."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
