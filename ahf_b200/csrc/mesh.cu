@@ -892,6 +892,31 @@ __global__ void k_test_node(LV v, const float *__restrict__ dens, const uint8_t 
   tn[c] = hit ? 1 : 0;
 }
 
+// F1 on the dense domain grid (L a multiple of 32): a CTA stages the comparison bits of a 33 x 10 x 10 block in shared memory and
+// evaluates the 18-cell stencil of its 32 x 8 x 8 cells from there (the per-cell form re-reads every density 18 times through L1)
+__global__ void __launch_bounds__(256) k_test_node_dense(LV v, const float *__restrict__ dens, double thr, uint8_t *__restrict__ tn)
+{
+  __shared__ uint8_t b[10][10][36];                       // [z][y][x], 33 x used
+  const int M = (int)(v.L - 1), logL = v.logL;
+  const int tx = blockIdx.x * 32, ty = blockIdx.y * 8, tz = blockIdx.z * 8;
+  for (int i = threadIdx.x; i < 10 * 10 * 33; i += 256) {
+    const int x = i % 33, r = i / 33, y = r % 10, z = r / 10;
+    const int gx = (tx + x) & M, gy = (ty + y - 1) & M, gz = (tz + z - 1) & M;
+    b[z][y][x] = ((double)dens[((((size_t)gz << logL) | (size_t)gy) << logL) | (size_t)gx] >= thr) ? 1 : 0;
+  }
+  __syncthreads();
+  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+#pragma unroll
+  for (int z = 0; z < 8; z++) {
+    unsigned hit = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) hit |= (unsigned)b[z + k][y + j][x] | (unsigned)b[z + k][y + j][x + 1];
+    tn[((((size_t)(tz + z) << logL) | (size_t)(ty + y)) << logL) | (size_t)(tx + x)] = hit ? 1 : 0;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // F2: which cells spawn children (ref_pquad / ref_cquad / ref_nquad)
 // ------------------------------------------------------------------------------------------------
@@ -1565,7 +1590,10 @@ void amr_build(ahfgpu_ctx *c)
     {
       Stage st(c, "flag", nc);
       Stage stl(c, lvl_name("flag", lev).c_str(), nc);
-      LAUNCH(c, k_test_node, nblk(nc, 256), 256, 0, cv, cur.dens, cur.interior, cur.nbr, cur.critdens - 1.0, cur.tn);
+      if (cur.dense && cur.L >= 32 && !getenv("AHFGPU_TESTNODE_V1"))
+        LAUNCH(c, k_test_node_dense, dim3((unsigned)(cur.L / 32), (unsigned)(cur.L / 8), (unsigned)(cur.L / 8)), 256, 0, cv, cur.dens, cur.critdens - 1.0, cur.tn);
+      else
+        LAUNCH(c, k_test_node, nblk(nc, 256), 256, 0, cv, cur.dens, cur.interior, cur.nbr, cur.critdens - 1.0, cur.tn);
       if (cur.dense) LAUNCH(c, k_mark_dense, nblk(nc, 256), 256, 0, cv, cur.tn, cur.mark);
       else LAUNCH(c, k_mark_sparse, nblk(nc, 256), 256, 0, cv, cur.tn, cur.interior, cur.crow, cur.row_c0, cur.row_tested, cur.mark);
     }
