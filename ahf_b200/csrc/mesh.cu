@@ -1600,15 +1600,13 @@ void amr_build(ahfgpu_ctx *c)
     {
       Stage st(c, "refine", nc);
       Stage stl(c, lvl_name("refine", lev).c_str(), nc);
-      DevBuf<uint8_t> flag;
-      flag.reserve(nc); S.reserve(nc);
-      LAUNCH(c, k_nonzero, nblk(nc, 256), 256, 0, cur.mark, nc, flag.p);
+      S.reserve(nc);
       int h3[3] = { 0, 0, 0 };
       {
         DevBuf<int> t3, bs;
         t3.reserve(4);
         CUDA_CHECK(cudaMemsetAsync(t3.p, 0, 4 * sizeof(int), c->stream));
-        exclusive_scan_async<uint8_t>(c, flag.p, S.p, nc, t3.p, bs);
+        exclusive_scan_async<uint8_t, true>(c, cur.mark, S.p, nc, t3.p, bs);            // marks are 0 / 1 (refined) / 2 (ghost pair): count the non-zero ones
         const int cnrow = cur.dense ? (int)(cur.L * cur.L) : (int)cur.nrow, cnplane = cur.dense ? (int)cur.L : (int)cur.nplane;
         LAUNCH(c, k_count_marked, nblk(cnrow, 256), 256, 0, cv, S.p, t3.p, cur.row_c0, cur.plane_r0, cnrow, cnplane, t3.p + 1);
         CUDA_CHECK(cudaMemcpyAsync(h3, t3.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -1616,7 +1614,6 @@ void amr_build(ahfgpu_ctx *c)
         t3.release(); bs.release();
       }
       M = h3[0];
-      flag.release();
       if (M == 0) { S.release(); break; }                             // refine_grid returned FALSE
       if ((long long)M * 8 > 2000000000ll) AHF_FAIL("refinement level exceeds 2^31 cells");
       Level f;

@@ -135,7 +135,7 @@ static __global__ void __launch_bounds__(1024) k_sc_small(int *__restrict__ a, u
 // (1: aggregate of the tile, 2: inclusive prefix up to and including the tile).  The state array lives in the context, starts
 // zeroed and is zeroed again by the last tile to finish, so no memset precedes the launch.  In-place use (in == out) is fine: a
 // tile reads its inputs before it writes its outputs and touches no other tile's data.
-template <typename T>
+template <typename T, bool NZ = false>      // NZ: scan the flags (in[i] != 0) instead of the values
 __global__ void __launch_bounds__(SC_THREADS) k_sc_lookback(const T *in, uint64_t n, int *out, unsigned long long *__restrict__ state,
                                                             unsigned *__restrict__ ctr, unsigned nblk, int *__restrict__ total)
 {
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_sc_lookback(const T *in, uint64_
   int v[SC_ITEMS], s = 0;
   sc_load_items(in, base, n, v);
 #pragma unroll
-  for (int i = 0; i < SC_ITEMS; i++) s += v[i];
+  for (int i = 0; i < SC_ITEMS; i++) { if (NZ) v[i] = v[i] != 0; s += v[i]; }
   int ex = block_exclusive_scan(s);
   if (threadIdx.x == SC_THREADS - 1) s_agg = ex + s;
   __syncthreads();
@@ -199,12 +199,12 @@ __global__ void __launch_bounds__(SC_THREADS) k_sc_lookback(const T *in, uint64_
 }
 
 // out[i] = sum_{j<i} in[j]; no host synchronisation; d_total (device, may be null) receives the sum
-template <typename T> void exclusive_scan_async(ahfgpu_ctx *c, const T *in, int *out, uint64_t n, int *d_total, DevBuf<int> &bs)
+template <typename T, bool NZ = false> void exclusive_scan_async(ahfgpu_ctx *c, const T *in, int *out, uint64_t n, int *d_total, DevBuf<int> &bs)
 {
   if (n == 0) return;
   const unsigned nblk = (unsigned)((n + SC_TILE - 1) / SC_TILE);
-  static const bool three_phase = getenv("AHFGPU_SCAN_V1") != nullptr;       // previous form (A/B timing)
-  if (three_phase) {
+  static const bool three_phase = getenv("AHFGPU_SCAN_V1") != nullptr;       // previous form (A/B timing; plain values only)
+  if (three_phase && !NZ) {
     bs.reserve(nblk);
     LAUNCH(c, (k_sc_reduce<T>), nblk, SC_THREADS, 0, in, n, bs.p);
     LAUNCH(c, k_sc_small, 1, 1024, 0, bs.p, (uint64_t)nblk, d_total);
@@ -220,7 +220,7 @@ template <typename T> void exclusive_scan_async(ahfgpu_ctx *c, const T *in, int 
   }
   // the two counters sit in the last word of the state array
   unsigned *ctr = reinterpret_cast<unsigned *>(c->scan_state + (c->scan_cap - 1));
-  LAUNCH(c, (k_sc_lookback<T>), nblk, SC_THREADS, 0, in, n, out, c->scan_state, ctr, nblk, d_total);
+  LAUNCH(c, (k_sc_lookback<T, NZ>), nblk, SC_THREADS, 0, in, n, out, c->scan_state, ctr, nblk, d_total);
 }
 
 // out[i] = sum_{j<i} in[j]; returns the total (synchronises the stream)
