@@ -317,34 +317,37 @@ void sfc_sort_resident(ahfgpu_ctx *c, uint64_t *keys_out, uint32_t *order_out)
   const uint64_t n = c->in_n;
   alloc_particles(c, n);
   c->has_weight = (c->in_w != nullptr); c->has_u = (c->in_u != nullptr);
-  DevBuf<uint64_t> k0, k1;
-  DevBuf<uint32_t> v0, v1;
-  k0.reserve(n); k1.reserve(n); v0.reserve(n); v1.reserve(n);
+  // the resident key / order arrays double as the first pair of sort buffers: an even number of passes ends in them
+  c->keys = static_cast<decltype(c->keys)>(ahf::cache_alloc((n ? n : 1) * sizeof(uint64_t)));
+  c->order = static_cast<decltype(c->order)>(ahf::cache_alloc((n ? n : 1) * sizeof(uint32_t)));
+  DevBuf<uint64_t> k1;
+  DevBuf<uint32_t> v1;
+  k1.reserve(n); v1.reserve(n);
   const unsigned nb = (unsigned)((n + 255) / 256);
   {
     Stage st(c, "keys", (int64_t)n);
-    if (n) { upload_hil_tab3(); LAUNCH(c, k_keys_soa_tab, keys_tab_grid(n), KT_THREADS, 0, c->in_pos, (uint64_t)0, n, k0.p, v0.p); }
+    if (n) { upload_hil_tab3(); LAUNCH(c, k_keys_soa_tab, keys_tab_grid(n), KT_THREADS, 0, c->in_pos, (uint64_t)0, n, c->keys, c->order); }
   }
   uint64_t *ks; uint32_t *vs;
   {
     Stage st(c, "sort", (int64_t)n);
-    radix_sort_pairs(c, k0.p, v0.p, k1.p, v1.p, n, 63, &ks, &vs);
+    radix_sort_pairs(c, c->keys, c->order, k1.p, v1.p, n, 63, &ks, &vs);
+    if (ks != c->keys) {
+      CUDA_CHECK(cudaMemcpyAsync(c->keys, ks, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
+      CUDA_CHECK(cudaMemcpyAsync(c->order, vs, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+    }
   }
   {
     Stage st(c, "gather", (int64_t)n);
-    if (n) LAUNCH(c, k_gather_soa, nb, 256, 0, c->in_pos, c->in_mom, c->in_w, c->in_u, vs, n, c->pos4, c->mom4);
+    if (n) LAUNCH(c, k_gather_soa, nb, 256, 0, c->in_pos, c->in_mom, c->in_w, c->in_u, c->order, n, c->pos4, c->mom4);
   }
-  c->keys = static_cast<decltype(c->keys)>(ahf::cache_alloc((n ? n : 1) * sizeof(uint64_t)));
-  c->order = static_cast<decltype(c->order)>(ahf::cache_alloc((n ? n : 1) * sizeof(uint32_t)));
-  CUDA_CHECK(cudaMemcpyAsync(c->keys, ks, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
-  CUDA_CHECK(cudaMemcpyAsync(c->order, vs, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
   if (keys_out || order_out) {
     Stage st(c, "d2h", (int64_t)((keys_out ? 8 * n : 0) + (order_out ? 4 * n : 0)));
     if (keys_out) CUDA_CHECK(cudaMemcpyAsync(keys_out, c->keys, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
     if (order_out) CUDA_CHECK(cudaMemcpyAsync(order_out, c->order, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   }
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  k0.release(); k1.release(); v0.release(); v1.release();
+  k1.release(); v1.release();
 }
 
 void sfc_sort_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, const float *w, const float *u, uint64_t n,
@@ -404,9 +407,9 @@ void sfc_sort_soa_async(ahfgpu_ctx *c, const float *pos3, const float *mom3, con
   c->has_weight = (w != nullptr); c->has_u = (u != nullptr);
   c->keys = static_cast<decltype(c->keys)>(ahf::cache_alloc((n ? n : 1) * sizeof(uint64_t)));
   c->order = static_cast<decltype(c->order)>(ahf::cache_alloc((n ? n : 1) * sizeof(uint32_t)));
-  DevBuf<uint64_t> k0, k1;
-  DevBuf<uint32_t> v0, v1;
-  k0.reserve(n); k1.reserve(n); v0.reserve(n); v1.reserve(n);
+  DevBuf<uint64_t> k1;
+  DevBuf<uint32_t> v1;
+  k1.reserve(n); v1.reserve(n);                     // c->keys / c->order are the first pair of sort buffers
   // the blocks above are ordered on the main stream (they may be recycled): the copy stream starts behind this point
   CUDA_CHECK(cudaEventRecord(c->ev_main, c->stream));
   CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
@@ -420,7 +423,7 @@ void sfc_sort_soa_async(ahfgpu_ctx *c, const float *pos3, const float *mom3, con
       if (i1 > i0) CUDA_CHECK(cudaMemcpyAsync(c->in_pos + 3 * i0, pos3 + 3 * i0, 3 * (i1 - i0) * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
       CUDA_CHECK(cudaEventRecord(c->ev_copy[q], c->copy_stream));
       CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_copy[q], 0));
-      if (i1 > i0) LAUNCH(c, k_keys_soa_tab, keys_tab_grid(i1 - i0), KT_THREADS, 0, c->in_pos, i0, i1, k0.p, v0.p);
+      if (i1 > i0) LAUNCH(c, k_keys_soa_tab, keys_tab_grid(i1 - i0), KT_THREADS, 0, c->in_pos, i0, i1, c->keys, c->order);
     }
   }
   if (w) CUDA_CHECK(cudaMemcpyAsync(c->in_w, w, n * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
@@ -430,13 +433,15 @@ void sfc_sort_soa_async(ahfgpu_ctx *c, const float *pos3, const float *mom3, con
   uint64_t *ks; uint32_t *vs;
   {
     Stage st(c, "sort", (int64_t)n);
-    radix_sort_pairs(c, k0.p, v0.p, k1.p, v1.p, n, 63, &ks, &vs);
+    radix_sort_pairs(c, c->keys, c->order, k1.p, v1.p, n, 63, &ks, &vs);
+    if (ks != c->keys) {
+      CUDA_CHECK(cudaMemcpyAsync(c->keys, ks, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
+      CUDA_CHECK(cudaMemcpyAsync(c->order, vs, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+    }
   }
   const unsigned nb = (unsigned)((n + 255) / 256);
   {
     Stage st(c, "gather", (int64_t)n);
-    CUDA_CHECK(cudaMemcpyAsync(c->keys, ks, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
-    CUDA_CHECK(cudaMemcpyAsync(c->order, vs, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
     CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_copy[NCH], 0));                 // weights
     if (n) LAUNCH(c, k_gather_pos, nb, 256, 0, c->in_pos, c->in_w, c->order, n, c->pos4);
   }
@@ -447,7 +452,7 @@ void sfc_sort_soa_async(ahfgpu_ctx *c, const float *pos3, const float *mom3, con
   CUDA_CHECK(cudaEventRecord(c->ev_mom, c->copy_stream));
   c->mom_pending = true;
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  k0.release(); k1.release(); v0.release(); v1.release();
+  k1.release(); v1.release();
 }
 
 __global__ void k_keys_pos4(const float4 *__restrict__ pos4, uint64_t n, uint64_t *__restrict__ keys, uint32_t *__restrict__ idx)
