@@ -1084,11 +1084,6 @@ __global__ void k_make_children(LV v, const uint8_t *__restrict__ mark, const in
   cbase[S[c]] = make_int4(cb[0], cb[1], cb[2], cb[3]);
 }
 
-__global__ void k_hash_clear(uint64_t *__restrict__ hkey, uint2 *__restrict__ hval, uint64_t cap)
-{
-  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i < cap) { hkey[i] = ~0ull; hval[i] = make_uint2(0x7fffffffu, 0u); }
-}
 // one insertion per block of 8 x-consecutive cells: the block's cells are consecutive in the sorted cell array, so the thread of
 // the block's first existing cell collects the occupancy mask from its (at most 7) successors and claims the slot -- one CAS and
 // one 8-byte store per block instead of three atomics per cell
@@ -1358,11 +1353,6 @@ __global__ void k_count_owner(const int8_t *__restrict__ owner, uint64_t n, unsi
   }
   __syncthreads();
   if (threadIdx.x < 64 && h[threadIdx.x]) atomicAdd(&cnt[threadIdx.x], (unsigned long long)h[threadIdx.x]);
-}
-__global__ void k_nonzero(const uint8_t *in, int n, uint8_t *out)
-{
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = in[i] ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------

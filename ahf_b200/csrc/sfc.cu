@@ -90,34 +90,6 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t *__restri
   bhist[(uint64_t)threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
 }
 
-// exclusive scan of m uint32 values in place, one CTA of 1024 threads
-__global__ void __launch_bounds__(1024) k_scan_u32(uint32_t *__restrict__ a, uint64_t m)
-{
-  __shared__ uint32_t wsum[32];
-  __shared__ uint32_t carry_s;
-  const int      t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const uint64_t per = (m + 1023) / 1024;
-  uint64_t       b = (uint64_t)t * per, e = b + per;
-  if (b > m) b = m;
-  if (e > m) e = m;
-  uint32_t s = 0;
-  for (uint64_t i = b; i < e; i++) s += a[i];
-  uint32_t v = s;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { uint32_t x = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += x; }
-  if (lane == 31) wsum[w] = v;
-  __syncthreads();
-  if (w == 0) {
-    uint32_t x = wsum[lane], y = x;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t q = __shfl_up_sync(0xffffffffu, y, o); if (lane >= o) y += q; }
-    wsum[lane] = y - x;
-  }
-  __syncthreads();
-  uint32_t run = wsum[w] + (v - s);
-  (void)carry_s;
-  for (uint64_t i = b; i < e; i++) { uint32_t x = a[i]; a[i] = run; run += x; }
-}
 
 // ranked scatter.  The tile is first sorted by digit in shared memory (stable), then written out digit run by digit run so that
 // consecutive threads store consecutive addresses (a direct scatter writes 12 useful bytes per pair of 32-byte sectors).
@@ -363,13 +335,6 @@ void sfc_sort_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, const flo
 // gathers pos4 -- everything ahfgpu_build_amr needs -- while the momenta are still on the bus.  The momentum gather runs on
 // the copy stream behind its copy and signals ev_mom, which the halo pass waits for on the device.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_keys_soa_chunk(const float *__restrict__ pos3, uint64_t i0, uint64_t i1, uint64_t *__restrict__ keys, uint32_t *__restrict__ idx)
-{
-  uint64_t i = i0 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= i1) return;
-  keys[i] = hilbert_key_pos(pos3[3 * i], pos3[3 * i + 1], pos3[3 * i + 2], 21);
-  idx[i]  = (uint32_t)i;
-}
 __global__ void k_gather_pos(const float *__restrict__ pos3, const float *__restrict__ w, const uint32_t *__restrict__ order, uint64_t n,
                              float4 *__restrict__ pos4)
 {
