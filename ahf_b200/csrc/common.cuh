@@ -83,6 +83,7 @@ struct Level {
   int32_t  *parent = nullptr;   // [ncell] cell of the coarser level this cell is a child of      (sparse levels)
   int32_t  *cidx = nullptr;     // [ncell] -1: no children; else slot in cbase | 0x40000000 when the children are a ghost pair
   int4     *cbase = nullptr;    // [marked cells] index on the next level of child (i=0, j, k): .x (0,0) .y (j=1,k=0) .z (0,1) .w (1,1)
+  int32_t  *cpar = nullptr;     // [marked cells] the marked cell of this level behind slot s of cbase
   // rows / planes of sparse levels
   int64_t  nrow = 0, nplane = 0;
   uint64_t *rowkey = nullptr;   // [nrow] z*L+y

@@ -1047,7 +1047,7 @@ __global__ void k_mark_sparse(LV v, const uint8_t *__restrict__ tn, const uint8_
 __global__ void k_make_children(LV v, const uint8_t *__restrict__ mark, const int *__restrict__ S, int Mtot,
                                 const int32_t *__restrict__ crow, const int32_t *__restrict__ row_c0, const int32_t *__restrict__ rowplane,
                                 const int32_t *__restrict__ plane_r0, int nrow, uint64_t *__restrict__ fkey, uint8_t *__restrict__ fbreak,
-                                int flogL, int32_t *__restrict__ fparent, int32_t *__restrict__ cidx, int4 *__restrict__ cbase)
+                                int flogL, int32_t *__restrict__ fparent, int32_t *__restrict__ cidx, int4 *__restrict__ cbase, int32_t *__restrict__ cpar)
 {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= v.ncell) return;
@@ -1082,6 +1082,7 @@ __global__ void k_make_children(LV v, const uint8_t *__restrict__ mark, const in
     }
   cidx[c] = S[c] | (ghost ? 0x40000000 : 0);
   cbase[S[c]] = make_int4(cb[0], cb[1], cb[2], cb[3]);
+  cpar[S[c]] = c;
 }
 
 // one insertion per block of 8 x-consecutive cells: the block's cells are consecutive in the sorted cell array, so the thread of
@@ -1269,6 +1270,82 @@ __global__ void __launch_bounds__(128) k_neighbours_pc(LV v, const int32_t *__re
   }
   nbr[(size_t)9 * os + (size_t)c] = (int32_t)vis;
   interior[c] = all ? 1 : 0;
+}
+
+// The same table once more, one thread per MARKED COARSE CELL (= the 8 children it spawned).  Existence and x-break of a fine cell
+// are properties of its parent alone (a marked cell has all 8 children; the run breaks after the i=1 child of a ghost pair), and the
+// compressed table needs an index only for the nine row centres, which always lie in the parent's own x column.  So a thread reads
+// the marks of the 27 coarse neighbours (two 27-bit masks E, G) and the child bases of the nine with da = 0, and everything else is
+// compile-time indexing over (i,j,k) x (b,c): ~90 instructions per fine cell instead of ~1000 in the per-cell kernel, which had to
+// select among its 8 parents with run-time indices (ncu: issue bound, 79 % issue active).
+__global__ void __launch_bounds__(128) k_neighbours_oct(LV v, LV cv, const int32_t *__restrict__ cnbr, const int32_t *__restrict__ cidx,
+                                                        const int4 *__restrict__ cbase, const int32_t *__restrict__ cpar, int M,
+                                                        int32_t *__restrict__ nbr, uint8_t *__restrict__ interior)
+{
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= M) return;
+  const int p = cpar[s];
+  int px, py, pz; lv_coords(cv, p, px, py, pz);
+  const int CM = (int)(cv.L - 1), L = (int)v.L;
+  uint32_t E = 0, G = 0;                       // bit (dc+1)*9 + (db+1)*3 + (da+1): that coarse neighbour has children / they are a ghost pair
+  int4 CB0[9];                                 // child bases of the neighbours with da = 0, index (dc+1)*3 + (db+1)
+#pragma unroll
+  for (int t = 0; t < 27; t++) {
+    const int da = t % 3 - 1, db = (t / 3) % 3 - 1, dc = t / 9 - 1;
+    int qc;
+    if (t == 13) qc = p;
+    else if (cv.dense) qc = (int)lv_key(cv, (px + da) & CM, (py + db) & CM, (pz + dc) & CM);
+    else qc = nb_get(cv, cnbr, p, (dc + 1) * 3 + (db + 1), da + 1, px);
+    const int ci = qc >= 0 ? cidx[qc] : -1;
+    if (ci >= 0) { E |= 1u << t; if (ci & 0x40000000) G |= 1u << t; }
+    if (da == 0) CB0[(dc + 1) * 3 + (db + 1)] = ci >= 0 ? cbase[ci & 0x3fffffff] : make_int4(-1, -1, -1, -1);
+  }
+  const int4 own = CB0[4];
+  const size_t os = (size_t)v.ncell;
+#pragma unroll
+  for (int k = 0; k < 2; k++)
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const int jk = k * 2 + j;
+      const int c0 = jk == 0 ? own.x : jk == 1 ? own.y : jk == 2 ? own.z : own.w;      // children (i=0,1) of this (j,k) pair: c0, c0+1
+      uint32_t vis[2] = { 0u, 0u };
+      bool     all[2] = { true, true };
+#pragma unroll
+      for (int cc = -1; cc <= 1; cc++)
+#pragma unroll
+        for (int b = -1; b <= 1; b++) {
+          const int q = (cc + 1) * 3 + (b + 1);
+          const int ty = j + b, tz = k + cc;                                            // -1..2
+          const int db = (ty >> 1), dc = (tz >> 1), comp = (tz & 1) * 2 + (ty & 1);
+          const int rowbit = (dc + 1) * 9 + (db + 1) * 3;                                // + (da+1)
+          const bool plane_ok = (E >> ((dc + 1) * 9 + 3 + 1)) & 1u;                      // the (x, y, z+cc) cell: parent (0, 0, dc)
+          const bool row_ok = plane_ok && ((E >> (rowbit + 1)) & 1u);
+          const int4 cb = CB0[(dc + 1) * 3 + (db + 1)];
+          const int  r0 = comp == 0 ? cb.x : comp == 1 ? cb.y : comp == 2 ? cb.z : cb.w;
+          int2 rm = make_int2(row_ok ? r0 : -1, row_ok ? r0 + 1 : -1);
+          *reinterpret_cast<int2 *>(nbr + (size_t)q * os + (size_t)c0) = rm;
+          if (!row_ok) { all[0] = all[1] = false; continue; }
+          const bool gh0 = (G >> (rowbit + 1)) & 1u;                                    // ghost flag of the row centre's parent (da = 0)
+          // child i = 0 (x = 2 px): x-1 is the i=1 child of the da=-1 parent, x+1 its own sibling (i=1, da=0)
+          {
+            const bool em = (E >> (rowbit + 0)) & 1u, brk_m = (G >> (rowbit + 0)) & 1u;  // that neighbour is an i=1 child: break iff ghost
+            const bool vm = em && ((2 * px > 0) ? !brk_m : true);
+            const bool vp = true;                                                        // sibling exists; the centre (i=0) never ends a run
+            if (vm) vis[0] |= 1u << q; else all[0] = false;
+            if (vp) vis[0] |= 1u << (9 + q);
+          }
+          // child i = 1 (x = 2 px + 1): x-1 is its sibling (i=0, never a break), x+1 the i=0 child of the da=+1 parent
+          {
+            const bool ep = (E >> (rowbit + 2)) & 1u;
+            const bool vm = true;
+            const bool vp = ep && ((2 * px + 1 < L - 1) ? !gh0 : true);                  // the centre is an i=1 child: the run ends after it iff ghost
+            if (vm) vis[1] |= 1u << q;
+            if (vp) vis[1] |= 1u << (9 + q); else all[1] = false;
+          }
+        }
+      *reinterpret_cast<int2 *>(nbr + (size_t)9 * os + (size_t)c0) = make_int2((int)vis[0], (int)vis[1]);
+      *reinterpret_cast<uchar2 *>(interior + c0) = make_uchar2(all[0] ? 1 : 0, all[1] ? 1 : 0);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1612,9 +1689,9 @@ void amr_build(ahfgpu_ctx *c)
       f.critdens = par.nth_ref * f.masstopartdens;
       f.ckey = dalloc<uint64_t>(f.ncell); f.xbreak = dalloc<uint8_t>(f.ncell);
       int flogL = cv.logL + 1;
-      f.parent = dalloc<int32_t>(f.ncell); cur.cidx = dalloc<int32_t>(nc); cur.cbase = dalloc<int4>(M);
+      f.parent = dalloc<int32_t>(f.ncell); cur.cidx = dalloc<int32_t>(nc); cur.cbase = dalloc<int4>(M); cur.cpar = dalloc<int32_t>(M);
       LAUNCH(c, k_make_children, nblk(nc, 256), 256, 0, cv, cur.mark, S.p, M, cur.crow, cur.row_c0, cur.dense ? nullptr : cur.rowplane,
-             cur.plane_r0, (int)cur.nrow, f.ckey, f.xbreak, flogL, f.parent, cur.cidx, cur.cbase);
+             cur.plane_r0, (int)cur.nrow, f.ckey, f.xbreak, flogL, f.parent, cur.cidx, cur.cbase, cur.cpar);
       S.release();
       // hash
       // slots hold 8 x-consecutive cells; children come in x-pairs, so there are at most ncell/2 occupied slots
@@ -1626,7 +1703,8 @@ void amr_build(ahfgpu_ctx *c)
       f.interior = dalloc<uint8_t>(f.ncell); f.nbr = dalloc<int32_t>((size_t)f.ncell * 10);
       LV fv = view(f);
       if (getenv("AHFGPU_NBR_V1")) LAUNCH(c, k_neighbours, nblk(f.ncell, 128), 128, 0, fv, f.nbr, f.interior);      // hash probes (A/B timing)
-      else LAUNCH(c, k_neighbours_pc, nblk(f.ncell, 128), 128, 0, fv, f.parent, cv, cur.nbr, cur.cidx, cur.cbase, f.nbr, f.interior);
+      else if (getenv("AHFGPU_NBR_V2")) LAUNCH(c, k_neighbours_pc, nblk(f.ncell, 128), 128, 0, fv, f.parent, cv, cur.nbr, cur.cidx, cur.cbase, f.nbr, f.interior);   // per fine cell (A/B timing)
+      else LAUNCH(c, k_neighbours_oct, nblk(M, 128), 128, 0, fv, cv, cur.nbr, cur.cidx, cur.cbase, cur.cpar, M, f.nbr, f.interior);
       if (getenv("AHFGPU_DEBUG_NBR")) {                 // both constructions must give the same table
         DevBuf<int32_t> nb2; DevBuf<uint8_t> in2; DevBuf<unsigned long long> out;
         nb2.reserve((size_t)f.ncell * 10); in2.reserve(f.ncell); out.reserve(3);
