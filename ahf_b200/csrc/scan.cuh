@@ -135,15 +135,59 @@ static __global__ void __launch_bounds__(1024) k_sc_small(int *__restrict__ a, u
 // (1: aggregate of the tile, 2: inclusive prefix up to and including the tile).  The state array lives in the context, starts
 // zeroed and is zeroed again by the last tile to finish, so no memset precedes the launch.  In-place use (in == out) is fine: a
 // tile reads its inputs before it writes its outputs and touches no other tile's data.
+// building blocks of the chained scan, also used by kernels that fuse a compaction with their own work (mesh.cu k_relink_fused):
+// sc_ticket: tile id in launch order; sc_lookback_prefix: called by the first warp with the tile's aggregate, returns the exclusive
+// prefix (valid in lane 0) and publishes the inclusive one; sc_finish: the last tile to finish re-zeroes the state.
+__device__ __forceinline__ unsigned sc_ticket(unsigned *__restrict__ ctr)
+{
+  __shared__ unsigned s_bid;
+  if (threadIdx.x == 0) s_bid = atomicAdd(&ctr[0], 1u);
+  __syncthreads();
+  return s_bid;
+}
+__device__ __forceinline__ int sc_lookback_prefix(unsigned long long *__restrict__ state, unsigned bid, int agg, unsigned nblk, int *__restrict__ total)
+{
+  int prefix = 0;
+  if (bid == 0) {
+    if (threadIdx.x == 0) atomicExch(&state[0], (2ull << 32) | (unsigned)agg);
+  } else {
+    if (threadIdx.x == 0) atomicExch(&state[bid], (1ull << 32) | (unsigned)agg);
+    long long j0 = (long long)bid - 1;                      // window [j0-31, j0], lane q looks at j0 - q
+    for (;;) {
+      const long long j = j0 - (long long)threadIdx.x;
+      unsigned long long st = 2ull << 32;                   // before tile 0: prefix 0
+      if (j >= 0) { do { st = *reinterpret_cast<volatile unsigned long long *>(&state[j]); } while ((st >> 32) == 0); }
+      const unsigned isp = __ballot_sync(0xffffffffu, (st >> 32) == 2);
+      const int      first = isp ? __ffs(isp) - 1 : 32;      // nearest predecessor that already has its inclusive prefix
+      int add = ((int)threadIdx.x <= first) ? (int)(unsigned)st : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
+      prefix += add;
+      if (isp) break;
+      j0 -= 32;
+    }
+    if (threadIdx.x == 0) atomicExch(&state[bid], (2ull << 32) | (unsigned)(prefix + agg));
+  }
+  if (threadIdx.x == 0 && bid == nblk - 1 && total) *total = prefix + agg;
+  return prefix;
+}
+__device__ __forceinline__ void sc_finish(unsigned long long *__restrict__ state, unsigned *__restrict__ ctr, unsigned nblk)
+{
+  __shared__ int s_last;
+  if (threadIdx.x == 0) { __threadfence(); s_last = (atomicAdd(&ctr[1], 1u) == nblk - 1) ? 1 : 0; }
+  __syncthreads();
+  if (s_last) {
+    for (unsigned i = threadIdx.x; i < nblk; i += blockDim.x) state[i] = 0ull;
+    if (threadIdx.x == 0) { ctr[0] = 0u; ctr[1] = 0u; }
+  }
+}
+
 template <typename T, bool NZ = false>      // NZ: scan the flags (in[i] != 0) instead of the values
 __global__ void __launch_bounds__(SC_THREADS) k_sc_lookback(const T *in, uint64_t n, int *out, unsigned long long *__restrict__ state,
                                                             unsigned *__restrict__ ctr, unsigned nblk, int *__restrict__ total)
 {
-  __shared__ unsigned s_bid;
-  __shared__ int      s_prefix, s_agg, s_last;
-  if (threadIdx.x == 0) s_bid = atomicAdd(&ctr[0], 1u);
-  __syncthreads();
-  const unsigned bid = s_bid;
+  __shared__ int s_prefix, s_agg;
+  const unsigned bid = sc_ticket(ctr);
   const uint64_t base = (uint64_t)bid * SC_TILE + (uint64_t)threadIdx.x * SC_ITEMS;
   int v[SC_ITEMS], s = 0;
   sc_load_items(in, base, n, v);
@@ -153,29 +197,8 @@ __global__ void __launch_bounds__(SC_THREADS) k_sc_lookback(const T *in, uint64_
   if (threadIdx.x == SC_THREADS - 1) s_agg = ex + s;
   __syncthreads();
   if (threadIdx.x < 32) {
-    const int agg = s_agg;
-    int prefix = 0;
-    if (bid == 0) {
-      if (threadIdx.x == 0) atomicExch(&state[0], (2ull << 32) | (unsigned)agg);
-    } else {
-      if (threadIdx.x == 0) atomicExch(&state[bid], (1ull << 32) | (unsigned)agg);
-      long long j0 = (long long)bid - 1;                      // window [j0-31, j0], lane q looks at j0 - q
-      for (;;) {
-        const long long j = j0 - (long long)threadIdx.x;
-        unsigned long long st = 2ull << 32;                   // before tile 0: prefix 0
-        if (j >= 0) { do { st = *reinterpret_cast<volatile unsigned long long *>(&state[j]); } while ((st >> 32) == 0); }
-        const unsigned isp = __ballot_sync(0xffffffffu, (st >> 32) == 2);
-        const int      first = isp ? __ffs(isp) - 1 : 32;      // nearest predecessor that already has its inclusive prefix
-        int add = ((int)threadIdx.x <= first) ? (int)(unsigned)st : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
-        prefix += add;
-        if (isp) break;
-        j0 -= 32;
-      }
-      if (threadIdx.x == 0) atomicExch(&state[bid], (2ull << 32) | (unsigned)(prefix + agg));
-    }
-    if (threadIdx.x == 0) { s_prefix = prefix; if (bid == nblk - 1 && total) *total = prefix + agg; }
+    const int prefix = sc_lookback_prefix(state, bid, s_agg, nblk, total);
+    if (threadIdx.x == 0) s_prefix = prefix;
   }
   __syncthreads();
   ex += s_prefix;
@@ -189,14 +212,20 @@ __global__ void __launch_bounds__(SC_THREADS) k_sc_lookback(const T *in, uint64_
 #pragma unroll
     for (int i = 0; i < SC_ITEMS; i++) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
   }
-  // the last tile to finish leaves the state zeroed for the next scan
-  if (threadIdx.x == 0) { __threadfence(); s_last = (atomicAdd(&ctr[1], 1u) == nblk - 1) ? 1 : 0; }
-  __syncthreads();
-  if (s_last) {
-    for (unsigned i = threadIdx.x; i < nblk; i += SC_THREADS) state[i] = 0ull;
-    if (threadIdx.x == 0) { ctr[0] = 0u; ctr[1] = 0u; }
-  }
+  sc_finish(state, ctr, nblk);
 }
+
+// the zeroed look-back state of the context (grown on demand); the two counters sit in its last word
+static inline void scan_state_reserve(ahfgpu_ctx *c, unsigned nblk)
+{
+  if ((size_t)nblk + 2 <= c->scan_cap) return;
+  if (c->scan_state) ahf::dfree(c->scan_state);
+  size_t cap = 4096; while (cap < (size_t)nblk + 2) cap <<= 1;
+  c->scan_state = static_cast<unsigned long long *>(ahf::cache_alloc(cap * sizeof(unsigned long long)));
+  CUDA_CHECK(cudaMemsetAsync(c->scan_state, 0, cap * sizeof(unsigned long long), c->stream));
+  c->scan_cap = cap;
+}
+static inline unsigned *scan_state_ctr(ahfgpu_ctx *c) { return reinterpret_cast<unsigned *>(c->scan_state + (c->scan_cap - 1)); }
 
 // out[i] = sum_{j<i} in[j]; no host synchronisation; d_total (device, may be null) receives the sum
 template <typename T, bool NZ = false> void exclusive_scan_async(ahfgpu_ctx *c, const T *in, int *out, uint64_t n, int *d_total, DevBuf<int> &bs)
@@ -211,15 +240,8 @@ template <typename T, bool NZ = false> void exclusive_scan_async(ahfgpu_ctx *c, 
     LAUNCH(c, (k_sc_down<T>), nblk, SC_THREADS, 0, in, n, bs.p, out);
     return;
   }
-  if ((size_t)nblk + 2 > c->scan_cap) {                                       // grow the (zeroed) look-back state
-    if (c->scan_state) ahf::dfree(c->scan_state);
-    size_t cap = 4096; while (cap < (size_t)nblk + 2) cap <<= 1;
-    c->scan_state = static_cast<unsigned long long *>(ahf::cache_alloc(cap * sizeof(unsigned long long)));
-    CUDA_CHECK(cudaMemsetAsync(c->scan_state, 0, cap * sizeof(unsigned long long), c->stream));
-    c->scan_cap = cap;
-  }
-  // the two counters sit in the last word of the state array
-  unsigned *ctr = reinterpret_cast<unsigned *>(c->scan_state + (c->scan_cap - 1));
+  scan_state_reserve(c, nblk);
+  unsigned *ctr = scan_state_ctr(c);
   LAUNCH(c, (k_sc_lookback<T, NZ>), nblk, SC_THREADS, 0, in, n, out, c->scan_state, ctr, nblk, d_total);
 }
 
