@@ -1368,6 +1368,16 @@ __global__ void k_relink(const float4 *__restrict__ pos4, const float4 *__restri
     const int    b[3] = { 2 * cx, 2 * cy, 2 * cz };
     // child b+e (e = 0,1) contains the particle iff b+e <= t <= b+e+1 (inclusive on both faces, relink.c:153)
     const int4 cb = cbase[cidx[c] & 0x3fffffff];        // the cell's children on the fine level (k_make_children): no hash probe
+    // common case: no coordinate sits exactly on a face of the fine grid, so exactly one child contains the particle
+    const int e0 = (int)t[0] - b[0], e1 = (int)t[1] - b[1], e2 = (int)t[2] - b[2];
+    if (t[0] != (double)(int)t[0] && t[1] != (double)(int)t[1] && t[2] != (double)(int)t[2] && (unsigned)(e0 | e1 | e2) <= 1u) {
+      const int jk = e2 * 2 + e1;
+      const int f = (jk == 0 ? cb.x : jk == 1 ? cb.y : jk == 2 ? cb.z : cb.w) + e0;
+      newcell[i] = finterior[f] ? f : -1;
+      moved[i]   = finterior[f] ? 1 : 0;
+      dlt[i]     = 0;
+      return;
+    }
     bool ok[3][2];
 #pragma unroll
     for (int d = 0; d < 3; d++) {
