@@ -79,7 +79,7 @@ using namespace ahf;
 
 void ahfgpu_ctx::stage_reset()
 {
-  for (auto &s : stages) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+  for (auto &s : stages) { event_pool.push_back(s.a); event_pool.push_back(s.b); }
   stages.clear(); stage_ms.clear(); stage_cnt.clear(); stage_cnt_extra.clear(); stage_wall.clear(); stages_resolved = true;
 }
 void ahfgpu_ctx::stage_resolve()
@@ -190,6 +190,8 @@ int ahfgpu_finalize(ahfgpu_ctx *c)
   c->stage_reset(); c->free_halos(); c->free_levels(); c->free_particles();
   ahf::dfree(c->in_pos); ahf::dfree(c->in_mom); ahf::dfree(c->in_w); ahf::dfree(c->in_u);
   ahf::dfree(c->scan_state); c->scan_state = nullptr; c->scan_cap = 0;
+  for (auto &e : c->event_pool) cudaEventDestroy(e);
+  c->event_pool.clear();
   for (auto &e : c->ev) if (e) cudaEventDestroy(e);
   {                                                   // blocks cached for this context's stream go back to the driver pool
     std::lock_guard<std::mutex> lk(g_cache_mu);

@@ -102,6 +102,26 @@ struct Level {
 
 struct StageRec { std::string name; cudaEvent_t a, b; int64_t count; };
 
+// A/B and debug switches of the mesh pass, read from the environment ONCE per ahfgpu_build_amr call (the level loop used to call
+// getenv ~15 times per level; tests flip the switches between calls, so they are not cached for the life of the process)
+struct MeshEnv {
+  bool generic_deposit = false, deposit_v1 = false, dom_persist = false, sparse_v1 = false, sparse_v2 = false, testnode_v1 = false, nbr_v1 = false,
+       nbr_v2 = false, debug_nbr = false, debug_relink = false, level_stages = false, stages = true;
+  int  dom_variant = 0, dom_rmax = 1;
+  void read()
+  {
+    auto on = [](const char *n) { return getenv(n) != nullptr; };
+    generic_deposit = on("AHFGPU_GENERIC_DEPOSIT"); deposit_v1 = on("AHFGPU_DEPOSIT_V1"); dom_persist = on("AHFGPU_DOM_PERSIST");
+    sparse_v1 = on("AHFGPU_SPARSE_V1"); sparse_v2 = on("AHFGPU_SPARSE_V2"); testnode_v1 = on("AHFGPU_TESTNODE_V1"); nbr_v1 = on("AHFGPU_NBR_V1");
+    nbr_v2 = on("AHFGPU_NBR_V2"); debug_nbr = on("AHFGPU_DEBUG_NBR"); debug_relink = on("AHFGPU_DEBUG_RELINK"); level_stages = on("AHFGPU_LEVEL_STAGES");
+    // AHFGPU_STAGES=0: only the timers a caller cannot do without (amr_total, deposit_dom_kernel); every event record is a marker
+    // between kernels on the stream, and ~90 of them per pass cost ~0.3 ms at 256^3
+    const char *es = getenv("AHFGPU_STAGES"); stages = !(es && es[0] == '0');
+    const char *ev = getenv("AHFGPU_DOM_VARIANT"); dom_variant = ev ? atoi(ev) : 0;
+    const char *er = getenv("AHFGPU_DOM_RMAX"); dom_rmax = er ? atoi(er) : 1;
+  }
+};
+
 }  // namespace ahf
 
 struct ahfgpu_ctx {
@@ -150,6 +170,8 @@ struct ahfgpu_ctx {
   std::map<std::string, int64_t> stage_cnt_extra;   // counters set directly by the stages (not event based)
   std::map<std::string, double>  stage_wall;        // host wall clock spent inside the stage scopes (ms); query "<name>@wall"
   bool stages_resolved = true;
+  ahf::MeshEnv env;
+  std::vector<cudaEvent_t> event_pool;        // stage-timer events are recycled, not created and destroyed every call
 
   void stage_reset();
   void stage_resolve();
@@ -164,15 +186,18 @@ namespace ahf {
 struct Stage {
   ahfgpu_ctx *c; size_t idx;
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-  Stage(ahfgpu_ctx *ctx, const char *name, int64_t count = 0) : c(ctx)
+  Stage(ahfgpu_ctx *ctx, const char *name, int64_t count = 0, bool enabled = true) : c(ctx), idx((size_t)-1)
   {
+    if (!enabled) return;                     // opt-in timers (per-level stages): no events, no host time
     StageRec r; r.name = name; r.count = count;
-    CUDA_CHECK(cudaEventCreate(&r.a)); CUDA_CHECK(cudaEventCreate(&r.b));
+    auto take = [&](cudaEvent_t &e) { if (c->event_pool.empty()) CUDA_CHECK(cudaEventCreate(&e)); else { e = c->event_pool.back(); c->event_pool.pop_back(); } };
+    take(r.a); take(r.b);
     CUDA_CHECK(cudaEventRecord(r.a, c->stream));
     c->stages.push_back(r); idx = c->stages.size() - 1; c->stages_resolved = false;
   }
   ~Stage()
   {
+    if (idx == (size_t)-1) return;
     cudaEventRecord(c->stages[idx].b, c->stream);
     c->stage_wall[c->stages[idx].name] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   }

@@ -1506,19 +1506,21 @@ static void build_rows_planes(ahfgpu_ctx *c, Level &lv)
 }
 
 static std::string lvl_name(const char *base, int lev) { char b[48]; snprintf(b, sizeof(b), "%s_L%d", base, lev); return b; }
+// per-level stage timers (scripts/stage_breakdown.py) are opt-in: AHFGPU_LEVEL_STAGES=1 (MeshEnv); the per-pass totals are always taken
+
 
 static void deposit_level(ahfgpu_ctx *c, Level &lv)
 {
   const int lev_id = (int)c->levels.size() - 1;
-  Stage st(c, "deposit", lv.npart_dep);
-  Stage stl(c, lvl_name("deposit", lev_id).c_str(), lv.npart_dep);
+  Stage st(c, "deposit", lv.npart_dep, c->env.stages);
+  Stage stl(c, lvl_name("deposit", lev_id).c_str(), lv.npart_dep, c->env.level_stages);
   LV v = view(lv);
   const int nc = (int)lv.ncell;
   DevBuf<unsigned long long> acc;
   acc.reserve(nc);
   CUDA_CHECK(cudaMemsetAsync(acc.p, 0, sizeof(unsigned long long) * nc, c->stream));
-  const bool generic_only = getenv("AHFGPU_GENERIC_DEPOSIT") != nullptr;
-  const bool dom_v1       = getenv("AHFGPU_DEPOSIT_V1") != nullptr;           // previous float-weight domain kernel (A/B timing)
+  const bool generic_only = c->env.generic_deposit;
+  const bool dom_v1       = c->env.deposit_v1;           // previous float-weight domain kernel (A/B timing)
   const bool tiles_dense  = lv.dense && lv.L >= 2 * DT_T && lv.npart_dep > 0 && !generic_only;
   const int    S = (tiles_dense && !dom_v1) ? 32 : fx_shift_for(lv.masstopartdens);    // k_deposit_dom works in 2^-32 units
   const double fxscale = (double)(1ull << S);
@@ -1568,20 +1570,18 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
     work.reserve(W);
     LAUNCH(c, k_tile_work, nblk(ntile, 256), 256, 0, nchunk.p, woff.p, ntile, work.p);
     {
-      Stage sk(c, lv.dense ? "deposit_dom_kernel" : "deposit_ref_kernel", lv.npart_dep);
-      Stage skl(c, lvl_name("depk", lev_id).c_str(), W);
+      Stage sk(c, lv.dense ? "deposit_dom_kernel" : "deposit_ref_kernel", lv.npart_dep, lv.dense || c->env.stages);
+      Stage skl(c, lvl_name("depk", lev_id).c_str(), W, c->env.level_stages);
       if (tiles_dense && !dom_v1) {
-        const char *ev = getenv("AHFGPU_DOM_VARIANT");
-        const int var = ev ? atoi(ev) : 0;
-        const char *er = getenv("AHFGPU_DOM_RMAX");
-        const int rmax = er ? atoi(er) : 1;           // slices with at most this many distinct cells take the run-reduction path (measured: 1 = whole warp in one cell is best; partial-mask REDUX costs more than the conflicts it removes)
+        const int var = c->env.dom_variant;
+        const int rmax = c->env.dom_rmax;           // slices with at most this many distinct cells take the run-reduction path (measured: 1 = whole warp in one cell is best; partial-mask REDUX costs more than the conflicts it removes)
         work4.reserve(W);
         LAUNCH(c, k_tile_work4, nblk(ntile, 256), 256, 0, tstart.p, nchunk.p, woff.p, ntile, tbits, work4.p);
         int nsm = 0;
         CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->dev));
         // AHFGPU_DOM_PERSIST=1: two persistent CTAs per SM striding over the items (measured slower: static striding loses the
         // hardware's dynamic balance between light and heavy tiles); default: one CTA per item
-        const unsigned grid = getenv("AHFGPU_DOM_PERSIST") ? (unsigned)std::min(W, 2 * nsm) : (unsigned)W;
+        const unsigned grid = c->env.dom_persist ? (unsigned)std::min(W, 2 * nsm) : (unsigned)W;
 #define DOM_LAUNCH(V) LAUNCH(c, k_deposit_dom<V>, grid, DT_THREADS, DD_SMEM, c->pos4, work4.p, tot.p, (int)lv.L, v.logL, acc.p, 1u, rmax)
 #ifdef AHFGPU_EXPERIMENTS
         if (var == 1) DOM_LAUNCH(1); else if (var == 2) DOM_LAUNCH(2); else if (var == 3) DOM_LAUNCH(3); else if (var == 4) DOM_LAUNCH(4); else DOM_LAUNCH(0);
@@ -1594,7 +1594,7 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
       else if (tiles_dense)
         LAUNCH(c, k_deposit_tiles<false>, (unsigned)W, DT_THREADS, DT_SMEM, c->pos4, tstart.p, work.p, (int)lv.L, v.logL, tbits, acc.p,
                (const uint32_t *)nullptr, (const int32_t *)nullptr, v, (const int32_t *)nullptr, (float)fxscale, tot.p);
-      else if (getenv("AHFGPU_SPARSE_V1") || (!getenv("AHFGPU_SPARSE_V2") && (double)lv.npart_dep < 0.75 * (double)lv.ncell))
+      else if (c->env.sparse_v1 || (!c->env.sparse_v2 && (double)lv.npart_dep < 0.75 * (double)lv.ncell))
         // lane per particle: the thin tiles of the deepest levels (well under one particle per cell, a few hundred particles per
         // tile) have no runs to aggregate and want the larger CTA for the tile flush (measured: 0.23 vs 0.31 ms on level 6)
         LAUNCH(c, k_deposit_tiles<true>, (unsigned)W, DT_THREADS, DT_SMEM, lv.lpos, tstart.p, work.p, (int)lv.L, v.logL, tbits, acc.p,
@@ -1606,12 +1606,12 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
     if (lv.dense) c->stage_cnt_extra["deposit_dom_ctas"] = W;
     tstart.release(); nchunk.release(); woff.release(); bs.release(); tot.release(); work.release(); work4.release(); tlist.release(); head.release(); hs.release();
   } else if (lv.npart_dep > 0) {
-    Stage sk(c, lv.dense ? "deposit_dom_kernel" : "deposit_ref_kernel", lv.npart_dep);
+    Stage sk(c, lv.dense ? "deposit_dom_kernel" : "deposit_ref_kernel", lv.npart_dep, lv.dense || c->env.stages);
     LAUNCH(c, k_deposit_generic, nblk(lv.npart_dep, 256), 256, 0, c->pos4, lv.plist, lv.pcell, (uint64_t)lv.npart_dep, v, lv.nbr, acc.p, fxscale);
   }
   if (c->allreduce) {
     // several contexts share one box: sum the level's accumulators over all of them (exact: integers)
-    Stage sa(c, "allreduce", (int64_t)nc * 8);
+    Stage sa(c, "allreduce", (int64_t)nc * 8, c->env.stages);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     if (c->allreduce(c->allreduce_user, acc.p, (int64_t)nc) != 0) AHF_FAIL("all-reduce callback failed");
   }
@@ -1628,6 +1628,7 @@ static void alloc_cell_arrays(Level &lv)
 
 void amr_build(ahfgpu_ctx *c)
 {
+  c->env.read();
   Stage sall(c, "amr_total", (int64_t)c->n);
   c->free_levels();
   const uint64_t n = c->n;
@@ -1648,7 +1649,7 @@ void amr_build(ahfgpu_ctx *c)
     d.npart_dep = (int64_t)n;
     d.pcell = dalloc<int32_t>(n);
     {
-      Stage st(c, "ll", (int64_t)n);
+      Stage st(c, "ll", (int64_t)n, c->env.stages);
       LV v = view(d);
       if (n) LAUNCH(c, k_domain_cells, nblk(n, 256), 256, 0, c->pos4, n, (int)d.L, v.logL, d.pcell);
     }
@@ -1665,9 +1666,9 @@ void amr_build(ahfgpu_ctx *c)
     int M = 0;
     DevBuf<int> S;
     {
-      Stage st(c, "flag", nc);
-      Stage stl(c, lvl_name("flag", lev).c_str(), nc);
-      if (cur.dense && cur.L >= 32 && !getenv("AHFGPU_TESTNODE_V1"))
+      Stage st(c, "flag", nc, c->env.stages);
+      Stage stl(c, lvl_name("flag", lev).c_str(), nc, c->env.level_stages);
+      if (cur.dense && cur.L >= 32 && !c->env.testnode_v1)
         LAUNCH(c, k_test_node_dense, dim3((unsigned)(cur.L / 32), (unsigned)(cur.L / 8), (unsigned)(cur.L / 8)), 256, 0, cv, cur.dens, cur.critdens - 1.0, cur.tn);
       else
         LAUNCH(c, k_test_node, nblk(nc, 256), 256, 0, cv, cur.dens, cur.interior, cur.nbr, cur.critdens - 1.0, cur.tn);
@@ -1675,8 +1676,8 @@ void amr_build(ahfgpu_ctx *c)
       else LAUNCH(c, k_mark_sparse, nblk(nc, 256), 256, 0, cv, cur.tn, cur.interior, cur.crow, cur.row_c0, cur.row_tested, cur.mark);
     }
     {
-      Stage st(c, "refine", nc);
-      Stage stl(c, lvl_name("refine", lev).c_str(), nc);
+      Stage st(c, "refine", nc, c->env.stages);
+      Stage stl(c, lvl_name("refine", lev).c_str(), nc, c->env.level_stages);
       S.reserve(nc);
       int h3[3] = { 0, 0, 0 };
       {
@@ -1712,10 +1713,10 @@ void amr_build(ahfgpu_ctx *c)
       alloc_cell_arrays(f);
       f.interior = dalloc<uint8_t>(f.ncell); f.nbr = dalloc<int32_t>((size_t)f.ncell * 10);
       LV fv = view(f);
-      if (getenv("AHFGPU_NBR_V1")) LAUNCH(c, k_neighbours, nblk(f.ncell, 128), 128, 0, fv, f.nbr, f.interior);      // hash probes (A/B timing)
-      else if (getenv("AHFGPU_NBR_V2")) LAUNCH(c, k_neighbours_pc, nblk(f.ncell, 128), 128, 0, fv, f.parent, cv, cur.nbr, cur.cidx, cur.cbase, f.nbr, f.interior);   // per fine cell (A/B timing)
+      if (c->env.nbr_v1) LAUNCH(c, k_neighbours, nblk(f.ncell, 128), 128, 0, fv, f.nbr, f.interior);      // hash probes (A/B timing)
+      else if (c->env.nbr_v2) LAUNCH(c, k_neighbours_pc, nblk(f.ncell, 128), 128, 0, fv, f.parent, cv, cur.nbr, cur.cidx, cur.cbase, f.nbr, f.interior);   // per fine cell (A/B timing)
       else LAUNCH(c, k_neighbours_oct, nblk(M, 128), 128, 0, fv, cv, cur.nbr, cur.cidx, cur.cbase, cur.cpar, M, f.nbr, f.interior);
-      if (getenv("AHFGPU_DEBUG_NBR")) {                 // both constructions must give the same table
+      if (c->env.debug_nbr) {                 // both constructions must give the same table
         DevBuf<int32_t> nb2; DevBuf<uint8_t> in2; DevBuf<unsigned long long> out;
         nb2.reserve((size_t)f.ncell * 10); in2.reserve(f.ncell); out.reserve(3);
         unsigned long long h0[3] = { 0, 0, ~0ull }, h[3];
@@ -1728,7 +1729,7 @@ void amr_build(ahfgpu_ctx *c)
                 lev + 1, h[0], (unsigned long long)f.ncell * 10, h[2]);
         nb2.release(); in2.release(); out.release();
       }
-      if (getenv("AHFGPU_DEBUG_RELINK")) {
+      if (c->env.debug_relink) {
         DevBuf<int32_t> nb2; DevBuf<uint8_t> in2; DevBuf<unsigned long long> out;
         nb2.reserve((size_t)f.ncell * 10); in2.reserve(f.ncell); out.reserve(3);
         unsigned long long h0[3] = { 0, 0, ~0ull }, h[3];
@@ -1752,8 +1753,8 @@ void amr_build(ahfgpu_ctx *c)
     {
       Level &coa = c->levels[lev];
       Level &fin = c->levels[lev + 1];
-      Stage st(c, "relink", coa.npart_dep);
-      Stage stl(c, lvl_name("relink", lev).c_str(), coa.npart_dep);
+      Stage st(c, "relink", coa.npart_dep, c->env.stages);
+      Stage stl(c, lvl_name("relink", lev).c_str(), coa.npart_dep, c->env.level_stages);
       const uint64_t np = (uint64_t)coa.npart_dep;
       DevBuf<int32_t> newcell; DevBuf<uint8_t> moved, dlt; DevBuf<int> MS;
       newcell.reserve(np); moved.reserve(np); dlt.reserve(np); MS.reserve(np);
@@ -1761,7 +1762,7 @@ void amr_build(ahfgpu_ctx *c)
       if (np) {
         LAUNCH(c, k_relink, nblk(np, 256), 256, 0, c->pos4, coa.lpos, coa.plist, coa.pcell, np, view(coa), coa.mark, coa.cidx, coa.cbase, view(fin), fin.interior, newcell.p, moved.p, dlt.p);
         nmoved = exclusive_scan<uint8_t>(c, moved.p, MS.p, np);
-        if (getenv("AHFGPU_DEBUG_RELINK")) {
+        if (c->env.debug_relink) {
           DevBuf<int32_t> nc2; DevBuf<uint8_t> mv2, dl2; DevBuf<unsigned long long> out;
           nc2.reserve(np); mv2.reserve(np); dl2.reserve(np); out.reserve(3);
           unsigned long long h0[3] = { 0, 0, ~0ull }, h[3];

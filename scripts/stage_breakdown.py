@@ -1,5 +1,6 @@
 """Per-level stage table of one pass of the path on the bench workload (CUDA-event stage timers of the library)."""
 import os, sys, time
+os.environ.setdefault("AHFGPU_LEVEL_STAGES", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from ahf_b200 import ahf, synth
