@@ -171,6 +171,7 @@ struct ahfgpu_ctx {
   std::map<std::string, double>  stage_wall;        // host wall clock spent inside the stage scopes (ms); query "<name>@wall"
   bool stages_resolved = true;
   ahf::MeshEnv env;
+  void  *h_pin = nullptr; size_t h_pin_bytes = 0;       // pinned scratch of the small device->host read-backs (ahf::read_back)
   std::vector<cudaEvent_t> event_pool;        // stage-timer events are recycled, not created and destroyed every call
 
   void stage_reset();
@@ -202,6 +203,22 @@ struct Stage {
     c->stage_wall[c->stages[idx].name] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   }
 };
+
+// small device->host read-back through pinned memory + stream sync (a copy into pageable memory goes through a driver staging
+// buffer and blocks inside the call)
+inline void read_back(ahfgpu_ctx *c, void *host_dst, const void *dev_src, size_t bytes)
+{
+  if (bytes > c->h_pin_bytes) {
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    c->h_pin = nullptr; c->h_pin_bytes = 0;
+    const size_t cap = bytes > 65536 ? bytes : 65536;
+    CUDA_CHECK(cudaHostAlloc(&c->h_pin, cap, cudaHostAllocDefault));
+    c->h_pin_bytes = cap;
+  }
+  CUDA_CHECK(cudaMemcpyAsync(c->h_pin, dev_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  memcpy(host_dst, c->h_pin, bytes);
+}
 
 // entry points implemented in the .cu files
 void sfc_sort_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, const float *w, const float *u, uint64_t n,

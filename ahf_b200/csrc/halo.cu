@@ -2070,8 +2070,7 @@ static void unbind_cooperative(ahfgpu_ctx *c, int64_t nhalo, const HP &P, const 
         LAUNCH(c, k_g_mask<false>, (unsigned)nt, HB, 0, c->pos4, c->mom4, has_u, d_ctr, d_moff0, d_members, G, d_tiles, d_vesc2, d_tc, P, d_mask, d_tt, d_changed + q);
       }
       int chg[2];
-      CUDA_CHECK(cudaMemcpyAsync(chg, d_changed, sizeof(int) * 2, cudaMemcpyDeviceToHost, c->stream));
-      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      read_back(c, chg, d_changed, sizeof(int) * 2);
       if (!chg[1]) break;
     }
     LAUNCH(c, k_g_compact, (unsigned)nt, HB, 0, d_moff0, d_members, G, d_tiles, d_mask, d_tc, d_tmp);

@@ -1687,8 +1687,7 @@ void amr_build(ahfgpu_ctx *c)
         exclusive_scan_async<uint8_t, true>(c, cur.mark, S.p, nc, t3.p, bs);            // marks are 0 / 1 (refined) / 2 (ghost pair): count the non-zero ones
         const int cnrow = cur.dense ? (int)(cur.L * cur.L) : (int)cur.nrow, cnplane = cur.dense ? (int)cur.L : (int)cur.nplane;
         LAUNCH(c, k_count_marked, nblk(cnrow, 256), 256, 0, cv, S.p, t3.p, cur.row_c0, cur.plane_r0, cnrow, cnplane, t3.p + 1);
-        CUDA_CHECK(cudaMemcpyAsync(h3, t3.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        read_back(c, h3, t3.p, 3 * sizeof(int));
         t3.release(); bs.release();
       }
       M = h3[0];
@@ -1797,8 +1796,7 @@ void amr_build(ahfgpu_ctx *c)
     CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, 64 * sizeof(unsigned long long), c->stream));
     if (n) LAUNCH(c, k_count_owner, std::min(nblk(n, 256), 2368u), 256, 0, c->owner_level, n, cnt.p);
     unsigned long long h[64];
-    CUDA_CHECK(cudaMemcpyAsync(h, cnt.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    read_back(c, h, cnt.p, sizeof(h));
     for (size_t l = 0; l < c->levels.size(); l++) c->levels[l].npart_final = (int64_t)h[l];
     cnt.release();
   }

@@ -253,8 +253,7 @@ template <typename T> int exclusive_scan(ahfgpu_ctx *c, const T *in, int *out, u
   tot.reserve(1);
   exclusive_scan_async<T>(c, in, out, n, tot.p, bs);
   int h = 0;
-  CUDA_CHECK(cudaMemcpyAsync(&h, tot.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  read_back(c, &h, tot.p, sizeof(int));
   bs.release(); tot.release();
   return h;
 }
