@@ -191,6 +191,8 @@ int ahfgpu_finalize(ahfgpu_ctx *c)
   ahf::dfree(c->in_pos); ahf::dfree(c->in_mom); ahf::dfree(c->in_w); ahf::dfree(c->in_u);
   ahf::dfree(c->scan_state); c->scan_state = nullptr; c->scan_cap = 0;
   if (c->h_pin) cudaFreeHost(c->h_pin);
+  if (c->h_up) cudaFreeHost(c->h_up);
+  c->h_up = nullptr; c->h_up_bytes = 0;
   c->h_pin = nullptr; c->h_pin_bytes = 0;
   for (auto &e : c->event_pool) cudaEventDestroy(e);
   c->event_pool.clear();

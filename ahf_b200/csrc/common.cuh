@@ -171,6 +171,7 @@ struct ahfgpu_ctx {
   std::map<std::string, double>  stage_wall;        // host wall clock spent inside the stage scopes (ms); query "<name>@wall"
   bool stages_resolved = true;
   ahf::MeshEnv env;
+  void  *h_up = nullptr; size_t h_up_bytes = 0;         // pinned staging of small host->device uploads (halo tile lists)
   void  *h_pin = nullptr; size_t h_pin_bytes = 0;       // pinned scratch of the small device->host read-backs (ahf::read_back)
   std::vector<cudaEvent_t> event_pool;        // stage-timer events are recycled, not created and destroyed every call
 

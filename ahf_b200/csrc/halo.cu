@@ -1984,7 +1984,7 @@ static void unbind_cooperative(ahfgpu_ctx *c, int64_t nhalo, const HP &P, const 
   GH G;
   G.np = dalloc<int64_t>(nhalo); G.nb = dalloc<int64_t>(nhalo); G.nremove = dalloc<int64_t>(nhalo);
   G.Mvir = dalloc<double>(nhalo); G.Rvir = dalloc<double>(nhalo); G.ovd = dalloc<double>(nhalo); G.Phi0 = dalloc<double>(nhalo); G.seed = dalloc<double>(4 * nhalo);
-  G.first = dalloc<unsigned long long>(nhalo); G.tile0 = dalloc<int32_t>(nhalo); G.ntile = dalloc<int32_t>(nhalo);
+  G.first = dalloc<unsigned long long>(nhalo);
   int64_t *d_n6 = dalloc<int64_t>(nhalo), *d_n7 = dalloc<int64_t>(nhalo);
   CUDA_CHECK(cudaMemcpyAsync(G.np, d_ng, sizeof(int64_t) * nhalo, cudaMemcpyDeviceToDevice, c->stream));
   for (double *q : { G.Mvir, G.Rvir, G.ovd, G.Phi0 }) CUDA_CHECK(cudaMemsetAsync(q, 0, sizeof(double) * nhalo, c->stream));
@@ -1992,8 +1992,21 @@ static void unbind_cooperative(ahfgpu_ctx *c, int64_t nhalo, const HP &P, const 
   int64_t max_tiles = 0;
   for (int64_t h = 0; h < nhalo; h++) max_tiles += (h_ng[h] + HT - 1) / HT;
   if (max_tiles >= (1ll << 31)) AHF_FAIL("too many member tiles in one call");
-  int2    *d_tiles = dalloc<int2>(max_tiles);
-  int32_t *d_act = dalloc<int32_t>(nhalo);
+  // active list | first tile | tile count | tile list in ONE device block, filled by ONE copy from pinned staging per phase
+  // (four copies from pageable vectors before: each a blocking driver-staged transfer)
+  const size_t nh2 = (size_t)((nhalo + 1) & ~1ll);                       // keeps the int2 list 8-byte aligned
+  const size_t blk_bytes = 3 * nh2 * sizeof(int32_t) + (size_t)max_tiles * sizeof(int2);
+  int32_t *d_blk = static_cast<int32_t *>(ahf::cache_alloc(blk_bytes ? blk_bytes : 8));
+  int32_t *d_act = d_blk;
+  G.tile0 = d_blk + nh2; G.ntile = d_blk + 2 * nh2;
+  int2    *d_tiles = reinterpret_cast<int2 *>(d_blk + 3 * nh2);
+  if (blk_bytes > c->h_up_bytes) {
+    if (c->h_up) cudaFreeHost(c->h_up);
+    c->h_up = nullptr; c->h_up_bytes = 0;
+    CUDA_CHECK(cudaHostAlloc(&c->h_up, blk_bytes, cudaHostAllocDefault));
+    c->h_up_bytes = blk_bytes;
+  }
+  int32_t *h_blk = static_cast<int32_t *>(c->h_up);
   double  *d_tt = dalloc<double>((size_t)max_tiles * GNC), *d_tc = dalloc<double>((size_t)max_tiles * GNC);
   double  *d_htot1 = dalloc<double>(nhalo), *d_htot5 = dalloc<double>((size_t)nhalo * GNC);
   double  *d_vesc2 = dalloc<double>(tot_g), *d_Mpre = has_w ? dalloc<double>(tot_g) : nullptr;
@@ -2016,10 +2029,12 @@ static void unbind_cooperative(ahfgpu_ctx *c, int64_t nhalo, const HP &P, const 
     }
     nact = (int)act.size(); nt = (int)tiles.size();
     if (!nact) return;
-    CUDA_CHECK(cudaMemcpyAsync(d_act, act.data(), sizeof(int32_t) * nact, cudaMemcpyHostToDevice, c->stream));
-    CUDA_CHECK(cudaMemcpyAsync(G.tile0, tile0.data(), sizeof(int32_t) * nhalo, cudaMemcpyHostToDevice, c->stream));
-    CUDA_CHECK(cudaMemcpyAsync(G.ntile, ntile.data(), sizeof(int32_t) * nhalo, cudaMemcpyHostToDevice, c->stream));
-    CUDA_CHECK(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(int2) * nt, cudaMemcpyHostToDevice, c->stream));
+    // every phase ends with a read-back (stream synchronised), so the staging buffer is free again here
+    memcpy(h_blk, act.data(), sizeof(int32_t) * nact);
+    memcpy(h_blk + nh2, tile0.data(), sizeof(int32_t) * nhalo);
+    memcpy(h_blk + 2 * nh2, ntile.data(), sizeof(int32_t) * nhalo);
+    memcpy(h_blk + 3 * nh2, tiles.data(), sizeof(int2) * nt);
+    CUDA_CHECK(cudaMemcpyAsync(d_blk, h_blk, 3 * nh2 * sizeof(int32_t) + (size_t)nt * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
   };
   auto mass_prefix = [&]() {
     if (!has_w) return;
@@ -2089,7 +2104,7 @@ static void unbind_cooperative(ahfgpu_ctx *c, int64_t nhalo, const HP &P, const 
   c->stage_cnt_extra["halo_unbind_iterations"] = n_iter;
   c->stage_cnt_extra["halo_unbind_mask_sweeps"] = n_sweep;
   for (void *q : { (void *)G.np, (void *)G.nb, (void *)G.nremove, (void *)G.Mvir, (void *)G.Rvir, (void *)G.ovd, (void *)G.Phi0, (void *)G.seed, (void *)G.first,
-                   (void *)G.tile0, (void *)G.ntile, (void *)d_n6, (void *)d_n7, (void *)d_tiles, (void *)d_act, (void *)d_tt, (void *)d_tc, (void *)d_htot1,
+                   (void *)d_blk, (void *)d_n6, (void *)d_n7, (void *)d_tt, (void *)d_tc, (void *)d_htot1,
                    (void *)d_htot5, (void *)d_vesc2, (void *)d_Mpre, (void *)d_mask, (void *)d_tmp, (void *)d_changed })
     ahf::dfree(q);
 }
