@@ -126,7 +126,8 @@ void ahfgpu_ctx::free_halos()
 #define API_END                                                                                         \
   return 0; }                                                                                           \
   catch (const ahf::Error &e) { ahf::g_last_error = e.msg; return -1; }                                  \
-  catch (const std::exception &e) { ahf::g_last_error = e.what(); return -2; }
+  catch (const std::exception &e) { ahf::g_last_error = e.what(); return -2; }                          \
+  catch (...) { ahf::g_last_error = "unknown exception"; return -3; }
 
 static void check_params(const ahfgpu_params *p)
 {
@@ -158,12 +159,16 @@ int ahfgpu_init(ahfgpu_ctx **out, const ahfgpu_params *par)
   CUDA_CHECK(cudaSetDevice(par->device));
   ahfgpu_ctx *c = new ahfgpu_ctx();
   c->par = *par; c->dev = par->device;
-  CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  {
+  try {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     cudaMemPool_t pool;
     CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, par->device));
     uint64_t keep = ~0ull;
     CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  } catch (...) {
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    throw;
   }
   *out = c;
   API_END
@@ -404,6 +409,7 @@ int ahfgpu_halo_fetch(ahfgpu_ctx *c, double *scal, int64_t *member_offset, int64
   API_BEGIN
   if (!c) AHF_FAIL("null ctx");
   CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));       // the library's stream is non-blocking: the legacy-stream copies below do not wait for it
   if (scal && c->nhalo) CUDA_CHECK(cudaMemcpy(scal, c->h_scal, sizeof(double) * AHFGPU_NSCAL * c->nhalo, cudaMemcpyDeviceToHost));
   if (member_offset) CUDA_CHECK(cudaMemcpy(member_offset, c->h_moff, sizeof(int64_t) * (c->nhalo + 1), cudaMemcpyDeviceToHost));
   if (members && c->h_total_members) CUDA_CHECK(cudaMemcpy(members, c->h_members, sizeof(int64_t) * c->h_total_members, cudaMemcpyDeviceToHost));
