@@ -57,6 +57,25 @@ def ncu_traffic_bytes(n1d: int):
     return None if rd is None or wr is None else rd + wr
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: keep a private handle to the real stdout and point fd 1 at stderr, so that whatever
+    NCCL, the CUDA runtime or a child process prints (e.g. 'NCCL version ...' at NCCL_DEBUG=VERSION/WARN) cannot land next to it."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -201,7 +220,7 @@ def bench_slab(args, rank, world, local_rank, config):
         config = dict(config, workload=config["workload"].replace("seed 43+rank", "seed 43"), n_particles_total=n,
                       parallelism=f"one box, {world} SFC slabs: all-to-all exchange, NCCL all-reduce of level accumulators, all-gather for the halo pass")
         config.pop("n_particles_per_gpu", None)
-        print(json.dumps({"metric": METRIC, "value": n / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        emit(({"metric": METRIC, "value": n / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                           "dtype": "f32 particles, u32/u64 fixed-point deposit, f64 halo arithmetic", "data": "synthetic", "config": config,
                           "mode": "slab", "note": "host->device upload of the rank's file-order slice is inside the timed step",
@@ -229,6 +248,7 @@ def main():
                     help="N>1: 'boxes' = one independent box per GPU (weak, no collective; default); 'slab' = ONE box of --n1d^3 particles split "
                          "into SFC slabs over the GPUs (all-to-all exchange, NCCL all-reduce of the level accumulators, all-gather for the halo pass)")
     args = ap.parse_args()
+    claim_stdout()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -264,7 +284,7 @@ def main():
                                  "kind": "reference" if have_ref else "port", "sample": sample},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "detail": detail}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------------------------------ our arm
@@ -275,8 +295,6 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ahf.build()
     if args.mode == "slab":
@@ -413,7 +431,7 @@ def main():
     if args.breakdown:
         for k, v in sorted(line["stages_ms"].items()):
             print(f"  {k:22s} {v:10.3f} ms", file=sys.stderr)
-    print(json.dumps(line))
+    emit(line)
     g.close()
     if world > 1:
         dist.destroy_process_group()
