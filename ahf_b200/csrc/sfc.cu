@@ -186,10 +186,15 @@ static void radix_sort_pairs_t(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, ui
   bh.reserve((size_t)256 * nblk);
   uint64_t *ki = keys, *ko = keys_tmp;
   uint32_t *vi = vals, *vo = vals_tmp;
+  // AHFGPU_KERNEL_STAGES=1 (bench.py's instrumented passes): event pair around every scatter launch, the largest kernel share of a pass
+  const bool ktimer = getenv("AHFGPU_KERNEL_STAGES") != nullptr;
   for (int shift = first_bit; shift < key_bits; shift += 8) {          // bits below first_bit are left to the caller (ties)
     LAUNCH(c, k_rs_hist<RS_ITEMS>, nblk, RS_THREADS, 0, ki, n, shift, bh.p, nblk);
     exclusive_scan_async<int>(c, (const int *)bh.p, (int *)bh.p, (uint64_t)256 * nblk, nullptr, bs);   // in place: each tile is read before it is written
-    LAUNCH(c, k_rs_scatter<RS_ITEMS>, nblk, RS_THREADS, RS_SMEM, ki, vi, ko, vo, n, shift, bh.p, nblk);
+    {
+      Stage sk(c, "rs_scatter_kernel", (int64_t)n, ktimer);
+      LAUNCH(c, k_rs_scatter<RS_ITEMS>, nblk, RS_THREADS, RS_SMEM, ki, vi, ko, vo, n, shift, bh.p, nblk);
+    }
     uint64_t *tk = ki; ki = ko; ko = tk;
     uint32_t *tv = vi; vi = vo; vo = tv;
   }

@@ -319,6 +319,8 @@ def main():
         # event record between kernels on the stream; the per-stage table is taken from separate instrumented passes afterwards
         g.sfc_sort_resident()
         st = {k: g.stage_ms(k) for k in ("keys", "sort", "gather")}
+        st["rs_scatter_kernel"] = g.stage_ms("rs_scatter_kernel")          # -1 unless AHFGPU_KERNEL_STAGES=1 (instrumented passes)
+        st["rs_scatter_pairs"] = g.stage_count("rs_scatter_kernel")
         g.build_amr()
         st.update({k: g.stage_ms(k) for k in ("ll", "deposit", "deposit_dom_kernel", "flag", "refine", "relink")})
         st["deposit_particles"] = g.stage_count("deposit")
@@ -352,9 +354,9 @@ def main():
     barrier()
     ms_res = g.event_elapsed_ms(0, 1) / args.steps
     launches = g.launches() - l0
-    os.environ["AHFGPU_STAGES"] = "1"
+    os.environ["AHFGPU_STAGES"] = "1"; os.environ["AHFGPU_KERNEL_STAGES"] = "1"
     stages = [step_resident() for _ in range(3)][1:]            # instrumented passes (not timed): the per-stage table
-    os.environ["AHFGPU_STAGES"] = "0"
+    os.environ["AHFGPU_STAGES"] = "0"; os.environ.pop("AHFGPU_KERNEL_STAGES", None)
     # ---- end-to-end timing (pinned host -> device every step, results back every step)
     for _ in range(min(args.warmup, 2)):
         step_e2e()
@@ -399,6 +401,13 @@ def main():
         "flags (5 sum C_l)": _rf(5.0 * sumC, st["flag"]),
         "halo pass (92 n_gathered + 21 sum_i n^(i) + 28 n_final)": _rf(92.0 * st["halo_gathered"] + 21.0 * st["halo_iter_members"] + 28.0 * st["halo_final_members"], t_halo),
     }
+    # the kernel with the largest share of a pass (profiles/*_launches_summary.txt): the ranked scatter of the main radix sort; per launch it
+    # reads and writes every (u64 key, u32 index) pair once: 24 N algorithmic bytes (SURVEY 8d counts the sort as 8 passes x 2 x 12 N)
+    roofline_kernels = {}
+    if st.get("rs_scatter_kernel", -1) > 0 and st.get("rs_scatter_pairs", 0) > 0:
+        nl = st["rs_scatter_pairs"] / n
+        roofline_kernels["k_rs_scatter (main sort)"] = dict(_rf(24.0 * st["rs_scatter_pairs"], st["rs_scatter_kernel"]), launches_per_pass=nl,
+                                                           kernel_ms_per_launch=st["rs_scatter_kernel"] / nl, bound="hbm")
     line = {
         "metric": METRIC, "value": world * n / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -411,8 +420,9 @@ def main():
                      "frac": achieved / peak, "traffic": ncu_traffic_bytes(args.n1d), "peak_source": peak_src,
                      "algorithmic_bytes": dep_bytes, "kernel_ms": st["deposit_dom_kernel"]},
         "roofline_stages": roofline_stages,
+        "roofline_kernels": roofline_kernels,
         "stages_note": "timed passes run with AHFGPU_STAGES=0 (only the domain-deposit kernel timer, which `roofline` uses); stages_ms / roofline_stages come from two separate instrumented passes, so their sum exceeds ms_per_step by the cost of ~90 event records per pass",
-        "stages_ms": {k: v for k, v in st.items() if k not in ("deposit_particles", "halo_gathered", "halo_iter_members", "halo_final_members")},
+        "stages_ms": {k: v for k, v in st.items() if k not in ("deposit_particles", "halo_gathered", "halo_iter_members", "halo_final_members", "rs_scatter_pairs")},
         "throughput": {"deposit_pps": st["deposit_particles"] / (st["deposit"] * 1e-3), "deposit_particles_all_levels": st["deposit_particles"],
                        "unbind_pps": st["halo_gathered"] / ((st["halo_gather"] + st["halo_sort"] + st["halo_unbind"] + st["halo_profiles"]) * 1e-3),
                        "halo_gathered_particles": st["halo_gathered"], "levels": nlev, "halos_in": len(rad), "halos_ge_minpart": nhalo_ok},
