@@ -73,21 +73,35 @@ constexpr int RS_WARPS   = RS_THREADS / 32;
 #define RS_TILE   (RS_THREADS * RS_ITEMS)
 #define RS_WCHUNK (RS_TILE / RS_WARPS)
 
+// Digit histogram of every scatter tile.  One CTA counts RS_HT consecutive tiles (32 keys per thread, all loads issued before the first
+// shared atomic): with one 2048-key tile per CTA the kernel was bound by CTA turnover (8192 short-lived CTAs, 43 us for 134 MB at 256^3),
+// and a thread now writes RS_HT consecutive words of the digit-major table instead of one word per 32-byte sector.
+#define RS_HT (32 / RS_ITEMS)
 template <int RS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t *__restrict__ keys, uint64_t n, int shift,
                                                         uint32_t *__restrict__ bhist, uint32_t nblk)
 {
-  __shared__ uint32_t h[256];
-  h[threadIdx.x] = 0;
+  __shared__ uint32_t h[RS_HT][256];
+#pragma unroll
+  for (int q = 0; q < RS_HT; q++) h[q][threadIdx.x] = 0;
   __syncthreads();
-  uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
-#pragma unroll 4
-  for (int i = threadIdx.x; i < RS_TILE; i += RS_THREADS) {
-    uint64_t j = base + i;
-    if (j < n) atomicAdd(&h[(uint32_t)(keys[j] >> shift) & 255u], 1u);
+  const uint32_t t0 = blockIdx.x * RS_HT;
+  const uint64_t base = (uint64_t)t0 * RS_TILE + threadIdx.x;
+  uint64_t kk[RS_HT * RS_ITEMS];
+#pragma unroll
+  for (int i = 0; i < RS_HT * RS_ITEMS; i++) {                       // element i * RS_THREADS of the CTA's span: tile i / RS_ITEMS
+    const uint64_t j = base + (uint64_t)i * RS_THREADS;
+    kk[i] = j < n ? keys[j] : 0ull;
+  }
+#pragma unroll
+  for (int i = 0; i < RS_HT * RS_ITEMS; i++) {
+    const uint64_t j = base + (uint64_t)i * RS_THREADS;
+    if (j < n) atomicAdd(&h[i / RS_ITEMS][(uint32_t)(kk[i] >> shift) & 255u], 1u);
   }
   __syncthreads();
-  bhist[(uint64_t)threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
+#pragma unroll
+  for (int q = 0; q < RS_HT; q++)
+    if (t0 + q < nblk) bhist[(uint64_t)threadIdx.x * nblk + t0 + q] = h[q][threadIdx.x];
 }
 
 
@@ -95,7 +109,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t *__restri
 // consecutive threads store consecutive addresses (a direct scatter writes 12 useful bytes per pair of 32-byte sectors).
 #define RS_SMEM (RS_TILE * 12 + RS_WARPS * 256 * 4 + 2 * 256 * 4 + 64)
 template <int RS_ITEMS>
-__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
+__global__ void __launch_bounds__(RS_THREADS, RS_ITEMS == 8 ? 4 : 2) k_rs_scatter(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
                                                            uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, uint64_t n,
                                                            int shift, const uint32_t *__restrict__ bscan, uint32_t nblk)
 {
@@ -189,7 +203,7 @@ static void radix_sort_pairs_t(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, ui
   // AHFGPU_KERNEL_STAGES=1 (bench.py's instrumented passes): event pair around every scatter launch, the largest kernel share of a pass
   const bool ktimer = getenv("AHFGPU_KERNEL_STAGES") != nullptr;
   for (int shift = first_bit; shift < key_bits; shift += 8) {          // bits below first_bit are left to the caller (ties)
-    LAUNCH(c, k_rs_hist<RS_ITEMS>, nblk, RS_THREADS, 0, ki, n, shift, bh.p, nblk);
+    LAUNCH(c, k_rs_hist<RS_ITEMS>, (nblk + RS_HT - 1) / RS_HT, RS_THREADS, 0, ki, n, shift, bh.p, nblk);
     exclusive_scan_async<int>(c, (const int *)bh.p, (int *)bh.p, (uint64_t)256 * nblk, nullptr, bs);   // in place: each tile is read before it is written
     {
       Stage sk(c, "rs_scatter_kernel", (int64_t)n, ktimer);
