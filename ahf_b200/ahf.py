@@ -108,6 +108,7 @@ def lib():
         L.ahfgpu_amr_nlevels.argtypes = [C.c_void_p]
         L.ahfgpu_amr_level_header.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.ahfgpu_amr_level_get.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 8
+        L.ahfgpu_amr_patches.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ahfgpu_amr_particle_levels.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         L.ahfgpu_construct_halos.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ahfgpu_halo_sizes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -269,6 +270,13 @@ class AhfGpu:
         else:
             self._chk(self._L.ahfgpu_amr_level_get(self._h, lev, None, None, None, _p(dens), None, None, _p(mk), _p(cnt)))
         return GpuLevel(int(io[0]), nc, int(io[2]), int(io[3]), float(do[0]), float(do[1]), x, y, z, dens, rf, it, mk, cnt)
+
+    def patches(self, lev: int):
+        """Patch colouring of ahf_gridinfo (src/libahf/ahf_gridinfo.c:236-577) on the device: (iso[ncell], periodic[niso, 3])."""
+        nc = int(self.level_header(lev)[0][1])
+        iso = np.empty(nc, np.int32); per = np.zeros((max(nc, 1), 3), np.uint8); niso = C.c_int64(0)
+        self._chk(self._L.ahfgpu_amr_patches(self._h, lev, _p(iso), C.byref(niso), _p(per)))
+        return iso, per[:niso.value].copy()
 
     def particle_levels(self, with_cells: bool = True):
         nl = self.nlevels()

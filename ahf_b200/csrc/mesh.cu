@@ -8,6 +8,7 @@
 // HBM-bound integer/float scatter work: no tensor cores.
 #include "common.cuh"
 #include "scan.cuh"
+#include "patches.cuh"
 #include "hilbert.cuh"
 
 namespace ahf {
@@ -1853,9 +1854,100 @@ __global__ void k_scatter_cells(const uint32_t *__restrict__ plist, const int32_
   out[plist ? plist[i] : i] = pcell[i];
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// NEXT-1: patch labelling of a level -- the colouring sweep of ahf_gridinfo (src/libahf/ahf_gridinfo.c:236-577,
+// numbering :751-775, periodic flags :640-672 / testBound :1090-1118) as connected components over the face neighbours the
+// reference's search sees (patches.cuh states why this equals the sequential sweep).  The cell arrays are in traversal order.
+// ------------------------------------------------------------------------------------------------
+// face neighbour d (0 x-1, 1 x+1, 2 y-1, 3 y+1, 4 z-1, 5 z+1) of cell c, -1 when the reference's search does not see it
+__device__ __forceinline__ int face_nb(const LV &v, const int32_t *__restrict__ nbr, int c, int d, int x)
+{
+  if (v.dense) {                                   // periodic full grid: everything is visible
+    const int M = (int)v.L - 1, lg = v.logL;
+    int y = (c >> lg) & M, z = c >> (2 * lg), xx = x;
+    if (d == 0) xx = (x - 1) & M; else if (d == 1) xx = (x + 1) & M;
+    else if (d == 2) y = (y - 1) & M; else if (d == 3) y = (y + 1) & M;
+    else if (d == 4) z = (z - 1) & M; else z = (z + 1) & M;
+    return (((z << lg) | y) << lg) | xx;
+  }
+  if (d == 0) return nb_get(v, nbr, c, 4, 0, x);
+  if (d == 1) return nb_get(v, nbr, c, 4, 2, x);
+  return nb_get(v, nbr, c, d == 2 ? 3 : d == 3 ? 5 : d == 4 ? 1 : 7, 1, x);
+}
+__device__ __forceinline__ int cell_x(const LV &v, int c) { return (int)((v.dense ? (uint64_t)c : v.ckey[c]) & (uint64_t)(v.L - 1)); }
+
+__global__ void k_patch_init(int32_t *__restrict__ parent, int n)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) parent[c] = c;
+}
+// edges (c, n): n visible from c and earlier in traversal order (a later neighbour is still uncoloured when the sweep visits c)
+__global__ void k_patch_link(LV v, const int32_t *__restrict__ nbr, int32_t *parent)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= v.ncell) return;
+  const int x = cell_x(v, c);
+#pragma unroll
+  for (int d = 0; d < 6; d++) {
+    const int n = face_nb(v, nbr, c, d, x);
+    if (n >= 0 && n < c) uf_unite(parent, c, n);
+  }
+}
+__global__ void k_patch_roots(int32_t *parent, int n, int32_t *__restrict__ root, uint8_t *__restrict__ isroot)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const int r = uf_find(parent, c);
+  root[c] = r; isroot[c] = (r == c) ? 1 : 0;
+}
+// isolated-refinement index = rank of the component's first cell among the first cells; periodic flags as testBound sets them
+__global__ void k_patch_iso(LV v, const int32_t *__restrict__ nbr, const int32_t *__restrict__ root, const int *__restrict__ rank,
+                            int32_t *__restrict__ iso, uint8_t *__restrict__ periodic3)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= v.ncell) return;
+  const int i = rank[root[c]];
+  iso[c] = i;
+  int x, y, z;
+  lv_coords(v, c, x, y, z);
+  if (x == 0 && face_nb(v, nbr, c, 0, x) >= 0) periodic3[3 * (size_t)i + 0] = 1;
+  if (y == 0 && face_nb(v, nbr, c, 2, x) >= 0) periodic3[3 * (size_t)i + 1] = 1;
+  if (z == 0 && face_nb(v, nbr, c, 4, x) >= 0) periodic3[3 * (size_t)i + 2] = 1;
+}
+
 }  // namespace ahf
 
 using namespace ahf;
+
+extern "C" int ahfgpu_amr_patches(ahfgpu_ctx *c, int32_t lev, int32_t *iso, int64_t *niso, uint8_t *periodic3)
+{
+  try {
+    if (!c || lev < 0 || lev >= (int)c->levels.size()) AHF_FAIL("bad level");
+    CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
+    Level &l = c->levels[lev];
+    if (!l.dense && !l.nbr) AHF_FAIL("level has no neighbour table");
+    const int nc = (int)l.ncell;
+    int ni = 0;
+    if (nc > 0) {
+      LV v = view(l);
+      DevBuf<int32_t> parent, root, diso; DevBuf<uint8_t> isroot, per; DevBuf<int> rank;
+      parent.reserve(nc); root.reserve(nc); diso.reserve(nc); isroot.reserve(nc); rank.reserve(nc); per.reserve((size_t)3 * nc);
+      LAUNCH(c, k_patch_init, nblk(nc, 256), 256, 0, parent.p, nc);
+      LAUNCH(c, k_patch_link, nblk(nc, 256), 256, 0, v, l.nbr, parent.p);
+      LAUNCH(c, k_patch_roots, nblk(nc, 256), 256, 0, parent.p, nc, root.p, isroot.p);
+      ni = exclusive_scan<uint8_t>(c, isroot.p, rank.p, (uint64_t)nc);
+      CUDA_CHECK(cudaMemsetAsync(per.p, 0, (size_t)3 * nc, c->stream));
+      LAUNCH(c, k_patch_iso, nblk(nc, 256), 256, 0, v, l.nbr, root.p, rank.p, diso.p, per.p);
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      if (iso) CUDA_CHECK(cudaMemcpy(iso, diso.p, sizeof(int32_t) * (size_t)nc, cudaMemcpyDeviceToHost));
+      if (periodic3 && ni > 0) CUDA_CHECK(cudaMemcpy(periodic3, per.p, (size_t)3 * ni, cudaMemcpyDeviceToHost));
+      parent.release(); root.release(); diso.release(); isroot.release(); rank.release(); per.release();
+    }
+    if (niso) *niso = ni;
+    return 0;
+  } catch (const ahf::Error &e) { ahf::g_last_error = e.msg; return -1; }
+}
 
 extern "C" int ahfgpu_amr_level_get(ahfgpu_ctx *c, int32_t lev, int32_t *x, int32_t *y, int32_t *z, float *dens, uint8_t *runflags,
                                     uint8_t *interior, uint8_t *mark, int32_t *count)

@@ -100,6 +100,12 @@ int  ahfgpu_amr_level_header(ahfgpu_ctx *ctx, int32_t lev, int64_t *iout, double
  *   count    particles linked to the node when the level was deposited                                      */
 int  ahfgpu_amr_level_get(ahfgpu_ctx *ctx, int32_t lev, int32_t *x, int32_t *y, int32_t *z, float *dens,
                           uint8_t *runflags, uint8_t *interior, uint8_t *mark, int32_t *count);
+/* NEXT-1 of SURVEY 8f (first step past the hot path): the patch colouring of ahf_gridinfo (src/libahf/ahf_gridinfo.c:236-577) on the
+ * device.  iso[ncell]: index of the isolated refinement (6-connected patch over the neighbours the reference's search sees) every
+ * cell of level `lev` belongs to, numbered as the reference numbers them (spatialRefIndex[colour].isoRefIndex, :751-775: in the
+ * order of their first cell); *niso: their number (numIsoRef[lev - min_ref]); periodic3[3*i + d] (capacity 3*ncell bytes, may be
+ * NULL): SRINDEX.periodic.x/y/z of patch i (testBound, :1090-1118).  Cell order as in ahfgpu_amr_level_get. */
+int  ahfgpu_amr_patches(ahfgpu_ctx *ctx, int32_t lev, int32_t *iso, int64_t *niso, uint8_t *periodic3);
 /* per particle (sorted offset): deepest level that owns it (node.ll membership after all relinks) and its cell
  * index on every level it reached: cell_of[lev*n + i] = index into the level's cell list or -1 */
 int  ahfgpu_amr_particle_levels(ahfgpu_ctx *ctx, int8_t *owner_level, int32_t *cell_of, int32_t nlev_cap);

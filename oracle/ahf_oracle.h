@@ -37,6 +37,12 @@ void      orc_hier_level_header(const orc_hier *h, int lev, int64_t *iout, doubl
 void      orc_hier_level_get(const orc_hier *h, int lev, int32_t *x, int32_t *y, int32_t *z, float *dens,
                              uint8_t *runflags, uint8_t *interior, uint8_t *mark,
                              int32_t *cnt_flag, int64_t *plist_flag, int32_t *cnt_final, int64_t *plist_final);
+/* NEXT-1: patch colouring of ahf_gridinfo (src/libahf/ahf_gridinfo.c:236-577, :719-775).  iso[ncell]: index of the
+ * isolated refinement each cell of the level belongs to, numbered as the reference numbers them; periodic3[3*niso] (may be NULL):
+ * its periodic flags (testBound, :1090-1118).  Returns the number of isolated refinements of the level. */
+int64_t   orc_hier_patches(const orc_hier *h, int lev, int32_t *iso, uint8_t *periodic3);
+/* six face neighbours per cell as the reference's neighbour search sees them: nb6[6*c + (x-1, x+1, y-1, y+1, z-1, z+1)], -1 = not visible */
+void      orc_hier_face_neighbours(const orc_hier *h, int lev, int64_t *nb6);
 void      orc_hier_free(orc_hier *h);
 
 /* ---- G/U/P: halo pass -------------------------------------------------------------------------- */

@@ -693,6 +693,108 @@ void orc_hier_level_get(const orc_hier *h, int lev, int32_t *x, int32_t *y, int3
   }
 }
 
+/* ============================================================================================== */
+/* NEXT-1: patch colouring of ahf_gridinfo (ahf_gridinfo.c:236-577)             */
+/* ============================================================================================== */
+/* colourInfo (ahf_gridinfo.c:1126-1312): the distinct non-zero colours among the six face neighbours the
+ * reference's search sees, sorted ascending into holder[0..2] (zeros first), and the action code:
+ * 0 new colour, 1 take holder[2], 2 holder[2] -> holder[1], 4 holder[2] and holder[1] -> holder[0].
+ * (The reference's codes 2 with r==g / r==b and 3 need equal non-zero entries, which a list of DISTINCT
+ * colours cannot hold.)  More than three distinct colours overflow col.holder[NDIM] in the reference:
+ * reported as -1, the caller gives up on the level. */
+static int colour_info(const olevel *lv, const int32_t *colour, int64_t c, int holder[3])
+{
+  int64_t nb[3][3][3];
+  int     t[6], u[6], nu = 0, i, j;
+  neighbours27(lv, c, nb);
+  t[0] = nb[1][0][1] >= 0 ? colour[nb[1][0][1]] : 0;      /* y-1  (r) */
+  t[1] = nb[1][1][0] >= 0 ? colour[nb[1][1][0]] : 0;      /* x-1  (g) */
+  t[2] = nb[0][1][1] >= 0 ? colour[nb[0][1][1]] : 0;      /* z-1  (b) */
+  t[3] = nb[1][2][1] >= 0 ? colour[nb[1][2][1]] : 0;      /* y+1  (t) */
+  t[4] = nb[1][1][2] >= 0 ? colour[nb[1][1][2]] : 0;      /* x+1  (h) */
+  t[5] = nb[2][1][1] >= 0 ? colour[nb[2][1][1]] : 0;      /* z+1  (n) */
+  for (i = 0; i < 6; i++) {
+    if (t[i] == 0) continue;
+    for (j = 0; j < nu; j++) if (u[j] == t[i]) break;
+    if (j == nu) u[nu++] = t[i];
+  }
+  if (nu > 3) return -1;
+  holder[0] = holder[1] = holder[2] = 0;
+  for (i = 0; i < nu; i++) holder[i] = u[i];
+  for (i = 0; i < 3; i++) for (j = i + 1; j < 3; j++) if (holder[j] < holder[i]) { int w = holder[i]; holder[i] = holder[j]; holder[j] = w; }
+  return nu == 0 ? 0 : nu == 1 ? 1 : nu == 2 ? 2 : 4;
+}
+
+static void colour_replace(int32_t *colour, int64_t c, int code, const int holder[3])
+{
+  const int cur = colour[c];
+  if (code == 2) { if (cur == holder[2]) colour[c] = holder[1]; }
+  else if (code == 4) { if (cur == holder[2] || cur == holder[1]) colour[c] = holder[0]; }
+}
+
+/* One level, the reference's sequential sweep restated literally: cells in traversal order; a cell that joins two (three)
+ * colours takes the smallest, the SPATIALREF records of the others are deleted and the sweep JUMPS BACK to the first node of
+ * the (smaller) deleted colour and walks forward replacing until it meets the first uncoloured node (ahf_gridinfo.c:300-330,
+ * :395-450, :520-560).  Surviving records in creation order are the level's isolated refinements 0, 1, ... (:751-775).
+ * iso[ncell]: isolated-refinement index per cell; periodic3[3*niso]: testBound flags (:1090-1118, :640-672).
+ * returns the number of isolated refinements, -1 where the reference itself is undefined (see colour_info). */
+int64_t orc_hier_patches(const orc_hier *h, int lev, int32_t *iso, uint8_t *periodic3)
+{
+  const olevel *lv = h->lev[lev];
+  const int64_t nc = lv->ncell;
+  int32_t *colour = (int32_t *)calloc((size_t)nc + 1, sizeof(int32_t));
+  int64_t *first  = (int64_t *)malloc(sizeof(int64_t) * ((size_t)nc + 2));     /* first node of colour k (record position) */
+  uint8_t *alive  = (uint8_t *)calloc((size_t)nc + 2, 1);
+  int32_t *rank   = (int32_t *)malloc(sizeof(int32_t) * ((size_t)nc + 2));
+  int      counter = 0, replace = 0, code = 0, holder[3] = { 0, 0, 0 };
+  int64_t  c, niso = 0;
+  for (c = 0; c < nc; c++) {
+    if (replace && colour[c] == 0) replace = 0;
+    if (replace) { colour_replace(colour, c, code, holder); continue; }
+    code = colour_info(lv, colour, c, holder);
+    if (code < 0) { niso = -1; goto done; }
+    if (code == 0) { colour[c] = ++counter; first[counter] = c; alive[counter] = 1; }
+    else if (code == 1) colour[c] = holder[2];
+    else {
+      int back;
+      if (code == 2) { colour[c] = holder[1]; alive[holder[2]] = 0; back = holder[2]; }
+      else           { colour[c] = holder[0]; alive[holder[2]] = 0; alive[holder[1]] = 0; back = holder[1]; }
+      c = first[back];                          /* the for loop's c++ follows: the first node is treated here */
+      colour_replace(colour, c, code, holder);
+      replace = 1;
+    }
+  }
+  for (c = 1; c <= counter; c++) rank[c] = alive[c] ? (int32_t)niso++ : -1;
+  if (periodic3) memset(periodic3, 0, (size_t)(3 * niso));
+  for (c = 0; c < nc; c++) {
+    iso[c] = rank[colour[c]];
+    if (periodic3 && (lv->x[c] == 0 || lv->y[c] == 0 || lv->z[c] == 0) && iso[c] >= 0) {
+      int64_t nb[3][3][3];
+      neighbours27(lv, c, nb);
+      if (lv->x[c] == 0 && nb[1][1][0] >= 0) periodic3[3 * iso[c] + 0] = 1;
+      if (lv->y[c] == 0 && nb[1][0][1] >= 0) periodic3[3 * iso[c] + 1] = 1;
+      if (lv->z[c] == 0 && nb[0][1][1] >= 0) periodic3[3 * iso[c] + 2] = 1;
+    }
+  }
+done:
+  free(colour); free(first); free(alive); free(rank);
+  return niso;
+}
+
+/* the six face neighbours of every cell as the reference's search sees them (get_TSCnodes): nb6[6*c + d], d = x-1, x+1, y-1,
+ * y+1, z-1, z+1; -1 = not visible.  Lets tests state the colouring as a graph problem (ahf_b200/csrc/patches.cuh). */
+void orc_hier_face_neighbours(const orc_hier *h, int lev, int64_t *nb6)
+{
+  const olevel *lv = h->lev[lev];
+  int64_t c, nb[3][3][3];
+  for (c = 0; c < lv->ncell; c++) {
+    neighbours27(lv, c, nb);
+    nb6[6 * c + 0] = nb[1][1][0]; nb6[6 * c + 1] = nb[1][1][2];
+    nb6[6 * c + 2] = nb[1][0][1]; nb6[6 * c + 3] = nb[1][2][1];
+    nb6[6 * c + 4] = nb[0][1][1]; nb6[6 * c + 5] = nb[2][1][1];
+  }
+}
+
 void orc_hier_free(orc_hier *h)
 {
   int l;

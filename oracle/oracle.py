@@ -46,6 +46,9 @@ def lib():
         L.orc_hier_level_header.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_hier_level_get.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 11
         L.orc_hier_free.argtypes = [C.c_void_p]
+        L.orc_hier_face_neighbours.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_hier_patches.restype = C.c_int64
+        L.orc_hier_patches.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         if hasattr(L, "orc_halo_construct"):
             L.orc_halo_construct.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
             L.orc_halo_result_free.argtypes = [C.c_void_p]
@@ -89,6 +92,9 @@ class Level:
     mark: np.ndarray | None = None
     cnt_final: np.ndarray | None = None
     plist_final: np.ndarray | None = None
+    iso: np.ndarray | None = None               # isolated-refinement index per cell (ahf_gridinfo colouring), build_hierarchy(patches=True)
+    iso_periodic: np.ndarray | None = None      # [niso, 3] periodic flags of the isolated refinements
+    nb6: np.ndarray | None = None               # [ncell, 6] visible face neighbours (x-1, x+1, y-1, y+1, z-1, z+1), -1 = none
 
     def lin(self) -> np.ndarray:
         L = np.int64(self.l1dim)
@@ -96,7 +102,7 @@ class Level:
 
 
 def build_hierarchy(pos_sorted: np.ndarray, lgrid_dom: int, lgrid_max: int = 1 << 21, nth_dom: float = 2.0,
-                    nth_ref: float = 2.5) -> list[Level]:
+                    nth_ref: float = 2.5, patches: bool = False) -> list[Level]:
     pos_sorted = np.ascontiguousarray(pos_sorted, dtype=np.float32)
     L = lib()
     h = L.orc_hier_build(_p(pos_sorted), pos_sorted.shape[0], lgrid_dom, lgrid_max, nth_dom, nth_ref)
@@ -115,6 +121,15 @@ def build_hierarchy(pos_sorted: np.ndarray, lgrid_dom: int, lgrid_max: int = 1 <
                                  _p(cfin), _p(pfin))
             out.append(Level(int(io[0]), nc, float(do[0]), float(do[1]), x, y, z, dens, rf, cf, pf[:nf], it, mk,
                              cfin, pfin[:nfin]))
+            if patches and lev > 0:             # the reference colours refinement levels only (from ahf.min_ref >= 1)
+                iso = np.empty(nc, np.int32); per = np.zeros((nc, 3), np.uint8)
+                niso = int(L.orc_hier_patches(h, lev, _p(iso), _p(per)))
+                if niso < 0:
+                    raise RuntimeError(f"level {lev}: a cell joins more than three colours (undefined in the reference, ahf_gridinfo.c:1246)")
+                out[-1].iso = iso; out[-1].iso_periodic = per[:niso].copy()
+                nb6 = np.empty((nc, 6), np.int64)
+                L.orc_hier_face_neighbours(h, lev, _p(nb6))
+                out[-1].nb6 = nb6
     finally:
         L.orc_hier_free(h)
     return out
@@ -153,6 +168,19 @@ def read_particles(path: str, multimass: bool = False) -> RefParticles:
             w = np.fromfile(f, np.float32, n)
             u = np.fromfile(f, np.float32, n)
     return RefParticles(n, sc[0], sc[1], sc[2], sc[3], sc[4], sc[5], sc[6], ids, keys, pos, mom, w, u)
+
+
+def read_patches(path: str):
+    """patches.bin of oracle/ref_hooks.c dump_patches(): (min_ref, [(iso[ncell], periodic[niso,3]) per coloured level])"""
+    with open(path, "rb") as f:
+        min_ref, ngrids = (int(v) for v in np.fromfile(f, np.int32, 2))
+        out = []
+        for _ in range(max(ngrids, 0)):
+            nc, niso = (int(v) for v in np.fromfile(f, np.int64, 2))
+            iso = np.fromfile(f, np.int32, nc)
+            per = np.fromfile(f, np.int8, 3 * niso).reshape(niso, 3)
+            out.append((iso, per))
+    return min_ref, out
 
 
 def read_level(path: str) -> Level:

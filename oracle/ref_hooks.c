@@ -203,6 +203,56 @@ boolean refhook_relink(gridls *coa, gridls *fin)
   return r;
 }
 
+/* NEXT-1: the outcome of the patch colouring of ahf_gridinfo (ahf_gridinfo.c:236-577, :719-775), read from the
+ * reference's own globals after the call: per coloured level the isolated-refinement index of every node in traversal order
+ * (spatialRefIndex[node colour].isoRefIndex), the number of isolated refinements and their periodic flags. */
+extern SRINDEX *spatialRefIndex;
+extern int     *numIsoRef;
+static void dump_patches(void)
+{
+  FILE   *f = dump_open("patches.bin");
+  int32_t hdr[2];
+  int     i;
+  hdr[0] = ahf.min_ref; hdr[1] = ahf.no_grids;
+  fwrite(hdr, sizeof(int32_t), 2, f);
+  for (i = 0; i < ahf.no_grids; i++) {
+    gridls *g = global.dom_grid + ahf.min_ref + i;
+    pqptr   pq; cqptr cq, icq; nqptr nq, inq; nptr nd;
+    int64_t ncell = 0, ic = 0, lh[2];
+    int32_t *iso;
+    int8_t  *per = calloc((size_t)(3 * numIsoRef[i] + 3), 1);
+    int      pass;
+    iso = NULL;
+    for (pass = 0; pass < 2; pass++) {
+      ic = 0;
+      for (pq = g->pquad; pq != NULL; pq = pq->next)
+        for (cq = pq->loc; cq < pq->loc + pq->length; cq++)
+          for (icq = cq; icq != NULL; icq = icq->next)
+            for (nq = icq->loc; nq < icq->loc + icq->length; nq++)
+              for (inq = nq; inq != NULL; inq = inq->next)
+                for (nd = inq->loc; nd < inq->loc + inq->length; nd++) {
+                  if (pass == 1) {
+                    const SRINDEX *sr = spatialRefIndex + nd->force.colour;
+                    iso[ic] = (sr->refLevel == i) ? sr->isoRefIndex : -1000 - sr->refLevel;
+                    if (sr->refLevel == i && sr->isoRefIndex >= 0 && sr->isoRefIndex < numIsoRef[i]) {
+                      per[3 * sr->isoRefIndex + 0] = (int8_t)sr->periodic.x;
+                      per[3 * sr->isoRefIndex + 1] = (int8_t)sr->periodic.y;
+                      per[3 * sr->isoRefIndex + 2] = (int8_t)sr->periodic.z;
+                    }
+                  }
+                  ic++;
+                }
+      if (pass == 0) { ncell = ic; iso = malloc(sizeof(int32_t) * (size_t)(ncell + 1)); }
+    }
+    lh[0] = ncell; lh[1] = numIsoRef[i];
+    fwrite(lh, sizeof(int64_t), 2, f);
+    fwrite(iso, sizeof(int32_t), (size_t)ncell, f);
+    fwrite(per, 1, (size_t)(3 * numIsoRef[i]), f);
+    free(iso); free(per);
+  }
+  fclose(f);
+}
+
 void refhook_ahf_gridinfo(gridls *grid_list, int curgrid_no)
 {
   double t;
@@ -224,6 +274,7 @@ void refhook_ahf_gridinfo(gridls *grid_list, int curgrid_no)
   t = omp_get_wtime();
   ahf_gridinfo(grid_list, curgrid_no);
   t_gridinfo += omp_get_wtime() - t;
+  if (dump_dir()) dump_patches();
 }
 
 /* ------------------------------------------------------------------------------------------ */

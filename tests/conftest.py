@@ -43,6 +43,13 @@ class Golden:
         return {k: self.d[p + k] for k in ("l1dim", "critdens", "masstopartdens", "x", "y", "z", "dens", "runflags", "cnt",
                                            "plist", "cnt_final", "plist_final")}
 
+    def patches(self):
+        """(min_ref, {level: (iso[ncell], periodic[niso, 3])}) from tests/golden/patches.npz: the outcome of the reference's patch
+        colouring (ahf_gridinfo) for this case, written by tests/golden/make_golden.py patches"""
+        P = np.load(os.path.join(GOLDEN_DIR, "patches.npz"))
+        m = int(P[self.name + "_min_ref"]); n = int(P[self.name + "_nlev"])
+        return m, {l: (P["%s_L%d_iso" % (self.name, l)].astype(np.int32), P["%s_L%d_per" % (self.name, l)]) for l in range(m, m + n)}
+
     def members(self, i):
         return self.d["halo_members"][self.d["halo_moff"][i]:self.d["halo_moff"][i + 1]].astype(np.int64)
 

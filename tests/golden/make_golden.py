@@ -2,7 +2,8 @@
 /root/reference by oracle/build_ref.sh) on small synthetic boxes and collecting the hook dumps
 (oracle/ref_hooks.c).  Only runnable where the reference binary exists; the .npz files are committed.
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py              # the per-case fixtures
+    python tests/golden/make_golden.py patches      # tests/golden/patches.npz: the patch colouring of ahf_gridinfo for the same cases
 """
 import os
 import shutil
@@ -73,8 +74,40 @@ def collect(name, n1d, seed, ncl, nper_dom, nper_ref, centres, species=False):
         shutil.rmtree(work, ignore_errors=True)
 
 
+def collect_patches():
+    """patches.npz: per case the first coloured level (ahf.min_ref) and, per coloured level, the isolated-refinement index of every
+    node in traversal order plus the periodic flags of the isolated refinements (oracle/ref_hooks.c dump_patches)."""
+    out = {}
+    for table, species in ((CASES, False), (CASES_MM, True)):
+        for name, (n1d, seed, ncl, nper_dom, nper_ref, centres) in table.items():
+            work = tempfile.mkdtemp(prefix="ahf_golden_")
+            try:
+                cb = None if centres is None else np.array(centres)
+                if species:
+                    inp = synth.write_reference_case_species(synth.make_species_box(n1d, seed=seed, n_clumps=ncl, centres_box=cb), work,
+                                                             nper_dom=nper_dom, nper_ref=nper_ref)
+                else:
+                    inp = synth.write_reference_case(synth.make_box(n1d, seed=seed, n_clumps=ncl, centres_box=cb), work,
+                                                     nper_dom=nper_dom, nper_ref=nper_ref)
+                O.run_reference(inp, dump_dir=os.path.join(work, "dump"), threads=1, multimass=species)
+                min_ref, levels = O.read_patches(os.path.join(work, "dump", "patches.bin"))
+                out[name + "_min_ref"] = min_ref; out[name + "_nlev"] = len(levels)
+                for i, (iso, per) in enumerate(levels):
+                    out["%s_L%d_iso" % (name, min_ref + i)] = iso.astype(np.int16 if iso.max() < 32000 else np.int32)
+                    out["%s_L%d_per" % (name, min_ref + i)] = per.astype(np.uint8)
+                print(name, "min_ref", min_ref, "coloured levels", len(levels), "patches", [p.shape[0] for _, p in levels])
+            finally:
+                shutil.rmtree(work, ignore_errors=True)
+    path = os.path.join(ROOT, "tests", "golden", "patches.npz")
+    np.savez_compressed(path, **out)
+    print("patches.npz bytes", os.path.getsize(path))
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
+    if only == ["patches"]:
+        collect_patches()
+        sys.exit(0)
     for k, v in CASES.items():
         if not only or k in only:
             collect(k, *v)

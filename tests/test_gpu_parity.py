@@ -86,6 +86,28 @@ def test_amr_matches_reference(A, golden):
         print("max density error", worst)
 
 
+def test_patch_labels_match_reference(A, golden):
+    """NEXT-1: the patch colouring of ahf_gridinfo (src/libahf/ahf_gridinfo.c:236-577) on the device -- union-find over
+    the neighbour table (ahfgpu_amr_patches) -- numbers the isolated refinements of every level as the unmodified reference does
+    (tests/golden/patches.npz, its coloured levels) and as the CPU restatement of the sweep does (every refinement level)."""
+    from oracle import oracle as O
+    min_ref, ref = golden.patches()
+    H = O.build_hierarchy(golden.pos, golden.n1d, nth_dom=golden.nper_dom, nth_ref=golden.nper_ref, patches=True)
+    with _ctx(A, golden) as g:
+        g.sfc_sort(golden.pos, golden.mom, golden.weight, golden.u)
+        nl = g.build_amr()
+        assert nl == len(H)
+        for l in range(1, nl):
+            iso, per = g.patches(l)
+            assert np.array_equal(iso, H[l].iso), "patch labels differ from the restated sweep on level %d" % l
+            assert np.array_equal(per, H[l].iso_periodic), l
+            if l in ref:
+                assert np.array_equal(iso, ref[l][0]), "patch labels differ from the reference on level %d" % l
+                assert np.array_equal(per, ref[l][1]), l
+        iso0, per0 = g.patches(0)                     # the periodic domain grid is one patch, periodic in all three directions
+        assert iso0.min() == 0 and iso0.max() == 0 and per0.tolist() == [[1, 1, 1]]
+
+
 def _check_halos(g, golden, rtol=1e-9):
     res = g.construct_halos(golden.hs[:, 0:3].copy(), golden.hs[:, 3].copy(), golden.hs[:, 4].astype(np.int64))
     S = res["scal"]

@@ -144,3 +144,42 @@ extern "C" int hil_check(const float *pos, const unsigned long long *keys, long 
     L.hil_check.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
     pos = np.ascontiguousarray(golden.pos, np.float32); keys = np.ascontiguousarray(golden.keys, np.uint64)
     assert L.hil_check(pos.ctypes.data, keys.ctypes.data, len(keys)) == 0
+
+
+def test_patch_labels_as_union_find_equal_the_sweep(tmp_path, golden):
+    """patches.cuh is host+device code: the union-find the device kernels run (edges to the VISIBLE face neighbours EARLIER in
+    traversal order, larger root hooked under the smaller, patches numbered by the rank of their first cell) gives the labels of
+    the reference's sequential colouring sweep -- in traversal order and with the cells visited in a scrambled order."""
+    from oracle import oracle as O
+    src = tmp_path / "uf.cpp"
+    src.write_text('''
+#include "ahf_b200/csrc/patches.cuh"
+#include <vector>
+extern "C" long uf_labels(const long long *nb6, long ncell, int *iso, int seed) {
+  std::vector<int32_t> parent(ncell);
+  std::vector<long> ord(ncell);
+  for (long c = 0; c < ncell; c++) { parent[c] = (int32_t)c; ord[c] = c; }
+  unsigned long long s = (unsigned long long)seed;
+  if (seed) for (long c = ncell - 1; c > 0; c--) { s = s * 6364136223846793005ull + 1442695040888963407ull; long j = (long)((s >> 33) % (unsigned long long)(c + 1)); long t = ord[c]; ord[c] = ord[j]; ord[j] = t; }
+  for (long q = 0; q < ncell; q++) {
+    const long c = ord[q];
+    for (int d = 0; d < 6; d++) { const long long n = nb6[6 * c + d]; if (n >= 0 && n < c) ahf::uf_unite(parent.data(), (int32_t)c, (int32_t)n); }
+  }
+  std::vector<int> rank(ncell, -1);
+  long niso = 0;
+  for (long c = 0; c < ncell; c++) if (ahf::uf_find(parent.data(), (int32_t)c) == c) rank[c] = (int)niso++;
+  for (long c = 0; c < ncell; c++) iso[c] = rank[ahf::uf_find(parent.data(), (int32_t)c)];
+  return niso;
+}
+''')
+    so = tmp_path / "uf.so"
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", "-I", ROOT, "-o", str(so), str(src)])
+    L = C.CDLL(str(so))
+    L.uf_labels.restype = C.c_long
+    L.uf_labels.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_int]
+    H = O.build_hierarchy(golden.pos, golden.n1d, nth_dom=golden.nper_dom, nth_ref=golden.nper_ref, patches=True)
+    for lv in H[1:]:
+        for seed in (0, 7):
+            iso = np.empty(lv.ncell, np.int32)
+            n = L.uf_labels(lv.nb6.ctypes.data, lv.ncell, iso.ctypes.data, seed)
+            assert n == lv.iso_periodic.shape[0] and np.array_equal(iso, lv.iso)

@@ -57,3 +57,15 @@ def test_halo_pass_matches_reference(golden):
             assert golden.species(i)[0] + golden.species(i)[32] > 0
             assert np.allclose(golden.species(i), r["species"], rtol=1e-12, atol=0), (i, np.nonzero(~np.isclose(golden.species(i), r["species"], rtol=1e-12, atol=0)))
             assert np.allclose(golden.prof_species(i), r["prof_species"], rtol=1e-12, atol=0)
+
+
+def test_patch_colouring_matches_reference(golden):
+    """NEXT-1: the literal restatement of the colouring sweep of ahf_gridinfo (ahf_gridinfo.c:236-577) numbers the isolated
+    refinements of every coloured level exactly as the reference does, periodic flags included."""
+    min_ref, ref = golden.patches()
+    H = O.build_hierarchy(golden.pos, golden.n1d, nth_dom=golden.nper_dom, nth_ref=golden.nper_ref, patches=True)
+    assert min_ref >= 1 and max(ref) == len(H) - 1
+    for l, (iso, per) in ref.items():
+        assert np.array_equal(H[l].iso, iso), l
+        assert np.array_equal(H[l].iso_periodic, per), l
+        assert iso.min() == 0 and iso.max() == per.shape[0] - 1
