@@ -43,6 +43,11 @@ void      orc_hier_level_get(const orc_hier *h, int lev, int32_t *x, int32_t *y,
 int64_t   orc_hier_patches(const orc_hier *h, int lev, int32_t *iso, uint8_t *periodic3);
 /* six face neighbours per cell as the reference's neighbour search sees them: nb6[6*c + (x-1, x+1, y-1, y+1, z-1, z+1)], -1 = not visible */
 void      orc_hier_face_neighbours(const orc_hier *h, int lev, int64_t *nb6);
+/* NEXT-2, first half: RefCentre (src/libahf/ahf_halos.c:935-1390).  out[niso][ORC_NPATCH]: 0 numNodes, 1 numParts, 2-4 centre
+ * (= centreCMpart: the shipped define.h:101 sets AHFcomcentre), 5 maxDens, 6-8 centreGEOM, 9-11 centreDens; iso / periodic3 / niso from
+ * orc_hier_patches of the same level. */
+#define ORC_NPATCH 12
+void      orc_hier_patch_centres(const orc_hier *h, int lev, const int32_t *iso, const uint8_t *periodic3, int64_t niso, double *out);
 void      orc_hier_free(orc_hier *h);
 
 /* ---- G/U/P: halo pass -------------------------------------------------------------------------- */

@@ -795,6 +795,63 @@ void orc_hier_face_neighbours(const orc_hier *h, int lev, int64_t *nb6)
   }
 }
 
+/* ============================================================================================== */
+/* NEXT-2, first half: RefCentre (ahf_halos.c:935-1390) -- per isolated refinement the node and     */
+/* particle counts and the geometric / density-weighted / particle centres                         */
+/* ============================================================================================== */
+static double f1mod1x(double v) { return v >= 2.0 ? v - 2.0 : v >= 1.0 ? v - 1.0 : v; }     /* specific.c:120-129 */
+
+/* iso / periodic3 / niso as returned by orc_hier_patches for the same level.  out[niso][ORC_NPATCH]:
+ *   0 numNodes, 1 numParts, 2-4 centre = centreCMpart (the shipped define.h:101 sets AHFcomcentre: the halo centre is the centre of
+ *   mass of the particles linked to the refinement; GEOM where it holds none, ahf_halos.c:1276-1298, :1366-1370), 5 maxDens,
+ *   6-8 centreGEOM, 9-11 centreDens (density weighted, with the reference's fall-backs :1248-1274, :1329-1350).
+ * Sums run in the reference's order: nodes in traversal order, the particles of a node in list order (ahf_halos.c:1012-1200);
+ * node positions are cell centres in double, shifted by one box where the refinement is periodic and the coordinate < 0.5
+ * (:1032-1040); tmpDens = dens + mean_dens (= 1), negative values count as zero (:1057-1075). */
+void orc_hier_patch_centres(const orc_hier *h, int lev, const int32_t *iso, const uint8_t *periodic3, int64_t niso, double *out)
+{
+  const olevel *lv = h->lev[lev];
+  const double  L = (double)lv->L, shift = 0.5 / (double)lv->L;
+  double *acc = (double *)calloc((size_t)niso * 16 + 1, sizeof(double));   /* 0 nodes 1 parts | 2-5 geom+norm | 6-9 dens+norm | 10 maxDens | 11-14 cm+norm */
+  int64_t c, i, ip = 0;
+  for (i = 0; i < niso; i++) acc[16 * i + 10] = -1.0;                       /* ahf_halos.c:288 */
+  for (c = 0; c < lv->ncell; c++) {
+    double *a = acc + 16 * (int64_t)iso[c];
+    const uint8_t *per = periodic3 + 3 * (int64_t)iso[c];
+    double xx = fmod((double)lv->x[c] / L + shift + 1.0, 1.0), yy = fmod((double)lv->y[c] / L + shift + 1.0, 1.0),
+           zz = fmod((double)lv->z[c] / L + shift + 1.0, 1.0), d;
+    int32_t k;
+    if (per[0] && xx < 0.5) xx += 1.0;
+    if (per[1] && yy < 0.5) yy += 1.0;
+    if (per[2] && zz < 0.5) zz += 1.0;
+    a[0] += 1.0;
+    a[2] += xx; a[3] += yy; a[4] += zz; a[5] += 1.0;
+    d = (double)lv->dens[c] + 1.0;
+    if (d < 0.0) d = 0.0;
+    a[6] += xx * d; a[7] += yy * d; a[8] += zz * d; a[9] += d;
+    if (d > a[10]) a[10] = d;
+    for (k = 0; k < lv->cnt_final[c]; k++, ip++) {
+      const int64_t p = lv->plist_final[ip];
+      double xp = (double)h->pos[3 * p], yp = (double)h->pos[3 * p + 1], zp = (double)h->pos[3 * p + 2];
+      if (per[0] && xp < 0.5) xp += 1.0;
+      if (per[1] && yp < 0.5) yp += 1.0;
+      if (per[2] && zp < 0.5) zp += 1.0;
+      a[11] += xp; a[12] += yp; a[13] += zp; a[14] += 1.0; a[1] += 1.0;
+    }
+  }
+  for (i = 0; i < niso; i++) {
+    const double *a = acc + 16 * i;
+    double *o = out + ORC_NPATCH * i;
+    int q;
+    o[0] = a[0]; o[1] = a[1]; o[5] = a[10];
+    for (q = 0; q < 3; q++) o[6 + q] = a[5] > 0 ? f1mod1x(a[2 + q] / a[5] + 1.0) : a[2 + q];
+    for (q = 0; q < 3; q++) o[9 + q] = a[9] > 0 ? f1mod1x(a[6 + q] / a[9] + 1.0) : o[6 + q];
+    for (q = 0; q < 3; q++) o[2 + q] = a[14] > 0 ? f1mod1x(a[11 + q] / a[14] + 1.0) : o[6 + q];
+    if (a[10] <= 5e-16) for (q = 0; q < 3; q++) o[9 + q] = o[6 + q];       /* MACHINE_ZERO, ahf_halos.c:1329-1350 */
+  }
+  free(acc);
+}
+
 void orc_hier_free(orc_hier *h)
 {
   int l;

@@ -6,6 +6,9 @@
 #                              dumps when $AHF_DUMP_DIR is set).  Arithmetic untouched: the hooks are reached by
 #                              compiling the CALLING translation units with -Dcallee=refhook_callee.
 #   oracle/_ref/ahf_ref_mm     same, built with -DMULTIMASS -DGAS_PARTICLES (multi-species config)
+#   oracle/_ref/ahf_ref_gt     same as ahf_ref plus the reference's own -DAHFgridtreefile option (define.h:108): ahf_halos writes
+#                              <prefix>.AHF_gridtree -- centre, node / particle counts and tree links of every isolated refinement
+#                              after RefCentre + analyseRef (ahf_halos.c:3066-3120); the pin of the NEXT-2 restatement
 #
 # Flags follow the reference's default SYSTEM "Standard OpenMP" (Makefile.config:17,200-208):
 #   gcc -fopenmp -std=c99 -O2 -DWITH_OPENMP -DAHF
@@ -56,4 +59,5 @@ build_variant() {
 
 build_variant ahf_ref
 build_variant ahf_ref_mm -DMULTIMASS -DGAS_PARTICLES
+build_variant ahf_ref_gt -DAHFgridtreefile
 ls -la "$OUT"

@@ -16,6 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libahf_oracle.so")
 REF_BIN = os.path.join(HERE, "_ref", "ahf_ref")
 REF_BIN_MM = os.path.join(HERE, "_ref", "ahf_ref_mm")
+REF_BIN_GT = os.path.join(os.path.dirname(REF_BIN), "ahf_ref_gt")      # -DAHFgridtreefile variant (writes .AHF_gridtree)
 
 _lib = None
 
@@ -47,6 +48,7 @@ def lib():
         L.orc_hier_level_get.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 11
         L.orc_hier_free.argtypes = [C.c_void_p]
         L.orc_hier_face_neighbours.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_hier_patch_centres.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.orc_hier_patches.restype = C.c_int64
         L.orc_hier_patches.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         if hasattr(L, "orc_halo_construct"):
@@ -95,6 +97,7 @@ class Level:
     iso: np.ndarray | None = None               # isolated-refinement index per cell (ahf_gridinfo colouring), build_hierarchy(patches=True)
     iso_periodic: np.ndarray | None = None      # [niso, 3] periodic flags of the isolated refinements
     nb6: np.ndarray | None = None               # [ncell, 6] visible face neighbours (x-1, x+1, y-1, y+1, z-1, z+1), -1 = none
+    patch: np.ndarray | None = None             # [niso, 12] RefCentre: numNodes, numParts, centre(3) (= particle centre of mass, AHFcomcentre), maxDens, centreGEOM(3), centreDens(3)
 
     def lin(self) -> np.ndarray:
         L = np.int64(self.l1dim)
@@ -130,6 +133,10 @@ def build_hierarchy(pos_sorted: np.ndarray, lgrid_dom: int, lgrid_max: int = 1 <
                 nb6 = np.empty((nc, 6), np.int64)
                 L.orc_hier_face_neighbours(h, lev, _p(nb6))
                 out[-1].nb6 = nb6
+                pc = np.zeros((max(niso, 1), 12), np.float64)
+                per_c = np.ascontiguousarray(per[:max(niso, 1)])
+                L.orc_hier_patch_centres(h, lev, _p(iso), _p(per_c), niso, _p(pc))
+                out[-1].patch = pc[:niso]
     finally:
         L.orc_hier_free(h)
     return out
@@ -180,6 +187,27 @@ def read_patches(path: str):
             iso = np.fromfile(f, np.int32, nc)
             per = np.fromfile(f, np.int8, 3 * niso).reshape(niso, 3)
             out.append((iso, per))
+    return min_ref, out
+
+
+def read_gridtree(path: str):
+    """<prefix>.AHF_gridtree of the reference built with -DAHFgridtreefile (ahf_halos.c:3066-3120):
+    (min_ref, {level: dict(centre[n,3], close[n], nodes[n], parts[n], daughter[n,2], sub=[list of (level, index)])})"""
+    with open(path) as f:
+        tok = f.read().split()
+    it = iter(tok)
+    min_ref, ngrids = int(next(it)), int(next(it))
+    out = {}
+    for _ in range(ngrids):
+        lev, n = int(next(it)), int(next(it))
+        cen = np.zeros((n, 3)); close = np.zeros(n); nodes = np.zeros(n, np.int64); parts = np.zeros(n, np.int64)
+        dau = np.zeros((n, 2), np.int64); sub = []
+        for j in range(n):
+            cen[j] = [float(next(it)) for _ in range(3)]; close[j] = float(next(it))
+            nodes[j] = int(next(it)); parts[j] = int(next(it)); dau[j] = [int(next(it)), int(next(it))]
+            ns = int(next(it))
+            sub.append([(int(next(it)), int(next(it))) for _ in range(ns)])
+        out[lev] = dict(centre=cen, close=close, nodes=nodes, parts=parts, daughter=dau, sub=sub)
     return min_ref, out
 
 

@@ -50,6 +50,16 @@ class Golden:
         m = int(P[self.name + "_min_ref"]); n = int(P[self.name + "_nlev"])
         return m, {l: (P["%s_L%d_iso" % (self.name, l)].astype(np.int32), P["%s_L%d_per" % (self.name, l)]) for l in range(m, m + n)}
 
+    def gridtree(self):
+        """{level: dict(centre, close, nodes, parts, daughter, sub_off, sub)} from tests/golden/gridtree.npz (the reference's own
+        .AHF_gridtree, -DAHFgridtreefile build; default-build cases only) or None"""
+        P = np.load(os.path.join(GOLDEN_DIR, "gridtree.npz"))
+        if self.name + "_min_ref" not in P.files:
+            return None
+        m = int(P[self.name + "_min_ref"]); n = int(P[self.name + "_nlev"])
+        return {l: {k: P["%s_L%d_%s" % (self.name, l, k)] for k in ("centre", "close", "nodes", "parts", "daughter", "sub_off", "sub")}
+                for l in range(m, m + n)}
+
     def members(self, i):
         return self.d["halo_members"][self.d["halo_moff"][i]:self.d["halo_moff"][i + 1]].astype(np.int64)
 

@@ -4,6 +4,7 @@
 
     python tests/golden/make_golden.py              # the per-case fixtures
     python tests/golden/make_golden.py patches      # tests/golden/patches.npz: the patch colouring of ahf_gridinfo for the same cases
+    python tests/golden/make_golden.py gridtree     # tests/golden/gridtree.npz: the reference's own .AHF_gridtree (-DAHFgridtreefile build)
 """
 import os
 import shutil
@@ -103,8 +104,42 @@ def collect_patches():
     print("patches.npz bytes", os.path.getsize(path))
 
 
+def collect_gridtree():
+    """gridtree.npz: what the reference built with its -DAHFgridtreefile option (oracle/_ref/ahf_ref_gt) writes after RefCentre and
+    analyseRef (ahf_halos.c:3066-3120): per isolated refinement the centre, closeRefDist, node / particle counts, the daughter and the
+    substructure links.  Default-build cases only."""
+    import glob
+    import subprocess
+    out = {}
+    for name, (n1d, seed, ncl, nper_dom, nper_ref, centres) in CASES.items():
+        work = tempfile.mkdtemp(prefix="ahf_golden_")
+        try:
+            cb = None if centres is None else np.array(centres)
+            inp = synth.write_reference_case(synth.make_box(n1d, seed=seed, n_clumps=ncl, centres_box=cb), work, nper_dom=nper_dom, nper_ref=nper_ref)
+            env = dict(os.environ, OMP_NUM_THREADS="1")
+            env.pop("AHF_DUMP_DIR", None)
+            subprocess.run([O.REF_BIN_GT, inp], cwd=work, env=env, capture_output=True, text=True, check=True)
+            min_ref, T = O.read_gridtree(glob.glob(os.path.join(work, "*.AHF_gridtree"))[0])
+            out[name + "_min_ref"] = min_ref; out[name + "_nlev"] = len(T)
+            for lev, t in T.items():
+                p = "%s_L%d_" % (name, lev)
+                out[p + "centre"] = t["centre"]; out[p + "close"] = t["close"]; out[p + "nodes"] = t["nodes"]; out[p + "parts"] = t["parts"]
+                out[p + "daughter"] = t["daughter"]
+                out[p + "sub_off"] = np.concatenate([[0], np.cumsum([len(x) for x in t["sub"]])]).astype(np.int64)
+                out[p + "sub"] = np.array([y for x in t["sub"] for y in x], np.int64).reshape(-1, 2)
+            print(name, "min_ref", min_ref, "patches per level", [len(t["nodes"]) for t in T.values()])
+        finally:
+            shutil.rmtree(work, ignore_errors=True)
+    path = os.path.join(ROOT, "tests", "golden", "gridtree.npz")
+    np.savez_compressed(path, **out)
+    print("gridtree.npz bytes", os.path.getsize(path))
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
+    if only == ["gridtree"]:
+        collect_gridtree()
+        sys.exit(0)
     if only == ["patches"]:
         collect_patches()
         sys.exit(0)

@@ -69,3 +69,24 @@ def test_patch_colouring_matches_reference(golden):
         assert np.array_equal(H[l].iso, iso), l
         assert np.array_equal(H[l].iso_periodic, per), l
         assert iso.min() == 0 and iso.max() == per.shape[0] - 1
+
+
+def test_patch_centres_match_reference_gridtree(golden):
+    """NEXT-2, first half: RefCentre (ahf_halos.c:935-1390).  Node and particle counts of every isolated refinement are those of the
+    reference's own .AHF_gridtree, its centres (centre of mass of the linked particles, AHFcomcentre in the shipped define.h) agree
+    to the 14 decimals the file prints."""
+    T = golden.gridtree()
+    if T is None:
+        import pytest
+        pytest.skip("no -DAHFgridtreefile variant of the multi-species build")
+    H = O.build_hierarchy(golden.pos, golden.n1d, nth_dom=golden.nper_dom, nth_ref=golden.nper_ref, patches=True)
+    for l, t in T.items():
+        pc = H[l].patch
+        assert np.array_equal(pc[:, 0].astype(np.int64), t["nodes"]) and np.array_equal(pc[:, 1].astype(np.int64), t["parts"]), l
+        d = np.abs(pc[:, 2:5] - t["centre"])
+        assert np.minimum(d, 1.0 - d).max() <= 6e-15, (l, d.max())
+        # a leaf refinement holds every particle that deposits on it, and TSC preserves the first moment: density-weighted == particle centre
+        leaf = t["daughter"][:, 1] < 0
+        if leaf.any():
+            dd = np.abs(pc[leaf, 9:12] - pc[leaf, 2:5])
+            assert np.minimum(dd, 1.0 - dd).max() < 1e-6
