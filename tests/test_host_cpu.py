@@ -183,3 +183,54 @@ extern "C" long uf_labels(const long long *nb6, long ncell, int *iso, int seed) 
             iso = np.empty(lv.ncell, np.int32)
             n = L.uf_labels(lv.nb6.ctypes.data, lv.ncell, iso.ctypes.data, seed)
             assert n == lv.iso_periodic.shape[0] and np.array_equal(iso, lv.iso)
+
+
+def test_union_find_primitives_on_random_graphs(tmp_path):
+    """patches.cuh (host build) against scipy's connected components on random graphs: same partition, and with every union hooking
+    the larger root under the smaller one the root of a component is its smallest member (what the patch numbering relies on)."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    src = tmp_path / "ufg.cpp"
+    src.write_text('''
+#include "ahf_b200/csrc/patches.cuh"
+extern "C" void uf_graph(const int *a, const int *b, long ne, int *parent, long n) {
+  for (long i = 0; i < n; i++) parent[i] = (int)i;
+  for (long e = 0; e < ne; e++) ahf::uf_unite(parent, a[e], b[e]);
+  for (long i = 0; i < n; i++) parent[i] = ahf::uf_find(parent, (int32_t)i);
+}
+''')
+    so = tmp_path / "ufg.so"
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", "-I", ROOT, "-o", str(so), str(src)])
+    L = C.CDLL(str(so))
+    L.uf_graph.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long]
+    rng = np.random.default_rng(3)
+    for n, ne in ((1, 0), (2, 1), (50, 20), (1000, 700), (20000, 15000), (20000, 60000)):
+        a = rng.integers(0, n, ne).astype(np.int32); b = rng.integers(0, n, ne).astype(np.int32)
+        root = np.empty(n, np.int32)
+        L.uf_graph(a.ctypes.data, b.ctypes.data, ne, root.ctypes.data, n)
+        ncomp, lab = connected_components(coo_matrix((np.ones(ne), (a, b)), shape=(n, n)), directed=False)
+        assert len(np.unique(root)) == ncomp
+        first = np.full(ncomp, n, np.int64)
+        np.minimum.at(first, lab, np.arange(n))                  # smallest member of every scipy component
+        assert np.array_equal(root, first[lab])
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """the bench lines kept under profiles/ carry every key the measurement contract names (a guard for edits of bench.py)"""
+    import glob
+    import json
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r1[f-z]_bench_256_n1.json")))
+    assert files
+    for f in files:
+        d = json.loads([l for l in open(f) if l.startswith("{")][0])
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                  "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
+            assert k in d, (f, k)
+        assert d["warmup"] >= 3 and d["gpu_launches"] > 0 and "workload" in d["config"] and "l2" in d["config"]
+        assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
+        r = d["roofline"]
+        assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(r) and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+        assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    full = json.load(open(os.path.join(ROOT, "profiles", "r1f_bench_256_n1.json")))
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(full["cpu_baseline"]) and full["cpu_baseline"]["kind"] == "reference"
