@@ -211,6 +211,131 @@ def read_gridtree(path: str):
     return min_ref, out
 
 
+# ------------------------------------------------------------------------------------------------
+# NEXT-2, second half: extents of the isolated refinements (end of RefCentre) and the refinement tree (analyseRef).
+# Patch-level work (tens to thousands of patches): numpy for the per-cell extents, plain loops over patches for the tree.
+# ------------------------------------------------------------------------------------------------
+def patch_extents(lv: Level) -> np.ndarray:
+    """[niso, 3, 2] (min, max) per dimension as RefCentre leaves them (src/libahf/ahf_halos.c:1400-1620): a periodic refinement is
+    cut at boundRefDiv = fmod(centreDens + 1/2, 1) (:1413-1470; the radius term cancels in (a+b)/2) and keeps max over the nodes
+    below the cut, min over those above (MinMaxBound, src/libutility/specific.c:227-254), so max < min there; untouched sentinels
+    become 0 / 1 (:1597-1612)."""
+    n = len(lv.patch)
+    L = float(lv.l1dim)
+    cd = lv.patch[:, 9:12]
+    per = lv.iso_periodic.astype(bool)
+    vol = lv.patch[:, 0] * ((1.0 / L) * (1.0 / L) * (1.0 / L))
+    rad = np.array([((3.0 * v) / (4 * 3.14159265358979323846)) ** 0.333333333 * 1.1 for v in vol])
+    div = np.full((n, 3), -1.0)
+    for j in range(n):
+        if per[j].any():
+            for d in range(3):
+                if per[j, d]:
+                    a = rad[j] + cd[j, d]; b = 1.0 - rad[j] + cd[j, d]
+                    div[j, d] = np.fmod((a + b) / 2.0, 1.0)
+    ext = np.zeros((n, 3, 2))
+    shift = 0.5 / L
+    for d, c in enumerate((lv.x, lv.y, lv.z)):
+        xx = np.fmod(c.astype(np.float64) / L + shift + 1.0, 1.0)
+        mn = np.full(n, 100000.0); mx = np.full(n, -100000.0)
+        dv = div[lv.iso, d]
+        plain = dv < 0.0
+        np.minimum.at(mn, lv.iso[plain], xx[plain]); np.maximum.at(mx, lv.iso[plain], xx[plain])
+        low = ~plain & (xx < dv); up = ~plain & ~(xx < dv)
+        np.maximum.at(mx, lv.iso[low], xx[low]); np.minimum.at(mn, lv.iso[up], xx[up])
+        mn[mn == 100000.0] = 0.0; mx[mx == -100000.0] = 1.0
+        ext[:, d, 0] = mn; ext[:, d, 1] = mx
+    return ext
+
+
+def _pdist2(a, b):
+    d = np.abs(a - b)
+    d = np.where(d > 0.5, 1.0 - d, d)
+    return d[0] * d[0] + d[1] * d[1] + d[2] * d[2]
+
+
+def patch_tree(levels: list[Level]):
+    """analyseRef (src/libahf/ahf_halos.c:1652-2300) over the coloured levels (levels[0] = ahf.min_ref), default switches of the shipped
+    define.h (PARDAU_PARTS).  Returns per level dict(sub=[lists of indices on the next level], daughter=[index or -1], close=[closeRefDist]).
+    Steps as the reference takes them: (1) a finer refinement is listed under every coarser one whose [min,max] box holds its density
+    centre (:1693-1800; periodic boxes have max < min); (2) one with several parents keeps the closest (first minimum) and is struck
+    from the others -- only for levels 1 .. n-2, the loop bound of :1817 leaves the finest level alone; (3) one without a parent is
+    given to the closest refinement of the level above and inherits its centres (:2030-2165); (4) the main branch is the listed
+    refinement with most particles (first maximum, :2190-2235), the others get closeRefDist = half the distance to their nearest
+    sibling (:2245-2285)."""
+    n = len(levels)
+    cd = [lv.patch[:, 9:12].copy() for lv in levels]
+    ext = [patch_extents(lv) for lv in levels]
+    sub = [[[] for _ in range(len(lv.patch))] for lv in levels]
+    par = [[[] for _ in range(len(lv.patch))] for lv in levels]
+    detail = False
+    for i in range(n - 1):
+        for j in range(len(sub[i])):
+            for k in range(len(sub[i + 1])):
+                ok = True
+                for d in range(3):
+                    lo, hi = ext[i][j, d]; v = cd[i + 1][k, d]
+                    if lo < hi:
+                        inside = (v > lo) and (v < hi)
+                    else:
+                        inside = ((v >= 0) and (v < hi)) or ((v > lo) and (v <= 1.0))
+                    if not inside:
+                        ok = False
+                        break
+                if ok:
+                    sub[i][j].append(k); par[i + 1][k].append(j)
+                    if len(par[i + 1][k]) > 1:
+                        detail = True
+    if detail:
+        for i in range(1, n - 1):
+            for j in range(len(par[i])):
+                if len(par[i][j]) > 1:
+                    best, tmin = -1, 10000000000000.0
+                    for q in par[i][j]:
+                        dist = _pdist2(cd[i][j], cd[i - 1][q])
+                        if dist < tmin:
+                            best, tmin = q, dist
+                    for q in par[i][j]:
+                        if q != best:
+                            sub[i - 1][q] = [t for t in sub[i - 1][q] if t != j]
+                    par[i][j] = [best]
+    for i in range(1, n):
+        for j in range(len(par[i])):
+            if len(par[i][j]) == 0:
+                best, tmin = -1, 10000000000000.0
+                for q in range(len(cd[i - 1])):
+                    dist = _pdist2(cd[i][j], cd[i - 1][q])
+                    if dist < tmin:
+                        best, tmin = q, dist
+                par[i][j] = [best]; sub[i - 1][best].append(j)
+                cd[i][j] = cd[i - 1][best]
+    out = []
+    close = [np.full(len(lv.patch), -1.0) for lv in levels]
+    for i in range(n):
+        dau = np.full(len(sub[i]), -1, np.int64)
+        if i < n - 1:
+            for j, sl in enumerate(sub[i]):
+                if len(sl) > 1:
+                    best, mp = -1, -1
+                    for k in sl:
+                        if levels[i + 1].patch[k, 1] > mp:
+                            best, mp = k, levels[i + 1].patch[k, 1]
+                    dau[j] = best
+                    for a, k in enumerate(sl):
+                        if k != best:
+                            tmin = 10000000000000.0
+                            for b, l in enumerate(sl):
+                                if a != b:
+                                    tmin = min(tmin, _pdist2(cd[i + 1][k], cd[i + 1][l]))
+                            close[i + 1][k] = 0.5 * np.sqrt(tmin)
+                elif len(sl) == 1:
+                    dau[j] = sl[0]
+        out.append(dict(sub=sub[i], daughter=dau))
+    for i in range(n):
+        out[i]["close"] = close[i]
+    return out
+
+
 def read_level(path: str) -> Level:
     with open(path, "rb") as f:
         hdr = np.fromfile(f, np.int64, 4)

@@ -90,3 +90,22 @@ def test_patch_centres_match_reference_gridtree(golden):
         if leaf.any():
             dd = np.abs(pc[leaf, 9:12] - pc[leaf, 2:5])
             assert np.minimum(dd, 1.0 - dd).max() < 1e-6
+
+
+def test_refinement_tree_matches_reference_gridtree(golden):
+    """NEXT-2, second half: extents of the isolated refinements and analyseRef (ahf_halos.c:1400-1620, :1652-2300).  Substructure lists
+    (members and order), main-branch daughter and closeRefDist of every isolated refinement equal the reference's own .AHF_gridtree."""
+    T = golden.gridtree()
+    if T is None:
+        import pytest
+        pytest.skip("no -DAHFgridtreefile variant of the multi-species build")
+    H = O.build_hierarchy(golden.pos, golden.n1d, nth_dom=golden.nper_dom, nth_ref=golden.nper_ref, patches=True)
+    tree = O.patch_tree(H[min(T):])
+    for i, l in enumerate(sorted(T)):
+        t, o = T[l], tree[i]
+        subs = [[int(v) for v in t["sub"][t["sub_off"][j]:t["sub_off"][j + 1], 1]] for j in range(len(t["nodes"]))]
+        assert o["sub"] == subs, l
+        assert np.array_equal(o["daughter"], t["daughter"][:, 1]), l
+        assert np.abs(o["close"] - t["close"]).max() <= 1e-13, l
+        if len(t["sub"]):
+            assert np.all(t["sub"][:, 0] == l + 1)
