@@ -330,10 +330,73 @@ def patch_tree(levels: list[Level]):
                             close[i + 1][k] = 0.5 * np.sqrt(tmin)
                 elif len(sl) == 1:
                     dau[j] = sl[0]
-        out.append(dict(sub=sub[i], daughter=dau))
+        out.append(dict(sub=sub[i], daughter=dau, npar=[len(p) for p in par[i]]))
     for i in range(n):
         out[i]["close"] = close[i]
     return out
+
+
+def tree_to_halos(levels: list[Level], tree, max_gather_rad: float):
+    """spatialRef2halos (src/libahf/ahf_halos.c:2405-3058): the halo seeds the per-halo pass starts from.  Walks the refinement tree
+    level by level as the reference does: a refinement without finer structure closes its halo (position = its centre, :2548-2570,
+    :2680-2700), one with a single finer refinement hands its halo down the main branch, one with several opens a sub-halo for every
+    listed refinement but the main-branch daughter (first guess R_vir = closeRefDist, :2620-2650, :2760-2790); particle counts add up
+    along the main branch.  Gathering radius (:2985-3052): half the distance to the nearest halo with MORE particles (MaxGatherRad
+    when there is none), at least R_vir, at most min(MaxGatherRad / boxsize, 1/4).  Returns (pos[nh,3], gatherRad[nh], npart[nh],
+    hostHalo[nh]) in the order of the reference's halos[] array."""
+    n = len(levels)
+    niso = [len(lv.patch) for lv in levels]
+    hidx = [np.full(k, -1, np.int64) for k in niso]
+    pos, npart, rvir, host = [], [], [], []
+
+    def new():
+        pos.append(np.zeros(3)); npart.append(0); rvir.append(-1.0); host.append(-1)
+        return len(pos) - 1
+    expect = 0
+    for i in range(n):
+        for j in range(niso[i]):
+            ns = len(tree[i]["sub"][j])
+            expect += (1 if ns == 0 else ns) if i == 0 else (ns - 1 if ns > 1 else 0)
+    for i in range(n):
+        for j in range(niso[i]):
+            sub = tree[i]["sub"][j]; dau = int(tree[i]["daughter"][j]); ns = len(sub)
+            cen = levels[i].patch[j, 2:5]; np_ = int(levels[i].patch[j, 1])
+            if i == 0:
+                h = new()
+                npart[h] = np_
+                if ns == 0:
+                    pos[h] = cen.copy()
+            else:
+                if tree[i]["npar"][j] == 0:
+                    continue
+                h = int(hidx[i][j])
+                if h < 0:
+                    raise RuntimeError("refinement without a halo (the reference exits here, ahf_halos.c:2676)")
+                npart[h] += np_
+                if ns != 1:
+                    pos[h] = cen.copy()
+            if ns >= 1 and dau != -1:
+                hidx[i + 1][dau] = h
+            if ns > 1:
+                for k in sub:
+                    if k != dau:
+                        c = new()
+                        host[c] = h; hidx[i + 1][k] = c; rvir[c] = float(tree[i + 1]["close"][k])
+    while len(pos) < expect:
+        new()
+    nh = len(pos)
+    P = np.array(pos).reshape(nh, 3); N = np.array(npart, np.int64); R = np.array(rvir)
+    maxg = min(max_gather_rad, 0.25)
+    G = np.empty(nh)
+    for i in range(nh):
+        more = N > N[i]
+        if more.any():
+            d = np.abs(P[more] - P[i]); d = np.where(d > 0.5, 1.0 - d, d)
+            g = np.sqrt((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]).min()) * 0.5
+        else:
+            g = maxg
+        G[i] = min(max(g, R[i]), maxg)
+    return P, G, N, np.array(host, np.int64)
 
 
 def read_level(path: str) -> Level:

@@ -109,3 +109,18 @@ def test_refinement_tree_matches_reference_gridtree(golden):
         assert np.abs(o["close"] - t["close"]).max() <= 1e-13, l
         if len(t["sub"]):
             assert np.all(t["sub"][:, 0] == l + 1)
+
+
+def test_halo_seeds_match_reference(golden):
+    """NEXT-2/3 glue: spatialRef2halos (ahf_halos.c:2405-3058) on top of the restated colouring, RefCentre and analyseRef gives the
+    halo seeds -- centre, gathering radius, particle count, in the order of the reference's halos[] array -- that the reference hands
+    to ahf_halos_sfc_constructHalo (golden `halo_s` columns 0-4, dumped at ahf_halos.c:508): bit for bit.  With this the oracle
+    restates the whole chain particles -> keys -> hierarchy -> patches -> tree -> seeds -> halo pass."""
+    min_ref, _ = golden.patches()
+    H = O.build_hierarchy(golden.pos, golden.n1d, nth_dom=golden.nper_dom, nth_ref=golden.nper_ref, patches=True)
+    tree = O.patch_tree(H[min_ref:])
+    pos, gather, npart, host = O.tree_to_halos(H[min_ref:], tree, 3.0 / float(golden.d["boxsize"]))      # MaxGatherRad 3.0 (AHF.input-example)
+    hs = golden.hs
+    assert len(npart) == len(hs)
+    assert np.array_equal(npart, hs[:, 4].astype(np.int64))
+    assert np.array_equal(pos, hs[:, 0:3]) and np.array_equal(gather, hs[:, 3])
