@@ -109,6 +109,7 @@ def lib():
         L.ahfgpu_amr_level_header.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.ahfgpu_amr_level_get.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 8
         L.ahfgpu_amr_patches.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ahfgpu_amr_patch_stats.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
         L.ahfgpu_amr_particle_levels.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         L.ahfgpu_construct_halos.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ahfgpu_halo_sizes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -277,6 +278,13 @@ class AhfGpu:
         iso = np.empty(nc, np.int32); per = np.zeros((max(nc, 1), 3), np.uint8); niso = C.c_int64(0)
         self._chk(self._L.ahfgpu_amr_patches(self._h, lev, _p(iso), C.byref(niso), _p(per)))
         return iso, per[:niso.value].copy()
+
+    def patch_stats(self, lev: int, niso: int) -> np.ndarray:
+        """RefCentre on the device (src/libahf/ahf_halos.c:935-1620): [niso, 18] per isolated refinement, columns as in include/ahfgpu.h."""
+        st = np.zeros((max(niso, 1), 18), np.float64); n = C.c_int64(0)
+        self._chk(self._L.ahfgpu_amr_patch_stats(self._h, lev, C.byref(n), _p(st), max(niso, 1)))
+        assert n.value == niso, (n.value, niso)
+        return st[:niso]
 
     def particle_levels(self, with_cells: bool = True):
         nl = self.nlevels()

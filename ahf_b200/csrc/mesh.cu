@@ -1916,6 +1916,150 @@ __global__ void k_patch_iso(LV v, const int32_t *__restrict__ nbr, const int32_t
   if (z == 0 && face_nb(v, nbr, c, 4, x) >= 0) periodic3[3 * (size_t)i + 2] = 1;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// NEXT-2, first half: RefCentre (src/libahf/ahf_halos.c:935-1620) as segmented reductions over the patch labels.
+// Per isolated refinement: node and particle counts, sums of node positions (plain and density weighted), maximum density, sum of the
+// positions of the particles the level finally owns, extents.  Sums are double atomics: the counts, the maximum and the extents are
+// exact, the centres differ from the reference's sequential sums in the last bits only.
+// ------------------------------------------------------------------------------------------------
+constexpr int PS_ACC = 16;      // 0 nodes 1 parts | 2-4 geom 5 norm | 6-8 dens-weighted 9 norm | 10 maxDens (bits) | 11-13 particle sums 14 norm
+__device__ __forceinline__ double node_coord(int x, double L, double shift) { return fmod((double)x / L + shift + 1.0, 1.0); }   // ahf_halos.c:1024-1029
+__device__ __forceinline__ void atomic_max_pos(double *a, double v) { atomicMax(reinterpret_cast<unsigned long long *>(a), (unsigned long long)__double_as_longlong(v)); }
+__device__ __forceinline__ void atomic_min_pos(double *a, double v) { atomicMin(reinterpret_cast<unsigned long long *>(a), (unsigned long long)__double_as_longlong(v)); }
+
+__global__ void k_pstat_cells(LV v, const int32_t *__restrict__ iso, const uint8_t *__restrict__ per3, const float *__restrict__ dens, double *acc)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= v.ncell) return;
+  const int i = iso[c];
+  int x, y, z;
+  lv_coords(v, c, x, y, z);
+  const double L = (double)v.L, shift = 0.5 / L;
+  double xx = node_coord(x, L, shift), yy = node_coord(y, L, shift), zz = node_coord(z, L, shift);
+  if (per3[3 * i + 0] && xx < 0.5) xx += 1.0;                        // :1032-1040
+  if (per3[3 * i + 1] && yy < 0.5) yy += 1.0;
+  if (per3[3 * i + 2] && zz < 0.5) zz += 1.0;
+  double d = (double)dens[c] + 1.0;                                  // + simu.mean_dens, :1057
+  if (d < 0.0) d = 0.0;
+  double *a = acc + (size_t)PS_ACC * i;
+  atomicAdd(a + 0, 1.0);
+  atomicAdd(a + 2, xx); atomicAdd(a + 3, yy); atomicAdd(a + 4, zz); atomicAdd(a + 5, 1.0);
+  atomicAdd(a + 6, xx * d); atomicAdd(a + 7, yy * d); atomicAdd(a + 8, zz * d); atomicAdd(a + 9, d);
+  atomic_max_pos(a + 10, d);
+}
+// particles the level finally owns (node.ll at ahf_halos time): centre of mass of the refinement's particles (:1120-1180)
+__global__ void k_pstat_parts(const float4 *__restrict__ pos4, const uint32_t *__restrict__ plist, const int32_t *__restrict__ pcell, uint64_t np,
+                              const int8_t *__restrict__ owner, int lev, const int32_t *__restrict__ iso, const uint8_t *__restrict__ per3, double *acc)
+{
+  uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (k >= np) return;
+  const uint64_t p = plist ? plist[k] : k;
+  if (owner[p] != lev) return;
+  const int cc = pcell[k];
+  if (cc < 0) return;
+  const int i = iso[cc];
+  const float4 q = pos4[p];
+  double xp = (double)q.x, yp = (double)q.y, zp = (double)q.z;
+  if (per3[3 * i + 0] && xp < 0.5) xp += 1.0;
+  if (per3[3 * i + 1] && yp < 0.5) yp += 1.0;
+  if (per3[3 * i + 2] && zp < 0.5) zp += 1.0;
+  double *a = acc + (size_t)PS_ACC * i;
+  atomicAdd(a + 1, 1.0);
+  atomicAdd(a + 11, xp); atomicAdd(a + 12, yp); atomicAdd(a + 13, zp); atomicAdd(a + 14, 1.0);
+}
+__device__ __forceinline__ double f1mod1(double v) { return v >= 2.0 ? v - 2.0 : v >= 1.0 ? v - 1.0 : v; }     // specific.c:120-129
+// normalisation and fall-backs (:1240-1370), boundRefDiv of the periodic refinements (:1400-1470).
+// out[i][18]: 0 numNodes 1 numParts 2-4 centre (= particle centre, AHFcomcentre) 5 maxDens 6-8 centreGEOM 9-11 centreDens 12-17 extents
+__global__ void k_pstat_finish(const double *__restrict__ acc, const uint8_t *__restrict__ per3, int niso, double L, double *__restrict__ out, double *__restrict__ div3)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= niso) return;
+  const double *a = acc + (size_t)PS_ACC * i;
+  double *o = out + (size_t)18 * i;
+  o[0] = a[0]; o[1] = a[1]; o[5] = a[10];
+  for (int q = 0; q < 3; q++) o[6 + q] = a[5] > 0 ? f1mod1(a[2 + q] / a[5] + 1.0) : a[2 + q];
+  for (int q = 0; q < 3; q++) o[9 + q] = a[9] > 0 ? f1mod1(a[6 + q] / a[9] + 1.0) : o[6 + q];
+  for (int q = 0; q < 3; q++) o[2 + q] = a[14] > 0 ? f1mod1(a[11 + q] / a[14] + 1.0) : o[6 + q];
+  if (a[10] <= 5e-16) for (int q = 0; q < 3; q++) o[9 + q] = o[6 + q];
+  const double bl = 1.0 / L, vol = a[0] * (bl * bl * bl);
+  const double rad = pow((3.0 * vol) / (4 * 3.14159265358979323846), 0.333333333) * 1.1;
+  for (int q = 0; q < 3; q++) {
+    double dv = -1.0;
+    if (per3[3 * i + q]) { const double aa = rad + o[9 + q], bb = 1.0 - rad + o[9 + q]; dv = fmod((aa + bb) / 2.0, 1.0); }
+    div3[3 * i + q] = dv;
+    o[12 + 2 * q] = 100000.0; o[13 + 2 * q] = 0.0;       // min sentinel as in the reference; max: node coordinates are > 0, so 0 = untouched
+  }
+}
+// extents (:1480-1595): MinMax, or MinMaxBound at boundRefDiv for the periodic refinements (specific.c:204-254)
+__global__ void k_pstat_extents(LV v, const int32_t *__restrict__ iso, const double *__restrict__ div3, double *out)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= v.ncell) return;
+  const int i = iso[c];
+  int xyz[3];
+  lv_coords(v, c, xyz[0], xyz[1], xyz[2]);
+  const double L = (double)v.L, shift = 0.5 / L;
+  double *o = out + (size_t)18 * i;
+#pragma unroll
+  for (int q = 0; q < 3; q++) {
+    const double xx = node_coord(xyz[q], L, shift), dv = div3[3 * i + q];
+    if (dv < 0.0) { atomic_min_pos(o + 12 + 2 * q, xx); atomic_max_pos(o + 13 + 2 * q, xx); }
+    else if (xx < dv) atomic_max_pos(o + 13 + 2 * q, xx);
+    else atomic_min_pos(o + 12 + 2 * q, xx);
+  }
+}
+__global__ void k_pstat_fix(int niso, double *out)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= niso) return;
+  double *o = out + (size_t)18 * i;
+  for (int q = 0; q < 3; q++) { if (o[12 + 2 * q] == 100000.0) o[12 + 2 * q] = 0.0; if (o[13 + 2 * q] == 0.0) o[13 + 2 * q] = 1.0; }    // :1597-1612
+}
+
+}  // namespace ahf
+
+using namespace ahf;
+
+extern "C" int ahfgpu_amr_patch_stats(ahfgpu_ctx *c, int32_t lev, int64_t *niso, double *stats, int64_t stats_cap)
+{
+  try {
+    if (!c || lev < 0 || lev >= (int)c->levels.size()) AHF_FAIL("bad level");
+    if (!c->owner_level) AHF_FAIL("no hierarchy");
+    CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
+    Level &l = c->levels[lev];
+    if (!l.dense && !l.nbr) AHF_FAIL("level has no neighbour table");
+    const int nc = (int)l.ncell;
+    int ni = 0;
+    if (nc > 0) {
+      LV v = view(l);
+      DevBuf<int32_t> parent, root, diso; DevBuf<uint8_t> isroot, per; DevBuf<int> rank; DevBuf<double> acc, out, div3;
+      parent.reserve(nc); root.reserve(nc); diso.reserve(nc); isroot.reserve(nc); rank.reserve(nc); per.reserve((size_t)3 * nc);
+      LAUNCH(c, k_patch_init, nblk(nc, 256), 256, 0, parent.p, nc);
+      LAUNCH(c, k_patch_link, nblk(nc, 256), 256, 0, v, l.nbr, parent.p);
+      LAUNCH(c, k_patch_roots, nblk(nc, 256), 256, 0, parent.p, nc, root.p, isroot.p);
+      ni = exclusive_scan<uint8_t>(c, isroot.p, rank.p, (uint64_t)nc);
+      CUDA_CHECK(cudaMemsetAsync(per.p, 0, (size_t)3 * nc, c->stream));
+      LAUNCH(c, k_patch_iso, nblk(nc, 256), 256, 0, v, l.nbr, root.p, rank.p, diso.p, per.p);
+      if (stats && (int64_t)ni > stats_cap) AHF_FAIL("stats buffer too small");
+      acc.reserve((size_t)PS_ACC * ni); out.reserve((size_t)18 * ni); div3.reserve((size_t)3 * ni);
+      CUDA_CHECK(cudaMemsetAsync(acc.p, 0, sizeof(double) * PS_ACC * ni, c->stream));
+      LAUNCH(c, k_pstat_cells, nblk(nc, 256), 256, 0, v, diso.p, per.p, l.dens, acc.p);
+      if (l.npart_dep > 0)
+        LAUNCH(c, k_pstat_parts, nblk(l.npart_dep, 256), 256, 0, c->pos4, l.plist, l.pcell, (uint64_t)l.npart_dep, c->owner_level, (int)lev, diso.p, per.p, acc.p);
+      LAUNCH(c, k_pstat_finish, nblk(ni, 128), 128, 0, acc.p, per.p, ni, (double)l.L, out.p, div3.p);
+      LAUNCH(c, k_pstat_extents, nblk(nc, 256), 256, 0, v, diso.p, div3.p, out.p);
+      LAUNCH(c, k_pstat_fix, nblk(ni, 128), 128, 0, ni, out.p);
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      if (stats && ni > 0) CUDA_CHECK(cudaMemcpy(stats, out.p, sizeof(double) * 18 * (size_t)ni, cudaMemcpyDeviceToHost));
+      parent.release(); root.release(); diso.release(); isroot.release(); rank.release(); per.release(); acc.release(); out.release(); div3.release();
+    }
+    if (niso) *niso = ni;
+    return 0;
+  } catch (const ahf::Error &e) { ahf::g_last_error = e.msg; return -1; }
+}
+
+namespace ahf {
 }  // namespace ahf
 
 using namespace ahf;

@@ -106,6 +106,13 @@ int  ahfgpu_amr_level_get(ahfgpu_ctx *ctx, int32_t lev, int32_t *x, int32_t *y, 
  * order of their first cell); *niso: their number (numIsoRef[lev - min_ref]); periodic3[3*i + d] (capacity 3*ncell bytes, may be
  * NULL): SRINDEX.periodic.x/y/z of patch i (testBound, :1090-1118).  Cell order as in ahfgpu_amr_level_get. */
 int  ahfgpu_amr_patches(ahfgpu_ctx *ctx, int32_t lev, int32_t *iso, int64_t *niso, uint8_t *periodic3);
+/* NEXT-2 of SURVEY 8f, first half: RefCentre (src/libahf/ahf_halos.c:935-1620) as segmented reductions over the patch labels of
+ * level `lev`.  stats[i*18 + k] for isolated refinement i (numbered as in ahfgpu_amr_patches): 0 numNodes, 1 numParts (particles the
+ * level finally owns), 2-4 centre (= centre of mass of those particles: the shipped define.h:101 sets AHFcomcentre; geometric centre
+ * where there are none), 5 maxDens, 6-8 centreGEOM, 9-11 centreDens (density weighted, with the fall-backs of :1248-1350),
+ * 12-17 x.min x.max y.min y.max z.min z.max (periodic refinements are cut at boundRefDiv, so max < min there, :1400-1612).
+ * *niso: number of refinements; stats may be NULL (count only), stats_cap = its capacity in refinements. */
+int  ahfgpu_amr_patch_stats(ahfgpu_ctx *ctx, int32_t lev, int64_t *niso, double *stats, int64_t stats_cap);
 /* per particle (sorted offset): deepest level that owns it (node.ll membership after all relinks) and its cell
  * index on every level it reached: cell_of[lev*n + i] = index into the level's cell list or -1 */
 int  ahfgpu_amr_particle_levels(ahfgpu_ctx *ctx, int8_t *owner_level, int32_t *cell_of, int32_t nlev_cap);
