@@ -64,6 +64,20 @@ def params_from_reference(glob: np.ndarray, *, lgrid_dom: int, device: int = 0, 
                   rho_fac=glob[4], phi_fac=glob[5], hubble=glob[6], ovlim=glob[7], rho_vir=glob[8])
 
 
+def min_ref(par: Params, l1dims, med_weight: float = 1.0) -> int:
+    """ahf.min_ref: the first refinement level the patch colouring considers (reference src/libahf/ahf_gridinfo.c:147-175): the last
+    level whose refinement threshold, expressed as an overdensity Nth_ref * pmass * med_weight / cell volume / rho_vir, is still below
+    the virial overdensity (levels counted from the domain grid, start value 1; AHF_MIN_REF_OFFSET = 0, src/param.h:21).
+    `med_weight` is simu.med_weight (1 for equal-mass runs; the heaviest species weight in a MULTIMASS run, src/startrun.c:663)."""
+    start = 1
+    for i, l1dim in enumerate(l1dims):
+        refine_len = par.x_fac / float(l1dim)
+        refine_ovdens = (par.nth_ref * (par.m_fac * med_weight) / (refine_len * refine_len * refine_len)) / par.rho_vir
+        if refine_ovdens < par.ovlim:
+            start = i
+    return start
+
+
 _lib = None
 
 
@@ -278,6 +292,9 @@ class AhfGpu:
         iso = np.empty(nc, np.int32); per = np.zeros((max(nc, 1), 3), np.uint8); niso = C.c_int64(0)
         self._chk(self._L.ahfgpu_amr_patches(self._h, lev, _p(iso), C.byref(niso), _p(per)))
         return iso, per[:niso.value].copy()
+
+    def min_ref(self, med_weight: float = 1.0) -> int:
+        return min_ref(self.params, [int(self.level_header(l)[0][0]) for l in range(self.nlevels())], med_weight)
 
     def patch_stats(self, lev: int, niso: int) -> np.ndarray:
         """RefCentre on the device (src/libahf/ahf_halos.c:935-1620): [niso, 18] per isolated refinement, columns as in include/ahfgpu.h."""

@@ -234,3 +234,13 @@ def test_committed_bench_lines_follow_the_contract():
         assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     full = json.load(open(os.path.join(ROOT, "profiles", "r1f_bench_256_n1.json")))
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(full["cpu_baseline"]) and full["cpu_baseline"]["kind"] == "reference"
+
+
+def test_min_ref_follows_reference(golden):
+    """host arithmetic of ahf_gridinfo.c:147-175 (ahf.min_ref) against the first coloured level of the reference (tests/golden/patches.npz);
+    frag16 sits on the edge: its level 3 has refine_ovdens = 199.99999999999997 against ovlim = 200"""
+    from ahf_b200 import ahf
+    par = ahf.params_from_reference(golden.glob, lgrid_dom=golden.n1d, nper_dom=golden.nper_dom, nper_ref=golden.nper_ref)
+    l1dims = [int(golden.level(l)["l1dim"]) for l in range(golden.nlev)]
+    medw = float(golden.weight.max()) if golden.weight is not None else 1.0
+    assert ahf.min_ref(par, l1dims, medw) == golden.patches()[0]
