@@ -78,6 +78,31 @@ def min_ref(par: Params, l1dims, med_weight: float = 1.0) -> int:
     return start
 
 
+def tree_halos(stats_per_level, max_gather_rad: float) -> dict:
+    """Host side of NEXT-2 (ahfgpu_tree_halos): refinement tree and halo seeds from the per-refinement tables ([niso, 18] per coloured
+    level, first level = ahf.min_ref).  Returns daughter / close / sub (lists per level) and pos, gather_rad, npart, host per halo."""
+    L = lib()
+    niso = np.array([len(s) for s in stats_per_level], np.int64)
+    rows = int(niso.sum())
+    st = np.ascontiguousarray(np.concatenate([np.asarray(s, np.float64).reshape(-1, 18) for s in stats_per_level]) if rows else np.zeros((0, 18)))
+    dau = np.empty(max(rows, 1), np.int32); close = np.empty(max(rows, 1), np.float64); off = np.zeros(rows + 1, np.int64)
+    sub = np.empty(max(rows, 1) * 2 + 8, np.int32); cap = rows + 1
+    nh = C.c_int64(0)
+    pos = np.zeros((cap, 3)); g = np.zeros(cap); npart = np.zeros(cap, np.int64); host = np.zeros(cap, np.int32)
+    rc = L.ahfgpu_tree_halos(len(niso), _p(niso), _p(st), max_gather_rad, _p(dau), _p(close), _p(off), _p(sub), len(sub), C.byref(nh),
+                             _p(pos), _p(g), _p(npart), _p(host), cap)
+    if rc != 0:
+        raise AhfGpuError(L.ahfgpu_last_error().decode())
+    out = dict(daughter=[], close=[], sub=[], pos=pos[:nh.value].copy(), gather_rad=g[:nh.value].copy(), npart=npart[:nh.value].copy(),
+               host=host[:nh.value].copy())
+    r = 0
+    for n in niso:
+        out["daughter"].append(dau[r:r + n].astype(np.int64)); out["close"].append(close[r:r + n].copy())
+        out["sub"].append([[int(v) for v in sub[off[q]:off[q + 1]]] for q in range(r, r + n)])
+        r += int(n)
+    return out
+
+
 _lib = None
 
 
@@ -124,6 +149,8 @@ def lib():
         L.ahfgpu_amr_level_get.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 8
         L.ahfgpu_amr_patches.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ahfgpu_amr_patch_stats.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
+        L.ahfgpu_tree_halos.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
         L.ahfgpu_amr_particle_levels.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         L.ahfgpu_construct_halos.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ahfgpu_halo_sizes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]

@@ -1,0 +1,184 @@
+// tree.cu -- HOST code of libahfgpu.so (no kernels): the refinement tree and the halo seeds from the per-refinement tables of
+// ahfgpu_amr_patch_stats.  Replaces analyseRef (src/libahf/ahf_halos.c:1652-2300) and spatialRef2halos (:2405-3058) of the
+// reference: both are loops over isolated refinements (hundreds to thousands per level), not over nodes or particles, so they stay
+// on the host; only their inputs come from the device.  Default switches of the shipped define.h: PARDAU_PARTS (main branch = listed
+// refinement with most particles), AHFcomcentre (halo centre = centre of mass of the refinement's particles).
+#include "common.cuh"
+#include <cmath>
+#include <vector>
+
+namespace {
+
+struct Ref {                      // one isolated refinement (SPATIALREF, src/tdef.h)
+  double centre[3], cd[3];        // halo centre (stats 2-4), density-weighted centre (stats 9-11; analyseRef works on this one)
+  double ext[3][2];               // min, max per dimension (stats 12-17); max < min across a periodic face
+  long long nodes, parts;
+  std::vector<int> sub, par;      // refinements of the next finer / next coarser level listed with this one
+  int    daughter = -1;
+  double close = -1.0;            // closeRefDist
+  int    halo = -1;               // haloIndex
+};
+
+inline double pdist2(const double *a, const double *b)
+{
+  double s = 0.0, d[3];
+  for (int q = 0; q < 3; q++) { d[q] = std::fabs(a[q] - b[q]); if (d[q] > 0.5) d[q] = 1.0 - d[q]; }
+  s = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+  return s;
+}
+
+// is v inside [lo, hi] of a refinement (ahf_halos.c:1710-1745; a periodic extent has hi < lo)
+inline bool inside(double v, double lo, double hi)
+{
+  if (lo < hi) return v > lo && v < hi;
+  return (v >= 0 && v < hi) || (v > lo && v <= 1.0);
+}
+
+}  // namespace
+
+extern "C" int ahfgpu_tree_halos(int32_t nlev, const int64_t *niso, const double *stats, double max_gather_rad,
+                                 int32_t *daughter, double *close_ref_dist, int64_t *sub_offset, int32_t *sub, int64_t sub_cap,
+                                 int64_t *nhalo, double *halo_pos3, double *halo_gather_rad, int64_t *halo_npart, int32_t *halo_host,
+                                 int64_t halo_cap)
+{
+  try {
+    if (nlev < 0 || (nlev && (!niso || !stats)) || !nhalo) AHF_FAIL("null argument");
+    const int n = nlev;
+    std::vector<std::vector<Ref>> R(n);
+    {
+      const double *s = stats;
+      for (int i = 0; i < n; i++) {
+        R[i].resize((size_t)niso[i]);
+        for (auto &r : R[i]) {
+          r.nodes = (long long)s[0]; r.parts = (long long)s[1];
+          for (int q = 0; q < 3; q++) { r.centre[q] = s[2 + q]; r.cd[q] = s[9 + q]; r.ext[q][0] = s[12 + 2 * q]; r.ext[q][1] = s[13 + 2 * q]; }
+          s += 18;
+        }
+      }
+    }
+    // ---- analyseRef (1): a finer refinement is listed with every coarser one whose box holds its density centre (:1693-1800)
+    bool detail = false;
+    for (int i = 0; i + 1 < n; i++)
+      for (int j = 0; j < (int)R[i].size(); j++)
+        for (int k = 0; k < (int)R[i + 1].size(); k++) {
+          const Ref &p = R[i][j]; Ref &c = R[i + 1][k];
+          if (inside(c.cd[0], p.ext[0][0], p.ext[0][1]) && inside(c.cd[1], p.ext[1][0], p.ext[1][1]) && inside(c.cd[2], p.ext[2][0], p.ext[2][1])) {
+            R[i][j].sub.push_back(k); c.par.push_back(j);
+            if (c.par.size() > 1) detail = true;
+          }
+        }
+    // ---- (2) several parents: keep the closest (first minimum), strike the refinement from the others.  The reference's loop runs over
+    //      levels 1 .. n-2 only (:1817): a refinement of the finest level keeps all its parents
+    if (detail)
+      for (int i = 1; i + 1 < n; i++)
+        for (int j = 0; j < (int)R[i].size(); j++) {
+          Ref &r = R[i][j];
+          if (r.par.size() <= 1) continue;
+          int best = -1; double tmin = 10000000000000.0;
+          for (int q : r.par) { const double d = pdist2(r.cd, R[i - 1][q].cd); if (d < tmin) { best = q; tmin = d; } }
+          if (best < 0) AHF_FAIL("refinement with parents but none closest");
+          for (int q : r.par)
+            if (q != best) {
+              std::vector<int> keep;
+              for (int t : R[i - 1][q].sub) if (t != j) keep.push_back(t);
+              R[i - 1][q].sub.swap(keep);
+            }
+          r.par.assign(1, best);
+        }
+    // ---- (3) no parent: adopt the closest refinement of the level above and inherit its centres (:2030-2165)
+    for (int i = 1; i < n; i++)
+      for (int j = 0; j < (int)R[i].size(); j++) {
+        Ref &r = R[i][j];
+        if (!r.par.empty()) continue;
+        int best = -1; double tmin = 10000000000000.0;
+        for (int q = 0; q < (int)R[i - 1].size(); q++) { const double d = pdist2(r.cd, R[i - 1][q].cd); if (d < tmin) { best = q; tmin = d; } }
+        if (best < 0) continue;                                   // nothing above: the reference would index with -1 here
+        r.par.assign(1, best); R[i - 1][best].sub.push_back(j);
+        for (int q = 0; q < 3; q++) r.cd[q] = R[i - 1][best].cd[q];
+      }
+    // ---- (4) main branch (PARDAU_PARTS: most particles, first maximum, :2190-2235) and closeRefDist of the other listed refinements
+    //      (half the distance to the nearest sibling, :2245-2285)
+    for (int i = 0; i + 1 < n; i++)
+      for (auto &r : R[i]) {
+        if (r.sub.size() > 1) {
+          long long mp = -1; int best = -1;
+          for (int k : r.sub) if (R[i + 1][k].parts > mp) { best = k; mp = R[i + 1][k].parts; }
+          r.daughter = best;
+          for (size_t a = 0; a < r.sub.size(); a++) {
+            const int k = r.sub[a];
+            if (k == best) continue;
+            double tmin = 10000000000000.0;
+            for (size_t b = 0; b < r.sub.size(); b++) if (a != b) { const double d = pdist2(R[i + 1][k].cd, R[i + 1][r.sub[b]].cd); if (d < tmin) tmin = d; }
+            R[i + 1][k].close = 0.5 * std::sqrt(tmin);
+          }
+        } else if (r.sub.size() == 1) r.daughter = r.sub[0];
+      }
+    // ---- tables out
+    {
+      int64_t row = 0, ns = 0;
+      for (int i = 0; i < n; i++)
+        for (auto &r : R[i]) {
+          if (daughter) daughter[row] = r.daughter;
+          if (close_ref_dist) close_ref_dist[row] = r.close;
+          if (sub_offset) sub_offset[row] = ns;
+          for (int k : r.sub) { if (sub) { if (ns >= sub_cap) AHF_FAIL("substructure buffer too small"); sub[ns] = k; } ns++; }
+          row++;
+        }
+      if (sub_offset) sub_offset[row] = ns;
+    }
+    // ---- spatialRef2halos (:2405-2960): walk the tree level by level
+    struct Halo { double pos[3] = { 0, 0, 0 }; long long npart = 0; double rvir = -1.0; int host = -1; };
+    std::vector<Halo> H;
+    long long expect = 0;
+    for (int i = 0; i < n; i++)
+      for (auto &r : R[i]) {
+        const long long ns = (long long)r.sub.size();
+        expect += (i == 0) ? (ns == 0 ? 1 : ns) : (ns > 1 ? ns - 1 : 0);
+      }
+    for (int i = 0; i < n; i++)
+      for (auto &r : R[i]) {
+        const size_t ns = r.sub.size();
+        int h;
+        if (i == 0) {
+          H.emplace_back(); h = (int)H.size() - 1;
+          H[h].npart = r.parts;
+          if (ns == 0) for (int q = 0; q < 3; q++) H[h].pos[q] = r.centre[q];
+        } else {
+          if (r.par.empty()) continue;                            // counted as a lost refinement by the reference (:2905-2925)
+          h = r.halo;
+          if (h < 0) AHF_FAIL("refinement without a halo (the reference exits here, ahf_halos.c:2676)");
+          H[h].npart += r.parts;
+          if (ns != 1) for (int q = 0; q < 3; q++) H[h].pos[q] = r.centre[q];
+        }
+        if (ns >= 1 && r.daughter != -1) R[i + 1][r.daughter].halo = h;
+        if (ns > 1)
+          for (int k : r.sub)
+            if (k != r.daughter) {
+              H.emplace_back(); const int c = (int)H.size() - 1;
+              H[c].host = h; R[i + 1][k].halo = c; H[c].rvir = R[i + 1][k].close;
+            }
+      }
+    while ((long long)H.size() < expect) H.emplace_back();
+    // ---- gathering radius (:2985-3052): half the distance to the nearest halo with MORE particles, at least R_vir, at most
+    //      min(MaxGatherRad / boxsize, 1/4)
+    const int64_t nh = (int64_t)H.size();
+    *nhalo = nh;
+    if (nh > halo_cap && (halo_pos3 || halo_gather_rad || halo_npart || halo_host)) AHF_FAIL("halo buffers too small");
+    const double maxg = max_gather_rad < 0.25 ? max_gather_rad : 0.25;
+    for (int64_t i = 0; i < nh; i++) {
+      double g2 = 100000000000.0; long long cnt = 0;
+      for (int64_t j = 0; j < nh; j++)
+        if (H[j].npart > H[i].npart) { const double d = pdist2(H[i].pos, H[j].pos); if (d < g2) g2 = d; cnt++; }
+      double g = cnt ? std::sqrt(g2) * 0.5 : maxg;
+      if (g < H[i].rvir) g = H[i].rvir;
+      if (g > maxg) g = maxg;
+      if (halo_pos3) for (int q = 0; q < 3; q++) halo_pos3[3 * i + q] = H[i].pos[q];
+      if (halo_gather_rad) halo_gather_rad[i] = g;
+      if (halo_npart) halo_npart[i] = H[i].npart;
+      if (halo_host) halo_host[i] = H[i].host;
+    }
+    return 0;
+  }
+  catch (const ahf::Error &e) { ahf::g_last_error = e.msg; return -1; }
+  catch (const std::exception &e) { ahf::g_last_error = e.what(); return -2; }
+}

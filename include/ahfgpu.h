@@ -113,6 +113,18 @@ int  ahfgpu_amr_patches(ahfgpu_ctx *ctx, int32_t lev, int32_t *iso, int64_t *nis
  * 12-17 x.min x.max y.min y.max z.min z.max (periodic refinements are cut at boundRefDiv, so max < min there, :1400-1612).
  * *niso: number of refinements; stats may be NULL (count only), stats_cap = its capacity in refinements. */
 int  ahfgpu_amr_patch_stats(ahfgpu_ctx *ctx, int32_t lev, int64_t *niso, double *stats, int64_t stats_cap);
+/* NEXT-2, second half -- HOST code (no device work): the refinement tree and the halo seeds from the tables of
+ * ahfgpu_amr_patch_stats.  Replaces analyseRef (src/libahf/ahf_halos.c:1652-2300) and spatialRef2halos (:2405-3058), default switches
+ * of the shipped define.h (PARDAU_PARTS, AHFcomcentre).  In: nlev coloured levels (level 0 = ahf.min_ref), niso[nlev] refinements per
+ * level, stats = their 18-column rows concatenated level by level, max_gather_rad = MaxGatherRad / boxsize.  Out, per refinement row
+ * (any pointer may be NULL): daughter = main-branch refinement on the next level or -1 (SPATIALREF.daughter), close_ref_dist
+ * (.closeRefDist), substructure lists as CSR (sub_offset[rows+1], sub[] = indices on the next level, in the reference's order).
+ * Out, per halo in the order of the reference's halos[] array: centre (HALO.pos), gatherRad, npart, hostHalo -- the inputs of
+ * ahfgpu_construct_halos.  *nhalo is always set; buffers are checked against sub_cap / halo_cap. */
+int  ahfgpu_tree_halos(int32_t nlev, const int64_t *niso, const double *stats, double max_gather_rad,
+                       int32_t *daughter, double *close_ref_dist, int64_t *sub_offset, int32_t *sub, int64_t sub_cap,
+                       int64_t *nhalo, double *halo_pos3, double *halo_gather_rad, int64_t *halo_npart, int32_t *halo_host,
+                       int64_t halo_cap);
 /* per particle (sorted offset): deepest level that owns it (node.ll membership after all relinks) and its cell
  * index on every level it reached: cell_of[lev*n + i] = index into the level's cell list or -1 */
 int  ahfgpu_amr_particle_levels(ahfgpu_ctx *ctx, int8_t *owner_level, int32_t *cell_of, int32_t nlev_cap);

@@ -244,3 +244,25 @@ def test_min_ref_follows_reference(golden):
     l1dims = [int(golden.level(l)["l1dim"]) for l in range(golden.nlev)]
     medw = float(golden.weight.max()) if golden.weight is not None else 1.0
     assert ahf.min_ref(par, l1dims, medw) == golden.patches()[0]
+
+
+def test_host_tree_and_halo_seeds_follow_reference(golden):
+    """ahfgpu_tree_halos (host code of the library: analyseRef + spatialRef2halos on per-refinement tables) fed with the tables the
+    oracle's restated RefCentre produces -- the same 18 columns ahfgpu_amr_patch_stats delivers from the device: substructure lists,
+    main-branch daughters and closeRefDist equal the restated analyseRef (pinned on the reference's .AHF_gridtree), and the halo seeds
+    (centre, gathering radius, particle count, order) equal the ones the reference hands to ahf_halos_sfc_constructHalo, bit for bit."""
+    from ahf_b200 import ahf
+    from oracle import oracle as O
+    min_ref = golden.patches()[0]
+    H = O.build_hierarchy(golden.pos, golden.n1d, nth_dom=golden.nper_dom, nth_ref=golden.nper_ref, patches=True)
+    stats = [np.hstack([lv.patch, O.patch_extents(lv).reshape(len(lv.patch), 6)]) for lv in H[min_ref:]]
+    out = ahf.tree_halos(stats, 3.0 / float(golden.d["boxsize"]))
+    tree = O.patch_tree(H[min_ref:])
+    for i, t in enumerate(tree):
+        assert out["sub"][i] == t["sub"], i
+        assert np.array_equal(out["daughter"][i], t["daughter"]) and np.array_equal(out["close"][i], t["close"]), i
+    hs = golden.hs
+    assert len(out["npart"]) == len(hs) and np.array_equal(out["npart"], hs[:, 4].astype(np.int64))
+    assert np.array_equal(out["pos"], hs[:, 0:3]) and np.array_equal(out["gather_rad"], hs[:, 3])
+    _, _, _, host = O.tree_to_halos(H[min_ref:], tree, 3.0 / float(golden.d["boxsize"]))
+    assert np.array_equal(out["host"], host)
