@@ -323,6 +323,20 @@ class AhfGpu:
     def min_ref(self, med_weight: float = 1.0) -> int:
         return min_ref(self.params, [int(self.level_header(l)[0][0]) for l in range(self.nlevels())], med_weight)
 
+    def halo_seeds(self, max_gather_rad: float, med_weight: float = 1.0) -> dict:
+        """From the resident hierarchy to the inputs of construct_halos without the reference's host-side mesh walk: first coloured
+        level (ahf_gridinfo.c:147-175), per level patch labels + RefCentre tables on the device (ahfgpu_amr_patch_stats), then the tree
+        and the seeds on the host (ahfgpu_tree_halos).  max_gather_rad = MaxGatherRad / boxsize."""
+        m = self.min_ref(med_weight)
+        stats = []
+        for lev in range(m, self.nlevels()):
+            n = C.c_int64(0)
+            self._chk(self._L.ahfgpu_amr_patch_stats(self._h, lev, C.byref(n), None, 0))
+            stats.append(self.patch_stats(lev, n.value))
+        out = tree_halos(stats, max_gather_rad)
+        out["min_ref"] = m; out["stats"] = stats
+        return out
+
     def patch_stats(self, lev: int, niso: int) -> np.ndarray:
         """RefCentre on the device (src/libahf/ahf_halos.c:935-1620): [niso, 18] per isolated refinement, columns as in include/ahfgpu.h."""
         st = np.zeros((max(niso, 1), 18), np.float64); n = C.c_int64(0)

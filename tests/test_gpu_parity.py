@@ -219,3 +219,21 @@ def test_patch_stats_match_reference(A, golden):
                 assert np.array_equal(st[:, 0].astype(np.int64), T[l]["nodes"]) and np.array_equal(st[:, 1].astype(np.int64), T[l]["parts"])
                 d = np.abs(st[:, 2:5] - T[l]["centre"])
                 assert np.minimum(d, 1.0 - d).max() <= 1e-11, l
+
+
+@pytest.mark.xfail(strict=False, reason="chains ahfgpu_amr_patch_stats, whose parity is not yet confirmed on hardware (see above)")
+def test_halo_seeds_from_the_device_hierarchy(A, golden):
+    """particles -> keys -> hierarchy -> patch labels -> RefCentre tables (device) -> tree and seeds (host code of the library): the
+    halo seeds equal the ones the reference's own ahf_gridinfo / RefCentre / analyseRef / spatialRef2halos hand to the halo pass
+    (golden halo_s columns 0-4): count, order and particle numbers exactly, centres and gathering radii to 1e-11."""
+    with _ctx(A, golden) as g:
+        g.sfc_sort(golden.pos, golden.mom, golden.weight, golden.u)
+        g.build_amr()
+        medw = float(golden.weight.max()) if golden.weight is not None else 1.0
+        out = g.halo_seeds(3.0 / float(golden.d["boxsize"]), medw)
+    assert out["min_ref"] == golden.patches()[0]
+    hs = golden.hs
+    assert len(out["npart"]) == len(hs) and np.array_equal(out["npart"], hs[:, 4].astype(np.int64))
+    d = np.abs(out["pos"] - hs[:, 0:3])
+    assert np.minimum(d, 1.0 - d).max() <= 1e-11
+    assert np.abs(out["gather_rad"] - hs[:, 3]).max() <= 1e-11
