@@ -1,0 +1,80 @@
+"""GPU: the entry points past the hot path whose parity is NOT yet confirmed on hardware (SURVEY 8f NEXT-2: per-patch reductions of
+RefCentre on the device, and the chain from the device hierarchy to the halo seeds).  Kept in a file that sorts last and NOT parametrised
+over the session-scoped golden fixture (pytest groups such tests by parameter across files), so that these run after every confirmed
+parity test of the suite."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, Golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def A():
+    from ahf_b200 import ahf
+    return ahf
+
+
+def _ctx(A, golden, **kw):
+    par = A.params_from_reference(golden.glob, lgrid_dom=golden.n1d, nper_dom=golden.nper_dom, nper_ref=golden.nper_ref, **kw)
+    return A.AhfGpu(par)
+
+
+# First (and only) run on hardware in round 1 -- the round's last GPU seconds: node and particle counts equal, then the maximum density
+# was (wrongly) asserted bit for bit (2096.26611 on the device against 2096.26562 of the float-accumulating reference: inside the 1e-5 of
+# `dens`).  The tolerances below are the corrected ones and have not run on a GPU yet: non-strict xfail until they have.
+def _patch_stats_case(A, golden):
+    """NEXT-2, first half: RefCentre on the device (ahfgpu_amr_patch_stats) against the restated RefCentre of the oracle (itself pinned on
+    the reference's .AHF_gridtree) and, where the fixture has the case, against the gridtree file directly: node and particle counts,
+    extents exact, geometric and particle centres to 1e-11 (double atomics sum in another order); the maximum density and the density-weighted
+    centre inherit the tolerance of `dens` itself (1e-5: the device deposit is fixed point, the reference accumulates in float)."""
+    from oracle import oracle as O
+    H = O.build_hierarchy(golden.pos, golden.n1d, nth_dom=golden.nper_dom, nth_ref=golden.nper_ref, patches=True)
+    T = golden.gridtree()
+    with _ctx(A, golden) as g:
+        g.sfc_sort(golden.pos, golden.mom, golden.weight, golden.u)
+        nl = g.build_amr()
+        for l in range(1, nl):
+            niso = len(H[l].patch)
+            st = g.patch_stats(l, niso)
+            ref = H[l].patch
+            assert np.array_equal(st[:, 0:2], ref[:, 0:2]), l
+            assert np.allclose(st[:, 5], ref[:, 5], rtol=1e-5, atol=0), l
+            for a, b, tol in ((st[:, 2:5], ref[:, 2:5], 1e-11), (st[:, 6:9], ref[:, 6:9], 1e-11), (st[:, 9:12], ref[:, 9:12], 2e-5)):
+                d = np.abs(a - b)
+                assert np.minimum(d, 1.0 - d).max() <= tol, l
+            assert np.array_equal(st[:, 12:18].reshape(niso, 3, 2), O.patch_extents(H[l])), l
+            if T is not None and l in T:
+                assert np.array_equal(st[:, 0].astype(np.int64), T[l]["nodes"]) and np.array_equal(st[:, 1].astype(np.int64), T[l]["parts"])
+                d = np.abs(st[:, 2:5] - T[l]["centre"])
+                assert np.minimum(d, 1.0 - d).max() <= 1e-11, l
+
+
+def _halo_seeds_case(A, golden):
+    """particles -> keys -> hierarchy -> patch labels -> RefCentre tables (device) -> tree and seeds (host code of the library): the
+    halo seeds equal the ones the reference's own ahf_gridinfo / RefCentre / analyseRef / spatialRef2halos hand to the halo pass
+    (golden halo_s columns 0-4): count, order and particle numbers exactly, centres and gathering radii to 1e-11."""
+    with _ctx(A, golden) as g:
+        g.sfc_sort(golden.pos, golden.mom, golden.weight, golden.u)
+        g.build_amr()
+        medw = float(golden.weight.max()) if golden.weight is not None else 1.0
+        out = g.halo_seeds(3.0 / float(golden.d["boxsize"]), medw)
+    assert out["min_ref"] == golden.patches()[0]
+    hs = golden.hs
+    assert len(out["npart"]) == len(hs) and np.array_equal(out["npart"], hs[:, 4].astype(np.int64))
+    d = np.abs(out["pos"] - hs[:, 0:3])
+    assert np.minimum(d, 1.0 - d).max() <= 1e-11
+    assert np.abs(out["gather_rad"] - hs[:, 3]).max() <= 1e-11
+
+
+@pytest.mark.xfail(strict=False, reason="tolerances corrected after the last GPU run of round 1; not yet re-run on hardware")
+def test_patch_stats_match_reference(A):
+    for name in GOLDEN_CASES:
+        _patch_stats_case(A, Golden(name))
+
+
+@pytest.mark.xfail(strict=False, reason="chains ahfgpu_amr_patch_stats, whose parity is not yet confirmed on hardware")
+def test_halo_seeds_from_the_device_hierarchy(A):
+    for name in GOLDEN_CASES:
+        _halo_seeds_case(A, Golden(name))
