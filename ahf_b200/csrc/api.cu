@@ -157,6 +157,14 @@ int ahfgpu_init(ahfgpu_ctx **out, const ahfgpu_params *par)
   if (ndev <= 0) AHF_FAIL("no CUDA device: libahfgpu has no CPU fallback");
   if (par->device < 0 || par->device >= ndev) AHF_FAIL("device ordinal out of range");
   CUDA_CHECK(cudaSetDevice(par->device));
+  {                                                   // kernel attributes / __constant__ symbols are per device: once for each ordinal
+    static std::mutex mu; static bool done[64] = {};
+    std::lock_guard<std::mutex> lk(mu);
+    if (par->device >= 64 || !done[par->device]) {
+      ahf::mesh_device_init(); ahf::sfc_device_init();
+      if (par->device < 64) done[par->device] = true;
+    }
+  }
   ahfgpu_ctx *c = new ahfgpu_ctx();
   c->par = *par; c->dev = par->device;
   try {

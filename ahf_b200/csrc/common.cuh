@@ -234,6 +234,8 @@ void sfc_keys_only(ahfgpu_ctx *c, const float *pos3, uint64_t n, uint32_t bits, 
 void radix_sort_pairs(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, uint64_t n,
                       int key_bits, uint64_t **keys_sorted, uint32_t **vals_sorted, int first_bit = 0);
 void amr_build(ahfgpu_ctx *c);
+void mesh_device_init();
+void sfc_device_init();
 void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const double *gather_rad, const int64_t *seed);
 
 }  // namespace ahf

@@ -1510,6 +1510,25 @@ static std::string lvl_name(const char *base, int lev) { char b[48]; snprintf(b,
 // per-level stage timers (scripts/stage_breakdown.py) are opt-in: AHFGPU_LEVEL_STAGES=1 (MeshEnv); the per-pass totals are always taken
 
 
+// per-DEVICE setup of the mesh kernels (function attributes and __constant__ symbols belong to the current device): called once per
+// device from ahfgpu_init
+void mesh_device_init()
+{
+  CUDA_CHECK(cudaFuncSetAttribute(k_deposit_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
+  CUDA_CHECK(cudaFuncSetAttribute(k_deposit_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
+  CUDA_CHECK(cudaFuncSetAttribute(k_deposit_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, DR_SMEM));
+  CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
+#ifdef AHFGPU_EXPERIMENTS      // timing-only variants of the domain kernel (wrong densities on purpose): never in the shipped library
+  CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
+  CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
+  CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
+  CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
+#endif
+  uint16_t off[27];
+  for (int k = 0; k < 3; k++) for (int j = 0; j < 3; j++) for (int a = 0; a < 3; a++) off[k * 9 + j * 3 + a] = (uint16_t)(4 * ((k * DT_H + j) * DT_H + a));
+  CUDA_CHECK(cudaMemcpyToSymbol(c_dom_off, off, sizeof(off)));
+}
+
 static void deposit_level(ahfgpu_ctx *c, Level &lv)
 {
   const int lev_id = (int)c->levels.size() - 1;
@@ -1526,23 +1545,6 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
   const int    S = (tiles_dense && !dom_v1) ? 32 : fx_shift_for(lv.masstopartdens);    // k_deposit_dom works in 2^-32 units
   const double fxscale = (double)(1ull << S);
   const bool tiles_sparse = !lv.dense && lv.lpos && lv.npart_dep >= 2048 && v.logL - 4 <= 20 && !generic_only;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_deposit_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
-    CUDA_CHECK(cudaFuncSetAttribute(k_deposit_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
-    CUDA_CHECK(cudaFuncSetAttribute(k_deposit_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, DR_SMEM));
-    CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
-#ifdef AHFGPU_EXPERIMENTS      // timing-only variants of the domain kernel (wrong densities on purpose): never in the shipped library
-    CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
-    CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
-    CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
-    CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
-#endif
-    uint16_t off[27];
-    for (int k = 0; k < 3; k++) for (int j = 0; j < 3; j++) for (int a = 0; a < 3; a++) off[k * 9 + j * 3 + a] = (uint16_t)(4 * ((k * DT_H + j) * DT_H + a));
-    CUDA_CHECK(cudaMemcpyToSymbol(c_dom_off, off, sizeof(off)));
-    attr_set = true;
-  }
   if (tiles_dense || tiles_sparse) {
     // tiles are Hilbert cells of (logL - 4) bits per dimension: contiguous ranges of the (level's) particle list
     const int tbits = v.logL - 4;
@@ -1928,7 +1930,14 @@ __device__ __forceinline__ double node_coord(int x, double L, double shift) { re
 __device__ __forceinline__ void atomic_max_pos(double *a, double v) { atomicMax(reinterpret_cast<unsigned long long *>(a), (unsigned long long)__double_as_longlong(v)); }
 __device__ __forceinline__ void atomic_min_pos(double *a, double v) { atomicMin(reinterpret_cast<unsigned long long *>(a), (unsigned long long)__double_as_longlong(v)); }
 
-__global__ void k_pstat_cells(LV v, const int32_t *__restrict__ iso, const uint8_t *__restrict__ per3, const float *__restrict__ dens, double *acc)
+// Integer sums (PS_IACC u64 words per refinement: 0 nodes, 1-3 sum of (2x+1) [+2L across a periodic face], 4 particles, 5-7 sum of
+// trunc(x * 2^36)): node coordinates are the dyadic rationals (2x+1)/(2L) and particle coordinates are float32, so these sums are EXACT
+// (particles: for coordinates >= 2^-13, below that truncated to 2^-36), independent of the order of the atomics -- the table is bit
+// reproducible from run to run and equals the reference's sequential double sums wherever those are exact themselves.
+constexpr int PS_IACC = 8;
+constexpr double PS_PSCALE = 68719476736.0;       // 2^36: 2 * 2^36 * 2^26 particles of one refinement fit 63 bits
+__global__ void k_pstat_cells(LV v, const int32_t *__restrict__ iso, const uint8_t *__restrict__ per3, const float *__restrict__ dens, double *acc,
+                              unsigned long long *iacc)
 {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= v.ncell) return;
@@ -1937,20 +1946,22 @@ __global__ void k_pstat_cells(LV v, const int32_t *__restrict__ iso, const uint8
   lv_coords(v, c, x, y, z);
   const double L = (double)v.L, shift = 0.5 / L;
   double xx = node_coord(x, L, shift), yy = node_coord(y, L, shift), zz = node_coord(z, L, shift);
-  if (per3[3 * i + 0] && xx < 0.5) xx += 1.0;                        // :1032-1040
-  if (per3[3 * i + 1] && yy < 0.5) yy += 1.0;
-  if (per3[3 * i + 2] && zz < 0.5) zz += 1.0;
+  unsigned long long ix = 2ull * (unsigned long long)x + 1ull, iy = 2ull * (unsigned long long)y + 1ull, iz = 2ull * (unsigned long long)z + 1ull;
+  if (per3[3 * i + 0] && xx < 0.5) { xx += 1.0; ix += 2ull * (unsigned long long)v.L; }                        // :1032-1040
+  if (per3[3 * i + 1] && yy < 0.5) { yy += 1.0; iy += 2ull * (unsigned long long)v.L; }
+  if (per3[3 * i + 2] && zz < 0.5) { zz += 1.0; iz += 2ull * (unsigned long long)v.L; }
   double d = (double)dens[c] + 1.0;                                  // + simu.mean_dens, :1057
   if (d < 0.0) d = 0.0;
   double *a = acc + (size_t)PS_ACC * i;
-  atomicAdd(a + 0, 1.0);
-  atomicAdd(a + 2, xx); atomicAdd(a + 3, yy); atomicAdd(a + 4, zz); atomicAdd(a + 5, 1.0);
+  unsigned long long *ia = iacc + (size_t)PS_IACC * i;
+  atomicAdd(ia + 0, 1ull); atomicAdd(ia + 1, ix); atomicAdd(ia + 2, iy); atomicAdd(ia + 3, iz);
   atomicAdd(a + 6, xx * d); atomicAdd(a + 7, yy * d); atomicAdd(a + 8, zz * d); atomicAdd(a + 9, d);
   atomic_max_pos(a + 10, d);
 }
 // particles the level finally owns (node.ll at ahf_halos time): centre of mass of the refinement's particles (:1120-1180)
 __global__ void k_pstat_parts(const float4 *__restrict__ pos4, const uint32_t *__restrict__ plist, const int32_t *__restrict__ pcell, uint64_t np,
-                              const int8_t *__restrict__ owner, int lev, const int32_t *__restrict__ iso, const uint8_t *__restrict__ per3, double *acc)
+                              const int8_t *__restrict__ owner, int lev, const int32_t *__restrict__ iso, const uint8_t *__restrict__ per3,
+                              unsigned long long *iacc)
 {
   uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (k >= np) return;
@@ -1964,25 +1975,28 @@ __global__ void k_pstat_parts(const float4 *__restrict__ pos4, const uint32_t *_
   if (per3[3 * i + 0] && xp < 0.5) xp += 1.0;
   if (per3[3 * i + 1] && yp < 0.5) yp += 1.0;
   if (per3[3 * i + 2] && zp < 0.5) zp += 1.0;
-  double *a = acc + (size_t)PS_ACC * i;
-  atomicAdd(a + 1, 1.0);
-  atomicAdd(a + 11, xp); atomicAdd(a + 12, yp); atomicAdd(a + 13, zp); atomicAdd(a + 14, 1.0);
+  unsigned long long *ia = iacc + (size_t)PS_IACC * i;
+  atomicAdd(ia + 4, 1ull);
+  atomicAdd(ia + 5, (unsigned long long)(xp * PS_PSCALE)); atomicAdd(ia + 6, (unsigned long long)(yp * PS_PSCALE)); atomicAdd(ia + 7, (unsigned long long)(zp * PS_PSCALE));
 }
 __device__ __forceinline__ double f1mod1(double v) { return v >= 2.0 ? v - 2.0 : v >= 1.0 ? v - 1.0 : v; }     // specific.c:120-129
 // normalisation and fall-backs (:1240-1370), boundRefDiv of the periodic refinements (:1400-1470).
 // out[i][18]: 0 numNodes 1 numParts 2-4 centre (= particle centre, AHFcomcentre) 5 maxDens 6-8 centreGEOM 9-11 centreDens 12-17 extents
-__global__ void k_pstat_finish(const double *__restrict__ acc, const uint8_t *__restrict__ per3, int niso, double L, double *__restrict__ out, double *__restrict__ div3)
+__global__ void k_pstat_finish(const double *__restrict__ acc, const unsigned long long *__restrict__ iacc, const uint8_t *__restrict__ per3, int niso, double L,
+                               double *__restrict__ out, double *__restrict__ div3)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= niso) return;
   const double *a = acc + (size_t)PS_ACC * i;
+  const unsigned long long *ia = iacc + (size_t)PS_IACC * i;
   double *o = out + (size_t)18 * i;
-  o[0] = a[0]; o[1] = a[1]; o[5] = a[10];
-  for (int q = 0; q < 3; q++) o[6 + q] = a[5] > 0 ? f1mod1(a[2 + q] / a[5] + 1.0) : a[2 + q];
+  const double nnode = (double)ia[0], npart = (double)ia[4];
+  o[0] = nnode; o[1] = npart; o[5] = a[10];
+  for (int q = 0; q < 3; q++) o[6 + q] = nnode > 0 ? f1mod1(((double)ia[1 + q] / (2.0 * L)) / nnode + 1.0) : 0.0;
   for (int q = 0; q < 3; q++) o[9 + q] = a[9] > 0 ? f1mod1(a[6 + q] / a[9] + 1.0) : o[6 + q];
-  for (int q = 0; q < 3; q++) o[2 + q] = a[14] > 0 ? f1mod1(a[11 + q] / a[14] + 1.0) : o[6 + q];
+  for (int q = 0; q < 3; q++) o[2 + q] = npart > 0 ? f1mod1(((double)ia[5 + q] / PS_PSCALE) / npart + 1.0) : o[6 + q];
   if (a[10] <= 5e-16) for (int q = 0; q < 3; q++) o[9 + q] = o[6 + q];
-  const double bl = 1.0 / L, vol = a[0] * (bl * bl * bl);
+  const double bl = 1.0 / L, vol = nnode * (bl * bl * bl);
   const double rad = pow((3.0 * vol) / (4 * 3.14159265358979323846), 0.333333333) * 1.1;
   for (int q = 0; q < 3; q++) {
     double dv = -1.0;
@@ -2033,7 +2047,7 @@ extern "C" int ahfgpu_amr_patch_stats(ahfgpu_ctx *c, int32_t lev, int64_t *niso,
     int ni = 0;
     if (nc > 0) {
       LV v = view(l);
-      DevBuf<int32_t> parent, root, diso; DevBuf<uint8_t> isroot, per; DevBuf<int> rank; DevBuf<double> acc, out, div3;
+      DevBuf<int32_t> parent, root, diso; DevBuf<uint8_t> isroot, per; DevBuf<int> rank; DevBuf<double> acc, out, div3; DevBuf<unsigned long long> iacc;
       parent.reserve(nc); root.reserve(nc); diso.reserve(nc); isroot.reserve(nc); rank.reserve(nc); per.reserve((size_t)3 * nc);
       LAUNCH(c, k_patch_init, nblk(nc, 256), 256, 0, parent.p, nc);
       LAUNCH(c, k_patch_link, nblk(nc, 256), 256, 0, v, l.nbr, parent.p);
@@ -2043,16 +2057,18 @@ extern "C" int ahfgpu_amr_patch_stats(ahfgpu_ctx *c, int32_t lev, int64_t *niso,
       LAUNCH(c, k_patch_iso, nblk(nc, 256), 256, 0, v, l.nbr, root.p, rank.p, diso.p, per.p);
       if (stats && (int64_t)ni > stats_cap) AHF_FAIL("stats buffer too small");
       acc.reserve((size_t)PS_ACC * ni); out.reserve((size_t)18 * ni); div3.reserve((size_t)3 * ni);
+      iacc.reserve((size_t)PS_IACC * ni);
       CUDA_CHECK(cudaMemsetAsync(acc.p, 0, sizeof(double) * PS_ACC * ni, c->stream));
-      LAUNCH(c, k_pstat_cells, nblk(nc, 256), 256, 0, v, diso.p, per.p, l.dens, acc.p);
+      CUDA_CHECK(cudaMemsetAsync(iacc.p, 0, sizeof(unsigned long long) * PS_IACC * ni, c->stream));
+      LAUNCH(c, k_pstat_cells, nblk(nc, 256), 256, 0, v, diso.p, per.p, l.dens, acc.p, iacc.p);
       if (l.npart_dep > 0)
-        LAUNCH(c, k_pstat_parts, nblk(l.npart_dep, 256), 256, 0, c->pos4, l.plist, l.pcell, (uint64_t)l.npart_dep, c->owner_level, (int)lev, diso.p, per.p, acc.p);
-      LAUNCH(c, k_pstat_finish, nblk(ni, 128), 128, 0, acc.p, per.p, ni, (double)l.L, out.p, div3.p);
+        LAUNCH(c, k_pstat_parts, nblk(l.npart_dep, 256), 256, 0, c->pos4, l.plist, l.pcell, (uint64_t)l.npart_dep, c->owner_level, (int)lev, diso.p, per.p, iacc.p);
+      LAUNCH(c, k_pstat_finish, nblk(ni, 128), 128, 0, acc.p, iacc.p, per.p, ni, (double)l.L, out.p, div3.p);
       LAUNCH(c, k_pstat_extents, nblk(nc, 256), 256, 0, v, diso.p, div3.p, out.p);
       LAUNCH(c, k_pstat_fix, nblk(ni, 128), 128, 0, ni, out.p);
       CUDA_CHECK(cudaStreamSynchronize(c->stream));
       if (stats && ni > 0) CUDA_CHECK(cudaMemcpy(stats, out.p, sizeof(double) * 18 * (size_t)ni, cudaMemcpyDeviceToHost));
-      parent.release(); root.release(); diso.release(); isroot.release(); rank.release(); per.release(); acc.release(); out.release(); div3.release();
+      parent.release(); root.release(); diso.release(); isroot.release(); rank.release(); per.release(); acc.release(); out.release(); div3.release(); iacc.release();
     }
     if (niso) *niso = ni;
     return 0;

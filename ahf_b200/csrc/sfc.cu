@@ -26,17 +26,7 @@ __global__ void k_keys_soa(const float *__restrict__ pos3, uint64_t n, uint32_t 
 // CTA, which then strides over the particles [i0, i1).  The generic k_keys_soa needs ~420 dependent integer instructions per key
 // and was issue bound (0.43 ms for 256^3); this form needs about a third.
 __device__ uint16_t g_hil_tab3[12 * 512];
-static void upload_hil_tab3()
-{
-  static bool done[64] = {};
-  int dev = 0;
-  CUDA_CHECK(cudaGetDevice(&dev));
-  if (dev < 64 && done[dev]) return;
-  static uint16_t h[12 * 512];
-  hilbert_build_tab3(h);
-  CUDA_CHECK(cudaMemcpyToSymbol(g_hil_tab3, h, sizeof(h)));
-  if (dev < 64) done[dev] = true;
-}
+static void upload_hil_tab3() {}      // done per device in sfc_device_init (ahfgpu_init)
 constexpr int KT_THREADS = 256;
 __global__ void __launch_bounds__(KT_THREADS) k_keys_soa_tab(const float *__restrict__ pos3, uint64_t i0, uint64_t i1, uint64_t *__restrict__ keys,
                                                              uint32_t *__restrict__ idx)
@@ -195,8 +185,6 @@ static void radix_sort_pairs_t(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, ui
   const uint32_t nblk = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
   DevBuf<uint32_t> bh;
   DevBuf<int>      bs;
-  static bool attr_set = false;
-  if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(k_rs_scatter<RS_ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM)); attr_set = true; }
   bh.reserve((size_t)256 * nblk);
   uint64_t *ki = keys, *ko = keys_tmp;
   uint32_t *vi = vals, *vo = vals_tmp;
@@ -214,6 +202,22 @@ static void radix_sort_pairs_t(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, ui
   }
   bh.release(); bs.release();                       // stream-ordered block cache: no host sync needed
   *keys_sorted = ki; *vals_sorted = vi;
+}
+
+// per-DEVICE setup of the sort kernels and the Hilbert table (called once per device from ahfgpu_init)
+void sfc_device_init()
+{
+  {
+    constexpr int RS_ITEMS = 8;
+    CUDA_CHECK(cudaFuncSetAttribute(k_rs_scatter<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM));
+  }
+  {
+    constexpr int RS_ITEMS = 16;
+    CUDA_CHECK(cudaFuncSetAttribute(k_rs_scatter<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM));
+  }
+  std::vector<uint16_t> h(12 * 512);
+  hilbert_build_tab3(h.data());
+  CUDA_CHECK(cudaMemcpyToSymbol(g_hil_tab3, h.data(), h.size() * sizeof(uint16_t)));
 }
 
 void radix_sort_pairs(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, uint64_t n,

@@ -6,15 +6,20 @@
  * `-Dcallee=ahfb200_callee`, which lands the calls in this file, and this file calls libahfgpu.so (include/ahfgpu.h).
  *
  *   src/main.c:343-356        key loop + qsort            -> ahfb200_calcKey (stub) + ahfb200_qsort  -> ahfgpu_sfc_sort_particles
- *   src/libahf/ahf_halos.c:504-510   OpenMP halo loop     -> ahfb200_constructHalo (collects the HALO pointers)
- *                                                            + ahfb200_fprintf (first serial statement after the loop)
- *                                                            -> ahfgpu_construct_halos / ahfgpu_halo_fetch -> HALO, c_profile arrays
+ *   src/libahf/ahf_halos.c:504-510   OpenMP halo loop     -> ahfb200_constructHalo (collects the HALO pointers); the batched device pass
+ *                                                            runs when the loop's parallel region ends (GOMP_parallel below: deterministic,
+ *                                                            independent of VERBOSE) -> ahfgpu_construct_halos / ahfgpu_halo_fetch
+ *                                                            -> HALO, c_profile arrays.  A build without OpenMP handles every halo at once.
  *   src/main.c:616-648        gen_domgrids / ll / zero_dens / assign_npart / gen_AMRhierarchy
  *                                                         -> ahfb200_gen_domgrids -> ahfgpu_build_amr + rebuild of the reference's quads
  *                                                            (only in the AHF-b200 build; AHF-b200-kh keeps the CPU mesh)
  * Everything else -- readers, ahf_gridinfo, tree, subhalo re-hash, writers -- is the reference, so the catalogues come out in
  * AHF's own formats.
  */
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE                /* RTLD_NEXT */
+#endif
+#include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <stdarg.h>
@@ -219,13 +224,18 @@ boolean ahfb200_gen_AMRhierarchy(gridls **grid_list, int *no_grids) { (void)grid
 static HALO **pend = NULL;
 static long   npend = 0, cappend = 0;
 
+static void flush_halos(void);
+
 void ahfb200_constructHalo(HALO *h)
 {
 #pragma omp critical(ahfb200_pend)
   {
-    if (npend == cappend) { cappend = cappend ? 2 * cappend : 1024; pend = realloc(pend, cappend * sizeof(HALO *)); }
+    if (npend == cappend) { cappend = cappend ? 2 * cappend : 1024; pend = realloc(pend, cappend * sizeof(HALO *)); if (!pend) { fprintf(stderr, "ahf_glue: out of memory\n"); exit(EXIT_FAILURE); } }
     pend[npend++] = h;
   }
+#ifndef _OPENMP
+  flush_halos();                    /* serial build: no parallel region whose end could trigger the batch */
+#endif
 }
 
 static int cmp_ptr(const void *a, const void *b)
@@ -322,15 +332,26 @@ static void flush_halos(void)
   free(ctr); free(rad); free(seed); free(scal); free(moff); free(poff); free(mem); free(prof);
 }
 
-/* every fprintf of ahf_halos.c passes through here; the first one issued from serial code after the halo loop
- * (ahf_halos.c:540, VERBOSE is on in define.h:20) triggers the batched device pass */
-int ahfb200_fprintf(FILE *f, const char *fmt, ...)
+/* The halo loop is `#pragma omp parallel for` (ahf_halos.c:504-510): gcc lowers it to GOMP_parallel(outlined body).  This definition
+ * takes precedence over libgomp's for the whole program; it runs the region through the real entry point and, when the region that
+ * collected HALO pointers has ended, runs the batched device pass -- before the first serial statement that reads a HALO (the
+ * sub-halo re-hash, ahf_halos.c:553), whatever that statement is and whether or not VERBOSE is defined. */
+#ifdef _OPENMP
+void GOMP_parallel(void (*fn)(void *), void *data, unsigned num_threads, unsigned flags)
 {
-  va_list ap;
-  int     r;
+  static void (*real)(void (*)(void *), void *, unsigned, unsigned) = NULL;
+  if (!real) {
+    *(void **)(&real) = dlsym(RTLD_NEXT, "GOMP_parallel");
+    if (!real) { fprintf(stderr, "ahf_glue: libgomp's GOMP_parallel not found\n"); exit(EXIT_FAILURE); }
+  }
+  real(fn, data, num_threads, flags);
   if (npend > 0 && !omp_in_parallel()) flush_halos();
-  va_start(ap, fmt);
-  r = vfprintf(f, fmt, ap);
-  va_end(ap);
-  return r;
 }
+#endif
+
+/* safety net: the catalogue writers must never see haloes the device pass has not filled */
+static void check_flushed(void)
+{
+  if (npend > 0) { fprintf(stderr, "ahf_glue: %ld haloes were collected but never constructed on the device\n", npend); _Exit(EXIT_FAILURE); }
+}
+__attribute__((constructor)) static void ahfb200_register(void) { atexit(check_flushed); }

@@ -19,7 +19,7 @@ for f in "$REF"/*.c "$REF"/lib*/*.c; do
   extra=""
   case "$base" in
     src_main)         extra="-Dsfc_curve_calcKey=ahfb200_calcKey -Dqsort=ahfb200_qsort $mainflags" ;;
-    libahf_ahf_halos) extra="-U_FORTIFY_SOURCE -D_FORTIFY_SOURCE=0 -Dahf_halos_sfc_constructHalo=ahfb200_constructHalo -Dfprintf=ahfb200_fprintf" ;;   # fortify would turn fprintf into an inline wrapper
+    libahf_ahf_halos) extra="-Dahf_halos_sfc_constructHalo=ahfb200_constructHalo" ;;
   esac
   $CC $extra -c "$f" -o "$OUT/obj/$base.o" &
   pids+=($!)
@@ -29,7 +29,7 @@ wait
 $CC -c "$HERE/ahf_glue.c" -o "$OUT/ahf_glue.o"
 mv "$OUT/obj/src_main.o" "$OUT/"
 ar rcs "$OUT/libref.a" "$OUT"/obj/*.o
-gcc -fopenmp -o "$OUT/$name" "$OUT/src_main.o" "$OUT/ahf_glue.o" "$OUT/libref.a" -L"$REPO/ahf_b200" -lahfgpu -Wl,-rpath,'$ORIGIN/../..' -lm
+gcc -fopenmp -o "$OUT/$name" "$OUT/src_main.o" "$OUT/ahf_glue.o" "$OUT/libref.a" -L"$REPO/ahf_b200" -lahfgpu -Wl,-rpath,'$ORIGIN/../..' -lm -ldl
 rm -rf "$OUT/obj" "$OUT/src_main.o" "$OUT/ahf_glue.o" "$OUT/libref.a"
 }
 # AHF-b200    : key/sort, mesh and halo loop on the GPU

@@ -1,0 +1,142 @@
+"""Shared checkers of the GPU parity tests: the CUDA path (through the C-ABI) against a dump of the UNMODIFIED reference
+(oracle/_ref/ahf_ref run on the box, oracle/ref_hooks.c dumps) with the tolerances of BASELINE.json's north star written out:
+
+  * Hilbert keys, cell sets, run structure, particles per node, particle -> node maps, final ownership: identical
+  * density per cell: 1e-5 relative (against max(|dens|, 1): dens is a contrast that crosses zero)
+  * halo count and all stage counts: identical
+  * M_vir, R_vir: 1e-4 relative (asserted at 1e-9 as well: the halo arithmetic is double on both sides)
+  * bound-member overlap >= 99.9 % for haloes above 100 particles (asserted: identical ID lists)
+  * profile columns 1e-8 relative, eigenvector columns up to sign
+
+Everything that refers to a position in the key-sorted particle array is translated to particle IDs first, because particles with
+equal Hilbert keys may be ordered differently by the two sorts (libc qsort is unstable)."""
+import os
+
+import numpy as np
+
+DENS_TOL = 1e-5
+MR_TOL = 1e-4
+OVERLAP_MIN = 0.999
+
+
+def eigvec_cols_match(pr, pg, rtol=1e-6, atol=1e-8):
+    """profile columns 13-24: (axis, Ex, Ey, Ez) x 3 per bin; eigenvectors are defined up to sign, and up to a rotation inside a
+    degenerate eigenspace (bins whose axes coincide to 1e-6 are skipped)"""
+    bad = []
+    ax = np.stack([pr[13], pr[17], pr[21]])
+    for b in range(pr.shape[1]):
+        for t, c0 in enumerate((14, 18, 22)):
+            others = [ax[q, b] for q in range(3) if q != t]
+            if any(abs(ax[t, b] - o) <= 1e-6 * max(abs(ax[t, b]), abs(o), 1e-300) for o in others):
+                continue
+            va, vb = pr[c0:c0 + 3, b], pg[c0:c0 + 3, b]
+            if not (np.allclose(va, vb, rtol=rtol, atol=atol) or np.allclose(va, -vb, rtol=rtol, atol=atol)):
+                bad.append((b, c0, va.tolist(), vb.tolist()))
+    return bad
+
+
+def run_reference_dump(box, workdir, lgrid_dom=None):
+    """unmodified reference on `box`; returns dict(P=particles, H=halos, levels=[...], finals=[...])"""
+    from ahf_b200 import synth
+    from oracle import oracle as O
+    inp = synth.write_reference_case(box, workdir, lgrid_domain=lgrid_dom)
+    d = os.path.join(workdir, "dump")
+    timing = O.run_reference(inp, dump_dir=d)
+    P = O.read_particles(os.path.join(d, "particles.bin"))
+    H = O.read_halos(d)
+    nlev = len([f for f in os.listdir(d) if f.startswith("flag_level_")])
+    return dict(P=P, H=H, nlev=nlev, dir=d, timing=timing)
+
+
+def compare_with_reference(A, box, R, lgrid_dom, check_cells_of=True):
+    """the whole path on the device against the dump `R`; returns a dict of measured worst-case deviations"""
+    from oracle import oracle as O
+    P, H, d = R["P"], R["H"], R["dir"]
+    out = {}
+    par = A.params_from_reference(H.glob, lgrid_dom=lgrid_dom)
+    with A.AhfGpu(par) as g:
+        keys, order = g.sfc_sort(box.pos, box.mom)
+        assert np.array_equal(keys, P.keys), "Hilbert keys / sorted key sequence"
+        ids_ref = P.ids.astype(np.int64)
+        order = order.astype(np.int64)
+        assert np.array_equal(np.sort(order), np.arange(len(order)))
+        ties = int((keys[1:] == keys[:-1]).sum())
+        out["equal_key_pairs"] = ties
+        if ties == 0:
+            assert np.array_equal(order, ids_ref)
+        nl = g.build_amr()
+        assert nl == R["nlev"], (nl, R["nlev"])
+        owner, cells = g.particle_levels(with_cells=check_cells_of)
+        n = len(keys)
+        owner_by_id = np.empty(n, np.int8); owner_by_id[order] = owner
+        worst = 0.0
+        for l in range(nl):
+            G = g.level(l)
+            Rl = O.read_level(os.path.join(d, "flag_level_%02d.bin" % l))
+            Fl = O.read_level(os.path.join(d, "final_level_%02d.bin" % l))
+            assert G.l1dim == Rl.l1dim and G.ncell == Rl.ncell, (l, G.ncell, Rl.ncell)
+            assert np.array_equal(G.lin(), Rl.lin()), "cell set differs on level %d" % l
+            assert np.array_equal(G.runflags, Rl.runflags), "run structure differs on level %d" % l
+            assert np.array_equal(G.count, Rl.cnt_flag), "particles per node differ on level %d" % l
+            err = np.abs(G.dens.astype(np.float64) - Rl.dens) / np.maximum(np.abs(Rl.dens), 1.0)
+            worst = max(worst, float(err.max()))
+            assert err.max() <= DENS_TOL, (l, err.max())
+            assert abs(G.critdens - Rl.critdens) <= 1e-12 * G.critdens
+            if check_cells_of:                      # particle -> node map, by particle ID
+                cell_ref = np.full(n, -1, np.int64)
+                cell_ref[ids_ref[Rl.plist_flag]] = np.repeat(np.arange(G.ncell), Rl.cnt_flag)
+                cell_gpu = np.empty(n, np.int64); cell_gpu[order] = cells[l]
+                assert np.array_equal(cell_gpu, cell_ref), "particle -> node map differs on level %d" % l
+            fin_ref = np.zeros(n, bool); fin_ref[ids_ref[Fl.plist_flag]] = True
+            assert np.array_equal(owner_by_id == l, fin_ref), "final ownership differs on level %d" % l
+            del G, Rl, Fl
+        out["dens_max_rel_err"] = worst
+        # ---- halo pass on the reference's own seeds
+        res = g.construct_halos(H.s[:, 0:3].copy(), H.s[:, 3].copy(), H.s[:, 4].astype(np.int64))
+        S = res["scal"]
+        minpart = int(H.glob[9])
+        assert int((S[:, 9] >= minpart).sum()) == int((H.s[:, 9] >= minpart).sum()), "halo count"
+        nbig = n100 = 0
+        worst_mr = worst_scal = worst_prof = 0.0
+        slots = [10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37,
+                 38, 39, 40, 41, 42, 43, 53, 54, 55, 56, 57]
+        for i in range(H.n):
+            if H.s[i, 4] == 0:
+                assert S[i, 9] == 0
+                continue
+            assert np.array_equal(S[i, 5:10], H.s[i, 5:10]), (i, S[i, 5:10], H.s[i, 5:10])     # gathered / Rvir / unbound / Rvir / final counts
+            m_gpu = order[g.halo_members(res, i)]
+            m_ref = ids_ref[H.members[i]]
+            if not np.array_equal(m_gpu, m_ref):
+                # equal radii (identical positions) may swap places; the SETS must agree to the north-star overlap
+                inter = np.intersect1d(m_gpu, m_ref).size
+                assert inter >= OVERLAP_MIN * max(len(m_ref), 1) and len(m_gpu) == len(m_ref), (i, inter, len(m_ref))
+                assert inter == len(m_ref), ("member IDs differ", i, inter, len(m_ref))
+            if H.s[i, 9] > 100:
+                n100 += 1
+            if H.s[i, 9] < minpart:
+                continue
+            nbig += 1
+            for k in (10, 11):
+                e = abs(S[i, k] - H.s[i, k]) / abs(H.s[i, k])
+                worst_mr = max(worst_mr, e)
+                assert e <= MR_TOL, (i, k, S[i, k], H.s[i, k])
+            a, b = H.s[i, slots], S[i, slots]
+            ok = np.isclose(a, b, rtol=1e-8, atol=1e-300)
+            assert ok.all(), (i, [(slots[k], a[k], b[k]) for k in np.nonzero(~ok)[0]])
+            nz = a != 0
+            if nz.any():
+                worst_scal = max(worst_scal, float(np.max(np.abs(a[nz] - b[nz]) / np.abs(a[nz]))))
+            for k0 in (44, 47, 50):                # eigenvectors: up to sign
+                va, vb = H.s[i, k0:k0 + 3], S[i, k0:k0 + 3]
+                assert np.allclose(va, vb, rtol=1e-6, atol=1e-8) or np.allclose(va, -vb, rtol=1e-6, atol=1e-8), (i, k0, va, vb)
+            pr, pg = H.prof[i], g.halo_profile(res, i)
+            assert pg is not None and pg.shape == pr.shape
+            cols = [c for c in range(25) if c not in (14, 15, 16, 18, 19, 20, 22, 23, 24)]
+            okp = np.isclose(pr[cols], pg[cols], rtol=1e-8, atol=1e-300)
+            assert okp.all(), (i, np.argwhere(~okp)[:5])
+            bad = eigvec_cols_match(pr, pg)
+            assert not bad, (i, bad[:3])
+        out.update(halos=H.n, halos_ge_minpart=nbig, halos_gt_100=n100, mvir_rvir_max_rel_err=worst_mr, scalar_max_rel_err=worst_scal,
+                   levels=nl)
+    return out
