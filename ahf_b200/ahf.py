@@ -139,7 +139,18 @@ def lib():
         L.ahfgpu_device_ptr.restype = C.c_void_p
         L.ahfgpu_device_ptr.argtypes = [C.c_void_p, C.c_char_p]
         L.ahfgpu_set_global_count.argtypes = [C.c_void_p, C.c_uint64]
-        L.ahfgpu_set_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ahfgpu_comm_nccl_unique_id.argtypes = [C.c_void_p]
+        L.ahfgpu_comm_init_nccl.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        L.ahfgpu_comm_local_group_create.restype = C.c_void_p
+        L.ahfgpu_comm_local_group_create.argtypes = [C.c_int32]
+        L.ahfgpu_comm_local_group_destroy.argtypes = [C.c_void_p]
+        L.ahfgpu_comm_local_group_abort.argtypes = [C.c_void_p]
+        L.ahfgpu_comm_init_local.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.ahfgpu_slab_distribute.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_int32]
+        L.ahfgpu_slab_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ahfgpu_slab_owner_of.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.ahfgpu_amr_level_owned.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.ahfgpu_particle_ids.argtypes = [C.c_void_p, C.c_void_p]
         L.ahfgpu_adopt_sorted.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_int32]
         L.ahfgpu_sfc_sort_device4.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_int32]
         L.ahfgpu_hilbert_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
@@ -161,6 +172,28 @@ def lib():
         L.ahfgpu_stage_count.argtypes = [C.c_void_p, C.c_char_p]
         _lib = L
     return _lib
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    if lib().ahfgpu_comm_nccl_unique_id(buf) != 0:
+        raise AhfGpuError(lib().ahfgpu_last_error().decode())
+    return buf.raw
+
+
+def local_group_create(nranks: int) -> int:
+    g = lib().ahfgpu_comm_local_group_create(nranks)
+    if not g:
+        raise AhfGpuError("could not create a local group")
+    return int(g)
+
+
+def local_group_abort(group: int) -> None:
+    lib().ahfgpu_comm_local_group_abort(C.c_void_p(group))
+
+
+def local_group_destroy(group: int) -> None:
+    lib().ahfgpu_comm_local_group_destroy(C.c_void_p(group))
 
 
 def exported_symbols() -> list[str]:
@@ -287,6 +320,45 @@ class AhfGpu:
         self._chk(self._L.ahfgpu_sfc_sort_particles(self._h, _p(part), n, stride, off_pos, off_mom, off_key, off_id,
                                                     off_weight, off_u))
         self.n = n
+
+    # ---- ONE box on several GPUs (include/ahfgpu.h "several GPUs working on ONE box") -----------
+    def comm_init_nccl(self, rank: int, nranks: int, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._chk(self._L.ahfgpu_comm_init_nccl(self._h, rank, nranks, buf))
+
+    def comm_init_local(self, rank: int, group: int):
+        self._chk(self._L.ahfgpu_comm_init_local(self._h, rank, C.c_void_p(group)))
+
+    def slab_distribute(self, id_base: int, ghost_width: float = 0.0, decomp_bits: int = 0):
+        """keys + block histogram + equal-particle Hilbert ranges + ONE exchange (owner and ghost holders) + ONE sort of the particles
+        uploaded with upload(); afterwards the context holds its key range plus the ghost shell"""
+        self._chk(self._L.ahfgpu_slab_distribute(self._h, id_base, ghost_width, decomp_bits))
+        self.n = int(self.slab_info()["resident"])
+
+    def slab_info(self) -> dict:
+        io = np.zeros(12, np.int64); do = np.zeros(4, np.float64)
+        self._chk(self._L.ahfgpu_slab_info(self._h, _p(io), _p(do)))
+        keys = ("rank", "nranks", "resident", "own_lo", "own_hi", "n_total", "decomp_bits", "shell_blocks", "block_lo", "block_hi", "levels", "coll_calls")
+        out = {k: int(v) for k, v in zip(keys, io)}
+        out.update(ghost_width=float(do[0]), coll_ms=float(do[1]), coll_bytes=float(do[2]))
+        return out
+
+    def slab_owner_of(self, pos: np.ndarray) -> np.ndarray:
+        pos = np.ascontiguousarray(pos, np.float64).reshape(-1, 3)
+        owner = np.empty(pos.shape[0], np.int32)
+        self._chk(self._L.ahfgpu_slab_owner_of(self._h, pos.shape[0], _p(pos), _p(owner)))
+        return owner
+
+    def level_owned(self, lev: int) -> np.ndarray:
+        nc = int(self.level_header(lev)[0][1])
+        owned = np.empty(nc, np.uint8)
+        self._chk(self._L.ahfgpu_amr_level_owned(self._h, lev, _p(owned)))
+        return owned.astype(bool)
+
+    def particle_ids(self) -> np.ndarray:
+        ids = np.empty(self.n, np.uint32)
+        self._chk(self._L.ahfgpu_particle_ids(self._h, _p(ids)))
+        return ids
 
     # ---- D / F / R / L -------------------------------------------------------------------------
     def build_amr(self) -> int:

@@ -1,5 +1,7 @@
 // api.cu -- extern "C" entry points of libahfgpu.so (see include/ahfgpu.h) and context housekeeping.
 #include "common.cuh"
+#include "comm.cuh"
+#include "hilbert.cuh"
 #include <mutex>
 #include <unordered_map>
 
@@ -68,7 +70,7 @@ void cache_release_all()
 void Level::free_all()
 {
   ahf::dfree(ckey); ahf::dfree(xbreak); ahf::dfree(dens); ahf::dfree(interior); ahf::dfree(tn); ahf::dfree(mark); ahf::dfree(nbr);
-  ahf::dfree(crow); ahf::dfree(count); ahf::dfree(hkey); ahf::dfree(hval); ahf::dfree(rowkey); ahf::dfree(row_c0); ahf::dfree(row_tested);
+  ahf::dfree(crow); ahf::dfree(count); ahf::dfree(hkey); ahf::dfree(hval); ahf::dfree(rowkey); ahf::dfree(row_c0); ahf::dfree(row_tested); ahf::dfree(row_flags);
   ahf::dfree(plane_r0); ahf::dfree(rowplane); ahf::dfree(plist); ahf::dfree(pcell); ahf::dfree(lpos);
   ahf::dfree(parent); ahf::dfree(cidx); ahf::dfree(cbase); ahf::dfree(cpar);
   *this = Level();
@@ -201,6 +203,8 @@ int ahfgpu_finalize(ahfgpu_ctx *c)
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   cudaStreamSynchronize(c->stream);
   c->stage_reset(); c->free_halos(); c->free_levels(); c->free_particles();
+  slab_free(c);
+  if (c->comm) { delete c->comm; c->comm = nullptr; }
   ahf::dfree(c->in_pos); ahf::dfree(c->in_mom); ahf::dfree(c->in_w); ahf::dfree(c->in_u);
   ahf::dfree(c->scan_state); c->scan_state = nullptr; c->scan_cap = 0;
   if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -298,11 +302,103 @@ int ahfgpu_set_global_count(ahfgpu_ctx *c, uint64_t n_total)
   API_END
 }
 
-int ahfgpu_set_allreduce(ahfgpu_ctx *c, ahfgpu_allreduce_fn fn, void *user)
+// ---- ONE box on several GPUs (comm.cuh, slab.cu) ----------------------------------------------------------------------------------
+int ahfgpu_comm_nccl_unique_id(void *id128)
+{
+  API_BEGIN
+  if (!id128) AHF_FAIL("null argument");
+  comm_nccl_unique_id(id128);
+  API_END
+}
+
+int ahfgpu_comm_init_nccl(ahfgpu_ctx *c, int32_t rank, int32_t nranks, const void *id128)
+{
+  API_BEGIN
+  if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) AHF_FAIL("bad argument");
+  CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
+  if (c->comm) { delete c->comm; c->comm = nullptr; }
+  c->comm = comm_create_nccl(rank, nranks, id128, c->dev);
+  API_END
+}
+
+void *ahfgpu_comm_local_group_create(int32_t nranks)
+{
+  try { if (nranks < 1) return nullptr; return comm_local_group_create(nranks); } catch (...) { return nullptr; }
+}
+
+int ahfgpu_comm_local_group_destroy(void *group)
+{
+  API_BEGIN
+  comm_local_group_destroy(group);
+  API_END
+}
+
+int ahfgpu_comm_local_group_abort(void *group)
+{
+  API_BEGIN
+  comm_local_group_abort(group);
+  API_END
+}
+
+int ahfgpu_comm_init_local(ahfgpu_ctx *c, int32_t rank, void *group)
+{
+  API_BEGIN
+  if (!c || !group) AHF_FAIL("bad argument");
+  if (c->comm) { delete c->comm; c->comm = nullptr; }
+  c->comm = comm_create_local(rank, group);
+  API_END
+}
+
+int ahfgpu_slab_distribute(ahfgpu_ctx *c, uint64_t id_base, double ghost_width, int32_t decomp_bits)
 {
   API_BEGIN
   if (!c) AHF_FAIL("null ctx");
-  c->allreduce = fn; c->allreduce_user = user;
+  CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
+  c->stage_reset();
+  slab_distribute(c, id_base, ghost_width, decomp_bits);
+  API_END
+}
+
+int ahfgpu_slab_info(ahfgpu_ctx *c, int64_t *iout, double *dout)
+{
+  API_BEGIN
+  if (!c || !c->slab || !c->comm) AHF_FAIL("the resident particles are not a slab of a distributed box");
+  const Slab &S = *c->slab;
+  if (iout) {
+    iout[0] = c->comm->rank; iout[1] = c->comm->nranks; iout[2] = (int64_t)c->n; iout[3] = (int64_t)S.own_lo; iout[4] = (int64_t)S.own_hi;
+    iout[5] = (int64_t)S.n_total; iout[6] = S.bd; iout[7] = S.T; iout[8] = (int64_t)S.split[c->comm->rank]; iout[9] = (int64_t)S.split[c->comm->rank + 1];
+    iout[10] = c->g_nlevels; iout[11] = c->comm->coll_calls;
+  }
+  if (dout) { dout[0] = S.ghost_width; dout[1] = c->comm->coll_ms; dout[2] = (double)c->comm->coll_bytes; dout[3] = 0.0; }
+  API_END
+}
+
+int ahfgpu_slab_owner_of(ahfgpu_ctx *c, int64_t n, const double *pos3, int32_t *owner)
+{
+  API_BEGIN
+  if (!c || !c->slab || !c->comm) AHF_FAIL("the resident particles are not a slab of a distributed box");
+  if (n && (!pos3 || !owner)) AHF_FAIL("null argument");
+  const Slab &S = *c->slab;
+  const int R = c->comm->nranks;
+  for (int64_t i = 0; i < n; i++) {
+    double q[3];
+    for (int d = 0; d < 3; d++) { q[d] = pos3[3 * i + d]; q[d] -= std::floor(q[d]); if (q[d] >= 1.0) q[d] = 0.0; }
+    const uint64_t h = hilbert_key_posd(q[0], q[1], q[2], (unsigned)S.bd);
+    int r = 0;
+    while (r + 1 < R && S.split[r + 1] <= h) r++;
+    owner[i] = r;
+  }
+  API_END
+}
+
+int ahfgpu_particle_ids(ahfgpu_ctx *c, uint32_t *ids)
+{
+  API_BEGIN
+  if (!c || !c->order) AHF_FAIL("no resident particle index (order) array");
+  if (!ids && c->n) AHF_FAIL("null argument");
+  CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (c->n) CUDA_CHECK(cudaMemcpy(ids, c->order, sizeof(uint32_t) * c->n, cudaMemcpyDeviceToHost));
   API_END
 }
 

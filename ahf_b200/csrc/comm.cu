@@ -39,14 +39,23 @@ struct CollTimer {           // CUDA events on the context's stream around one d
 struct LocalGroup {
   int n = 0;
   std::mutex mu; std::condition_variable cv; int arrived = 0; uint64_t gen = 0;
+  bool aborted = false;            // a rank failed: the others must not wait for it for ever
   struct Slot { const void *a = nullptr; const void *b = nullptr; const void *c = nullptr; };
   std::vector<Slot> slot;
   void barrier()
   {
     std::unique_lock<std::mutex> lk(mu);
+    if (aborted) AHF_FAIL("local group aborted (another rank failed)");
     const uint64_t g = gen;
     if (++arrived == n) { arrived = 0; gen++; cv.notify_all(); }
-    else cv.wait(lk, [&] { return gen != g; });
+    else cv.wait(lk, [&] { return gen != g || aborted; });
+    if (aborted) AHF_FAIL("local group aborted (another rank failed)");
+  }
+  void abort()
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    aborted = true;
+    cv.notify_all();
   }
 };
 
@@ -243,6 +252,7 @@ void *comm_local_group_create(int nranks)
   return g;
 }
 void comm_local_group_destroy(void *group) { delete static_cast<LocalGroup *>(group); }
+void comm_local_group_abort(void *group) { if (group) static_cast<LocalGroup *>(group)->abort(); }
 Comm *comm_create_local(int rank, void *group)
 {
   LocalGroup *g = static_cast<LocalGroup *>(group);

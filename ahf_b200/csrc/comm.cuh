@@ -45,6 +45,7 @@ Comm *comm_create_nccl(int rank, int nranks, const void *id128, int device);
 void  comm_nccl_unique_id(void *id128);
 void *comm_local_group_create(int nranks);
 void  comm_local_group_destroy(void *group);
+void  comm_local_group_abort(void *group);
 Comm *comm_create_local(int rank, void *group);
 
 void slab_distribute(ahfgpu_ctx *c, uint64_t id_base, double ghost_width, int decomp_bits);

@@ -89,16 +89,23 @@ struct Level {
   uint64_t *rowkey = nullptr;   // [nrow] z*L+y
   int32_t  *row_c0 = nullptr;   // [nrow+1]
   uint8_t  *row_tested = nullptr;
+  uint8_t  *row_flags = nullptr;  // [nrow] bit 2/3 first/last row of its y-run (cquad), bit 4/5 first/last plane of its z-run (pquad)
   int32_t  *plane_r0 = nullptr; // [nplane+1]
   int32_t  *rowplane = nullptr; // [nrow]
   double   critdens = 0, masstopartdens = 0;
   int64_t  npart_dep = 0, npart_final = 0;
+  // the same counts over the WHOLE box when the box is split over several contexts (slab.cu; equal to the local ones otherwise): kernel
+  // and fixed-point scale of the deposit are chosen from these, so that every rank rounds every term exactly as one GPU would
+  int64_t  g_ncell = 0, g_npart_dep = 0;
   // particles that reached this level (ascending sorted offsets) and their cell on this level
   uint32_t *plist = nullptr;    // [npart_dep]   (nullptr on the domain level = all particles)
   int32_t  *pcell = nullptr;    // [npart_dep]
   float4   *lpos = nullptr;     // [npart_dep] positions of the level's particles, contiguous (refinement levels)
   void free_all();
 };
+
+struct Comm;     // comm.cuh
+struct Slab;
 
 struct StageRec { std::string name; cudaEvent_t a, b; int64_t count; };
 
@@ -138,7 +145,9 @@ struct ahfgpu_ctx {
   bool      has_weight = false, has_u = false;
   bool      adopted = false;          // pos4/mom4/keys belong to the caller (ahfgpu_adopt_sorted)
   uint64_t  n_total = 0;              // particles of the whole box when the box is split over several contexts (0: n)
-  ahfgpu_allreduce_fn allreduce = nullptr; void *allreduce_user = nullptr;
+  ahf::Comm *comm = nullptr;          // several contexts working on ONE box (comm.cuh); owned by the context
+  ahf::Slab *slab = nullptr;          // decomposition of the resident set (slab.cu): owned range + ghost shell
+  int        g_nlevels = 0;           // levels of the whole box (a rank whose cells end earlier holds fewer)
   // unsorted device copy kept by ahfgpu_upload_soa
   float    *in_pos = nullptr, *in_mom = nullptr, *in_w = nullptr, *in_u = nullptr;
   uint64_t  in_n = 0;

@@ -2344,7 +2344,8 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
              c->h_scal, c->h_poff, c->h_prof, d_soff, d_scratch);
     else
       profiles_cooperative(c, nhalo, P, d_ctr, d_moff0, d_members, tot_g, d_np, h_np);
-    LAUNCH(c, k_members_out, (unsigned)nhalo, 256, 0, d_moff0, d_np, c->h_moff, d_members, d_gid, c->h_members);
+    // a slab of a distributed box reports GLOBAL INPUT INDICES (the resident `order` array), not offsets into its own sorted set
+    LAUNCH(c, k_members_out, (unsigned)nhalo, 256, 0, d_moff0, d_np, c->h_moff, d_members, d_gid ? d_gid : (c->slab ? c->order : (uint32_t *)nullptr), c->h_members);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
   }
   ahf::dfree(d_ctr); ahf::dfree(d_rad); ahf::dfree(d_seed); ahf::dfree(d_rlo); ahf::dfree(d_rhi); ahf::dfree(d_cand); ahf::dfree(d_candoff); ahf::dfree(d_ng);

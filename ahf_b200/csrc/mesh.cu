@@ -10,6 +10,7 @@
 #include "scan.cuh"
 #include "patches.cuh"
 #include "hilbert.cuh"
+#include "comm.cuh"
 
 namespace ahf {
 
@@ -984,7 +985,8 @@ __global__ void k_plane_runs(const int32_t *__restrict__ pz, int nplane, int32_t
 
 __global__ void k_row_tested(const uint64_t *__restrict__ rowkey, const int32_t *__restrict__ plane_r0, const int32_t *__restrict__ rowplane,
                              const int32_t *__restrict__ rq0, const int32_t *__restrict__ rq1, const int32_t *__restrict__ pp0,
-                             const int32_t *__restrict__ pp1, int nrow, int nplane, long long L, int logL, uint8_t *__restrict__ row_tested)
+                             const int32_t *__restrict__ pp1, int nrow, int nplane, long long L, int logL, uint8_t *__restrict__ row_tested,
+                             uint8_t *__restrict__ row_flags)
 {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nrow) return;
@@ -1005,6 +1007,8 @@ __global__ void k_row_tested(const uint64_t *__restrict__ rowkey, const int32_t 
   run_offsets(ywrapped, y0, y1, L, low, up);
   bool ty = tested_idx(r - q0, low, up, q1 - q0, (q1 == plane_r0[P + 1]) && (y1 == L));
   row_tested[r] = (tz && ty) ? 1 : 0;
+  // first / last row of its cquad, first / last plane of its pquad (the run flags the query API exports)
+  row_flags[r] = (uint8_t)((r == q0 ? 4 : 0) | (r == q1 - 1 ? 8 : 0) | (P == a ? 16 : 0) | (P == b - 1 ? 32 : 0));
 }
 
 __global__ void k_mark_sparse(LV v, const uint8_t *__restrict__ tn, const uint8_t *__restrict__ interior, const int32_t *__restrict__ crow,
@@ -1474,9 +1478,36 @@ __global__ void k_count_marked(LV v, const int *__restrict__ S, const int *__res
   if ((threadIdx.x & 31) == 0) { if (br) atomicAdd(&out[0], __popc(br)); if (bp) atomicAdd(&out[1], __popc(bp)); }
 }
 
+// plane tables, run bounds, tested flag and run flags of a sorted list of row keys (z * L + y).  nplane < 0: counted here (one
+// read-back).  The list is the level's own rows on one GPU, and the rows of ALL ranks when the box is split (the reference's run
+// structure is not local: whether a row / plane is tested depends on rows and planes arbitrarily far away, refine_grid.c:346-405,
+// :645-703).
+static void rows_tested_flags(ahfgpu_ctx *c, const uint64_t *rowkey, int64_t nrow, int64_t nplane, long long L, int logL, uint8_t *tested, uint8_t *flags,
+                              int32_t **rowplane_out, int32_t **plane_r0_out)
+{
+  DevBuf<uint8_t> head; DevBuf<int> hs, bs;
+  head.reserve(nrow); hs.reserve(nrow);
+  LAUNCH(c, k_plane_heads, nblk(nrow, 256), 256, 0, rowkey, (int)nrow, logL, head.p);
+  if (nplane < 0) nplane = exclusive_scan<uint8_t>(c, head.p, hs.p, nrow);
+  else exclusive_scan_async<uint8_t>(c, head.p, hs.p, nrow, nullptr, bs);
+  int32_t *rowplane = dalloc<int32_t>(nrow), *plane_r0 = dalloc<int32_t>(nplane + 1);
+  LAUNCH(c, k_plane_fill, nblk(nrow, 256), 256, 0, (int)nrow, head.p, hs.p, rowplane, plane_r0, (int)nplane);
+  int32_t *rq0 = dalloc<int32_t>(nrow), *rq1 = dalloc<int32_t>(nrow), *pp0 = dalloc<int32_t>(nplane), *pp1 = dalloc<int32_t>(nplane);
+  LAUNCH(c, k_row_runs, nblk(nrow, 256), 256, 0, rowkey, plane_r0, rowplane, (int)nrow, rq0, rq1);
+  int32_t *pz = dalloc<int32_t>(nplane);
+  LAUNCH(c, k_plane_z, nblk(nplane, 128), 128, 0, rowkey, plane_r0, (int)nplane, logL, pz);
+  LAUNCH(c, k_plane_runs, nblk(nplane, 128), 128, 0, pz, (int)nplane, pp0, pp1);
+  LAUNCH(c, k_row_tested, nblk(nrow, 256), 256, 0, rowkey, plane_r0, rowplane, rq0, rq1, pp0, pp1, (int)nrow, (int)nplane, L, logL, tested, flags);
+  ahf::dfree(rq0); ahf::dfree(rq1); ahf::dfree(pp0); ahf::dfree(pp1); ahf::dfree(pz);      // stream-ordered block cache: no host sync needed
+  head.release(); hs.release(); bs.release();
+  if (rowplane_out) *rowplane_out = rowplane; else ahf::dfree(rowplane);
+  if (plane_r0_out) *plane_r0_out = plane_r0; else ahf::dfree(plane_r0);
+}
+
 // lv.nrow / lv.nplane are known before the level exists (4 rows per marked coarse row, 2 planes per marked coarse plane: counted
-// next to the prefix sum over the marks and read back with it), so nothing here waits for the device
-static void build_rows_planes(ahfgpu_ctx *c, Level &lv)
+// next to the prefix sum over the marks and read back with it), so nothing here waits for the device.
+// local_only: only the level's own index tables (crow, rowkey, row_c0); the tested flags follow from the rows of all ranks
+static void build_rows_planes(ahfgpu_ctx *c, Level &lv, bool with_tested)
 {
   LV v = view(lv);
   const int nc = (int)lv.ncell;
@@ -1486,24 +1517,132 @@ static void build_rows_planes(ahfgpu_ctx *c, Level &lv)
   exclusive_scan_async<uint8_t>(c, head.p, hs.p, nc, nullptr, bs);
   lv.crow = dalloc<int32_t>(nc); lv.rowkey = dalloc<uint64_t>(lv.nrow); lv.row_c0 = dalloc<int32_t>(lv.nrow + 1);
   LAUNCH(c, k_row_fill, nblk(nc, 256), 256, 0, lv.ckey, nc, v.logL, head.p, hs.p, lv.crow, lv.rowkey, lv.row_c0, (int)lv.nrow);
-  head.reserve(lv.nrow); hs.reserve(lv.nrow);
-  LAUNCH(c, k_plane_heads, nblk(lv.nrow, 256), 256, 0, lv.rowkey, (int)lv.nrow, v.logL, head.p);
-  exclusive_scan_async<uint8_t>(c, head.p, hs.p, lv.nrow, nullptr, bs);
-  int32_t *rowplane = dalloc<int32_t>(lv.nrow);
-  lv.plane_r0 = dalloc<int32_t>(lv.nplane + 1);
-  LAUNCH(c, k_plane_fill, nblk(lv.nrow, 256), 256, 0, (int)lv.nrow, head.p, hs.p, rowplane, lv.plane_r0, (int)lv.nplane);
-  // run bounds + tested rows
-  int32_t *rq0 = dalloc<int32_t>(lv.nrow), *rq1 = dalloc<int32_t>(lv.nrow), *pp0 = dalloc<int32_t>(lv.nplane), *pp1 = dalloc<int32_t>(lv.nplane);
-  LAUNCH(c, k_row_runs, nblk(lv.nrow, 256), 256, 0, lv.rowkey, lv.plane_r0, rowplane, (int)lv.nrow, rq0, rq1);
-  int32_t *pz = dalloc<int32_t>(lv.nplane);
-  LAUNCH(c, k_plane_z, nblk(lv.nplane, 128), 128, 0, lv.rowkey, lv.plane_r0, (int)lv.nplane, v.logL, pz);
-  LAUNCH(c, k_plane_runs, nblk(lv.nplane, 128), 128, 0, pz, (int)lv.nplane, pp0, pp1);
-  lv.row_tested = dalloc<uint8_t>(lv.nrow);
-  LAUNCH(c, k_row_tested, nblk(lv.nrow, 256), 256, 0, lv.rowkey, lv.plane_r0, rowplane, rq0, rq1, pp0, pp1, (int)lv.nrow, (int)lv.nplane,
-         (long long)lv.L, v.logL, lv.row_tested);
-  ahf::dfree(rq0); ahf::dfree(rq1); ahf::dfree(pp0); ahf::dfree(pp1); ahf::dfree(pz);      // stream-ordered block cache: no host sync needed
   head.release(); hs.release(); bs.release();
-  lv.rowplane = rowplane;
+  lv.row_tested = dalloc<uint8_t>(lv.nrow); lv.row_flags = dalloc<uint8_t>(lv.nrow);
+  if (with_tested) rows_tested_flags(c, lv.rowkey, lv.nrow, lv.nplane, (long long)lv.L, v.logL, lv.row_tested, lv.row_flags, &lv.rowplane, &lv.plane_r0);
+  else {
+    // the plane index tables of the level's own rows are still needed (child order of the next level); tested / flags are set later
+    DevBuf<uint8_t> t2, f2;
+    t2.reserve(lv.nrow); f2.reserve(lv.nrow);
+    rows_tested_flags(c, lv.rowkey, lv.nrow, lv.nplane, (long long)lv.L, v.logL, t2.p, f2.p, &lv.rowplane, &lv.plane_r0);
+    t2.release(); f2.release();
+  }
+}
+
+// ---- ONE box on several ranks: which cells / rows / moved particles belong to the rank's own key range
+__device__ __forceinline__ bool cell_owned(const LV &v, int c, const uint8_t *__restrict__ own3, int bd, int rank)
+{
+  int x, y, z; lv_coords(v, c, x, y, z);
+  const int s = v.logL - bd;
+  return own3[((((size_t)(z >> s)) << bd) | (size_t)(y >> s)) << bd | (size_t)(x >> s)] == (uint8_t)rank;
+}
+__global__ void k_owned_cells(LV v, const uint8_t *__restrict__ own3, int bd, int rank, uint8_t *__restrict__ owned)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < v.ncell) owned[c] = cell_owned(v, c, own3, bd, rank) ? 1 : 0;
+}
+__global__ void k_count_owned_marked(LV v, const uint8_t *__restrict__ mark, const uint8_t *__restrict__ own3, int bd, int rank, int *__restrict__ out)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool hit = c < v.ncell && mark[c] && cell_owned(v, c, own3, bd, rank);
+  const unsigned b = __ballot_sync(0xffffffffu, hit);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, __popc(b));
+}
+__global__ void k_rows_owned(LV v, const int32_t *__restrict__ crow, const uint8_t *__restrict__ own3, int bd, int rank, uint8_t *__restrict__ rowown)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < v.ncell && cell_owned(v, c, own3, bd, rank)) rowown[crow[c]] = 1;
+}
+__global__ void k_compact_rows(const uint64_t *__restrict__ rowkey, const uint8_t *__restrict__ rowown, const int *__restrict__ pos, int nrow, uint64_t *__restrict__ out)
+{
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < nrow && rowown[r]) out[pos[r]] = rowkey[r];
+}
+__global__ void k_count_owned_moved(const uint32_t *__restrict__ plist, const uint8_t *__restrict__ moved, uint64_t np, uint32_t own_lo, uint32_t own_hi, int *__restrict__ out)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  bool hit = false;
+  if (i < np && moved[i]) { const uint32_t p = plist ? plist[i] : (uint32_t)i; hit = p >= own_lo && p < own_hi; }
+  const unsigned b = __ballot_sync(0xffffffffu, hit);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, __popc(b));
+}
+__global__ void k_unique_heads(const uint64_t *__restrict__ k, uint64_t n, uint8_t *__restrict__ head)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) head[i] = (i == 0 || k[i] != k[i - 1]) ? 1 : 0;
+}
+__global__ void k_unique_fill(const uint64_t *__restrict__ k, uint64_t n, const uint8_t *__restrict__ head, const int *__restrict__ pos, uint64_t *__restrict__ out)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n && head[i]) out[pos[i]] = k[i];
+}
+// tested flag / run flags of the level's own rows from the table of ALL rows (rows nobody owns exist only in the rank's ghost fringe)
+__global__ void k_map_rows(const uint64_t *__restrict__ rowkey, int nrow, const uint64_t *__restrict__ grow, int ng, const uint8_t *__restrict__ gtested,
+                           const uint8_t *__restrict__ gflags, uint8_t *__restrict__ tested, uint8_t *__restrict__ flags)
+{
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrow) return;
+  const uint64_t k = rowkey[r];
+  int lo = 0, hi = ng;
+  while (lo < hi) { const int mid = lo + ((hi - lo) >> 1); if (grow[mid] < k) lo = mid + 1; else hi = mid; }
+  const bool found = lo < ng && grow[lo] == k;
+  tested[r] = found ? gtested[lo] : 0;
+  flags[r] = found ? gflags[lo] : 0;
+}
+
+// the rows of a level that hold at least one cell of the rank's own key range: compacted keys (device, caller frees) and their number
+static int64_t owned_rows(ahfgpu_ctx *c, Level &lv, uint64_t **send_out)
+{
+  Comm *cm = c->comm; Slab *S = c->slab;
+  DevBuf<uint8_t> ro; DevBuf<int> pos, bs, tot;
+  ro.reserve(lv.nrow); pos.reserve(lv.nrow); tot.reserve(1);
+  CUDA_CHECK(cudaMemsetAsync(ro.p, 0, lv.nrow, c->stream));
+  CUDA_CHECK(cudaMemsetAsync(tot.p, 0, sizeof(int), c->stream));
+  LAUNCH(c, k_rows_owned, nblk(lv.ncell, 256), 256, 0, view(lv), lv.crow, S->own3, S->bd, cm->rank, ro.p);
+  exclusive_scan_async<uint8_t>(c, ro.p, pos.p, lv.nrow, tot.p, bs);
+  uint64_t *send = dalloc<uint64_t>(lv.nrow);
+  LAUNCH(c, k_compact_rows, nblk(lv.nrow, 256), 256, 0, lv.rowkey, ro.p, pos.p, (int)lv.nrow, send);
+  int h = 0;
+  read_back(c, &h, tot.p, sizeof(int));
+  ro.release(); pos.release(); bs.release(); tot.release();
+  *send_out = send;
+  return h;
+}
+
+// rows of all ranks -> tested / run flags of this rank's rows.  Every rank contributes the rows that hold at least one of ITS cells
+// (`send`, nrows_rank[rank] keys); lv == nullptr: the rank has no cells on this level and only takes part in the exchange.
+static void rows_from_all_ranks(ahfgpu_ctx *c, Level *lv, const uint64_t *send, const std::vector<int64_t> &nrows_rank, long long L, int logL)
+{
+  Comm *cm = c->comm;
+  const int R = cm->nranks;
+  std::vector<size_t> bytes(R), off(R + 1, 0);
+  for (int p = 0; p < R; p++) { bytes[p] = (size_t)nrows_rank[p] * 8; off[p + 1] = off[p] + bytes[p]; }
+  const int64_t nall = (int64_t)(off[R] / 8);
+  uint64_t *all = dalloc<uint64_t>(nall);
+  {
+    Stage st(c, "rows_allgather", (int64_t)nall * 8, c->env.stages);
+    cm->allgatherv(c, send, all, bytes.data(), off.data());
+  }
+  if (lv && lv->nrow > 0) {
+    if (nall == 0) AHF_FAIL("a level without rows on any rank");
+    // sort + unique (every row key is 2 logL bits)
+    uint64_t *k1 = dalloc<uint64_t>(nall); uint32_t *v0 = dalloc<uint32_t>(nall), *v1 = dalloc<uint32_t>(nall);
+    uint64_t *ks; uint32_t *vs;
+    int kb = 2 * logL; kb = ((kb + 7) / 8) * 8;
+    radix_sort_pairs(c, all, v0, k1, v1, (uint64_t)nall, kb, &ks, &vs);
+    DevBuf<uint8_t> head; DevBuf<int> pos;
+    head.reserve(nall); pos.reserve(nall);
+    LAUNCH(c, k_unique_heads, nblk(nall, 256), 256, 0, ks, (uint64_t)nall, head.p);
+    const int ng = exclusive_scan<uint8_t>(c, head.p, pos.p, (uint64_t)nall);
+    uint64_t *grow = dalloc<uint64_t>(ng);
+    LAUNCH(c, k_unique_fill, nblk(nall, 256), 256, 0, ks, (uint64_t)nall, head.p, pos.p, grow);
+    uint8_t *gt = dalloc<uint8_t>(ng), *gf = dalloc<uint8_t>(ng);
+    rows_tested_flags(c, grow, ng, -1, L, logL, gt, gf, nullptr, nullptr);
+    LAUNCH(c, k_map_rows, nblk(lv->nrow, 256), 256, 0, lv->rowkey, (int)lv->nrow, grow, ng, gt, gf, lv->row_tested, lv->row_flags);
+    head.release(); pos.release();
+    ahf::dfree(k1); ahf::dfree(v0); ahf::dfree(v1); ahf::dfree(grow); ahf::dfree(gt); ahf::dfree(gf);
+  }
+  ahf::dfree(all);
 }
 
 static std::string lvl_name(const char *base, int lev) { char b[48]; snprintf(b, sizeof(b), "%s_L%d", base, lev); return b; }
@@ -1541,11 +1680,12 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
   CUDA_CHECK(cudaMemsetAsync(acc.p, 0, sizeof(unsigned long long) * nc, c->stream));
   const bool generic_only = c->env.generic_deposit;
   const bool dom_v1       = c->env.deposit_v1;           // previous float-weight domain kernel (A/B timing)
-  const bool tiles_dense  = lv.dense && lv.L >= 2 * DT_T && lv.npart_dep > 0 && !generic_only;
+  // choice of kernel and fixed-point scale from the counts of the WHOLE box (g_*): every rank of a split box rounds like one GPU
+  const bool tiles_dense  = lv.dense && lv.L >= 2 * DT_T && lv.g_npart_dep > 0 && !generic_only;
   const int    S = (tiles_dense && !dom_v1) ? 32 : fx_shift_for(lv.masstopartdens);    // k_deposit_dom works in 2^-32 units
   const double fxscale = (double)(1ull << S);
-  const bool tiles_sparse = !lv.dense && lv.lpos && lv.npart_dep >= 2048 && v.logL - 4 <= 20 && !generic_only;
-  if (tiles_dense || tiles_sparse) {
+  const bool tiles_sparse = !lv.dense && lv.lpos && lv.g_npart_dep >= 2048 && v.logL - 4 <= 20 && !generic_only;
+  if ((tiles_dense || tiles_sparse) && lv.npart_dep > 0) {
     // tiles are Hilbert cells of (logL - 4) bits per dimension: contiguous ranges of the (level's) particle list
     const int tbits = v.logL - 4;
     int ntile = 0;
@@ -1597,7 +1737,7 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
       else if (tiles_dense)
         LAUNCH(c, k_deposit_tiles<false>, (unsigned)W, DT_THREADS, DT_SMEM, c->pos4, tstart.p, work.p, (int)lv.L, v.logL, tbits, acc.p,
                (const uint32_t *)nullptr, (const int32_t *)nullptr, v, (const int32_t *)nullptr, (float)fxscale, tot.p);
-      else if (c->env.sparse_v1 || (!c->env.sparse_v2 && (double)lv.npart_dep < 0.75 * (double)lv.ncell))
+      else if (c->env.sparse_v1 || (!c->env.sparse_v2 && (double)lv.g_npart_dep < 0.75 * (double)lv.g_ncell))
         // lane per particle: the thin tiles of the deepest levels (well under one particle per cell, a few hundred particles per
         // tile) have no runs to aggregate and want the larger CTA for the tile flush (measured: 0.23 vs 0.31 ms on level 6)
         LAUNCH(c, k_deposit_tiles<true>, (unsigned)W, DT_THREADS, DT_SMEM, lv.lpos, tstart.p, work.p, (int)lv.L, v.logL, tbits, acc.p,
@@ -1608,15 +1748,9 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
     }
     if (lv.dense) c->stage_cnt_extra["deposit_dom_ctas"] = W;
     tstart.release(); nchunk.release(); woff.release(); bs.release(); tot.release(); work.release(); work4.release(); tlist.release(); head.release(); hs.release();
-  } else if (lv.npart_dep > 0) {
+  } else if (lv.npart_dep > 0 && !(tiles_dense || tiles_sparse)) {
     Stage sk(c, lv.dense ? "deposit_dom_kernel" : "deposit_ref_kernel", lv.npart_dep, lv.dense || c->env.stages);
     LAUNCH(c, k_deposit_generic, nblk(lv.npart_dep, 256), 256, 0, c->pos4, lv.plist, lv.pcell, (uint64_t)lv.npart_dep, v, lv.nbr, acc.p, fxscale);
-  }
-  if (c->allreduce) {
-    // several contexts share one box: sum the level's accumulators over all of them (exact: integers)
-    Stage sa(c, "allreduce", (int64_t)nc * 8, c->env.stages);
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    if (c->allreduce(c->allreduce_user, acc.p, (int64_t)nc) != 0) AHF_FAIL("all-reduce callback failed");
   }
   LAUNCH(c, k_finish_dens, nblk(nc, 256), 256, 0, acc.p, lv.dens, nc, lv.masstopartdens / fxscale);
   acc.release();                                    // stream-ordered block cache: no host sync needed
@@ -1639,6 +1773,14 @@ void amr_build(ahfgpu_ctx *c)
   long long lmax = par.lgrid_max;
   if (lmax > (1 << 21) || lmax <= 0) lmax = (1 << 21);
   if (par.lgrid_dom > 1024) AHF_FAIL("dense domain grids above 1024^3 need 64-bit cell indices (not in this round)");
+  // ONE box split over several contexts (slab.cu): the resident set is the rank's key range plus a ghost shell wide enough that every
+  // level is exact on the rank's own cells; what is NOT local -- does any rank still refine, is the next level large enough, how many
+  // particles deposit on it, which rows / planes exist -- is exchanged once per level (one small all-gather, one all-gather of row keys)
+  Comm *cm = c->comm; Slab *S = c->slab;
+  const bool split = cm != nullptr && S != nullptr;
+  const int  R = split ? cm->nranks : 1;
+  if (cm && !S) AHF_FAIL("a communicator is attached but the particles were not distributed: call ahfgpu_slab_distribute");
+  const uint64_t n_box = c->n_total ? c->n_total : n;
   c->owner_level = dalloc<int8_t>(n);
   CUDA_CHECK(cudaMemsetAsync(c->owner_level, 0, n, c->stream));
 
@@ -1646,10 +1788,11 @@ void amr_build(ahfgpu_ctx *c)
   {
     Level d;
     d.L = par.lgrid_dom; d.ncell = d.L * d.L * d.L; d.dense = true;
-    d.masstopartdens = ((double)d.L * (double)d.L * (double)d.L) / (double)(c->n_total ? c->n_total : n);
+    d.masstopartdens = ((double)d.L * (double)d.L * (double)d.L) / (double)n_box;
     d.critdens = par.nth_dom * d.masstopartdens;
     alloc_cell_arrays(d);
     d.npart_dep = (int64_t)n;
+    d.g_ncell = d.ncell; d.g_npart_dep = (int64_t)n_box;
     d.pcell = dalloc<int32_t>(n);
     {
       Stage st(c, "ll", (int64_t)n, c->env.stages);
@@ -1658,44 +1801,57 @@ void amr_build(ahfgpu_ctx *c)
     }
     c->levels.push_back(d);
   }
+  bool      active = true;                 // this rank still has cells on the current level
+  long long curL = par.lgrid_dom;
+  int       glev = 0;                      // index of the current level in the box-wide count
   for (;;) {
-    Level &cur = c->levels.back();
-    const int lev = (int)c->levels.size() - 1;
-    deposit_level(c, cur);
-    if (cur.L == lmax) break;                                          // generate_grids.c:307-308
-    if ((c->n_total ? c->n_total : n) == 0) break;                     // empty box: the domain grid alone, nothing to flag
-    LV cv = view(cur);
-    const int nc = (int)cur.ncell;
-    int M = 0;
-    DevBuf<int> S;
-    {
-      Stage st(c, "flag", nc, c->env.stages);
-      Stage stl(c, lvl_name("flag", lev).c_str(), nc, c->env.level_stages);
-      if (cur.dense && cur.L >= 32 && !c->env.testnode_v1)
-        LAUNCH(c, k_test_node_dense, dim3((unsigned)(cur.L / 32), (unsigned)(cur.L / 8), (unsigned)(cur.L / 8)), 256, 0, cv, cur.dens, cur.critdens - 1.0, cur.tn);
-      else
-        LAUNCH(c, k_test_node, nblk(nc, 256), 256, 0, cv, cur.dens, cur.interior, cur.nbr, cur.critdens - 1.0, cur.tn);
-      if (cur.dense) LAUNCH(c, k_mark_dense, nblk(nc, 256), 256, 0, cv, cur.tn, cur.mark);
-      else LAUNCH(c, k_mark_sparse, nblk(nc, 256), 256, 0, cv, cur.tn, cur.interior, cur.crow, cur.row_c0, cur.row_tested, cur.mark);
+    const int lev = glev;
+    if (active) deposit_level(c, c->levels.back());
+    if (curL == lmax) break;                                           // generate_grids.c:307-308
+    if (n_box == 0) break;                                             // empty box: the domain grid alone, nothing to flag
+    int M = 0, h3[4] = { 0, 0, 0, 0 };
+    DevBuf<int> S_;
+    if (active) {
+      Level &cur = c->levels.back();
+      LV cv = view(cur);
+      const int nc = (int)cur.ncell;
+      {
+        Stage st(c, "flag", nc, c->env.stages);
+        Stage stl(c, lvl_name("flag", lev).c_str(), nc, c->env.level_stages);
+        if (cur.dense && cur.L >= 32 && !c->env.testnode_v1)
+          LAUNCH(c, k_test_node_dense, dim3((unsigned)(cur.L / 32), (unsigned)(cur.L / 8), (unsigned)(cur.L / 8)), 256, 0, cv, cur.dens, cur.critdens - 1.0, cur.tn);
+        else
+          LAUNCH(c, k_test_node, nblk(nc, 256), 256, 0, cv, cur.dens, cur.interior, cur.nbr, cur.critdens - 1.0, cur.tn);
+        if (cur.dense) LAUNCH(c, k_mark_dense, nblk(nc, 256), 256, 0, cv, cur.tn, cur.mark);
+        else LAUNCH(c, k_mark_sparse, nblk(nc, 256), 256, 0, cv, cur.tn, cur.interior, cur.crow, cur.row_c0, cur.row_tested, cur.mark);
+      }
+      Stage st(c, "refine", nc, c->env.stages);
+      S_.reserve(nc);
+      DevBuf<int> t3, bs;
+      t3.reserve(4);
+      CUDA_CHECK(cudaMemsetAsync(t3.p, 0, 4 * sizeof(int), c->stream));
+      exclusive_scan_async<uint8_t, true>(c, cur.mark, S_.p, nc, t3.p, bs);            // marks are 0 / 1 (refined) / 2 (ghost pair): count the non-zero ones
+      const int cnrow = cur.dense ? (int)(cur.L * cur.L) : (int)cur.nrow, cnplane = cur.dense ? (int)cur.L : (int)cur.nplane;
+      LAUNCH(c, k_count_marked, nblk(cnrow, 256), 256, 0, cv, S_.p, t3.p, cur.row_c0, cur.plane_r0, cnrow, cnplane, t3.p + 1);
+      if (split) LAUNCH(c, k_count_owned_marked, nblk(nc, 256), 256, 0, cv, cur.mark, S->own3, S->bd, cm->rank, t3.p + 3);
+      read_back(c, h3, t3.p, 4 * sizeof(int));
+      t3.release(); bs.release();
+      M = h3[0];
+      if (!split) h3[3] = M;
     }
-    {
+    if (!split && M == 0) { S_.release(); break; }                     // refine_grid returned FALSE
+    if ((long long)M * 8 > 2000000000ll) AHF_FAIL("refinement level exceeds 2^31 cells");
+    // ---- next level, built locally from the rank's marks (exact on its own cells and well into the ghost shell)
+    const bool built = active && M > 0;
+    DevBuf<int32_t> newcell; DevBuf<uint8_t> moved, dlt; DevBuf<int> MS;
+    int nmoved = 0, nmoved_own = 0;
+    uint64_t *rows_send = nullptr; int64_t nrows_own = 0;
+    if (built) {
+      Level &cur = c->levels.back();
+      LV cv = view(cur);
+      const int nc = (int)cur.ncell;
       Stage st(c, "refine", nc, c->env.stages);
       Stage stl(c, lvl_name("refine", lev).c_str(), nc, c->env.level_stages);
-      S.reserve(nc);
-      int h3[3] = { 0, 0, 0 };
-      {
-        DevBuf<int> t3, bs;
-        t3.reserve(4);
-        CUDA_CHECK(cudaMemsetAsync(t3.p, 0, 4 * sizeof(int), c->stream));
-        exclusive_scan_async<uint8_t, true>(c, cur.mark, S.p, nc, t3.p, bs);            // marks are 0 / 1 (refined) / 2 (ghost pair): count the non-zero ones
-        const int cnrow = cur.dense ? (int)(cur.L * cur.L) : (int)cur.nrow, cnplane = cur.dense ? (int)cur.L : (int)cur.nplane;
-        LAUNCH(c, k_count_marked, nblk(cnrow, 256), 256, 0, cv, S.p, t3.p, cur.row_c0, cur.plane_r0, cnrow, cnplane, t3.p + 1);
-        read_back(c, h3, t3.p, 3 * sizeof(int));
-        t3.release(); bs.release();
-      }
-      M = h3[0];
-      if (M == 0) { S.release(); break; }                             // refine_grid returned FALSE
-      if ((long long)M * 8 > 2000000000ll) AHF_FAIL("refinement level exceeds 2^31 cells");
       Level f;
       f.L = cur.L * 2; f.ncell = (int64_t)M * 8; f.dense = false;
       f.masstopartdens = cur.masstopartdens * CRITMULTI;               // generate_grids.c:164-170
@@ -1703,9 +1859,8 @@ void amr_build(ahfgpu_ctx *c)
       f.ckey = dalloc<uint64_t>(f.ncell); f.xbreak = dalloc<uint8_t>(f.ncell);
       int flogL = cv.logL + 1;
       f.parent = dalloc<int32_t>(f.ncell); cur.cidx = dalloc<int32_t>(nc); cur.cbase = dalloc<int4>(M); cur.cpar = dalloc<int32_t>(M);
-      LAUNCH(c, k_make_children, nblk(nc, 256), 256, 0, cv, cur.mark, S.p, M, cur.crow, cur.row_c0, cur.dense ? nullptr : cur.rowplane,
+      LAUNCH(c, k_make_children, nblk(nc, 256), 256, 0, cv, cur.mark, S_.p, M, cur.crow, cur.row_c0, cur.dense ? nullptr : cur.rowplane,
              cur.plane_r0, (int)cur.nrow, f.ckey, f.xbreak, flogL, f.parent, cur.cidx, cur.cbase, cur.cpar);
-      S.release();
       // hash
       // slots hold 8 x-consecutive cells; children come in x-pairs, so there are at most ncell/2 occupied slots
       uint64_t cap = 16; while (cap < (uint64_t)f.ncell + 2) cap <<= 1;
@@ -1731,77 +1886,96 @@ void amr_build(ahfgpu_ctx *c)
                 lev + 1, h[0], (unsigned long long)f.ncell * 10, h[2]);
         nb2.release(); in2.release(); out.release();
       }
-      if (c->env.debug_relink) {
-        DevBuf<int32_t> nb2; DevBuf<uint8_t> in2; DevBuf<unsigned long long> out;
-        nb2.reserve((size_t)f.ncell * 10); in2.reserve(f.ncell); out.reserve(3);
-        unsigned long long h0[3] = { 0, 0, ~0ull }, h[3];
-        CUDA_CHECK(cudaMemcpyAsync(out.p, h0, sizeof(h0), cudaMemcpyHostToDevice, c->stream));
-        LAUNCH(c, k_neighbours, nblk(f.ncell, 128), 128, 0, fv, nb2.p, in2.p);
-        LAUNCH(c, k_dbg_compare, nblk((uint64_t)f.ncell * 10, 256), 256, 0, f.nbr, nb2.p, (uint64_t)f.ncell * 10, out.p);
-        CUDA_CHECK(cudaMemcpyAsync(h, out.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        static std::map<int, unsigned long long> refcnt;
-        if (h[0]) fprintf(stderr, "[nbr dbg] level %d: %llu neighbour entries differ between two runs (first at %llu)\n", lev + 1, h[0], h[2]);
-        if (refcnt.count(lev + 1) && refcnt[lev + 1] != h[1])
-          fprintf(stderr, "[nbr dbg] level %d: %llu existing neighbour entries, %llu in the first build\n", lev + 1, h[1], refcnt[lev + 1]);
-        if (!refcnt.count(lev + 1)) refcnt[lev + 1] = h[1];
-        nb2.release(); in2.release(); out.release();
-      }
       f.nrow = 4ll * h3[1]; f.nplane = 2ll * h3[2];               // every marked coarse cell spawns 2x2x2 children
-      build_rows_planes(c, f);
+      build_rows_planes(c, f, !split);
       c->levels.push_back(f);
     }
-    // ---- relink
-    {
-      Level &coa = c->levels[lev];
-      Level &fin = c->levels[lev + 1];
+    S_.release();
+    // ---- relink, first half: which particles would move to the new level
+    if (built) {
+      Level &coa = c->levels[c->levels.size() - 2];
+      Level &fin = c->levels.back();
       Stage st(c, "relink", coa.npart_dep, c->env.stages);
       Stage stl(c, lvl_name("relink", lev).c_str(), coa.npart_dep, c->env.level_stages);
       const uint64_t np = (uint64_t)coa.npart_dep;
-      DevBuf<int32_t> newcell; DevBuf<uint8_t> moved, dlt; DevBuf<int> MS;
       newcell.reserve(np); moved.reserve(np); dlt.reserve(np); MS.reserve(np);
-      int nmoved = 0;
       if (np) {
         LAUNCH(c, k_relink, nblk(np, 256), 256, 0, c->pos4, coa.lpos, coa.plist, coa.pcell, np, view(coa), coa.mark, coa.cidx, coa.cbase, view(fin), fin.interior, newcell.p, moved.p, dlt.p);
-        nmoved = exclusive_scan<uint8_t>(c, moved.p, MS.p, np);
-        if (c->env.debug_relink) {
-          DevBuf<int32_t> nc2; DevBuf<uint8_t> mv2, dl2; DevBuf<unsigned long long> out;
-          nc2.reserve(np); mv2.reserve(np); dl2.reserve(np); out.reserve(3);
-          unsigned long long h0[3] = { 0, 0, ~0ull }, h[3];
-          CUDA_CHECK(cudaMemcpyAsync(out.p, h0, sizeof(h0), cudaMemcpyHostToDevice, c->stream));
-          LAUNCH(c, k_relink, nblk(np, 256), 256, 0, c->pos4, coa.lpos, coa.plist, coa.pcell, np, view(coa), coa.mark, coa.cidx, coa.cbase, view(fin), fin.interior, nc2.p, mv2.p, dl2.p);
-          LAUNCH(c, k_dbg_compare, nblk(np, 256), 256, 0, newcell.p, nc2.p, np, out.p);
-          CUDA_CHECK(cudaMemcpyAsync(h, out.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-          CUDA_CHECK(cudaStreamSynchronize(c->stream));
-          if (h[0] || (long long)h[1] != nmoved)
-            fprintf(stderr, "[relink dbg] level %d -> %d: %llu of %llu newcell differ between two runs (first at %llu); count(res>=0) %llu, scan total %d\n",
-                    lev, lev + 1, h[0], (unsigned long long)np, h[2], h[1], nmoved);
-          nc2.release(); mv2.release(); dl2.release(); out.release();
+        if (split) {
+          DevBuf<int> t2, bs;
+          t2.reserve(2);
+          CUDA_CHECK(cudaMemsetAsync(t2.p, 0, 2 * sizeof(int), c->stream));
+          exclusive_scan_async<uint8_t>(c, moved.p, MS.p, np, t2.p, bs);
+          LAUNCH(c, k_count_owned_moved, nblk(np, 256), 256, 0, coa.plist, moved.p, np, (uint32_t)S->own_lo, (uint32_t)S->own_hi, t2.p + 1);
+          int h2[2];
+          read_back(c, h2, t2.p, sizeof(h2));
+          nmoved = h2[0]; nmoved_own = h2[1];
+          t2.release(); bs.release();
+        } else {
+          nmoved = exclusive_scan<uint8_t>(c, moved.p, MS.p, np);
+          nmoved_own = nmoved;
         }
       }
-      if (fin.ncell < MIN_NNODES) {                                   // generate_grids.c:231 / density.c:420: level rejected
-        fin.free_all();
-        c->levels.pop_back();
-        newcell.release(); moved.release(); dlt.release(); MS.release();
-        break;
-      }
+      if (split) nrows_own = owned_rows(c, fin, &rows_send);
+    }
+    // ---- what the whole box decides
+    long long g_M = h3[3], g_moved = nmoved_own;
+    std::vector<int64_t> nrows_rank(R, 0);
+    if (split) {
+      Stage st(c, "level_allgather", 24 * R, c->env.stages);
+      long long mine[3] = { (long long)h3[3], (long long)nmoved_own, (long long)nrows_own };
+      std::vector<long long> all((size_t)3 * R);
+      cm->allgather_host(c, mine, all.data(), sizeof(mine));
+      g_M = 0; g_moved = 0;
+      for (int p = 0; p < R; p++) { g_M += all[3 * p]; g_moved += all[3 * p + 1]; nrows_rank[p] = all[3 * p + 2]; }
+    }
+    const bool refined = g_M > 0;                                      // refine_grid returned TRUE somewhere
+    const bool accepted = refined && g_M * 8 >= MIN_NNODES;            // generate_grids.c:231 / density.c:420
+    if (!accepted) {
+      if (built) { c->levels.back().free_all(); c->levels.pop_back(); }
+      ahf::dfree(rows_send);
+      newcell.release(); moved.release(); dlt.release(); MS.release();
+      break;
+    }
+    if (split) {
+      Stage st(c, "refine", 0, c->env.stages);
+      int flogL = 0; while ((1ll << flogL) < curL * 2) flogL++;
+      rows_from_all_ranks(c, built ? &c->levels.back() : nullptr, rows_send, nrows_rank, curL * 2, flogL);
+      ahf::dfree(rows_send);
+    }
+    // ---- relink, second half
+    if (built) {
+      Level &coa = c->levels[c->levels.size() - 2];
+      Level &fin = c->levels.back();
+      Stage st(c, "relink", 0, c->env.stages);
+      const uint64_t np = (uint64_t)coa.npart_dep;
       fin.npart_dep = nmoved;
+      fin.g_ncell = g_M * 8; fin.g_npart_dep = g_moved;
       fin.plist = dalloc<uint32_t>(nmoved); fin.pcell = dalloc<int32_t>(nmoved); fin.lpos = dalloc<float4>(nmoved);
       if (np) LAUNCH(c, k_compact_moved, nblk(np, 256), 256, 0, coa.plist, newcell.p, moved.p, MS.p, np, fin.plist, fin.pcell, c->owner_level, (int8_t)(lev + 1), c->pos4, coa.lpos, fin.lpos, dlt.p);
-      newcell.release(); moved.release(); dlt.release(); MS.release();      // stream-ordered block cache: no host sync needed
     }
-    if (c->levels.size() >= 60) break;
+    newcell.release(); moved.release(); dlt.release(); MS.release();      // stream-ordered block cache: no host sync needed
+    active = built;
+    curL *= 2; glev++;
+    if (glev + 1 >= 60) break;
   }
-  // final ownership counts
+  c->g_nlevels = glev + 1;
+  // final ownership counts (of the rank's own particles when the box is split)
   {
     DevBuf<unsigned long long> cnt;
     cnt.reserve(64);
     CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, 64 * sizeof(unsigned long long), c->stream));
-    if (n) LAUNCH(c, k_count_owner, std::min(nblk(n, 256), 2368u), 256, 0, c->owner_level, n, cnt.p);
+    const uint64_t o0 = split ? S->own_lo : 0, on = split ? S->own_hi - S->own_lo : n;
+    if (on) LAUNCH(c, k_count_owner, std::min(nblk(on, 256), 2368u), 256, 0, c->owner_level + o0, on, cnt.p);
     unsigned long long h[64];
     read_back(c, h, cnt.p, sizeof(h));
     for (size_t l = 0; l < c->levels.size(); l++) c->levels[l].npart_final = (int64_t)h[l];
     cnt.release();
+  }
+  if (split) {
+    c->stage_cnt_extra["comm_calls"] = cm->coll_calls;
+    c->stage_cnt_extra["comm_bytes"] = cm->coll_bytes;
+    c->stage_cnt_extra["comm_us"] = (int64_t)(cm->coll_ms * 1000.0);
   }
 }
 
@@ -1809,7 +1983,7 @@ void amr_build(ahfgpu_ctx *c)
 // queries
 // ------------------------------------------------------------------------------------------------
 __global__ void k_level_export(LV v, const int32_t *__restrict__ crow, const int32_t *__restrict__ row_c0, const uint64_t *__restrict__ rowkey,
-                               const int32_t *__restrict__ rowplane, const int32_t *__restrict__ plane_r0, int nrow, int nplane,
+                               const int32_t *__restrict__ rowplane, const int32_t *__restrict__ plane_r0, int nrow, int nplane, const uint8_t *__restrict__ row_flags,
                                int32_t *__restrict__ x, int32_t *__restrict__ y, int32_t *__restrict__ z, uint8_t *__restrict__ rf)
 {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1825,14 +1999,9 @@ __global__ void k_level_export(LV v, const int32_t *__restrict__ crow, const int
     uint64_t k = v.ckey[c];
     if ((c == c0) || (v.ckey[c - 1] + 1 != k) || v.xbreak[c - 1]) f |= 1;
     if ((c == c1 - 1) || (v.ckey[c + 1] != k + 1) || v.xbreak[c]) f |= 2;
-    int P = rowplane[r], r0 = plane_r0[P], r1 = plane_r0[P + 1];
-    if (r == r0 || rowkey[r - 1] + 1 != rowkey[r]) f |= 4;
-    if (r == r1 - 1 || rowkey[r + 1] != rowkey[r] + 1) f |= 8;
-    uint64_t zp = rowkey[r0] >> v.logL;
-    if (P == 0 || (rowkey[plane_r0[P - 1]] >> v.logL) + 1 != zp) f |= 16;
-    if (P == nplane - 1 || (rowkey[plane_r0[P + 1]] >> v.logL) != zp + 1) f |= 32;
+    f |= row_flags[r];            // first / last row of its cquad, plane of its pquad: from the rows of the whole box (k_row_tested)
   }
-  (void)nrow;
+  (void)nrow; (void)nplane; (void)rowkey; (void)rowplane; (void)plane_r0;
   rf[c] = f;
 }
 
@@ -2040,6 +2209,7 @@ extern "C" int ahfgpu_amr_patch_stats(ahfgpu_ctx *c, int32_t lev, int64_t *niso,
   try {
     if (!c || lev < 0 || lev >= (int)c->levels.size()) AHF_FAIL("bad level");
     if (!c->owner_level) AHF_FAIL("no hierarchy");
+    if (c->slab) AHF_FAIL("patch statistics of a box split over several ranks are not implemented (patches cross rank boundaries)");
     CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
     Level &l = c->levels[lev];
     if (!l.dense && !l.nbr) AHF_FAIL("level has no neighbour table");
@@ -2073,6 +2243,8 @@ extern "C" int ahfgpu_amr_patch_stats(ahfgpu_ctx *c, int32_t lev, int64_t *niso,
     if (niso) *niso = ni;
     return 0;
   } catch (const ahf::Error &e) { ahf::g_last_error = e.msg; return -1; }
+    catch (const std::exception &e) { ahf::g_last_error = e.what(); return -2; }
+    catch (...) { ahf::g_last_error = "unknown exception"; return -3; }
 }
 
 namespace ahf {
@@ -2107,6 +2279,28 @@ extern "C" int ahfgpu_amr_patches(ahfgpu_ctx *c, int32_t lev, int32_t *iso, int6
     if (niso) *niso = ni;
     return 0;
   } catch (const ahf::Error &e) { ahf::g_last_error = e.msg; return -1; }
+    catch (const std::exception &e) { ahf::g_last_error = e.what(); return -2; }
+    catch (...) { ahf::g_last_error = "unknown exception"; return -3; }
+}
+
+extern "C" int ahfgpu_amr_level_owned(ahfgpu_ctx *c, int32_t lev, uint8_t *owned)
+{
+  try {
+    if (!c || lev < 0 || lev >= (int)c->levels.size()) AHF_FAIL("bad level");
+    if (!owned) AHF_FAIL("null argument");
+    CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
+    Level &l = c->levels[lev];
+    const size_t nc = (size_t)l.ncell;
+    if (!c->slab || !c->comm) { memset(owned, 1, nc); return 0; }
+    DevBuf<uint8_t> o;
+    o.reserve(nc);
+    LAUNCH(c, k_owned_cells, nblk(nc, 256), 256, 0, view(l), c->slab->own3, c->slab->bd, c->comm->rank, o.p);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    CUDA_CHECK(cudaMemcpy(owned, o.p, nc, cudaMemcpyDeviceToHost));
+    o.release();
+    return 0;
+  } catch (const ahf::Error &e) { ahf::g_last_error = e.msg; return -1; }
+    catch (const std::exception &e) { ahf::g_last_error = e.what(); return -2; }
 }
 
 extern "C" int ahfgpu_amr_level_get(ahfgpu_ctx *c, int32_t lev, int32_t *x, int32_t *y, int32_t *z, float *dens, uint8_t *runflags,
@@ -2121,7 +2315,7 @@ extern "C" int ahfgpu_amr_level_get(ahfgpu_ctx *c, int32_t lev, int32_t *x, int3
       DevBuf<int32_t> dx, dy, dz; DevBuf<uint8_t> rf;
       dx.reserve(nc); dy.reserve(nc); dz.reserve(nc); rf.reserve(nc);
       LAUNCH(c, k_level_export, nblk(nc, 256), 256, 0, view(l), l.crow, l.row_c0, l.rowkey, l.dense ? nullptr : l.rowplane, l.plane_r0,
-             (int)l.nrow, (int)l.nplane, dx.p, dy.p, dz.p, rf.p);
+             (int)l.nrow, (int)l.nplane, l.row_flags, dx.p, dy.p, dz.p, rf.p);
       CUDA_CHECK(cudaStreamSynchronize(c->stream));
       if (x) CUDA_CHECK(cudaMemcpy(x, dx.p, nc * 4, cudaMemcpyDeviceToHost));
       if (y) CUDA_CHECK(cudaMemcpy(y, dy.p, nc * 4, cudaMemcpyDeviceToHost));
@@ -2143,6 +2337,8 @@ extern "C" int ahfgpu_amr_level_get(ahfgpu_ctx *c, int32_t lev, int32_t *x, int3
     }
     return 0;
   } catch (const ahf::Error &e) { ahf::g_last_error = e.msg; return -1; }
+    catch (const std::exception &e) { ahf::g_last_error = e.what(); return -2; }
+    catch (...) { ahf::g_last_error = "unknown exception"; return -3; }
 }
 
 extern "C" int ahfgpu_amr_particle_levels(ahfgpu_ctx *c, int8_t *owner_level, int32_t *cell_of, int32_t nlev_cap)
@@ -2166,4 +2362,6 @@ extern "C" int ahfgpu_amr_particle_levels(ahfgpu_ctx *c, int8_t *owner_level, in
     }
     return 0;
   } catch (const ahf::Error &e) { ahf::g_last_error = e.msg; return -1; }
+    catch (const std::exception &e) { ahf::g_last_error = e.what(); return -2; }
+    catch (...) { ahf::g_last_error = "unknown exception"; return -3; }
 }

@@ -451,6 +451,17 @@ __global__ void k_keys_pos4(const float4 *__restrict__ pos4, uint64_t n, uint64_
   keys[i] = hilbert_key_pos(p.x, p.y, p.z, 21);
   idx[i]  = (uint32_t)i;
 }
+__global__ void __launch_bounds__(KT_THREADS) k_keys_pos4_tab(const float4 *__restrict__ pos4, uint64_t n, uint64_t *__restrict__ keys, uint32_t *__restrict__ idx)
+{
+  __shared__ __align__(16) uint16_t tab[12 * 512];
+  for (int i = threadIdx.x; i < 12 * 512 / 8; i += KT_THREADS) reinterpret_cast<uint4 *>(tab)[i] = reinterpret_cast<const uint4 *>(g_hil_tab3)[i];
+  __syncthreads();
+  for (uint64_t i = blockIdx.x * (uint64_t)KT_THREADS + threadIdx.x; i < n; i += (uint64_t)gridDim.x * KT_THREADS) {
+    const float4 p = pos4[i];
+    keys[i] = hilbert_key_pos21_tab(p.x, p.y, p.z, tab);
+    idx[i] = (uint32_t)i;
+  }
+}
 __global__ void k_gather4(const float4 *__restrict__ pin, const float4 *__restrict__ min_, const uint32_t *__restrict__ order, uint64_t n,
                           float4 *__restrict__ pos4, float4 *__restrict__ mom4)
 {
@@ -460,7 +471,26 @@ __global__ void k_gather4(const float4 *__restrict__ pin, const float4 *__restri
   pos4[i] = pin[o]; mom4[i] = min_[o];
 }
 
+__global__ void k_map_u32(const uint32_t *__restrict__ idx, const uint32_t *__restrict__ table, uint64_t n, uint32_t *__restrict__ out)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = table[idx[i]];
+}
+
+// 21-bit keys of unsorted float3 positions on the device (slab.cu: block histogram of what a rank has read)
+void sfc_keys_f3(ahfgpu_ctx *c, const float *pos3, uint64_t n, uint64_t *keys)
+{
+  if (n) LAUNCH(c, k_keys_soa_tab, keys_tab_grid(n), KT_THREADS, 0, pos3, (uint64_t)0, n, keys, (uint32_t *)nullptr);
+}
+
+void sfc_sort_device4_gid(ahfgpu_ctx *c, const void *pos4_dev, const void *mom4_dev, const uint32_t *gid, uint64_t n, bool has_w, bool has_u);
 void sfc_sort_device4(ahfgpu_ctx *c, const void *pos4_dev, const void *mom4_dev, uint64_t n, bool has_w, bool has_u)
+{
+  sfc_sort_device4_gid(c, pos4_dev, mom4_dev, nullptr, n, has_w, has_u);
+}
+// gid (may be null): caller's identifier of input particle i; the resident `order` array then holds gid of the sorted particles
+// instead of their input position (slab.cu: global input index of particles that came from several ranks)
+void sfc_sort_device4_gid(ahfgpu_ctx *c, const void *pos4_dev, const void *mom4_dev, const uint32_t *gid, uint64_t n, bool has_w, bool has_u)
 {
   if (n >= (1ull << 32)) AHF_FAIL("more than 2^32-1 particles per device are not supported");
   alloc_particles(c, n);
@@ -471,7 +501,7 @@ void sfc_sort_device4(ahfgpu_ctx *c, const void *pos4_dev, const void *mom4_dev,
   const unsigned nb = (unsigned)((n + 255) / 256);
   {
     Stage st(c, "keys", (int64_t)n);
-    if (n) LAUNCH(c, k_keys_pos4, nb, 256, 0, (const float4 *)pos4_dev, n, k0.p, v0.p);
+    if (n) LAUNCH(c, k_keys_pos4_tab, keys_tab_grid(n), KT_THREADS, 0, (const float4 *)pos4_dev, n, k0.p, v0.p);
   }
   uint64_t *ks; uint32_t *vs;
   {
@@ -485,7 +515,8 @@ void sfc_sort_device4(ahfgpu_ctx *c, const void *pos4_dev, const void *mom4_dev,
   c->keys = static_cast<decltype(c->keys)>(ahf::cache_alloc((n ? n : 1) * sizeof(uint64_t)));
   c->order = static_cast<decltype(c->order)>(ahf::cache_alloc((n ? n : 1) * sizeof(uint32_t)));
   CUDA_CHECK(cudaMemcpyAsync(c->keys, ks, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
-  CUDA_CHECK(cudaMemcpyAsync(c->order, vs, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+  if (gid && n) LAUNCH(c, k_map_u32, nb, 256, 0, vs, gid, n, c->order);
+  else CUDA_CHECK(cudaMemcpyAsync(c->order, vs, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
   k0.release(); k1.release(); v0.release(); v1.release();
 }

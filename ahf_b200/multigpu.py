@@ -1,167 +1,125 @@
-"""One box on several GPUs of one node: one process per GPU, torch.distributed (NCCL over
-NVLink / NVSwitch) for the plumbing, libahfgpu.so for all compute.
+"""ONE box on several GPUs of one node: host-side driver of the slab decomposition in libahfgpu.so.
 
-    slab exchange   every rank sorts the particles it read, equal-particle Hilbert key ranges are chosen from regular
-                    samples (the reference's MPI load balancer uses a per-cell histogram, src/libutility/loadbalance.c:383)
-                    and the particles travel to the owner of their key range with ONE all-to-all (comm.c:104-316)
-    mesh            every rank holds the (small) cell structure of every level, deposits only its slab; the u64
-                    fixed-point accumulators of each level are summed with an NCCL all-reduce -- the ghost-cell exchange,
-                    exact and order independent, so every rank takes bit-identical refinement decisions
-    halo pass       the sorted slabs are all-gathered once (48 B/particle fits every GPU), haloes are assigned
-                    to ranks by greedy LPT on their seed particle count and each rank constructs its share
+Everything on the data path is C++/CUDA behind the C-ABI (ahf_b200/csrc/slab.cu, comm.cu, mesh.cu):
 
-There is no CPU path here either: every tensor lives on the rank's GPU.
+    distribute      keys of what the rank read, histogram over the Hilbert cells of the decomposition level (all-reduce),
+                    equal-particle key ranges (the reference's MPI load balancer, src/libutility/loadbalance.c:383), ONE
+                    personalised exchange that sends every particle to its owner AND to the ranks whose range lies within the
+                    ghost width of it (comm_dist_part + boundary duplication, src/comm.c:104-316, :324ff), ONE sort
+    build_amr       every rank builds all levels over its own cells + ghost shell; per level one small all-gather (marked cells,
+                    particles on the next level, row counts) and one all-gather of row keys
+    construct_halos every rank serves the haloes whose centre lies in its key range: their gathering spheres are inside the
+                    ghost shell, so the halo pass needs no communication; member lists come back as global input indices
+
+Two transports: NCCL (one process per GPU; this module only hands the 128-byte NCCL id from rank 0 to the others through
+torch.distributed) and an in-process group of host threads (`run_local`: 2, 4 or 8 "ranks" on ONE GPU, used by the tests).
+There is no CPU path: every array lives on a GPU.
 """
 from __future__ import annotations
 
-import ctypes as C
+import threading
 
 import numpy as np
-import torch
-import torch.distributed as dist
 
-from . import ahf, parallel
+from . import ahf
 
 
-class _DevArray:
-    """zero-copy torch view of device memory owned by libahfgpu (CUDA array interface)"""
+class SlabRank:
+    """One rank's share of ONE box."""
 
-    def __init__(self, ptr: int, shape, typestr: str):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
-
-
-def dev_tensor(ptr: int, shape, typestr: str, device) -> torch.Tensor:
-    if int(np.prod(shape)) == 0:
-        return torch.empty(tuple(shape), dtype={"<f4": torch.float32, "<i8": torch.int64}[typestr], device=device)
-    return torch.as_tensor(_DevArray(ptr, shape, typestr), device=device)
-
-
-_ALLREDUCE_T = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
-
-
-class SlabBox:
-    """The path for ONE box split over `world` ranks."""
-
-    def __init__(self, params: ahf.Params, rank: int, world: int, device: int):
+    def __init__(self, params: ahf.Params, rank: int, world: int, device: int, *, nccl_id: bytes | None = None, local_group: int | None = None):
         self.rank, self.world = rank, world
-        self.device = torch.device("cuda", device)
-        params.device = device
-        self.g = ahf.AhfGpu(params)                 # mesh context: the rank's slab
-        self.gh = ahf.AhfGpu(params)                # halo context: adopts the all-gathered box
-        self.n_total = 0
-        self._cb = _ALLREDUCE_T(self._allreduce)    # keep the ctypes thunk alive
-        self._keep = []
+        p = ahf.Params.from_buffer_copy(bytes(params))
+        p.device = device
+        self.params = p
+        self.g = ahf.AhfGpu(p)
+        if local_group is not None:
+            self.g.comm_init_local(rank, local_group)
+        elif nccl_id is not None:
+            self.g.comm_init_nccl(rank, world, nccl_id)
+        else:
+            raise ValueError("need nccl_id or local_group")
+        self.mine = None
 
     def close(self):
-        self.gh.close(); self.g.close()
+        self.g.close()
 
-    # ------------------------------------------------------------------------------------------------ exchange
-    def distribute(self, pos_local: np.ndarray, mom_local: np.ndarray):
-        """pos_local / mom_local: the particles this rank read (any order).  Afterwards the rank holds its SFC slab,
-        key sorted, resident in the mesh context."""
-        g, L, dev = self.g, ahf.lib(), self.device
-        n_local = int(pos_local.shape[0])
-        if isinstance(pos_local, torch.Tensor):     # (pinned) host tensors: no staging copy inside the driver
-            g.sfc_sort_ptr(pos_local.data_ptr(), mom_local.data_ptr(), n_local)
-        else:
-            g.sfc_sort(pos_local, mom_local, want_keys=False, want_order=False)
-        pos4 = dev_tensor(L.ahfgpu_device_ptr(g._h, b"pos4"), (n_local, 4), "<f4", dev)
-        mom4 = dev_tensor(L.ahfgpu_device_ptr(g._h, b"mom4"), (n_local, 4), "<f4", dev)
-        keys = dev_tensor(L.ahfgpu_device_ptr(g._h, b"keys"), (n_local,), "<i8", dev)       # 63-bit keys: non-negative as int64
-        if self.world == 1:
-            self.n_total = n_local
-            return
-        tot = torch.tensor([n_local], device=dev, dtype=torch.int64)
-        dist.all_reduce(tot)
-        self.n_total = int(tot.item())
-        # splitters from regular samples of every rank's sorted keys
-        ns = 4096
-        idx = (torch.arange(ns, device=dev, dtype=torch.int64) * max(n_local - 1, 0)) // (ns - 1)     # integer arithmetic: float32 linspace overflows 2^24
-        samp = keys[idx] if n_local else torch.zeros(ns, dtype=torch.int64, device=dev)
-        allsamp = [torch.empty_like(samp) for _ in range(self.world)]
-        dist.all_gather(allsamp, samp)
-        allsamp = torch.sort(torch.cat(allsamp)).values
-        split = allsamp[(torch.arange(1, self.world, device=dev) * allsamp.numel()) // self.world]
-        bounds = torch.searchsorted(keys, split).tolist() if n_local else [0] * (self.world - 1)
-        bounds = [0] + bounds + [n_local]
-        send_counts = [bounds[r + 1] - bounds[r] for r in range(self.world)]
-        sc = torch.tensor(send_counts, device=dev, dtype=torch.int64)
-        rc = torch.empty_like(sc)
-        dist.all_to_all_single(rc, sc)
-        recv_counts = rc.tolist()
-        n_new = int(sum(recv_counts))
-        rpos = torch.empty((n_new, 4), dtype=torch.float32, device=dev)
-        rmom = torch.empty((n_new, 4), dtype=torch.float32, device=dev)
-        dist.all_to_all_single(rpos, pos4.contiguous(), output_split_sizes=recv_counts, input_split_sizes=send_counts)
-        dist.all_to_all_single(rmom, mom4.contiguous(), output_split_sizes=recv_counts, input_split_sizes=send_counts)
-        torch.cuda.synchronize(dev)
-        g._chk(L.ahfgpu_sfc_sort_device4(g._h, C.c_void_p(rpos.data_ptr()), C.c_void_p(rmom.data_ptr()), n_new, 0, 0))
-        g.n = n_new
-        del rpos, rmom
+    # ---- exchange ------------------------------------------------------------------------------------------
+    def distribute(self, pos, mom, weight=None, u=None, *, id_base: int, ghost_width: float = 0.0, decomp_bits: int = 0):
+        """pos / mom: what this rank read (any subset of the box, any order); id_base: global index of its first particle"""
+        self.g.upload(pos, mom, weight, u)
+        self.g.slab_distribute(id_base, ghost_width, decomp_bits)
 
-    # ------------------------------------------------------------------------------------------------ mesh
-    def _allreduce(self, user, ptr, count):
-        try:
-            t = dev_tensor(ptr, (int(count),), "<i8", self.device)
-            dist.all_reduce(t)                      # SUM of two's-complement words == sum of the u64 fixed-point accumulators
-            torch.cuda.synchronize(self.device)
-            return 0
-        except Exception as e:                      # noqa: BLE001 -- reported through the C status
-            print("all-reduce callback failed:", e)
-            return 1
+    def distribute_ptr(self, pos_ptr: int, mom_ptr: int, n: int, *, id_base: int, ghost_width: float = 0.0, decomp_bits: int = 0):
+        """same from raw (pinned) host pointers: the upload is part of the call"""
+        import ctypes as C
+        g = self.g
+        g._chk(g._L.ahfgpu_upload_soa(g._h, C.c_void_p(pos_ptr), C.c_void_p(mom_ptr), None, None, n))
+        g.slab_distribute(id_base, ghost_width, decomp_bits)
 
+    def redistribute(self, *, id_base: int, ghost_width: float = 0.0, decomp_bits: int = 0):
+        """again from the copy already uploaded (timing with the input resident in HBM)"""
+        self.g.slab_distribute(id_base, ghost_width, decomp_bits)
+
+    # ---- mesh ----------------------------------------------------------------------------------------------
     def build_amr(self) -> int:
-        g, L = self.g, ahf.lib()
-        g._chk(L.ahfgpu_set_global_count(g._h, self.n_total))
-        if self.world > 1:
-            g._chk(L.ahfgpu_set_allreduce(g._h, C.cast(self._cb, C.c_void_p), None))
-        return g.build_amr()
+        self.g.build_amr()
+        return self.g.slab_info()["levels"]
 
-    # ------------------------------------------------------------------------------------------------ halo pass
-    def gather_box(self):
-        """all-gather the sorted slabs (rank order == key order) and adopt them in the halo context"""
-        g, L, dev = self.g, ahf.lib(), self.device
-        n_local = g.n
-        pos4 = dev_tensor(L.ahfgpu_device_ptr(g._h, b"pos4"), (n_local, 4), "<f4", dev)
-        mom4 = dev_tensor(L.ahfgpu_device_ptr(g._h, b"mom4"), (n_local, 4), "<f4", dev)
-        keys = dev_tensor(L.ahfgpu_device_ptr(g._h, b"keys"), (n_local,), "<i8", dev)
-        if self.world == 1:
-            full = (pos4, mom4, keys)
-        else:
-            cnt = torch.tensor([n_local], device=dev, dtype=torch.int64)
-            cnts = [torch.empty_like(cnt) for _ in range(self.world)]
-            dist.all_gather(cnts, cnt)
-            cnts = [int(c.item()) for c in cnts]
-            nmax = max(cnts)
-
-            def gather(t, width):
-                pad = torch.zeros((nmax,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-                pad[:n_local] = t
-                out = torch.empty((self.world * nmax,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-                dist.all_gather_into_tensor(out, pad)
-                return torch.cat([out[r * nmax:r * nmax + cnts[r]] for r in range(self.world)]).contiguous()
-            full = (gather(pos4, 4), gather(mom4, 4), gather(keys, 1))
-        torch.cuda.synchronize(dev)
-        self._keep = list(full)                     # the library only borrows these arrays
-        n = int(full[2].shape[0])
-        self.gh._chk(L.ahfgpu_adopt_sorted(self.gh._h, C.c_void_p(full[0].data_ptr()), C.c_void_p(full[1].data_ptr()),
-                                           C.c_void_p(full[2].data_ptr()), n, 0, 0))
-        self.gh.n = n
-        return n
-
-    def construct_halos(self, centres: np.ndarray, gather_rad: np.ndarray, seed_npart: np.ndarray) -> np.ndarray:
-        """every rank gets the full (nhalo, 64) scalar table; member lists / profiles stay with the constructing rank"""
-        owner = parallel.assign_halos_lpt(seed_npart, self.world)
+    # ---- halo pass -----------------------------------------------------------------------------------------
+    def construct_halos(self, centres: np.ndarray, gather_rad: np.ndarray, seed_npart: np.ndarray, fetch: bool = True, scal_only: bool = False):
+        """the haloes whose centre this rank owns; returns (indices into the caller's list, result dict or None)"""
+        info = self.g.slab_info()
+        if len(gather_rad) and float(np.max(gather_rad)) > info["ghost_width"] * (1 + 1e-12):
+            raise ahf.AhfGpuError("a gathering radius exceeds the ghost width the particles were distributed with")
+        owner = self.g.slab_owner_of(centres)
         mine = np.nonzero(owner == self.rank)[0]
-        scal = np.zeros((len(gather_rad), ahf.NSCAL))
-        self.local_halos = mine
-        self.local_result = None
-        if len(mine):
-            res = self.gh.construct_halos(centres[mine], gather_rad[mine], seed_npart[mine])
-            scal[mine] = res["scal"]
-            self.local_result = res
-        if self.world > 1:
-            t = torch.from_numpy(scal).to(self.device)
-            dist.all_reduce(t)                      # disjoint rows: the sum is the union
-            scal = t.cpu().numpy()
-        return scal
+        self.mine = mine
+        res = self.g.construct_halos(centres[mine], gather_rad[mine], seed_npart[mine], fetch=False)
+        if fetch:
+            res = self.g.fetch_halos(len(mine), scal_only=scal_only)
+        return mine, res
+
+
+def nccl_id_via_torch(rank: int, device) -> bytes:
+    """rank 0 makes the NCCL id, torch.distributed (already initialised by the caller) hands it to everybody"""
+    import torch
+    import torch.distributed as dist
+    t = torch.zeros(128, dtype=torch.uint8, device=device)
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(ahf.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, 0)
+    return bytes(t.cpu().numpy().tobytes())
+
+
+def run_local(world: int, params: ahf.Params, fn, device: int = 0):
+    """`world` ranks as host threads of this process on ONE device: fn(rank, SlabRank) -> result; returns the list of results.
+    An exception in one rank aborts the group (the others leave their collectives with an error) and is re-raised."""
+    group = ahf.local_group_create(world)
+    results, errors = [None] * world, [None] * world
+
+    def work(r):
+        sb = None
+        try:
+            sb = SlabRank(params, r, world, device, local_group=group)
+            results[r] = fn(r, sb)
+        except BaseException as e:  # noqa: BLE001
+            errors[r] = e
+            ahf.local_group_abort(group)
+        finally:
+            if sb is not None:
+                try:
+                    sb.close()
+                except Exception:  # noqa: BLE001
+                    pass
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    ahf.local_group_destroy(group)
+    first = [e for e in errors if e is not None and "aborted" not in str(e)] or [e for e in errors if e is not None]
+    if first:
+        raise first[0]
+    return results

@@ -157,22 +157,49 @@ int  ahfgpu_halo_fetch(ahfgpu_ctx *ctx, double *scal, int64_t *member_offset, in
  *   prof_species  per halo nbins x 3 (column-major, CSR via prof_offset): HALOPROFILE.M_gas, .M_star, .u_gas        */
 int  ahfgpu_halo_fetch_species(ahfgpu_ctx *ctx, double *species, double *prof_species);
 
-/* ---- several GPUs working on ONE box: particles are split into SFC slabs, one per process/GPU; every process
- * holds the full (small) cell structure of every level, deposits its own particles and the level accumulators are summed
- * over the processes through a caller-supplied all-reduce (NCCL via torch.distributed in ahf_b200/multigpu.py) -- the
- * ghost-cell exchange of the reference's MPI mode (src/comm.c:324ff duplicates boundary PARTICLES instead) generalised to
- * a sum of the u64 fixed-point accumulators, which is exact and order independent.
+/* ---- several GPUs working on ONE box -------------------------------------------------------------------------------
+ * Replaces the reference's MPI mode: loadbalance_update / local_equalpart (src/libutility/loadbalance.c:206,383: histogram of the
+ * particles over the Hilbert cells of LevelDomainDecomp, MPI_Allreduce :480, equal-particle key ranges), comm_dist_part
+ * (src/comm.c:104-316: every particle to the owner of its key range) and comm_dist_part_ahf (src/comm.c:324ff with
+ * sfc_boundary_2_get, src/libsfc/sfc_boundary.c:100-144: duplication of the boundary-shell particles on the neighbours).
+ * One context per GPU; every context is given a communicator and the particles ITS process read (any subset, any order):
+ *   ahfgpu_comm_nccl_unique_id / ahfgpu_comm_init_nccl : one process per GPU, NCCL over NVLink (id: 128 bytes made on rank 0 and handed
+ *                                to all ranks by the caller -- MPI_Bcast, torch.distributed, a file ...)
+ *   ahfgpu_comm_local_group_create / ahfgpu_comm_init_local : several contexts of ONE process, each driven by its own host thread (they
+ *                                may share a device); for tests of the decomposition on a box with one GPU
+ *   ahfgpu_upload_soa + ahfgpu_slab_distribute : keys, block histogram (all-reduce), equal-particle Hilbert ranges, ONE personalised
+ *                                exchange that sends every particle to its owner and to the ranks whose range lies within `ghost_width`
+ *                                (box units; at least 8 domain cells, the reach of the hierarchy construction, and >= the largest
+ *                                gathering radius) of it, ONE sort.  id_base = global input index of the rank's first particle (ranks
+ *                                in rank order; all indices < 2^32).  decomp_bits = LevelDomainDecomp (0: blocks of 4 domain cells).
+ * Afterwards ahfgpu_build_amr builds every level over the rank's own cells + ghost shell (results are exact on the own cells --
+ * ahfgpu_amr_level_owned -- and identical to a single-GPU run, bit for bit), and ahfgpu_construct_halos serves the haloes whose
+ * centre the rank owns (ahfgpu_slab_owner_of); member lists then hold GLOBAL INPUT INDICES instead of sorted offsets.
+ *   ahfgpu_slab_info : iout[12] = rank, nranks, resident particles (own + ghost), first own, one past last own (sorted offsets),
+ *                      particles of the box, decomp bits, shell thickness in blocks, first own block, one past last own block,
+ *                      levels of the whole box, collectives since distribute; dout[4] = ghost width, ms inside device collectives
+ *                      (CUDA events), bytes received by them, 0
+ *   ahfgpu_particle_ids : per resident sorted particle its input position (single GPU) / global input index (slab)            */
+int  ahfgpu_comm_nccl_unique_id(void *id128);
+int  ahfgpu_comm_init_nccl(ahfgpu_ctx *ctx, int32_t rank, int32_t nranks, const void *id128);
+void *ahfgpu_comm_local_group_create(int32_t nranks);
+int  ahfgpu_comm_local_group_destroy(void *group);
+int  ahfgpu_comm_local_group_abort(void *group);      /* wakes every rank waiting in a collective with an error (a peer failed) */
+int  ahfgpu_comm_init_local(ahfgpu_ctx *ctx, int32_t rank, void *group);
+int  ahfgpu_slab_distribute(ahfgpu_ctx *ctx, uint64_t id_base, double ghost_width, int32_t decomp_bits);
+int  ahfgpu_slab_info(ahfgpu_ctx *ctx, int64_t *iout, double *dout);
+int  ahfgpu_slab_owner_of(ahfgpu_ctx *ctx, int64_t n, const double *pos3, int32_t *owner);
+int  ahfgpu_amr_level_owned(ahfgpu_ctx *ctx, int32_t lev, uint8_t *owned);
+int  ahfgpu_particle_ids(ahfgpu_ctx *ctx, uint32_t *ids);
+/* lower-level pieces kept for callers that place particles themselves:
  *   ahfgpu_set_global_count : N of the whole box (masstopartdens = L^3 / N, generate_grids.c:66-69)
- *   ahfgpu_set_allreduce    : fn(user, device pointer, number of uint64) must sum the buffer over all processes in place
  *   ahfgpu_adopt_sorted     : make caller-owned DEVICE arrays (float4 pos+weight, float4 mom+u, u64 keys; key sorted) the
- *                             resident particle set, e.g. the all-gathered box for the halo pass (not freed by the library)
- *   ahfgpu_device_ptr       : device pointers of the resident sorted set ("pos4","mom4","keys") for the exchange         */
-/*   ahfgpu_sfc_sort_device4 : keys + sort + gather of particles that already sit on the device as float4 (x,y,z,weight) /
- *                             float4 (px,py,pz,u) arrays, e.g. what a rank received in the slab exchange               */
-typedef int (*ahfgpu_allreduce_fn)(void *user, void *dev_u64, int64_t count);
+ *                             resident particle set (not freed by the library)
+ *   ahfgpu_device_ptr       : device pointers of the resident sorted set ("pos4","mom4","keys")
+ *   ahfgpu_sfc_sort_device4 : keys + sort + gather of particles that already sit on the device as float4 (x,y,z,weight) /
+ *                             float4 (px,py,pz,u) arrays                                                                  */
 int  ahfgpu_sfc_sort_device4(ahfgpu_ctx *ctx, const void *pos4_dev, const void *mom4_dev, uint64_t n, int32_t has_weight, int32_t has_u);
 int  ahfgpu_set_global_count(ahfgpu_ctx *ctx, uint64_t n_total);
-int  ahfgpu_set_allreduce(ahfgpu_ctx *ctx, ahfgpu_allreduce_fn fn, void *user);
 int  ahfgpu_adopt_sorted(ahfgpu_ctx *ctx, const void *pos4_dev, const void *mom4_dev, const void *keys_dev, uint64_t n,
                          int32_t has_weight, int32_t has_u);
 void *ahfgpu_device_ptr(ahfgpu_ctx *ctx, const char *name);

@@ -1,6 +1,8 @@
-"""Run under torchrun on >= 2 GPUs: one box split into SFC slabs over the ranks (ahf_b200/multigpu.py) must give exactly the
-single-GPU result: same levels, bit-identical densities and refinement marks, same halo table."""
+"""Run under torchrun on >= 2 GPUs: one box split into SFC slabs over the ranks with the NCCL transport (ahf_b200/csrc/comm.cu, slab.cu)
+must give exactly the single-GPU result (tests/slab_util.py): every rank checks its own part against the truth it computes itself, the
+partition property is checked on rank 0 from the gathered reports."""
 import os
+import pickle
 import sys
 
 import numpy as np
@@ -9,7 +11,9 @@ import torch.distributed as dist
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 from ahf_b200 import ahf, multigpu, synth   # noqa: E402
+import slab_util                             # noqa: E402
 
 
 def main():
@@ -18,41 +22,23 @@ def main():
     os.environ.setdefault("NCCL_DEBUG", "WARN")
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     n1d = int(os.environ.get("AHF_MGPU_N1D", "64"))
-    box = synth.make_box(n1d, seed=17, n_clumps=10)
+    cb = np.array([[0.5, 0.5, 0.5], [0.5, 0.25, 0.75], [0.999, 0.5, 0.3], [0.001, 0.002, 0.998], [0.25, 0.5, 0.5]])
+    box = synth.make_box(n1d, seed=17, n_clumps=14, centres_box=cb)
     n = box.npart
+    c, r, seed = synth.halo_seeds(box)
     b = (np.arange(world + 1) * n) // world
     par = ahf.make_params(boxsize=box.boxsize, pmass=box.pmass, lgrid_dom=n1d, device=lr)
-    sb = multigpu.SlabBox(par, rank, world, lr)
-    sb.distribute(box.pos[b[rank]:b[rank + 1]], box.mom[b[rank]:b[rank + 1]])       # each rank "reads" a file-order slice
-    nl = sb.build_amr()
-    ntot = sb.gather_box()
-    assert ntot == n, (ntot, n)
-    c, r, seed = synth.halo_seeds(box)
-    scal = sb.construct_halos(c, r, seed)
-    # single-GPU truth on every rank
-    par1 = ahf.make_params(boxsize=box.boxsize, pmass=box.pmass, lgrid_dom=n1d, device=lr)
-    with ahf.AhfGpu(par1) as g:
-        keys, _ = g.sfc_sort(box.pos, box.mom)
-        nl1 = g.build_amr()
-        assert nl == nl1, (nl, nl1)
-        dep = torch.zeros(nl, dtype=torch.int64, device="cuda")
-        for l in range(nl):
-            A, B = sb.g.level(l), g.level(l)
-            assert A.ncell == B.ncell and np.array_equal(A.lin(), B.lin()), "level %d cells" % l
-            assert np.array_equal(A.dens, B.dens), "level %d densities are not bit identical" % l
-            assert np.array_equal(A.mark, B.mark) and np.array_equal(A.runflags, B.runflags)
-            dep[l] = A.npart_dep
-        dist.all_reduce(dep)
-        assert [int(v) for v in dep] == [g.level_header(l)[0][2] for l in range(nl)], "particles per level"
-        res1 = g.construct_halos(c, r, seed)
-        assert np.array_equal(scal[:, 5:10], res1["scal"][:, 5:10])
-        assert np.allclose(scal, res1["scal"], rtol=1e-12, atol=0, equal_nan=True)
-        for k, h in enumerate(sb.local_halos):
-            assert np.array_equal(sb.gh.halo_members(sb.local_result, k), g.halo_members(res1, h))
+    sb = multigpu.SlabRank(par, rank, world, lr, nccl_id=multigpu.nccl_id_via_torch(rank, torch.device("cuda", lr)))
+    sb.distribute(box.pos[b[rank]:b[rank + 1]], box.mom[b[rank]:b[rank + 1]], id_base=int(b[rank]))
+    rep = slab_util.rank_report(sb, c, r, seed)
     sb.close()
-    dist.barrier()
+    blobs = [None] * world
+    dist.all_gather_object(blobs, pickle.dumps(rep))
     if rank == 0:
-        print("MGPU_OK world=%d levels=%d haloes=%d" % (world, nl, len(r)))
+        T = slab_util.single_gpu_truth(ahf, box, n1d, c, r, seed, device=lr)
+        out = slab_util.check_against_truth([pickle.loads(x) for x in blobs], T, n)
+        print("MGPU_OK world=%d %s" % (world, out))
+    dist.barrier()
     dist.destroy_process_group()
 
 
