@@ -434,15 +434,22 @@ class AhfGpu:
             return None
         return self.fetch_halos(nh)
 
-    def fetch_halos(self, nh: int, scal_only: bool = False):
+    def fetch_halos(self, nh: int, scal_only: bool = False, bufs: dict | None = None):
+        """bufs: caller-owned host arrays to fetch into (e.g. numpy views of PINNED memory, so that the copies run at bus speed):
+        'scal' (nh*64 f64), 'moff' / 'poff' (nh+1 i64), 'members' (i64), 'prof' (f64) -- each at least as large as needed"""
         tm = C.c_int64(); tb = C.c_int64()
         self._chk(self._L.ahfgpu_halo_sizes(self._h, C.byref(tm), C.byref(tb)))
-        scal = np.empty((nh, NSCAL), np.float64)
+
+        def take(name, count, dtype):
+            if bufs is not None and name in bufs and bufs[name].size >= count:
+                return bufs[name].reshape(-1)[:count]
+            return np.empty(count, dtype)
+        scal = take("scal", nh * NSCAL, np.float64).reshape(nh, NSCAL)
         if scal_only:
             self._chk(self._L.ahfgpu_halo_fetch(self._h, _p(scal), None, None, None, None))
             return dict(scal=scal)
-        moff = np.empty(nh + 1, np.int64); poff = np.empty(nh + 1, np.int64)
-        members = np.empty(max(tm.value, 1), np.int64); prof = np.empty(max(tb.value, 1) * NPROFCOL, np.float64)
+        moff = take("moff", nh + 1, np.int64); poff = take("poff", nh + 1, np.int64)
+        members = take("members", max(tm.value, 1), np.int64); prof = take("prof", max(tb.value, 1) * NPROFCOL, np.float64)
         self._chk(self._L.ahfgpu_halo_fetch(self._h, _p(scal), _p(moff), _p(members), _p(poff), _p(prof)))
         res = dict(scal=scal, member_offset=moff, members=members[:tm.value], prof_offset=poff, prof=prof[:tb.value * NPROFCOL])
         # GAS_PARTICLES build (particles carry u): HALO.gas_only / HALO.stars_only and the M_gas, M_star, u_gas profile columns

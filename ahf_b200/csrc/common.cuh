@@ -101,6 +101,8 @@ struct Level {
   uint32_t *plist = nullptr;    // [npart_dep]   (nullptr on the domain level = all particles)
   int32_t  *pcell = nullptr;    // [npart_dep]
   float4   *lpos = nullptr;     // [npart_dep] positions of the level's particles, contiguous (refinement levels)
+  double   *pstat = nullptr;    // [pstat_n][18] RefCentre table of the level (ahfgpu_amr_patch_stats), kept until the hierarchy is rebuilt
+  int64_t   pstat_n = -1;
   void free_all();
 };
 

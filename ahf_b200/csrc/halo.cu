@@ -459,7 +459,7 @@ __device__ RvirOut rvir_cut(const float4 *__restrict__ pos4, const uint32_t *__r
 __global__ void __launch_bounds__(HB) k_halo_unbind(const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, int has_u,
                                                     const double *__restrict__ centre, const int64_t *__restrict__ moff0, const int64_t *__restrict__ ngather,
                                                     uint32_t *__restrict__ members, HP P, double *__restrict__ scal, int64_t *__restrict__ npart_out,
-                                                    int64_t *__restrict__ iter_work)
+                                                    int64_t *__restrict__ iter_work, const int32_t *__restrict__ sel)
 {
   __shared__ double    smd[(HB / 32) * 4];
   __shared__ long long sml[HB / 32];
@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(HB) k_halo_unbind(const float4 *__restrict__ p
   __shared__ double    nb_r[HB + 1], nb_I[HB + 1];
   __shared__ double    s_seed[4];
   __shared__ double    s_R;
-  const int64_t h = blockIdx.x;
+  const int64_t h = sel ? (int64_t)sel[blockIdx.x] : (int64_t)blockIdx.x;      // sel: the haloes this launch serves (the small ones of the hybrid pass)
   uint32_t     *ip = members + moff0[h];
   long long     np = ngather[h];
   double       *S = scal + h * AHFGPU_NSCAL;
@@ -1977,7 +1977,7 @@ static inline unsigned nblk(uint64_t n, int b) { return (unsigned)((n + b - 1) /
 // host side of the cooperative U2/U3 pass: tile lists per phase, kernel sequences, the few per-halo read-backs
 static void unbind_cooperative(ahfgpu_ctx *c, int64_t nhalo, const HP &P, const double *d_ctr, const int64_t *d_moff0, const std::vector<int64_t> &moff0,
                                const int64_t *d_ng, const std::vector<int64_t> &h_ng, uint32_t *d_members, int64_t tot_g, int64_t *d_np_out,
-                               std::vector<int64_t> &h_np, int64_t *iter_members)
+                               std::vector<int64_t> &h_np, int64_t *iter_members, const std::vector<char> &include)
 {
   const bool has_w = c->has_weight;
   const int  has_u = c->has_u ? 1 : 0;
@@ -2048,7 +2048,7 @@ static void unbind_cooperative(ahfgpu_ctx *c, int64_t nhalo, const HP &P, const 
   };
   auto rvir = [&]() {
     std::vector<char> sel(nhalo);
-    for (int64_t h = 0; h < nhalo; h++) sel[h] = h_np[h] >= P.min_part;
+    for (int64_t h = 0; h < nhalo; h++) sel[h] = include[h] && h_np[h] >= P.min_part;
     build(sel);
     if (!nact) return;
     mass_prefix();
@@ -2063,7 +2063,7 @@ static void unbind_cooperative(ahfgpu_ctx *c, int64_t nhalo, const HP &P, const 
   std::vector<char> active(nhalo);
   std::vector<int64_t> h_nrem(nhalo);
   int64_t work = 0, n_iter = 0, n_sweep = 0;
-  for (int64_t h = 0; h < nhalo; h++) active[h] = h_np[h] >= P.min_part;
+  for (int64_t h = 0; h < nhalo; h++) active[h] = include[h] && h_np[h] >= P.min_part;
   for (int iter = 1;; iter++) {
     build(active);
     if (!nact) break;
@@ -2296,22 +2296,39 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
     c->pos4 = hpos; c->mom4 = hmom;
   }
   int64_t *d_np = dalloc<int64_t>(nhalo), *d_work = dalloc<int64_t>(nhalo);
-  if (getenv("AHFGPU_UNBIND_V1")) {           // previous form: one CTA per halo (kept for A/B timing)
-    {
-      Stage st(c, "halo_unbind", tot_g);
-      LAUNCH(c, k_halo_unbind, (unsigned)nhalo, HB, 0, c->pos4, c->mom4, c->has_u ? 1 : 0, d_ctr, d_moff0, d_ng, d_members, P, c->h_scal, d_np, d_work);
-      CUDA_CHECK(cudaMemcpyAsync(h_np.data(), d_np, sizeof(int64_t) * nhalo, cudaMemcpyDeviceToHost, c->stream));
-      CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    }
-    std::vector<int64_t> h_work(nhalo);
-    CUDA_CHECK(cudaMemcpy(h_work.data(), d_work, sizeof(int64_t) * nhalo, cudaMemcpyDeviceToHost));
-    int64_t tw = 0; for (auto w : h_work) tw += w;
-    c->stage_cnt_extra["halo_unbind_iter_members"] = tw;
-  } else {
+  // U2/U3.  Hybrid: a halo up to `small_max` (16384) gathered members is unbound by ONE CTA that runs all its iterations inside one launch
+  // (k_halo_unbind); larger haloes take the cooperative multi-block pass, whose every iteration is a dozen launches and two read-backs
+  // -- right for 10^5..10^7 members, but with hundreds of small haloes the slowest of them sets the iteration count for all (256^3
+  // box with the 470 seeds of the device tree: 2.4 ms, of which 1.5 ms were launches over nearly empty lists).  The member lists of
+  // the two forms are identical, the scalars agree to rounding (fixed but different summation trees); which form serves a halo depends
+  // on its gathered count alone.  AHFGPU_UNBIND_V1: everything by one CTA per halo; AHFGPU_UNBIND_SMALL=<n>: the threshold (0: none).
+  {
     Stage st(c, "halo_unbind", tot_g);
+    const bool all_v1 = getenv("AHFGPU_UNBIND_V1") != nullptr;
+    int64_t small_max = 16384;          // measured on the 256^3 box with the 470 device-tree seeds: 0 -> 2.48 ms, 4096 -> 2.47, 16384 -> 1.36, 65536 -> 1.76, all -> 3.78 (scripts/unbind_diag.py)
+    if (getenv("AHFGPU_UNBIND_SMALL")) small_max = atoll(getenv("AHFGPU_UNBIND_SMALL"));
+    std::vector<char>    include(nhalo, 0);
+    std::vector<int32_t> small;
+    for (int64_t h = 0; h < nhalo; h++) {
+      if (all_v1 || h_ng[h] <= small_max) small.push_back((int32_t)h); else include[h] = 1;
+    }
     int64_t tw = 0;
-    unbind_cooperative(c, nhalo, P, d_ctr, d_moff0, moff0, d_ng, h_ng, d_members, tot_g, d_np, h_np, &tw);
+    if (small.size() < (size_t)nhalo) unbind_cooperative(c, nhalo, P, d_ctr, d_moff0, moff0, d_ng, h_ng, d_members, tot_g, d_np, h_np, &tw, include);
+    else { c->stage_cnt_extra["halo_unbind_iterations"] = 0; c->stage_cnt_extra["halo_unbind_mask_sweeps"] = 0; }
+    if (!small.empty()) {
+      int32_t *d_sel = dalloc<int32_t>(small.size());
+      CUDA_CHECK(cudaMemcpyAsync(d_sel, small.data(), sizeof(int32_t) * small.size(), cudaMemcpyHostToDevice, c->stream));
+      CUDA_CHECK(cudaMemsetAsync(d_work, 0, sizeof(int64_t) * nhalo, c->stream));
+      LAUNCH(c, k_halo_unbind, (unsigned)small.size(), HB, 0, c->pos4, c->mom4, c->has_u ? 1 : 0, d_ctr, d_moff0, d_ng, d_members, P, c->h_scal, d_np, d_work, d_sel);
+      std::vector<int64_t> h_work(nhalo);
+      CUDA_CHECK(cudaMemcpyAsync(h_np.data(), d_np, sizeof(int64_t) * nhalo, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_CHECK(cudaMemcpyAsync(h_work.data(), d_work, sizeof(int64_t) * nhalo, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));          // `small` was read by the copy above
+      for (int32_t h : small) tw += h_work[h];
+      ahf::dfree(d_sel);
+    }
     c->stage_cnt_extra["halo_unbind_iter_members"] = tw;
+    c->stage_cnt_extra["halo_unbind_small"] = (int64_t)small.size();
   }
   if (d_gid) {                                          // back to particle offsets and the shared particle arrays
     LAUNCH(c, k_globalize_members, nblk(tot_g, 256), 256, 0, d_members, (uint64_t)tot_g, d_gid);

@@ -848,6 +848,26 @@ k_deposit_dom(const float4 *__restrict__ pos4, const int4 *__restrict__ work, co
   }
 }
 
+// EXPERIMENT (AHFGPU_DOM_CELLSORT=1): order the particles of every tile by cell (z, y, x) before the domain deposit, to measure what
+// bank-conflict-free lanes are worth to the shared-memory atomics (the sums are integers: any order gives the same result)
+__global__ void k_cellsort_keys(const float4 *__restrict__ pos4, const uint64_t *__restrict__ keys, uint64_t n, int logL, int tbits,
+                                uint64_t *__restrict__ ck, uint32_t *__restrict__ idx)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 q = pos4[i];
+  const int sh = 32 - logL;
+  const uint32_t cx = pos_q32(q.x) >> sh, cy = pos_q32(q.y) >> sh, cz = pos_q32(q.z) >> sh;
+  const uint64_t tile = keys[i] >> (3 * (21 - tbits));
+  ck[i] = (tile << 12) | (uint64_t)(((cz & 15u) << 8) | ((cy & 15u) << 4) | (cx & 15u));
+  idx[i] = (uint32_t)i;
+}
+__global__ void k_gather_f4(const float4 *__restrict__ in, const uint32_t *__restrict__ idx, uint64_t n, float4 *__restrict__ out)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[idx[i]];
+}
+
 __global__ void k_finish_dens(const unsigned long long *__restrict__ acc, float *__restrict__ dens, int ncell, double m2d_over_scale)
 {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1712,6 +1732,19 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
     const int W = ntile + (int)(lv.npart_dep / DT_CHUNK) + 1;
     work.reserve(W);
     LAUNCH(c, k_tile_work, nblk(ntile, 256), 256, 0, nchunk.p, woff.p, ntile, work.p);
+    const float4 *dom_pos = c->pos4;
+    DevBuf<float4> pos_c;
+    if (tiles_dense && !dom_v1 && getenv("AHFGPU_DOM_CELLSORT")) {
+      const uint64_t np = c->n;
+      DevBuf<uint64_t> k0, k1; DevBuf<uint32_t> v0, v1;
+      k0.reserve(np); k1.reserve(np); v0.reserve(np); v1.reserve(np); pos_c.reserve(np);
+      LAUNCH(c, k_cellsort_keys, nblk(np, 256), 256, 0, c->pos4, c->keys, np, v.logL, tbits, k0.p, v0.p);
+      uint64_t *ks; uint32_t *vs;
+      radix_sort_pairs(c, k0.p, v0.p, k1.p, v1.p, np, ((3 * tbits + 12 + 7) / 8) * 8, &ks, &vs);
+      LAUNCH(c, k_gather_f4, nblk(np, 256), 256, 0, c->pos4, vs, np, pos_c.p);
+      dom_pos = pos_c.p;
+      k0.release(); k1.release(); v0.release(); v1.release();
+    }
     {
       Stage sk(c, lv.dense ? "deposit_dom_kernel" : "deposit_ref_kernel", lv.npart_dep, lv.dense || c->env.stages);
       Stage skl(c, lvl_name("depk", lev_id).c_str(), W, c->env.level_stages);
@@ -1725,7 +1758,7 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
         // AHFGPU_DOM_PERSIST=1: two persistent CTAs per SM striding over the items (measured slower: static striding loses the
         // hardware's dynamic balance between light and heavy tiles); default: one CTA per item
         const unsigned grid = c->env.dom_persist ? (unsigned)std::min(W, 2 * nsm) : (unsigned)W;
-#define DOM_LAUNCH(V) LAUNCH(c, k_deposit_dom<V>, grid, DT_THREADS, DD_SMEM, c->pos4, work4.p, tot.p, (int)lv.L, v.logL, acc.p, 1u, rmax)
+#define DOM_LAUNCH(V) LAUNCH(c, k_deposit_dom<V>, grid, DT_THREADS, DD_SMEM, dom_pos, work4.p, tot.p, (int)lv.L, v.logL, acc.p, 1u, rmax)
 #ifdef AHFGPU_EXPERIMENTS
         if (var == 1) DOM_LAUNCH(1); else if (var == 2) DOM_LAUNCH(2); else if (var == 3) DOM_LAUNCH(3); else if (var == 4) DOM_LAUNCH(4); else DOM_LAUNCH(0);
 #else
@@ -1746,6 +1779,7 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
         LAUNCH(c, k_deposit_runs, (unsigned)W, DR_THREADS, DR_SMEM, lv.lpos, tstart.p, work.p, (int)lv.L, v.logL, tbits, acc.p,
                tlist.p, lv.pcell, v, lv.nbr, (float)fxscale, tot.p);
     }
+    pos_c.release();
     if (lv.dense) c->stage_cnt_extra["deposit_dom_ctas"] = W;
     tstart.release(); nchunk.release(); woff.release(); bs.release(); tot.release(); work.release(); work4.release(); tlist.release(); head.release(); hs.release();
   } else if (lv.npart_dep > 0 && !(tiles_dense || tiles_sparse)) {
@@ -2215,9 +2249,14 @@ extern "C" int ahfgpu_amr_patch_stats(ahfgpu_ctx *c, int32_t lev, int64_t *niso,
     if (!l.dense && !l.nbr) AHF_FAIL("level has no neighbour table");
     const int nc = (int)l.ncell;
     int ni = 0;
-    if (nc > 0) {
+    if (nc > 0 && l.pstat_n >= 0) {                  // the table of this hierarchy is still there (a count query came first)
+      ni = (int)l.pstat_n;
+      if (stats && (int64_t)ni > stats_cap) AHF_FAIL("stats buffer too small");
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      if (stats && ni > 0) CUDA_CHECK(cudaMemcpy(stats, l.pstat, sizeof(double) * 18 * (size_t)ni, cudaMemcpyDeviceToHost));
+    } else if (nc > 0) {
       LV v = view(l);
-      DevBuf<int32_t> parent, root, diso; DevBuf<uint8_t> isroot, per; DevBuf<int> rank; DevBuf<double> acc, out, div3; DevBuf<unsigned long long> iacc;
+      DevBuf<int32_t> parent, root, diso; DevBuf<uint8_t> isroot, per; DevBuf<int> rank; DevBuf<double> acc, div3; DevBuf<unsigned long long> iacc;
       parent.reserve(nc); root.reserve(nc); diso.reserve(nc); isroot.reserve(nc); rank.reserve(nc); per.reserve((size_t)3 * nc);
       LAUNCH(c, k_patch_init, nblk(nc, 256), 256, 0, parent.p, nc);
       LAUNCH(c, k_patch_link, nblk(nc, 256), 256, 0, v, l.nbr, parent.p);
@@ -2226,19 +2265,21 @@ extern "C" int ahfgpu_amr_patch_stats(ahfgpu_ctx *c, int32_t lev, int64_t *niso,
       CUDA_CHECK(cudaMemsetAsync(per.p, 0, (size_t)3 * nc, c->stream));
       LAUNCH(c, k_patch_iso, nblk(nc, 256), 256, 0, v, l.nbr, root.p, rank.p, diso.p, per.p);
       if (stats && (int64_t)ni > stats_cap) AHF_FAIL("stats buffer too small");
-      acc.reserve((size_t)PS_ACC * ni); out.reserve((size_t)18 * ni); div3.reserve((size_t)3 * ni);
+      acc.reserve((size_t)PS_ACC * ni); div3.reserve((size_t)3 * ni);
+      double *out = dalloc<double>((size_t)18 * ni);
       iacc.reserve((size_t)PS_IACC * ni);
       CUDA_CHECK(cudaMemsetAsync(acc.p, 0, sizeof(double) * PS_ACC * ni, c->stream));
       CUDA_CHECK(cudaMemsetAsync(iacc.p, 0, sizeof(unsigned long long) * PS_IACC * ni, c->stream));
       LAUNCH(c, k_pstat_cells, nblk(nc, 256), 256, 0, v, diso.p, per.p, l.dens, acc.p, iacc.p);
       if (l.npart_dep > 0)
         LAUNCH(c, k_pstat_parts, nblk(l.npart_dep, 256), 256, 0, c->pos4, l.plist, l.pcell, (uint64_t)l.npart_dep, c->owner_level, (int)lev, diso.p, per.p, iacc.p);
-      LAUNCH(c, k_pstat_finish, nblk(ni, 128), 128, 0, acc.p, iacc.p, per.p, ni, (double)l.L, out.p, div3.p);
-      LAUNCH(c, k_pstat_extents, nblk(nc, 256), 256, 0, v, diso.p, div3.p, out.p);
-      LAUNCH(c, k_pstat_fix, nblk(ni, 128), 128, 0, ni, out.p);
+      LAUNCH(c, k_pstat_finish, nblk(ni, 128), 128, 0, acc.p, iacc.p, per.p, ni, (double)l.L, out, div3.p);
+      LAUNCH(c, k_pstat_extents, nblk(nc, 256), 256, 0, v, diso.p, div3.p, out);
+      LAUNCH(c, k_pstat_fix, nblk(ni, 128), 128, 0, ni, out);
       CUDA_CHECK(cudaStreamSynchronize(c->stream));
-      if (stats && ni > 0) CUDA_CHECK(cudaMemcpy(stats, out.p, sizeof(double) * 18 * (size_t)ni, cudaMemcpyDeviceToHost));
-      parent.release(); root.release(); diso.release(); isroot.release(); rank.release(); per.release(); acc.release(); out.release(); div3.release(); iacc.release();
+      if (stats && ni > 0) CUDA_CHECK(cudaMemcpy(stats, out, sizeof(double) * 18 * (size_t)ni, cudaMemcpyDeviceToHost));
+      ahf::dfree(l.pstat); l.pstat = out; l.pstat_n = ni;
+      parent.release(); root.release(); diso.release(); isroot.release(); rank.release(); per.release(); acc.release(); div3.release(); iacc.release();
     }
     if (niso) *niso = ni;
     return 0;

@@ -53,11 +53,16 @@ __global__ void k_keys_aos(const unsigned char *__restrict__ rec, uint64_t n, ui
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: LSD radix sort, 8-bit digits, (u64 key, u32 value) pairs, stable
+// K2: LSD radix sort, RS_BITS-bit digits, (u64 key, u32 value) pairs, stable.  8 bits (8 passes over the 63 key bits): measured against
+//   9 bits (7 passes) at 256^3: 0.153 vs 0.187 ms per scatter launch -- with 512 digits the digit runs of a 2048-pair tile are 4 pairs
+//   long and the run-by-run output no longer fills its sectors; 1.63 vs 1.80 ms for the whole sort (profiles/r2i_bench_256_n1.json)
 //   per pass: block histograms -> exclusive scan over [digit][block] -> ranked scatter
 // ------------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS   = RS_THREADS / 32;
+constexpr int RS_BITS    = 8;
+constexpr int RS_NB      = 1 << RS_BITS;             // digits per pass
+constexpr int RS_DPT     = RS_NB / RS_THREADS;       // digits per thread in the digit loops (consecutive digits)
 // pairs per thread: 8 (tile 2048, 3 CTAs/SM) or 16 (tile 4096: digit runs twice as long, so the run-by-run output fills its
 // sectors better; 128 registers, 2 CTAs/SM).  Chosen at run time in radix_sort_pairs (AHFGPU_RS_ITEMS).
 #define RS_TILE   (RS_THREADS * RS_ITEMS)
@@ -71,9 +76,11 @@ template <int RS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t *__restrict__ keys, uint64_t n, int shift,
                                                         uint32_t *__restrict__ bhist, uint32_t nblk)
 {
-  __shared__ uint32_t h[RS_HT][256];
+  __shared__ uint32_t h[RS_HT][RS_NB];
 #pragma unroll
-  for (int q = 0; q < RS_HT; q++) h[q][threadIdx.x] = 0;
+  for (int q = 0; q < RS_HT; q++)
+#pragma unroll
+    for (int d = 0; d < RS_DPT; d++) h[q][threadIdx.x + d * RS_THREADS] = 0;
   __syncthreads();
   const uint32_t t0 = blockIdx.x * RS_HT;
   const uint64_t base = (uint64_t)t0 * RS_TILE + threadIdx.x;
@@ -86,18 +93,21 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t *__restri
 #pragma unroll
   for (int i = 0; i < RS_HT * RS_ITEMS; i++) {
     const uint64_t j = base + (uint64_t)i * RS_THREADS;
-    if (j < n) atomicAdd(&h[i / RS_ITEMS][(uint32_t)(kk[i] >> shift) & 255u], 1u);
+    if (j < n) atomicAdd(&h[i / RS_ITEMS][(uint32_t)(kk[i] >> shift) & (uint32_t)(RS_NB - 1)], 1u);
   }
   __syncthreads();
 #pragma unroll
   for (int q = 0; q < RS_HT; q++)
-    if (t0 + q < nblk) bhist[(uint64_t)threadIdx.x * nblk + t0 + q] = h[q][threadIdx.x];
+    if (t0 + q < nblk) {
+#pragma unroll
+      for (int d = 0; d < RS_DPT; d++) { const int dg = threadIdx.x + d * RS_THREADS; bhist[(uint64_t)dg * nblk + t0 + q] = h[q][dg]; }
+    }
 }
 
 
 // ranked scatter.  The tile is first sorted by digit in shared memory (stable), then written out digit run by digit run so that
 // consecutive threads store consecutive addresses (a direct scatter writes 12 useful bytes per pair of 32-byte sectors).
-#define RS_SMEM (RS_TILE * 12 + RS_WARPS * 256 * 4 + 2 * 256 * 4 + 64)
+#define RS_SMEM (RS_TILE * 12 + RS_WARPS * RS_NB * 4 + 2 * RS_NB * 4 + 64)
 template <int RS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS, RS_ITEMS == 8 ? 4 : 2) k_rs_scatter(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
                                                            uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, uint64_t n,
@@ -106,11 +116,11 @@ __global__ void __launch_bounds__(RS_THREADS, RS_ITEMS == 8 ? 4 : 2) k_rs_scatte
   extern __shared__ __align__(16) unsigned char rsm[];
   uint64_t *sk = reinterpret_cast<uint64_t *>(rsm);                                  // [RS_TILE]
   uint32_t *sv = reinterpret_cast<uint32_t *>(rsm + RS_TILE * 8);                    // [RS_TILE]
-  uint32_t (*whist)[256] = reinterpret_cast<uint32_t (*)[256]>(rsm + RS_TILE * 12);  // [RS_WARPS][256]
-  uint32_t *gbase = reinterpret_cast<uint32_t *>(rsm + RS_TILE * 12 + RS_WARPS * 256 * 4);   // [256] global address of tile slot 0 of the digit's run
-  uint32_t *wtot  = gbase + 256;                                                     // [RS_WARPS] scratch of the digit scan
+  uint32_t (*whist)[RS_NB] = reinterpret_cast<uint32_t (*)[RS_NB]>(rsm + RS_TILE * 12);  // [RS_WARPS][RS_NB]
+  uint32_t *gbase = reinterpret_cast<uint32_t *>(rsm + RS_TILE * 12 + RS_WARPS * RS_NB * 4);   // [RS_NB] global address of tile slot 0 of the digit's run
+  uint32_t *wtot  = gbase + RS_NB;                                                   // [RS_WARPS] scratch of the digit scan
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&whist[0][0])[i] = 0;
+  for (int i = threadIdx.x; i < RS_WARPS * RS_NB; i += RS_THREADS) (&whist[0][0])[i] = 0;
   __syncthreads();
   const uint64_t tile0 = (uint64_t)blockIdx.x * RS_TILE, base = tile0 + (uint64_t)w * RS_WCHUNK;
   uint64_t k[RS_ITEMS];
@@ -127,8 +137,8 @@ __global__ void __launch_bounds__(RS_THREADS, RS_ITEMS == 8 ? 4 : 2) k_rs_scatte
   for (int s = 0; s < RS_ITEMS; s++) {
     uint64_t j = base + (uint64_t)s * 32 + lane;
     bool     valid = j < n;
-    uint32_t d  = (uint32_t)(k[s] >> shift) & 255u;
-    uint32_t dd = valid ? d : (256u + lane);
+    uint32_t d  = (uint32_t)(k[s] >> shift) & (uint32_t)(RS_NB - 1);
+    uint32_t dd = valid ? d : ((uint32_t)RS_NB + lane);
     uint32_t peers  = __match_any_sync(0xffffffffu, dd);
     int      leader = __ffs(peers) - 1;
     uint32_t r = __popc(peers & ((1u << lane) - 1u));
@@ -140,12 +150,19 @@ __global__ void __launch_bounds__(RS_THREADS, RS_ITEMS == 8 ? 4 : 2) k_rs_scatte
   }
   __syncthreads();
   {
-    const int t = threadIdx.x;   // digit: counts of the warps -> exclusive offsets inside the digit, tile count of the digit
-    uint32_t  run = 0;
+    // thread t owns the RS_DPT consecutive digits t*RS_DPT ...: counts of the warps -> exclusive offsets inside the digit, then an
+    // exclusive scan over all digits: where the digit's run starts inside the tile
+    const int t = threadIdx.x;
+    uint32_t  run[RS_DPT], tot = 0;
 #pragma unroll
-    for (int q = 0; q < RS_WARPS; q++) { uint32_t c = whist[q][t]; whist[q][t] = run; run += c; }
-    // exclusive scan of the 256 digit counts: where the digit's run starts inside the tile
-    uint32_t inc = run;
+    for (int d = 0; d < RS_DPT; d++) {
+      const int dg = t * RS_DPT + d;
+      uint32_t  r = 0;
+#pragma unroll
+      for (int q = 0; q < RS_WARPS; q++) { uint32_t c = whist[q][dg]; whist[q][dg] = r; r += c; }
+      run[d] = r; tot += r;
+    }
+    uint32_t inc = tot;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
     if (lane == 31) wtot[w] = inc;
@@ -153,17 +170,22 @@ __global__ void __launch_bounds__(RS_THREADS, RS_ITEMS == 8 ? 4 : 2) k_rs_scatte
     uint32_t wb = 0;
 #pragma unroll
     for (int q = 0; q < RS_WARPS; q++) if (q < w) wb += wtot[q];
-    const uint32_t dstart = wb + inc - run;
+    uint32_t dstart = wb + inc - tot;
 #pragma unroll
-    for (int q = 0; q < RS_WARPS; q++) whist[q][t] += dstart;
-    gbase[t] = bscan[(uint64_t)t * nblk + blockIdx.x] - dstart;
+    for (int d = 0; d < RS_DPT; d++) {
+      const int dg = t * RS_DPT + d;
+#pragma unroll
+      for (int q = 0; q < RS_WARPS; q++) whist[q][dg] += dstart;
+      gbase[dg] = bscan[(uint64_t)dg * nblk + blockIdx.x] - dstart;
+      dstart += run[d];
+    }
   }
   __syncthreads();
 #pragma unroll
   for (int s = 0; s < RS_ITEMS; s++) {
     uint64_t j = base + (uint64_t)s * 32 + lane;
     if (j < n) {
-      uint32_t d = (uint32_t)(k[s] >> shift) & 255u;
+      uint32_t d = (uint32_t)(k[s] >> shift) & (uint32_t)(RS_NB - 1);
       uint32_t lp = whist[w][d] + rank[s];
       sk[lp] = k[s]; sv[lp] = v[s];
     }
@@ -173,7 +195,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_ITEMS == 8 ? 4 : 2) k_rs_scatte
 #pragma unroll 4
   for (int i = threadIdx.x; i < nv; i += RS_THREADS) {
     const uint64_t kk = sk[i];
-    const uint32_t p = gbase[(uint32_t)(kk >> shift) & 255u] + (uint32_t)i;
+    const uint32_t p = gbase[(uint32_t)(kk >> shift) & (uint32_t)(RS_NB - 1)] + (uint32_t)i;
     kout[p] = kk; vout[p] = sv[i];
   }
 }
@@ -185,14 +207,14 @@ static void radix_sort_pairs_t(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, ui
   const uint32_t nblk = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
   DevBuf<uint32_t> bh;
   DevBuf<int>      bs;
-  bh.reserve((size_t)256 * nblk);
+  bh.reserve((size_t)RS_NB * nblk);
   uint64_t *ki = keys, *ko = keys_tmp;
   uint32_t *vi = vals, *vo = vals_tmp;
   // AHFGPU_KERNEL_STAGES=1 (bench.py's instrumented passes): event pair around every scatter launch, the largest kernel share of a pass
   const bool ktimer = getenv("AHFGPU_KERNEL_STAGES") != nullptr;
-  for (int shift = first_bit; shift < key_bits; shift += 8) {          // bits below first_bit are left to the caller (ties)
+  for (int shift = first_bit; shift < key_bits; shift += RS_BITS) {    // bits below first_bit are left to the caller (ties)
     LAUNCH(c, k_rs_hist<RS_ITEMS>, (nblk + RS_HT - 1) / RS_HT, RS_THREADS, 0, ki, n, shift, bh.p, nblk);
-    exclusive_scan_async<int>(c, (const int *)bh.p, (int *)bh.p, (uint64_t)256 * nblk, nullptr, bs);   // in place: each tile is read before it is written
+    exclusive_scan_async<int>(c, (const int *)bh.p, (int *)bh.p, (uint64_t)RS_NB * nblk, nullptr, bs);   // in place: each tile is read before it is written
     {
       Stage sk(c, "rs_scatter_kernel", (int64_t)n, ktimer);
       LAUNCH(c, k_rs_scatter<RS_ITEMS>, nblk, RS_THREADS, RS_SMEM, ki, vi, ko, vo, n, shift, bh.p, nblk);
@@ -203,6 +225,9 @@ static void radix_sort_pairs_t(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, ui
   bh.release(); bs.release();                       // stream-ordered block cache: no host sync needed
   *keys_sorted = ki; *vals_sorted = vi;
 }
+
+// number of passes radix_sort_pairs will make (callers that want the result in a particular buffer pick the start buffer by parity)
+int radix_sort_passes(int key_bits, int first_bit) { int p = 0; for (int s = first_bit; s < key_bits; s += RS_BITS) p++; return p; }
 
 // per-DEVICE setup of the sort kernels and the Hilbert table (called once per device from ahfgpu_init)
 void sfc_device_init()
@@ -220,6 +245,7 @@ void sfc_device_init()
   CUDA_CHECK(cudaMemcpyToSymbol(g_hil_tab3, h.data(), h.size() * sizeof(uint16_t)));
 }
 
+int radix_sort_passes(int key_bits, int first_bit);
 void radix_sort_pairs(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, uint64_t n,
                       int key_bits, uint64_t **keys_sorted, uint32_t **vals_sorted, int first_bit)
 {
@@ -319,14 +345,18 @@ void sfc_sort_resident(ahfgpu_ctx *c, uint64_t *keys_out, uint32_t *order_out)
   DevBuf<uint32_t> v1;
   k1.reserve(n); v1.reserve(n);
   const unsigned nb = (unsigned)((n + 255) / 256);
+  // an odd number of passes ends in the OTHER buffer: start in the scratch pair then, so that the result lands in keys / order
+  const bool odd = (radix_sort_passes(63, 0) & 1) != 0;
+  uint64_t *kA = odd ? k1.p : c->keys, *kB = odd ? c->keys : k1.p;
+  uint32_t *vA = odd ? v1.p : c->order, *vB = odd ? c->order : v1.p;
   {
     Stage st(c, "keys", (int64_t)n);
-    if (n) { upload_hil_tab3(); LAUNCH(c, k_keys_soa_tab, keys_tab_grid(n), KT_THREADS, 0, c->in_pos, (uint64_t)0, n, c->keys, c->order); }
+    if (n) { upload_hil_tab3(); LAUNCH(c, k_keys_soa_tab, keys_tab_grid(n), KT_THREADS, 0, c->in_pos, (uint64_t)0, n, kA, vA); }
   }
   uint64_t *ks; uint32_t *vs;
   {
     Stage st(c, "sort", (int64_t)n);
-    radix_sort_pairs(c, c->keys, c->order, k1.p, v1.p, n, 63, &ks, &vs);
+    radix_sort_pairs(c, kA, vA, kB, vB, n, 63, &ks, &vs);
     if (ks != c->keys) {
       CUDA_CHECK(cudaMemcpyAsync(c->keys, ks, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
       CUDA_CHECK(cudaMemcpyAsync(c->order, vs, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
@@ -403,6 +433,9 @@ void sfc_sort_soa_async(ahfgpu_ctx *c, const float *pos3, const float *mom3, con
   CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
   constexpr int NCH = 4;
   upload_hil_tab3();
+  const bool odd = (radix_sort_passes(63, 0) & 1) != 0;      // see sfc_sort_resident
+  uint64_t *kA = odd ? k1.p : c->keys, *kB = odd ? c->keys : k1.p;
+  uint32_t *vA = odd ? v1.p : c->order, *vB = odd ? c->order : v1.p;
   const uint64_t per = ((n + NCH - 1) / NCH + 255) & ~255ull;
   {
     Stage st(c, "keys", (int64_t)n);
@@ -411,7 +444,7 @@ void sfc_sort_soa_async(ahfgpu_ctx *c, const float *pos3, const float *mom3, con
       if (i1 > i0) CUDA_CHECK(cudaMemcpyAsync(c->in_pos + 3 * i0, pos3 + 3 * i0, 3 * (i1 - i0) * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
       CUDA_CHECK(cudaEventRecord(c->ev_copy[q], c->copy_stream));
       CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_copy[q], 0));
-      if (i1 > i0) LAUNCH(c, k_keys_soa_tab, keys_tab_grid(i1 - i0), KT_THREADS, 0, c->in_pos, i0, i1, c->keys, c->order);
+      if (i1 > i0) LAUNCH(c, k_keys_soa_tab, keys_tab_grid(i1 - i0), KT_THREADS, 0, c->in_pos, i0, i1, kA, vA);
     }
   }
   if (w) CUDA_CHECK(cudaMemcpyAsync(c->in_w, w, n * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
@@ -421,7 +454,7 @@ void sfc_sort_soa_async(ahfgpu_ctx *c, const float *pos3, const float *mom3, con
   uint64_t *ks; uint32_t *vs;
   {
     Stage st(c, "sort", (int64_t)n);
-    radix_sort_pairs(c, c->keys, c->order, k1.p, v1.p, n, 63, &ks, &vs);
+    radix_sort_pairs(c, kA, vA, kB, vB, n, 63, &ks, &vs);
     if (ks != c->keys) {
       CUDA_CHECK(cudaMemcpyAsync(c->keys, ks, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
       CUDA_CHECK(cudaMemcpyAsync(c->order, vs, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));

@@ -2,15 +2,17 @@
 """bench.py -- the AHF particle hot path on B200: Hilbert keys + sort, TSC deposit on the domain grid and every
 refinement level, refinement flags / next level / relink, per-halo gather + radial sort + unbinding + profiles.
 
-One "step" = one pass of the whole path over one synthetic box (BASELINE.json configs[1]: 256^3 particles,
-LgridDomain 256, AHF.input-example settings).  Prints ONE JSON line (rank 0).
+One "step" = one pass of the whole path over one synthetic box.  Prints ONE JSON line (rank 0).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--n1d 256] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--n1d L] [--mode auto|boxes|slab] [--impl ours|reference]
 
-N > 1 (torchrun): the path is embarrassingly parallel over independent boxes; every rank processes its own box
-(different seed) on its own GPU, no data-path collective -> "scaling": "weak".
---impl reference: the reference's own CPU implementation (oracle/_ref/ahf_ref = unmodified NegriAndrea/AHF with
-timing hooks) on a bounded sample (128^3 box of the same generator), all host threads, rank 0 only.
+N = 1: BASELINE.json configs[1] -- 256^3 particles, LgridDomain 256, AHF.input-example settings, halo seeds from the DEVICE hierarchy
+       (patch labels + RefCentre tables on the GPU, tree on the host, computed once before the timed passes).
+N > 1 (torchrun): BASELINE.json configs[2] -- ONE 512^3 box split over the N GPUs (SFC slabs + ghost shell, NCCL), "scaling": "strong".
+       (--mode boxes: one independent 256^3 box per GPU, no collective, "weak" -- the replica number of round 1.)
+--impl reference: the reference's own CPU implementation (oracle/_ref/ahf_ref = unmodified NegriAndrea/AHF with timing hooks) on the
+       box's host cores, rank 0 only: the 256^3 box of the N = 1 arm (for N > 1 the same 256^3 box as a bounded sample of the 512^3
+       workload), OMP_NUM_THREADS = nproc, best of min(K, 3) runs, plus one run with 1 thread in `detail`.
 """
 from __future__ import annotations
 
@@ -130,21 +132,26 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(self.samples), "source": "nvml"}
 
 
+_REF_CASES = {}
+
+
 def run_reference_sample(n1d: int, seed: int, threads: int | None):
-    """Unmodified reference on a bounded sample; returns (pps, detail dict)."""
+    """Unmodified reference on one box of the bench generator; returns (pps, detail dict).  The snapshot is written once per (n1d, seed)."""
     from ahf_b200 import synth
     from oracle import oracle as O
-    box = synth.make_box(n1d, seed=seed)
-    work = tempfile.mkdtemp(prefix="ahf_refbench_")
-    try:
-        inp = synth.write_reference_case(box, work)
-        t0 = time.perf_counter()
-        t = O.run_reference(inp, dump_dir=None, threads=threads)
-        wall = time.perf_counter() - t0
-    finally:
-        shutil.rmtree(work, ignore_errors=True)
+    import atexit
+    if (n1d, seed) not in _REF_CASES:
+        box = synth.make_box(n1d, seed=seed)
+        work = tempfile.mkdtemp(prefix="ahf_refbench_")
+        atexit.register(shutil.rmtree, work, ignore_errors=True)
+        _REF_CASES[(n1d, seed)] = (synth.write_reference_case(box, work), box.npart)
+        del box
+    inp, npart = _REF_CASES[(n1d, seed)]
+    t0 = time.perf_counter()
+    t = O.run_reference(inp, dump_dir=None, threads=threads)
+    wall = time.perf_counter() - t0
     path_s = t["keys"] + t["sort"] + t["ll"] + t["deposit"] + t["refine"] + t["relink"] + t["halo_loop"]
-    return box.npart / path_s, dict(t, wall_s=wall, path_s=path_s, npart=box.npart)
+    return npart / path_s, dict(t, wall_s=wall, path_s=path_s, npart=npart)
 
 
 def run_port_sample(n1d: int, seed: int):
@@ -166,68 +173,127 @@ def run_port_sample(n1d: int, seed: int):
 
 
 def bench_slab(args, rank, world, local_rank, config):
-    """ONE box over all ranks (strong scaling): time = exchange + sort, mesh with all-reduce, all-gather + halo pass."""
+    """ONE box over all ranks (strong scaling): a step = exchange (keys, block histogram all-reduce, partition, NCCL send/recv to owners and
+    ghost holders, the one sort) + mesh on own cells and ghost shell (per level one small all-gather and one all-gather of row keys) + halo pass
+    of the haloes centred in the rank's key range.  `value`: the rank's file share already resident in HBM; `e2e`: pinned host share uploaded
+    and every result of the rank's haloes (scalars, member lists as global particle indices, profiles) fetched, every step."""
     import torch
     import torch.distributed as dist
     from ahf_b200 import ahf, multigpu, synth
-    # every rank generates only its own share of the box (a z-slab of the lattice + every world-th clump)
+    dev = torch.device("cuda", local_rank)
+    # every rank generates only its own share of the box (a z-slab of the lattice + every world-th clump): what it would read from its file
     pos_np, mom_np, cl, boxsize, pmass = synth.make_box_slice(args.n1d, rank, world, seed=43)
     c, r, seed = synth.halo_seeds_from(cl["centres"], cl["npart"], cl["scale"], boxsize)
-    # pinned host buffers: what a reader would fill; the upload is part of every step
+    n_loc = int(pos_np.shape[0])
     pos_l = torch.empty(pos_np.shape, dtype=torch.float32, pin_memory=True); pos_l.numpy()[:] = pos_np
     mom_l = torch.empty(mom_np.shape, dtype=torch.float32, pin_memory=True); mom_l.numpy()[:] = mom_np
-    del pos_np, mom_np
-    nl = torch.tensor([pos_l.shape[0]], device="cuda", dtype=torch.int64)
+    counts = torch.zeros(world, device=dev, dtype=torch.int64); counts[rank] = n_loc
     if world > 1:
-        dist.all_reduce(nl)
-    n = int(nl.item())
+        dist.all_reduce(counts)
+    counts = counts.cpu().numpy()
+    n = int(counts.sum()); id_base = int(counts[:rank].sum())
     pmass = 0.3 * synth.RHOC0 * boxsize ** 3 / n
     par = ahf.make_params(boxsize=boxsize, pmass=pmass, lgrid_dom=args.n1d, device=local_rank)
-    sb = multigpu.SlabBox(par, rank, world, local_rank)
+    nid = multigpu.nccl_id_via_torch(rank, dev) if world > 1 else ahf.nccl_unique_id()
+    sb = multigpu.SlabRank(par, rank, world, local_rank, nccl_id=nid)
+    g = sb.g
+    g.upload(pos_np, mom_np)
+    del pos_np, mom_np
 
-    def step():
-        sb.distribute(pos_l, mom_l)
+    def barrier():
+        g.synchronize(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        st = {}
+        sb.redistribute(id_base=id_base)
+        st.update({k: g.stage_ms(k) for k in ("slab_keys", "slab_histogram_allreduce", "slab_decompose", "slab_partition", "slab_exchange", "keys", "sort", "gather")})
         sb.build_amr()
-        sb.gather_box()
-        return sb.construct_halos(c, r, seed)
+        st.update({k: g.stage_ms(k) for k in ("amr_total", "ll", "deposit", "deposit_dom_kernel", "flag", "refine", "relink", "rows_allgather", "level_allgather")})
+        st["deposit_particles"] = g.stage_count("deposit")
+        mine, _ = sb.construct_halos(c, r, seed, fetch=False)
+        st.update({k: g.stage_ms(k) for k in ("halo_gather", "halo_sort", "halo_unbind", "halo_profiles")})
+        st["halo_gathered"] = g.stage_count("halo_gathered"); st["halos_mine"] = len(mine)
+        return st
 
+    def step_e2e():
+        sb.distribute_ptr(pos_l.data_ptr(), mom_l.data_ptr(), n_loc, id_base=id_base)
+        sb.build_amr()
+        mine, res = sb.construct_halos(c, r, seed, fetch=True)
+        return mine, res
+
+    os.environ["AHFGPU_STAGES"] = "0"
     for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    tphase = {}
-    def timed(name, fn):
-        t0 = time.perf_counter(); out = fn(); sb.g.synchronize(); sb.gh.synchronize(); torch.cuda.synchronize()
-        tphase[name] = tphase.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
-        return out
-    def step():           # noqa: F811 -- same sequence with per-phase wall clocks
-        timed("exchange+sort", lambda: sb.distribute(pos_l, mom_l))
-        timed("mesh", sb.build_amr)
-        timed("allgather", sb.gather_box)
-        return timed("halos", lambda: sb.construct_halos(c, r, seed))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(); e0.record()
+        step_resident()
+    sampler = ClockSampler(local_rank); sampler.start()
+    barrier()
+    l0 = g.launches()
+    g.event_record(0)
+    timed = [step_resident() for _ in range(args.steps)]
+    g.event_record(1)
+    barrier()
+    ms_res = g.event_elapsed_ms(0, 1) / args.steps
+    launches = g.launches() - l0
+    info = g.slab_info()
+    os.environ["AHFGPU_STAGES"] = "1"
+    stages = [step_resident() for _ in range(2)][1:]
+    os.environ["AHFGPU_STAGES"] = "0"
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    g.event_record(2)
     for _ in range(args.steps):
-        scal = step()
-    sb.g.synchronize(); sb.gh.synchronize(); torch.cuda.synchronize(); e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
+        mine, res = step_e2e()
+    g.event_record(3)
+    barrier()
+    ms_e2e = g.event_elapsed_ms(2, 3) / args.steps
+    os.environ.pop("AHFGPU_STAGES", None)
+    clocks = sampler.stop()
+    d2h = int(sum(v.nbytes for v in res.values() if hasattr(v, "nbytes")))
+    nh_ok = int((res["scal"][:, 9] >= par.min_part).sum())
+    st = {k: float(np.mean([q[k] for q in stages])) for k in stages[0]}
+    st["deposit_dom_kernel"] = float(np.mean([t["deposit_dom_kernel"] for t in timed]))
+    # per-rank facts: maxima / sums over the ranks
+    loc = torch.tensor([ms_res, ms_e2e, st["slab_exchange"], st["slab_histogram_allreduce"], max(st["rows_allgather"], 0.0), max(st["level_allgather"], 0.0),
+                        st["amr_total"], st["halo_gather"] + st["halo_sort"] + st["halo_unbind"] + st["halo_profiles"], float(info["resident"]),
+                        st["keys"] + st["sort"] + st["gather"], st["slab_keys"] + st["slab_decompose"] + st["slab_partition"]], device=dev, dtype=torch.float64)
+    mx = loc.clone(); sm = torch.tensor([float(info["resident"]), float(d2h), float(nh_ok), float(launches), st["halo_gathered"], st["deposit_particles"]], device=dev, dtype=torch.float64)
+    mn = loc.clone()
     if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t[0])
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX); dist.all_reduce(mn, op=dist.ReduceOp.MIN); dist.all_reduce(sm)
+    ms_res, ms_e2e = float(mx[0]), float(mx[1])
     if rank == 0:
-        config = dict(config, workload=config["workload"].replace("seed 43+rank", "seed 43"), n_particles_total=n,
-                      parallelism=f"one box, {world} SFC slabs: all-to-all exchange, NCCL all-reduce of level accumulators, all-gather for the halo pass")
+        peak, peak_src = measured_peak_gbs()
+        C0 = args.n1d ** 3
+        dep_bytes = 16.0 * info["resident"] + 4.0 * C0
+        achieved = dep_bytes / (st["deposit_dom_kernel"] * 1e-3) / 1e9
+        colls = {"particle exchange (ncclSend/ncclRecv, owners + ghost holders)": float(mx[2]), "block histogram (ncclAllReduce)": float(mx[3]),
+                 "row keys per level (grouped ncclBroadcast)": float(mx[4]), "per-level scalars (ncclAllGather)": float(mx[5])}
+        config = dict(config, workload=config["workload"].replace("seed 43+rank", "seed 43, generated per rank as its file share"), n_particles_total=n,
+                      parallelism=f"ONE box over {world} GPU(s): Hilbert-block slabs with equal particle counts, ghost shell of {info['shell_blocks']} blocks "
+                                  f"(2^-{info['decomp_bits']} box each, >= 8 domain cells and >= the largest gathering radius) sent as particles in the one "
+                                  "exchange; per level one scalar all-gather + one all-gather of row keys; haloes served by the owner of their centre")
         config.pop("n_particles_per_gpu", None)
-        emit(({"metric": METRIC, "value": n / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                          "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                          "dtype": "f32 particles, u32/u64 fixed-point deposit, f64 halo arithmetic", "data": "synthetic", "config": config,
-                          "mode": "slab", "note": "host->device upload of the rank's file-order slice is inside the timed step",
-                          "levels": sb.g.nlevels(), "halos_ge_minpart": int((scal[:, 9] >= par.min_part).sum()),
-                          "phases_ms_rank0": {k: v / args.steps for k, v in tphase.items()},
-                          "mesh_stages_ms_rank0": {k: sb.g.stage_ms(k) for k in ("amr_total", "ll", "deposit", "deposit_dom_kernel", "allreduce", "flag", "refine", "relink")},
-                          "mesh_stages_host_wall_ms_rank0": {k: sb.g.stage_ms(k + "@wall") for k in ("amr_total", "deposit", "allreduce", "flag", "refine", "relink")}}))
+        line = {"metric": METRIC, "value": n / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_res, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32 particles, u32/u64 fixed-point deposit, f64 halo arithmetic", "data": "synthetic", "config": config, "mode": "slab",
+                "e2e": {"value": n / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": 24 * n + 56 * len(r) * world,
+                        "d2h_bytes_per_step": int(sm[1]), "returns": "per rank: scalars, member lists (global particle indices) and profiles of the haloes it serves"},
+                "gpu_launches": int(sm[3]), "clocks": clocks,
+                "roofline": {"kernel": "TSC deposit, domain level (k_deposit_dom), rank 0", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes": dep_bytes, "kernel_ms": st["deposit_dom_kernel"]},
+                "limiting_collective": max(colls, key=colls.get), "collectives_ms_max_over_ranks": colls,
+                "phases_ms_max_over_ranks": {"decompose (keys, histogram, partition)": float(mx[10]), "exchange": float(mx[2]), "sort (keys+radix+gather)": float(mx[9]),
+                                             "mesh": float(mx[6]), "halo pass": float(mx[7])},
+                "phases_ms_min_over_ranks": {"mesh": float(mn[6]), "halo pass": float(mn[7]), "sort (keys+radix+gather)": float(mn[9])},
+                "balance": {"resident_particles_max": float(mx[8]), "resident_particles_min": float(mn[8]), "resident_particles_sum": float(sm[0]),
+                            "ghost_overhead": float(sm[0]) / n - 1.0, "own_particles_rank0": info["own_hi"] - info["own_lo"]},
+                "stages_ms_rank0": {k: v for k, v in st.items() if k not in ("deposit_particles", "halo_gathered", "halos_mine")},
+                "throughput": {"levels": info["levels"], "halos_in": len(r), "halos_ge_minpart": int(sm[2]), "halo_gathered_particles": float(sm[4]),
+                               "deposit_particles_all_levels_incl_ghosts": float(sm[5])}}
+        emit(line)
     sb.close()
     if world > 1:
         dist.destroy_process_group()
@@ -239,19 +305,24 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--n1d", type=int, default=256)
+    ap.add_argument("--n1d", type=int, default=0, help="particles per dimension (default: 256 on one GPU / per box, 512 for ONE box over several GPUs)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ref-n1d", type=int, default=128)
+    ap.add_argument("--ref-n1d", type=int, default=256, help="box of the reference arm / cpu_baseline leg (default: the N = 1 workload itself)")
+    ap.add_argument("--seeds", default="device", choices=["device", "generator"], help="halo seeds of the N = 1 arm: from the device hierarchy (default) or the generator's clump centres")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print the per-stage table to stderr")
-    ap.add_argument("--mode", default="boxes", choices=["boxes", "slab"],
-                    help="N>1: 'boxes' = one independent box per GPU (weak, no collective; default); 'slab' = ONE box of --n1d^3 particles split "
-                         "into SFC slabs over the GPUs (all-to-all exchange, NCCL all-reduce of the level accumulators, all-gather for the halo pass)")
+    ap.add_argument("--mode", default="auto", choices=["auto", "boxes", "slab"],
+                    help="'slab' = ONE box of --n1d^3 particles split into SFC slabs over the GPUs (default for N > 1, strong scaling); "
+                         "'boxes' = one independent box per GPU (default for N = 1; weak, no collective)")
     args = ap.parse_args()
     claim_stdout()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.mode == "auto":
+        args.mode = "slab" if max(world, args.gpus) > 1 else "boxes"
+    if args.n1d <= 0:
+        args.n1d = 512 if args.mode == "slab" else 256
     config = {"workload": f"synthetic {args.n1d}^3-particle box (jittered lattice + Plummer clumps, seed 43+rank), LgridDomain {args.n1d}, "
                           "AHF.input-example settings (NperDomCell 2.0, NperRefCell 2.5, VescTune 1.5, NminPerHalo 20, Dvir 200)",
               "n_particles_per_gpu": args.n1d ** 3, "lgrid_domain": args.n1d,
@@ -265,25 +336,32 @@ def main():
         from oracle import oracle as O
         nthreads = os.cpu_count() or 1
         have_ref = os.path.exists(O.REF_BIN)
-        vals = []
-        detail = {}
-        for i in range(args.warmup + args.steps):
-            if have_ref:
-                v, detail = run_reference_sample(args.ref_n1d, 43, nthreads)
-            else:
-                v, detail = run_port_sample(min(args.ref_n1d, 64), 43)
-            if i >= args.warmup:
-                vals.append(v)
-        val = float(np.mean(vals))
-        sample = (f"{args.ref_n1d}^3 box of the same generator per step (bounded sample of the {args.n1d}^3 workload); "
-                  "time = keys+qsort+ll+deposit(all levels, as the reference does them: twice)+refine+relink+halo loop")
-        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": 1e3 * detail.get("path_s", 0.0), "higher_is_better": True, "scaling": "weak",
+        ref_n1d = args.ref_n1d if have_ref else min(args.ref_n1d, 64)
+        nrun = max(1, min(args.steps, 3))               # a 256^3 pass of the reference is about 25 s of wall clock
+        vals, details = [], []
+        for i in range(nrun):
+            v, d = run_reference_sample(ref_n1d, 43, nthreads) if have_ref else run_port_sample(ref_n1d, 43)
+            vals.append(v); details.append(d)
+        one = None
+        if have_ref:
+            v1, d1 = run_reference_sample(ref_n1d, 43, 1)
+            one = dict(d1, value=v1)
+        val = float(max(vals))                           # best of nrun
+        best = details[int(np.argmax(vals))]
+        same = (ref_n1d == args.n1d)
+        sample = (f"{ref_n1d}^3 box of the same generator (seed 43), " + ("the configuration of the GPU arm itself" if same else f"a bounded sample of the {args.n1d}^3 workload")
+                  + f"; OMP_NUM_THREADS={nthreads}, best of {nrun} run(s), no warm-up run (the CPU arm has no warm-up effects worth a 25 s pass); "
+                  "time = keys+qsort+ll+deposit(all levels, as the reference does them: twice)+refine+relink+halo loop from hook timers inside the unmodified binary")
+        config = dict(config, reference_arm_box=f"{ref_n1d}^3", reference_arm_same_config=same)
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": nrun, "steps_requested": args.steps,
+                "warmup": 0, "warmup_requested": args.warmup, "ms_per_step": 1e3 * best.get("path_s", 0.0), "higher_is_better": True,
+                "scaling": "strong" if args.mode == "slab" else "weak",
                 "vs_baseline": None, "dtype": "f32 particles / f64 halo arithmetic", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads if have_ref else 1,
                                  "kind": "reference" if have_ref else "port", "sample": sample},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "detail": detail}
+                "detail": {"runs_pps": vals, "best": best, "one_thread": one,
+                           "note": "only the halo loop, zero_dens and the gathering-radius loop are OpenMP-parallel in the reference's default build (SURVEY 2.1): the thread count barely matters"}}
         emit(line)
         return 0
 
@@ -301,12 +379,24 @@ def main():
         return bench_slab(args, rank, world, local_rank, config)
     box = synth.make_box(args.n1d, seed=43 + rank)
     n = box.npart
-    centres, rad, seednp = synth.halo_seeds(box)
     par = ahf.make_params(boxsize=box.boxsize, pmass=box.pmass, lgrid_dom=args.n1d, device=local_rank)
     g = ahf.AhfGpu(par)
     # pinned host buffers for the end-to-end leg
     hpos = torch.empty((n, 3), dtype=torch.float32, pin_memory=True); hpos.numpy()[:] = box.pos
     hmom = torch.empty((n, 3), dtype=torch.float32, pin_memory=True); hmom.numpy()[:] = box.mom
+    horder = torch.empty((n,), dtype=torch.int32, pin_memory=True)       # sorted offset -> input index: what a caller needs to read the member lists
+    # halo seeds: what AHF's tree stage hands to the halo loop.  Default: from OUR hierarchy on the device (patch labels + RefCentre tables
+    # on the GPU, analyseRef / spatialRef2halos on the host), computed once here; --seeds generator: the generator's clump centres
+    seeds_ms = None
+    if args.seeds == "device":
+        g.upload(box.pos, box.mom); g.sfc_sort_resident(); g.build_amr()
+        g.halo_seeds(3.0 / box.boxsize)                                   # warm
+        t0 = time.perf_counter()
+        hs = g.halo_seeds(3.0 / box.boxsize)
+        seeds_ms = 1e3 * (time.perf_counter() - t0)
+        centres, rad, seednp = np.ascontiguousarray(hs["pos"]), np.ascontiguousarray(hs["gather_rad"]), np.ascontiguousarray(hs["npart"], np.int64)
+    else:
+        centres, rad, seednp = synth.halo_seeds(box)
 
     def barrier():
         g.synchronize(); torch.cuda.synchronize()
@@ -331,11 +421,19 @@ def main():
         st["halo_final_members"] = g.stage_count("halo_final_members")
         return st
 
+    pinned = {}                                                        # result buffers of the end-to-end leg: pinned, sized after the first pass
+
     def step_e2e():
         g.sfc_sort_async_ptr(hpos.data_ptr(), hmom.data_ptr(), n)      # momenta travel behind the sort and the hierarchy build
         g.build_amr()
         g.construct_halos(centres, rad, seednp, fetch=False)
-        return g.fetch_halos(len(rad), scal_only=True)["scal"]
+        res = g.fetch_halos(len(rad), bufs={k: v.numpy() for k, v in pinned.items()})   # scalars, member lists, profiles: everything the catalogue writers read
+        if not pinned:
+            for k, v in res.items():
+                if k in ("scal", "members", "prof"):
+                    pinned[k] = torch.empty((int(v.size * 1.25) + 1024,), dtype=torch.float64 if v.dtype == np.float64 else torch.int64, pin_memory=True)
+        g._chk(g._L.ahfgpu_particle_ids(g._h, horder.data_ptr()))      # + the permutation that ties member offsets to the caller's particles
+        return res
 
     # ---- HBM-resident timing
     g.upload(box.pos, box.mom)
@@ -365,7 +463,9 @@ def main():
     barrier()
     g.event_record(2)
     for _ in range(args.steps):
-        scal = step_e2e()
+        e2e_res = step_e2e()
+    scal = e2e_res["scal"]
+    d2h_bytes = int(sum(v.nbytes for v in e2e_res.values() if hasattr(v, "nbytes"))) + 4 * n
     g.event_record(3)
     barrier()
     ms_e2e = g.event_elapsed_ms(2, 3) / args.steps
@@ -415,7 +515,10 @@ def main():
         "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 particles, u32/u64 fixed-point deposit, f64 halo arithmetic", "data": "synthetic", "config": config,
         "e2e": {"value": world * n / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": 24 * n + 32 * len(rad) + 8 * len(rad),
-                "d2h_bytes_per_step": int(scal.nbytes)},
+                "d2h_bytes_per_step": d2h_bytes,
+                "returns": "halo scalars (64 doubles each), member lists, profiles (25 columns per bin) and the sorted-offset -> input-index permutation"},
+        "halo_seeds": {"source": args.seeds, "n": int(len(rad)), "ms_once_outside_the_timed_step": seeds_ms,
+                       "note": "device: ahfgpu_amr_patch_stats per level (GPU) + ahfgpu_tree_halos (host, includes the O(N_h^2) gathering-radius loop)"},
         "gpu_launches": int(launches),
         "resident_step_ms_host": [round(x, 3) for x in host_ms],
         "clocks": clocks,
@@ -436,7 +539,8 @@ def main():
         if os.path.exists(O.REF_BIN):
             v, d = run_reference_sample(args.ref_n1d, 43, nthreads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": nthreads, "kind": "reference",
-                                    "sample": f"unmodified reference (oracle/_ref/ahf_ref) on a {args.ref_n1d}^3 box of the same generator, one run",
+                                    "sample": f"unmodified reference (oracle/_ref/ahf_ref) on the {args.ref_n1d}^3 box of the same generator and seed"
+                                              + (" -- the GPU arm's own box" if args.ref_n1d == args.n1d else "") + ", one run, hook timers of the path's phases",
                                     "detail": {k: d[k] for k in ("keys", "sort", "ll", "deposit", "refine", "relink", "halo_loop", "path_s")}}
         else:
             v, d = run_port_sample(64, 43)

@@ -198,3 +198,16 @@ def test_cooperative_halo_pass_equals_one_cta_per_halo(A):
     assert np.array_equal(a["members"], b["members"]) and np.array_equal(a["member_offset"], b["member_offset"])
     assert np.allclose(a["scal"], b["scal"], rtol=1e-10, atol=1e-300, equal_nan=True)
     assert np.allclose(a["prof"], b["prof"], rtol=1e-9, atol=1e-300, equal_nan=True)
+
+
+def test_large_multispecies_host_against_oracle(A):
+    """BASELINE.json configs[4], scaled to what the CPU oracle finishes in seconds: a 1.5e6-particle dark matter + gas + star host with
+    subclumps -- the cooperative multi-block kernels against the oracle (stage counts and member lists identical, scalars 1e-8, profiles
+    1e-7, species blocks).  scripts/big_host_check.py runs the same check at 1e7 (profiles/)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("big_host_check", os.path.join(os.path.dirname(__file__), "..", "scripts", "big_host_check.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    out = m.run(1_500_000, 2)
+    assert out["host_gathered"] > 1_000_000 and out["members_identical"]
+    print(out)

@@ -165,12 +165,22 @@ def _check_halos(g, golden, rtol=1e-9, order=None):
             assert np.allclose(golden.prof_species(i), g.halo_profile_species(res, i), rtol=1e-8, atol=1e-300)
 
 
-def test_halo_pass_matches_reference(A, golden):
+@pytest.mark.parametrize("unbind", ["hybrid", "cooperative", "one_cta"])
+def test_halo_pass_matches_reference(A, golden, unbind):
     """species32: the -DMULTIMASS -DGAS_PARTICLES build (weights in M_vir / potential / profiles, thermal energy in the bound test
-    and Ekin, R_max and r2 from the dark matter alone)"""
-    with _ctx(A, golden) as g:
-        g.sfc_sort(golden.pos, golden.mom, golden.weight, golden.u)
-        _check_halos(g, golden)
+    and Ekin, R_max and r2 from the dark matter alone).  unbind: the default hybrid (haloes up to 16384 gathered members by one CTA each,
+    larger ones by the cooperative multi-block pass), everything cooperative, everything by one CTA per halo -- all three must give the
+    reference's member lists and scalars."""
+    import os
+    env = {"hybrid": {}, "cooperative": {"AHFGPU_UNBIND_SMALL": "0"}, "one_cta": {"AHFGPU_UNBIND_V1": "1"}}[unbind]
+    os.environ.update(env)
+    try:
+        with _ctx(A, golden) as g:
+            g.sfc_sort(golden.pos, golden.mom, golden.weight, golden.u)
+            _check_halos(g, golden)
+    finally:
+        for k in env:
+            os.environ.pop(k, None)
 
 
 def test_end_to_end_from_file_order(A, golden):
