@@ -632,6 +632,11 @@ k_deposit_runs(const float4 *__restrict__ lpos, const int32_t *__restrict__ tsta
 constexpr int DD_CO   = DT_HH + 8;                                   // word offset of copy B: == 16 (mod 32 banks)
 constexpr int DD_CAR  = 2 * DD_CO;                                   // word offset of the carry counters
 constexpr int DD_NS   = 4;                                           // TMA stages of DT_SUB particles (ring)
+// Fixed-point scale of the domain deposit: every particle deposits EXACTLY 2^32 units (complement weights).  Measured and rejected in
+// round 2 (profiles/r2l_bench_256_n1.json): 2^26 units per particle with the carry detection only where an atomic returned a value
+// with its top bit set -- about 80 of the 354 warp instructions per 32 particles less (no carry replay loop, no per-term carry pair)
+// -- did NOT change the kernel time (0.344 vs 0.349 ms): the kernel is not bound by instruction issue.
+constexpr int DD_S    = 32;
 constexpr int DD_SMEM = DD_NS * DT_SUB * 16 + (DD_CAR + DT_HH) * 4 + 8 * DD_NS * (DT_THREADS / 32);   // DT_SUB*16 = 16 warps x 512 B per ring slot
 
 __device__ __forceinline__ uint32_t pos_q32(float x) { return x >= 1.0f ? 0u : __float2uint_rz(x * 4294967296.0f); }   // x == 1 -> cell 0 (lltools.c:61-64)
@@ -1596,6 +1601,30 @@ __global__ void k_unique_fill(const uint64_t *__restrict__ k, uint64_t n, const 
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i < n && head[i]) out[pos[i]] = k[i];
 }
+// R sorted lists of row keys, concatenated (list p = [off[p], off[p+1])): every element finds its place in the merged order
+struct RowLists { int R; int off[33]; };
+__global__ void k_rows_rank(const uint64_t *__restrict__ all, RowLists RL, uint64_t *__restrict__ merged, uint8_t *__restrict__ first)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= RL.off[RL.R]) return;
+  int p = 0;
+  while (i >= RL.off[p + 1]) p++;
+  const uint64_t k = all[i];
+  int  place = i - RL.off[p];
+  bool dup = false;
+  for (int q = 0; q < RL.R; q++) {
+    if (q == p) continue;
+    int lo = RL.off[q], hi = RL.off[q + 1];
+    const int b = lo;
+    // q < p: elements <= k come first (and an equal one makes k a duplicate); q > p: elements < k
+    if (q < p) { while (lo < hi) { const int mid = lo + ((hi - lo) >> 1); if (all[mid] <= k) lo = mid + 1; else hi = mid; } dup |= (lo > b && all[lo - 1] == k); }
+    else       { while (lo < hi) { const int mid = lo + ((hi - lo) >> 1); if (all[mid] < k) lo = mid + 1; else hi = mid; } }
+    place += lo - b;
+  }
+  merged[place] = k;
+  first[place] = dup ? 0 : 1;
+}
+
 // tested flag / run flags of the level's own rows from the table of ALL rows (rows nobody owns exist only in the rank's ghost fringe)
 __global__ void k_map_rows(const uint64_t *__restrict__ rowkey, int nrow, const uint64_t *__restrict__ grow, int ng, const uint8_t *__restrict__ gtested,
                            const uint8_t *__restrict__ gflags, uint8_t *__restrict__ tested, uint8_t *__restrict__ flags)
@@ -1613,6 +1642,7 @@ __global__ void k_map_rows(const uint64_t *__restrict__ rowkey, int nrow, const 
 // the rows of a level that hold at least one cell of the rank's own key range: compacted keys (device, caller frees) and their number
 static int64_t owned_rows(ahfgpu_ctx *c, Level &lv, uint64_t **send_out)
 {
+  Stage sto(c, "rows_owned", lv.nrow, c->env.stages);
   Comm *cm = c->comm; Slab *S = c->slab;
   DevBuf<uint8_t> ro; DevBuf<int> pos, bs, tot;
   ro.reserve(lv.nrow); pos.reserve(lv.nrow); tot.reserve(1);
@@ -1644,23 +1674,26 @@ static void rows_from_all_ranks(ahfgpu_ctx *c, Level *lv, const uint64_t *send, 
     cm->allgatherv(c, send, all, bytes.data(), off.data());
   }
   if (lv && lv->nrow > 0) {
+    Stage stm(c, "rows_merge", nall, c->env.stages);
     if (nall == 0) AHF_FAIL("a level without rows on any rank");
-    // sort + unique (every row key is 2 logL bits)
-    uint64_t *k1 = dalloc<uint64_t>(nall); uint32_t *v0 = dalloc<uint32_t>(nall), *v1 = dalloc<uint32_t>(nall);
-    uint64_t *ks; uint32_t *vs;
-    int kb = 2 * logL; kb = ((kb + 7) / 8) * 8;
-    radix_sort_pairs(c, all, v0, k1, v1, (uint64_t)nall, kb, &ks, &vs);
-    DevBuf<uint8_t> head; DevBuf<int> pos;
-    head.reserve(nall); pos.reserve(nall);
-    LAUNCH(c, k_unique_heads, nblk(nall, 256), 256, 0, ks, (uint64_t)nall, head.p);
-    const int ng = exclusive_scan<uint8_t>(c, head.p, pos.p, (uint64_t)nall);
+    // merge of the R sorted lists without a sort: the place of an element among all elements is its index in its own list plus, for every
+    // other list, the number of elements below it (binary searches); an element that also occurs in an earlier list is a duplicate
+    RowLists RL;
+    RL.R = R;
+    for (int p = 0; p < R; p++) { RL.off[p] = (int)(off[p] / 8); }
+    RL.off[R] = (int)nall;
+    uint64_t *merged = dalloc<uint64_t>(nall);
+    DevBuf<uint8_t> first; DevBuf<int> pos;
+    first.reserve(nall); pos.reserve(nall);
+    LAUNCH(c, k_rows_rank, nblk(nall, 256), 256, 0, all, RL, merged, first.p);
+    const int ng = exclusive_scan<uint8_t>(c, first.p, pos.p, (uint64_t)nall);
     uint64_t *grow = dalloc<uint64_t>(ng);
-    LAUNCH(c, k_unique_fill, nblk(nall, 256), 256, 0, ks, (uint64_t)nall, head.p, pos.p, grow);
+    LAUNCH(c, k_unique_fill, nblk(nall, 256), 256, 0, merged, (uint64_t)nall, first.p, pos.p, grow);
     uint8_t *gt = dalloc<uint8_t>(ng), *gf = dalloc<uint8_t>(ng);
     rows_tested_flags(c, grow, ng, -1, L, logL, gt, gf, nullptr, nullptr);
     LAUNCH(c, k_map_rows, nblk(lv->nrow, 256), 256, 0, lv->rowkey, (int)lv->nrow, grow, ng, gt, gf, lv->row_tested, lv->row_flags);
-    head.release(); pos.release();
-    ahf::dfree(k1); ahf::dfree(v0); ahf::dfree(v1); ahf::dfree(grow); ahf::dfree(gt); ahf::dfree(gf);
+    first.release(); pos.release();
+    ahf::dfree(merged); ahf::dfree(grow); ahf::dfree(gt); ahf::dfree(gf);
   }
   ahf::dfree(all);
 }
@@ -1702,7 +1735,7 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
   const bool dom_v1       = c->env.deposit_v1;           // previous float-weight domain kernel (A/B timing)
   // choice of kernel and fixed-point scale from the counts of the WHOLE box (g_*): every rank of a split box rounds like one GPU
   const bool tiles_dense  = lv.dense && lv.L >= 2 * DT_T && lv.g_npart_dep > 0 && !generic_only;
-  const int    S = (tiles_dense && !dom_v1) ? 32 : fx_shift_for(lv.masstopartdens);    // k_deposit_dom works in 2^-32 units
+  const int    S = (tiles_dense && !dom_v1) ? DD_S : fx_shift_for(lv.masstopartdens);    // k_deposit_dom works in 2^-DD_S units
   const double fxscale = (double)(1ull << S);
   const bool tiles_sparse = !lv.dense && lv.lpos && lv.g_npart_dep >= 2048 && v.logL - 4 <= 20 && !generic_only;
   if ((tiles_dense || tiles_sparse) && lv.npart_dep > 0) {

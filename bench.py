@@ -211,7 +211,7 @@ def bench_slab(args, rank, world, local_rank, config):
         sb.redistribute(id_base=id_base)
         st.update({k: g.stage_ms(k) for k in ("slab_keys", "slab_histogram_allreduce", "slab_decompose", "slab_partition", "slab_exchange", "keys", "sort", "gather")})
         sb.build_amr()
-        st.update({k: g.stage_ms(k) for k in ("amr_total", "ll", "deposit", "deposit_dom_kernel", "flag", "refine", "relink", "rows_allgather", "level_allgather")})
+        st.update({k: g.stage_ms(k) for k in ("amr_total", "ll", "deposit", "deposit_dom_kernel", "flag", "refine", "relink", "rows_allgather", "level_allgather", "rows_merge", "rows_owned")})
         st["deposit_particles"] = g.stage_count("deposit")
         mine, _ = sb.construct_halos(c, r, seed, fetch=False)
         st.update({k: g.stage_ms(k) for k in ("halo_gather", "halo_sort", "halo_unbind", "halo_profiles")})
