@@ -2172,27 +2172,61 @@ __device__ __forceinline__ void atomic_min_pos(double *a, double v) { atomicMin(
 // reproducible from run to run and equals the reference's sequential double sums wherever those are exact themselves.
 constexpr int PS_IACC = 8;
 constexpr double PS_PSCALE = 68719476736.0;       // 2^36: 2 * 2^36 * 2^26 particles of one refinement fit 63 bits
+// Cells come in (z, y, x) order, so the cells of one refinement are runs along x: a warp first adds up its runs of equal refinement
+// index (segmented scan by shuffles: keys are contiguous, so "key 2^k lanes back is mine" means the whole span is) and only the last
+// lane of a run touches the accumulators.  One atomic per value and RUN instead of per cell: the first version spent 4.4 ms per level
+// of the 256^3 box in same-address atomics (profiles/r2n_launches_summary.txt), 28 % of all kernel time of that capture.
+template <typename T> __device__ __forceinline__ T seg_shfl_up(T v, int o) { return __shfl_up_sync(0xffffffffu, v, o); }
+template <> __device__ __forceinline__ unsigned long long seg_shfl_up<unsigned long long>(unsigned long long v, int o)
+{
+  const unsigned lo = __shfl_up_sync(0xffffffffu, (unsigned)v, o), hi = __shfl_up_sync(0xffffffffu, (unsigned)(v >> 32), o);
+  return ((unsigned long long)hi << 32) | lo;
+}
 __global__ void k_pstat_cells(LV v, const int32_t *__restrict__ iso, const uint8_t *__restrict__ per3, const float *__restrict__ dens, double *acc,
                               unsigned long long *iacc)
 {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= v.ncell) return;
-  const int i = iso[c];
-  int x, y, z;
-  lv_coords(v, c, x, y, z);
-  const double L = (double)v.L, shift = 0.5 / L;
-  double xx = node_coord(x, L, shift), yy = node_coord(y, L, shift), zz = node_coord(z, L, shift);
-  unsigned long long ix = 2ull * (unsigned long long)x + 1ull, iy = 2ull * (unsigned long long)y + 1ull, iz = 2ull * (unsigned long long)z + 1ull;
-  if (per3[3 * i + 0] && xx < 0.5) { xx += 1.0; ix += 2ull * (unsigned long long)v.L; }                        // :1032-1040
-  if (per3[3 * i + 1] && yy < 0.5) { yy += 1.0; iy += 2ull * (unsigned long long)v.L; }
-  if (per3[3 * i + 2] && zz < 0.5) { zz += 1.0; iz += 2ull * (unsigned long long)v.L; }
-  double d = (double)dens[c] + 1.0;                                  // + simu.mean_dens, :1057
-  if (d < 0.0) d = 0.0;
-  double *a = acc + (size_t)PS_ACC * i;
-  unsigned long long *ia = iacc + (size_t)PS_IACC * i;
-  atomicAdd(ia + 0, 1ull); atomicAdd(ia + 1, ix); atomicAdd(ia + 2, iy); atomicAdd(ia + 3, iz);
-  atomicAdd(a + 6, xx * d); atomicAdd(a + 7, yy * d); atomicAdd(a + 8, zz * d); atomicAdd(a + 9, d);
-  atomic_max_pos(a + 10, d);
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = c < v.ncell;
+  const int lane = threadIdx.x & 31;
+  int i = -1 - lane;                                       // invalid lanes: keys that match nobody
+  unsigned long long iv[4] = { 0, 0, 0, 0 };
+  double dv[4] = { 0, 0, 0, 0 }, dmax = 0.0;
+  if (valid) {
+    i = iso[c];
+    int x, y, z;
+    lv_coords(v, c, x, y, z);
+    const double L = (double)v.L, shift = 0.5 / L;
+    double xx = node_coord(x, L, shift), yy = node_coord(y, L, shift), zz = node_coord(z, L, shift);
+    unsigned long long ix = 2ull * (unsigned long long)x + 1ull, iy = 2ull * (unsigned long long)y + 1ull, iz = 2ull * (unsigned long long)z + 1ull;
+    if (per3[3 * i + 0] && xx < 0.5) { xx += 1.0; ix += 2ull * (unsigned long long)v.L; }                        // :1032-1040
+    if (per3[3 * i + 1] && yy < 0.5) { yy += 1.0; iy += 2ull * (unsigned long long)v.L; }
+    if (per3[3 * i + 2] && zz < 0.5) { zz += 1.0; iz += 2ull * (unsigned long long)v.L; }
+    double d = (double)dens[c] + 1.0;                                  // + simu.mean_dens, :1057
+    if (d < 0.0) d = 0.0;
+    iv[0] = 1ull; iv[1] = ix; iv[2] = iy; iv[3] = iz;
+    dv[0] = xx * d; dv[1] = yy * d; dv[2] = zz * d; dv[3] = d; dmax = d;
+  }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int ko = __shfl_up_sync(0xffffffffu, i, o);
+    const bool take = lane >= o && ko == i;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const unsigned long long a = seg_shfl_up(iv[q], o);
+      const double b = __shfl_up_sync(0xffffffffu, dv[q], o);
+      if (take) { iv[q] += a; dv[q] += b; }
+    }
+    const double m = __shfl_up_sync(0xffffffffu, dmax, o);
+    if (take && m > dmax) dmax = m;
+  }
+  const int inext = __shfl_down_sync(0xffffffffu, i, 1);
+  if (valid && (lane == 31 || inext != i)) {               // last lane of its run
+    double *a = acc + (size_t)PS_ACC * i;
+    unsigned long long *ia = iacc + (size_t)PS_IACC * i;
+    atomicAdd(ia + 0, iv[0]); atomicAdd(ia + 1, iv[1]); atomicAdd(ia + 2, iv[2]); atomicAdd(ia + 3, iv[3]);
+    atomicAdd(a + 6, dv[0]); atomicAdd(a + 7, dv[1]); atomicAdd(a + 8, dv[2]); atomicAdd(a + 9, dv[3]);
+    atomic_max_pos(a + 10, dmax);
+  }
 }
 // particles the level finally owns (node.ll at ahf_halos time): centre of mass of the refinement's particles (:1120-1180)
 __global__ void k_pstat_parts(const float4 *__restrict__ pos4, const uint32_t *__restrict__ plist, const int32_t *__restrict__ pcell, uint64_t np,
@@ -2244,19 +2278,43 @@ __global__ void k_pstat_finish(const double *__restrict__ acc, const unsigned lo
 // extents (:1480-1595): MinMax, or MinMaxBound at boundRefDiv for the periodic refinements (specific.c:204-254)
 __global__ void k_pstat_extents(LV v, const int32_t *__restrict__ iso, const double *__restrict__ div3, double *out)
 {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= v.ncell) return;
-  const int i = iso[c];
-  int xyz[3];
-  lv_coords(v, c, xyz[0], xyz[1], xyz[2]);
-  const double L = (double)v.L, shift = 0.5 / L;
-  double *o = out + (size_t)18 * i;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = c < v.ncell;
+  const int lane = threadIdx.x & 31;
+  int i = -1 - lane;
+  // per axis: candidate for the minimum and for the maximum of the refinement (+inf / -1: none), as MinMax / MinMaxBound would see this node
+  double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1.0, -1.0, -1.0 };
+  if (valid) {
+    i = iso[c];
+    int xyz[3];
+    lv_coords(v, c, xyz[0], xyz[1], xyz[2]);
+    const double L = (double)v.L, shift = 0.5 / L;
 #pragma unroll
-  for (int q = 0; q < 3; q++) {
-    const double xx = node_coord(xyz[q], L, shift), dv = div3[3 * i + q];
-    if (dv < 0.0) { atomic_min_pos(o + 12 + 2 * q, xx); atomic_max_pos(o + 13 + 2 * q, xx); }
-    else if (xx < dv) atomic_max_pos(o + 13 + 2 * q, xx);
-    else atomic_min_pos(o + 12 + 2 * q, xx);
+    for (int q = 0; q < 3; q++) {
+      const double xx = node_coord(xyz[q], L, shift), dv = div3[3 * i + q];
+      if (dv < 0.0) { lo[q] = xx; hi[q] = xx; }
+      else if (xx < dv) hi[q] = xx;
+      else lo[q] = xx;
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {                         // runs of equal refinement index: segmented min / max (see k_pstat_cells)
+    const int ko = __shfl_up_sync(0xffffffffu, i, o);
+    const bool take = lane >= o && ko == i;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      const double a = __shfl_up_sync(0xffffffffu, lo[q], o), b = __shfl_up_sync(0xffffffffu, hi[q], o);
+      if (take) { if (a < lo[q]) lo[q] = a; if (b > hi[q]) hi[q] = b; }
+    }
+  }
+  const int inext = __shfl_down_sync(0xffffffffu, i, 1);
+  if (valid && (lane == 31 || inext != i)) {
+    double *o = out + (size_t)18 * i;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      if (lo[q] < 1e299) atomic_min_pos(o + 12 + 2 * q, lo[q]);
+      if (hi[q] >= 0.0) atomic_max_pos(o + 13 + 2 * q, hi[q]);
+    }
   }
 }
 __global__ void k_pstat_fix(int niso, double *out)
