@@ -2173,8 +2173,7 @@ __device__ __forceinline__ void atomic_min_pos(double *a, double v) { atomicMin(
 constexpr int PS_IACC = 8;
 constexpr double PS_PSCALE = 68719476736.0;       // 2^36: 2 * 2^36 * 2^26 particles of one refinement fit 63 bits
 // Cells come in (z, y, x) order, so the cells of one refinement are runs along x: a warp first adds up its runs of equal refinement
-// index (segmented scan by shuffles: keys are contiguous, so "key 2^k lanes back is mine" means the whole span is) and only the last
-// lane of a run touches the accumulators.  One atomic per value and RUN instead of per cell: the first version spent 4.4 ms per level
+// index (segmented scan by shuffles over the run number) and only the last lane of a run touches the accumulators.  One atomic per value and RUN instead of per cell: the first version spent 4.4 ms per level
 // of the 256^3 box in same-address atomics (profiles/r2n_launches_summary.txt), 28 % of all kernel time of that capture.
 template <typename T> __device__ __forceinline__ T seg_shfl_up(T v, int o) { return __shfl_up_sync(0xffffffffu, v, o); }
 template <> __device__ __forceinline__ unsigned long long seg_shfl_up<unsigned long long>(unsigned long long v, int o)
@@ -2206,10 +2205,14 @@ __global__ void k_pstat_cells(LV v, const int32_t *__restrict__ iso, const uint8
     iv[0] = 1ull; iv[1] = ix; iv[2] = iy; iv[3] = iz;
     dv[0] = xx * d; dv[1] = yy * d; dv[2] = zz * d; dv[3] = d; dmax = d;
   }
+  // runs of equal refinement index (the same index may come back later in the warp: A B A; the RUN number is what is contiguous)
+  const int iprev = __shfl_up_sync(0xffffffffu, i, 1);
+  const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || iprev != i);
+  const int run = __popc(heads & (0xffffffffu >> (31 - lane)));
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const int ko = __shfl_up_sync(0xffffffffu, i, o);
-    const bool take = lane >= o && ko == i;
+    const int ko = __shfl_up_sync(0xffffffffu, run, o);
+    const bool take = lane >= o && ko == run;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       const unsigned long long a = seg_shfl_up(iv[q], o);
@@ -2297,10 +2300,13 @@ __global__ void k_pstat_extents(LV v, const int32_t *__restrict__ iso, const dou
       else lo[q] = xx;
     }
   }
+  const int iprev = __shfl_up_sync(0xffffffffu, i, 1);
+  const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || iprev != i);
+  const int run = __popc(heads & (0xffffffffu >> (31 - lane)));
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {                         // runs of equal refinement index: segmented min / max (see k_pstat_cells)
-    const int ko = __shfl_up_sync(0xffffffffu, i, o);
-    const bool take = lane >= o && ko == i;
+    const int ko = __shfl_up_sync(0xffffffffu, run, o);
+    const bool take = lane >= o && ko == run;
 #pragma unroll
     for (int q = 0; q < 3; q++) {
       const double a = __shfl_up_sync(0xffffffffu, lo[q], o), b = __shfl_up_sync(0xffffffffu, hi[q], o);
