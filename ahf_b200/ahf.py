@@ -151,6 +151,8 @@ def lib():
         L.ahfgpu_slab_owner_of.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.ahfgpu_amr_level_owned.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.ahfgpu_particle_ids.argtypes = [C.c_void_p, C.c_void_p]
+        L.ahfgpu_ingest_gadget.argtypes = [C.c_void_p, C.c_char_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+        L.ahfgpu_particles_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ahfgpu_adopt_sorted.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_int32]
         L.ahfgpu_sfc_sort_device4.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_int32]
         L.ahfgpu_hilbert_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
@@ -293,6 +295,26 @@ class AhfGpu:
                                                     C.c_void_p(weight_ptr) if weight_ptr else None,
                                                     C.c_void_p(u_ptr) if u_ptr else None, n))
         self.n = n
+
+    def ingest_gadget(self, path: str, posscale: float = 1.0, weightscale: float = 1.0, want_ids: bool = True):
+        """bulk GADGET ingest with on-device unit scaling (NEXT-4): returns (info dict, ids or None); continue with sfc_sort_resident()"""
+        info = np.zeros(16, np.float64)
+        self._chk(self._L.ahfgpu_ingest_gadget(self._h, path.encode(), posscale, weightscale, None, _p(info)))
+        n = int(info[0])
+        ids = None
+        if want_ids:
+            ids = np.empty(n, np.uint64)
+            self._chk(self._L.ahfgpu_ingest_gadget(self._h, path.encode(), posscale, weightscale, _p(ids), _p(info)))
+        self.n = n
+        keys = ("n", "boxsize", "expansion", "omega0", "lambda0", "pmass", "shift_x", "shift_y", "shift_z", "scale_pos", "scale_mom", "version", "swapped",
+                "hubble", "read_ms", "device_ms")
+        return dict(zip(keys, info.tolist())), ids
+
+    def particles(self):
+        """the resident sorted particles: (pos4 [n,4] x y z weight, mom4 [n,4] px py pz u)"""
+        pos4 = np.empty((self.n, 4), np.float32); mom4 = np.empty((self.n, 4), np.float32)
+        self._chk(self._L.ahfgpu_particles_get(self._h, _p(pos4), _p(mom4)))
+        return pos4, mom4
 
     def upload(self, pos, mom, weight=None, u=None):
         pos = np.ascontiguousarray(pos, np.float32); mom = np.ascontiguousarray(mom, np.float32)

@@ -391,6 +391,18 @@ int ahfgpu_slab_owner_of(ahfgpu_ctx *c, int64_t n, const double *pos3, int32_t *
   API_END
 }
 
+int ahfgpu_particles_get(ahfgpu_ctx *c, float *pos4, float *mom4)
+{
+  API_BEGIN
+  if (!c || !c->pos4) AHF_FAIL("no resident particles");
+  CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
+  c->wait_mom(true);
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (pos4 && c->n) CUDA_CHECK(cudaMemcpy(pos4, c->pos4, sizeof(float4) * c->n, cudaMemcpyDeviceToHost));
+  if (mom4 && c->n) CUDA_CHECK(cudaMemcpy(mom4, c->mom4, sizeof(float4) * c->n, cudaMemcpyDeviceToHost));
+  API_END
+}
+
 int ahfgpu_particle_ids(ahfgpu_ctx *c, uint32_t *ids)
 {
   API_BEGIN

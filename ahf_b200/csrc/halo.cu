@@ -691,6 +691,27 @@ __global__ void __launch_bounds__(HB) k_gather_tiles(const float4 *__restrict__ 
 #pragma unroll
   for (int i = 0; i < HI; i++) if (in[i]) { r2buf[out] = r2[i]; idxbuf[out] = start + (uint32_t)(threadIdx.x * HI + i); out++; }
 }
+// tile list of the gather pass, built on the device (round 2: with 2e4 haloes the host version -- 27 ranges per halo read back, a host
+// loop, the list uploaded again -- took 9 of the 11 ms of the stage): tiles per (halo, search cell) range -> exclusive scan -> fill
+__global__ void k_gt_count(const int64_t *__restrict__ rlo, const int64_t *__restrict__ rhi, int64_t nrange, int *__restrict__ nt)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < nrange) { const int64_t len = rhi[i] - rlo[i]; nt[i] = len > 0 ? (int)((len + HT - 1) / HT) : 0; }
+}
+__global__ void k_gt_fill(const int64_t *__restrict__ rlo, const int64_t *__restrict__ rhi, int64_t nrange, const int *__restrict__ toff, const int *__restrict__ ttot,
+                          int4 *__restrict__ tiles, int32_t *__restrict__ act, int32_t *__restrict__ tile0, int32_t *__restrict__ ntile)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nrange) return;
+  const int h = (int)(i / 27), q = (int)(i - (int64_t)h * 27);
+  int o = toff[i];
+  for (int64_t a = rlo[i]; a < rhi[i]; a += HT) { const int64_t len = rhi[i] - a; tiles[o++] = make_int4(h, q, (int)(uint32_t)a, (int)(len < HT ? len : HT)); }
+  if (q == 0) {
+    act[h] = h; tile0[h] = toff[i];
+    const int64_t e = i + 27;
+    ntile[h] = (e < nrange ? toff[e] : *ttot) - toff[i];
+  }
+}
 __global__ void k_gather_counts(const double *__restrict__ htot, int64_t nhalo, int64_t *__restrict__ ngather)
 {
   const int64_t h = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -1090,33 +1111,53 @@ constexpr int NACC = 21;   // CoM3, a11 a22 a33 a12 a13 a23, L3, Ekin, Epot, Mhi
 constexpr int NSPC = 19;   // per species: n, M, com(3), P(3), L(3), a11 a22 a33 a12 a13 a23, Epot, Ekin
 
 // per-bin cumulative values, Jacobi, profile columns and the integral properties (ahf_halos.c:4632-4710, :4870-5018); one thread
+// one radial bin of HaloProfiles from the CUMULATIVE sums up to and including it (cum), the mass / volume of the previous bin, the
+// escape velocity of the last non-empty bin so far and the bin's own u_gas sum
+#define PR(col, bb) pr[(col) * nbins + (bb)]
+__device__ __forceinline__ void prof_bin(const int b, const int nbins, const double *cum, const double shell_u, const double cur_rad, const double M_prev,
+                                         const double V_prev, const double vesc_run, double *pr, double *prsp)
+{
+  const double F43 = 4. * PI_ / 3.;
+  const double M = cum[16], Volume = F43 * (cur_rad * cur_rad * cur_rad), dM = M - M_prev, dV = Volume - V_prev;
+  double it[3][3], ax1, ax2, ax3;
+  if (cum[17] > (double)MINPART_SHELL) {
+    it[0][0] = cum[3]; it[1][1] = cum[4]; it[2][2] = cum[5]; it[0][1] = it[1][0] = cum[6]; it[0][2] = it[2][0] = cum[7]; it[1][2] = it[2][1] = cum[8];
+    get_axes(it, ax1, ax2, ax3);
+  } else { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) it[i][j] = 0.0; ax1 = 1; ax2 = 0; ax3 = 0; }
+  PR(0, b) = cum[17]; PR(1, b) = cur_rad; PR(2, b) = M; PR(3, b) = M / Volume; PR(4, b) = (dV > 0) ? dM / dV : 0.0;
+  PR(5, b) = M / cur_rad; PR(6, b) = vesc_run; PR(7, b) = sqrt(cum[12] / M); PR(8, b) = 0.5 * cum[12]; PR(9, b) = 0.5 * cum[13];
+  PR(10, b) = cum[9]; PR(11, b) = cum[10]; PR(12, b) = cum[11];
+  PR(13, b) = 1.0; PR(14, b) = it[0][0]; PR(15, b) = it[1][0]; PR(16, b) = it[2][0];
+  PR(17, b) = (ax1 > 0.) ? sqrt(ax2 / ax1) : 0.0; PR(18, b) = it[0][1]; PR(19, b) = it[1][1]; PR(20, b) = it[2][1];
+  PR(21, b) = (ax1 > 0.) ? sqrt(ax3 / ax1) : 0.0; PR(22, b) = it[0][2]; PR(23, b) = it[1][2]; PR(24, b) = it[2][2];
+  if (prsp) { prsp[0 * nbins + b] = cum[18]; prsp[1 * nbins + b] = cum[19]; prsp[2 * nbins + b] = shell_u; }   // M_gas, M_star cumulative; u_gas of the shell (:4713-4715)
+}
+__device__ void prof_tail(const int nbins, const double *cum, const double *Pl, double *pr, double *S, const double R_vir, const HP &P, const long long best_j,
+                          const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, const uint32_t *__restrict__ ip, const double c[3]);
+
+// serial form (one thread): the bins in order, then the integral properties
 __device__ void prof_finalize(const int nbins, const double (*acc)[NACC], const double *edge, const double *vesc_bin, const double (*Vc_bin)[3],
                               double *pr, double *S, const double R_vir, const HP &P, const long long best_j, const float4 *__restrict__ pos4,
                               const float4 *__restrict__ mom4, const uint32_t *__restrict__ ip, const double c[3], double *prsp = nullptr)
 {
   const double F43 = 4. * PI_ / 3.;
-    double cum[NACC];
-    for (int q = 0; q < NACC; q++) cum[q] = 0.0;
-    double M_prev = 0.0, V_prev = 0.0, vesc_run = 0.0, Pl[3] = { 0, 0, 0 };
-    for (int b = 0; b < nbins; b++) {
-      for (int q = 0; q < NACC; q++) cum[q] += acc[b][q];
-      if (acc[b][17] > 0.0) { vesc_run = vesc_bin[b]; Pl[0] = Vc_bin[b][0]; Pl[1] = Vc_bin[b][1]; Pl[2] = Vc_bin[b][2]; }
-      const double cur_rad = edge[b], M = cum[16], Volume = F43 * (cur_rad * cur_rad * cur_rad), dM = M - M_prev, dV = Volume - V_prev;
-      double it[3][3], ax1, ax2, ax3;
-      if (cum[17] > (double)MINPART_SHELL) {
-        it[0][0] = cum[3]; it[1][1] = cum[4]; it[2][2] = cum[5]; it[0][1] = it[1][0] = cum[6]; it[0][2] = it[2][0] = cum[7]; it[1][2] = it[2][1] = cum[8];
-        get_axes(it, ax1, ax2, ax3);
-      } else { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) it[i][j] = 0.0; ax1 = 1; ax2 = 0; ax3 = 0; }
-#define PR(col, bb) pr[(col) * nbins + (bb)]
-      PR(0, b) = cum[17]; PR(1, b) = cur_rad; PR(2, b) = M; PR(3, b) = M / Volume; PR(4, b) = (dV > 0) ? dM / dV : 0.0;
-      PR(5, b) = M / cur_rad; PR(6, b) = vesc_run; PR(7, b) = sqrt(cum[12] / M); PR(8, b) = 0.5 * cum[12]; PR(9, b) = 0.5 * cum[13];
-      PR(10, b) = cum[9]; PR(11, b) = cum[10]; PR(12, b) = cum[11];
-      PR(13, b) = 1.0; PR(14, b) = it[0][0]; PR(15, b) = it[1][0]; PR(16, b) = it[2][0];
-      PR(17, b) = (ax1 > 0.) ? sqrt(ax2 / ax1) : 0.0; PR(18, b) = it[0][1]; PR(19, b) = it[1][1]; PR(20, b) = it[2][1];
-      PR(21, b) = (ax1 > 0.) ? sqrt(ax3 / ax1) : 0.0; PR(22, b) = it[0][2]; PR(23, b) = it[1][2]; PR(24, b) = it[2][2];
-      if (prsp) { prsp[0 * nbins + b] = cum[18]; prsp[1 * nbins + b] = cum[19]; prsp[2 * nbins + b] = acc[b][20]; }   // M_gas, M_star cumulative; u_gas of the shell (:4713-4715)
-      M_prev = M; V_prev = Volume;
-    }
+  double cum[NACC];
+  for (int q = 0; q < NACC; q++) cum[q] = 0.0;
+  double M_prev = 0.0, V_prev = 0.0, vesc_run = 0.0, Pl[3] = { 0, 0, 0 };
+  for (int b = 0; b < nbins; b++) {
+    for (int q = 0; q < NACC; q++) cum[q] += acc[b][q];
+    if (acc[b][17] > 0.0) { vesc_run = vesc_bin[b]; Pl[0] = Vc_bin[b][0]; Pl[1] = Vc_bin[b][1]; Pl[2] = Vc_bin[b][2]; }
+    const double cur_rad = edge[b];
+    prof_bin(b, nbins, cum, acc[b][20], cur_rad, M_prev, V_prev, vesc_run, pr, prsp);
+    M_prev = cum[16]; V_prev = F43 * (cur_rad * cur_rad * cur_rad);
+  }
+  prof_tail(nbins, cum, Pl, pr, S, R_vir, P, best_j, pos4, mom4, ip, c);
+}
+
+// integral properties of the halo from the finished profile (ahf_halos.c:4870-5018)
+__device__ void prof_tail(const int nbins, const double *cum, const double *Pl, double *pr, double *S, const double R_vir, const HP &P, const long long best_j,
+                          const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, const uint32_t *__restrict__ ip, const double c[3])
+{
     const double M = cum[16];
     const int    lb = nbins - 1;
     double CoM[3];
@@ -1797,6 +1838,25 @@ __global__ void __launch_bounds__(HB) k_p_finish(const float4 *__restrict__ pos4
     for (int q = 0; q < 3; q++) Vc_bin[i][q] = G.Vc_bin[((size_t)h * MAXBINS + i) * 3 + q];
   }
   __syncthreads();
+  // The bins in parallel (round 2): prof_finalize walked them with ONE thread per halo -- a dozen 3x3 Jacobi decompositions in a row,
+  // 0.4 ms per halo; with 2e4 haloes that kernel alone took 6.6 ms.  Same arithmetic per bin (prof_bin), so the numbers are those of
+  // the serial form: cumulative sums in place (one thread per component, bins in order), then one thread per bin, then the tail.
+  __shared__ double raw17[MAXBINS], raw20[MAXBINS];
+  for (int b = threadIdx.x; b < nbins; b += HB) { raw17[b] = acc[b][17]; raw20[b] = acc[b][20]; }
+  __syncthreads();
+  if (threadIdx.x < NACC) { double run = 0.0; for (int b = 0; b < nbins; b++) { run += acc[b][threadIdx.x]; acc[b][threadIdx.x] = run; } }
+  __syncthreads();
+  {
+    const double F43 = 4. * PI_ / 3.;
+    double *pr = prof + poff[h] * AHFGPU_NPROFCOL, *prsp = G.prof_species ? G.prof_species + poff[h] * 3 : nullptr;
+    for (int b = threadIdx.x; b < nbins; b += HB) {
+      double vesc_run = 0.0;                                            // escape velocity of the last non-empty bin up to b
+      for (int q = b; q >= 0; q--) if (raw17[q] > 0.0) { vesc_run = vesc_bin[q]; break; }
+      const double M_prev = b ? acc[b - 1][16] : 0.0, V_prev = b ? F43 * (edge[b - 1] * edge[b - 1] * edge[b - 1]) : 0.0;
+      prof_bin(b, nbins, acc[b], raw20[b], edge[b], M_prev, V_prev, vesc_run, pr, prsp);
+    }
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
     double e = 1e30; long long bj = -1;
     for (int t = t0; t < t0 + nt; t++) {
@@ -1804,8 +1864,9 @@ __global__ void __launch_bounds__(HB) k_p_finish(const float4 *__restrict__ pos4
       if (jj != 0x7fffffffffffffffll && (G.tbest_e[t] < e || bj < 0)) { e = G.tbest_e[t]; bj = jj; }
     }
     const double c[3] = { centre[3 * h], centre[3 * h + 1], centre[3 * h + 2] };
-    prof_finalize(nbins, acc, edge, vesc_bin, Vc_bin, prof + poff[h] * AHFGPU_NPROFCOL, S, S[11], P, bj, pos4, mom4, members + moff0[h], c,
-                  G.prof_species ? G.prof_species + poff[h] * 3 : nullptr);
+    double Pl[3] = { 0, 0, 0 };
+    for (int q = nbins - 1; q >= 0; q--) if (raw17[q] > 0.0) { Pl[0] = Vc_bin[q][0]; Pl[1] = Vc_bin[q][1]; Pl[2] = Vc_bin[q][2]; break; }
+    prof_tail(nbins, acc[nbins - 1], Pl, prof + poff[h] * AHFGPU_NPROFCOL, S, S[11], P, bj, pos4, mom4, members + moff0[h], c);
     if (G.species) {                       // gas_only / stars_only (ahf_halos.c:5020-5181): tile sums in tile order
       const double M = S[10], R_vir = S[11];
       for (int t = 0; t < 2; t++) {
@@ -2211,26 +2272,19 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
       LAUNCH(c, k_gather_fill, (unsigned)nhalo, HB, 0, c->pos4, d_ctr, d_rad, d_rlo, d_rhi, d_candoff, d_r2, d_idx, d_ng);
     } else {
       // tile list: chunks of HT candidates of every (halo, search cell) range, in the reference's append order
-      std::vector<int64_t> h_rlo(27 * nhalo), h_rhi(27 * nhalo);
-      CUDA_CHECK(cudaMemcpyAsync(h_rlo.data(), d_rlo, sizeof(int64_t) * 27 * nhalo, cudaMemcpyDeviceToHost, c->stream));
-      CUDA_CHECK(cudaMemcpyAsync(h_rhi.data(), d_rhi, sizeof(int64_t) * 27 * nhalo, cudaMemcpyDeviceToHost, c->stream));
-      CUDA_CHECK(cudaStreamSynchronize(c->stream));
-      std::vector<int4> tiles; std::vector<int32_t> act, tile0(nhalo, 0), ntile(nhalo, 0);
-      for (int64_t h = 0; h < nhalo; h++) {
-        act.push_back((int32_t)h);
-        tile0[h] = (int32_t)tiles.size();
-        for (int q = 0; q < 27; q++)
-          for (int64_t a = h_rlo[h * 27 + q]; a < h_rhi[h * 27 + q]; a += HT)
-            tiles.push_back(make_int4((int)h, q, (int)(uint32_t)a, (int)std::min<int64_t>(HT, h_rhi[h * 27 + q] - a)));
-        ntile[h] = (int32_t)tiles.size() - tile0[h];
-      }
-      const int nt = (int)tiles.size();
+      const int64_t nrange = 27 * nhalo;
+      if (nrange >= (1ll << 31)) AHF_FAIL("too many haloes in one call");
+      DevBuf<int> ntr, toff, bs, ttot;
+      ntr.reserve(nrange); toff.reserve(nrange); ttot.reserve(1);
+      CUDA_CHECK(cudaMemsetAsync(ttot.p, 0, sizeof(int), c->stream));
+      LAUNCH(c, k_gt_count, nblk(nrange, 256), 256, 0, d_rlo, d_rhi, nrange, ntr.p);
+      exclusive_scan_async<int>(c, ntr.p, toff.p, (uint64_t)nrange, ttot.p, bs);
+      int nt = 0;
+      read_back(c, &nt, ttot.p, sizeof(int));
       int4 *d_gt = dalloc<int4>(nt); int32_t *d_act = dalloc<int32_t>(nhalo), *d_t0 = dalloc<int32_t>(nhalo), *d_ntl = dalloc<int32_t>(nhalo);
       double *d_tt = dalloc<double>(nt), *d_tc = dalloc<double>(nt), *d_ht = dalloc<double>(nhalo);
-      CUDA_CHECK(cudaMemcpyAsync(d_gt, tiles.data(), sizeof(int4) * nt, cudaMemcpyHostToDevice, c->stream));
-      CUDA_CHECK(cudaMemcpyAsync(d_act, act.data(), sizeof(int32_t) * nhalo, cudaMemcpyHostToDevice, c->stream));
-      CUDA_CHECK(cudaMemcpyAsync(d_t0, tile0.data(), sizeof(int32_t) * nhalo, cudaMemcpyHostToDevice, c->stream));
-      CUDA_CHECK(cudaMemcpyAsync(d_ntl, ntile.data(), sizeof(int32_t) * nhalo, cudaMemcpyHostToDevice, c->stream));
+      LAUNCH(c, k_gt_fill, nblk(nrange, 256), 256, 0, d_rlo, d_rhi, nrange, toff.p, ttot.p, d_gt, d_act, d_t0, d_ntl);
+      ntr.release(); toff.release(); bs.release(); ttot.release();
       if (nt) LAUNCH(c, k_gather_tiles<false>, (unsigned)nt, HB, 0, c->pos4, d_ctr, d_rad, d_gt, d_candoff, d_tc, d_tt, d_r2, d_idx);
       LAUNCH(c, k_g_scan<1>, (unsigned)nhalo, HB, 0, d_act, d_t0, d_ntl, d_tt, d_tc, d_ht);
       if (nt) LAUNCH(c, k_gather_tiles<true>, (unsigned)nt, HB, 0, c->pos4, d_ctr, d_rad, d_gt, d_candoff, d_tc, d_tt, d_r2, d_idx);

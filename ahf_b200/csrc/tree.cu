@@ -4,6 +4,8 @@
 // on the host; only their inputs come from the device.  Default switches of the shipped define.h: PARDAU_PARTS (main branch = listed
 // refinement with most particles), AHFcomcentre (halo centre = centre of mass of the refinement's particles).
 #include "common.cuh"
+#include <thread>
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -57,16 +59,43 @@ extern "C" int ahfgpu_tree_halos(int32_t nlev, const int64_t *niso, const double
       }
     }
     // ---- analyseRef (1): a finer refinement is listed with every coarser one whose box holds its density centre (:1693-1800)
+    //      The reference tests every pair of two consecutive levels (an O(n_i n_{i+1}) loop: 3.5 s for the 2e4 refinements per level of
+    //      a 256^3 box with 2e4 haloes).  Same lists in the same order from a sorted x coordinate: the candidates of a parent are the
+    //      children whose centre lies in its x extent (binary searches), tested in y and z and appended in ascending index order; the
+    //      parent lists are filled afterwards, parents ascending -- exactly the order the nested loops produce.
     bool detail = false;
-    for (int i = 0; i + 1 < n; i++)
-      for (int j = 0; j < (int)R[i].size(); j++)
-        for (int k = 0; k < (int)R[i + 1].size(); k++) {
-          const Ref &p = R[i][j]; Ref &c = R[i + 1][k];
-          if (inside(c.cd[0], p.ext[0][0], p.ext[0][1]) && inside(c.cd[1], p.ext[1][0], p.ext[1][1]) && inside(c.cd[2], p.ext[2][0], p.ext[2][1])) {
-            R[i][j].sub.push_back(k); c.par.push_back(j);
-            if (c.par.size() > 1) detail = true;
+    for (int i = 0; i + 1 < n; i++) {
+      std::vector<Ref> &Pn = R[i], &Cn = R[i + 1];
+      const int nc = (int)Cn.size();
+      std::vector<int> ord(nc);
+      for (int k = 0; k < nc; k++) ord[k] = k;
+      std::sort(ord.begin(), ord.end(), [&](int a, int b) { return Cn[a].cd[0] < Cn[b].cd[0] || (Cn[a].cd[0] == Cn[b].cd[0] && a < b); });
+      std::vector<double> xs(nc);
+      for (int k = 0; k < nc; k++) xs[k] = Cn[ord[k]].cd[0];
+      std::vector<int> cand;
+      for (int j = 0; j < (int)Pn.size(); j++) {
+        const Ref &p = Pn[j];
+        cand.clear();
+        auto take = [&](size_t a, size_t b) {
+          for (size_t t = a; t < b; t++) {
+            const int k = ord[t];
+            const Ref &c = Cn[k];
+            if (inside(c.cd[0], p.ext[0][0], p.ext[0][1]) && inside(c.cd[1], p.ext[1][0], p.ext[1][1]) && inside(c.cd[2], p.ext[2][0], p.ext[2][1])) cand.push_back(k);
           }
+        };
+        const double lo = p.ext[0][0], hi = p.ext[0][1];
+        if (lo < hi) take((size_t)(std::upper_bound(xs.begin(), xs.end(), lo) - xs.begin()), (size_t)(std::lower_bound(xs.begin(), xs.end(), hi) - xs.begin()));
+        else {
+          take(0, (size_t)(std::lower_bound(xs.begin(), xs.end(), hi) - xs.begin()));          // [.., hi): inside() rejects v < 0 itself
+          take((size_t)(std::upper_bound(xs.begin(), xs.end(), lo) - xs.begin()), (size_t)nc);  // (lo, ..]: inside() rejects v > 1 itself
         }
+        std::sort(cand.begin(), cand.end());
+        cand.erase(std::unique(cand.begin(), cand.end()), cand.end());                          // the two periodic ranges may overlap
+        Pn[j].sub.insert(Pn[j].sub.end(), cand.begin(), cand.end());
+      }
+      for (int j = 0; j < (int)Pn.size(); j++)
+        for (int k : Pn[j].sub) { Cn[k].par.push_back(j); if (Cn[k].par.size() > 1) detail = true; }
+    }
     // ---- (2) several parents: keep the closest (first minimum), strike the refinement from the others.  The reference's loop runs over
     //      levels 1 .. n-2 only (:1817): a refinement of the finest level keeps all its parents
     if (detail)
@@ -165,15 +194,32 @@ extern "C" int ahfgpu_tree_halos(int32_t nlev, const int64_t *niso, const double
     *nhalo = nh;
     if (nh > halo_cap && (halo_pos3 || halo_gather_rad || halo_npart || halo_host)) AHF_FAIL("halo buffers too small");
     const double maxg = max_gather_rad < 0.25 ? max_gather_rad : 0.25;
+    // the O(N_h^2) loop is an OpenMP loop in the reference (ahf_halos.c:2989-2993); here: host threads over blocks of haloes
+    std::vector<double> gr((size_t)nh);
+    auto work = [&](int64_t i0, int64_t i1) {
+      for (int64_t i = i0; i < i1; i++) {
+        double g2 = 100000000000.0; long long cnt = 0;
+        for (int64_t j = 0; j < nh; j++)
+          if (H[j].npart > H[i].npart) { const double d = pdist2(H[i].pos, H[j].pos); if (d < g2) g2 = d; cnt++; }
+        double g = cnt ? std::sqrt(g2) * 0.5 : maxg;
+        if (g < H[i].rvir) g = H[i].rvir;
+        if (g > maxg) g = maxg;
+        gr[(size_t)i] = g;
+      }
+    };
+    unsigned nthr = std::thread::hardware_concurrency();
+    if (nthr == 0) nthr = 1;
+    if (nthr > 64) nthr = 64;
+    if (nh < 2048 || nthr == 1) work(0, nh);
+    else {
+      std::vector<std::thread> pool;
+      const int64_t per = (nh + nthr - 1) / nthr;
+      for (unsigned t = 0; t < nthr; t++) { const int64_t a = (int64_t)t * per, b = std::min<int64_t>(nh, a + per); if (a < b) pool.emplace_back(work, a, b); }
+      for (auto &th : pool) th.join();
+    }
     for (int64_t i = 0; i < nh; i++) {
-      double g2 = 100000000000.0; long long cnt = 0;
-      for (int64_t j = 0; j < nh; j++)
-        if (H[j].npart > H[i].npart) { const double d = pdist2(H[i].pos, H[j].pos); if (d < g2) g2 = d; cnt++; }
-      double g = cnt ? std::sqrt(g2) * 0.5 : maxg;
-      if (g < H[i].rvir) g = H[i].rvir;
-      if (g > maxg) g = maxg;
       if (halo_pos3) for (int q = 0; q < 3; q++) halo_pos3[3 * i + q] = H[i].pos[q];
-      if (halo_gather_rad) halo_gather_rad[i] = g;
+      if (halo_gather_rad) halo_gather_rad[i] = gr[(size_t)i];
       if (halo_npart) halo_npart[i] = H[i].npart;
       if (halo_host) halo_host[i] = H[i].host;
     }

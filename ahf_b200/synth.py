@@ -124,8 +124,11 @@ def make_box(n1d: int, seed: int = 42, clump_frac: float = 0.3, n_clumps: int | 
                vel_kms=v32, clump_centres=centres / box, clump_npart=cn, clump_scale=a_pl / box)
 
 
-def write_gadget1(box: Box, path: str) -> None:
-    """Little-endian GADGET-1, all particles of type 1 with massarr[1] > 0 (no MASS block)."""
+def write_gadget1(box: Box, path: str, big_endian: bool = False, version: int = 1, pos_offset: float = 0.0) -> None:
+    """GADGET-1 (default little-endian; big_endian / version=2 framing for the reader tests), all particles of type 1 with
+    massarr[1] > 0 (no MASS block).  pos_offset shifts all positions (file units; negative coordinates make the reader shift them back)."""
+    if big_endian or version != 1 or pos_offset != 0.0:
+        return _write_gadget_variant(box, path, big_endian, version, pos_offset)
     n = box.npart
     if n >= 2 ** 31 // 12:
         raise ValueError("single GADGET file limited by 32-bit block lengths; split the snapshot")
@@ -151,6 +154,32 @@ def write_gadget1(box: Box, path: str) -> None:
         block(f, x.tobytes())
         block(f, box.vel_kms.astype("<f4").tobytes())
         block(f, box.ids.astype("<u4").tobytes())
+
+
+def _write_gadget_variant(box: Box, path: str, big_endian: bool, version: int, pos_offset: float) -> None:
+    e = ">" if big_endian else "<"
+    n = box.npart
+    hdr = bytearray(256)
+    np_ = [0, n, 0, 0, 0, 0]
+    struct.pack_into(e + "6i", hdr, 0, *np_)
+    struct.pack_into(e + "6d", hdr, 24, 0.0, box.pmass / 1e10, 0.0, 0.0, 0.0, 0.0)
+    struct.pack_into(e + "2d", hdr, 72, 1.0, 0.0)
+    struct.pack_into(e + "2i", hdr, 88, 0, 0)
+    struct.pack_into(e + "6I", hdr, 96, *np_)
+    struct.pack_into(e + "2i", hdr, 120, 0, 1)
+    struct.pack_into(e + "4d", hdr, 128, box.boxsize, box.omega0, box.lambda0, 0.7)
+
+    def block(f, name: bytes, payload: bytes):
+        if version == 2:
+            f.write(struct.pack(e + "I", 8)); f.write(name); f.write(struct.pack(e + "I", len(payload) + 8)); f.write(struct.pack(e + "I", 8))
+        f.write(struct.pack(e + "I", len(payload))); f.write(payload); f.write(struct.pack(e + "I", len(payload)))
+
+    x = (box.pos.astype(np.float32) * np.float32(box.boxsize) + np.float32(pos_offset)).astype(e + "f4")
+    with open(path, "wb") as f:
+        block(f, b"HEAD", bytes(hdr))
+        block(f, b"POS ", x.tobytes())
+        block(f, b"VEL ", box.vel_kms.astype(e + "f4").tobytes())
+        block(f, b"ID  ", box.ids.astype(e + "u4").tobytes())
 
 
 def write_ahf_input(path: str, ic_filename: str, prefix: str, lgrid_domain: int, *, lgrid_max: int = 16777216,

@@ -172,6 +172,40 @@ def run_port_sample(n1d: int, seed: int):
     return box.npart / dt, dict(path_s=dt, npart=box.npart)
 
 
+def many_haloes_leg(g, ahf, synth, n1d, peak):
+    """The halo pass at a realistic halo count: the same generator with 2e4 small clumps (what a cosmological box of this size holds),
+    seeds from the DEVICE hierarchy; gather / sort / unbind / profiles timed with CUDA events over 3 passes (not part of `value`)."""
+    box = synth.make_box(n1d, seed=44, n_clumps=20000)
+    par = ahf.make_params(boxsize=box.boxsize, pmass=box.pmass, lgrid_dom=n1d)
+    g.set_params(par)
+    g.upload(box.pos, box.mom); g.sfc_sort_resident(); g.build_amr()
+    t0 = time.perf_counter()
+    hs = g.halo_seeds(3.0 / box.boxsize)
+    seeds_ms = 1e3 * (time.perf_counter() - t0)
+    c, r, s = np.ascontiguousarray(hs["pos"]), np.ascontiguousarray(hs["gather_rad"]), np.ascontiguousarray(hs["npart"], np.int64)
+    os.environ["AHFGPU_STAGES"] = "1"
+    st = []
+    for _ in range(4):
+        g.event_record(4)
+        g.construct_halos(c, r, s, fetch=False)
+        g.event_record(5)
+        q = {k: g.stage_ms(k) for k in ("halo_gather", "halo_sort", "halo_localize", "halo_unbind", "halo_profiles")}
+        q["total_events"] = g.event_elapsed_ms(4, 5)
+        q["gathered"] = g.stage_count("halo_gathered"); q["iter_members"] = g.stage_count("halo_unbind_iter_members"); q["final"] = g.stage_count("halo_final_members")
+        st.append(q)
+    os.environ["AHFGPU_STAGES"] = "0"
+    st = st[1:]
+    m = {k: float(np.mean([q[k] for q in st])) for k in st[0]}
+    scal = g.fetch_halos(len(r), scal_only=True)["scal"]
+    t = m["halo_gather"] + m["halo_sort"] + m["halo_unbind"] + m["halo_profiles"]
+    nbytes = 92.0 * m["gathered"] + 21.0 * m["iter_members"] + 28.0 * m["final"]
+    return {"workload": f"synthetic {n1d}^3 box with 20000 Plummer clumps (seed 44), halo seeds from the device hierarchy", "seeds": int(len(r)),
+            "haloes_ge_minpart": int((scal[:, 9] >= par.min_part).sum()), "seeds_ms": seeds_ms,
+            "stages_ms": {k: m[k] for k in ("halo_gather", "halo_sort", "halo_localize", "halo_unbind", "halo_profiles")}, "halo_pass_ms_events": m["total_events"],
+            "gathered_particles": m["gathered"], "unbind_pps": m["gathered"] / (t * 1e-3),
+            "roofline": {"algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (t * 1e-3) / 1e9, "frac": nbytes / (t * 1e-3) / 1e9 / peak}}
+
+
 def bench_slab(args, rank, world, local_rank, config):
     """ONE box over all ranks (strong scaling): a step = exchange (keys, block histogram all-reduce, partition, NCCL send/recv to owners and
     ghost holders, the one sort) + mesh on own cells and ghost shell (per level one small all-gather and one all-gather of row keys) + halo pass
@@ -310,6 +344,7 @@ def main():
     ap.add_argument("--ref-n1d", type=int, default=256, help="box of the reference arm / cpu_baseline leg (default: the N = 1 workload itself)")
     ap.add_argument("--seeds", default="device", choices=["device", "generator"], help="halo seeds of the N = 1 arm: from the device hierarchy (default) or the generator's clump centres")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-many-haloes", action="store_true", help="skip the second halo-pass measurement (box with 2e4 clumps, seeds from the device tree)")
     ap.add_argument("--breakdown", action="store_true", help="print the per-stage table to stderr")
     ap.add_argument("--mode", default="auto", choices=["auto", "boxes", "slab"],
                     help="'slab' = ONE box of --n1d^3 particles split into SFC slabs over the GPUs (default for N > 1, strong scaling); "
@@ -535,6 +570,8 @@ def main():
                        "unbind_pps": st["halo_gathered"] / ((st["halo_gather"] + st["halo_sort"] + st["halo_unbind"] + st["halo_profiles"]) * 1e-3),
                        "halo_gathered_particles": st["halo_gathered"], "levels": nlev, "halos_in": len(rad), "halos_ge_minpart": nhalo_ok},
     }
+    if not args.no_many_haloes and world == 1:
+        line["halo_pass_many_haloes"] = many_haloes_leg(g, ahf, synth, args.n1d, peak)
     if not args.no_cpu_baseline:
         from oracle import oracle as O
         nthreads = os.cpu_count() or 1

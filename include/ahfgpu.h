@@ -204,6 +204,21 @@ int  ahfgpu_adopt_sorted(ahfgpu_ctx *ctx, const void *pos4_dev, const void *mom4
                          int32_t has_weight, int32_t has_u);
 void *ahfgpu_device_ptr(ahfgpu_ctx *ctx, const char *name);
 
+/* ---- NEXT-4 of SURVEY 8f: bulk snapshot ingest --------------------------------------------------------------------------------------
+ * Replaces, for single-file GADGET-1/2 snapshots whose particle masses are in the header (no MASS block) and that hold no gas (no U
+ * block) -- BASELINE.json configs 1-4 --, io_gadget_readpart_raw (src/libio/io_gadget.c:427-568: one fread per value) and
+ * io_gadget_scale_particles (:857-995): the POS / VEL / ID blocks are read with one pread each into pinned memory and the extreme
+ * positions, the shift, the box check and the conversion to internal units run on the device in the reference's float32 arithmetic,
+ * so positions, momenta and keys are bit-identical to the reference's after startrun().  Afterwards the context holds the unsorted
+ * particles like after ahfgpu_upload_soa: continue with ahfgpu_sfc_sort_resident.  posscale / weightscale = GADGET_LUNIT / GADGET_MUNIT
+ * of AHF.input (<= 0: 1).  ids_out (n, may be NULL; query n with a first call): the ID block.  info[16]: 0 particles, 1 boxsize
+ * (simu.boxsize), 2 expansion, 3 omega0, 4 lambda0, 5 pmass, 6-8 shift applied, 9 scale_pos, 10 scale_mom, 11 GADGET version,
+ * 12 byte swapped, 13 hubble parameter, 14 ms reading + staging (host wall clock), 15 ms on the device (upload + kernels, CUDA events).
+ * Unsupported files are refused with an error, never read partially.
+ * ahfgpu_particles_get: the resident SORTED particles (float4 x,y,z,weight / float4 px,py,pz,u) copied to the host (tests).       */
+int  ahfgpu_ingest_gadget(ahfgpu_ctx *ctx, const char *path, double posscale, double weightscale, uint64_t *ids_out, double *info);
+int  ahfgpu_particles_get(ahfgpu_ctx *ctx, float *pos4, float *mom4);
+
 /* ---- measurement hooks (bench.py): milliseconds of the last call, by stage, measured with CUDA events on
  * the library's stream.  names: "h2d","keys","sort","gather","d2h","deposit","flag","refine","relink",
  * "halo_gather","halo_sort","halo_unbind","halo_profiles", ... ; returns <0 for an unknown name.             */
