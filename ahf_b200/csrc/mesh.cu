@@ -636,7 +636,14 @@ constexpr int DD_NS   = 4;                                           // TMA stag
 // round 2 (profiles/r2l_bench_256_n1.json): 2^26 units per particle with the carry detection only where an atomic returned a value
 // with its top bit set -- about 80 of the 354 warp instructions per 32 particles less (no carry replay loop, no per-term carry pair)
 // -- did NOT change the kernel time (0.344 vs 0.349 ms): the kernel is not bound by instruction issue.
+// Round 2b: the experiment k_deposit_dom2 works in 2^28 units per particle (D2_S): the z weights are taken at 28 bits (dom_wz_scale), the
+// products stay IMAD.HI, the middle term of every triple stays the complement, so every particle deposits EXACTLY 2^28 units and a 32-bit
+// word holds 16 particles' worth.  k_deposit_dom runs the same arithmetic when asked to (AHFGPU_DOM_S=28, implied by AHFGPU_DOM_V2=1): then
+// both kernels add the same integers.  It is NOT the default: truncation errors have a sign (edge terms down, middle terms up), so next to a
+// cell with 10^4 particles a neighbour's sum is off by ~10^4 units -- 1.1e-6 of its own density at 2^-28 (measured on the 128^3 box against
+// the float64 sum; the north star's 1e-5 still holds), 16 times less at 2^-32.
 constexpr int DD_S    = 32;
+constexpr int D2_S    = 28;
 constexpr int DD_SMEM = DD_NS * DT_SUB * 16 + (DD_CAR + DT_HH) * 4 + 8 * DD_NS * (DT_THREADS / 32);   // DT_SUB*16 = 16 warps x 512 B per ring slot
 
 __device__ __forceinline__ uint32_t pos_q32(float x) { return x >= 1.0f ? 0u : __float2uint_rz(x * 4294967296.0f); }   // x == 1 -> cell 0 (lltools.c:61-64)
@@ -646,6 +653,10 @@ __device__ __forceinline__ void tsc_q32(uint32_t t32, uint32_t (&w)[3])
   w[0] = (uint32_t)(((unsigned long long)a31 * a31) >> 31);
   w[2] = (uint32_t)(((unsigned long long)t31 * t31) >> 31);
   w[1] = 0u - w[0] - w[2];
+}
+__device__ __forceinline__ void dom_wz_scale(uint32_t (&wz)[3], const int wsh)      // z weights in 2^-(32 - wsh): the three still add up to exactly one particle
+{
+  if (wsh) { wz[0] >>= wsh; wz[2] >>= wsh; wz[1] = (1u << (32 - wsh)) - wz[0] - wz[2]; }
 }
 // low word += v (native ATOMS.ADD, old value returned).  Whether the low word wrapped is the carry-out of old + v; dom_carry
 // shifts it into a per-thread bit mask (IADD3 with carry-out + IADD3.X: two instructions, no predicate, no branch).  The
@@ -666,7 +677,7 @@ __constant__ uint16_t c_dom_off[27];     // byte offset of term (k,j,a) inside t
 template <int VAR>      // 0 = product; 1..4 = timing experiments (AHFGPU_DOM_VARIANT): 1 no return/carry, 2 no atomics, 3 no flush, 4 one copy
 __global__ void __launch_bounds__(DT_THREADS, 2)
 k_deposit_dom(const float4 *__restrict__ pos4, const int4 *__restrict__ work, const int *__restrict__ Wp, int L, int logL,
-              unsigned long long *__restrict__ acc, const uint32_t one /* == 1, a run-time value on purpose: see dom_carry */, const int rmax)
+              unsigned long long *__restrict__ acc, const uint32_t one /* == 1, a run-time value on purpose: see dom_carry */, const int rmax, const int wsh)
 {
   const int W = *Wp;                                   // the grid is an upper bound of the work list (no host read-back of its length)
   if ((int)blockIdx.x >= W) return;
@@ -743,6 +754,7 @@ k_deposit_dom(const float4 *__restrict__ pos4, const int4 *__restrict__ work, co
     const int  cid = valid ? (intile ? widx : -2) : -1;
     uint32_t wx[3], wy[3], wz[3], wyz[9];
     tsc_q32(ux << logL, wx); tsc_q32(uy << logL, wy); tsc_q32(uz << logL, wz);
+    dom_wz_scale(wz, wsh);
 #pragma unroll
     for (int k = 0; k < 3; k++) {
       wyz[k * 3 + 0] = __umulhi(wy[0], wz[k]); wyz[k * 3 + 2] = __umulhi(wy[2], wz[k]);
@@ -850,6 +862,350 @@ k_deposit_dom(const float4 *__restrict__ pos4, const int4 *__restrict__ work, co
     }
   }
   __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// D4 domain level, round 2b: k_deposit_dom2 -- EXPERIMENT, opt-in (AHFGPU_DOM_V2=1), bit-identical to k_deposit_dom, measured SLOWER.
+//   k_deposit_dom is bound by the shared-memory atomic pipe: 27 ATOMS per particle at ~3 wavefronts each (the cells of 32 Hilbert-adjacent
+//   particles fall on effectively random banks), two cycles per wavefront = 86 % l1tex busy at 0.35 ms (profiles/r2n_*).  No tile layout removes
+//   that (scripts/bank_sim.py); what removes it is giving the LANES a structure:
+//     pass 0  the particles of a tile are one contiguous range in which the particles of one CELL are adjacent (the key's leading bits are the
+//             cell): heads of the cell runs are found by comparing neighbours, first[cell] = index of the run's first particle; the others
+//             go to lists (ranks 1 .. 7 of a run: list A; the body of a longer run: list B);
+//     march   thread = one (x, y) column of the tile, a warp = 16 x-consecutive columns of rows y and y + 8 (8 x 18 words = 16 banks apart),
+//             walking z = 0 .. 15.  The column's 27 running sums live in REGISTERS as a window of three z planes: the first particle of cell
+//             (x, y, z) adds its 27 terms, then plane z is complete for this column and leaves with 9 ATOMS whose 32 addresses are 2 x 16
+//             consecutive words: one wavefront each.  9 conflict-free atomics per CELL instead of 27 conflicting ones per particle;
+//     rest    list A scatters lane per particle.
+//   Sums are single 32-bit words in 2^-28 units (16 particles' worth).  Every particle deposits exactly 2^28 units, so a wrapped word shows as
+//   a tile total that is short by a multiple of 2^32: the CTA checks sum(tile) == np * 2^28 and, if not (clump tiles; normally caught in pass 0
+//   by a run longer than 8), redoes the tile in the `heavy` form: every sum leaves as two 16-bit limbs into two words per cell (no wrap for
+//   any count a chunk can hold), and list B is walked: a thread takes 8 consecutive entries, keeps the 27 sums of the current cell in
+//   registers, flushes on a cell change, with REDUX when the flushing lanes hold one cell.  Chunks of tiles above 8192 particles go there
+//   directly.  All terms are the integers of k_deposit_dom: the sums are identical bit for bit whatever path served a tile
+//   (tests/test_gpu_large.py::test_domain_deposit_kernels_agree).
+//   MEASURED (profiles/r2w_dom2_ncu_summary.txt, 256^3): the march does what it was built for -- 1.00 wavefronts per ATOMS, shared-memory
+//   wavefronts of the whole kernel 56 M -> 22 M, l1tex busy 86 % -> 48 % -- but the kernel needs MORE instructions than k_deposit_dom
+//   (226 M against 185 M warp instructions: pass 0 57 M, march + list A 68 M, heavy tiles 58 M, flush 32 M, against a lattice that fills only
+//   ~55 % of the march's lanes) and is issue / latency bound at 24 warps per SM: 0.39 ms against 0.35 ms on the bench box, 0.28 against 0.26
+//   on a pure lattice.  A TSC deposit with exact integer sums costs >= ~100 instructions per particle (27 products, 27 sums, 36 for the
+//   weights) before any bookkeeping: 52 M warp instructions at 256^3, 0.08 ms at the 60 % issue rate these kernels reach -- the shared-atomic
+//   pipe is not the only wall between this stage and half the HBM roofline.
+// ------------------------------------------------------------------------------------------------
+constexpr int D2_THREADS = 256;
+constexpr int D2_NW      = D2_THREADS / 32;
+constexpr int D2_FP      = DT_T + 2;                   // row pitch of first[] (u16): rows y and y + 8 fall on different banks
+constexpr int D2_FIRST_N = DT_T * DT_T * D2_FP;
+constexpr int D2_EMPTY   = 0xFFFF;
+constexpr int D2_WALK    = 8;
+constexpr int D2_RUN     = 8;                          // particles of a cell run beyond this rank go to the walk list
+constexpr int D2_LEFT_N  = DT_CHUNK + 32 * D2_NW;      // every warp's segment starts at a multiple of 32
+constexpr int D2_SMEM    = 2 * DT_HH * 4 + D2_FIRST_N * 2 + D2_LEFT_N * 2;              // LO | HI | first[] | left[]
+static_assert(DT_CHUNK <= 65534, "u16 particle indices");
+static_assert((2 * DT_HH * 4) % 16 == 0 && (D2_FIRST_N * 2) % 16 == 0, "left[] is read with 16-byte loads");
+
+__device__ __forceinline__ void red_s32(uint32_t addr, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+// in-tile particle: no x == 1 clamp to think of (pass 0 sends such a tile to the heavy form, whose walk uses pos_q32)
+__device__ __forceinline__ uint32_t pos_q32_in(float x) { return __float2uint_rz(x * 4294967296.0f); }
+template <bool INTILE>
+__device__ __forceinline__ void dom2_weights(const float4 q, const int logL, const bool act, uint32_t (&wx)[3], uint32_t (&wyz)[9])
+{
+  const uint32_t ux = INTILE ? pos_q32_in(q.x) : pos_q32(q.x), uy = INTILE ? pos_q32_in(q.y) : pos_q32(q.y), uz = INTILE ? pos_q32_in(q.z) : pos_q32(q.z);
+  uint32_t wy[3], wz[3];
+  tsc_q32(ux << logL, wx); tsc_q32(uy << logL, wy); tsc_q32(uz << logL, wz);
+  dom_wz_scale(wz, 32 - D2_S);
+#pragma unroll
+  for (int k = 0; k < 3; k++) wz[k] = act ? wz[k] : 0u;                    // an empty cell adds zeros: no divergence in the 27-term block
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    wyz[k * 3 + 0] = __umulhi(wy[0], wz[k]); wyz[k * 3 + 2] = __umulhi(wy[2], wz[k]);
+    wyz[k * 3 + 1] = wz[k] - wyz[k * 3 + 0] - wyz[k * 3 + 2];
+  }
+}
+// one sum into the tile: a single word (light form) or two 16-bit limbs into LO and HI = LO + DT_HH words (heavy form)
+template <bool SPLIT> __device__ __forceinline__ void dom2_put(uint32_t lo_addr, uint32_t v)
+{
+  if (SPLIT) { red_s32(lo_addr, v & 0xffffu); red_s32(lo_addr + 4u * DT_HH, v >> 16); }
+  else red_s32(lo_addr, v);
+}
+// local cell of a particle inside the tile at (x0, y0, z0): (lz * 16 + ly) * 16 + lx, or -2 (outside: only x == 1.0f, which ll() clamps to
+// cell 0, can do that).  trunc(x * L) == trunc(x * 2^32) >> (32 - logL) for 0 <= x < 1 (L is a power of two: the product is exact)
+__device__ __forceinline__ int dom2_cell(const float4 q, const float Lf, const int x0, const int y0, const int z0)
+{
+  const int lx = __float2int_rz(q.x * Lf) - x0, ly = __float2int_rz(q.y * Lf) - y0, lz = __float2int_rz(q.z * Lf) - z0;
+  return ((unsigned)(lx | ly | lz) < (unsigned)DT_T) ? (lz * DT_T + ly) * DT_T + lx : -2;
+}
+
+// march: column (x, y), source cells z = 0 .. 15; a[(z + c) % 3][b * 3 + t] = running sum of target plane z + c (tile coordinates with the rim).
+// Steps z = 16, 17 have no source cell and only let the last two planes leave.  Unrolled by three (the window's period), not by 18: the
+// fully unrolled kernel was 300 KB of code and a third of its stalls were instruction fetches.
+template <bool SPLIT>
+__device__ __forceinline__ void dom2_march(const float4 *__restrict__ P, const uint32_t first_s, const uint32_t lo_s, const int lane, const int wrp, const int logL)
+{
+  const int x = lane & 15, y = wrp + 8 * (lane >> 4);
+  uint32_t pb = lo_s + 4u * (uint32_t)(y * DT_H + x);                     // target (a, b, c) = (0, 0, 0) of the current source cell
+  uint32_t fa = first_s + 2u * (uint32_t)(y * D2_FP + x);
+  uint32_t a[3][9];
+#pragma unroll
+  for (int t = 0; t < 9; t++) { a[0][t] = 0u; a[1][t] = 0u; }
+  uint32_t idn = lds_u16(fa);
+  float4   qn = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (idn != (uint32_t)D2_EMPTY) qn = __ldg(P + idn);
+#pragma unroll 1
+  for (int zz = 0; zz < DT_T + 2; zz += 3) {
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+      const int    z = zz + u;
+      const bool   act = idn != (uint32_t)D2_EMPTY;
+      const float4 q = qn;
+      idn = (uint32_t)D2_EMPTY;
+      if (z + 1 < DT_T) {
+        fa += 2u * (uint32_t)(DT_T * D2_FP);
+        idn = lds_u16(fa);
+        if (idn != (uint32_t)D2_EMPTY) qn = __ldg(P + idn);
+      }
+      if (z < DT_T) {                                                     // warp uniform
+        uint32_t wx[3], wyz[9];
+        dom2_weights<true>(q, logL, act, wx, wyz);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const int slot = (u + c) % 3;
+#pragma unroll
+          for (int b = 0; b < 3; b++) {
+            const uint32_t w = wyz[c * 3 + b];
+            const uint32_t v0 = __umulhi(wx[0], w), v2 = __umulhi(wx[2], w), v1 = w - v0 - v2;
+            if (c == 2) { a[slot][b * 3 + 0] = v0; a[slot][b * 3 + 1] = v1; a[slot][b * 3 + 2] = v2; }      // a plane enters the window
+            else { a[slot][b * 3 + 0] += v0; a[slot][b * 3 + 1] += v1; a[slot][b * 3 + 2] += v2; }
+          }
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < 3; b++)                                         // plane z has all it gets from this column
+#pragma unroll
+        for (int t = 0; t < 3; t++) dom2_put<SPLIT>(pb + 4u * (uint32_t)(b * DT_H + t), a[u][b * 3 + t]);
+      pb += 4u * (uint32_t)(DT_H * DT_H);
+    }
+  }
+}
+// lane per particle: the entries [0, n) of a warp's list
+template <bool SPLIT>
+__device__ __forceinline__ void dom2_scatter(const float4 *__restrict__ P, const uint32_t list_s, const int n, const uint32_t lo_s, const int lane, const int logL,
+                                             const int sh, const int x0, const int y0, const int z0)
+{
+  for (int j = lane; j < n; j += 32) {
+    const float4 q = __ldg(P + lds_u16(list_s + 2u * (uint32_t)j));
+    const int lx = (int)(pos_q32_in(q.x) >> sh) - x0, ly = (int)(pos_q32_in(q.y) >> sh) - y0, lz = (int)(pos_q32_in(q.z) >> sh) - z0;
+    const uint32_t t0 = lo_s + 4u * (uint32_t)((lz * DT_H + ly) * DT_H + lx);
+    uint32_t wx[3], wyz[9];
+    dom2_weights<true>(q, logL, true, wx, wyz);
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int b = 0; b < 3; b++) {
+        const uint32_t w = wyz[c * 3 + b];
+        const uint32_t v0 = __umulhi(wx[0], w), v2 = __umulhi(wx[2], w), v1 = w - v0 - v2;
+        const uint32_t tb = t0 + 4u * (uint32_t)((c * DT_H + b) * DT_H);
+        dom2_put<SPLIT>(tb, v0); dom2_put<SPLIT>(tb + 4u, v1); dom2_put<SPLIT>(tb + 8u, v2);
+      }
+  }
+}
+
+__global__ void __launch_bounds__(D2_THREADS, 3)
+k_deposit_dom2(const float4 *__restrict__ pos4, const int4 *__restrict__ work, const int *__restrict__ Wp, int L, int logL,
+               unsigned long long *__restrict__ acc, const int force_heavy, unsigned int *__restrict__ stats)
+{
+  const int W = *Wp;                                   // the grid is an upper bound of the work list (no host read-back of its length)
+  if ((int)blockIdx.x >= W) return;
+  extern __shared__ __align__(16) unsigned char dsm[];
+  uint32_t *LO = reinterpret_cast<uint32_t *>(dsm);
+  __shared__ int s_heavy;
+  __shared__ unsigned long long s_red[D2_NW];
+  const int4 wk = work[blockIdx.x];
+  const int  np = wk.y;
+  const bool sole = wk.w != 0;
+  const int  x0 = (wk.z & 1023) * DT_T, y0 = ((wk.z >> 10) & 1023) * DT_T, z0 = ((wk.z >> 20) & 1023) * DT_T;
+  const int  M = L - 1, sh = 32 - logL;
+  const float Lf = (float)L;
+  const int  lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const uint32_t lo_s = smem_u32(LO), first_s = lo_s + 8u * DT_HH, left_s = first_s + 2u * D2_FIRST_N;
+  const float4 *__restrict__ P = pos4 + wk.x;
+  for (int i = threadIdx.x; i < DT_HH; i += D2_THREADS) LO[i] = 0u;
+  for (int i = threadIdx.x; i < D2_FIRST_N / 2; i += D2_THREADS) LO[2 * DT_HH + i] = 0xFFFFFFFFu;
+  if (threadIdx.x == 0) s_heavy = (!sole || force_heavy) ? 1 : 0;
+  __syncthreads();
+  // ---- pass 0: warp w owns the slices [sl0, sl1) of 32 particles.  Heads of the cell runs -> first[]; every other particle goes to the
+  //      warp's own segment of left[]: ranks 1 .. D2_RUN - 1 of a run from the segment's start upwards (list A, nA entries), the body of a
+  //      long run (clump cores) from its end downwards (list B, nB entries; in particle order reversed: the runs of one cell stay together)
+  const int ns = (np + 31) >> 5, sl0 = (wrp * ns) / D2_NW, sl1 = ((wrp + 1) * ns) / D2_NW;
+  const uint32_t segA = left_s + 2u * (uint32_t)(sl0 * 32 + 32 * wrp);
+  const int      cap = (sl1 - sl0) * 32;
+  int nA = 0, nB = 0;
+  {
+    int carry = -3, carry_len = 0;                     // cell of the particle before the slice; length of the run it ends
+    if (sl0 > 0 && sl0 < sl1) carry = dom2_cell(__ldg(P + sl0 * 32 - 1), Lf, x0, y0, z0);
+    bool flag = false;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int sl = sl0; sl < sl1; sl += 4) {
+      float4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) { const int i = (sl + u) * 32 + lane; if (sl + u < sl1 && i < np) q[u] = __ldg(P + i); }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (sl + u >= sl1) break;                       // warp uniform
+        const int  i = (sl + u) * 32 + lane;
+        const bool valid = i < np;
+        const int  cid = valid ? dom2_cell(q[u], Lf, x0, y0, z0) : -1;
+        int prev = __shfl_up_sync(0xffffffffu, cid, 1);
+        if (lane == 0) prev = carry;
+        carry = __shfl_sync(0xffffffffu, cid, 31);
+        const bool     brk = cid != prev;                                  // a new run starts here (a clamped particle starts one too)
+        const bool     head = valid && brk && cid >= 0;
+        const unsigned bb = __ballot_sync(0xffffffffu, brk), vb = __ballot_sync(0xffffffffu, valid);
+        const unsigned hb = __ballot_sync(0xffffffffu, head);
+        flag = flag || (__ballot_sync(0xffffffffu, valid && cid < 0) != 0u);                   // a clamped particle: heavy form (its walk knows ll()'s clamp)
+        // rank of the particle inside its run
+        const unsigned below = bb & (lt | (1u << lane));
+        const int rank = below ? lane - (31 - __clz(below)) : carry_len + lane + 1;
+        carry_len = (bb ? 31 - (31 - __clz(bb)) : carry_len + 32);       // run length up to and including lane 31
+        const bool toB = valid && !head && (rank >= D2_RUN || cid < 0);
+        const bool toA = valid && !head && !toB;
+        const unsigned ab = __ballot_sync(0xffffffffu, toA), Bb = __ballot_sync(0xffffffffu, toB);
+        flag = flag || Bb != 0u;                                           // a cell with more than D2_RUN particles: single words will not do
+        if (head) sts_u16(first_s + 2u * (uint32_t)((cid >> 4) * D2_FP + (cid & 15)), (uint32_t)i);
+        if (toA) sts_u16(segA + 2u * (uint32_t)(nA + __popc(ab & lt)), (uint32_t)i);
+        if (toB) sts_u16(segA + 2u * (uint32_t)(cap - 1 - nB - __popc(Bb & lt)), (uint32_t)i);
+        nA += __popc(ab); nB += __popc(Bb);
+        (void)hb; (void)vb;
+      }
+    }
+    if (flag && lane == 0) s_heavy = 1;
+  }
+  __syncthreads();
+  bool heavy = s_heavy != 0;
+  for (;;) {
+    if (!heavy) {
+      dom2_march<false>(P, first_s, lo_s, lane, wrp, logL);
+      dom2_scatter<false>(P, segA, nA, lo_s, lane, logL, sh, x0, y0, z0);
+      __syncthreads();
+      // every particle deposited exactly 2^DD_S units: a wrapped word (or a particle pass 0 lost) shows in the total
+      unsigned long long s = 0;
+      for (int i = threadIdx.x; i < DT_HH; i += D2_THREADS) s += LO[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) s_red[wrp] = s;
+      __syncthreads();
+      unsigned long long tot = 0;
+#pragma unroll
+      for (int w = 0; w < D2_NW; w++) tot += s_red[w];
+      if (tot == ((unsigned long long)np << D2_S)) break;
+      heavy = true;
+      if (stats && threadIdx.x == 0) atomicAdd(stats + 1, 1u);
+      __syncthreads();                                  // everybody has read LO
+    }
+    // ---- heavy form: sums leave as two 16-bit limbs (LO and HI get < 2^16 each per flush, at most DT_CHUNK flushes reach a word: no wrap).
+    //      First particles by the same march, list A lane per particle; list B (the bodies of long runs) by a register walk: a thread takes
+    //      D2_WALK consecutive entries (in a clump core: one cell), keeps the 27 sums of its current cell in registers (D2_WALK * 2^28 < 2^32)
+    //      and flushes on a cell change.  When all flushing lanes of the warp hold the same cell the limbs are summed with REDUX and one
+    //      lane issues the atomics.
+    if (stats && threadIdx.x == 0) atomicAdd(stats, 1u);
+    for (int i = threadIdx.x; i < 2 * DT_HH; i += D2_THREADS) LO[i] = 0u;
+    __syncthreads();
+    dom2_march<true>(P, first_s, lo_s, lane, wrp, logL);
+    dom2_scatter<true>(P, segA, nA, lo_s, lane, logL, sh, x0, y0, z0);
+    const uint32_t segB = segA + 2u * (uint32_t)(cap - nB);              // cap and nA + nB are multiples of ... not of 8: single loads
+    for (int e0 = 0; e0 < nB; e0 += 32 * D2_WALK) {
+      const int eb = e0 + lane * D2_WALK;
+      uint32_t a[27];
+      int      cur = -1;
+      float4   qn = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (eb < nB) qn = __ldg(P + lds_u16(segB + 2u * (uint32_t)eb));
+#pragma unroll 1
+      for (int k = 0; k <= D2_WALK; k++) {
+        const bool   have = k < D2_WALK && eb + k < nB;
+        const float4 q = qn;
+        if (k + 1 < D2_WALK && eb + k + 1 < nB) qn = __ldg(P + lds_u16(segB + 2u * (uint32_t)(eb + k + 1)));
+        int widx = -1, cx = 0, cy = 0, cz = 0;
+        uint32_t wx[3], wyz[9];
+        if (have) {
+          cx = (int)(pos_q32(q.x) >> sh); cy = (int)(pos_q32(q.y) >> sh); cz = (int)(pos_q32(q.z) >> sh);
+          const int lx = cx - x0, ly = cy - y0, lz = cz - z0;
+          if ((unsigned)(lx | ly | lz) < (unsigned)DT_T) widx = (lz * DT_H + ly) * DT_H + lx;
+          dom2_weights<false>(q, logL, true, wx, wyz);
+        }
+        const bool     need = widx != cur && cur >= 0;
+        const unsigned fm = __ballot_sync(0xffffffffu, need);
+        if (fm) {
+          const int  c0 = __shfl_sync(0xffffffffu, cur, __ffs(fm) - 1);
+          const bool same = __popc(fm) >= 4 && __ballot_sync(0xffffffffu, need && cur == c0) == fm;
+          if (same) {
+            if (need) {
+              const uint32_t t0 = lo_s + 4u * (uint32_t)cur;
+              const bool     leader = lane == __ffs(fm) - 1;
+#pragma unroll
+              for (int t = 0; t < 27; t++) {
+                const uint32_t l0 = __reduce_add_sync(fm, a[t] & 0xffffu), l1 = __reduce_add_sync(fm, a[t] >> 16);
+                if (leader) {
+                  const uint32_t ad = t0 + 4u * (uint32_t)(((t / 9) * DT_H + (t / 3) % 3) * DT_H + t % 3);
+                  red_s32(ad, l0); red_s32(ad + 4u * DT_HH, l1);
+                }
+              }
+            }
+          } else if (need) {
+            const uint32_t t0 = lo_s + 4u * (uint32_t)cur;
+#pragma unroll
+            for (int t = 0; t < 27; t++) dom2_put<true>(t0 + 4u * (uint32_t)(((t / 9) * DT_H + (t / 3) % 3) * DT_H + t % 3), a[t]);
+          }
+        }
+        if (widx != cur) {
+          cur = widx;
+#pragma unroll
+          for (int t = 0; t < 27; t++) a[t] = 0u;
+        }
+        if (have) {
+#pragma unroll
+          for (int r = 0; r < 9; r++) {
+            const uint32_t w = wyz[r];
+            const uint32_t v0 = __umulhi(wx[0], w), v2 = __umulhi(wx[2], w), v1 = w - v0 - v2;
+            if (widx >= 0) { a[r * 3 + 0] += v0; a[r * 3 + 1] += v1; a[r * 3 + 2] += v2; }
+            else {
+              // ll()'s coordinate clamp put the particle into a cell outside this tile: straight to the global accumulators
+              const int y = (cy + (r % 3) - 1) & M, z = (cz + (r / 3) - 1) & M;
+              const uint32_t vv[3] = { v0, v1, v2 };
+#pragma unroll
+              for (int t = 0; t < 3; t++) atomicAdd(&acc[(((size_t)z << logL | y) << logL) | (size_t)((cx + t - 1) & M)], (unsigned long long)vv[t]);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    break;
+  }
+  // ---- flush: plain 8-byte stores for the cells no other CTA can touch, REDG.ADD.64 for the tile rim and multi-chunk tiles.
+  //      Thread = one (hx, hy) column marching in z (no div / mod in the loop); the 68 columns beyond the 256 threads are spread item-wise
+  auto put = [&](const uint32_t ad, unsigned long long *col, const int hz, const bool inxy) {
+    unsigned long long val = lds_u32(ad);
+    if (heavy) val += (unsigned long long)lds_u32(ad + 4u * DT_HH) << 16;
+    if (val == 0) return;
+    unsigned long long *dstp = col + ((size_t)((z0 + hz - 1) & M) << (2 * logL));
+    if (inxy && hz >= 2 && hz <= DT_T - 1) *dstp = val; else atomicAdd(dstp, val);
+  };
+  {
+    const int hx = threadIdx.x % DT_H, hy = threadIdx.x / DT_H;         // columns 0 .. 255
+    const bool inxy = sole && hx >= 2 && hx <= DT_T - 1 && hy >= 2 && hy <= DT_T - 1;
+    unsigned long long *col = acc + (((size_t)((y0 + hy - 1) & M) << logL) | (size_t)((x0 + hx - 1) & M));
+#pragma unroll 1
+    for (int hz = 0; hz < DT_H; hz++) put(lo_s + 4u * (uint32_t)(hz * DT_H * DT_H + threadIdx.x), col, hz, inxy);
+    constexpr int REST = DT_H * DT_H - D2_THREADS;
+    for (int e = threadIdx.x; e < REST * DT_H; e += D2_THREADS) {
+      const int hz = e / REST, r = D2_THREADS + (e - hz * REST), hx2 = r % DT_H, hy2 = r / DT_H;
+      put(lo_s + 4u * (uint32_t)(hz * DT_H * DT_H + r), acc + (((size_t)((y0 + hy2 - 1) & M) << logL) | (size_t)((x0 + hx2 - 1) & M)), hz,
+          sole && hx2 >= 2 && hx2 <= DT_T - 1 && hy2 >= 2 && hy2 <= DT_T - 1);
+    }
   }
 }
 
@@ -1710,6 +2066,7 @@ void mesh_device_init()
   CUDA_CHECK(cudaFuncSetAttribute(k_deposit_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
   CUDA_CHECK(cudaFuncSetAttribute(k_deposit_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, DR_SMEM));
   CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
+  CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom2, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM));
 #ifdef AHFGPU_EXPERIMENTS      // timing-only variants of the domain kernel (wrong densities on purpose): never in the shipped library
   CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
   CUDA_CHECK(cudaFuncSetAttribute(k_deposit_dom<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
@@ -1735,7 +2092,7 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
   const bool dom_v1       = c->env.deposit_v1;           // previous float-weight domain kernel (A/B timing)
   // choice of kernel and fixed-point scale from the counts of the WHOLE box (g_*): every rank of a split box rounds like one GPU
   const bool tiles_dense  = lv.dense && lv.L >= 2 * DT_T && lv.g_npart_dep > 0 && !generic_only;
-  const int    S = (tiles_dense && !dom_v1) ? DD_S : fx_shift_for(lv.masstopartdens);    // k_deposit_dom works in 2^-DD_S units
+  const int    S = (tiles_dense && !dom_v1) ? (c->env.dom_v2 ? D2_S : c->env.dom_s) : fx_shift_for(lv.masstopartdens);    // k_deposit_dom works in 2^-S units
   const double fxscale = (double)(1ull << S);
   const bool tiles_sparse = !lv.dense && lv.lpos && lv.g_npart_dep >= 2048 && v.logL - 4 <= 20 && !generic_only;
   if ((tiles_dense || tiles_sparse) && lv.npart_dep > 0) {
@@ -1781,7 +2138,20 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
     {
       Stage sk(c, lv.dense ? "deposit_dom_kernel" : "deposit_ref_kernel", lv.npart_dep, lv.dense || c->env.stages);
       Stage skl(c, lvl_name("depk", lev_id).c_str(), W, c->env.level_stages);
-      if (tiles_dense && !dom_v1) {
+      if (tiles_dense && !dom_v1 && c->env.dom_v2 && c->env.dom_variant == 0) {
+        work4.reserve(W);
+        LAUNCH(c, k_tile_work4, nblk(ntile, 256), 256, 0, tstart.p, nchunk.p, woff.p, ntile, tbits, work4.p);
+        DevBuf<unsigned int> d2s;
+        if (c->env.dom2_stats) { d2s.reserve(2); CUDA_CHECK(cudaMemsetAsync(d2s.p, 0, 2 * sizeof(unsigned int), c->stream)); }
+        LAUNCH(c, k_deposit_dom2, (unsigned)W, D2_THREADS, D2_SMEM, c->pos4, work4.p, tot.p, (int)lv.L, v.logL, acc.p, c->env.dom2_heavy ? 1 : 0, d2s.p);
+        if (c->env.dom2_stats) {
+          unsigned int h[2] = { 0, 0 };
+          read_back(c, h, d2s.p, sizeof(h));
+          c->stage_cnt_extra["dom2_heavy_ctas"] = h[0]; c->stage_cnt_extra["dom2_failed_light"] = h[1];
+          d2s.release();
+        }
+      }
+      else if (tiles_dense && !dom_v1) {
         const int var = c->env.dom_variant;
         const int rmax = c->env.dom_rmax;           // slices with at most this many distinct cells take the run-reduction path (measured: 1 = whole warp in one cell is best; partial-mask REDUX costs more than the conflicts it removes)
         work4.reserve(W);
@@ -1791,7 +2161,7 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
         // AHFGPU_DOM_PERSIST=1: two persistent CTAs per SM striding over the items (measured slower: static striding loses the
         // hardware's dynamic balance between light and heavy tiles); default: one CTA per item
         const unsigned grid = c->env.dom_persist ? (unsigned)std::min(W, 2 * nsm) : (unsigned)W;
-#define DOM_LAUNCH(V) LAUNCH(c, k_deposit_dom<V>, grid, DT_THREADS, DD_SMEM, dom_pos, work4.p, tot.p, (int)lv.L, v.logL, acc.p, 1u, rmax)
+#define DOM_LAUNCH(V) LAUNCH(c, k_deposit_dom<V>, grid, DT_THREADS, DD_SMEM, dom_pos, work4.p, tot.p, (int)lv.L, v.logL, acc.p, 1u, rmax, 32 - S)
 #ifdef AHFGPU_EXPERIMENTS
         if (var == 1) DOM_LAUNCH(1); else if (var == 2) DOM_LAUNCH(2); else if (var == 3) DOM_LAUNCH(3); else if (var == 4) DOM_LAUNCH(4); else DOM_LAUNCH(0);
 #else

@@ -172,6 +172,37 @@ def test_domain_deposit_conserves_mass_exactly(A):
         assert np.array_equal(g.level(0, cells=False).dens.astype(np.float64), d)
 
 
+@pytest.mark.parametrize("n1d,seed,clumps", [(64, 46, None), (128, 43, None), (64, 5, 300)])
+def test_domain_deposit_kernels_agree(A, n1d, seed, clumps):
+    """k_deposit_dom2 (light form: cell heads + column march + leftovers; heavy form: register walk with two limbs; the mixture the box
+    asks for) and k_deposit_dom (asked to work in the same 2^-28 units) add the SAME integers: the domain densities must be identical bit for bit whichever serves a tile."""
+    from ahf_b200 import synth
+    box = synth.make_box(n1d, seed=seed, n_clumps=clumps)
+    par = A.make_params(boxsize=box.boxsize, pmass=box.pmass, lgrid_dom=n1d, lgrid_max=n1d)
+    out = {}
+    try:
+        for name, env in (("dom2", {"AHFGPU_DOM_V2": "1", "AHFGPU_DOM2_STATS": "1"}), ("dom2_heavy", {"AHFGPU_DOM_V2": "1", "AHFGPU_DOM2_HEAVY": "1", "AHFGPU_DOM2_STATS": "1"}),
+                          ("dom", {"AHFGPU_DOM_V2": "0", "AHFGPU_DOM_S": "28"})):
+            for k in ("AHFGPU_DOM2_HEAVY", "AHFGPU_DOM_V2", "AHFGPU_DOM2_STATS", "AHFGPU_DOM_S"):
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            with A.AhfGpu(par) as g:
+                g.sfc_sort(box.pos, box.mom)
+                g.build_amr()
+                out[name] = g.level(0, cells=False).dens.copy()
+                if name != "dom":
+                    out[name + "_stats"] = (g.stage_count("deposit_dom_ctas"), g.stage_count("dom2_heavy_ctas"), g.stage_count("dom2_failed_light"))
+    finally:
+        for k in ("AHFGPU_DOM2_HEAVY", "AHFGPU_DOM_V2", "AHFGPU_DOM2_STATS", "AHFGPU_DOM_S"):
+            os.environ.pop(k, None)
+    print(n1d, seed, out["dom2_stats"], out["dom2_heavy_stats"])
+    ctas, heavy, failed = out["dom2_stats"]
+    assert 0 < heavy < ctas, "the box should exercise both forms"
+    assert out["dom2_heavy_stats"][1] >= heavy and out["dom2_heavy_stats"][2] == 0
+    assert np.array_equal(out["dom2"].view(np.uint32), out["dom"].view(np.uint32))
+    assert np.array_equal(out["dom2_heavy"].view(np.uint32), out["dom"].view(np.uint32))
+
+
 def test_cooperative_halo_pass_equals_one_cta_per_halo(A):
     """one large host (4e5 members) with subclumps: the cooperative multi-block kernels (default) and the one-CTA-per-halo kernels
     give identical member lists and scalars / profiles equal to rounding (different but fixed summation trees)"""
