@@ -103,6 +103,56 @@ def tree_halos(stats_per_level, max_gather_rad: float) -> dict:
     return out
 
 
+class _CatalogueIn(C.Structure):
+    _fields_ = ([("nhalo", C.c_int64)] + [(k, C.c_void_p) for k in ("scal", "pos3", "member_off", "members", "prof_off", "prof", "species", "prof_species", "host",
+                                                                     "host_level", "sub_off", "sub", "part_id", "part_weight", "part_u")]
+                + [(k, C.c_double) for k in ("x_fac", "r_fac", "v_fac", "m_fac", "rho_fac", "phi_fac", "u_fac", "rho_vir", "pmass")]
+                + [("min_part", C.c_int32), ("flags", C.c_int32)])
+
+
+def catalogue_write(fprefix, scal, pos3, members, profiles, host, host_level, sub, part_id, fac: dict, min_part: int,
+                    part_u=None, part_weight=None, species=None, prof_species=None) -> dict:
+    """NEXT-3 (ahfgpu_catalogue_write): sub-halo re-hash, ordering and the four catalogue files.  members / profiles / sub: one array
+    per halo (profiles [25, nbins] or None, prof_species [3, nbins] or None); fac: x_fac r_fac v_fac m_fac rho_fac phi_fac u_fac rho_vir
+    pmass.  fprefix None: only the re-hash and the ordering.  Returns host / nsub after the re-hash and the rank (= halo ID) of every halo."""
+    L = lib()
+    nh = len(scal)
+    keep = []
+
+    def arr(a, dt):
+        a = np.ascontiguousarray(a, dt); keep.append(a); return a.ctypes.data
+    moff = np.zeros(nh + 1, np.int64); poff = np.zeros(nh + 1, np.int64); soff = np.zeros(nh + 1, np.int64)
+    for i in range(nh):
+        moff[i + 1] = moff[i] + len(members[i])
+        poff[i + 1] = poff[i] + (0 if profiles[i] is None else profiles[i].shape[1])
+        soff[i + 1] = soff[i] + len(sub[i])
+    mem = np.concatenate([np.asarray(m, np.int64) for m in members]) if nh and moff[-1] else np.zeros(1, np.int64)
+    prof = np.concatenate([np.asarray(p, np.float64).reshape(-1) for p in profiles if p is not None]) if poff[-1] else np.zeros(1)
+    subs = np.concatenate([np.asarray(q, np.int32) for q in sub]) if soff[-1] else np.zeros(1, np.int32)
+    cin = _CatalogueIn()
+    cin.nhalo = nh
+    cin.scal = arr(scal, np.float64); cin.pos3 = arr(pos3, np.float64); cin.member_off = arr(moff, np.int64); cin.members = arr(mem, np.int64)
+    cin.prof_off = arr(poff, np.int64); cin.prof = arr(prof, np.float64)
+    cin.host = arr(host, np.int32); cin.host_level = arr(host_level, np.int32); cin.sub_off = arr(soff, np.int64); cin.sub = arr(subs, np.int32)
+    cin.part_id = arr(part_id, np.uint64)
+    cin.part_u = arr(part_u, np.float32) if part_u is not None else None
+    cin.part_weight = arr(part_weight, np.float32) if part_weight is not None else None
+    flags = 0
+    if species is not None:
+        psp = np.concatenate([np.asarray(p, np.float64).reshape(-1) for p in prof_species if p is not None]) if poff[-1] else np.zeros(1)
+        cin.species = arr(species, np.float64); cin.prof_species = arr(psp, np.float64)
+        flags |= 1
+    for k in ("x_fac", "r_fac", "v_fac", "m_fac", "rho_fac", "phi_fac", "u_fac", "rho_vir", "pmass"):
+        setattr(cin, k, float(fac[k]))
+    cin.min_part = int(min_part); cin.flags = flags
+    ho = np.empty(max(nh, 1), np.int32); ns = np.empty(max(nh, 1), np.int32); rk = np.empty(max(nh, 1), np.int64)
+    L.ahfgpu_catalogue_write.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = L.ahfgpu_catalogue_write(None if fprefix is None else fprefix.encode(), C.byref(cin), _p(ho), _p(ns), _p(rk))
+    if rc != 0:
+        raise AhfGpuError(L.ahfgpu_last_error().decode())
+    return dict(host=ho[:nh].copy(), nsub=ns[:nh].copy(), rank=rk[:nh].copy())
+
+
 _lib = None
 
 

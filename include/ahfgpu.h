@@ -219,6 +219,43 @@ void *ahfgpu_device_ptr(ahfgpu_ctx *ctx, const char *name);
 int  ahfgpu_ingest_gadget(ahfgpu_ctx *ctx, const char *path, double posscale, double weightscale, uint64_t *ids_out, double *info);
 int  ahfgpu_particles_get(ahfgpu_ctx *ctx, float *pos4, float *mom4);
 
+/* ---- NEXT-3 of SURVEY 8f: what ahf_halos() does after the halo loop -- HOST code, no device work --------------------------------------
+ * Replaces the sub-halo re-hash with the final radii (src/libahf/ahf_halos.c:550-640, check_subhalo :5900-5916), the ordering by particle
+ * number (:720-741, Numerical Recipes' indexx, libutility/general.c:1093: the order of haloes with equal counts is reproduced) and the
+ * writers of the default build (libahf/ahf_io.c: <fprefix>.AHF_halos :2209-2345, .AHF_profiles :637-826, .AHF_substructure :429-503,
+ * .AHF_particles :1094-1175), byte for byte.  All arrays are in the order of the reference's halos[] array (ahfgpu_tree_halos):
+ *   scal / member_off / members / prof_off / prof / species / prof_species  as delivered by ahfgpu_halo_fetch(_species); members index
+ *                  part_id / part_u / part_weight (any numbering the caller likes, e.g. the input index of ahfgpu_particle_ids);
+ *   pos3           HALO.pos (the centres handed to ahfgpu_construct_halos);
+ *   host, host_level, sub_off / sub   hostHalo, hostHaloLevel and subStruct[] as spatialRef2halos leaves them (ahfgpu_tree_halos_ex);
+ *   part_u         GAS_PARTICLES build: type column = u >= 0 ? 0 : -u;  part_weight: MULTIMASS build without gas: (int)weight;  both NULL: 1;
+ *   flags bit 0    multi-species columns (the -DMULTIMASS -DGAS_PARTICLES build: gas / star blocks, M_gas M_star U_gas profile columns).
+ * fprefix = "<outfile_prefix>.z<redshift %.3f>" (ahf_halos.c:246-256); NULL: no files, only the outputs below.
+ * Optional outputs (nhalo each): host_out = hostHalo after the re-hash, nsub_out = numSubStruct after it, rank_out = the halo's ID
+ * (its position in the written order, counted over ALL haloes like the reference's j).                                            */
+typedef struct ahfgpu_catalogue_in {
+  int64_t         nhalo;
+  const double   *scal;
+  const double   *pos3;
+  const int64_t  *member_off;
+  const int64_t  *members;
+  const int64_t  *prof_off;
+  const double   *prof;
+  const double   *species;
+  const double   *prof_species;
+  const int32_t  *host;
+  const int32_t  *host_level;
+  const int64_t  *sub_off;
+  const int32_t  *sub;
+  const uint64_t *part_id;
+  const float    *part_weight;
+  const float    *part_u;
+  double          x_fac, r_fac, v_fac, m_fac, rho_fac, phi_fac, u_fac, rho_vir, pmass;
+  int32_t         min_part;
+  int32_t         flags;
+} ahfgpu_catalogue_in;
+int  ahfgpu_catalogue_write(const char *fprefix, const ahfgpu_catalogue_in *in, int32_t *host_out, int32_t *nsub_out, int64_t *rank_out);
+
 /* ---- measurement hooks (bench.py): milliseconds of the last call, by stage, measured with CUDA events on
  * the library's stream.  names: "h2d","keys","sort","gather","d2h","deposit","flag","refine","relink",
  * "halo_gather","halo_sort","halo_unbind","halo_profiles", ... ; returns <0 for an unknown name.             */

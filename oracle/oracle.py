@@ -450,6 +450,22 @@ def read_halos(dump_dir: str) -> RefHalos:
     return rh
 
 
+def read_halo_tree(dump_dir: str) -> dict:
+    """halo_tree.bin of oracle/ref_hooks.c dump_halo_tree(): hostHalo / hostHaloLevel / subStruct[] of every halo as spatialRef2halos
+    left them (the inputs of the sub-halo re-hash, ahf_halos.c:550-640) and hostHalo / subStruct[] after it."""
+    a = np.fromfile(os.path.join(dump_dir, "halo_tree.bin"), np.int32)
+    n = int(a[0]); k = 1
+    host_pre = np.empty(n, np.int32); level_pre = np.empty(n, np.int32); host_post = np.empty(n, np.int32)
+    sub_pre, sub_post = [], []
+    for i in range(n):
+        host_pre[i], level_pre[i], ns = a[k], a[k + 1], int(a[k + 2]); k += 3
+        sub_pre.append(a[k:k + ns].copy()); k += ns
+        host_post[i], ns = a[k], int(a[k + 1]); k += 2
+        sub_post.append(a[k:k + ns].copy()); k += ns
+    assert k == len(a)
+    return dict(host_pre=host_pre, level_pre=level_pre, sub_pre=sub_pre, host_post=host_post, sub_post=sub_post)
+
+
 def run_reference(ahf_input: str, dump_dir: str | None = None, threads: int | None = None, multimass: bool = False,
                   cwd: str | None = None) -> dict:
     """Run the hooked, otherwise unmodified reference binary; returns the REFHOOK_TIMING fields."""

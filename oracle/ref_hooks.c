@@ -285,6 +285,8 @@ typedef struct {
   uint64_t in_npart;
   uint64_t n_gather, n_rvir0, n_unbound, n_rvir1;
   int      nbins;
+  int      host_pre, hostlevel_pre, nsub_pre;     /* hostHalo / hostHaloLevel / subStruct[] as spatialRef2halos left them (before the re-hash) */
+  int     *sub_pre;
 } halorec;
 
 static halorec *recs  = NULL;
@@ -319,6 +321,11 @@ void refhook_constructHalo(HALO *h)
   r.halo = h;
   r.in_pos[0] = h->pos.x; r.in_pos[1] = h->pos.y; r.in_pos[2] = h->pos.z;
   r.in_gatherRad = h->gatherRad; r.in_npart = h->npart;
+  r.host_pre = h->hostHalo; r.hostlevel_pre = h->hostHaloLevel; r.nsub_pre = h->numSubStruct; r.sub_pre = NULL;
+  if (dump_dir() && h->numSubStruct > 0 && h->subStruct) {
+    r.sub_pre = malloc(h->numSubStruct * sizeof(int));
+    memcpy(r.sub_pre, h->subStruct, h->numSubStruct * sizeof(int));
+  }
   cur_rec = &r;
   ahf_halos_sfc_constructHalo(h);
   cur_rec = NULL;
@@ -339,6 +346,26 @@ void refhook_constructHalo(HALO *h)
 
 #define NSCAL 64
 static HALO *g_halos = NULL; static int g_numHalos = 0;
+static double u_fac_of_run(void) { double q = simu.boxsize / simu.t_unit; return q * q; }     /* ahf_halos.c:203 */
+/* halo_tree.bin: per halo (halos[] order) hostHalo, hostHaloLevel, numSubStruct, subStruct[] BEFORE the sub-halo re-hash (int32 each),
+ * then hostHalo, numSubStruct, subStruct[] AFTER it -- input and expected output of the re-hash restatement */
+static void dump_halo_tree(halorec *byidx)
+{
+  FILE *f = dump_open("halo_tree.bin");
+  long  i;
+  int32_t n = g_numHalos;
+  fwrite(&n, sizeof(int32_t), 1, f);
+  for (i = 0; i < g_numHalos; i++) {
+    HALO   *h = g_halos + i;
+    int32_t v[3] = { byidx[i].host_pre, byidx[i].hostlevel_pre, byidx[i].nsub_pre }, w[2] = { h->hostHalo, h->numSubStruct };
+    int     k;
+    fwrite(v, sizeof(int32_t), 3, f);
+    for (k = 0; k < byidx[i].nsub_pre; k++) { int32_t q = byidx[i].sub_pre ? byidx[i].sub_pre[k] : -1; fwrite(&q, sizeof(int32_t), 1, f); }
+    fwrite(w, sizeof(int32_t), 2, f);
+    for (k = 0; k < h->numSubStruct; k++) { int32_t q = h->subStruct[k]; fwrite(&q, sizeof(int32_t), 1, f); }
+  }
+  fclose(f);
+}
 static void dump_halos(void)
 {
   FILE *f, *fi, *fp;
@@ -346,6 +373,7 @@ static void dump_halos(void)
   int   k;
   halorec *byidx = calloc(g_numHalos > 0 ? g_numHalos : 1, sizeof(halorec));
   for (i = 0; i < nrecs; i++) { long j = recs[i].halo - g_halos; if (j >= 0 && j < g_numHalos) byidx[j] = recs[i]; }
+  dump_halo_tree(byidx);
   f  = dump_open("halos.bin");
   fi = dump_open("halo_ipart.bin");
   fp = dump_open("halo_prof.bin");
@@ -358,7 +386,7 @@ static void dump_halos(void)
     memset(g, 0, sizeof(g));
     g[0] = r_fac; g[1] = x_fac; g[2] = v_fac; g[3] = m_fac; g[4] = rho_fac; g[5] = phi_fac; g[6] = Hubble;
     g[7] = global.ovlim; g[8] = global.rho_vir; g[9] = (double)simu.AHF_MINPART; g[10] = simu.AHF_VTUNE;
-    g[11] = simu.MaxGatherRad; g[12] = global.a;
+    g[11] = simu.MaxGatherRad; g[12] = global.a; g[13] = u_fac_of_run(); g[14] = simu.pmass; g[15] = global.z;
     fwrite(hdr, sizeof(int64_t), 2, f);
     fwrite(g, sizeof(double), 16, f);
   }

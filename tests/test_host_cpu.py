@@ -266,3 +266,56 @@ def test_host_tree_and_halo_seeds_follow_reference(golden):
     assert np.array_equal(out["pos"], hs[:, 0:3]) and np.array_equal(out["gather_rad"], hs[:, 3])
     _, _, _, host = O.tree_to_halos(H[min_ref:], tree, 3.0 / float(golden.d["boxsize"]))
     assert np.array_equal(out["host"], host)
+
+
+# ---- NEXT-3: sub-halo re-hash, ordering, catalogue writers ------------------------------------------------------------------------------
+def _catalogue_case(kind):
+    from ahf_b200 import synth
+    if kind == "bench64":
+        return synth.make_box(64, seed=43), None, False
+    if kind == "clumps64":
+        return synth.make_box(64, seed=7, n_clumps=40, clump_frac=0.5), None, False
+    if kind == "host_a":
+        return synth.make_host_box(60000, n_sub=8, n1d_bg=32, seed=47), 64, False
+    if kind == "host_b":
+        return synth.make_host_box(30000, n_sub=12, n1d_bg=32, seed=48), 64, False
+    if kind == "species":
+        return synth.make_species_box(32, seed=42), None, True
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["bench64", "clumps64", "host_a", "host_b", "species"])
+def test_catalogue_writer_equals_reference_files(kind, tmp_path):
+    """ahfgpu_catalogue_write (host code of the library) fed with what the UNMODIFIED reference held when its halo loop had finished --
+    halo scalars, member lists, profiles, and hostHalo / hostHaloLevel / subStruct[] as its tree left them (oracle/ref_hooks.c) -- must
+    reproduce the re-hashed host links and substructure lists, the halo order, and the four catalogue files byte for byte."""
+    from ahf_b200 import ahf, synth
+    from oracle import oracle as O
+    box, lgrid, mm = _catalogue_case(kind)
+    exe = O.REF_BIN_MM if mm else O.REF_BIN
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    w = str(tmp_path)
+    inp = synth.write_reference_case_species(box, w) if mm else synth.write_reference_case(box, w, lgrid_domain=lgrid)
+    d = os.path.join(w, "dump")
+    O.run_reference(inp, dump_dir=d, multimass=mm)
+    P = O.read_particles(os.path.join(d, "particles.bin"), multimass=mm)
+    H = O.read_halos(d)
+    T = O.read_halo_tree(d)
+    g = H.glob
+    fac = dict(r_fac=g[0], x_fac=g[1], v_fac=g[2], m_fac=g[3], rho_fac=g[4], phi_fac=g[5], rho_vir=g[8], u_fac=g[13], pmass=g[14])
+    assert abs(g[15]) < 1e-12                                  # z = 0: the reference's file prefix is <prefix>.z0.000
+    profiles = [H.prof[i] if H.s[i, 9] >= g[9] else None for i in range(H.n)]
+    psp = None if not mm else [H.prof_species[i] if H.s[i, 9] >= g[9] else None for i in range(H.n)]
+    out = ahf.catalogue_write(os.path.join(w, "own.z0.000"), H.s, H.s[:, 0:3].copy(), H.members, profiles, T["host_pre"], T["level_pre"], T["sub_pre"],
+                              P.ids, fac, int(g[9]), part_u=P.u if mm else None, species=H.species if mm else None, prof_species=psp)
+    assert np.array_equal(out["host"], T["host_post"])
+    assert np.array_equal(out["nsub"], [len(q) for q in T["sub_post"]])
+    for ext in ("AHF_halos", "AHF_profiles", "AHF_substructure", "AHF_particles"):
+        a = open(os.path.join(w, "ref.z0.000." + ext), "rb").read(); b = open(os.path.join(w, "own.z0.000." + ext), "rb").read()
+        if a != b:
+            la, lb = a.split(b"\n"), b.split(b"\n")
+            k = next((q for q in range(min(len(la), len(lb))) if la[q] != lb[q]), min(len(la), len(lb)))
+            raise AssertionError("%s differs at line %d:\n ref %r\n own %r" % (ext, k, la[k:k + 1], lb[k:k + 1]))
+    if kind.startswith("host"):
+        assert (T["host_post"] >= 0).sum() >= 5                # the case does exercise surviving sub-haloes
