@@ -89,12 +89,16 @@ def tree_halos(stats_per_level, max_gather_rad: float) -> dict:
     sub = np.empty(max(rows, 1) * 2 + 8, np.int32); cap = rows + 1
     nh = C.c_int64(0)
     pos = np.zeros((cap, 3)); g = np.zeros(cap); npart = np.zeros(cap, np.int64); host = np.zeros(cap, np.int32)
-    rc = L.ahfgpu_tree_halos(len(niso), _p(niso), _p(st), max_gather_rad, _p(dau), _p(close), _p(off), _p(sub), len(sub), C.byref(nh),
-                             _p(pos), _p(g), _p(npart), _p(host), cap)
+    hlev = np.zeros(cap, np.int32); hsoff = np.zeros(cap + 1, np.int64); hsub = np.zeros(cap, np.int32)
+    L.ahfgpu_tree_halos_ex.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    rc = L.ahfgpu_tree_halos_ex(len(niso), _p(niso), _p(st), max_gather_rad, _p(dau), _p(close), _p(off), _p(sub), len(sub), C.byref(nh),
+                                _p(pos), _p(g), _p(npart), _p(host), cap, _p(hlev), _p(hsoff), _p(hsub), cap)
     if rc != 0:
         raise AhfGpuError(L.ahfgpu_last_error().decode())
     out = dict(daughter=[], close=[], sub=[], pos=pos[:nh.value].copy(), gather_rad=g[:nh.value].copy(), npart=npart[:nh.value].copy(),
-               host=host[:nh.value].copy())
+               host=host[:nh.value].copy(), host_level=hlev[:nh.value].copy(),
+               halo_sub=[hsub[hsoff[i]:hsoff[i + 1]].copy() for i in range(nh.value)])
     r = 0
     for n in niso:
         out["daughter"].append(dau[r:r + n].astype(np.int64)); out["close"].append(close[r:r + n].copy())

@@ -38,10 +38,10 @@ inline bool inside(double v, double lo, double hi)
 
 }  // namespace
 
-extern "C" int ahfgpu_tree_halos(int32_t nlev, const int64_t *niso, const double *stats, double max_gather_rad,
-                                 int32_t *daughter, double *close_ref_dist, int64_t *sub_offset, int32_t *sub, int64_t sub_cap,
-                                 int64_t *nhalo, double *halo_pos3, double *halo_gather_rad, int64_t *halo_npart, int32_t *halo_host,
-                                 int64_t halo_cap)
+extern "C" int ahfgpu_tree_halos_ex(int32_t nlev, const int64_t *niso, const double *stats, double max_gather_rad,
+                                   int32_t *daughter, double *close_ref_dist, int64_t *sub_offset, int32_t *sub, int64_t sub_cap,
+                                   int64_t *nhalo, double *halo_pos3, double *halo_gather_rad, int64_t *halo_npart, int32_t *halo_host,
+                                   int64_t halo_cap, int32_t *halo_host_level, int64_t *halo_sub_offset, int32_t *halo_sub, int64_t halo_sub_cap)
 {
   try {
     if (nlev < 0 || (nlev && (!niso || !stats)) || !nhalo) AHF_FAIL("null argument");
@@ -156,7 +156,7 @@ extern "C" int ahfgpu_tree_halos(int32_t nlev, const int64_t *niso, const double
       if (sub_offset) sub_offset[row] = ns;
     }
     // ---- spatialRef2halos (:2405-2960): walk the tree level by level
-    struct Halo { double pos[3] = { 0, 0, 0 }; long long npart = 0; double rvir = -1.0; int host = -1; };
+    struct Halo { double pos[3] = { 0, 0, 0 }; long long npart = 0; double rvir = -1.0; int host = -1, host_level = -1; std::vector<int> subs; };
     std::vector<Halo> H;
     long long expect = 0;
     for (int i = 0; i < n; i++)
@@ -184,7 +184,8 @@ extern "C" int ahfgpu_tree_halos(int32_t nlev, const int64_t *niso, const double
           for (int k : r.sub)
             if (k != r.daughter) {
               H.emplace_back(); const int c = (int)H.size() - 1;
-              H[c].host = h; R[i + 1][k].halo = c; H[c].rvir = R[i + 1][k].close;
+              H[c].host = h; H[c].host_level = i; R[i + 1][k].halo = c; H[c].rvir = R[i + 1][k].close;
+              H[h].subs.push_back(c);                              // halos[primHaloIndex].subStruct[kcount] = count (:2705, :2872)
             }
       }
     while ((long long)H.size() < expect) H.emplace_back();
@@ -192,7 +193,7 @@ extern "C" int ahfgpu_tree_halos(int32_t nlev, const int64_t *niso, const double
     //      min(MaxGatherRad / boxsize, 1/4)
     const int64_t nh = (int64_t)H.size();
     *nhalo = nh;
-    if (nh > halo_cap && (halo_pos3 || halo_gather_rad || halo_npart || halo_host)) AHF_FAIL("halo buffers too small");
+    if (nh > halo_cap && (halo_pos3 || halo_gather_rad || halo_npart || halo_host || halo_host_level || halo_sub_offset)) AHF_FAIL("halo buffers too small");
     const double maxg = max_gather_rad < 0.25 ? max_gather_rad : 0.25;
     // the O(N_h^2) loop is an OpenMP loop in the reference (ahf_halos.c:2989-2993); here: host threads over blocks of haloes
     std::vector<double> gr((size_t)nh);
@@ -222,9 +223,27 @@ extern "C" int ahfgpu_tree_halos(int32_t nlev, const int64_t *niso, const double
       if (halo_gather_rad) halo_gather_rad[i] = gr[(size_t)i];
       if (halo_npart) halo_npart[i] = H[i].npart;
       if (halo_host) halo_host[i] = H[i].host;
+      if (halo_host_level) halo_host_level[i] = H[i].host_level;
+    }
+    if (halo_sub_offset) {
+      int64_t ns = 0;
+      for (int64_t i = 0; i < nh; i++) {
+        halo_sub_offset[i] = ns;
+        for (int k : H[i].subs) { if (halo_sub) { if (ns >= halo_sub_cap) AHF_FAIL("halo substructure buffer too small"); halo_sub[ns] = k; } ns++; }
+      }
+      halo_sub_offset[nh] = ns;
     }
     return 0;
   }
   catch (const ahf::Error &e) { ahf::g_last_error = e.msg; return -1; }
   catch (const std::exception &e) { ahf::g_last_error = e.what(); return -2; }
+}
+
+extern "C" int ahfgpu_tree_halos(int32_t nlev, const int64_t *niso, const double *stats, double max_gather_rad,
+                                 int32_t *daughter, double *close_ref_dist, int64_t *sub_offset, int32_t *sub, int64_t sub_cap,
+                                 int64_t *nhalo, double *halo_pos3, double *halo_gather_rad, int64_t *halo_npart, int32_t *halo_host,
+                                 int64_t halo_cap)
+{
+  return ahfgpu_tree_halos_ex(nlev, niso, stats, max_gather_rad, daughter, close_ref_dist, sub_offset, sub, sub_cap, nhalo, halo_pos3, halo_gather_rad,
+                              halo_npart, halo_host, halo_cap, nullptr, nullptr, nullptr, 0);
 }

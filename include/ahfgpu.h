@@ -125,6 +125,13 @@ int  ahfgpu_tree_halos(int32_t nlev, const int64_t *niso, const double *stats, d
                        int32_t *daughter, double *close_ref_dist, int64_t *sub_offset, int32_t *sub, int64_t sub_cap,
                        int64_t *nhalo, double *halo_pos3, double *halo_gather_rad, int64_t *halo_npart, int32_t *halo_host,
                        int64_t halo_cap);
+/* the same with what the sub-halo re-hash needs (ahfgpu_catalogue_write): per halo hostHaloLevel (coloured level that opened the
+ * sub-halo, ahf_halos.c:2699 / :2863; -1 for a field halo) and the substructure lists of the halos[] array as spatialRef2halos leaves
+ * them (CSR over the haloes, halo_sub_offset[nhalo + 1]; entries in the reference's order).  Capacity of halo_sub: halo_sub_cap. */
+int  ahfgpu_tree_halos_ex(int32_t nlev, const int64_t *niso, const double *stats, double max_gather_rad,
+                          int32_t *daughter, double *close_ref_dist, int64_t *sub_offset, int32_t *sub, int64_t sub_cap,
+                          int64_t *nhalo, double *halo_pos3, double *halo_gather_rad, int64_t *halo_npart, int32_t *halo_host,
+                          int64_t halo_cap, int32_t *halo_host_level, int64_t *halo_sub_offset, int32_t *halo_sub, int64_t halo_sub_cap);
 /* per particle (sorted offset): deepest level that owns it (node.ll membership after all relinks) and its cell
  * index on every level it reached: cell_of[lev*n + i] = index into the level's cell list or -1 */
 int  ahfgpu_amr_particle_levels(ahfgpu_ctx *ctx, int8_t *owner_level, int32_t *cell_of, int32_t nlev_cap);

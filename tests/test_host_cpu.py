@@ -319,3 +319,15 @@ def test_catalogue_writer_equals_reference_files(kind, tmp_path):
             raise AssertionError("%s differs at line %d:\n ref %r\n own %r" % (ext, k, la[k:k + 1], lb[k:k + 1]))
     if kind.startswith("host"):
         assert (T["host_post"] >= 0).sum() >= 5                # the case does exercise surviving sub-haloes
+    if not mm:
+        # the same links from the library's own tree (ahfgpu_tree_halos_ex on the per-refinement tables): hostHalo, hostHaloLevel and the
+        # substructure lists of halos[] as spatialRef2halos leaves them
+        n1d = lgrid or box.n1d
+        par = ahf.params_from_reference(g, lgrid_dom=n1d)
+        Hh = O.build_hierarchy(P.pos, n1d, patches=True)
+        m = ahf.min_ref(par, [lv.l1dim for lv in Hh])
+        stats = [np.hstack([lv.patch, O.patch_extents(lv).reshape(len(lv.patch), 6)]) for lv in Hh[m:]]
+        tr = ahf.tree_halos(stats, g[11] / g[1])
+        assert np.array_equal(tr["host"], T["host_pre"]) and np.array_equal(tr["host_level"], T["level_pre"])
+        assert all(np.array_equal(a, b) for a, b in zip(tr["halo_sub"], T["sub_pre"]))
+        assert np.array_equal(tr["pos"], H.s[:, 0:3]) and np.array_equal(tr["npart"], H.s[:, 4].astype(np.int64))
