@@ -15,6 +15,12 @@
  *                                                            (only in the AHF-b200 build; AHF-b200-kh keeps the CPU mesh)
  * Everything else -- readers, ahf_gridinfo, tree, subhalo re-hash, writers -- is the reference, so the catalogues come out in
  * AHF's own formats.
+ *
+ * -DAHFB200_FULL (binaries AHF-b200-full, AHF-b200-mm-full): main.c's calls of ahf_gridinfo (main.c:657) and ahf_halos (:662) land here
+ * as well.  ahfb200_halos does what ahf_halos() does (src/libahf/ahf_halos.c:166-930) with the library alone: patch labels and
+ * per-refinement tables on the device (NEXT-1/2: ahfgpu_amr_patch_stats), tree and halo seeds (ahfgpu_tree_halos_ex), the halo pass
+ * (ahfgpu_construct_halos), sub-halo re-hash, ordering and the four catalogue files (NEXT-3: ahfgpu_catalogue_write).  No quads are
+ * rebuilt and none of the reference's mesh walkers run; of the reference there remain the reader, startrun and the log file.
  */
 #ifndef _GNU_SOURCE
 #define _GNU_SOURCE                /* RTLD_NEXT */
@@ -164,6 +170,35 @@ static void build_level_quads(gridls *g, int64_t nc, const int32_t *x, const int
   { long i = 0; for (pqptr q = pq; q != NULL; q = q->next) g->pquad_array[i++] = q; }
 }
 
+#ifdef AHFB200_FULL
+/* nobody walks the reference's quads in this build: the grid list carries the level headers only (write_logfile, specific.c:1132) */
+gridls *ahfb200_gen_domgrids(int *no_grids)
+{
+  ahfgpu_params p;
+  gridls       *gl;
+  int           nlev, l;
+  if (simu.NGRID_MIN != simu.NGRID_DOM) { fprintf(stderr, "ahf_glue: NGRID_MIN != NGRID_DOM is not supported\n"); common_terminate(EXIT_FAILURE); }
+  ensure_ctx();
+  fill_params(&p);
+  if (ahfgpu_set_params(G, &p)) die("ahfgpu_set_params");
+  if (ahfgpu_build_amr(G)) die("ahfgpu_build_amr");
+  nlev = ahfgpu_amr_nlevels(G);
+  gl = (gridls *)calloc(nlev, sizeof(gridls));
+  for (l = 0; l < nlev; l++) {
+    int64_t io[4]; double dd[2];
+    gridls *g = gl + l;
+    if (ahfgpu_amr_level_header(G, l, io, dd)) die("ahfgpu_amr_level_header");
+    g->l1dim = (long unsigned)io[0]; g->spacing = 1.0 / (double)io[0]; g->spacing2 = g->spacing * g->spacing;
+    g->critdens = dd[0]; g->masstopartdens = dd[1];
+    g->masstodens = dd[1] * (double)simu.no_part / simu.no_vpart;
+    g->size.no_part = (long unsigned)io[2]; g->size.no_nodes = (long unsigned)io[1];
+    g->timecounter = global.super_t; g->next = (l < nlev - 1) ? TRUE : FALSE;
+  }
+  global.dom_grid = gl; global.domgrid_no = 0; global.fin_l1dim = gl[nlev - 1].l1dim;
+  *no_grids = nlev;
+  return gl;
+}
+#else
 gridls *ahfb200_gen_domgrids(int *no_grids)
 {
   ahfgpu_params p;
@@ -197,6 +232,7 @@ gridls *ahfb200_gen_domgrids(int *no_grids)
     build_level_quads(g, io[1], x, y, z, dens, rf, nodeptr[l]);
     free(x); free(y); free(z); free(dens); free(rf);
   }
+  global.fin_l1dim = gl[nlev - 1].l1dim;
   /* node particle lists */
   owner = malloc(n); cell_of = malloc((size_t)nlev * n * sizeof(int32_t));
   if (ahfgpu_amr_particle_levels(G, owner, cell_of, nlev)) die("ahfgpu_amr_particle_levels");
@@ -214,6 +250,8 @@ gridls *ahfb200_gen_domgrids(int *no_grids)
   *no_grids = nlev;
   return gl;
 }
+
+#endif /* AHFB200_FULL */
 
 void    ahfb200_ll(long unsigned npart, partptr fst_part, gridls *cur_grid) { (void)npart; (void)fst_part; (void)cur_grid; }
 void    ahfb200_zero_dens(gridls *g) { (void)g; }
@@ -355,3 +393,123 @@ static void check_flushed(void)
   if (npend > 0) { fprintf(stderr, "ahf_glue: %ld haloes were collected but never constructed on the device\n", npend); _Exit(EXIT_FAILURE); }
 }
 __attribute__((constructor)) static void ahfb200_register(void) { atexit(check_flushed); }
+
+
+#ifdef AHFB200_FULL
+/* ---- main.c:657 / :662 -- ahf_gridinfo + ahf_halos ---------------------------------------------------------------------------------------
+ * ahf_gridinfo's colouring runs on the device inside ahfb200_halos (ahfgpu_amr_patch_stats labels a level before it reduces it); what is
+ * left of it here is the level count and the log lines. */
+#include <math.h>
+#include <time.h>
+#include "libutility/cosmology.h"
+extern double u_fac;                                       /* src/libahf/ahf_halos.c:163 */
+
+void ahfb200_gridinfo(gridls *grid_list, int curgrid_no)
+{
+  (void)grid_list;
+  ahf.no_grids = curgrid_no - global.domgrid_no;          /* ahf_gridinfo.c:123; min_ref is subtracted in ahfb200_halos */
+  fprintf(io.logfile, "################## ahf_gridinfo ###################\n");
+  fprintf(io.logfile, "Number of grids           = %d\n", curgrid_no + 1);
+  fflush(io.logfile);
+}
+
+void ahfb200_halos(gridls *grid_list)
+{
+  ahfgpu_params       p;
+  ahfgpu_catalogue_in cat;
+  char     fprefix[MAXSTRING], file_no[MAXSTRING];
+  double   a = global.a, a3 = a * a * a, omega, ovlim, rho_crit, rho_b, rho_vir, refine_ovdens = 0.0;
+  int      nlev = ahfgpu_amr_nlevels(G), i, start = 1, nref, lev;
+  int64_t *niso, rows = 0, nh = 0, nmem = 0, nbin = 0, r0, k;
+  double  *stats, *ctr, *rad, *scal, *prof, *spc = NULL, *psp = NULL;
+  int64_t *seed, *moff, *mem, *poff, *hsoff;
+  int32_t *hhost, *hlev, *hsub;
+  uint64_t *pid;
+  float   *pu = NULL;
+  uint64_t n = global_info.no_part;
+  (void)grid_list;
+  /* conversion factors and cosmology, as ahf_halos.c:196-222 */
+  r_fac = simu.boxsize * global.a; x_fac = simu.boxsize; v_fac = simu.boxsize / simu.t_unit / global.a; m_fac = simu.pmass;
+  u_fac = pow2(simu.boxsize / simu.t_unit); rho_fac = simu.pmass / pow3(simu.boxsize); phi_fac = Grav * simu.pmass / (simu.boxsize * global.a);
+  omega = calc_omega(a); ovlim = calc_virial(a); Hubble = calc_Hubble(a);
+  rho_crit = a3 * calc_rho_crit(a); rho_b = omega * rho_crit; rho_vir = a3 * calc_rho_vir(a);
+  global.ovlim = ovlim; global.rho_b = rho_b; global.rho_vir = rho_vir;
+  /* first coloured level, as ahf_gridinfo.c:147-190 */
+  for (i = 0; i <= ahf.no_grids; i++) {
+    double fl1dim = (double)global.dom_grid[i].l1dim, refine_len = (double)(simu.boxsize / fl1dim), refine_vol = pow3(refine_len);
+    refine_ovdens = (simu.Nth_ref * (simu.pmass * simu.med_weight) / refine_vol) / rho_vir;
+    fprintf(io.logfile, "l1dim = %16.0f refine_ovdens = %16.4g ovlim = %16.4g\n", fl1dim, refine_ovdens, ovlim);
+    if (refine_ovdens < ovlim) start = i;
+  }
+  global.max_ovdens = refine_ovdens;
+  ahf.min_ref = start + AHF_MIN_REF_OFFSET;
+  ahf.no_grids = ahf.no_grids - ahf.min_ref + 1;
+  fprintf(io.logfile, "min_ref = %d    (ahf_nogrids = %d)\n", ahf.min_ref, ahf.no_grids);
+  fprintf(io.logfile, "#################### ahf_halos ####################\n");
+  fflush(io.logfile);
+  if (ahf.no_grids <= 0) return;                           /* ahf_halos.c:195 */
+  snprintf(fprefix, MAXSTRING, "%s.", global_io.params->outfile_prefix);
+  sprintf(file_no, "z%.3f", fabs(global.z));
+  strcat(fprefix, file_no);
+  fill_params(&p);
+  if (ahfgpu_set_params(G, &p)) die("ahfgpu_set_params");
+  /* per-refinement tables of the coloured levels (RefCentre), then tree + seeds (analyseRef, spatialRef2halos) */
+  timing.RefCentre -= time(NULL);
+  nref = nlev - ahf.min_ref;
+  niso = calloc(nref > 0 ? nref : 1, sizeof(int64_t));
+  for (lev = ahf.min_ref; lev < nlev; lev++) {
+    if (ahfgpu_amr_patch_stats(G, lev, niso + (lev - ahf.min_ref), NULL, 0)) die("ahfgpu_amr_patch_stats");
+    rows += niso[lev - ahf.min_ref];
+  }
+  stats = malloc((rows > 0 ? rows : 1) * 18 * sizeof(double));
+  for (lev = ahf.min_ref, r0 = 0; lev < nlev; lev++) {
+    int64_t q = 0;
+    if (ahfgpu_amr_patch_stats(G, lev, &q, stats + 18 * r0, rows - r0)) die("ahfgpu_amr_patch_stats");
+    r0 += q;
+  }
+  timing.RefCentre += time(NULL);
+  timing.analyseRef -= time(NULL);
+  ctr = malloc((rows + 1) * 3 * sizeof(double)); rad = malloc((rows + 1) * sizeof(double)); seed = malloc((rows + 1) * sizeof(int64_t));
+  hhost = malloc((rows + 1) * sizeof(int32_t)); hlev = malloc((rows + 1) * sizeof(int32_t)); hsoff = malloc((rows + 2) * sizeof(int64_t));
+  hsub = malloc((rows + 1) * sizeof(int32_t));
+  if (ahfgpu_tree_halos_ex(nref, niso, stats, simu.MaxGatherRad / simu.boxsize, NULL, NULL, NULL, NULL, 0, &nh, ctr, rad, seed, hhost, rows + 1,
+                           hlev, hsoff, hsub, rows + 1)) die("ahfgpu_tree_halos_ex");
+  timing.analyseRef += time(NULL);
+  simu.no_halos = (int)nh;
+  fprintf(io.logfile, "\nConstructing Halos (%ld)\n", (long)nh);
+  fflush(io.logfile);
+  /* halo pass */
+  timing.ahf_halos_sfc_constructHalo -= time(NULL);
+  if (ahfgpu_construct_halos(G, nh, ctr, rad, seed)) die("ahfgpu_construct_halos");
+  if (ahfgpu_halo_sizes(G, &nmem, &nbin)) die("ahfgpu_halo_sizes");
+  scal = malloc((nh > 0 ? nh : 1) * AHFGPU_NSCAL * sizeof(double)); moff = malloc((nh + 1) * sizeof(int64_t)); poff = malloc((nh + 1) * sizeof(int64_t));
+  mem = malloc((nmem > 0 ? nmem : 1) * sizeof(int64_t)); prof = malloc((nbin > 0 ? nbin : 1) * AHFGPU_NPROFCOL * sizeof(double));
+  if (ahfgpu_halo_fetch(G, scal, moff, mem, poff, prof)) die("ahfgpu_halo_fetch");
+#ifdef GAS_PARTICLES
+  spc = malloc((nh > 0 ? nh : 1) * 64 * sizeof(double)); psp = malloc((nbin > 0 ? nbin : 1) * 3 * sizeof(double));
+  if (ahfgpu_halo_fetch_species(G, spc, psp)) die("ahfgpu_halo_fetch_species");
+#endif
+  timing.ahf_halos_sfc_constructHalo += time(NULL);
+  /* re-hash, ordering, catalogues */
+  timing.ahf_io -= time(NULL);
+  pid = malloc((n > 0 ? n : 1) * sizeof(uint64_t));
+  for (k = 0; k < (int64_t)n; k++) pid[k] = (uint64_t)global_info.fst_part[k].id;
+#ifdef GAS_PARTICLES
+  pu = malloc((n > 0 ? n : 1) * sizeof(float));
+  for (k = 0; k < (int64_t)n; k++) pu[k] = (float)global_info.fst_part[k].u;
+#endif
+  memset(&cat, 0, sizeof(cat));
+  cat.nhalo = nh; cat.scal = scal; cat.pos3 = ctr; cat.member_off = moff; cat.members = mem; cat.prof_off = poff; cat.prof = prof;
+  cat.species = spc; cat.prof_species = psp; cat.host = hhost; cat.host_level = hlev; cat.sub_off = hsoff; cat.sub = hsub;
+  cat.part_id = pid; cat.part_u = pu; cat.part_weight = NULL;
+  cat.x_fac = x_fac; cat.r_fac = r_fac; cat.v_fac = v_fac; cat.m_fac = m_fac; cat.rho_fac = rho_fac; cat.phi_fac = phi_fac; cat.u_fac = u_fac;
+  cat.rho_vir = global.rho_vir; cat.pmass = simu.pmass; cat.min_part = simu.AHF_MINPART;
+#ifdef GAS_PARTICLES
+  cat.flags = 1;
+#endif
+  if (ahfgpu_catalogue_write(fprefix, &cat, NULL, NULL, NULL)) die("ahfgpu_catalogue_write");
+  timing.ahf_io += time(NULL);
+  free(niso); free(stats); free(ctr); free(rad); free(seed); free(hhost); free(hlev); free(hsoff); free(hsub);
+  free(scal); free(moff); free(poff); free(mem); free(prof); free(spc); free(psp); free(pid); free(pu);
+}
+#endif /* AHFB200_FULL */

@@ -38,4 +38,9 @@ build_one AHF-b200 "-Dgen_domgrids=ahfb200_gen_domgrids -Dll=ahfb200_ll -Dzero_d
 build_one AHF-b200-kh ""
 # AHF-b200-mm : the multi-species build (-DMULTIMASS -DGAS_PARTICLES), everything on the GPU
 build_one AHF-b200-mm "-Dgen_domgrids=ahfb200_gen_domgrids -Dll=ahfb200_ll -Dzero_dens=ahfb200_zero_dens -Dassign_npart=ahfb200_assign_npart -Dgen_AMRhierarchy=ahfb200_gen_AMRhierarchy" "-DMULTIMASS -DGAS_PARTICLES"
+# AHF-b200-full / AHF-b200-mm-full : additionally ahf_gridinfo and ahf_halos themselves (patch tables on the device, tree, halo pass, re-hash,
+#                                    ordering and catalogue writers from the library: NEXT-1/2/3 of SURVEY 8f); no quads are rebuilt
+MESH="-Dgen_domgrids=ahfb200_gen_domgrids -Dll=ahfb200_ll -Dzero_dens=ahfb200_zero_dens -Dassign_npart=ahfb200_assign_npart -Dgen_AMRhierarchy=ahfb200_gen_AMRhierarchy"
+build_one AHF-b200-full "$MESH -Dahf_gridinfo=ahfb200_gridinfo -Dahf_halos=ahfb200_halos" "-DAHFB200_FULL"
+build_one AHF-b200-mm-full "$MESH -Dahf_gridinfo=ahfb200_gridinfo -Dahf_halos=ahfb200_halos" "-DMULTIMASS -DGAS_PARTICLES -DAHFB200_FULL"
 ls -la "$OUT"

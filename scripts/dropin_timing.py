@@ -16,6 +16,7 @@ from ahf_b200 import synth          # noqa: E402
 from oracle import oracle as O      # noqa: E402
 
 DROPIN = os.path.join(ROOT, "ahf_b200", "host", "_build", "AHF-b200")
+DROPIN_FULL = os.path.join(ROOT, "ahf_b200", "host", "_build", "AHF-b200-full")     # ahf_gridinfo + ahf_halos replaced as well (NEXT-1/2/3)
 
 
 def run(exe, inp, cwd, threads):
@@ -43,7 +44,7 @@ def main():
         try:
             res = {"n1d": n1d, "particles": box.npart}
             dirs = {}
-            for tag, exe in (("reference", O.REF_BIN), ("dropin", DROPIN)):
+            for tag, exe in (("reference", O.REF_BIN), ("dropin", DROPIN), ("dropin_full", DROPIN_FULL)):
                 d = os.path.join(work, tag); dirs[tag] = d
                 inp = synth.write_reference_case(box, d)
                 walls = []
@@ -55,13 +56,15 @@ def main():
                     walls.append(w)
                 res[tag] = {"wall_s": walls, "best_s": min(walls), "hook_timing": t}
             pre = "ref.z0.000.AHF_"
-            same = {}
-            for f in ("particles", "substructure", "halos", "profiles"):
-                a = open(os.path.join(dirs["reference"], pre + f)).read(); b = open(os.path.join(dirs["dropin"], pre + f)).read()
-                same[f] = (a == b)
-            res["catalogues_byte_identical"] = same
+            for tag in ("dropin", "dropin_full"):
+                same = {}
+                for f in ("particles", "substructure", "halos", "profiles"):
+                    a = open(os.path.join(dirs["reference"], pre + f)).read(); b = open(os.path.join(dirs[tag], pre + f)).read()
+                    same[f] = (a == b)
+                res["catalogues_byte_identical" + ("" if tag == "dropin" else "_full")] = same
             res["halos"] = sum(1 for line in open(os.path.join(dirs["dropin"], pre + "halos")) if not line.startswith("#"))
             res["speedup_wall"] = res["reference"]["best_s"] / res["dropin"]["best_s"]
+            res["speedup_wall_full"] = res["reference"]["best_s"] / res["dropin_full"]["best_s"]
             out["runs"].append(res)
             print(json.dumps(res), file=sys.stderr, flush=True)
         finally:

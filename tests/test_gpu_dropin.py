@@ -25,7 +25,8 @@ def _num_table(path):
     return rows
 
 
-@pytest.mark.parametrize("variant", ["AHF-b200", "AHF-b200-kh"])      # full path on the GPU / CPU mesh + GPU sort & haloes
+# full path on the GPU / CPU mesh + GPU sort & haloes / ahf_gridinfo + ahf_halos replaced as well (device patch tables, library tree, re-hash, writers)
+@pytest.mark.parametrize("variant", ["AHF-b200", "AHF-b200-kh", "AHF-b200-full"])
 @pytest.mark.parametrize("n1d,seed,ncl", [(32, 21, 6), (64, 12, 14)])
 def test_catalogues_equal_reference(n1d, seed, ncl, variant):
     DROPIN = os.path.join(DROPIN_DIR, variant)
@@ -64,11 +65,12 @@ def test_catalogues_equal_reference(n1d, seed, ncl, variant):
         shutil.rmtree(work, ignore_errors=True)
 
 
+@pytest.mark.parametrize("variant", ["AHF-b200-mm", "AHF-b200-mm-full"])
 @pytest.mark.parametrize("n1d,seed,ncl", [(32, 11, 6), (64, 5, 10)])
-def test_species_catalogues_equal_reference(n1d, seed, ncl):
+def test_species_catalogues_equal_reference(n1d, seed, ncl, variant):
     """the multi-species build (-DMULTIMASS -DGAS_PARTICLES: gas + dark matter + stars): AHF-b200-mm against the reference's own
     multi-species binary -- the _halos file then carries the gas_only / stars_only columns, _profiles the M_gas / M_star / u_gas ones"""
-    DROPIN = os.path.join(DROPIN_DIR, "AHF-b200-mm")
+    DROPIN = os.path.join(DROPIN_DIR, variant)
     from ahf_b200 import synth
     from oracle import oracle as O
     if not (os.path.exists(DROPIN) and os.path.exists(O.REF_BIN_MM)):
@@ -101,5 +103,38 @@ def test_species_catalogues_equal_reference(n1d, seed, ncl):
             assert a[1] == b[1]
             cols = [i for i in range(len(a)) if i not in range(16, 25)]
             assert np.allclose(np.array(a)[cols], np.array(b)[cols], rtol=2e-5, atol=1e-4), [(i, a[i], b[i]) for i in cols if not np.isclose(a[i], b[i], rtol=2e-5, atol=1e-4)]
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def test_full_dropin_with_surviving_subhaloes():
+    """AHF-b200-full on a host with sub-clumps: the sub-halo re-hash keeps most of them (the boxes above have none that survive), so
+    hostHalo / numSubStruct columns and the .AHF_substructure file are exercised with content"""
+    DROPIN = os.path.join(DROPIN_DIR, "AHF-b200-full")
+    from ahf_b200 import synth
+    from oracle import oracle as O
+    if not (os.path.exists(DROPIN) and os.path.exists(O.REF_BIN)):
+        pytest.skip("drop-in / reference binaries not built (need /root/reference at build time)")
+    box = synth.make_host_box(60000, n_sub=8, n1d_bg=32, seed=47)
+    work = tempfile.mkdtemp(prefix="ahf_dropin_sub_")
+    try:
+        out = {}
+        for tag, exe in (("ref", O.REF_BIN), ("gpu", DROPIN)):
+            d = os.path.join(work, tag)
+            inp = synth.write_reference_case(box, d, lgrid_domain=64)
+            env = dict(os.environ); env.pop("AHF_DUMP_DIR", None)
+            pr = subprocess.run([exe, inp], cwd=d, env=env, capture_output=True, text=True)
+            assert pr.returncode == 0, pr.stderr[-3000:]
+            out[tag] = d
+        pre = "ref.z0.000.AHF_"
+        sub = open(os.path.join(out["ref"], pre + "substructure")).read()
+        assert len(sub.split()) >= 6
+        assert sub == open(os.path.join(out["gpu"], pre + "substructure")).read()
+        assert open(os.path.join(out["ref"], pre + "particles")).read() == open(os.path.join(out["gpu"], pre + "particles")).read()
+        hr, hg = _num_table(os.path.join(out["ref"], pre + "halos")), _num_table(os.path.join(out["gpu"], pre + "halos"))
+        assert len(hr) == len(hg)
+        for a, b in zip(hr, hg):
+            assert a[:3] == b[:3] and a[4] == b[4]
+            assert np.allclose(a, b, rtol=2e-5, atol=1e-4)
     finally:
         shutil.rmtree(work, ignore_errors=True)
