@@ -207,6 +207,8 @@ def lib():
         L.ahfgpu_particle_ids.argtypes = [C.c_void_p, C.c_void_p]
         L.ahfgpu_ingest_gadget.argtypes = [C.c_void_p, C.c_char_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
         L.ahfgpu_particles_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ahfgpu_input_peek.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.ahfgpu_ingest_prefetch.argtypes = [C.c_char_p]
         L.ahfgpu_adopt_sorted.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_int32]
         L.ahfgpu_sfc_sort_device4.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_int32]
         L.ahfgpu_hilbert_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
@@ -350,9 +352,12 @@ class AhfGpu:
                                                     C.c_void_p(u_ptr) if u_ptr else None, n))
         self.n = n
 
-    def ingest_gadget(self, path: str, posscale: float = 1.0, weightscale: float = 1.0, want_ids: bool = True):
-        """bulk GADGET ingest with on-device unit scaling (NEXT-4): returns (info dict, ids or None); continue with sfc_sort_resident()"""
-        info = np.zeros(16, np.float64)
+    def ingest_gadget(self, path: str, posscale: float = 1.0, weightscale: float = 1.0, want_ids: bool = True, prefetch: bool = False):
+        """bulk GADGET ingest with on-device unit scaling (NEXT-4): returns (info dict, ids or None); continue with sfc_sort_resident().
+        prefetch: read the blocks through ahfgpu_ingest_prefetch first (the host-only half the drop-in program runs ahead of the context)"""
+        if prefetch:
+            self._chk(self._L.ahfgpu_ingest_prefetch(path.encode()))
+        info = np.zeros(24, np.float64)
         self._chk(self._L.ahfgpu_ingest_gadget(self._h, path.encode(), posscale, weightscale, None, _p(info)))
         n = int(info[0])
         ids = None
@@ -361,7 +366,7 @@ class AhfGpu:
             self._chk(self._L.ahfgpu_ingest_gadget(self._h, path.encode(), posscale, weightscale, _p(ids), _p(info)))
         self.n = n
         keys = ("n", "boxsize", "expansion", "omega0", "lambda0", "pmass", "shift_x", "shift_y", "shift_z", "scale_pos", "scale_mom", "version", "swapped",
-                "hubble", "read_ms", "device_ms")
+                "hubble", "read_ms", "device_ms", "min_x", "min_y", "min_z", "max_x", "max_y", "max_z", "boxsize_file")
         return dict(zip(keys, info.tolist())), ids
 
     def particles(self):

@@ -1,5 +1,6 @@
 // api.cu -- extern "C" entry points of libahfgpu.so (see include/ahfgpu.h) and context housekeeping.
 #include "common.cuh"
+#include <chrono>
 #include "comm.cuh"
 #include "hilbert.cuh"
 #include <mutex>
@@ -138,6 +139,26 @@ static void check_params(const ahfgpu_params *p)
   if (p->lgrid_dom > (1 << 21)) AHF_FAIL("lgrid_dom above 2^21");
 }
 
+// context creation + module load + per-device kernel attributes / __constant__ symbols: once for each ordinal
+static void device_setup(int dev)
+{
+  const bool tm = getenv("AHFGPU_INIT_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
+  CUDA_CHECK(cudaSetDevice(dev));
+  static std::mutex mu; static bool done[64] = {};
+  std::lock_guard<std::mutex> lk(mu);
+  if (dev >= 64 || !done[dev]) {
+    CUDA_CHECK(cudaFree(nullptr));
+    const double t1 = now();
+    ahf::mesh_device_init();
+    const double t2 = now();
+    ahf::sfc_device_init();
+    if (dev < 64) done[dev] = true;
+    if (tm) fprintf(stderr, "AHFGPU_INIT_TIMING context=%.3f mesh_device_init=%.3f sfc_device_init=%.3f\n", t1 - t0, t2 - t1, now() - t2);
+  }
+}
+
 extern "C" {
 
 const char *ahfgpu_last_error(void) { return ahf::g_last_error.c_str(); }
@@ -149,6 +170,19 @@ int ahfgpu_device_count(void)
   return n;
 }
 
+// creates the CUDA context of `device` and loads the kernels ahead of ahfgpu_init: a host program calls it from a helper thread while it
+// parses its parameter file, so that the 0.5-1 s of driver start-up do not sit on its critical path (ahf_b200/host/ahf_glue.c)
+int ahfgpu_warmup(int32_t device)
+{
+  API_BEGIN
+  int ndev = 0;
+  CUDA_CHECK(cudaGetDeviceCount(&ndev));
+  if (ndev <= 0) AHF_FAIL("no CUDA device: libahfgpu has no CPU fallback");
+  if (device < 0 || device >= ndev) AHF_FAIL("device ordinal out of range");
+  device_setup(device);
+  API_END
+}
+
 int ahfgpu_init(ahfgpu_ctx **out, const ahfgpu_params *par)
 {
   API_BEGIN
@@ -158,15 +192,7 @@ int ahfgpu_init(ahfgpu_ctx **out, const ahfgpu_params *par)
   CUDA_CHECK(cudaGetDeviceCount(&ndev));
   if (ndev <= 0) AHF_FAIL("no CUDA device: libahfgpu has no CPU fallback");
   if (par->device < 0 || par->device >= ndev) AHF_FAIL("device ordinal out of range");
-  CUDA_CHECK(cudaSetDevice(par->device));
-  {                                                   // kernel attributes / __constant__ symbols are per device: once for each ordinal
-    static std::mutex mu; static bool done[64] = {};
-    std::lock_guard<std::mutex> lk(mu);
-    if (par->device >= 64 || !done[par->device]) {
-      ahf::mesh_device_init(); ahf::sfc_device_init();
-      if (par->device < 64) done[par->device] = true;
-    }
-  }
+  device_setup(par->device);
   ahfgpu_ctx *c = new ahfgpu_ctx();
   c->par = *par; c->dev = par->device;
   try {

@@ -13,6 +13,8 @@
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <memory>
+#include <mutex>
 
 namespace ahf {
 
@@ -77,18 +79,22 @@ __global__ void k_scale(float *__restrict__ pos3, float *__restrict__ mom3, uint
 
 }  // namespace
 
-// info[16]: 0 particles, 1 boxsize (after the extent check, file units x posscale), 2 expansion, 3 omega0, 4 lambda0, 5 pmass (mass of a
-// type-1 particle x weightscale, or of the lightest type present), 6-8 shift applied, 9 scale_pos, 10 scale_mom, 11 version (1/2),
-// 12 byte swapped, 13 hubble parameter of the file, 14 milliseconds reading (host wall clock), 15 milliseconds on the device (events)
-void ingest_gadget(ahfgpu_ctx *c, const char *path, double posscale, double weightscale, uint64_t *ids_out, double *info)
+// what the host-only half of the ingest leaves: header, framing, and (when prefetched) the three blocks in pageable memory
+struct Snapshot {
+  GadgetHeader H;
+  bool     swapped = false;
+  int      ver = 1;
+  uint64_t n = 0;
+  double   pmass = 0.0;
+  off_t    p_pos = 0, p_vel = 0, p_id = 0;
+  std::vector<float>    pos, vel;       // filled by the prefetch only
+  std::vector<uint32_t> id;
+  double   read_ms = 0.0;
+};
+
+// framing + header + block offsets (io_gadget.c:1107-1231, :427-470); refuses what the bulk path does not cover
+static void snapshot_open(int fd, Snapshot &S)
 {
-  const auto t0 = std::chrono::steady_clock::now();
-  const int fd = open(path, O_RDONLY);
-  if (fd < 0) AHF_FAIL(std::string("cannot open ") + path);
-  struct Closer { int fd; ~Closer() { close(fd); } } closer{ fd };
-  struct stat sb;
-  if (fstat(fd, &sb) != 0) AHF_FAIL("cannot stat the snapshot file");
-  // ---- framing: GADGET-1 starts with the header block (length 256), GADGET-2 with an 8-byte label block "HEAD" (io_gadget.c:1107-1231)
   uint32_t first = 0;
   pread_all(fd, &first, 4, 0);
   bool swapped = false; int ver = 1;
@@ -114,7 +120,7 @@ void ingest_gadget(ahfgpu_ctx *c, const char *path, double posscale, double weig
     off = payload + len + 4;
     return payload;
   };
-  GadgetHeader H;
+  GadgetHeader &H = S.H;
   {
     const off_t p = block("HEAD", 256);
     static_assert(sizeof(GadgetHeader) <= 256, "header layout");
@@ -139,12 +145,78 @@ void ingest_gadget(ahfgpu_ctx *c, const char *path, double posscale, double weig
   if (H.np[0] > 0) AHF_FAIL("gas particles (U block) are not supported by the bulk ingest");
   if (H.numfiles > 1) AHF_FAIL("multi-file snapshots are read one file per call: not in this round");
   if (n == 0 || n >= (1ull << 32)) AHF_FAIL("particle count out of range");
-  const off_t p_pos = block("POS ", 12 * n), p_vel = block("VEL ", 12 * n), p_id = block("ID  ", 4 * n);
+  S.swapped = swapped; S.ver = ver; S.n = n; S.pmass = pmass;
+  S.p_pos = block("POS ", 12 * n); S.p_vel = block("VEL ", 12 * n); S.p_id = block("ID  ", 4 * n);
+}
+
+// snapshots read ahead of the CUDA context (ahfgpu_ingest_prefetch), by path
+static std::mutex g_pref_mu;
+static std::map<std::string, std::unique_ptr<Snapshot>> g_pref;
+
+void ingest_prefetch(const char *path)
+{
+  const auto t0 = std::chrono::steady_clock::now();
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) AHF_FAIL(std::string("cannot open ") + path);
+  struct Closer { int fd; ~Closer() { close(fd); } } closer{ fd };
+  std::unique_ptr<Snapshot> S(new Snapshot());
+  snapshot_open(fd, *S);
+  const uint64_t n = S->n;
+  S->pos.resize(3 * n); S->vel.resize(3 * n); S->id.resize(n);
+  pread_all(fd, S->pos.data(), 12 * n, S->p_pos);
+  pread_all(fd, S->vel.data(), 12 * n, S->p_vel);
+  pread_all(fd, S->id.data(), 4 * n, S->p_id);
+  S->read_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  std::lock_guard<std::mutex> lk(g_pref_mu);
+  g_pref[path] = std::move(S);
+}
+
+// info[24]: 0 particles, 1 boxsize (after the extent check, file units x posscale), 2 expansion, 3 omega0, 4 lambda0, 5 pmass (mass of a
+// type-1 particle x weightscale, or of the lightest type present), 6-8 shift applied, 9 scale_pos, 10 scale_mom, 11 version (1/2),
+// 12 byte swapped, 13 hubble parameter of the file, 14 milliseconds reading (host wall clock), 15 milliseconds on the device (events),
+// 16-18 smallest / 19-21 largest raw position per axis (f->minpos / f->maxpos of the reference's file object), 22 boxsize after the extent
+// check in file units (what the reference leaves in header->boxsize), 23 reserved
+void ingest_gadget(ahfgpu_ctx *c, const char *path, double posscale, double weightscale, uint64_t *ids_out, double *info)
+{
+  const auto t0 = std::chrono::steady_clock::now();
+  std::unique_ptr<Snapshot> pre;
+  {
+    std::lock_guard<std::mutex> lk(g_pref_mu);
+    auto it = g_pref.find(path);
+    if (it != g_pref.end()) { pre = std::move(it->second); g_pref.erase(it); }
+  }
+  int fd = -1;
+  struct Closer { int &fd; ~Closer() { if (fd >= 0) close(fd); } } closer{ fd };
+  Snapshot S_local;
+  if (!pre) {
+    fd = open(path, O_RDONLY);
+    if (fd < 0) AHF_FAIL(std::string("cannot open ") + path);
+    snapshot_open(fd, S_local);
+  }
+  const Snapshot &S = pre ? *pre : S_local;
+  const GadgetHeader &H = S.H;
+  const uint64_t n = S.n;
+  const bool swapped = S.swapped;
+  const int ver = S.ver;
+  const double pmass = S.pmass;
+  const off_t p_pos = S.p_pos, p_vel = S.p_vel, p_id = S.p_id;
   // ---- bulk read + upload, block by block; ids stay on the host (the path carries the input index, ahfgpu_particle_ids)
   c->wait_mom(false);
   dfree(c->in_pos); dfree(c->in_mom); dfree(c->in_w); dfree(c->in_u);
   c->in_pos = c->in_mom = c->in_w = c->in_u = nullptr; c->in_n = n;
   c->in_pos = static_cast<float *>(cache_alloc(12 * n)); c->in_mom = static_cast<float *>(cache_alloc(12 * n));
+  cudaEvent_t e0, e1;
+  CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+  double read_ms = 0.0;
+  if (pre) {
+    // the blocks were read while the CUDA context was still being created: upload from pageable memory (the driver stages it; pinning
+    // 24 n bytes for one use would cost more than the staging)
+    CUDA_CHECK(cudaEventRecord(e0, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(c->in_pos, pre->pos.data(), 12 * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(c->in_mom, pre->vel.data(), 12 * n, cudaMemcpyHostToDevice, c->stream));
+    if (ids_out) for (uint64_t i = 0; i < n; i++) ids_out[i] = swapped ? bswap32(pre->id[i]) : pre->id[i];
+    read_ms = pre->read_ms;
+  } else {
   if (24 * n > c->h_up_bytes) {                                 // pinned staging of the context (kept between calls): positions | velocities
     if (c->h_up) cudaFreeHost(c->h_up);
     c->h_up = nullptr; c->h_up_bytes = 0;
@@ -152,8 +224,6 @@ void ingest_gadget(ahfgpu_ctx *c, const char *path, double posscale, double weig
     c->h_up_bytes = 24 * n;
   }
   void *stage2 = static_cast<char *>(c->h_up) + 12 * n;
-  cudaEvent_t e0, e1;
-  CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
   pread_all(fd, c->h_up, 12 * n, p_pos);
   CUDA_CHECK(cudaEventRecord(e0, c->stream));
   CUDA_CHECK(cudaMemcpyAsync(c->in_pos, c->h_up, 12 * n, cudaMemcpyHostToDevice, c->stream));
@@ -164,7 +234,8 @@ void ingest_gadget(ahfgpu_ctx *c, const char *path, double posscale, double weig
     pread_all(fd, raw.data(), 4 * n, p_id);
     for (uint64_t i = 0; i < n; i++) ids_out[i] = swapped ? bswap32(raw[i]) : raw[i];
   }
-  const double read_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  read_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
   if (swapped) {
     LAUNCH(c, k_bswap32, (unsigned)((3 * n + 255) / 256), 256, 0, reinterpret_cast<uint32_t *>(c->in_pos), 3 * n);
     LAUNCH(c, k_bswap32, (unsigned)((3 * n + 255) / 256), 256, 0, reinterpret_cast<uint32_t *>(c->in_mom), 3 * n);
@@ -197,10 +268,43 @@ void ingest_gadget(ahfgpu_ctx *c, const char *path, double posscale, double weig
     info[0] = (double)n; info[1] = boxsize * posscale; info[2] = H.expansion; info[3] = H.omega0; info[4] = H.omegalambda; info[5] = pmass * weightscale;
     info[6] = shift[0]; info[7] = shift[1]; info[8] = shift[2]; info[9] = scale_pos; info[10] = scale_mom; info[11] = ver; info[12] = swapped ? 1 : 0;
     info[13] = H.hubble; info[14] = read_ms; info[15] = dev_ms;
+    for (int d = 0; d < 3; d++) { info[16 + d] = (double)hmm[d]; info[19 + d] = (double)hmm[3 + d]; }
+    info[22] = boxsize; info[23] = 0.0;
   }
 }
 
 }  // namespace ahf
+
+// one particle of the UNSORTED input set (after ahfgpu_upload_soa / ahfgpu_ingest_gadget, before the sort releases it): the reference's
+// startrun prints the first and the last particle into its log file (startrun.c:378-431)
+// host-only half of ahfgpu_ingest_gadget: header checks and the three block reads into pageable memory, kept until the next
+// ahfgpu_ingest_gadget of the same path consumes them -- callable before any CUDA context exists (the drop-in program reads the
+// snapshot while its helper thread is still creating the context)
+extern "C" int ahfgpu_ingest_prefetch(const char *path)
+{
+  try {
+    if (!path) AHF_FAIL("null argument");
+    ahf::ingest_prefetch(path);
+    return 0;
+  } catch (const ahf::Error &e) { ahf::g_last_error = e.msg; return -1; }
+    catch (const std::exception &e) { ahf::g_last_error = e.what(); return -2; }
+    catch (...) { ahf::g_last_error = "unknown exception"; return -3; }
+}
+
+extern "C" int ahfgpu_input_peek(ahfgpu_ctx *c, uint64_t index, float *pos3, float *mom3)
+{
+  try {
+    if (!c || !pos3 || !mom3) AHF_FAIL("null argument");
+    if (!c->in_pos || !c->in_mom || index >= c->in_n) AHF_FAIL("no unsorted input particle with that index is resident");
+    CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
+    CUDA_CHECK(cudaMemcpyAsync(pos3, c->in_pos + 3 * index, 12, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(mom3, c->in_mom + 3 * index, 12, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+  } catch (const ahf::Error &e) { ahf::g_last_error = e.msg; return -1; }
+    catch (const std::exception &e) { ahf::g_last_error = e.what(); return -2; }
+    catch (...) { ahf::g_last_error = "unknown exception"; return -3; }
+}
 
 extern "C" int ahfgpu_ingest_gadget(ahfgpu_ctx *c, const char *path, double posscale, double weightscale, uint64_t *ids_out, double *info)
 {

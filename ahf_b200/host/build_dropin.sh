@@ -10,7 +10,7 @@ REF="${AHF_REFERENCE_SRC:-/root/reference/src}"
 OUT="$HERE/_build"
 [ -d "$REF" ] || { echo "build_dropin.sh: $REF not present - keeping prebuilt $OUT" >&2; exit 0; }
 build_one() {
-name="$1"; mainflags="$2"; defs="$3"
+name="$1"; mainflags="$2"; defs="$3"; iofileflags="$4"
 mkdir -p "$OUT/obj"
 CC="gcc -fopenmp -std=c99 -O2 -DWITH_OPENMP -DAHF $defs -w -I$REF -I$REPO/include"
 pids=()
@@ -20,6 +20,7 @@ for f in "$REF"/*.c "$REF"/lib*/*.c; do
   case "$base" in
     src_main)         extra="-Dsfc_curve_calcKey=ahfb200_calcKey -Dqsort=ahfb200_qsort $mainflags" ;;
     libahf_ahf_halos) extra="-Dahf_halos_sfc_constructHalo=ahfb200_constructHalo" ;;
+    libio_io_file)    extra="$iofileflags" ;;
   esac
   $CC $extra -c "$f" -o "$OUT/obj/$base.o" &
   pids+=($!)
@@ -29,7 +30,7 @@ wait
 $CC -c "$HERE/ahf_glue.c" -o "$OUT/ahf_glue.o"
 mv "$OUT/obj/src_main.o" "$OUT/"
 ar rcs "$OUT/libref.a" "$OUT"/obj/*.o
-gcc -fopenmp -o "$OUT/$name" "$OUT/src_main.o" "$OUT/ahf_glue.o" "$OUT/libref.a" -L"$REPO/ahf_b200" -lahfgpu -Wl,-rpath,'$ORIGIN/../..' -lm -ldl
+gcc -fopenmp -o "$OUT/$name" "$OUT/src_main.o" "$OUT/ahf_glue.o" "$OUT/libref.a" -L"$REPO/ahf_b200" -lahfgpu -Wl,-rpath,'$ORIGIN/../..' -lm -ldl -lpthread
 rm -rf "$OUT/obj" "$OUT/src_main.o" "$OUT/ahf_glue.o" "$OUT/libref.a"
 }
 # AHF-b200    : key/sort, mesh and halo loop on the GPU
@@ -41,6 +42,7 @@ build_one AHF-b200-mm "-Dgen_domgrids=ahfb200_gen_domgrids -Dll=ahfb200_ll -Dzer
 # AHF-b200-full / AHF-b200-mm-full : additionally ahf_gridinfo and ahf_halos themselves (patch tables on the device, tree, halo pass, re-hash,
 #                                    ordering and catalogue writers from the library: NEXT-1/2/3 of SURVEY 8f); no quads are rebuilt
 MESH="-Dgen_domgrids=ahfb200_gen_domgrids -Dll=ahfb200_ll -Dzero_dens=ahfb200_zero_dens -Dassign_npart=ahfb200_assign_npart -Dgen_AMRhierarchy=ahfb200_gen_AMRhierarchy"
-build_one AHF-b200-full "$MESH -Dahf_gridinfo=ahfb200_gridinfo -Dahf_halos=ahfb200_halos" "-DAHFB200_FULL"
+# AHF-b200-full additionally reads single-file GADGET snapshots through the bulk ingest (NEXT-4): libio/io_file.c's call of io_gadget_readpart lands in the glue
+build_one AHF-b200-full "$MESH -Dahf_gridinfo=ahfb200_gridinfo -Dahf_halos=ahfb200_halos" "-DAHFB200_FULL" "-Dio_gadget_readpart=ahfb200_gadget_readpart"
 build_one AHF-b200-mm-full "$MESH -Dahf_gridinfo=ahfb200_gridinfo -Dahf_halos=ahfb200_halos" "-DMULTIMASS -DGAS_PARTICLES -DAHFB200_FULL"
 ls -la "$OUT"

@@ -154,6 +154,49 @@ def run_reference_sample(n1d: int, seed: int, threads: int | None):
     return npart / path_s, dict(t, wall_s=wall, path_s=path_s, npart=npart)
 
 
+def dropin_leg(n1d: int, seed: int, ref_wall_s: float):
+    """The drop-in PROGRAM on the GADGET file the reference has just analysed (cpu_baseline leg): ahf_b200/host/_build/AHF-b200-full = the
+    reference's main / startrun / reader with key+sort, mesh, ahf_gridinfo and ahf_halos replaced by libahfgpu, from AHF.input to the four
+    written catalogues, wall clock of the whole process (CUDA context creation included), and whether the catalogues equal the reference's
+    byte for byte."""
+    import hashlib
+    import subprocess
+    exe = os.path.join(ROOT, "ahf_b200", "host", "_build", "AHF-b200-full")
+    if not os.path.exists(exe) or (n1d, seed) not in _REF_CASES:
+        return None
+    inp, npart = _REF_CASES[(n1d, seed)]
+    d = os.path.dirname(inp)
+    names = [f for f in sorted(os.listdir(d)) if ".AHF_" in f]
+
+    def digests():
+        return {f.split(".AHF_")[1]: hashlib.md5(open(os.path.join(d, f), "rb").read()).hexdigest() for f in names}
+    ref = digests()
+    for f in names:
+        os.remove(os.path.join(d, f))
+    env = dict(os.environ); env.pop("AHF_DUMP_DIR", None); env["AHFB200_TIMING"] = "1"
+    walls, phases = [], {}
+    for _ in range(2):                       # best of two: the CUDA driver start-up of a fresh process varies between 1 and 3 s on these boxes
+        for f in names:
+            if os.path.exists(os.path.join(d, f)):
+                os.remove(os.path.join(d, f))
+        t0 = time.perf_counter()
+        pr = subprocess.run([exe, inp], cwd=d, env=env, capture_output=True, text=True)
+        wall = time.perf_counter() - t0
+        if pr.returncode != 0:
+            return {"error": pr.stderr[-400:]}
+        if not walls or wall < min(walls):
+            for ln in pr.stderr.splitlines():
+                if ln.startswith("AHFB200_TIMING"):
+                    phases = {k: float(v) for k, v in (t.split("=") for t in ln.split()[1:])}
+        walls.append(wall)
+    wall = min(walls)
+    own = digests() if all(os.path.exists(os.path.join(d, f)) for f in names) else {}
+    return {"program": "ahf_b200/host/_build/AHF-b200-full", "workload": f"GADGET file of the {n1d}^3 box, AHF.input to the four catalogue files", "wall_s": wall,
+            "wall_s_runs": walls, "reference_wall_s": ref_wall_s, "speedup_wall": ref_wall_s / wall, "particles_per_s_wall": npart / wall,
+            "phases_s": phases, "phases_note": "ahfgpu_init = CUDA driver start-up + context creation of the fresh process (helper thread from program start)",
+            "catalogues_byte_identical": {k: own.get(k) == v for k, v in ref.items()}}
+
+
 def run_port_sample(n1d: int, seed: int):
     """CPU port (oracle/) on a bounded sample when the reference binary is not available."""
     from ahf_b200 import synth, ahf
@@ -344,6 +387,7 @@ def main():
     ap.add_argument("--ref-n1d", type=int, default=256, help="box of the reference arm / cpu_baseline leg (default: the N = 1 workload itself)")
     ap.add_argument("--seeds", default="device", choices=["device", "generator"], help="halo seeds of the N = 1 arm: from the device hierarchy (default) or the generator's clump centres")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the wall-clock run of the drop-in program on the reference leg's GADGET file")
     ap.add_argument("--no-many-haloes", action="store_true", help="skip the second halo-pass measurement (box with 2e4 clumps, seeds from the device tree)")
     ap.add_argument("--breakdown", action="store_true", help="print the per-stage table to stderr")
     ap.add_argument("--mode", default="auto", choices=["auto", "boxes", "slab"],
@@ -584,6 +628,10 @@ def main():
         else:
             v, d = run_port_sample(64, 43)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": "oracle/ C port on a 64^3 box of the same generator"}
+    if not args.no_cpu_baseline and "cpu_baseline" in line and line["cpu_baseline"]["kind"] == "reference" and not args.no_dropin:
+        dl = dropin_leg(args.ref_n1d, 43, d["wall_s"])
+        if dl is not None:
+            line["e2e_dropin"] = dl
     if args.breakdown:
         for k, v in sorted(line["stages_ms"].items()):
             print(f"  {k:22s} {v:10.3f} ms", file=sys.stderr)

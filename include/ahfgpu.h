@@ -45,7 +45,9 @@ typedef struct {
 const char *ahfgpu_last_error(void);
 int  ahfgpu_device_count(void);
 
-/* after startrun() (src/main.c:128) / before the final frees (src/main.c:671-707) */
+/* after startrun() (src/main.c:128) / before the final frees (src/main.c:671-707).  ahfgpu_warmup(device) may be called earlier, from a
+ * helper thread at program start: it creates the CUDA context and loads the kernels while the host parses its parameter file */
+int  ahfgpu_warmup(int32_t device);
 int  ahfgpu_init(ahfgpu_ctx **ctx, const ahfgpu_params *par);
 int  ahfgpu_set_params(ahfgpu_ctx *ctx, const ahfgpu_params *par);
 int  ahfgpu_finalize(ahfgpu_ctx *ctx);
@@ -218,13 +220,19 @@ void *ahfgpu_device_ptr(ahfgpu_ctx *ctx, const char *name);
  * positions, the shift, the box check and the conversion to internal units run on the device in the reference's float32 arithmetic,
  * so positions, momenta and keys are bit-identical to the reference's after startrun().  Afterwards the context holds the unsorted
  * particles like after ahfgpu_upload_soa: continue with ahfgpu_sfc_sort_resident.  posscale / weightscale = GADGET_LUNIT / GADGET_MUNIT
- * of AHF.input (<= 0: 1).  ids_out (n, may be NULL; query n with a first call): the ID block.  info[16]: 0 particles, 1 boxsize
+ * of AHF.input (<= 0: 1).  ids_out (n, may be NULL; query n with a first call): the ID block.  info[24]: 0 particles, 1 boxsize
  * (simu.boxsize), 2 expansion, 3 omega0, 4 lambda0, 5 pmass, 6-8 shift applied, 9 scale_pos, 10 scale_mom, 11 GADGET version,
- * 12 byte swapped, 13 hubble parameter, 14 ms reading + staging (host wall clock), 15 ms on the device (upload + kernels, CUDA events).
- * Unsupported files are refused with an error, never read partially.
+ * 12 byte swapped, 13 hubble parameter, 14 ms reading + staging (host wall clock), 15 ms on the device (upload + kernels, CUDA events),
+ * 16-18 / 19-21 smallest / largest raw position per axis (io_gadget_t minpos / maxpos, io_gadget.c:1320-1347), 22 header boxsize after
+ * the extent check (:879-896, file units), 23 reserved.  Unsupported files are refused with an error, never read partially.
+ * ahfgpu_ingest_prefetch(path): the host-only half (header checks + the three block reads into pageable memory), kept until the next
+ * ahfgpu_ingest_gadget of the same path; needs no CUDA context, so a host program can read while its context is still being created.
+ * ahfgpu_input_peek: one particle of the unsorted input set (the reference logs the first and last one, startrun.c:378-431).
  * ahfgpu_particles_get: the resident SORTED particles (float4 x,y,z,weight / float4 px,py,pz,u) copied to the host (tests).       */
 int  ahfgpu_ingest_gadget(ahfgpu_ctx *ctx, const char *path, double posscale, double weightscale, uint64_t *ids_out, double *info);
 int  ahfgpu_particles_get(ahfgpu_ctx *ctx, float *pos4, float *mom4);
+int  ahfgpu_ingest_prefetch(const char *path);
+int  ahfgpu_input_peek(ahfgpu_ctx *ctx, uint64_t index, float *pos3, float *mom3);
 
 /* ---- NEXT-3 of SURVEY 8f: what ahf_halos() does after the halo loop -- HOST code, no device work --------------------------------------
  * Replaces the sub-halo re-hash with the final radii (src/libahf/ahf_halos.c:550-640, check_subhalo :5900-5916), the ordering by particle

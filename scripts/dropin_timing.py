@@ -20,7 +20,7 @@ DROPIN_FULL = os.path.join(ROOT, "ahf_b200", "host", "_build", "AHF-b200-full") 
 
 
 def run(exe, inp, cwd, threads):
-    env = dict(os.environ); env.pop("AHF_DUMP_DIR", None); env["OMP_NUM_THREADS"] = str(threads)
+    env = dict(os.environ); env.pop("AHF_DUMP_DIR", None); env["OMP_NUM_THREADS"] = str(threads); env["AHFB200_TIMING"] = "1"
     t0 = time.perf_counter()
     pr = subprocess.run([exe, inp], cwd=cwd, env=env, capture_output=True, text=True)
     dt = time.perf_counter() - t0
@@ -28,7 +28,7 @@ def run(exe, inp, cwd, threads):
         raise RuntimeError(pr.stderr[-2000:])
     t = {}
     for line in pr.stderr.splitlines():
-        if line.startswith("REFHOOK_TIMING"):
+        if line.startswith("REFHOOK_TIMING") or line.startswith("AHFB200_TIMING"):
             for tok in line.split()[1:]:
                 k, v = tok.split("="); t[k] = float(v)
     return dt, t

@@ -26,9 +26,12 @@ def _num_table(path):
 
 
 # full path on the GPU / CPU mesh + GPU sort & haloes / ahf_gridinfo + ahf_halos replaced as well (device patch tables, library tree, re-hash, writers)
-@pytest.mark.parametrize("variant", ["AHF-b200", "AHF-b200-kh", "AHF-b200-full"])
+# AHF-b200-full reads the snapshot through the bulk ingest (ahfgpu_ingest_gadget behind io_gadget_readpart); "...:reader" = the same
+# binary with AHFB200_NO_INGEST=1, i.e. the reference's own reader and the host AoS path
+@pytest.mark.parametrize("variant", ["AHF-b200", "AHF-b200-kh", "AHF-b200-full", "AHF-b200-full:reader"])
 @pytest.mark.parametrize("n1d,seed,ncl", [(32, 21, 6), (64, 12, 14)])
 def test_catalogues_equal_reference(n1d, seed, ncl, variant):
+    variant, _, mode = variant.partition(":")
     DROPIN = os.path.join(DROPIN_DIR, variant)
     from ahf_b200 import synth
     from oracle import oracle as O
@@ -41,11 +44,21 @@ def test_catalogues_equal_reference(n1d, seed, ncl, variant):
         for tag, exe in (("ref", O.REF_BIN), ("gpu", DROPIN)):
             d = os.path.join(work, tag)
             inp = synth.write_reference_case(box, d)
-            env = dict(os.environ); env.pop("AHF_DUMP_DIR", None)
+            env = dict(os.environ); env.pop("AHF_DUMP_DIR", None); env["AHFB200_TIMING"] = "1"
+            if mode == "reader":
+                env["AHFB200_NO_INGEST"] = "1"
             pr = subprocess.run([exe, inp], cwd=d, env=env, capture_output=True, text=True)
             assert pr.returncode == 0, pr.stderr[-3000:]
             out[tag] = d
+            if tag == "gpu" and variant == "AHF-b200-full":
+                assert ("ingest_gadget=" in pr.stderr) == (mode != "reader"), pr.stderr[-600:]
         pre = "ref.z0.000.AHF_"
+        if variant == "AHF-b200-full":
+            # what startrun derives from the file object (boxsize, pmass, no_vpart, weights, species ...) must not depend on who read the file
+            pa, pb = (open(os.path.join(out[t], "ref.parameter")).read() for t in ("ref", "gpu"))
+            assert pa == pb
+            ha, hb = (open(os.path.join(out[t], pre + "halos")).read() for t in ("ref", "gpu"))
+            assert ha == hb
         # haloes: same count, integer columns identical, float columns to the precision the writer prints
         hr, hg = _num_table(os.path.join(out["ref"], pre + "halos")), _num_table(os.path.join(out["gpu"], pre + "halos"))
         assert len(hr) == len(hg) and len(hr) >= 3
