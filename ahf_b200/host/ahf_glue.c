@@ -617,6 +617,7 @@ void ahfb200_halos(gridls *grid_list)
   if (G_ingested) {                                          /* IDs of the ingested file through the sorted-offset -> input-index permutation */
     uint32_t *perm = malloc((n > 0 ? n : 1) * sizeof(uint32_t));
     if (!perm || ahfgpu_particle_ids(G, perm)) die("ahfgpu_particle_ids");
+#pragma omp parallel for schedule(static)
     for (k = 0; k < (int64_t)n; k++) pid[k] = G_ids[perm[k]];
     free(perm);
   } else

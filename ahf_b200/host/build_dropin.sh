@@ -18,7 +18,7 @@ for f in "$REF"/*.c "$REF"/lib*/*.c; do
   base="$(basename "$(dirname "$f")")_$(basename "$f" .c)"
   extra=""
   case "$base" in
-    src_main)         extra="-Dsfc_curve_calcKey=ahfb200_calcKey -Dqsort=ahfb200_qsort $mainflags" ;;
+    src_main)         case "$mainflags" in *ahfb200_nokeys*) extra="-Dqsort=ahfb200_qsort $mainflags" ;; *) extra="-Dsfc_curve_calcKey=ahfb200_calcKey -Dqsort=ahfb200_qsort $mainflags" ;; esac ;;
     libahf_ahf_halos) extra="-Dahf_halos_sfc_constructHalo=ahfb200_constructHalo" ;;
     libio_io_file)    extra="$iofileflags" ;;
   esac
@@ -41,8 +41,13 @@ build_one AHF-b200-kh ""
 build_one AHF-b200-mm "-Dgen_domgrids=ahfb200_gen_domgrids -Dll=ahfb200_ll -Dzero_dens=ahfb200_zero_dens -Dassign_npart=ahfb200_assign_npart -Dgen_AMRhierarchy=ahfb200_gen_AMRhierarchy" "-DMULTIMASS -DGAS_PARTICLES"
 # AHF-b200-full / AHF-b200-mm-full : additionally ahf_gridinfo and ahf_halos themselves (patch tables on the device, tree, halo pass, re-hash,
 #                                    ordering and catalogue writers from the library: NEXT-1/2/3 of SURVEY 8f); no quads are rebuilt
+# in the -full builds nobody reads the host AoS' keys (the device computes and sorts them): main.c's key loop (:343-350,
+#   `part->sfckey = sfc_curve_calcKey(ctype, x, y, z, bits)`) is reduced to a self-assignment the compiler drops, so that the loop does not
+#   page in the whole calloc'ed particle array (0.3-0.5 s at 256^3): ahfb200_nokeys.h, pre-included into main.c.  If upstream renames the
+#   loop variable the build fails loudly.  The patch a maintainer would make instead is in INTEGRATION.md.
+NOKEYS="-include $HERE/ahfb200_nokeys.h"
 MESH="-Dgen_domgrids=ahfb200_gen_domgrids -Dll=ahfb200_ll -Dzero_dens=ahfb200_zero_dens -Dassign_npart=ahfb200_assign_npart -Dgen_AMRhierarchy=ahfb200_gen_AMRhierarchy"
 # AHF-b200-full additionally reads single-file GADGET snapshots through the bulk ingest (NEXT-4): libio/io_file.c's call of io_gadget_readpart lands in the glue
-build_one AHF-b200-full "$MESH -Dahf_gridinfo=ahfb200_gridinfo -Dahf_halos=ahfb200_halos" "-DAHFB200_FULL" "-Dio_gadget_readpart=ahfb200_gadget_readpart"
-build_one AHF-b200-mm-full "$MESH -Dahf_gridinfo=ahfb200_gridinfo -Dahf_halos=ahfb200_halos" "-DMULTIMASS -DGAS_PARTICLES -DAHFB200_FULL"
+build_one AHF-b200-full "$MESH -Dahf_gridinfo=ahfb200_gridinfo -Dahf_halos=ahfb200_halos $NOKEYS" "-DAHFB200_FULL" "-Dio_gadget_readpart=ahfb200_gadget_readpart"
+build_one AHF-b200-mm-full "$MESH -Dahf_gridinfo=ahfb200_gridinfo -Dahf_halos=ahfb200_halos $NOKEYS" "-DMULTIMASS -DGAS_PARTICLES -DAHFB200_FULL"
 ls -la "$OUT"
