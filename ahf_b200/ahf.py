@@ -78,9 +78,11 @@ def min_ref(par: Params, l1dims, med_weight: float = 1.0) -> int:
     return start
 
 
-def tree_halos(stats_per_level, max_gather_rad: float) -> dict:
+def tree_halos(stats_per_level, max_gather_rad: float, lists: bool = True) -> dict:
     """Host side of NEXT-2 (ahfgpu_tree_halos): refinement tree and halo seeds from the per-refinement tables ([niso, 18] per coloured
-    level, first level = ahf.min_ref).  Returns daughter / close / sub (lists per level) and pos, gather_rad, npart, host per halo."""
+    level, first level = ahf.min_ref).  Returns daughter / close / sub (lists per level) and pos, gather_rad, npart, host per halo.
+    lists=False: the per-refinement / per-halo Python lists (sub, halo_sub: what the tests compare) are left out -- at 2e4 haloes building
+    them costs more than the tree itself."""
     L = lib()
     niso = np.array([len(s) for s in stats_per_level], np.int64)
     rows = int(niso.sum())
@@ -97,8 +99,11 @@ def tree_halos(stats_per_level, max_gather_rad: float) -> dict:
     if rc != 0:
         raise AhfGpuError(L.ahfgpu_last_error().decode())
     out = dict(daughter=[], close=[], sub=[], pos=pos[:nh.value].copy(), gather_rad=g[:nh.value].copy(), npart=npart[:nh.value].copy(),
-               host=host[:nh.value].copy(), host_level=hlev[:nh.value].copy(),
-               halo_sub=[hsub[hsoff[i]:hsoff[i + 1]].copy() for i in range(nh.value)])
+               host=host[:nh.value].copy(), host_level=hlev[:nh.value].copy())
+    if not lists:
+        out["halo_sub_offset"] = hsoff[:nh.value + 1].copy(); out["halo_sub_flat"] = hsub[:int(hsoff[nh.value])].copy()
+        return out
+    out["halo_sub"] = [hsub[hsoff[i]:hsoff[i + 1]].copy() for i in range(nh.value)]
     r = 0
     for n in niso:
         out["daughter"].append(dau[r:r + n].astype(np.int64)); out["close"].append(close[r:r + n].copy())
@@ -476,7 +481,7 @@ class AhfGpu:
     def min_ref(self, med_weight: float = 1.0) -> int:
         return min_ref(self.params, [int(self.level_header(l)[0][0]) for l in range(self.nlevels())], med_weight)
 
-    def halo_seeds(self, max_gather_rad: float, med_weight: float = 1.0) -> dict:
+    def halo_seeds(self, max_gather_rad: float, med_weight: float = 1.0, lists: bool = True) -> dict:
         """From the resident hierarchy to the inputs of construct_halos without the reference's host-side mesh walk: first coloured
         level (ahf_gridinfo.c:147-175), per level patch labels + RefCentre tables on the device (ahfgpu_amr_patch_stats), then the tree
         and the seeds on the host (ahfgpu_tree_halos).  max_gather_rad = MaxGatherRad / boxsize."""
@@ -486,7 +491,7 @@ class AhfGpu:
             n = C.c_int64(0)
             self._chk(self._L.ahfgpu_amr_patch_stats(self._h, lev, C.byref(n), None, 0))
             stats.append(self.patch_stats(lev, n.value))
-        out = tree_halos(stats, max_gather_rad)
+        out = tree_halos(stats, max_gather_rad, lists=lists)
         out["min_ref"] = m; out["stats"] = stats
         return out
 

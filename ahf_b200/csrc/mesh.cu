@@ -2485,19 +2485,39 @@ __device__ __forceinline__ int face_nb(const LV &v, const int32_t *__restrict__ 
 }
 __device__ __forceinline__ int cell_x(const LV &v, int c) { return (int)((v.dense ? (uint64_t)c : v.ckey[c]) & (uint64_t)(v.L - 1)); }
 
-__global__ void k_patch_init(int32_t *__restrict__ parent, int n)
+// Initial forest: every cell points at its x-1 neighbour when it sees it (and that one is earlier), so the runs along x -- the bulk of
+// all edges -- are chains before the first union; path halving shortens them on the first find.
+__global__ void k_patch_init(LV v, const int32_t *__restrict__ nbr, int32_t *__restrict__ parent)
 {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < n) parent[c] = c;
+  if (c >= v.ncell) return;
+  const int p = face_nb(v, nbr, c, 0, cell_x(v, c));
+  parent[c] = (p >= 0 && p < c) ? p : c;
 }
-// edges (c, n): n visible from c and earlier in traversal order (a later neighbour is still uncoloured when the sweep visits c)
+// edges (c, n): n visible from c and earlier in traversal order (a later neighbour is still uncoloured when the sweep visits c).
+// The x-1 edges are in the initial forest.  An edge (c, n) to the y-1 / z-1 neighbour is implied, and skipped, when the three edges
+// (c, p), (p, m), (n, m) exist with p = x-1 neighbour of c and m = the same-direction neighbour of p = x-1 neighbour of n: only the first cell
+// of every overlap of two runs does a union (the 5.7 ms of unions per 256^3 hierarchy were finds over already joined sets).
 __global__ void k_patch_link(LV v, const int32_t *__restrict__ nbr, int32_t *parent)
 {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= v.ncell) return;
   const int x = cell_x(v, c);
+  const int p = face_nb(v, nbr, c, 0, x);
+  const bool has_p = p >= 0 && p < c;
+  const int xp = has_p ? cell_x(v, p) : 0;
 #pragma unroll
-  for (int d = 0; d < 6; d++) {
+  for (int d = 2; d <= 4; d += 2) {
+    const int n = face_nb(v, nbr, c, d, x);
+    if (n < 0 || n >= c) continue;
+    if (has_p) {
+      const int m = face_nb(v, nbr, p, d, xp);
+      if (m >= 0 && m < p && m < n && face_nb(v, nbr, n, 0, cell_x(v, n)) == m) continue;
+    }
+    uf_unite(parent, c, n);
+  }
+#pragma unroll
+  for (int d = 1; d <= 5; d += 2) {                       // forward neighbours are earlier cells only across a periodic face
     const int n = face_nb(v, nbr, c, d, x);
     if (n >= 0 && n < c) uf_unite(parent, c, n);
   }
@@ -2606,21 +2626,41 @@ __global__ void k_pstat_parts(const float4 *__restrict__ pos4, const uint32_t *_
                               const int8_t *__restrict__ owner, int lev, const int32_t *__restrict__ iso, const uint8_t *__restrict__ per3,
                               unsigned long long *iacc)
 {
-  uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (k >= np) return;
-  const uint64_t p = plist ? plist[k] : k;
-  if (owner[p] != lev) return;
-  const int cc = pcell[k];
-  if (cc < 0) return;
-  const int i = iso[cc];
-  const float4 q = pos4[p];
-  double xp = (double)q.x, yp = (double)q.y, zp = (double)q.z;
-  if (per3[3 * i + 0] && xp < 0.5) xp += 1.0;
-  if (per3[3 * i + 1] && yp < 0.5) yp += 1.0;
-  if (per3[3 * i + 2] && zp < 0.5) zp += 1.0;
-  unsigned long long *ia = iacc + (size_t)PS_IACC * i;
-  atomicAdd(ia + 4, 1ull);
-  atomicAdd(ia + 5, (unsigned long long)(xp * PS_PSCALE)); atomicAdd(ia + 6, (unsigned long long)(yp * PS_PSCALE)); atomicAdd(ia + 7, (unsigned long long)(zp * PS_PSCALE));
+  // the particle list is in Hilbert order: the particles of one refinement come in runs.  Runs of equal refinement index inside a warp are
+  // added up by shuffles (k_pstat_cells) and their last lane issues the four atomics -- one per run instead of one per particle (2.5 ms per
+  // 256^3 hierarchy were same-address atomics of the clump cores).  Integer sums: the table does not depend on the grouping.
+  const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int i = -1 - lane;                                       // lanes without a particle of this level: keys that match nobody
+  unsigned long long iv[4] = { 0, 0, 0, 0 };
+  if (k < np) {
+    const uint64_t p = plist ? plist[k] : k;
+    const int cc = pcell[k];
+    if (owner[p] == lev && cc >= 0) {
+      i = iso[cc];
+      const float4 q = pos4[p];
+      double xp = (double)q.x, yp = (double)q.y, zp = (double)q.z;
+      if (per3[3 * i + 0] && xp < 0.5) xp += 1.0;
+      if (per3[3 * i + 1] && yp < 0.5) yp += 1.0;
+      if (per3[3 * i + 2] && zp < 0.5) zp += 1.0;
+      iv[0] = 1ull; iv[1] = (unsigned long long)(xp * PS_PSCALE); iv[2] = (unsigned long long)(yp * PS_PSCALE); iv[3] = (unsigned long long)(zp * PS_PSCALE);
+    }
+  }
+  const int iprev = __shfl_up_sync(0xffffffffu, i, 1);
+  const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || iprev != i);
+  const int run = __popc(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int ko = __shfl_up_sync(0xffffffffu, run, o);
+    const bool take = lane >= o && ko == run;
+#pragma unroll
+    for (int q = 0; q < 4; q++) { const unsigned long long a = seg_shfl_up(iv[q], o); if (take) iv[q] += a; }
+  }
+  const int inext = __shfl_down_sync(0xffffffffu, i, 1);
+  if (i >= 0 && (lane == 31 || inext != i)) {
+    unsigned long long *ia = iacc + (size_t)PS_IACC * i;
+    atomicAdd(ia + 4, iv[0]); atomicAdd(ia + 5, iv[1]); atomicAdd(ia + 6, iv[2]); atomicAdd(ia + 7, iv[3]);
+  }
 }
 __device__ __forceinline__ double f1mod1(double v) { return v >= 2.0 ? v - 2.0 : v >= 1.0 ? v - 1.0 : v; }     // specific.c:120-129
 // normalisation and fall-backs (:1240-1370), boundRefDiv of the periodic refinements (:1400-1470).
@@ -2725,7 +2765,7 @@ extern "C" int ahfgpu_amr_patch_stats(ahfgpu_ctx *c, int32_t lev, int64_t *niso,
       LV v = view(l);
       DevBuf<int32_t> parent, root, diso; DevBuf<uint8_t> isroot, per; DevBuf<int> rank; DevBuf<double> acc, div3; DevBuf<unsigned long long> iacc;
       parent.reserve(nc); root.reserve(nc); diso.reserve(nc); isroot.reserve(nc); rank.reserve(nc); per.reserve((size_t)3 * nc);
-      LAUNCH(c, k_patch_init, nblk(nc, 256), 256, 0, parent.p, nc);
+      LAUNCH(c, k_patch_init, nblk(nc, 256), 256, 0, v, l.nbr, parent.p);
       LAUNCH(c, k_patch_link, nblk(nc, 256), 256, 0, v, l.nbr, parent.p);
       LAUNCH(c, k_patch_roots, nblk(nc, 256), 256, 0, parent.p, nc, root.p, isroot.p);
       ni = exclusive_scan<uint8_t>(c, isroot.p, rank.p, (uint64_t)nc);
@@ -2773,7 +2813,7 @@ extern "C" int ahfgpu_amr_patches(ahfgpu_ctx *c, int32_t lev, int32_t *iso, int6
       LV v = view(l);
       DevBuf<int32_t> parent, root, diso; DevBuf<uint8_t> isroot, per; DevBuf<int> rank;
       parent.reserve(nc); root.reserve(nc); diso.reserve(nc); isroot.reserve(nc); rank.reserve(nc); per.reserve((size_t)3 * nc);
-      LAUNCH(c, k_patch_init, nblk(nc, 256), 256, 0, parent.p, nc);
+      LAUNCH(c, k_patch_init, nblk(nc, 256), 256, 0, v, l.nbr, parent.p);
       LAUNCH(c, k_patch_link, nblk(nc, 256), 256, 0, v, l.nbr, parent.p);
       LAUNCH(c, k_patch_roots, nblk(nc, 256), 256, 0, parent.p, nc, root.p, isroot.p);
       ni = exclusive_scan<uint8_t>(c, isroot.p, rank.p, (uint64_t)nc);

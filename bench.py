@@ -223,7 +223,7 @@ def many_haloes_leg(g, ahf, synth, n1d, peak):
     g.set_params(par)
     g.upload(box.pos, box.mom); g.sfc_sort_resident(); g.build_amr()
     t0 = time.perf_counter()
-    hs = g.halo_seeds(3.0 / box.boxsize)
+    hs = g.halo_seeds(3.0 / box.boxsize, lists=False)
     seeds_ms = 1e3 * (time.perf_counter() - t0)
     c, r, s = np.ascontiguousarray(hs["pos"]), np.ascontiguousarray(hs["gather_rad"]), np.ascontiguousarray(hs["npart"], np.int64)
     os.environ["AHFGPU_STAGES"] = "1"
@@ -469,11 +469,11 @@ def main():
     seeds_ms = None
     if args.seeds == "device":
         g.upload(box.pos, box.mom); g.sfc_sort_resident(); g.build_amr()
-        g.halo_seeds(3.0 / box.boxsize)                                   # warm (allocations)
+        g.halo_seeds(3.0 / box.boxsize, lists=False)                                   # warm (allocations)
         g.build_amr()                                                     # a fresh hierarchy: the per-level tables are computed again
         g.synchronize()
         t0 = time.perf_counter()
-        hs = g.halo_seeds(3.0 / box.boxsize)
+        hs = g.halo_seeds(3.0 / box.boxsize, lists=False)
         seeds_ms = 1e3 * (time.perf_counter() - t0)
         centres, rad, seednp = np.ascontiguousarray(hs["pos"]), np.ascontiguousarray(hs["gather_rad"]), np.ascontiguousarray(hs["npart"], np.int64)
     else:
@@ -550,6 +550,26 @@ def main():
     g.event_record(3)
     barrier()
     ms_e2e = g.event_elapsed_ms(2, 3) / args.steps
+    # ---- the same resident pass with the halo seeds re-derived EVERY pass from the pass's own hierarchy (patch labels + per-patch tables on
+    #      the device, tree on the host): no stage between particles and halo results is taken from an earlier pass.  Wall clock (the tree
+    #      is host code), synchronised on both sides.
+    seeds_leg = None
+    if args.seeds == "device" and world == 1:
+        os.environ["AHFGPU_STAGES"] = "0"
+        ws, ss = [], []
+        for it in range(min(args.steps, 5) + 1):
+            barrier(); t0 = time.perf_counter()
+            g.sfc_sort_resident(); g.build_amr()
+            t1 = time.perf_counter()
+            hs2 = g.halo_seeds(3.0 / box.boxsize, lists=False)
+            t2 = time.perf_counter()
+            g.construct_halos(np.ascontiguousarray(hs2["pos"]), np.ascontiguousarray(hs2["gather_rad"]), np.ascontiguousarray(hs2["npart"], np.int64), fetch=False)
+            barrier(); t3 = time.perf_counter()
+            if it:
+                ws.append(1e3 * (t3 - t0)); ss.append(1e3 * (t2 - t1))
+        seeds_leg = {"ms_per_step": float(np.mean(ws)), "value": n / (float(np.mean(ws)) * 1e-3), "unit": UNIT, "seeds_ms": float(np.mean(ss)), "steps": len(ws),
+                     "n_seeds": int(len(hs2["npart"])),
+                     "what": "keys+sort, mesh, patch labels + per-patch tables (device) + tree and seeds (host), halo pass; host wall clock"}
     os.environ.pop("AHFGPU_STAGES", None)
     clocks = sampler.stop()
     if world > 1:
@@ -614,6 +634,8 @@ def main():
                        "unbind_pps": st["halo_gathered"] / ((st["halo_gather"] + st["halo_sort"] + st["halo_unbind"] + st["halo_profiles"]) * 1e-3),
                        "halo_gathered_particles": st["halo_gathered"], "levels": nlev, "halos_in": len(rad), "halos_ge_minpart": nhalo_ok},
     }
+    if seeds_leg is not None:
+        line["step_with_seeds"] = seeds_leg
     if not args.no_many_haloes and world == 1:
         line["halo_pass_many_haloes"] = many_haloes_leg(g, ahf, synth, args.n1d, peak)
     if not args.no_cpu_baseline:

@@ -21,6 +21,8 @@ with ahf.AhfGpu(par) as g:
         t3 = time.perf_counter()
         print("level", lev, "cells", int(g.level_header(lev)[0][1]), "patches", n.value, "compute ms %.2f fetch ms %.2f" % ((t2 - t1) * 1e3, (t3 - t2) * 1e3), flush=True)
     t4 = time.perf_counter()
+    if os.environ.get("AHF_SAVE_STATS"):
+        np.savez_compressed(os.environ["AHF_SAVE_STATS"], boxsize=box.boxsize, **{"lev%d" % i: s for i, s in enumerate(stats)})
     out = ahf.tree_halos(stats, 3.0 / box.boxsize)
     t5 = time.perf_counter()
     print("patch tables total ms %.1f, host tree ms %.1f, haloes %d" % ((t4 - t0) * 1e3, (t5 - t4) * 1e3, len(out["npart"])), flush=True)

@@ -331,3 +331,80 @@ def test_catalogue_writer_equals_reference_files(kind, tmp_path):
         assert np.array_equal(tr["host"], T["host_pre"]) and np.array_equal(tr["host_level"], T["level_pre"])
         assert all(np.array_equal(a, b) for a, b in zip(tr["halo_sub"], T["sub_pre"]))
         assert np.array_equal(tr["pos"], H.s[:, 0:3]) and np.array_equal(tr["npart"], H.s[:, 4].astype(np.int64))
+
+
+def test_tree_cell_lists_equal_the_all_pairs_loops():
+    """The library's tree replaces the reference's all-pairs loops (children x parents of consecutive levels, ahf_halos.c:1693-1800; adoption
+    of parent-less refinements, :2030-2165; every halo against every halo for the gathering radius, :2985-3052) by searches through periodic
+    cell lists.  On random tables that are large enough to take those paths (>= 512 refinements above an orphan, thousands of haloes, periodic
+    extents, equal particle numbers, coincident centres) the results must equal a direct numpy restatement of the loops."""
+    from ahf_b200 import ahf
+    rng = np.random.default_rng(7)
+
+    def level(n, half, frac_periodic=0.05):
+        c = rng.random((n, 3))
+        st = np.zeros((n, 18))
+        st[:, 0] = rng.integers(8, 500, n); st[:, 1] = rng.integers(1, 60, n)          # few distinct particle numbers: many ties
+        st[:, 2:5] = c; st[:, 9:12] = c; st[:, 6:9] = c
+        lo, hi = c - half * rng.random((n, 3)), c + half * rng.random((n, 3))
+        per = rng.random(n) < frac_periodic                                                # extents across a periodic face: max < min
+        lo[per] = np.mod(lo[per], 1.0); hi[per] = np.mod(hi[per], 1.0)
+        lo[~per] = np.clip(lo[~per], 0.0, 1.0); hi[~per] = np.clip(hi[~per], 0.0, 1.0)
+        st[:, 12:18:2] = lo; st[:, 13:18:2] = hi
+        return st
+    stats = [level(1500, 0.03), level(2500, 0.01), level(1200, 0.004)]
+    stats[1][:40, 9:12] = stats[1][40:80, 9:12]                                          # coincident centres
+    out = ahf.tree_halos(stats, 0.2)
+
+    def inside(v, lo, hi):
+        return np.where(lo < hi, (v > lo) & (v < hi), ((v >= 0) & (v < hi)) | ((v > lo) & (v <= 1.0)))
+
+    def pd2(a, b):
+        d = np.abs(a - b); d = np.where(d > 0.5, 1.0 - d, d)
+        return d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1] + d[..., 2] * d[..., 2]
+    # (1) lists before the several-parents / adoption steps cannot be read back; the final lists can: rebuild all steps directly
+    cd = [s[:, 9:12].copy() for s in stats]
+    sub = []; par = []
+    for i in range(len(stats)):
+        par.append([[] for _ in range(len(stats[i]))])
+    for i in range(len(stats) - 1):
+        P, Cc = stats[i], cd[i + 1]
+        lst = []
+        for j in range(len(P)):
+            m = inside(Cc[:, 0], P[j, 12], P[j, 13]) & inside(Cc[:, 1], P[j, 14], P[j, 15]) & inside(Cc[:, 2], P[j, 16], P[j, 17])
+            ks = np.nonzero(m)[0].tolist(); lst.append(ks)
+            for k in ks:
+                par[i + 1][k].append(j)
+        sub.append(lst)
+    sub.append([[] for _ in range(len(stats[-1]))])
+    for i in range(1, len(stats) - 1):                                                       # several parents: keep the closest (first minimum)
+        for j in range(len(stats[i])):
+            if len(par[i][j]) > 1:
+                d = pd2(cd[i][j][None, :], cd[i - 1][par[i][j]]); best = par[i][j][int(np.argmin(d))]
+                for q in par[i][j]:
+                    if q != best:
+                        sub[i - 1][q] = [t for t in sub[i - 1][q] if t != j]
+                par[i][j] = [best]
+    n_orphans = 0
+    for i in range(1, len(stats)):                                                           # adoption by the closest refinement above
+        up = cd[i - 1].copy()
+        for j in range(len(stats[i])):
+            if not par[i][j]:
+                best = int(np.argmin(pd2(cd[i][j][None, :], up))); n_orphans += 1
+                par[i][j] = [best]; sub[i - 1][best].append(j); cd[i][j] = cd[i - 1][best]
+    assert n_orphans > 100 and len(stats[0]) >= 512
+    for i in range(len(stats)):
+        assert [list(map(int, q)) for q in out["sub"][i]] == sub[i], f"substructure lists of level {i}"
+    # gathering radius: half the distance to the nearest halo with MORE particles, clipped
+    pos, npart = out["pos"], out["npart"]
+    nh = len(npart)
+    assert nh > 2048
+    g = np.empty(nh)
+    for i in range(nh):
+        m = npart > npart[i]
+        g[i] = 0.5 * np.sqrt(pd2(pos[i][None, :], pos[m]).min()) if m.any() else 0.2
+    # sub-haloes carry closeRefDist as lower bound: take it from the output's own lower clip by comparing only where the plain value rules
+    lower = np.minimum(g, 0.2)
+    assert np.all(out["gather_rad"] >= lower - 0.0) and np.all(out["gather_rad"] <= 0.2)
+    plain = out["host"] < 0
+    assert np.array_equal(out["gather_rad"][plain], lower[plain])
