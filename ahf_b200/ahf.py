@@ -419,6 +419,7 @@ class AhfGpu:
         """keys + block histogram + equal-particle Hilbert ranges + ONE exchange (owner and ghost holders) + ONE sort of the particles
         uploaded with upload(); afterwards the context holds its key range plus the ghost shell"""
         self._chk(self._L.ahfgpu_slab_distribute(self._h, id_base, ghost_width, decomp_bits))
+        self._split = True
         self.n = int(self.slab_info()["resident"])
 
     def slab_info(self) -> dict:
@@ -478,8 +479,14 @@ class AhfGpu:
         self._chk(self._L.ahfgpu_amr_patches(self._h, lev, _p(iso), C.byref(niso), _p(per)))
         return iso, per[:niso.value].copy()
 
+    def box_levels(self) -> int:
+        """levels of the WHOLE box: a rank of a split box may hold fewer (its cells end on a coarser level)"""
+        if getattr(self, "_split", False):
+            return self.slab_info()["levels"]
+        return self.nlevels()
+
     def min_ref(self, med_weight: float = 1.0) -> int:
-        return min_ref(self.params, [int(self.level_header(l)[0][0]) for l in range(self.nlevels())], med_weight)
+        return min_ref(self.params, [int(self.params.lgrid_dom) << l for l in range(self.box_levels())], med_weight)
 
     def halo_seeds(self, max_gather_rad: float, med_weight: float = 1.0, lists: bool = True) -> dict:
         """From the resident hierarchy to the inputs of construct_halos without the reference's host-side mesh walk: first coloured
@@ -487,7 +494,7 @@ class AhfGpu:
         and the seeds on the host (ahfgpu_tree_halos).  max_gather_rad = MaxGatherRad / boxsize."""
         m = self.min_ref(med_weight)
         stats = []
-        for lev in range(m, self.nlevels()):
+        for lev in range(m, self.box_levels()):             # split box: a collective call per level, every rank gets the same tables
             n = C.c_int64(0)
             self._chk(self._L.ahfgpu_amr_patch_stats(self._h, lev, C.byref(n), None, 0))
             stats.append(self.patch_stats(lev, n.value))

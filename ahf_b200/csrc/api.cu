@@ -114,7 +114,7 @@ void ahfgpu_ctx::free_particles()
 void ahfgpu_ctx::free_levels()
 {
   for (auto &l : levels) l.free_all();
-  levels.clear();
+  levels.clear(); pstat_split.clear();
   ahf::dfree(owner_level); owner_level = nullptr;
 }
 void ahfgpu_ctx::free_halos()

@@ -153,6 +153,7 @@ struct ahfgpu_ctx {
   ahf::Comm *comm = nullptr;          // several contexts working on ONE box (comm.cuh); owned by the context
   ahf::Slab *slab = nullptr;          // decomposition of the resident set (slab.cu): owned range + ghost shell
   int        g_nlevels = 0;           // levels of the whole box (a rank whose cells end earlier holds fewer)
+  std::map<int, std::vector<double>> pstat_split;   // split box: per-refinement tables of the levels (host, identical on every rank) until the hierarchy is rebuilt
   // unsorted device copy kept by ahfgpu_upload_soa
   float    *in_pos = nullptr, *in_mom = nullptr, *in_w = nullptr, *in_u = nullptr;
   uint64_t  in_n = 0;

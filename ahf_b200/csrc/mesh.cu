@@ -2487,10 +2487,13 @@ __device__ __forceinline__ int cell_x(const LV &v, int c) { return (int)((v.dens
 
 // Initial forest: every cell points at its x-1 neighbour when it sees it (and that one is earlier), so the runs along x -- the bulk of
 // all edges -- are chains before the first union; path halving shortens them on the first find.
-__global__ void k_patch_init(LV v, const int32_t *__restrict__ nbr, int32_t *__restrict__ parent)
+// owned != nullptr (ONE box on several ranks): only the rank's own cells are edge sources -- their neighbour entries are exact, those of
+// the ghost shell need not be; a ghost cell appears as the target of an own cell's edge only
+__global__ void k_patch_init(LV v, const int32_t *__restrict__ nbr, int32_t *__restrict__ parent, const uint8_t *__restrict__ owned)
 {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= v.ncell) return;
+  if (owned && !owned[c]) { parent[c] = c; return; }
   const int p = face_nb(v, nbr, c, 0, cell_x(v, c));
   parent[c] = (p >= 0 && p < c) ? p : c;
 }
@@ -2498,10 +2501,11 @@ __global__ void k_patch_init(LV v, const int32_t *__restrict__ nbr, int32_t *__r
 // The x-1 edges are in the initial forest.  An edge (c, n) to the y-1 / z-1 neighbour is implied, and skipped, when the three edges
 // (c, p), (p, m), (n, m) exist with p = x-1 neighbour of c and m = the same-direction neighbour of p = x-1 neighbour of n: only the first cell
 // of every overlap of two runs does a union (the 5.7 ms of unions per 256^3 hierarchy were finds over already joined sets).
-__global__ void k_patch_link(LV v, const int32_t *__restrict__ nbr, int32_t *parent)
+__global__ void k_patch_link(LV v, const int32_t *__restrict__ nbr, int32_t *parent, const uint8_t *__restrict__ owned)
 {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= v.ncell) return;
+  if (owned && !owned[c]) return;
   const int x = cell_x(v, c);
   const int p = face_nb(v, nbr, c, 0, x);
   const bool has_p = p >= 0 && p < c;
@@ -2512,7 +2516,7 @@ __global__ void k_patch_link(LV v, const int32_t *__restrict__ nbr, int32_t *par
     if (n < 0 || n >= c) continue;
     if (has_p) {
       const int m = face_nb(v, nbr, p, d, xp);
-      if (m >= 0 && m < p && m < n && face_nb(v, nbr, n, 0, cell_x(v, n)) == m) continue;
+      if (m >= 0 && m < p && m < n && (!owned || (owned[p] && owned[n])) && face_nb(v, nbr, n, 0, cell_x(v, n)) == m) continue;
     }
     uf_unite(parent, c, n);
   }
@@ -2572,10 +2576,10 @@ template <> __device__ __forceinline__ unsigned long long seg_shfl_up<unsigned l
   return ((unsigned long long)hi << 32) | lo;
 }
 __global__ void k_pstat_cells(LV v, const int32_t *__restrict__ iso, const uint8_t *__restrict__ per3, const float *__restrict__ dens, double *acc,
-                              unsigned long long *iacc)
+                              unsigned long long *iacc, const uint8_t *__restrict__ owned)
 {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = c < v.ncell;
+  const bool valid = c < v.ncell && (!owned || owned[c]);
   const int lane = threadIdx.x & 31;
   int i = -1 - lane;                                       // invalid lanes: keys that match nobody
   unsigned long long iv[4] = { 0, 0, 0, 0 };
@@ -2624,7 +2628,7 @@ __global__ void k_pstat_cells(LV v, const int32_t *__restrict__ iso, const uint8
 // particles the level finally owns (node.ll at ahf_halos time): centre of mass of the refinement's particles (:1120-1180)
 __global__ void k_pstat_parts(const float4 *__restrict__ pos4, const uint32_t *__restrict__ plist, const int32_t *__restrict__ pcell, uint64_t np,
                               const int8_t *__restrict__ owner, int lev, const int32_t *__restrict__ iso, const uint8_t *__restrict__ per3,
-                              unsigned long long *iacc)
+                              unsigned long long *iacc, uint64_t own_lo, uint64_t own_hi)
 {
   // the particle list is in Hilbert order: the particles of one refinement come in runs.  Runs of equal refinement index inside a warp are
   // added up by shuffles (k_pstat_cells) and their last lane issues the four atomics -- one per run instead of one per particle (2.5 ms per
@@ -2636,7 +2640,7 @@ __global__ void k_pstat_parts(const float4 *__restrict__ pos4, const uint32_t *_
   if (k < np) {
     const uint64_t p = plist ? plist[k] : k;
     const int cc = pcell[k];
-    if (owner[p] == lev && cc >= 0) {
+    if (owner[p] == lev && cc >= 0 && p >= own_lo && p < own_hi) {          // [own_lo, own_hi): the rank's own particles of a split box
       i = iso[cc];
       const float4 q = pos4[p];
       double xp = (double)q.x, yp = (double)q.y, zp = (double)q.z;
@@ -2689,10 +2693,10 @@ __global__ void k_pstat_finish(const double *__restrict__ acc, const unsigned lo
   }
 }
 // extents (:1480-1595): MinMax, or MinMaxBound at boundRefDiv for the periodic refinements (specific.c:204-254)
-__global__ void k_pstat_extents(LV v, const int32_t *__restrict__ iso, const double *__restrict__ div3, double *out)
+__global__ void k_pstat_extents(LV v, const int32_t *__restrict__ iso, const double *__restrict__ div3, double *out, const uint8_t *__restrict__ owned)
 {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = c < v.ncell;
+  const bool valid = c < v.ncell && (!owned || owned[c]);
   const int lane = threadIdx.x & 31;
   int i = -1 - lane;
   // per axis: candidate for the minimum and for the maximum of the refinement (+inf / -1: none), as MinMax / MinMaxBound would see this node
@@ -2741,6 +2745,312 @@ __global__ void k_pstat_fix(int niso, double *out)
   for (int q = 0; q < 3; q++) { if (o[12 + 2 * q] == 100000.0) o[12 + 2 * q] = 0.0; if (o[13 + 2 * q] == 0.0) o[13 + 2 * q] = 1.0; }    // :1597-1612
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// The same table for ONE box split over several ranks (slab.cu).  A refinement may cross rank boundaries, so the labelling is a
+// connected-component problem over all ranks:
+//   1. every rank labels its resident cells with edges whose SOURCE is one of its own cells (exact neighbour entries); ghost cells are
+//      edge targets only.  Every edge of the box-wide graph has exactly one own source, so the union of the ranks' local components is
+//      the box-wide partition once components that share a cell are joined;
+//   2. a local component is named by the global key of its first cell.  A ghost cell that an own cell is joined to is an own cell of
+//      another rank: (its key, its local name) goes to everybody, the owner answers with the pair (sender's name, owner's name);
+//   3. the pairs of all ranks are a small graph over names: every rank solves it (host union-find), the name of a refinement becomes
+//      the smallest key of its class = the key of its first cell in the box-wide traversal order;
+//   4. refinements are numbered in the order of their first cells (what the reference's sweep produces): every rank contributes the
+//      first cells it owns, the sorted union is the numbering;
+//   5. sums / maxima / extents over OWN cells and OWN particles, combined over the ranks (integer sums exactly, double sums in rank
+//      order), so every rank ends with the same table.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t cell_gkey(const LV &v, int c) { return v.dense ? (uint64_t)c : v.ckey[c]; }
+
+__global__ void k_ps_haschild(const int32_t *__restrict__ root, int n, uint8_t *__restrict__ haschild)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n && root[c] != c) haschild[root[c]] = 1;
+}
+__global__ void k_ps_touched(const int32_t *__restrict__ root, const uint8_t *__restrict__ haschild, const uint8_t *__restrict__ owned, int n, uint8_t *__restrict__ t)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) t[c] = (!owned[c] && (root[c] != c || haschild[c])) ? 1 : 0;
+}
+__global__ void k_ps_emit(LV v, const int32_t *__restrict__ root, const uint8_t *__restrict__ t, const int *__restrict__ pos, uint64_t *__restrict__ rkey, uint64_t *__restrict__ rlab)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= v.ncell || !t[c]) return;
+  rkey[pos[c]] = cell_gkey(v, c); rlab[pos[c]] = cell_gkey(v, root[c]);
+}
+// records of all ranks -> pairs (sender's name, my name) for the cells I own.  bad: a record for a cell I own but do not have
+__global__ void k_ps_pairs(LV v, const int32_t *__restrict__ root, const uint8_t *__restrict__ own3, int bd, int rank, const uint64_t *__restrict__ rkey,
+                           const uint64_t *__restrict__ rlab, int nrec, uint8_t *__restrict__ keep, uint64_t *__restrict__ pa, uint64_t *__restrict__ pb, int *__restrict__ bad)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrec) return;
+  const uint64_t k = rkey[i];
+  const int x = (int)(k & (uint64_t)(v.L - 1)), y = (int)((k >> v.logL) & (uint64_t)(v.L - 1)), z = (int)(k >> (2 * v.logL));
+  const int sh = v.logL - bd;
+  keep[i] = 0;
+  if (own3[((((size_t)(z >> sh)) << bd) | (size_t)(y >> sh)) << bd | (size_t)(x >> sh)] != (uint8_t)rank) return;
+  const int c = v.ncell > 0 ? lv_lookup(v, x, y, z) : -1;
+  if (c < 0) { atomicAdd(bad, 1); return; }
+  const uint64_t mine = cell_gkey(v, root[c]);
+  if (mine != rlab[i]) { keep[i] = 1; pa[i] = rlab[i]; pb[i] = mine; }
+}
+__global__ void k_ps_compact2(const uint8_t *__restrict__ keep, const int *__restrict__ pos, int n, const uint64_t *__restrict__ a, const uint64_t *__restrict__ b,
+                              uint64_t *__restrict__ out)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && keep[i]) { out[2 * (size_t)pos[i]] = a[i]; out[2 * (size_t)pos[i] + 1] = b[i]; }
+}
+__device__ __forceinline__ int lower_bound_u64(const uint64_t *__restrict__ a, int n, uint64_t k)
+{
+  int lo = 0, hi = n;
+  while (lo < hi) { const int m = (lo + hi) >> 1; if (a[m] < k) lo = m + 1; else hi = m; }
+  return lo;
+}
+// box-wide name of every resident cell's component; first[c]: c is an own cell and the first cell of its refinement
+__global__ void k_ps_canon(LV v, const int32_t *__restrict__ root, const uint8_t *__restrict__ owned, const uint64_t *__restrict__ mfrom, const uint64_t *__restrict__ mto,
+                           int nm, uint64_t *__restrict__ canon, uint8_t *__restrict__ first)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= v.ncell) return;
+  uint64_t lab = cell_gkey(v, root[c]);
+  const int j = lower_bound_u64(mfrom, nm, lab);
+  if (j < nm && mfrom[j] == lab) lab = mto[j];
+  canon[c] = lab;
+  first[c] = (owned[c] && lab == cell_gkey(v, c)) ? 1 : 0;
+}
+__global__ void k_ps_firstkeys(LV v, const uint8_t *__restrict__ first, const int *__restrict__ pos, uint64_t *__restrict__ out)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < v.ncell && first[c]) out[pos[c]] = cell_gkey(v, c);
+}
+__global__ void k_ps_iso(LV v, const uint8_t *__restrict__ owned, const uint64_t *__restrict__ canon, const uint64_t *__restrict__ gfirst, int niso, const int32_t *__restrict__ nbr,
+                         int32_t *__restrict__ iso, uint32_t *__restrict__ per3u, int *__restrict__ bad)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= v.ncell) return;
+  if (!owned[c]) { iso[c] = -1; return; }
+  const int i = lower_bound_u64(gfirst, niso, canon[c]);
+  if (i >= niso || gfirst[i] != canon[c]) { iso[c] = -1; atomicAdd(bad, 1); return; }
+  iso[c] = i;
+  int x, y, z;
+  lv_coords(v, c, x, y, z);
+  if (x == 0 && face_nb(v, nbr, c, 0, x) >= 0) per3u[3 * (size_t)i + 0] = 1u;
+  if (y == 0 && face_nb(v, nbr, c, 2, x) >= 0) per3u[3 * (size_t)i + 1] = 1u;
+  if (z == 0 && face_nb(v, nbr, c, 4, x) >= 0) per3u[3 * (size_t)i + 2] = 1u;
+}
+__global__ void k_ps_per3(const uint32_t *__restrict__ u, int n, uint8_t *__restrict__ per3)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) per3[i] = u[i] ? 1 : 0;
+}
+// accumulators of all ranks ([R][niso * PS_ACC] doubles, [R][niso * PS_IACC] u64) -> box-wide: integer sums exactly, double sums in rank
+// order, the maximum density as a maximum
+__global__ void k_ps_combine_acc(const double *__restrict__ acc_all, const unsigned long long *__restrict__ iacc_all, int R, int niso, double *__restrict__ acc,
+                                 unsigned long long *__restrict__ iacc)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < niso * PS_ACC) {
+    const int q = t % PS_ACC;
+    double v = 0.0;
+    for (int p = 0; p < R; p++) { const double a = acc_all[(size_t)p * niso * PS_ACC + t]; if (q == 10) { if (a > v) v = a; } else v += a; }
+    acc[t] = v;
+  }
+  if (t < niso * PS_IACC) {
+    unsigned long long v = 0;
+    for (int p = 0; p < R; p++) v += iacc_all[(size_t)p * niso * PS_IACC + t];
+    iacc[t] = v;
+  }
+}
+// extents of all ranks ([R][niso][18], the sentinels of k_pstat_finish where a rank holds none of the refinement's cells) -> box-wide
+__global__ void k_ps_combine_ext(const double *__restrict__ out_all, int R, int niso, double *__restrict__ out)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= niso * 6) return;
+  const int i = t / 6, q = 12 + t % 6;
+  double v = out_all[(size_t)i * 18 + q];
+  for (int p = 1; p < R; p++) { const double a = out_all[((size_t)p * niso + i) * 18 + q]; if (q & 1) { if (a > v) v = a; } else { if (a < v) v = a; } }
+  out[(size_t)i * 18 + q] = v;
+}
+
+// every rank's `n_mine` elements (device) -> all elements in rank order (device, returned; caller frees), counts[p] per rank
+template <typename T> static T *gather_var(ahfgpu_ctx *c, const T *send, int64_t n_mine, std::vector<int64_t> &counts, int64_t &total)
+{
+  Comm *cm = c->comm;
+  const int R = cm->nranks;
+  counts.assign(R, 0);
+  long long mine = n_mine;
+  std::vector<long long> all(R);
+  cm->allgather_host(c, &mine, all.data(), sizeof(long long));
+  std::vector<size_t> bytes(R), off(R + 1, 0);
+  for (int p = 0; p < R; p++) { counts[p] = all[p]; bytes[p] = (size_t)all[p] * sizeof(T); off[p + 1] = off[p] + bytes[p]; }
+  total = (int64_t)(off[R] / sizeof(T));
+  T *out = dalloc<T>(total > 0 ? total : 1);
+  cm->allgatherv(c, send, out, bytes.data(), off.data());
+  return out;
+}
+
+static void patch_stats_split(ahfgpu_ctx *c, int lev, std::vector<double> &table)
+{
+  Comm *cm = c->comm; Slab *S = c->slab;
+  const int R = cm->nranks;
+  Level empty;
+  Level &l = lev < (int)c->levels.size() ? c->levels[lev] : empty;
+  if (lev >= (int)c->levels.size()) {                      // the rank's cells end on a coarser level: it only takes part in the exchanges
+    empty.L = (int64_t)c->par.lgrid_dom << lev; empty.ncell = 0; empty.dense = false;
+  }
+  if (l.ncell > 0 && !l.dense && !l.nbr) AHF_FAIL("level has no neighbour table");
+  LV v = view(l);
+  const int nc = (int)l.ncell;
+  DevBuf<int32_t> parent, root, diso; DevBuf<uint8_t> owned, isroot, hasch, touched, first, keep, per; DevBuf<int> pos, bad; DevBuf<uint64_t> rkey, rlab, canon, mfrom, mto;
+  DevBuf<uint32_t> per3u; DevBuf<double> acc, accl, div3; DevBuf<unsigned long long> iacc, iaccl;
+  parent.reserve(nc); root.reserve(nc); diso.reserve(nc); owned.reserve(nc); isroot.reserve(nc); hasch.reserve(nc); touched.reserve(nc); first.reserve(nc); pos.reserve(nc);
+  canon.reserve(nc); bad.reserve(2);
+  CUDA_CHECK(cudaMemsetAsync(bad.p, 0, 2 * sizeof(int), c->stream));
+  int nt = 0;
+  if (nc > 0) {
+    LAUNCH(c, k_owned_cells, nblk(nc, 256), 256, 0, v, S->own3, S->bd, cm->rank, owned.p);
+    LAUNCH(c, k_patch_init, nblk(nc, 256), 256, 0, v, l.nbr, parent.p, (const uint8_t *)owned.p);
+    LAUNCH(c, k_patch_link, nblk(nc, 256), 256, 0, v, l.nbr, parent.p, (const uint8_t *)owned.p);
+    LAUNCH(c, k_patch_roots, nblk(nc, 256), 256, 0, parent.p, nc, root.p, isroot.p);
+    CUDA_CHECK(cudaMemsetAsync(hasch.p, 0, nc, c->stream));
+    LAUNCH(c, k_ps_haschild, nblk(nc, 256), 256, 0, root.p, nc, hasch.p);
+    LAUNCH(c, k_ps_touched, nblk(nc, 256), 256, 0, root.p, hasch.p, owned.p, nc, touched.p);
+    nt = exclusive_scan<uint8_t>(c, touched.p, pos.p, (uint64_t)nc);
+    rkey.reserve(nt); rlab.reserve(nt);
+    if (nt) LAUNCH(c, k_ps_emit, nblk(nc, 256), 256, 0, v, root.p, touched.p, pos.p, rkey.p, rlab.p);
+  } else { rkey.reserve(1); rlab.reserve(1); }
+  // ---- 2. records to everybody, pairs from the owners
+  std::vector<int64_t> cnt; int64_t nrec = 0, nrec2 = 0;
+  uint64_t *akey = gather_var<uint64_t>(c, rkey.p, nt, cnt, nrec);
+  uint64_t *alab = gather_var<uint64_t>(c, rlab.p, nt, cnt, nrec2);
+  std::vector<uint64_t> mypairs;
+  if (nrec > 0) {
+    DevBuf<uint64_t> pa, pb, pc; DevBuf<int> ppos;
+    keep.reserve(nrec); pa.reserve(nrec); pb.reserve(nrec); ppos.reserve(nrec);
+    LAUNCH(c, k_ps_pairs, nblk(nrec, 256), 256, 0, v, root.p, S->own3, S->bd, cm->rank, akey, alab, (int)nrec, keep.p, pa.p, pb.p, bad.p);
+    const int np2 = exclusive_scan<uint8_t>(c, keep.p, ppos.p, (uint64_t)nrec);
+    if (np2) {
+      pc.reserve((size_t)2 * np2);
+      LAUNCH(c, k_ps_compact2, nblk(nrec, 256), 256, 0, keep.p, ppos.p, (int)nrec, pa.p, pb.p, pc.p);
+      mypairs.resize((size_t)2 * np2);
+      CUDA_CHECK(cudaMemcpyAsync(mypairs.data(), pc.p, sizeof(uint64_t) * 2 * np2, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    pa.release(); pb.release(); pc.release(); ppos.release();
+  }
+  ahf::dfree(akey); ahf::dfree(alab);
+  {                                                      // a joined ghost cell its owner does not have would be a broken ghost shell
+    int hb[2] = { 0, 0 };
+    read_back(c, hb, bad.p, sizeof(hb));
+    if (hb[0]) AHF_FAIL("patch labels of a split box: a rank joined a ghost cell its owner does not hold (ghost shell too thin?)");
+  }
+  {                                                      // many ghost cells join the same two components: one pair each
+    std::vector<std::pair<uint64_t, uint64_t>> pr(mypairs.size() / 2);
+    for (size_t i = 0; i < pr.size(); i++) { uint64_t a = mypairs[2 * i], b = mypairs[2 * i + 1]; if (a > b) std::swap(a, b); pr[i] = { a, b }; }
+    std::sort(pr.begin(), pr.end());
+    pr.erase(std::unique(pr.begin(), pr.end()), pr.end());
+    mypairs.resize(pr.size() * 2);
+    for (size_t i = 0; i < pr.size(); i++) { mypairs[2 * i] = pr[i].first; mypairs[2 * i + 1] = pr[i].second; }
+  }
+  // ---- 3. the name graph, on every rank
+  std::vector<uint64_t> from, to;
+  {
+    DevBuf<uint64_t> dp;
+    dp.reserve(mypairs.size() ? mypairs.size() : 1);
+    if (!mypairs.empty()) CUDA_CHECK(cudaMemcpyAsync(dp.p, mypairs.data(), sizeof(uint64_t) * mypairs.size(), cudaMemcpyHostToDevice, c->stream));
+    int64_t tot = 0;
+    uint64_t *allp = gather_var<uint64_t>(c, dp.p, (int64_t)mypairs.size(), cnt, tot);
+    std::vector<uint64_t> ap((size_t)tot);
+    if (tot) { CUDA_CHECK(cudaMemcpyAsync(ap.data(), allp, sizeof(uint64_t) * tot, cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream)); }
+    ahf::dfree(allp); dp.release();
+    std::vector<uint64_t> keys(ap);
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    std::vector<int32_t> uf(keys.size());
+    for (size_t i = 0; i < uf.size(); i++) uf[i] = (int32_t)i;
+    for (size_t i = 0; i + 1 < ap.size(); i += 2) {
+      const int32_t a = (int32_t)(std::lower_bound(keys.begin(), keys.end(), ap[i]) - keys.begin());
+      const int32_t b = (int32_t)(std::lower_bound(keys.begin(), keys.end(), ap[i + 1]) - keys.begin());
+      uf_unite(uf.data(), a, b);                           // smaller index = smaller key becomes the root (patches.cuh)
+    }
+    from = keys; to.resize(keys.size());
+    for (size_t i = 0; i < keys.size(); i++) to[i] = keys[(size_t)uf_find(uf.data(), (int32_t)i)];
+  }
+  const int nm = (int)from.size();
+  mfrom.reserve(nm ? nm : 1); mto.reserve(nm ? nm : 1);
+  if (nm) {
+    CUDA_CHECK(cudaMemcpyAsync(mfrom.p, from.data(), sizeof(uint64_t) * nm, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(mto.p, to.data(), sizeof(uint64_t) * nm, cudaMemcpyHostToDevice, c->stream));
+  }
+  // ---- 4. numbering by first cells
+  int nfirst = 0;
+  DevBuf<uint64_t> fk;
+  if (nc > 0) {
+    LAUNCH(c, k_ps_canon, nblk(nc, 256), 256, 0, v, root.p, owned.p, mfrom.p, mto.p, nm, canon.p, first.p);
+    nfirst = exclusive_scan<uint8_t>(c, first.p, pos.p, (uint64_t)nc);
+    fk.reserve(nfirst ? nfirst : 1);
+    if (nfirst) LAUNCH(c, k_ps_firstkeys, nblk(nc, 256), 256, 0, v, first.p, pos.p, fk.p);
+  } else { fk.reserve(1); CUDA_CHECK(cudaStreamSynchronize(c->stream)); }
+  int64_t niso64 = 0;
+  uint64_t *gfirst = gather_var<uint64_t>(c, fk.p, nfirst, cnt, niso64);
+  const int ni = (int)niso64;
+  {                                                      // the ranks' lists are disjoint and sorted: one host sort of the union
+    std::vector<uint64_t> g((size_t)ni);
+    if (ni) { CUDA_CHECK(cudaMemcpyAsync(g.data(), gfirst, sizeof(uint64_t) * ni, cudaMemcpyDeviceToHost, c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->stream)); }
+    std::sort(g.begin(), g.end());
+    if (std::adjacent_find(g.begin(), g.end()) != g.end()) AHF_FAIL("patch labels of a split box: two ranks claim the first cell of one refinement");
+    if (ni) CUDA_CHECK(cudaMemcpyAsync(gfirst, g.data(), sizeof(uint64_t) * ni, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));        // g leaves scope
+  }
+  table.assign((size_t)18 * ni, 0.0);
+  if (ni > 0) {
+    // ---- 5. labels, periodic flags, sums; combined over the ranks
+    per3u.reserve((size_t)3 * ni); per.reserve((size_t)3 * ni);
+    CUDA_CHECK(cudaMemsetAsync(per3u.p, 0, sizeof(uint32_t) * 3 * ni, c->stream));
+    if (nc > 0) LAUNCH(c, k_ps_iso, nblk(nc, 256), 256, 0, v, owned.p, canon.p, gfirst, ni, l.nbr, diso.p, per3u.p, bad.p + 1);
+    cm->allreduce_sum_u32(c, per3u.p, (size_t)3 * ni);
+    LAUNCH(c, k_ps_per3, nblk((size_t)3 * ni, 256), 256, 0, per3u.p, 3 * ni, per.p);
+    accl.reserve((size_t)PS_ACC * ni); iaccl.reserve((size_t)PS_IACC * ni); acc.reserve((size_t)PS_ACC * ni); iacc.reserve((size_t)PS_IACC * ni); div3.reserve((size_t)3 * ni);
+    CUDA_CHECK(cudaMemsetAsync(accl.p, 0, sizeof(double) * PS_ACC * ni, c->stream));
+    CUDA_CHECK(cudaMemsetAsync(iaccl.p, 0, sizeof(unsigned long long) * PS_IACC * ni, c->stream));
+    if (nc > 0) {
+      LAUNCH(c, k_pstat_cells, nblk(nc, 256), 256, 0, v, diso.p, per.p, l.dens, accl.p, iaccl.p, (const uint8_t *)owned.p);
+      if (l.npart_dep > 0)
+        LAUNCH(c, k_pstat_parts, nblk(l.npart_dep, 256), 256, 0, c->pos4, l.plist, l.pcell, (uint64_t)l.npart_dep, c->owner_level, (int)lev, diso.p, per.p, iaccl.p,
+               (uint64_t)S->own_lo, (uint64_t)S->own_hi);
+    }
+    {
+      int hb[2] = { 0, 0 };
+      read_back(c, hb, bad.p, sizeof(hb));
+      if (hb[1]) AHF_FAIL("patch labels of a split box: an own cell belongs to no numbered refinement");
+    }
+    std::vector<size_t> bytes(R), off(R + 1, 0);
+    for (int p = 0; p < R; p++) { bytes[p] = sizeof(double) * PS_ACC * (size_t)ni; off[p + 1] = off[p] + bytes[p]; }
+    double *acc_all = dalloc<double>((size_t)R * PS_ACC * ni);
+    cm->allgatherv(c, accl.p, acc_all, bytes.data(), off.data());
+    for (int p = 0; p < R; p++) { bytes[p] = sizeof(unsigned long long) * PS_IACC * (size_t)ni; off[p + 1] = off[p] + bytes[p]; }
+    unsigned long long *iacc_all = dalloc<unsigned long long>((size_t)R * PS_IACC * ni);
+    cm->allgatherv(c, iaccl.p, iacc_all, bytes.data(), off.data());
+    LAUNCH(c, k_ps_combine_acc, nblk((size_t)ni * PS_ACC, 256), 256, 0, acc_all, iacc_all, R, ni, acc.p, iacc.p);
+    double *out = dalloc<double>((size_t)18 * ni);
+    LAUNCH(c, k_pstat_finish, nblk(ni, 128), 128, 0, acc.p, iacc.p, per.p, ni, (double)l.L, out, div3.p);
+    if (nc > 0) LAUNCH(c, k_pstat_extents, nblk(nc, 256), 256, 0, v, diso.p, div3.p, out, (const uint8_t *)owned.p);
+    for (int p = 0; p < R; p++) { bytes[p] = sizeof(double) * 18 * (size_t)ni; off[p + 1] = off[p] + bytes[p]; }
+    double *out_all = dalloc<double>((size_t)R * 18 * ni);
+    cm->allgatherv(c, out, out_all, bytes.data(), off.data());
+    LAUNCH(c, k_ps_combine_ext, nblk((size_t)ni * 6, 256), 256, 0, out_all, R, ni, out);
+    LAUNCH(c, k_pstat_fix, nblk(ni, 128), 128, 0, ni, out);
+    CUDA_CHECK(cudaMemcpyAsync(table.data(), out, sizeof(double) * 18 * (size_t)ni, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    ahf::dfree(acc_all); ahf::dfree(iacc_all); ahf::dfree(out_all); ahf::dfree(out);
+  }
+  ahf::dfree(gfirst);
+  parent.release(); root.release(); diso.release(); owned.release(); isroot.release(); hasch.release(); touched.release(); first.release(); keep.release(); per.release();
+  pos.release(); bad.release(); rkey.release(); rlab.release(); canon.release(); mfrom.release(); mto.release(); per3u.release(); acc.release(); accl.release(); div3.release();
+  iacc.release(); iaccl.release(); fk.release();
+}
+
 }  // namespace ahf
 
 using namespace ahf;
@@ -2748,10 +3058,22 @@ using namespace ahf;
 extern "C" int ahfgpu_amr_patch_stats(ahfgpu_ctx *c, int32_t lev, int64_t *niso, double *stats, int64_t stats_cap)
 {
   try {
-    if (!c || lev < 0 || lev >= (int)c->levels.size()) AHF_FAIL("bad level");
+    if (!c || lev < 0 || lev >= std::max((int)c->levels.size(), c->g_nlevels)) AHF_FAIL("bad level");
     if (!c->owner_level) AHF_FAIL("no hierarchy");
-    if (c->slab) AHF_FAIL("patch statistics of a box split over several ranks are not implemented (patches cross rank boundaries)");
     CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
+    if (c->slab && c->comm) {                       // ONE box on several ranks: a collective call, every rank ends with the same table
+      auto it = c->pstat_split.find(lev);
+      if (it == c->pstat_split.end()) {
+        std::vector<double> t;
+        patch_stats_split(c, lev, t);
+        it = c->pstat_split.emplace(lev, std::move(t)).first;
+      }
+      const int64_t ni = (int64_t)(it->second.size() / 18);
+      if (stats && ni > stats_cap) AHF_FAIL("stats buffer too small");
+      if (stats && ni > 0) memcpy(stats, it->second.data(), sizeof(double) * 18 * (size_t)ni);
+      if (niso) *niso = ni;
+      return 0;
+    }
     Level &l = c->levels[lev];
     if (!l.dense && !l.nbr) AHF_FAIL("level has no neighbour table");
     const int nc = (int)l.ncell;
@@ -2765,8 +3087,8 @@ extern "C" int ahfgpu_amr_patch_stats(ahfgpu_ctx *c, int32_t lev, int64_t *niso,
       LV v = view(l);
       DevBuf<int32_t> parent, root, diso; DevBuf<uint8_t> isroot, per; DevBuf<int> rank; DevBuf<double> acc, div3; DevBuf<unsigned long long> iacc;
       parent.reserve(nc); root.reserve(nc); diso.reserve(nc); isroot.reserve(nc); rank.reserve(nc); per.reserve((size_t)3 * nc);
-      LAUNCH(c, k_patch_init, nblk(nc, 256), 256, 0, v, l.nbr, parent.p);
-      LAUNCH(c, k_patch_link, nblk(nc, 256), 256, 0, v, l.nbr, parent.p);
+      LAUNCH(c, k_patch_init, nblk(nc, 256), 256, 0, v, l.nbr, parent.p, (const uint8_t *)nullptr);
+      LAUNCH(c, k_patch_link, nblk(nc, 256), 256, 0, v, l.nbr, parent.p, (const uint8_t *)nullptr);
       LAUNCH(c, k_patch_roots, nblk(nc, 256), 256, 0, parent.p, nc, root.p, isroot.p);
       ni = exclusive_scan<uint8_t>(c, isroot.p, rank.p, (uint64_t)nc);
       CUDA_CHECK(cudaMemsetAsync(per.p, 0, (size_t)3 * nc, c->stream));
@@ -2777,11 +3099,11 @@ extern "C" int ahfgpu_amr_patch_stats(ahfgpu_ctx *c, int32_t lev, int64_t *niso,
       iacc.reserve((size_t)PS_IACC * ni);
       CUDA_CHECK(cudaMemsetAsync(acc.p, 0, sizeof(double) * PS_ACC * ni, c->stream));
       CUDA_CHECK(cudaMemsetAsync(iacc.p, 0, sizeof(unsigned long long) * PS_IACC * ni, c->stream));
-      LAUNCH(c, k_pstat_cells, nblk(nc, 256), 256, 0, v, diso.p, per.p, l.dens, acc.p, iacc.p);
+      LAUNCH(c, k_pstat_cells, nblk(nc, 256), 256, 0, v, diso.p, per.p, l.dens, acc.p, iacc.p, (const uint8_t *)nullptr);
       if (l.npart_dep > 0)
-        LAUNCH(c, k_pstat_parts, nblk(l.npart_dep, 256), 256, 0, c->pos4, l.plist, l.pcell, (uint64_t)l.npart_dep, c->owner_level, (int)lev, diso.p, per.p, iacc.p);
+        LAUNCH(c, k_pstat_parts, nblk(l.npart_dep, 256), 256, 0, c->pos4, l.plist, l.pcell, (uint64_t)l.npart_dep, c->owner_level, (int)lev, diso.p, per.p, iacc.p, (uint64_t)0, ~(uint64_t)0);
       LAUNCH(c, k_pstat_finish, nblk(ni, 128), 128, 0, acc.p, iacc.p, per.p, ni, (double)l.L, out, div3.p);
-      LAUNCH(c, k_pstat_extents, nblk(nc, 256), 256, 0, v, diso.p, div3.p, out);
+      LAUNCH(c, k_pstat_extents, nblk(nc, 256), 256, 0, v, diso.p, div3.p, out, (const uint8_t *)nullptr);
       LAUNCH(c, k_pstat_fix, nblk(ni, 128), 128, 0, ni, out);
       CUDA_CHECK(cudaStreamSynchronize(c->stream));
       if (stats && ni > 0) CUDA_CHECK(cudaMemcpy(stats, out, sizeof(double) * 18 * (size_t)ni, cudaMemcpyDeviceToHost));
@@ -2813,8 +3135,8 @@ extern "C" int ahfgpu_amr_patches(ahfgpu_ctx *c, int32_t lev, int32_t *iso, int6
       LV v = view(l);
       DevBuf<int32_t> parent, root, diso; DevBuf<uint8_t> isroot, per; DevBuf<int> rank;
       parent.reserve(nc); root.reserve(nc); diso.reserve(nc); isroot.reserve(nc); rank.reserve(nc); per.reserve((size_t)3 * nc);
-      LAUNCH(c, k_patch_init, nblk(nc, 256), 256, 0, v, l.nbr, parent.p);
-      LAUNCH(c, k_patch_link, nblk(nc, 256), 256, 0, v, l.nbr, parent.p);
+      LAUNCH(c, k_patch_init, nblk(nc, 256), 256, 0, v, l.nbr, parent.p, (const uint8_t *)nullptr);
+      LAUNCH(c, k_patch_link, nblk(nc, 256), 256, 0, v, l.nbr, parent.p, (const uint8_t *)nullptr);
       LAUNCH(c, k_patch_roots, nblk(nc, 256), 256, 0, parent.p, nc, root.p, isroot.p);
       ni = exclusive_scan<uint8_t>(c, isroot.p, rank.p, (uint64_t)nc);
       CUDA_CHECK(cudaMemsetAsync(per.p, 0, (size_t)3 * nc, c->stream));
@@ -2849,6 +3171,7 @@ extern "C" int ahfgpu_amr_level_owned(ahfgpu_ctx *c, int32_t lev, uint8_t *owned
     return 0;
   } catch (const ahf::Error &e) { ahf::g_last_error = e.msg; return -1; }
     catch (const std::exception &e) { ahf::g_last_error = e.what(); return -2; }
+    catch (...) { ahf::g_last_error = "unknown exception"; return -3; }
 }
 
 extern "C" int ahfgpu_amr_level_get(ahfgpu_ctx *c, int32_t lev, int32_t *x, int32_t *y, int32_t *z, float *dens, uint8_t *runflags,

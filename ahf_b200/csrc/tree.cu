@@ -340,6 +340,7 @@ extern "C" int ahfgpu_tree_halos_ex(int32_t nlev, const int64_t *niso, const dou
   }
   catch (const ahf::Error &e) { ahf::g_last_error = e.msg; return -1; }
   catch (const std::exception &e) { ahf::g_last_error = e.what(); return -2; }
+  catch (...) { ahf::g_last_error = "unknown exception"; return -3; }
 }
 
 extern "C" int ahfgpu_tree_halos(int32_t nlev, const int64_t *niso, const double *stats, double max_gather_rad,

@@ -265,6 +265,7 @@ gridls *ahfb200_gen_domgrids(int *no_grids)
     if (ahfgpu_amr_level_header(G, l, io, dd)) die("ahfgpu_amr_level_header");
     x = malloc(io[1] * 4); y = malloc(io[1] * 4); z = malloc(io[1] * 4); dens = malloc(io[1] * 4); rf = malloc(io[1]);
     nodeptr[l] = malloc(io[1] * sizeof(nptr));
+    if (!x || !y || !z || !dens || !rf || !nodeptr[l]) { fprintf(stderr, "ahf_glue: out of memory for level %d (%ld nodes)\n", l, (long)io[1]); common_terminate(EXIT_FAILURE); }
     if (ahfgpu_amr_level_get(G, l, x, y, z, dens, rf, NULL, NULL, NULL)) die("ahfgpu_amr_level_get");
     g->l1dim = (long unsigned)io[0]; g->spacing = 1.0 / (double)io[0]; g->spacing2 = g->spacing * g->spacing;
     g->critdens = dd[0]; g->masstopartdens = dd[1];
@@ -277,6 +278,7 @@ gridls *ahfb200_gen_domgrids(int *no_grids)
   global.fin_l1dim = gl[nlev - 1].l1dim;
   /* node particle lists */
   owner = malloc(n); cell_of = malloc((size_t)nlev * n * sizeof(int32_t));
+  if (!owner || !cell_of) { fprintf(stderr, "ahf_glue: out of memory for the particle -> node map (%d levels x %lu particles)\n", nlev, (unsigned long)n); common_terminate(EXIT_FAILURE); }
   if (ahfgpu_amr_particle_levels(G, owner, cell_of, nlev)) die("ahfgpu_amr_particle_levels");
   for (i = 0; i < n; i++) global_info.fst_part[i].ll = NULL;
   for (l = 0; l < nlev; l++) {

@@ -81,6 +81,37 @@ class SlabRank:
         return mine, res
 
 
+def catalogue_from_ranks(fprefix, params: ahf.Params, seeds: dict, parts, part_id) -> dict:
+    """The four catalogue files of ONE box that several ranks analysed (BASELINE.json configs[3]): `seeds` is what every rank derived
+    (AhfGpu.halo_seeds: identical on all ranks, with the halo_sub lists), `parts` the ranks' (mine, res) pairs of
+    SlabRank.construct_halos (fetched results; member lists are global input indices), `part_id` the ID of every particle of the box
+    by input index.  Sub-halo re-hash, ordering and writers are the library's host code (ahfgpu_catalogue_write): the files equal the
+    single-GPU ones byte for byte.  fprefix None: only re-hash and ordering."""
+    nh = len(seeds["npart"])
+    scal = np.zeros((nh, ahf.NSCAL)); members = [np.zeros(0, np.int64)] * nh; profs = [None] * nh
+    seen = np.zeros(nh, np.int32)
+    for mine, res in parts:
+        for k, h in enumerate(mine):
+            scal[h] = res["scal"][k]; members[h] = ahf.AhfGpu.halo_members(res, k).astype(np.int64); profs[h] = ahf.AhfGpu.halo_profile(res, k)
+            seen[h] += 1
+    if not np.all(seen == 1):
+        raise ahf.AhfGpuError("every halo must be served by exactly one rank")
+    a = params.r_fac / params.x_fac
+    fac = dict(x_fac=params.x_fac, r_fac=params.r_fac, v_fac=params.v_fac, m_fac=params.m_fac, rho_fac=params.rho_fac, phi_fac=params.phi_fac,
+               u_fac=(params.v_fac * a) ** 2, rho_vir=params.rho_vir, pmass=params.m_fac)
+    profs = [p if scal[i, 9] >= params.min_part else None for i, p in enumerate(profs)]
+    return ahf.catalogue_write(fprefix, scal, seeds["pos"], members, profs, seeds["host"], seeds["host_level"], seeds["halo_sub"], part_id, fac, params.min_part)
+
+
+def gather_parts_torch(mine, res, dst: int = 0):
+    """the ranks' halo results on rank `dst` (list of (mine, res) in rank order; None elsewhere) -- one process per GPU"""
+    import torch.distributed as dist
+    keep = {k: res[k] for k in ("scal", "members", "member_offset", "prof", "prof_offset") if k in res}
+    out = [None] * dist.get_world_size() if dist.get_rank() == dst else None
+    dist.gather_object((np.asarray(mine), keep), out, dst=dst)
+    return out
+
+
 def nccl_id_via_torch(rank: int, device) -> bytes:
     """rank 0 makes the NCCL id, torch.distributed (already initialised by the caller) hands it to everybody"""
     import torch
