@@ -283,9 +283,27 @@ def bench_slab(args, rank, world, local_rank, config):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # halo seeds: from the box's OWN hierarchy (default) -- patch labels joined across the rank boundaries, per-refinement tables combined
+    # over the ranks (a collective call per level), the tree on every rank; computed once before the timed passes, like the N = 1 arm
+    gw = 0.0
+    seeds_info = {"source": args.seeds}
+    hs = None
+    if args.seeds == "device":
+        maxg = 3.0 / boxsize
+        sb.redistribute(id_base=id_base, ghost_width=min(maxg, 0.25)); sb.build_amr()
+        g.halo_seeds(maxg)                                                # warm (allocations)
+        sb.build_amr()
+        barrier(); t0 = time.perf_counter()
+        hs = g.halo_seeds(maxg)
+        barrier(); seeds_info["ms_once_outside_the_timed_step"] = 1e3 * (time.perf_counter() - t0)
+        c, r, seed = np.ascontiguousarray(hs["pos"]), np.ascontiguousarray(hs["gather_rad"]), np.ascontiguousarray(hs["npart"], np.int64)
+        gw = float(r.max()) * (1.0 + 1e-9) if len(r) else 0.0              # the shell must hold the largest gathering sphere
+        seeds_info.update(n=int(len(r)), refinements=int(sum(len(q) for q in hs["stats"])), max_gather_rad=gw,
+                          what="labels + per-refinement tables on the devices (collective per level), tree + seeds on every rank, wall clock")
+
     def step_resident():
         st = {}
-        sb.redistribute(id_base=id_base)
+        sb.redistribute(id_base=id_base, ghost_width=gw)
         st.update({k: g.stage_ms(k) for k in ("slab_keys", "slab_histogram_allreduce", "slab_decompose", "slab_partition", "slab_exchange", "keys", "sort", "gather")})
         sb.build_amr()
         st.update({k: g.stage_ms(k) for k in ("amr_total", "ll", "deposit", "deposit_dom_kernel", "flag", "refine", "relink", "rows_allgather", "level_allgather", "rows_merge", "rows_owned")})
@@ -296,7 +314,7 @@ def bench_slab(args, rank, world, local_rank, config):
         return st
 
     def step_e2e():
-        sb.distribute_ptr(pos_l.data_ptr(), mom_l.data_ptr(), n_loc, id_base=id_base)
+        sb.distribute_ptr(pos_l.data_ptr(), mom_l.data_ptr(), n_loc, id_base=id_base, ghost_width=gw)
         sb.build_amr()
         mine, res = sb.construct_halos(c, r, seed, fetch=True)
         return mine, res
@@ -330,6 +348,32 @@ def bench_slab(args, rank, world, local_rank, config):
     clocks = sampler.stop()
     d2h = int(sum(v.nbytes for v in res.values() if hasattr(v, "nbytes")))
     nh_ok = int((res["scal"][:, 9] >= par.min_part).sum())
+    # ---- BASELINE.json configs[3]: the catalogue of the box.  The ranks' results go to rank 0 (scalars, member lists as global input
+    #      indices, profiles), which re-hashes the sub-haloes, orders and writes the four files (not timed as part of the step)
+    cat_info = None
+    members_total = int(len(res["members"]))
+    if hs is not None:
+        mt = torch.tensor([float(members_total)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(mt)
+        if float(mt[0]) <= args.catalogue_max_members:
+            import shutil, tempfile
+            barrier(); t0 = time.perf_counter()
+            parts = multigpu.gather_parts_torch(mine, res) if world > 1 else [(np.asarray(mine), res)]
+            if rank == 0:
+                d = tempfile.mkdtemp(prefix="ahf_b200_cat_")
+                try:
+                    out = multigpu.catalogue_from_ranks(os.path.join(d, "box.z0.000"), par, hs, parts, np.arange(n, dtype=np.uint64))
+                    files = {f.split(".AHF_")[1]: os.path.getsize(os.path.join(d, f)) for f in sorted(os.listdir(d))}
+                    nh_cat = sum(1 for ln in open(os.path.join(d, "box.z0.000.AHF_halos")) if not ln.startswith("#"))
+                    cat_info = {"files_bytes": files, "halos_written": nh_cat, "subhalos": int((out["host"] >= 0).sum()),
+                                "wall_s_gather_rehash_write": time.perf_counter() - t0, "members": int(float(mt[0])),
+                                "what": "results of all ranks gathered on rank 0, ahfgpu_catalogue_write (re-hash, ordering, the reference's four file formats)"}
+                finally:
+                    shutil.rmtree(d, ignore_errors=True)
+            barrier()
+        else:
+            cat_info = {"skipped": f"{int(float(mt[0]))} members above --catalogue-max-members {int(args.catalogue_max_members)}"}
     st = {k: float(np.mean([q[k] for q in stages])) for k in stages[0]}
     st["deposit_dom_kernel"] = float(np.mean([t["deposit_dom_kernel"] for t in timed]))
     # per-rank facts: maxima / sums over the ranks
@@ -369,7 +413,10 @@ def bench_slab(args, rank, world, local_rank, config):
                             "ghost_overhead": float(sm[0]) / n - 1.0, "own_particles_rank0": info["own_hi"] - info["own_lo"]},
                 "stages_ms_rank0": {k: v for k, v in st.items() if k not in ("deposit_particles", "halo_gathered", "halos_mine")},
                 "throughput": {"levels": info["levels"], "halos_in": len(r), "halos_ge_minpart": int(sm[2]), "halo_gathered_particles": float(sm[4]),
-                               "deposit_particles_all_levels_incl_ghosts": float(sm[5])}}
+                               "deposit_particles_all_levels_incl_ghosts": float(sm[5])},
+                "halo_seeds": seeds_info}
+        if cat_info is not None:
+            line["catalogue"] = cat_info
         emit(line)
     sb.close()
     if world > 1:
@@ -387,6 +434,7 @@ def main():
     ap.add_argument("--ref-n1d", type=int, default=256, help="box of the reference arm / cpu_baseline leg (default: the N = 1 workload itself)")
     ap.add_argument("--seeds", default="device", choices=["device", "generator"], help="halo seeds of the N = 1 arm: from the device hierarchy (default) or the generator's clump centres")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--catalogue-max-members", type=float, default=4e8, help="N > 1: write the box's catalogue once after the timed passes unless it holds more member entries than this")
     ap.add_argument("--no-dropin", action="store_true", help="skip the wall-clock run of the drop-in program on the reference leg's GADGET file")
     ap.add_argument("--no-many-haloes", action="store_true", help="skip the second halo-pass measurement (box with 2e4 clumps, seeds from the device tree)")
     ap.add_argument("--breakdown", action="store_true", help="print the per-stage table to stderr")

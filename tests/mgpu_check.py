@@ -31,12 +31,33 @@ def main():
     sb = multigpu.SlabRank(par, rank, world, lr, nccl_id=multigpu.nccl_id_via_torch(rank, torch.device("cuda", lr)))
     sb.distribute(box.pos[b[rank]:b[rank + 1]], box.mom[b[rank]:b[rank + 1]], id_base=int(b[rank]))
     rep = slab_util.rank_report(sb, c, r, seed)
+    # seeds from the split box's own hierarchy (labels joined across the ranks over NCCL), halo pass on the owners, catalogue on rank 0
+    maxg = 3.0 / box.boxsize
+    sb.distribute(box.pos[b[rank]:b[rank + 1]], box.mom[b[rank]:b[rank + 1]], id_base=int(b[rank]), ghost_width=min(maxg, 0.25))
+    sb.build_amr()
+    sd = sb.g.halo_seeds(maxg)
+    mine, res = sb.construct_halos(np.ascontiguousarray(sd["pos"]), np.ascontiguousarray(sd["gather_rad"]), np.ascontiguousarray(sd["npart"], np.int64))
+    parts = multigpu.gather_parts_torch(mine, res)
     sb.close()
     blobs = [None] * world
     dist.all_gather_object(blobs, pickle.dumps(rep))
     if rank == 0:
+        import tempfile
         T = slab_util.single_gpu_truth(ahf, box, n1d, c, r, seed, device=lr)
         out = slab_util.check_against_truth([pickle.loads(x) for x in blobs], T, n)
+        with tempfile.TemporaryDirectory() as d, ahf.AhfGpu(par) as g:
+            keys, order = g.sfc_sort(box.pos, box.mom); g.build_amr()
+            ref = g.halo_seeds(maxg)
+            for k in ("pos", "npart", "host", "host_level"):
+                assert np.array_equal(sd[k], ref[k]), k
+            assert np.allclose(sd["gather_rad"], ref["gather_rad"], rtol=1e-9, atol=0)
+            r1 = dict(g.construct_halos(np.ascontiguousarray(ref["pos"]), np.ascontiguousarray(ref["gather_rad"]), np.ascontiguousarray(ref["npart"], np.int64)))
+            r1["members"] = order.astype(np.int64)[r1["members"]]
+            multigpu.catalogue_from_ranks(os.path.join(d, "one.z0.000"), par, ref, [(np.arange(len(ref["npart"])), r1)], box.ids)
+            multigpu.catalogue_from_ranks(os.path.join(d, "split.z0.000"), par, sd, parts, box.ids)
+            for ext in ("AHF_halos", "AHF_profiles", "AHF_substructure", "AHF_particles"):
+                assert open(os.path.join(d, "one.z0.000." + ext), "rb").read() == open(os.path.join(d, "split.z0.000." + ext), "rb").read(), ext
+            out["seeds"] = len(ref["npart"])
         print("MGPU_OK world=%d %s" % (world, out))
     dist.barrier()
     dist.destroy_process_group()
