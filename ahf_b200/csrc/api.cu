@@ -440,6 +440,25 @@ int ahfgpu_particle_ids(ahfgpu_ctx *c, uint32_t *ids)
   API_END
 }
 
+// the same copy enqueued behind the momentum upload of ahfgpu_sfc_sort_soa_async on the library's copy stream: it travels (device -> host,
+// the idle direction of the bus) while the hierarchy is built and is complete when the next call that waits for the momenta returns
+// (ahfgpu_construct_halos).  ids should be pinned memory; without a pending asynchronous sort this is ahfgpu_particle_ids.
+int ahfgpu_particle_ids_async(ahfgpu_ctx *c, uint32_t *ids)
+{
+  API_BEGIN
+  if (!c || !c->order) AHF_FAIL("no resident particle index (order) array");
+  if (!ids && c->n) AHF_FAIL("null argument");
+  CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
+  if (!c->mom_pending || !c->copy_stream) {
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (c->n) CUDA_CHECK(cudaMemcpy(ids, c->order, sizeof(uint32_t) * c->n, cudaMemcpyDeviceToHost));
+  } else {
+    if (c->n) CUDA_CHECK(cudaMemcpyAsync(ids, c->order, sizeof(uint32_t) * c->n, cudaMemcpyDeviceToHost, c->copy_stream));
+    CUDA_CHECK(cudaEventRecord(c->ev_mom, c->copy_stream));       // whoever waits for the momenta now waits for this copy as well
+  }
+  API_END
+}
+
 int ahfgpu_adopt_sorted(ahfgpu_ctx *c, const void *pos4_dev, const void *mom4_dev, const void *keys_dev, uint64_t n, int32_t has_weight, int32_t has_u)
 {
   API_BEGIN

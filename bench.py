@@ -554,6 +554,7 @@ def main():
 
     def step_e2e():
         g.sfc_sort_async_ptr(hpos.data_ptr(), hmom.data_ptr(), n)      # momenta travel behind the sort and the hierarchy build
+        g._chk(g._L.ahfgpu_particle_ids_async(g._h, horder.data_ptr()))   # the permutation that ties member offsets to the caller's particles: device -> host behind the momenta
         g.build_amr()
         g.construct_halos(centres, rad, seednp, fetch=False)
         res = g.fetch_halos(len(rad), bufs={k: v.numpy() for k, v in pinned.items()})   # scalars, member lists, profiles: everything the catalogue writers read
@@ -561,7 +562,6 @@ def main():
             for k, v in res.items():
                 if k in ("scal", "members", "prof"):
                     pinned[k] = torch.empty((int(v.size * 1.25) + 1024,), dtype=torch.float64 if v.dtype == np.float64 else torch.int64, pin_memory=True)
-        g._chk(g._L.ahfgpu_particle_ids(g._h, horder.data_ptr()))      # + the permutation that ties member offsets to the caller's particles
         return res
 
     # ---- HBM-resident timing

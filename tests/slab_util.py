@@ -3,12 +3,12 @@ tests/mgpu_check.py): what a rank of a split box holds on ITS OWN cells / partic
 import numpy as np
 
 
-def single_gpu_truth(A, box, n1d, centres, rad, seed, device=0):
+def single_gpu_truth(A, box, n1d, centres, rad, seed, device=0, weight=None, u=None):
     """the whole box on one GPU: per level {cell key -> (dens bits, mark, runflags, count)}, final level of every particle, halo table"""
     par = A.make_params(boxsize=box.boxsize, pmass=box.pmass, lgrid_dom=n1d, device=device)
     T = {}
     with A.AhfGpu(par) as g:
-        keys, order = g.sfc_sort(box.pos, box.mom)
+        keys, order = g.sfc_sort(box.pos, box.mom, weight, u)
         nl = g.build_amr()
         T["nl"] = nl
         T["levels"] = []

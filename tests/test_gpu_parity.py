@@ -212,9 +212,13 @@ def test_overlapped_upload_gives_the_same_results(A, golden):
     if golden.weight is not None:
         hw = torch.from_numpy(np.ascontiguousarray(golden.weight, np.float32)).pin_memory()
         hu = torch.from_numpy(np.ascontiguousarray(golden.u, np.float32)).pin_memory()
+    ho = torch.full((hp.shape[0],), -1, dtype=torch.int32).pin_memory()
     with _ctx(A, golden) as g:
         for _ in range(2):
             g.sfc_sort_async_ptr(hp.data_ptr(), hm.data_ptr(), hp.shape[0], hw.data_ptr() if hw is not None else 0,
                                  hu.data_ptr() if hu is not None else 0)
+            ho.fill_(-1)
+            g._chk(g._L.ahfgpu_particle_ids_async(g._h, ho.data_ptr()))       # permutation: device -> host behind the momenta
             _check_levels(g, golden)
-            _check_halos(g, golden)
+            _check_halos(g, golden)                                            # construct_halos has returned: the copy is complete
+            assert np.array_equal(ho.numpy().view(np.uint32), g.particle_ids())
