@@ -642,6 +642,7 @@ def main():
     # stage-level fractions of the HBM peak with the ALGORITHMIC bytes of SURVEY 8d (explanatory; `roofline` above is the contract's object)
     sumN = st["deposit_particles"]
     sumC = float(sum(g.level_header(l)[0][1] for l in range(nlev)))
+    Clast, Nlast = float(g.level_header(nlev - 1)[0][1]), float(g.level_header(nlev - 1)[0][2])
     def _rf(nbytes, ms):
         gbs = nbytes / (ms * 1e-3) / 1e9
         return {"algorithmic_bytes": nbytes, "ms": ms, "achieved_gbs": gbs, "frac": gbs / peak}
@@ -650,6 +651,11 @@ def main():
         "keys+sort+gather (264 N)": _rf(264.0 * n, st["keys"] + st["sort"] + st["gather"]),
         "deposit, all levels (16 sum N_l + 4 sum C_l)": _rf(16.0 * sumN + 4.0 * sumC, st["deposit"]),
         "flags (5 sum C_l)": _rf(5.0 * sumC, st["flag"]),
+        # next-level construction: reads the marks of a level (1 B per cell), writes per NEW cell the key (8), the compressed neighbour
+        # table (40), parent link (4), interior / x-break / mark / tn bytes (4), dens (4) and the row index (4) = 64 B
+        "refine (1 sum C_l + 64 sum C_{l+1})": _rf(1.0 * (sumC - Clast) + 64.0 * (sumC - C0), st["refine"]),
+        # relink: positions of the particles of a level in (16 B each), cell + list entry + local position of the moved ones out (24 B)
+        "relink (16 sum N_l + 24 sum N_{l+1})": _rf(16.0 * (sumN - Nlast) + 24.0 * (sumN - n), st["relink"]),
         "halo pass (92 n_gathered + 21 sum_i n^(i) + 28 n_final)": _rf(92.0 * st["halo_gathered"] + 21.0 * st["halo_iter_members"] + 28.0 * st["halo_final_members"], t_halo),
     }
     # the kernel with the largest share of a pass (profiles/*_launches_summary.txt): the ranked scatter of the main radix sort; per launch it
