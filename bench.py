@@ -552,12 +552,21 @@ def main():
 
     pinned = {}                                                        # result buffers of the end-to-end leg: pinned, sized after the first pass
 
+    e2e_wall = {"upload_pos+keys+sort": 0.0, "mesh": 0.0, "halo pass (waits for the momenta)": 0.0, "fetch": 0.0}
+
     def step_e2e():
+        t0 = time.perf_counter()
         g.sfc_sort_async_ptr(hpos.data_ptr(), hmom.data_ptr(), n)      # momenta travel behind the sort and the hierarchy build
         g._chk(g._L.ahfgpu_particle_ids_async(g._h, horder.data_ptr()))   # the permutation that ties member offsets to the caller's particles: device -> host behind the momenta
+        t1 = time.perf_counter()
         g.build_amr()
+        t2 = time.perf_counter()
         g.construct_halos(centres, rad, seednp, fetch=False)
+        t3 = time.perf_counter()
         res = g.fetch_halos(len(rad), bufs={k: v.numpy() for k, v in pinned.items()})   # scalars, member lists, profiles: everything the catalogue writers read
+        t4 = time.perf_counter()
+        for k, dt in zip(e2e_wall, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+            e2e_wall[k] += 1e3 * dt
         if not pinned:
             for k, v in res.items():
                 if k in ("scal", "members", "prof"):
@@ -590,6 +599,8 @@ def main():
     for _ in range(min(args.warmup, 2)):
         step_e2e()
     barrier()
+    for k in e2e_wall:
+        e2e_wall[k] = 0.0
     g.event_record(2)
     for _ in range(args.steps):
         e2e_res = step_e2e()
@@ -671,7 +682,8 @@ def main():
         "dtype": "f32 particles, u32/u64 fixed-point deposit, f64 halo arithmetic", "data": "synthetic", "config": config,
         "e2e": {"value": world * n / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": 24 * n + 32 * len(rad) + 8 * len(rad),
                 "d2h_bytes_per_step": d2h_bytes,
-                "returns": "halo scalars (64 doubles each), member lists, profiles (25 columns per bin) and the sorted-offset -> input-index permutation"},
+                "returns": "halo scalars (64 doubles each), member lists, profiles (25 columns per bin) and the sorted-offset -> input-index permutation",
+                "host_wall_ms_per_call": {k: v / args.steps for k, v in e2e_wall.items()}},
         "halo_seeds": {"source": args.seeds, "n": int(len(rad)), "ms_once_outside_the_timed_step": seeds_ms, "what_is_timed": "patch labels + per-patch tables of every coloured level on the device, tree + seeds on the host, wall clock",
                        "note": "device: ahfgpu_amr_patch_stats per level (GPU) + ahfgpu_tree_halos (host, includes the O(N_h^2) gathering-radius loop)"},
         "gpu_launches": int(launches),
