@@ -1,6 +1,7 @@
 // api.cu -- extern "C" entry points of libahfgpu.so (see include/ahfgpu.h) and context housekeeping.
 #include "common.cuh"
 #include <chrono>
+#include <algorithm>
 #include "comm.cuh"
 #include "hilbert.cuh"
 #include <mutex>
@@ -96,6 +97,33 @@ void ahfgpu_ctx::stage_resolve()
     stage_ms[s.name] += ms; stage_cnt[s.name] += s.count;
   }
   stages_resolved = true;
+}
+void ahfgpu_ctx::ktime_mark(const char *name, bool begin)
+{
+  auto take = [&](cudaEvent_t &e) { if (event_pool.empty()) cudaEventCreate(&e); else { e = event_pool.back(); event_pool.pop_back(); } };
+  if (begin) { KRec r; r.name = name; take(r.a); take(r.b); cudaEventRecord(r.a, stream); krecs.push_back(r); }
+  else if (!krecs.empty()) cudaEventRecord(krecs.back().b, stream);
+}
+void ahfgpu_ctx::ktime_dump(const char *label)
+{
+  if (krecs.empty()) return;
+  cudaStreamSynchronize(stream);
+  std::map<std::string, std::pair<double, int>> sum;
+  double tk = 0.0, tg = 0.0, span = 0.0;
+  float ms = 0.f;
+  for (size_t i = 0; i < krecs.size(); i++) {
+    cudaEventElapsedTime(&ms, krecs[i].a, krecs[i].b);
+    sum[krecs[i].name].first += ms; sum[krecs[i].name].second++; tk += ms;
+    if (i + 1 < krecs.size()) { cudaEventElapsedTime(&ms, krecs[i].b, krecs[i + 1].a); tg += ms; }
+  }
+  cudaEventElapsedTime(&ms, krecs.front().a, krecs.back().b); span = ms;
+  std::vector<std::pair<double, std::string>> v;
+  for (auto &kv : sum) v.push_back({ kv.second.first, kv.first });
+  std::sort(v.begin(), v.end(), [](const std::pair<double, std::string> &x, const std::pair<double, std::string> &y) { return x.first > y.first; });
+  fprintf(stderr, "[ktime] %s: %zu launches, span %.3f ms, kernels %.3f ms, between kernels %.3f ms\n", label, krecs.size(), span, tk, tg);
+  for (auto &e : v) fprintf(stderr, "[ktime]   %-44s %4d x  %8.4f ms  %5.1f%%\n", e.second.c_str(), sum[e.second].second, e.first, 100.0 * e.first / span);
+  for (auto &r : krecs) { event_pool.push_back(r.a); event_pool.push_back(r.b); }
+  krecs.clear();
 }
 void ahfgpu_ctx::wait_mom(bool host)
 {
@@ -276,7 +304,9 @@ int ahfgpu_sfc_sort_soa(ahfgpu_ctx *c, const float *pos3, const float *mom3, con
   if (!c || ((!pos3 || !mom3) && n)) AHF_FAIL("null argument");
   CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
   c->stage_reset();
+  c->ktime = getenv("AHFGPU_KTIME") != nullptr;
   sfc_sort_soa(c, pos3, mom3, weight, u, n, keys_out, order_out);
+  c->ktime_dump("ahfgpu_sfc_sort_soa");
   API_END
 }
 
@@ -306,7 +336,9 @@ int ahfgpu_sfc_sort_resident(ahfgpu_ctx *c)
   if (!c) AHF_FAIL("null ctx");
   CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
   c->stage_reset();
+  c->ktime = getenv("AHFGPU_KTIME") != nullptr;
   sfc_sort_resident(c, nullptr, nullptr);
+  c->ktime_dump("ahfgpu_sfc_sort_resident");
   API_END
 }
 
@@ -527,7 +559,9 @@ int ahfgpu_build_amr(ahfgpu_ctx *c)
   if (!c->pos4) AHF_FAIL("no resident particles: call ahfgpu_sfc_sort_* first");
   CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
   c->stage_reset();
+  c->ktime = getenv("AHFGPU_KTIME") != nullptr;
   amr_build(c);
+  c->ktime_dump("ahfgpu_build_amr");
   API_END
 }
 
@@ -561,7 +595,9 @@ int ahfgpu_construct_halos(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, 
   CUDA_CHECK(cudaSetDevice(c->dev)); ahf::g_pool_stream = c->stream;
   c->stage_reset();
   c->wait_mom(false);                                  // momenta of ahfgpu_sfc_sort_soa_async: device-side wait, the host does not block
+  c->ktime = getenv("AHFGPU_KTIME") != nullptr;
   halos_construct(c, nhalo, centre3, gather_rad, seed);
+  c->ktime_dump("ahfgpu_construct_halos");
   API_END
 }
 

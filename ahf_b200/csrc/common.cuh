@@ -31,9 +31,13 @@ inline void fail(const char *file, int line, const std::string &what)
   } while (0)
 
 // every kernel launch of the library goes through this macro so that launches can be counted (bench.py gpu_launches)
+// AHFGPU_KTIME=1 (diagnostic, off by default): an event pair around EVERY launch; ahfgpu_ctx::ktime_dump prints the per-kernel sums of a
+// call and the idle time between consecutive kernels to stderr (warm caches, unlike an ncu launch list)
 #define LAUNCH(ctx, kernel, grid, block, smem, ...)                                                      \
   do {                                                                                                   \
+    if ((ctx)->ktime) (ctx)->ktime_mark(#kernel, true);                                                  \
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                                     \
+    if ((ctx)->ktime) (ctx)->ktime_mark(nullptr, false);                                                 \
     (ctx)->n_launches++;                                                                                 \
     CUDA_CHECK(cudaGetLastError());                                                                      \
   } while (0)
@@ -189,6 +193,12 @@ struct ahfgpu_ctx {
   void  *h_up = nullptr; size_t h_up_bytes = 0;         // pinned staging of small host->device uploads (halo tile lists)
   void  *h_pin = nullptr; size_t h_pin_bytes = 0;       // pinned scratch of the small device->host read-backs (ahf::read_back)
   std::vector<cudaEvent_t> event_pool;        // stage-timer events are recycled, not created and destroyed every call
+  // per-launch timing (AHFGPU_KTIME=1, see LAUNCH)
+  struct KRec { const char *name; cudaEvent_t a, b; };
+  bool ktime = false;
+  std::vector<KRec> krecs;
+  void ktime_mark(const char *name, bool begin);
+  void ktime_dump(const char *label);
 
   void stage_reset();
   void stage_resolve();

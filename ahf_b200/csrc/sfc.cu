@@ -257,6 +257,59 @@ void radix_sort_pairs(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t *k
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2, the 63-bit Hilbert keys of the particles: six passes instead of eight.  The LSD passes sort bits KS_SKIP..62 only; particles
+// whose keys agree in all of those bits sit in one cell of 2^-16 of the box per dimension -- none on the lattice part of a box, pairs
+// and triples in clump cores -- and are still in input order.  k_fix_key_ties puts every such run into the order of the full stable
+// sort (insertion sort by the whole key; equal keys keep their input order): one thread per run head, two key loads per particle
+// otherwise.  A run longer than KS_MAXRUN (thousands of particles inside one 2^-16 cell: degenerate inputs) raises a flag and the
+// arrangement is sorted again with all eight passes -- the stable sort of a stably pre-sorted array is the full stable sort.
+// ------------------------------------------------------------------------------------------------
+constexpr int KS_SKIP   = 15;
+constexpr int KS_MAXRUN = 32;
+__global__ void k_fix_key_ties(uint64_t *keys, uint32_t *vals, uint64_t n, int *flag)
+{
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i + 1 >= n) return;
+  const uint64_t top = keys[i] >> KS_SKIP;
+  if ((keys[i + 1] >> KS_SKIP) != top) return;                       // alone, or the last of its run
+  if (i > 0 && (keys[i - 1] >> KS_SKIP) == top) return;              // not the head (the top bits of a position never change below)
+  uint64_t j = i + 2;
+  while (j < n && j - i <= (uint64_t)KS_MAXRUN && (keys[j] >> KS_SKIP) == top) j++;
+  if (j - i > (uint64_t)KS_MAXRUN) { *flag = 1; return; }
+  for (uint64_t a = i + 1; a < j; a++) {
+    const uint64_t ka = keys[a];
+    const uint32_t va = vals[a];
+    uint64_t b = a;
+    while (b > i) {
+      const uint64_t kb = keys[b - 1];
+      if (kb <= ka) break;
+      keys[b] = kb; vals[b] = vals[b - 1]; b--;
+    }
+    if (b != a) { keys[b] = ka; vals[b] = va; }
+  }
+}
+int sort_keys63_passes() { const bool full = getenv("AHFGPU_SORT_FULL") != nullptr; return radix_sort_passes(63, full ? 0 : KS_SKIP); }
+void sort_keys63(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, uint64_t n, uint64_t **keys_sorted, uint32_t **vals_sorted)
+{
+  const bool full = getenv("AHFGPU_SORT_FULL") != nullptr;              // A/B timing and the parity tests of the tie fix
+  if (full || n < 2) { radix_sort_pairs(c, keys, vals, keys_tmp, vals_tmp, n, 63, keys_sorted, vals_sorted, 0); return; }
+  radix_sort_pairs(c, keys, vals, keys_tmp, vals_tmp, n, 63, keys_sorted, vals_sorted, KS_SKIP);
+  DevBuf<int> flag;
+  flag.reserve(1);
+  CUDA_CHECK(cudaMemsetAsync(flag.p, 0, sizeof(int), c->stream));
+  LAUNCH(c, k_fix_key_ties, (unsigned)((n + 255) / 256), 256, 0, *keys_sorted, *vals_sorted, n, flag.p);
+  int h = 0;
+  read_back(c, &h, flag.p, sizeof(int));
+  flag.release();
+  c->stage_cnt_extra["sort_full_fallback"] = h ? 1 : 0;
+  if (h) {
+    uint64_t *k0 = *keys_sorted, *k1 = (k0 == keys) ? keys_tmp : keys;
+    uint32_t *v0 = *vals_sorted, *v1 = (v0 == vals) ? vals_tmp : vals;
+    radix_sort_pairs(c, k0, v0, k1, v1, n, 63, keys_sorted, vals_sorted, 0);       // eight passes: ends in the buffer it started in
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // payload gather
 // ------------------------------------------------------------------------------------------------
 __global__ void k_gather_soa(const float *__restrict__ pos3, const float *__restrict__ mom3, const float *__restrict__ w,
@@ -346,7 +399,7 @@ void sfc_sort_resident(ahfgpu_ctx *c, uint64_t *keys_out, uint32_t *order_out)
   k1.reserve(n); v1.reserve(n);
   const unsigned nb = (unsigned)((n + 255) / 256);
   // an odd number of passes ends in the OTHER buffer: start in the scratch pair then, so that the result lands in keys / order
-  const bool odd = (radix_sort_passes(63, 0) & 1) != 0;
+  const bool odd = (sort_keys63_passes() & 1) != 0;
   uint64_t *kA = odd ? k1.p : c->keys, *kB = odd ? c->keys : k1.p;
   uint32_t *vA = odd ? v1.p : c->order, *vB = odd ? c->order : v1.p;
   {
@@ -356,7 +409,7 @@ void sfc_sort_resident(ahfgpu_ctx *c, uint64_t *keys_out, uint32_t *order_out)
   uint64_t *ks; uint32_t *vs;
   {
     Stage st(c, "sort", (int64_t)n);
-    radix_sort_pairs(c, kA, vA, kB, vB, n, 63, &ks, &vs);
+    sort_keys63(c, kA, vA, kB, vB, n, &ks, &vs);
     if (ks != c->keys) {
       CUDA_CHECK(cudaMemcpyAsync(c->keys, ks, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
       CUDA_CHECK(cudaMemcpyAsync(c->order, vs, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
@@ -433,7 +486,7 @@ void sfc_sort_soa_async(ahfgpu_ctx *c, const float *pos3, const float *mom3, con
   CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
   constexpr int NCH = 4;
   upload_hil_tab3();
-  const bool odd = (radix_sort_passes(63, 0) & 1) != 0;      // see sfc_sort_resident
+  const bool odd = (sort_keys63_passes() & 1) != 0;      // see sfc_sort_resident
   uint64_t *kA = odd ? k1.p : c->keys, *kB = odd ? c->keys : k1.p;
   uint32_t *vA = odd ? v1.p : c->order, *vB = odd ? c->order : v1.p;
   const uint64_t per = ((n + NCH - 1) / NCH + 255) & ~255ull;
@@ -454,7 +507,7 @@ void sfc_sort_soa_async(ahfgpu_ctx *c, const float *pos3, const float *mom3, con
   uint64_t *ks; uint32_t *vs;
   {
     Stage st(c, "sort", (int64_t)n);
-    radix_sort_pairs(c, kA, vA, kB, vB, n, 63, &ks, &vs);
+    sort_keys63(c, kA, vA, kB, vB, n, &ks, &vs);
     if (ks != c->keys) {
       CUDA_CHECK(cudaMemcpyAsync(c->keys, ks, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
       CUDA_CHECK(cudaMemcpyAsync(c->order, vs, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
@@ -539,7 +592,7 @@ void sfc_sort_device4_gid(ahfgpu_ctx *c, const void *pos4_dev, const void *mom4_
   uint64_t *ks; uint32_t *vs;
   {
     Stage st(c, "sort", (int64_t)n);
-    radix_sort_pairs(c, k0.p, v0.p, k1.p, v1.p, n, 63, &ks, &vs);
+    sort_keys63(c, k0.p, v0.p, k1.p, v1.p, n, &ks, &vs);
   }
   {
     Stage st(c, "gather", (int64_t)n);
@@ -578,7 +631,7 @@ void sfc_sort_aos(ahfgpu_ctx *c, void *part, uint64_t n, uint32_t stride, int of
   uint64_t *ks; uint32_t *vs;
   {
     Stage st(c, "sort", (int64_t)n);
-    radix_sort_pairs(c, k0.p, v0.p, k1.p, v1.p, n, 63, &ks, &vs);
+    sort_keys63(c, k0.p, v0.p, k1.p, v1.p, n, &ks, &vs);
   }
   {
     Stage st(c, "gather", (int64_t)n);

@@ -165,3 +165,48 @@ def test_halo_edge_cases(A, O):
             if o["npart"] >= par.min_part:
                 assert np.allclose(S[i, 10:14], o["s"][10:14], rtol=1e-9), i
         assert int(S[0, 9]) >= par.min_part                  # the wrapped clump is a real halo
+
+
+@pytest.mark.parametrize("case", ["pairs", "runs32", "long", "equal", "sorted_input"])
+def test_key_sort_tie_fix_equals_the_full_stable_sort(A, O, case, monkeypatch):
+    """K2 sorts bits 15..62 of the Hilbert keys in six radix passes and orders the particles that share all of them (one cell of
+    2^-16 of the box per dimension) by the whole key afterwards (sfc.cu: k_fix_key_ties); runs longer than 32 fall back to the
+    eight-pass sort.  Keys and permutation must equal the stable sort of the oracle's keys in every case."""
+    rng = np.random.default_rng(11)
+    n = 60000
+    pos = rng.random((n, 3), dtype=np.float32)
+    cell = np.float32(2.0 ** -16)
+    if case == "pairs":            # 2..4 particles per 2^-16 cell, distinct low bits
+        base = np.floor(rng.random((n // 3, 3)) * 65536).astype(np.float32) * cell
+        pos = (np.repeat(base, 3, axis=0) + rng.random((n, 3), dtype=np.float32) * cell).astype(np.float32)
+    elif case == "runs32":         # up to 32 per cell: the longest run the insertion sort takes
+        base = np.floor(rng.random((n // 30, 3)) * 65536).astype(np.float32) * cell
+        pos = (np.repeat(base, 30, axis=0) + rng.random((n, 3), dtype=np.float32) * cell).astype(np.float32)
+    elif case == "long":           # thousands of distinct keys inside one cell: the fallback
+        pos[:5000] = (np.float32(0.3) + rng.random((5000, 3), dtype=np.float32) * cell).astype(np.float32)
+    elif case == "equal":          # thousands of identical particles: equal FULL keys keep their input order
+        pos[1000:4000] = pos[7]
+        pos[10000:10020] = pos[8]
+    elif case == "sorted_input":
+        pass
+    pos = np.clip(pos, 0.0, np.float32(1.0) - np.float32(2.0 ** -24)).astype(np.float32)
+    rng.shuffle(pos, axis=0)
+    mom = rng.standard_normal((n, 3)).astype(np.float32)
+    okeys = O.hilbert_keys(pos)
+    if case == "sorted_input":
+        o = np.argsort(okeys, kind="stable"); pos, mom, okeys = pos[o], mom[o], okeys[o]
+    oorder = np.argsort(okeys, kind="stable")
+    top = okeys[oorder] >> np.uint64(15)
+    runlen = np.diff(np.flatnonzero(np.concatenate([[True], top[1:] != top[:-1], [True]])))
+    with A.AhfGpu(_par(A, 32, n)) as g:
+        keys, order = g.sfc_sort(pos, mom)
+        fell_back = g.stage_count("sort_full_fallback")
+    assert np.array_equal(keys, okeys[oorder])
+    assert np.array_equal(order.astype(np.int64), oorder)
+    assert fell_back == (1 if runlen.max() > 32 else 0), (case, runlen.max(), fell_back)
+    if case in ("pairs", "runs32"):
+        assert runlen.max() >= 2 and runlen.max() <= 32
+    monkeypatch.setenv("AHFGPU_SORT_FULL", "1")
+    with A.AhfGpu(_par(A, 32, n)) as g:
+        keys8, order8 = g.sfc_sort(pos, mom)
+    assert np.array_equal(keys8, keys) and np.array_equal(order8, order)
