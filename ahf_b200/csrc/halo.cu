@@ -205,43 +205,47 @@ __global__ void __launch_bounds__(HB) k_gather_fill(const float4 *__restrict__ p
 // ------------------------------------------------------------------------------------------------
 // U1: radial sort = LSD radix sort by r^2 bits, then stable sort by halo -> (halo, r^2, gather order)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_sort_setup(const int64_t *__restrict__ candoff, const int64_t *__restrict__ ngather, const int64_t *__restrict__ eoff, int64_t nhalo,
-                             int min_part, const double *__restrict__ r2buf, uint64_t *__restrict__ key, uint32_t *__restrict__ val,
-                             uint32_t *__restrict__ hid)
+// Radial sort of ALL haloes in one LSD sort: key = halo index (hb bits) | 6 exponent bits | mb mantissa bits of r^2, a monotone but
+// not injective image of (halo, r^2).  Exponents below 2^-64 collapse to zero and the mantissa is cut to mb bits; members whose keys
+// agree are still in gather order and k_fix_ties orders every such run by the whole r^2 (then by gather position): the result is the
+// full stable sort by (halo, r^2).  hb + 6 + mb is a multiple of 8: five passes for the 256^3 box (two sorts of 5 + 2 passes before).
+__device__ __forceinline__ uint64_t halo_sort_key(uint64_t h, double r2, int mb)
 {
-  const int64_t h = blockIdx.x;
-  if (h >= nhalo) return;
-  const int64_t ng = ngather[h];
-  if (ng < min_part) return;                                 // ahf_halos.c:5795: too small, left unsorted
-  const int64_t src = candoff[h], dst = eoff[h];
-  for (int64_t i = threadIdx.x; i < ng; i += blockDim.x) {
-    key[dst + i] = (uint64_t)__double_as_longlong(r2buf[src + i]);     // r^2 >= 0: the bit pattern orders like the value
-    val[dst + i] = (uint32_t)(dst + i);
-    hid[dst + i] = (uint32_t)h;
-  }
+  const uint64_t b = (uint64_t)__double_as_longlong(r2);               // r^2 >= 0: the bit pattern orders like the value
+  const int      e = (int)(b >> 52) - 959;
+  const uint64_t m = (b & ((1ull << 52) - 1ull)) >> (52 - mb);
+  const uint64_t q = e < 0 ? 0ull : e > 63 ? ((64ull << mb) - 1ull) : (((uint64_t)e << mb) | m);
+  return (h << (6 + mb)) | q;
 }
-__global__ void k_hid_keys(const uint32_t *__restrict__ val, const uint32_t *__restrict__ hid, uint64_t ne, uint64_t *__restrict__ key2, uint32_t *__restrict__ val2)
-{
-  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= ne) return;
-  key2[i] = hid[val[i]];
-  val2[i] = val[i];
-}
-// element e of the packed (>= min_part) layout lives at candoff[h] + (e - eoff[h]) of the candidate buffers
-// The radial sort skips the lowest `skip` bits of the r^2 keys (three of its eight passes): members whose keys agree in all the
-// sorted bits are still in gather order.  One thread per such run (a few per 10^5 members: 28 mantissa bits are sorted) puts it
-// into the order the full stable sort gives: by the whole key, then by gather position.
-__global__ void k_fix_ties(uint32_t *__restrict__ perm, const uint32_t *__restrict__ hid, const int64_t *__restrict__ candoff, const int64_t *__restrict__ eoff,
-                           const double *__restrict__ r2buf, uint64_t ne, int skip)
+// one thread per element of the eoff-packed layout (haloes below min_part have empty ranges there: ahf_halos.c:5795, left unsorted);
+// its halo by binary search in eoff -- a CTA per halo was bound by the largest halo (0.26 ms at 256^3)
+__global__ void k_sort_setup(const int64_t *__restrict__ candoff, const int64_t *__restrict__ eoff, int64_t nhalo, uint64_t ne,
+                             const double *__restrict__ r2buf, uint64_t *__restrict__ key, uint32_t *__restrict__ val,
+                             uint32_t *__restrict__ hid, int mb)
 {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= ne) return;
+  int64_t lo = 0, hi = nhalo;                                  // first h with eoff[h] > i, minus one
+  while (lo < hi) { const int64_t mid = lo + ((hi - lo) >> 1); if (eoff[mid] <= (int64_t)i) lo = mid + 1; else hi = mid; }
+  const int64_t h = lo - 1;
+  key[i] = halo_sort_key((uint64_t)h, r2buf[candoff[h] + ((int64_t)i - eoff[h])], mb);
+  val[i] = (uint32_t)i;
+  hid[i] = (uint32_t)h;
+}
+// element e of the packed (>= min_part) layout lives at candoff[h] + (e - eoff[h]) of the candidate buffers
+// One thread per run of equal sort keys (a few per 10^5 members: the mantissa bits kept resolve well below the spacing of neighbouring
+// r^2) puts the run into the order the full stable sort gives: by the whole r^2, then by gather position.
+__global__ void k_fix_ties(uint32_t *__restrict__ perm, const uint64_t *__restrict__ skey, const uint32_t *__restrict__ hid, const int64_t *__restrict__ candoff,
+                           const int64_t *__restrict__ eoff, const double *__restrict__ r2buf, uint64_t ne)
+{
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i + 1 >= ne) return;
+  const uint64_t top = skey[i];
+  if (skey[i + 1] != top) return;                                     // alone, or the last of its run
+  if (i > 0 && skey[i - 1] == top) return;                            // not the head of its run
   auto key = [&](uint32_t e) { const uint32_t h = hid[e]; return (uint64_t)__double_as_longlong(r2buf[candoff[h] + ((int64_t)e - eoff[h])]); };
-  const uint32_t e = perm[i], h = hid[e];
-  const uint64_t top = key(e) >> skip;
-  if (i > 0) { const uint32_t p = perm[i - 1]; if (hid[p] == h && (key(p) >> skip) == top) return; }       // not the head of its run
-  uint64_t j = i + 1;
-  while (j < ne) { const uint32_t q = perm[j]; if (hid[q] != h || (key(q) >> skip) != top) break; j++; }
+  uint64_t j = i + 2;
+  while (j < ne && skey[j] == top) j++;
   if (j - i < 2) return;
   auto less = [&](uint32_t ea, uint32_t eb) { const uint64_t ka = key(ea), kb = key(eb); return ka < kb || (ka == kb && ea < eb); };
   if (j - i > 32) {                                            // long run (thin shells, huge haloes): heap sort, O(L log L)
@@ -274,18 +278,16 @@ __global__ void k_fix_ties(uint32_t *__restrict__ perm, const uint32_t *__restri
     perm[b] = ea;
   }
 }
+// sorted position i of the eoff-packed layout -> the halo's slot of the moff0-packed member list (the sort is by halo first, so
+// position i belongs to the halo of the element that landed there)
 __global__ void k_apply_perm(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ hid, const int64_t *__restrict__ candoff,
-                             const int64_t *__restrict__ eoff, uint64_t ne, const uint32_t *__restrict__ idxbuf, uint32_t *__restrict__ sorted_idx)
+                             const int64_t *__restrict__ eoff, const int64_t *__restrict__ moff0, uint64_t ne, const uint32_t *__restrict__ idxbuf,
+                             uint32_t *__restrict__ out)
 {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= ne) return;
   uint32_t e = perm[i], h = hid[e];
-  sorted_idx[i] = idxbuf[candoff[h] + ((int64_t)e - eoff[h])];
-}
-__global__ void k_scatter_sorted(const int64_t *__restrict__ eoff, const int64_t *__restrict__ moff0, const uint32_t *__restrict__ sorted, uint32_t *__restrict__ out)
-{
-  const int64_t h = blockIdx.x, ne = eoff[h + 1] - eoff[h];
-  for (int64_t i = threadIdx.x; i < ne; i += blockDim.x) out[moff0[h] + i] = sorted[eoff[h] + i];
+  out[moff0[h] + ((int64_t)i - eoff[h])] = idxbuf[candoff[h] + ((int64_t)e - eoff[h])];
 }
 __global__ void k_copy_unsorted(const int64_t *__restrict__ candoff, const int64_t *__restrict__ ngather, const int64_t *__restrict__ eoff2,
                                 int min_part, const uint32_t *__restrict__ idxbuf, uint32_t *__restrict__ out)
@@ -2311,31 +2313,23 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
     if (tot_e > 0) {
       uint64_t *k0 = dalloc<uint64_t>(tot_e), *k1 = dalloc<uint64_t>(tot_e);
       uint32_t *v0 = dalloc<uint32_t>(tot_e), *v1 = dalloc<uint32_t>(tot_e), *hid = dalloc<uint32_t>(tot_e);
-      LAUNCH(c, k_sort_setup, (unsigned)nhalo, 256, 0, d_candoff, d_ng, d_eoff, nhalo, P.min_part, d_r2, k0, v0, hid);
       uint64_t *ks; uint32_t *vs;
-      // bits skipped: neighbouring r^2 of a halo with n members differ by ~1/n relative, so 52 - skip mantissa bits must resolve
-      // well below that or the tie runs grow (measured: skip 32 costs 2.7 instead of 0.85 ms at 256^3, seconds on a 1e7 host)
+      // mantissa bits kept: neighbouring r^2 of a halo with n members differ by ~1/n relative, so lg(n) + 6 bits leave a tie in about
+      // one pair of 64 (measured before the two sorts were merged: too few bits cost 2.7 instead of 0.85 ms at 256^3, seconds on a 1e7 host)
       int64_t nmax = 1;
       for (int64_t h = 0; h < nhalo; h++) nmax = std::max(nmax, h_ng[h]);
       int lg = 0; while ((1ll << lg) < nmax) lg++;
-      int skip = 8 * ((48 - lg) / 8); skip = skip < 0 ? 0 : skip > 24 ? 24 : skip;
-      if (getenv("AHFGPU_HALO_SORT_SKIP")) skip = atoi(getenv("AHFGPU_HALO_SORT_SKIP"));                       // multiple of 8, < 64
-      radix_sort_pairs(c, k0, v0, k1, v1, (uint64_t)tot_e, 64, &ks, &vs, skip);
-      // second, stable pass by halo index
-      uint64_t *k2 = (ks == k0) ? k1 : k0; uint32_t *v2 = (vs == v0) ? v1 : v0;
       int hb = 1; while ((1ll << hb) < nhalo) hb++;
-      // keys for pass 2 overwrite the other buffer; values need a third buffer because ks/vs are still read
-      uint32_t *v3 = dalloc<uint32_t>(tot_e);
-      LAUNCH(c, k_hid_keys, nblk(tot_e, 256), 256, 0, vs, hid, (uint64_t)tot_e, k2, v3);
-      uint64_t *ks2; uint32_t *vs2;
-      radix_sort_pairs(c, k2, v3, ks, v2, (uint64_t)tot_e, hb, &ks2, &vs2);
-      // sorted members go to the positions eoff-packed; map back to the moff0-packed layout per halo
-      uint32_t *sorted = dalloc<uint32_t>(tot_e);
-      if (skip > 0) LAUNCH(c, k_fix_ties, nblk(tot_e, 256), 256, 0, vs2, hid, d_candoff, d_eoff, d_r2, (uint64_t)tot_e, skip);
-      LAUNCH(c, k_apply_perm, nblk(tot_e, 256), 256, 0, vs2, hid, d_candoff, d_eoff, (uint64_t)tot_e, d_idx, sorted);
-      // scatter halo segments: eoff-layout -> moff0-layout
-      LAUNCH(c, k_scatter_sorted, (unsigned)nhalo, 256, 0, d_eoff, d_moff0, sorted, d_members);
-      ahf::dfree(k0); ahf::dfree(k1); ahf::dfree(v0); ahf::dfree(v1); ahf::dfree(hid); ahf::dfree(v3); ahf::dfree(sorted);
+      int mbmin = std::min(52, lg + 6);
+      if (getenv("AHFGPU_HALO_SORT_SKIP")) mbmin = std::max(0, 52 - atoi(getenv("AHFGPU_HALO_SORT_SKIP")));     // tests: long tie runs
+      const int passes = std::min(8, (hb + 6 + mbmin + 7) / 8);
+      const int mb = std::min(52, passes * 8 - hb - 6);                  // the key fits 64 bits: hb <= 32, so mb >= 26 in eight passes
+      LAUNCH(c, k_sort_setup, nblk(tot_e, 256), 256, 0, d_candoff, d_eoff, nhalo, (uint64_t)tot_e, d_r2, k0, v0, hid, mb);
+      radix_sort_pairs(c, k0, v0, k1, v1, (uint64_t)tot_e, hb + 6 + mb, &ks, &vs, 0);
+      uint32_t *vs2 = vs;
+      LAUNCH(c, k_fix_ties, nblk(tot_e, 256), 256, 0, vs2, ks, hid, d_candoff, d_eoff, d_r2, (uint64_t)tot_e);
+      LAUNCH(c, k_apply_perm, nblk(tot_e, 256), 256, 0, vs2, hid, d_candoff, d_eoff, d_moff0, (uint64_t)tot_e, d_idx, d_members);
+      ahf::dfree(k0); ahf::dfree(k1); ahf::dfree(v0); ahf::dfree(v1); ahf::dfree(hid);
     }
     LAUNCH(c, k_copy_unsorted, (unsigned)nhalo, 64, 0, d_candoff, d_ng, d_moff0, P.min_part, d_idx, d_members);
   }

@@ -165,14 +165,16 @@ def _check_halos(g, golden, rtol=1e-9, order=None):
             assert np.allclose(golden.prof_species(i), g.halo_profile_species(res, i), rtol=1e-8, atol=1e-300)
 
 
-@pytest.mark.parametrize("unbind", ["hybrid", "cooperative", "one_cta"])
+@pytest.mark.parametrize("unbind", ["hybrid", "cooperative", "one_cta", "sort_ties8", "sort_ties0"])
 def test_halo_pass_matches_reference(A, golden, unbind):
     """species32: the -DMULTIMASS -DGAS_PARTICLES build (weights in M_vir / potential / profiles, thermal energy in the bound test
     and Ekin, R_max and r2 from the dark matter alone).  unbind: the default hybrid (haloes up to 16384 gathered members by one CTA each,
     larger ones by the cooperative multi-block pass), everything cooperative, everything by one CTA per halo -- all three must give the
-    reference's member lists and scalars."""
+    reference's member lists and scalars.  sort_ties*: the radial sort keeps only 8 / 0 mantissa bits of r^2 in its keys, so that
+    k_fix_ties has to order long runs of equal keys (insertion and heap sort paths) -- the member ORDER must still be the reference's."""
     import os
-    env = {"hybrid": {}, "cooperative": {"AHFGPU_UNBIND_SMALL": "0"}, "one_cta": {"AHFGPU_UNBIND_V1": "1"}}[unbind]
+    env = {"hybrid": {}, "cooperative": {"AHFGPU_UNBIND_SMALL": "0"}, "one_cta": {"AHFGPU_UNBIND_V1": "1"},
+           "sort_ties8": {"AHFGPU_HALO_SORT_SKIP": "44"}, "sort_ties0": {"AHFGPU_HALO_SORT_SKIP": "52"}}[unbind]
     os.environ.update(env)
     try:
         with _ctx(A, golden) as g:
