@@ -120,6 +120,7 @@ struct StageRec { std::string name; cudaEvent_t a, b; int64_t count; };
 struct MeshEnv {
   bool generic_deposit = false, deposit_v1 = false, dom_persist = false, sparse_v1 = false, sparse_v2 = false, testnode_v1 = false, nbr_v1 = false,
        nbr_v2 = false, debug_nbr = false, debug_relink = false, level_stages = false, stages = true;
+  bool seg_v1 = false;              // AHFGPU_SEG_V1: heads kernel + scan + fill kernel instead of the fused k_seg_heads (A/B timing)
   bool dom_v2 = false, dom2_heavy = false, dom2_stats = false;     // AHFGPU_DOM_V2=1: k_deposit_dom2 (measured slower, see mesh.cu) / force its heavy form / count heavy tiles
   int  dom_variant = 0, dom_rmax = 1, dom_s = 32;
   void read()
@@ -130,6 +131,7 @@ struct MeshEnv {
     nbr_v2 = on("AHFGPU_NBR_V2"); debug_nbr = on("AHFGPU_DEBUG_NBR"); debug_relink = on("AHFGPU_DEBUG_RELINK"); level_stages = on("AHFGPU_LEVEL_STAGES");
     // AHFGPU_STAGES=0: only the timers a caller cannot do without (amr_total, deposit_dom_kernel); every event record is a marker
     // between kernels on the stream, and ~90 of them per pass cost ~0.3 ms at 256^3
+    seg_v1 = on("AHFGPU_SEG_V1");
     const char *es = getenv("AHFGPU_STAGES"); stages = !(es && es[0] == '0');
     const char *e2 = getenv("AHFGPU_DOM_V2"); dom_v2 = e2 && e2[0] == '1'; dom2_heavy = on("AHFGPU_DOM2_HEAVY"); dom2_stats = on("AHFGPU_DOM2_STATS");
     const char *e3 = getenv("AHFGPU_DOM_S"); dom_s = (e3 && atoi(e3) == 28) ? 28 : 32;

@@ -216,6 +216,26 @@ __global__ void k_tile_work4(const int32_t *__restrict__ tstart, const int *__re
   for (int q = 0; q < nc; q++) work[o + q] = make_int4(a + q * DT_CHUNK, min(DT_CHUNK, b - a - q * DT_CHUNK), (int)(tx | (ty << 10) | (tz << 20)), nc == 1 ? 1 : 0);
 }
 
+// functors of k_seg_heads (scan.cuh): deposit tiles of a refinement level, x-rows of a level's cells, z-planes of its rows
+struct TileSeg {
+  const uint64_t *keys; const uint32_t *plist; int sh; uint64_t np; uint32_t *tlist; int32_t *tstart;
+  __device__ uint64_t key(uint64_t i) const { return keys[plist[i]] >> sh; }
+  __device__ void emit(uint64_t i, int seg, int head, uint64_t k) const { if (head) { tlist[seg] = (uint32_t)k; tstart[seg] = (int32_t)i; } }
+  __device__ void end(int nseg) const { tstart[nseg] = (int32_t)np; }
+};
+struct RowSeg {
+  const uint64_t *ckey; int logL; int ncell; int32_t *crow; uint64_t *rowkey; int32_t *row_c0;
+  __device__ uint64_t key(uint64_t i) const { return ckey[i] >> logL; }
+  __device__ void emit(uint64_t i, int seg, int head, uint64_t k) const { crow[i] = seg; if (head) { rowkey[seg] = k; row_c0[seg] = (int32_t)i; } }
+  __device__ void end(int nseg) const { row_c0[nseg] = ncell; }
+};
+struct PlaneSeg {
+  const uint64_t *rowkey; int logL; int nrow; int32_t *rowplane; int32_t *plane_r0;
+  __device__ uint64_t key(uint64_t i) const { return rowkey[i] >> logL; }
+  __device__ void emit(uint64_t i, int seg, int head, uint64_t) const { rowplane[i] = seg; if (head) plane_r0[seg] = (int32_t)i; }
+  __device__ void end(int nseg) const { plane_r0[nseg] = nrow; }
+};
+
 // refinement levels: tile id (Hilbert prefix of the particle key) of every level particle, heads of equal-id runs
 __global__ void k_lvl_tile_heads(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ plist, uint64_t np, int sh, uint8_t *__restrict__ head)
 {
@@ -1867,12 +1887,18 @@ static void rows_tested_flags(ahfgpu_ctx *c, const uint64_t *rowkey, int64_t nro
                               int32_t **rowplane_out, int32_t **plane_r0_out)
 {
   DevBuf<uint8_t> head; DevBuf<int> hs, bs;
-  head.reserve(nrow); hs.reserve(nrow);
-  LAUNCH(c, k_plane_heads, nblk(nrow, 256), 256, 0, rowkey, (int)nrow, logL, head.p);
-  if (nplane < 0) nplane = exclusive_scan<uint8_t>(c, head.p, hs.p, nrow);
-  else exclusive_scan_async<uint8_t>(c, head.p, hs.p, nrow, nullptr, bs);
-  int32_t *rowplane = dalloc<int32_t>(nrow), *plane_r0 = dalloc<int32_t>(nplane + 1);
-  LAUNCH(c, k_plane_fill, nblk(nrow, 256), 256, 0, (int)nrow, head.p, hs.p, rowplane, plane_r0, (int)nplane);
+  int32_t *rowplane = nullptr, *plane_r0 = nullptr;
+  if (nplane < 0 || c->env.seg_v1) {
+    head.reserve(nrow); hs.reserve(nrow);
+    LAUNCH(c, k_plane_heads, nblk(nrow, 256), 256, 0, rowkey, (int)nrow, logL, head.p);
+    if (nplane < 0) nplane = exclusive_scan<uint8_t>(c, head.p, hs.p, nrow);
+    else exclusive_scan_async<uint8_t>(c, head.p, hs.p, nrow, nullptr, bs);
+    rowplane = dalloc<int32_t>(nrow); plane_r0 = dalloc<int32_t>(nplane + 1);
+    LAUNCH(c, k_plane_fill, nblk(nrow, 256), 256, 0, (int)nrow, head.p, hs.p, rowplane, plane_r0, (int)nplane);
+  } else {
+    rowplane = dalloc<int32_t>(nrow); plane_r0 = dalloc<int32_t>(nplane + 1);
+    seg_heads_async(c, (uint64_t)nrow, PlaneSeg{ rowkey, logL, (int)nrow, rowplane, plane_r0 }, nullptr);        // one launch: heads + scan + fill
+  }
   int32_t *rq0 = dalloc<int32_t>(nrow), *rq1 = dalloc<int32_t>(nrow), *pp0 = dalloc<int32_t>(nplane), *pp1 = dalloc<int32_t>(nplane);
   LAUNCH(c, k_row_runs, nblk(nrow, 256), 256, 0, rowkey, plane_r0, rowplane, (int)nrow, rq0, rq1);
   int32_t *pz = dalloc<int32_t>(nplane);
@@ -1893,11 +1919,14 @@ static void build_rows_planes(ahfgpu_ctx *c, Level &lv, bool with_tested)
   LV v = view(lv);
   const int nc = (int)lv.ncell;
   DevBuf<uint8_t> head; DevBuf<int> hs, bs;
-  head.reserve(nc); hs.reserve(nc);
-  LAUNCH(c, k_row_heads, nblk(nc, 256), 256, 0, lv.ckey, nc, v.logL, head.p);
-  exclusive_scan_async<uint8_t>(c, head.p, hs.p, nc, nullptr, bs);
   lv.crow = dalloc<int32_t>(nc); lv.rowkey = dalloc<uint64_t>(lv.nrow); lv.row_c0 = dalloc<int32_t>(lv.nrow + 1);
-  LAUNCH(c, k_row_fill, nblk(nc, 256), 256, 0, lv.ckey, nc, v.logL, head.p, hs.p, lv.crow, lv.rowkey, lv.row_c0, (int)lv.nrow);
+  if (c->env.seg_v1) {
+    head.reserve(nc); hs.reserve(nc);
+    LAUNCH(c, k_row_heads, nblk(nc, 256), 256, 0, lv.ckey, nc, v.logL, head.p);
+    exclusive_scan_async<uint8_t>(c, head.p, hs.p, nc, nullptr, bs);
+    LAUNCH(c, k_row_fill, nblk(nc, 256), 256, 0, lv.ckey, nc, v.logL, head.p, hs.p, lv.crow, lv.rowkey, lv.row_c0, (int)lv.nrow);
+  } else
+    seg_heads_async(c, (uint64_t)nc, RowSeg{ lv.ckey, v.logL, nc, lv.crow, lv.rowkey, lv.row_c0 }, nullptr);      // one launch: heads + scan + fill
   head.release(); hs.release(); bs.release();
   lv.row_tested = dalloc<uint8_t>(lv.nrow); lv.row_flags = dalloc<uint8_t>(lv.nrow);
   if (with_tested) rows_tested_flags(c, lv.rowkey, lv.nrow, lv.nplane, (long long)lv.L, v.logL, lv.row_tested, lv.row_flags, &lv.rowplane, &lv.plane_r0);
@@ -2108,11 +2137,20 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
     } else {
       const uint64_t np = (uint64_t)lv.npart_dep;
       const int sh = 3 * (21 - tbits);
-      head.reserve(np); hs.reserve(np);
-      LAUNCH(c, k_lvl_tile_heads, nblk(np, 256), 256, 0, c->keys, lv.plist, np, sh, head.p);
-      ntile = exclusive_scan<uint8_t>(c, head.p, hs.p, np);
-      tlist.reserve(ntile); tstart.reserve(ntile + 1);
-      LAUNCH(c, k_lvl_tile_fill, nblk(np, 256), 256, 0, c->keys, lv.plist, np, sh, head.p, hs.p, ntile, tlist.p, tstart.p);
+      if (c->env.seg_v1) {
+        head.reserve(np); hs.reserve(np);
+        LAUNCH(c, k_lvl_tile_heads, nblk(np, 256), 256, 0, c->keys, lv.plist, np, sh, head.p);
+        ntile = exclusive_scan<uint8_t>(c, head.p, hs.p, np);
+        tlist.reserve(ntile); tstart.reserve(ntile + 1);
+        LAUNCH(c, k_lvl_tile_fill, nblk(np, 256), 256, 0, c->keys, lv.plist, np, sh, head.p, hs.p, ntile, tlist.p, tstart.p);
+      } else {
+        // one launch: heads + scan + fill.  The lists are sized before the number of tiles is known: a tile with a particle holds at
+        // least one oct of the level's cells
+        const size_t cap = (size_t)std::min<uint64_t>(np, (uint64_t)lv.ncell / 8 + 1);
+        tlist.reserve(cap); tstart.reserve(cap + 1);
+        seg_heads_async(c, np, TileSeg{ c->keys, lv.plist, sh, np, tlist.p, tstart.p }, tot.p);
+        read_back(c, &ntile, tot.p, sizeof(int));
+      }
     }
     nchunk.reserve(ntile); woff.reserve(ntile);
     LAUNCH(c, k_tile_nchunk, nblk(ntile, 256), 256, 0, tstart.p, ntile, nchunk.p);

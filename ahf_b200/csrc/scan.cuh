@@ -215,6 +215,38 @@ __global__ void __launch_bounds__(SC_THREADS) k_sc_lookback(const T *in, uint64_
   sc_finish(state, ctr, nblk);
 }
 
+// Segment heads of a sorted sequence in ONE launch: flag (key differs from the predecessor's), chained scan, and the per-element /
+// per-head outputs -- instead of a heads kernel, a scan and a fill kernel (three launches, three sweeps over a flag array).
+// F: key(i), emit(i, segment index of i, is head, key), end(number of segments)
+template <typename F>
+__global__ void __launch_bounds__(SC_THREADS) k_seg_heads(uint64_t n, F f, unsigned long long *__restrict__ state, unsigned *__restrict__ ctr,
+                                                          unsigned nblk, int *__restrict__ total)
+{
+  __shared__ int s_prefix, s_agg;
+  const unsigned bid = sc_ticket(ctr);
+  const uint64_t base = (uint64_t)bid * SC_TILE + (uint64_t)threadIdx.x * SC_ITEMS;
+  uint64_t k[SC_ITEMS + 1];
+  k[0] = (base > 0 && base - 1 < n) ? f.key(base - 1) : 0ull;
+#pragma unroll
+  for (int i = 0; i < SC_ITEMS; i++) k[i + 1] = (base + i < n) ? f.key(base + i) : 0ull;
+  int v[SC_ITEMS], s = 0;
+#pragma unroll
+  for (int i = 0; i < SC_ITEMS; i++) { v[i] = (base + i < n && (base + i == 0 || k[i + 1] != k[i])) ? 1 : 0; s += v[i]; }
+  int ex = block_exclusive_scan(s);
+  if (threadIdx.x == SC_THREADS - 1) s_agg = ex + s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int prefix = sc_lookback_prefix(state, bid, s_agg, nblk, total);
+    if (threadIdx.x == 0) { s_prefix = prefix; if (bid == nblk - 1) f.end(prefix + s_agg); }
+  }
+  __syncthreads();
+  ex += s_prefix;
+#pragma unroll
+  for (int i = 0; i < SC_ITEMS; i++)
+    if (base + i < n) { ex += v[i]; f.emit(base + i, ex - 1, v[i], k[i + 1]); }
+  sc_finish(state, ctr, nblk);
+}
+
 // the zeroed look-back state of the context (grown on demand); the two counters sit in its last word
 static inline void scan_state_reserve(ahfgpu_ctx *c, unsigned nblk)
 {
@@ -243,6 +275,15 @@ template <typename T, bool NZ = false> void exclusive_scan_async(ahfgpu_ctx *c, 
   scan_state_reserve(c, nblk);
   unsigned *ctr = scan_state_ctr(c);
   LAUNCH(c, (k_sc_lookback<T, NZ>), nblk, SC_THREADS, 0, in, n, out, c->scan_state, ctr, nblk, d_total);
+}
+
+// segment heads of n > 0 sorted elements (see k_seg_heads); d_total (device, may be null) receives the number of segments
+template <typename F> void seg_heads_async(ahfgpu_ctx *c, uint64_t n, const F &f, int *d_total)
+{
+  const unsigned nblk = (unsigned)((n + SC_TILE - 1) / SC_TILE);
+  scan_state_reserve(c, nblk);
+  unsigned *ctr = scan_state_ctr(c);
+  LAUNCH(c, (k_seg_heads<F>), nblk, SC_THREADS, 0, n, f, c->scan_state, ctr, nblk, d_total);
 }
 
 // out[i] = sum_{j<i} in[j]; returns the total (synchronises the stream)
