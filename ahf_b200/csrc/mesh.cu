@@ -230,9 +230,9 @@ struct RowSeg {
   __device__ void end(int nseg) const { row_c0[nseg] = ncell; }
 };
 struct PlaneSeg {
-  const uint64_t *rowkey; int logL; int nrow; int32_t *rowplane; int32_t *plane_r0;
+  const uint64_t *rowkey; int logL; int nrow; int32_t *rowplane; int32_t *plane_r0; int32_t *pz;
   __device__ uint64_t key(uint64_t i) const { return rowkey[i] >> logL; }
-  __device__ void emit(uint64_t i, int seg, int head, uint64_t) const { rowplane[i] = seg; if (head) plane_r0[seg] = (int32_t)i; }
+  __device__ void emit(uint64_t i, int seg, int head, uint64_t k) const { rowplane[i] = seg; if (head) { plane_r0[seg] = (int32_t)i; pz[seg] = (int32_t)k; } }
   __device__ void end(int nseg) const { plane_r0[nseg] = nrow; }
 };
 
@@ -271,6 +271,26 @@ __device__ __forceinline__ void tile_add64(uint32_t saddr, unsigned long long v)
   const uint32_t hi = (uint32_t)(v >> 32) + ((old + lo < old) ? 1u : 0u);
   asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %0, 0;\n @p red.shared.add.u32 [%1], %0;\n}" ::"r"(hi), "r"(saddr + DT_HH * 4) : "memory");
 }
+
+// work list of the deposit kernels in one launch (k_scan_emit): chunks per tile, their prefix sum, the list entries
+struct TileWork {
+  const int32_t *tstart; int2 *work;
+  __device__ int  value(uint64_t t) const { return (tstart[t + 1] - tstart[t] + DT_CHUNK - 1) / DT_CHUNK; }
+  __device__ void emit(uint64_t t, int o, int nc) const { for (int q = 0; q < nc; q++) work[o + q] = make_int2((int)t, q | (nc == 1 ? 0x40000000 : 0)); }
+  __device__ void end(int) const {}
+};
+struct TileWork4 {
+  const int32_t *tstart; int tbits; int4 *work;
+  __device__ int  value(uint64_t t) const { return (tstart[t + 1] - tstart[t] + DT_CHUNK - 1) / DT_CHUNK; }
+  __device__ void emit(uint64_t t, int o, int nc) const
+  {
+    const int a = tstart[t], b = tstart[t + 1];
+    uint32_t tx, ty, tz;
+    hilbert_coords((uint64_t)t, (unsigned)tbits, tx, ty, tz);
+    for (int q = 0; q < nc; q++) work[o + q] = make_int4(a + q * DT_CHUNK, min(DT_CHUNK, b - a - q * DT_CHUNK), (int)(tx | (ty << 10) | (tz << 20)), nc == 1 ? 1 : 0);
+  }
+  __device__ void end(int) const {}
+};
 
 template <bool SPARSE>
 __global__ void __launch_bounds__(DT_THREADS, 3)
@@ -1887,7 +1907,7 @@ static void rows_tested_flags(ahfgpu_ctx *c, const uint64_t *rowkey, int64_t nro
                               int32_t **rowplane_out, int32_t **plane_r0_out)
 {
   DevBuf<uint8_t> head; DevBuf<int> hs, bs;
-  int32_t *rowplane = nullptr, *plane_r0 = nullptr;
+  int32_t *rowplane = nullptr, *plane_r0 = nullptr, *pz = nullptr;
   if (nplane < 0 || c->env.seg_v1) {
     head.reserve(nrow); hs.reserve(nrow);
     LAUNCH(c, k_plane_heads, nblk(nrow, 256), 256, 0, rowkey, (int)nrow, logL, head.p);
@@ -1896,13 +1916,12 @@ static void rows_tested_flags(ahfgpu_ctx *c, const uint64_t *rowkey, int64_t nro
     rowplane = dalloc<int32_t>(nrow); plane_r0 = dalloc<int32_t>(nplane + 1);
     LAUNCH(c, k_plane_fill, nblk(nrow, 256), 256, 0, (int)nrow, head.p, hs.p, rowplane, plane_r0, (int)nplane);
   } else {
-    rowplane = dalloc<int32_t>(nrow); plane_r0 = dalloc<int32_t>(nplane + 1);
-    seg_heads_async(c, (uint64_t)nrow, PlaneSeg{ rowkey, logL, (int)nrow, rowplane, plane_r0 }, nullptr);        // one launch: heads + scan + fill
+    rowplane = dalloc<int32_t>(nrow); plane_r0 = dalloc<int32_t>(nplane + 1); pz = dalloc<int32_t>(nplane);
+    seg_heads_async(c, (uint64_t)nrow, PlaneSeg{ rowkey, logL, (int)nrow, rowplane, plane_r0, pz }, nullptr);    // one launch: heads + scan + fill + z of the planes
   }
   int32_t *rq0 = dalloc<int32_t>(nrow), *rq1 = dalloc<int32_t>(nrow), *pp0 = dalloc<int32_t>(nplane), *pp1 = dalloc<int32_t>(nplane);
   LAUNCH(c, k_row_runs, nblk(nrow, 256), 256, 0, rowkey, plane_r0, rowplane, (int)nrow, rq0, rq1);
-  int32_t *pz = dalloc<int32_t>(nplane);
-  LAUNCH(c, k_plane_z, nblk(nplane, 128), 128, 0, rowkey, plane_r0, (int)nplane, logL, pz);
+  if (!pz) { pz = dalloc<int32_t>(nplane); LAUNCH(c, k_plane_z, nblk(nplane, 128), 128, 0, rowkey, plane_r0, (int)nplane, logL, pz); }
   LAUNCH(c, k_plane_runs, nblk(nplane, 128), 128, 0, pz, (int)nplane, pp0, pp1);
   LAUNCH(c, k_row_tested, nblk(nrow, 256), 256, 0, rowkey, plane_r0, rowplane, rq0, rq1, pp0, pp1, (int)nrow, (int)nplane, L, logL, tested, flags);
   ahf::dfree(rq0); ahf::dfree(rq1); ahf::dfree(pp0); ahf::dfree(pp1); ahf::dfree(pz);      // stream-ordered block cache: no host sync needed
@@ -2152,14 +2171,21 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
         read_back(c, &ntile, tot.p, sizeof(int));
       }
     }
-    nchunk.reserve(ntile); woff.reserve(ntile);
-    LAUNCH(c, k_tile_nchunk, nblk(ntile, 256), 256, 0, tstart.p, ntile, nchunk.p);
-    exclusive_scan_async<int>(c, nchunk.p, woff.p, ntile, tot.p, bs);
     // the work list has at most one entry per tile plus one per full chunk: launch that many CTAs, the kernels read the real
     // length from the device (no host read-back)
     const int W = ntile + (int)(lv.npart_dep / DT_CHUNK) + 1;
-    work.reserve(W);
-    LAUNCH(c, k_tile_work, nblk(ntile, 256), 256, 0, nchunk.p, woff.p, ntile, work.p);
+    const bool dom_default = tiles_dense && !dom_v1 && !(c->env.dom_v2 && c->env.dom_variant == 0);
+    const bool fused_work = !c->env.seg_v1 && (tiles_sparse || dom_default);
+    if (!fused_work) {
+      nchunk.reserve(ntile); woff.reserve(ntile);
+      LAUNCH(c, k_tile_nchunk, nblk(ntile, 256), 256, 0, tstart.p, ntile, nchunk.p);
+      exclusive_scan_async<int>(c, nchunk.p, woff.p, ntile, tot.p, bs);
+      work.reserve(W);
+      LAUNCH(c, k_tile_work, nblk(ntile, 256), 256, 0, nchunk.p, woff.p, ntile, work.p);
+    } else if (tiles_sparse) {
+      work.reserve(W);
+      scan_emit_async(c, (uint64_t)ntile, TileWork{ tstart.p, work.p }, tot.p);
+    }
     const float4 *dom_pos = c->pos4;
     DevBuf<float4> pos_c;
     if (tiles_dense && !dom_v1 && getenv("AHFGPU_DOM_CELLSORT")) {
@@ -2193,7 +2219,8 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
         const int var = c->env.dom_variant;
         const int rmax = c->env.dom_rmax;           // slices with at most this many distinct cells take the run-reduction path (measured: 1 = whole warp in one cell is best; partial-mask REDUX costs more than the conflicts it removes)
         work4.reserve(W);
-        LAUNCH(c, k_tile_work4, nblk(ntile, 256), 256, 0, tstart.p, nchunk.p, woff.p, ntile, tbits, work4.p);
+        if (fused_work) scan_emit_async(c, (uint64_t)ntile, TileWork4{ tstart.p, tbits, work4.p }, tot.p);
+        else LAUNCH(c, k_tile_work4, nblk(ntile, 256), 256, 0, tstart.p, nchunk.p, woff.p, ntile, tbits, work4.p);
         int nsm = 0;
         CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->dev));
         // AHFGPU_DOM_PERSIST=1: two persistent CTAs per SM striding over the items (measured slower: static striding loses the

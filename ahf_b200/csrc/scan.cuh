@@ -247,6 +247,32 @@ __global__ void __launch_bounds__(SC_THREADS) k_seg_heads(uint64_t n, F f, unsig
   sc_finish(state, ctr, nblk);
 }
 
+// Scan with the producer and the consumer of the values fused in: F: value(i) >= 0, emit(i, exclusive prefix, value), end(total)
+template <typename F>
+__global__ void __launch_bounds__(SC_THREADS) k_scan_emit(uint64_t n, F f, unsigned long long *__restrict__ state, unsigned *__restrict__ ctr,
+                                                          unsigned nblk, int *__restrict__ total)
+{
+  __shared__ int s_prefix, s_agg;
+  const unsigned bid = sc_ticket(ctr);
+  const uint64_t base = (uint64_t)bid * SC_TILE + (uint64_t)threadIdx.x * SC_ITEMS;
+  int v[SC_ITEMS], s = 0;
+#pragma unroll
+  for (int i = 0; i < SC_ITEMS; i++) { v[i] = (base + i < n) ? f.value(base + i) : 0; s += v[i]; }
+  int ex = block_exclusive_scan(s);
+  if (threadIdx.x == SC_THREADS - 1) s_agg = ex + s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int prefix = sc_lookback_prefix(state, bid, s_agg, nblk, total);
+    if (threadIdx.x == 0) { s_prefix = prefix; if (bid == nblk - 1) f.end(prefix + s_agg); }
+  }
+  __syncthreads();
+  ex += s_prefix;
+#pragma unroll
+  for (int i = 0; i < SC_ITEMS; i++)
+    if (base + i < n) { f.emit(base + i, ex, v[i]); ex += v[i]; }
+  sc_finish(state, ctr, nblk);
+}
+
 // the zeroed look-back state of the context (grown on demand); the two counters sit in its last word
 static inline void scan_state_reserve(ahfgpu_ctx *c, unsigned nblk)
 {
@@ -284,6 +310,14 @@ template <typename F> void seg_heads_async(ahfgpu_ctx *c, uint64_t n, const F &f
   scan_state_reserve(c, nblk);
   unsigned *ctr = scan_state_ctr(c);
   LAUNCH(c, (k_seg_heads<F>), nblk, SC_THREADS, 0, n, f, c->scan_state, ctr, nblk, d_total);
+}
+
+template <typename F> void scan_emit_async(ahfgpu_ctx *c, uint64_t n, const F &f, int *d_total)
+{
+  const unsigned nblk = (unsigned)((n + SC_TILE - 1) / SC_TILE);
+  scan_state_reserve(c, nblk);
+  unsigned *ctr = scan_state_ctr(c);
+  LAUNCH(c, (k_scan_emit<F>), nblk, SC_THREADS, 0, n, f, c->scan_state, ctr, nblk, d_total);
 }
 
 // out[i] = sum_{j<i} in[j]; returns the total (synchronises the stream)
