@@ -1991,11 +1991,17 @@ __global__ void k_p_vmax(const int64_t *__restrict__ moff0, PG G, const int32_t 
   S[54] = calc_cNFW(V_max, S[10] / S[11]);
 }
 
-__global__ void k_members_out(const int64_t *__restrict__ moff0, const int64_t *__restrict__ npart, const int64_t *__restrict__ moff, const uint32_t *__restrict__ members,
+// final member lists: one thread per member of the output (its halo by binary search in moff; a CTA per halo waited for the largest halo)
+__global__ void k_members_out(const int64_t *__restrict__ moff0, const int64_t *__restrict__ moff, int64_t nhalo, int64_t total, const uint32_t *__restrict__ members,
                               const uint32_t *__restrict__ gid, int64_t *__restrict__ out)
 {
-  const int64_t h = blockIdx.x, np = npart[h];
-  for (int64_t i = threadIdx.x; i < np; i += blockDim.x) { const uint32_t m = members[moff0[h] + i]; out[moff[h] + i] = (int64_t)(gid ? gid[m] : m); }
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int64_t lo = 0, hi = nhalo;                                  // first h with moff[h] > i, minus one
+  while (lo < hi) { const int64_t mid = lo + ((hi - lo) >> 1); if (moff[mid] <= i) lo = mid + 1; else hi = mid; }
+  const int64_t h = lo - 1;
+  const uint32_t m = members[moff0[h] + (i - moff[h])];
+  out[i] = (int64_t)(gid ? gid[m] : m);
 }
 
 // Halo-local particle copies.  After the radial sort the members of a halo are in radius order, i.e. scattered over the key-sorted
@@ -2410,7 +2416,7 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
     else
       profiles_cooperative(c, nhalo, P, d_ctr, d_moff0, d_members, tot_g, d_np, h_np);
     // a slab of a distributed box reports GLOBAL INPUT INDICES (the resident `order` array), not offsets into its own sorted set
-    LAUNCH(c, k_members_out, (unsigned)nhalo, 256, 0, d_moff0, d_np, c->h_moff, d_members, d_gid ? d_gid : (c->slab ? c->order : (uint32_t *)nullptr), c->h_members);
+    if (tot_m > 0) LAUNCH(c, k_members_out, nblk(tot_m, 256), 256, 0, d_moff0, c->h_moff, nhalo, (int64_t)tot_m, d_members, d_gid ? d_gid : (c->slab ? c->order : (uint32_t *)nullptr), c->h_members);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
   }
   ahf::dfree(d_ctr); ahf::dfree(d_rad); ahf::dfree(d_seed); ahf::dfree(d_rlo); ahf::dfree(d_rhi); ahf::dfree(d_cand); ahf::dfree(d_candoff); ahf::dfree(d_ng);
