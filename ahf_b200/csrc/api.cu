@@ -74,7 +74,7 @@ void Level::free_all()
   ahf::dfree(ckey); ahf::dfree(xbreak); ahf::dfree(dens); ahf::dfree(interior); ahf::dfree(tn); ahf::dfree(mark); ahf::dfree(nbr);
   ahf::dfree(crow); ahf::dfree(count); ahf::dfree(hkey); ahf::dfree(hval); ahf::dfree(rowkey); ahf::dfree(row_c0); ahf::dfree(row_tested); ahf::dfree(row_flags);
   ahf::dfree(plane_r0); ahf::dfree(rowplane); ahf::dfree(plist); ahf::dfree(pcell); ahf::dfree(lpos);
-  ahf::dfree(parent); ahf::dfree(cidx); ahf::dfree(cbase); ahf::dfree(cpar); ahf::dfree(pstat);
+  ahf::dfree(parent); ahf::dfree(cidx); ahf::dfree(cbase); ahf::dfree(cpar); ahf::dfree(pstat); ahf::dfree(tlist); ahf::dfree(tstart);
   *this = Level();
 }
 }  // namespace ahf

@@ -66,6 +66,7 @@ template <typename T> struct DevBuf {
     cap = n ? n : 1;
   }
   void release() { if (p) ahf::dfree(p); p = nullptr; cap = 0; }
+  void adopt(T *q) { release(); p = q; cap = q ? 1 : 0; }      // take over a block of the cache allocator (released like the others)
 };
 
 // one refinement level on the device (see DESIGN.md "data layout")
@@ -105,6 +106,8 @@ struct Level {
   uint32_t *plist = nullptr;    // [npart_dep]   (nullptr on the domain level = all particles)
   int32_t  *pcell = nullptr;    // [npart_dep]
   float4   *lpos = nullptr;     // [npart_dep] positions of the level's particles, contiguous (refinement levels)
+  // deposit tiles of the level's particle list, found right behind the relink that made the list (one host read-back for both counts)
+  uint32_t *tlist = nullptr; int32_t *tstart = nullptr; int ntile = -1;
   double   *pstat = nullptr;    // [pstat_n][18] RefCentre table of the level (ahfgpu_amr_patch_stats), kept until the hierarchy is rebuilt
   int64_t   pstat_n = -1;
   void free_all();
@@ -120,6 +123,7 @@ struct StageRec { std::string name; cudaEvent_t a, b; int64_t count; };
 struct MeshEnv {
   bool generic_deposit = false, deposit_v1 = false, dom_persist = false, sparse_v1 = false, sparse_v2 = false, testnode_v1 = false, nbr_v1 = false,
        nbr_v2 = false, debug_nbr = false, debug_relink = false, level_stages = false, stages = true;
+  bool relink_v1 = false;           // AHFGPU_RELINK_V1: scan + compaction kernel instead of the fused k_compact_fused, tiles found by the deposit (A/B timing)
   bool seg_v1 = false;              // AHFGPU_SEG_V1: heads kernel + scan + fill kernel instead of the fused k_seg_heads (A/B timing)
   bool dom_v2 = false, dom2_heavy = false, dom2_stats = false;     // AHFGPU_DOM_V2=1: k_deposit_dom2 (measured slower, see mesh.cu) / force its heavy form / count heavy tiles
   int  dom_variant = 0, dom_rmax = 1, dom_s = 32;
@@ -131,7 +135,7 @@ struct MeshEnv {
     nbr_v2 = on("AHFGPU_NBR_V2"); debug_nbr = on("AHFGPU_DEBUG_NBR"); debug_relink = on("AHFGPU_DEBUG_RELINK"); level_stages = on("AHFGPU_LEVEL_STAGES");
     // AHFGPU_STAGES=0: only the timers a caller cannot do without (amr_total, deposit_dom_kernel); every event record is a marker
     // between kernels on the stream, and ~90 of them per pass cost ~0.3 ms at 256^3
-    seg_v1 = on("AHFGPU_SEG_V1");
+    seg_v1 = on("AHFGPU_SEG_V1"); relink_v1 = on("AHFGPU_RELINK_V1");
     const char *es = getenv("AHFGPU_STAGES"); stages = !(es && es[0] == '0');
     const char *e2 = getenv("AHFGPU_DOM_V2"); dom_v2 = e2 && e2[0] == '1'; dom2_heavy = on("AHFGPU_DOM2_HEAVY"); dom2_stats = on("AHFGPU_DOM2_STATS");
     const char *e3 = getenv("AHFGPU_DOM_S"); dom_s = (e3 && atoi(e3) == 28) ? 28 : 32;

@@ -220,9 +220,10 @@ __global__ void __launch_bounds__(SC_THREADS) k_sc_lookback(const T *in, uint64_
 // F: key(i), emit(i, segment index of i, is head, key), end(number of segments)
 template <typename F>
 __global__ void __launch_bounds__(SC_THREADS) k_seg_heads(uint64_t n, F f, unsigned long long *__restrict__ state, unsigned *__restrict__ ctr,
-                                                          unsigned nblk, int *__restrict__ total)
+                                                          unsigned nblk, int *__restrict__ total, const int *__restrict__ n_dev)
 {
   __shared__ int s_prefix, s_agg;
+  if (n_dev) n = (uint64_t)*n_dev;            // element count still on the device (the grid covers an upper bound; empty tiles pass the prefix on)
   const unsigned bid = sc_ticket(ctr);
   const uint64_t base = (uint64_t)bid * SC_TILE + (uint64_t)threadIdx.x * SC_ITEMS;
   uint64_t k[SC_ITEMS + 1];
@@ -304,12 +305,13 @@ template <typename T, bool NZ = false> void exclusive_scan_async(ahfgpu_ctx *c, 
 }
 
 // segment heads of n > 0 sorted elements (see k_seg_heads); d_total (device, may be null) receives the number of segments
-template <typename F> void seg_heads_async(ahfgpu_ctx *c, uint64_t n, const F &f, int *d_total)
+// n_dev (device, may be null): the real element count, n then being an upper bound known to the host
+template <typename F> void seg_heads_async(ahfgpu_ctx *c, uint64_t n, const F &f, int *d_total, const int *n_dev = nullptr)
 {
   const unsigned nblk = (unsigned)((n + SC_TILE - 1) / SC_TILE);
   scan_state_reserve(c, nblk);
   unsigned *ctr = scan_state_ctr(c);
-  LAUNCH(c, (k_seg_heads<F>), nblk, SC_THREADS, 0, n, f, c->scan_state, ctr, nblk, d_total);
+  LAUNCH(c, (k_seg_heads<F>), nblk, SC_THREADS, 0, n, f, c->scan_state, ctr, nblk, d_total, n_dev);
 }
 
 template <typename F> void scan_emit_async(ahfgpu_ctx *c, uint64_t n, const F &f, int *d_total)
