@@ -1716,33 +1716,70 @@ __global__ void __launch_bounds__(HB, 2) k_p_main(const float4 *__restrict__ pos
       if (Epart < best_e) { best_e = Epart; best_j = j; }
     }
   }
-  for (int b = blo; b <= bhi; b++) {
-    double s[NACC];
+  // Per-bin sums of the tile.  The members are radius sorted and a thread owns HI consecutive ones, so the bins of a WARP form one range
+  // [wlo, whi] and only its first and last bin can also hold members of other warps: a warp reduces its own bins alone (no block-wide
+  // barrier per bin -- a one-tile halo of 500 members has a dozen bins, and 2e4 such haloes spent 3 ms here), writes the bins strictly
+  // inside its range straight to the partial table and leaves the two edge bins in shared memory, where they are added up over the warps
+  // in warp order.  Per-thread terms, the butterfly inside a warp and the order over the warps are those of the block-wide reduction
+  // this replaces (other warps contributed exact zeros), so the sums are the same bit for bit.
+  {
+    __shared__ double epart[HB / 32][2][NACC];
+    __shared__ int    s_wlo[HB / 32], s_whi[HB / 32];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    int mylo = 0x7fffffff, myhi = -1;
 #pragma unroll
-    for (int q = 0; q < NACC; q++) s[q] = 0.0;
+    for (int i = 0; i < HI; i++) if (T.act[i]) { mylo = min(mylo, bin[i]); myhi = max(myhi, bin[i]); }
+    const int wlo = __reduce_min_sync(0xffffffffu, mylo), whi = __reduce_max_sync(0xffffffffu, myhi);     // empty warp: wlo > whi
+    if (lane == 0) { s_wlo[wrp] = wlo; s_whi[wrp] = whi; }
+    double *pdst = G.partial + (size_t)G.slot_off[blockIdx.x] * NACC;
+    for (int b = wlo; b <= whi; b++) {
+      double s[NACC];
 #pragma unroll
-    for (int i = 0; i < HI; i++) {
-      if (T.act[i] && bin[i] == b) {
-        const double w = T.w[i];
-        s[0] += w * (c[0] + T.d[i][0]); s[1] += w * (c[1] + T.d[i][1]); s[2] += w * (c[2] + T.d[i][2]);
-        s[3] += w * T.d[i][0] * T.d[i][0]; s[4] += w * T.d[i][1] * T.d[i][1]; s[5] += w * T.d[i][2] * T.d[i][2];
-        s[6] += w * T.d[i][0] * T.d[i][1]; s[7] += w * T.d[i][0] * T.d[i][2]; s[8] += w * T.d[i][1] * T.d[i][2];
-        s[9] += Lm[i][0]; s[10] += Lm[i][1]; s[11] += Lm[i][2];
-        s[12] += Tp[i]; s[13] += Up[i];
-        if (has_w) { if (fabs(w - 1.0) < ZERO_F) s[14] += w; else if (w > 1.0) s[15] += w; } else s[14] += w;
-        s[16] += w; s[17] += 1.0;
-        if (has_u) {
-          if (uu[i] >= 0.0) { s[18] += w; s[20] += w * uu[i] / u_fac; }          // gas (:4424-4474)
-          if (fabs(uu[i] + 4.0) < ZERO_F) s[19] += w;                            // stars (:4484)
+      for (int q = 0; q < NACC; q++) s[q] = 0.0;
+#pragma unroll
+      for (int i = 0; i < HI; i++) {
+        if (T.act[i] && bin[i] == b) {
+          const double w = T.w[i];
+          s[0] += w * (c[0] + T.d[i][0]); s[1] += w * (c[1] + T.d[i][1]); s[2] += w * (c[2] + T.d[i][2]);
+          s[3] += w * T.d[i][0] * T.d[i][0]; s[4] += w * T.d[i][1] * T.d[i][1]; s[5] += w * T.d[i][2] * T.d[i][2];
+          s[6] += w * T.d[i][0] * T.d[i][1]; s[7] += w * T.d[i][0] * T.d[i][2]; s[8] += w * T.d[i][1] * T.d[i][2];
+          s[9] += Lm[i][0]; s[10] += Lm[i][1]; s[11] += Lm[i][2];
+          s[12] += Tp[i]; s[13] += Up[i];
+          if (has_w) { if (fabs(w - 1.0) < ZERO_F) s[14] += w; else if (w > 1.0) s[15] += w; } else s[14] += w;
+          s[16] += w; s[17] += 1.0;
+          if (has_u) {
+            if (uu[i] >= 0.0) { s[18] += w; s[20] += w * uu[i] / u_fac; }          // gas (:4424-4474)
+            if (fabs(uu[i] + 4.0) < ZERO_F) s[19] += w;                            // stars (:4484)
+          }
         }
       }
-    }
-    block_sum_n<NACC>(s, smd);
-    if (threadIdx.x == 0) {
-      double *dst = G.partial + ((size_t)G.slot_off[blockIdx.x] + (b - blo)) * NACC;
 #pragma unroll
-      for (int q = 0; q < NACC; q++) dst[q] = s[q];
+      for (int q = 0; q < NACC; q++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+      }
+      if (lane == 0) {
+        double *dst = (b == wlo) ? epart[wrp][0] : (b == whi) ? epart[wrp][1] : pdst + (size_t)(b - blo) * NACC;
+#pragma unroll
+        for (int q = 0; q < NACC; q++) dst[q] = s[q];
+      }
     }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < (bhi - blo + 1) * NACC; idx += HB) {
+      const int b = blo + idx / NACC, q = idx - (idx / NACC) * NACC;
+      double t = 0.0;
+      bool inside = false;
+#pragma unroll
+      for (int w = 0; w < HB / 32; w++) {
+        const int lo = s_wlo[w], hi = s_whi[w];
+        if (lo > hi) continue;
+        if (b == lo) t += epart[w][0][q];
+        else if (b == hi) t += epart[w][1][q];
+        else if (b > lo && b < hi) inside = true;
+      }
+      if (!inside) pdst[idx] = t;                    // edge bins: the warps in order; bins without a member: zeros
+    }
+    __syncthreads();
   }
   // GAS_PARTICLES build: gas_only / stars_only sums of the tile (:4420-4530) and the most bound member of each species
   if (has_u) {
@@ -1807,7 +1844,10 @@ __global__ void __launch_bounds__(HB, 2) k_p_main(const float4 *__restrict__ pos
   }
 }
 
-__global__ void __launch_bounds__(HB) k_p_finish(const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, const double *__restrict__ centre,
+// NT threads: 256 when a few large haloes have thousands of tiles to sum, 64 when there are thousands of small haloes -- the tail of a halo
+// (prof_tail: one thread) and its bins (one thread each) leave a large CTA idle, and 98 registers x 256 threads allow two CTAs per SM
+template <int NT>
+__global__ void __launch_bounds__(NT) k_p_finish(const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, const double *__restrict__ centre,
                                                  const int64_t *__restrict__ moff0, const uint32_t *__restrict__ members, PG G, const int32_t *__restrict__ act,
                                                  double *__restrict__ scal, const int64_t *__restrict__ poff, double *__restrict__ prof, HP P)
 {
@@ -1819,7 +1859,7 @@ __global__ void __launch_bounds__(HB) k_p_finish(const float4 *__restrict__ pos4
   // tiles touching bin b form one contiguous range (first and last bin of a tile both grow with the tile number): two binary
   // searches per bin, then the partials are summed in tile order -- a 10^7-particle host has 10^4 tiles
   __shared__ int s_tlo[MAXBINS], s_thi[MAXBINS];
-  for (int b = threadIdx.x; b < nbins; b += HB) {
+  for (int b = threadIdx.x; b < nbins; b += NT) {
     int lo = t0, hi = t0 + nt;                                        // first tile whose last bin >= b
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (G.tile_blo[mid] + G.tile_ns[mid] - 1 < b) lo = mid + 1; else hi = mid; }
     s_tlo[b] = lo;
@@ -1829,13 +1869,13 @@ __global__ void __launch_bounds__(HB) k_p_finish(const float4 *__restrict__ pos4
     s_thi[b] = l2;
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < nbins * NACC; idx += HB) {       // (bin, component)
+  for (int idx = threadIdx.x; idx < nbins * NACC; idx += NT) {       // (bin, component)
     const int b = idx / NACC, q = idx - b * NACC;
     double a = 0.0;
     for (int t = s_tlo[b]; t < s_thi[b]; t++) a += G.partial[((size_t)G.slot_off[t] + (b - G.tile_blo[t])) * NACC + q];
     acc[b][q] = a;
   }
-  for (int i = threadIdx.x; i < nbins; i += HB) {
+  for (int i = threadIdx.x; i < nbins; i += NT) {
     edge[i] = G.edge[(size_t)h * MAXBINS + i]; vesc_bin[i] = G.vesc_bin[(size_t)h * MAXBINS + i];
     for (int q = 0; q < 3; q++) Vc_bin[i][q] = G.Vc_bin[((size_t)h * MAXBINS + i) * 3 + q];
   }
@@ -1844,14 +1884,14 @@ __global__ void __launch_bounds__(HB) k_p_finish(const float4 *__restrict__ pos4
   // 0.4 ms per halo; with 2e4 haloes that kernel alone took 6.6 ms.  Same arithmetic per bin (prof_bin), so the numbers are those of
   // the serial form: cumulative sums in place (one thread per component, bins in order), then one thread per bin, then the tail.
   __shared__ double raw17[MAXBINS], raw20[MAXBINS];
-  for (int b = threadIdx.x; b < nbins; b += HB) { raw17[b] = acc[b][17]; raw20[b] = acc[b][20]; }
+  for (int b = threadIdx.x; b < nbins; b += NT) { raw17[b] = acc[b][17]; raw20[b] = acc[b][20]; }
   __syncthreads();
   if (threadIdx.x < NACC) { double run = 0.0; for (int b = 0; b < nbins; b++) { run += acc[b][threadIdx.x]; acc[b][threadIdx.x] = run; } }
   __syncthreads();
   {
     const double F43 = 4. * PI_ / 3.;
     double *pr = prof + poff[h] * AHFGPU_NPROFCOL, *prsp = G.prof_species ? G.prof_species + poff[h] * 3 : nullptr;
-    for (int b = threadIdx.x; b < nbins; b += HB) {
+    for (int b = threadIdx.x; b < nbins; b += NT) {
       double vesc_run = 0.0;                                            // escape velocity of the last non-empty bin up to b
       for (int q = b; q >= 0; q--) if (raw17[q] > 0.0) { vesc_run = vesc_bin[q]; break; }
       const double M_prev = b ? acc[b - 1][16] : 0.0, V_prev = b ? F43 * (edge[b - 1] * edge[b - 1] * edge[b - 1]) : 0.0;
@@ -2228,7 +2268,8 @@ static void profiles_cooperative(ahfgpu_ctx *c, int64_t nhalo, const HP &P, cons
   const int nslot = exclusive_scan<int32_t>(c, G.tile_ns, d_slot, (uint64_t)nt);
   G.partial = dalloc<double>((size_t)nslot * NACC);
   LAUNCH(c, k_p_main, (unsigned)nt, HB, 0, c->pos4, c->mom4, has_w, has_u, d_ctr, d_moff0, d_members, G, d_tiles, d_tc4, d_tc1, c->h_scal, P);
-  LAUNCH(c, k_p_finish, (unsigned)nact, HB, 0, c->pos4, c->mom4, d_ctr, d_moff0, d_members, G, d_act, c->h_scal, c->h_poff, c->h_prof, P);
+  if (nact >= 2048 && nt < 4 * nact) LAUNCH(c, k_p_finish<64>, (unsigned)nact, 64, 0, c->pos4, c->mom4, d_ctr, d_moff0, d_members, G, d_act, c->h_scal, c->h_poff, c->h_prof, P);
+  else LAUNCH(c, k_p_finish<HB>, (unsigned)nact, HB, 0, c->pos4, c->mom4, d_ctr, d_moff0, d_members, G, d_act, c->h_scal, c->h_poff, c->h_prof, P);
   LAUNCH(c, k_p_smooth, (unsigned)nt, HB, 0, d_moff0, G, d_tiles, G.y0a, G.y0b, G.y1a, G.y1b, 1);
   LAUNCH(c, k_p_smooth, (unsigned)nt, HB, 0, d_moff0, G, d_tiles, G.y0b, G.y0a, G.y1a, G.y1b, 0);
   LAUNCH(c, k_p_smooth, (unsigned)nt, HB, 0, d_moff0, G, d_tiles, G.y0a, G.y0b, G.y1a, G.y1b, 0);

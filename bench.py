@@ -37,26 +37,34 @@ UNIT = "particles/s"
 
 
 def ncu_traffic_bytes(n1d: int):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the domain deposit kernel, from the committed
-    `ncu --set full` summary (profiles/); only valid for the configuration that was profiled (256^3)."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the domain deposit kernel (k_deposit_dom), from the newest committed
+    `ncu --set full` summary under profiles/ that holds a launch of it; only valid for the configuration that was profiled (256^3)."""
     if n1d != 256:
         return None
     import glob, re
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_deposit_*_ncu_full.txt")))
-    if not files:
-        return None
-    rd = wr = None
-    for line in open(files[-1]):
-        if line.startswith("## launch id") and rd is not None:
-            break
-        m = re.match(r"\s+dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", line)
-        if m:
-            v = float(m.group(2)) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[m.group(3)]
-            if m.group(1) == "read":
-                rd = v
-            else:
-                wr = v
-    return None if rd is None or wr is None else rd + wr
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full.txt")), reverse=True)         # r3... before r2... before r1...: newest round first
+    for fn in files:
+        inside = False
+        rd = wr = None
+        for line in open(fn):
+            if line.startswith("## launch id"):
+                if inside and rd is not None and wr is not None:
+                    return rd + wr
+                inside = re.search(r"k_deposit_dom\s*[<(]", line) is not None
+                rd = wr = None
+                continue
+            if not inside:
+                continue
+            m = re.match(r"\s+dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", line)
+            if m:
+                v = float(m.group(2)) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[m.group(3)]
+                if m.group(1) == "read":
+                    rd = v
+                else:
+                    wr = v
+        if inside and rd is not None and wr is not None:
+            return rd + wr
+    return None
 
 
 _JSON_OUT = None

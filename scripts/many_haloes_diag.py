@@ -27,8 +27,12 @@ with ahf.AhfGpu(par) as g:
     t5 = time.perf_counter()
     print("patch tables total ms %.1f, host tree ms %.1f, haloes %d" % ((t4 - t0) * 1e3, (t5 - t4) * 1e3, len(out["npart"])), flush=True)
     c, r, s = np.ascontiguousarray(out["pos"]), np.ascontiguousarray(out["gather_rad"]), np.ascontiguousarray(out["npart"], np.int64)
-    for it in range(3):
-        g.synchronize(); t0 = time.perf_counter()
-        g.construct_halos(c, r, s, fetch=False)
-        g.synchronize(); t1 = time.perf_counter()
-    print("halo pass wall ms %.2f" % ((t1 - t0) * 1e3), {k: round(g.stage_ms(k), 3) for k in ("halo_gather", "halo_sort", "halo_localize", "halo_unbind", "halo_profiles")}, flush=True)
+    for mode, env in (("default", {}), ("profiles one CTA per halo", {"AHFGPU_PROFILES_V1": "1"}), ("default + per-launch events", {"AHFGPU_KTIME": "1"})):
+        os.environ.update(env)
+        for it in range(3):
+            g.synchronize(); t0 = time.perf_counter()
+            g.construct_halos(c, r, s, fetch=False)
+            g.synchronize(); t1 = time.perf_counter()
+        for k in env:
+            os.environ.pop(k)
+        print(mode, "halo pass wall ms %.2f" % ((t1 - t0) * 1e3), {k: round(g.stage_ms(k), 3) for k in ("halo_gather", "halo_sort", "halo_localize", "halo_unbind", "halo_profiles")}, flush=True)
