@@ -458,7 +458,10 @@ __device__ RvirOut rvir_cut(const float4 *__restrict__ pos4, const uint32_t *__r
 // ------------------------------------------------------------------------------------------------
 // stage kernel 1: virial cut, unbinding, virial cut.  One CTA per halo; the member list is compacted in place.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(HB) k_halo_unbind(const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, int has_u,
+// MB: CTAs per SM the register budget is cut for -- 1 (255 registers) when a few hundred haloes wait for the longest of them, 2 (128
+// registers, some spills) when thousands of small haloes queue for the SMs (2e4 haloes: 2.5 -> 1.8 ms)
+template <int MB>
+__global__ void __launch_bounds__(HB, MB) k_halo_unbind(const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, int has_u,
                                                     const double *__restrict__ centre, const int64_t *__restrict__ moff0, const int64_t *__restrict__ ngather,
                                                     uint32_t *__restrict__ members, HP P, double *__restrict__ scal, int64_t *__restrict__ npart_out,
                                                     int64_t *__restrict__ iter_work, const int32_t *__restrict__ sel)
@@ -1605,7 +1608,8 @@ __global__ void __launch_bounds__(HB) k_p_phi(const float4 *__restrict__ pos4, i
   if (threadIdx.x == 0) tt[blockIdx.x] = loc;
 }
 
-__global__ void __launch_bounds__(HB, 2) k_p_main(const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, int has_w, int has_u, const double *__restrict__ centre,
+template <int MB>      // CTAs per SM the register budget is cut for (3 for thousands of one-tile haloes)
+__global__ void __launch_bounds__(HB, MB) k_p_main(const float4 *__restrict__ pos4, const float4 *__restrict__ mom4, int has_w, int has_u, const double *__restrict__ centre,
                                                const int64_t *__restrict__ moff0, const uint32_t *__restrict__ members, PG G, const int2 *__restrict__ tiles,
                                                const double *__restrict__ tc4, const double *__restrict__ tcphi, const double *__restrict__ scal, HP P)
 {
@@ -2267,7 +2271,8 @@ static void profiles_cooperative(ahfgpu_ctx *c, int64_t nhalo, const HP &P, cons
   LAUNCH(c, k_g_scan<1>, (unsigned)nact, HB, 0, d_act, d_tile0, d_ntile, d_tt1, d_tc1, d_ht1);
   const int nslot = exclusive_scan<int32_t>(c, G.tile_ns, d_slot, (uint64_t)nt);
   G.partial = dalloc<double>((size_t)nslot * NACC);
-  LAUNCH(c, k_p_main, (unsigned)nt, HB, 0, c->pos4, c->mom4, has_w, has_u, d_ctr, d_moff0, d_members, G, d_tiles, d_tc4, d_tc1, c->h_scal, P);
+  if (nt >= 4096 && nt < 2 * nact && !getenv("AHFGPU_PMAIN_MB2")) LAUNCH(c, k_p_main<3>, (unsigned)nt, HB, 0, c->pos4, c->mom4, has_w, has_u, d_ctr, d_moff0, d_members, G, d_tiles, d_tc4, d_tc1, c->h_scal, P);
+  else LAUNCH(c, k_p_main<2>, (unsigned)nt, HB, 0, c->pos4, c->mom4, has_w, has_u, d_ctr, d_moff0, d_members, G, d_tiles, d_tc4, d_tc1, c->h_scal, P);
   if (nact >= 2048 && nt < 4 * nact) LAUNCH(c, k_p_finish<64>, (unsigned)nact, 64, 0, c->pos4, c->mom4, d_ctr, d_moff0, d_members, G, d_act, c->h_scal, c->h_poff, c->h_prof, P);
   else LAUNCH(c, k_p_finish<HB>, (unsigned)nact, HB, 0, c->pos4, c->mom4, d_ctr, d_moff0, d_members, G, d_act, c->h_scal, c->h_poff, c->h_prof, P);
   LAUNCH(c, k_p_smooth, (unsigned)nt, HB, 0, d_moff0, G, d_tiles, G.y0a, G.y0b, G.y1a, G.y1b, 1);
@@ -2414,7 +2419,8 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
       int32_t *d_sel = dalloc<int32_t>(small.size());
       CUDA_CHECK(cudaMemcpyAsync(d_sel, small.data(), sizeof(int32_t) * small.size(), cudaMemcpyHostToDevice, c->stream));
       CUDA_CHECK(cudaMemsetAsync(d_work, 0, sizeof(int64_t) * nhalo, c->stream));
-      LAUNCH(c, k_halo_unbind, (unsigned)small.size(), HB, 0, c->pos4, c->mom4, c->has_u ? 1 : 0, d_ctr, d_moff0, d_ng, d_members, P, c->h_scal, d_np, d_work, d_sel);
+      if (small.size() > 1024) LAUNCH(c, k_halo_unbind<2>, (unsigned)small.size(), HB, 0, c->pos4, c->mom4, c->has_u ? 1 : 0, d_ctr, d_moff0, d_ng, d_members, P, c->h_scal, d_np, d_work, d_sel);
+      else LAUNCH(c, k_halo_unbind<1>, (unsigned)small.size(), HB, 0, c->pos4, c->mom4, c->has_u ? 1 : 0, d_ctr, d_moff0, d_ng, d_members, P, c->h_scal, d_np, d_work, d_sel);
       std::vector<int64_t> h_work(nhalo);
       CUDA_CHECK(cudaMemcpyAsync(h_np.data(), d_np, sizeof(int64_t) * nhalo, cudaMemcpyDeviceToHost, c->stream));
       CUDA_CHECK(cudaMemcpyAsync(h_work.data(), d_work, sizeof(int64_t) * nhalo, cudaMemcpyDeviceToHost, c->stream));
