@@ -2229,9 +2229,10 @@ static void deposit_level(ahfgpu_ctx *c, Level &lv)
         tlist.reserve(ntile); tstart.reserve(ntile + 1);
         LAUNCH(c, k_lvl_tile_fill, nblk(np, 256), 256, 0, c->keys, lv.plist, np, sh, head.p, hs.p, ntile, tlist.p, tstart.p);
       } else {
-        // one launch: heads + scan + fill.  The lists are sized before the number of tiles is known: a tile with a particle holds at
-        // least one oct of the level's cells
-        const size_t cap = (size_t)std::min<uint64_t>(np, (uint64_t)lv.ncell / 8 + 1);
+        // one launch: heads + scan + fill.  The lists are sized before the number of tiles is known: a tile is named by the particle's
+        // KEY, the particle's cell lies in it or -- a particle exactly on a cell face, relink's face bits -- in one of the 7 tiles towards
+        // lower coordinates, and a tile with a cell holds a whole oct: at most 8 * ncell / 8 tiles
+        const size_t cap = (size_t)std::min<uint64_t>(np, (uint64_t)lv.ncell + 1);
         tlist.reserve(cap); tstart.reserve(cap + 1);
         seg_heads_async(c, np, TileSeg{ c->keys, lv.plist, sh, np, tlist.p, tstart.p, nullptr }, tot.p);
         read_back(c, &ntile, tot.p, sizeof(int));
@@ -2538,7 +2539,7 @@ void amr_build(ahfgpu_ctx *c)
           const int tbits = view(fin).logL - 4;
           const bool want_tiles = tbits <= 20 && tbits >= 0 && !c->env.generic_deposit && !c->env.seg_v1;
           if (want_tiles) {
-            const size_t cap = (size_t)std::min<uint64_t>(np, (uint64_t)fin.ncell / 8 + 1);
+            const size_t cap = (size_t)std::min<uint64_t>(np, (uint64_t)fin.ncell + 1);        // see deposit_level
             fin.tlist = dalloc<uint32_t>(cap); fin.tstart = dalloc<int32_t>(cap + 1);
             seg_heads_async(c, np, TileSeg{ c->keys, fin.plist, 3 * (21 - tbits), np, fin.tlist, fin.tstart, cnt.p }, cnt.p + 1, cnt.p);
           }
