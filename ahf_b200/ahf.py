@@ -211,6 +211,7 @@ def lib():
         L.ahfgpu_amr_level_owned.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.ahfgpu_particle_ids.argtypes = [C.c_void_p, C.c_void_p]
         L.ahfgpu_particle_ids_async.argtypes = [C.c_void_p, C.c_void_p]
+        L.ahfgpu_halo_members_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.ahfgpu_ingest_gadget.argtypes = [C.c_void_p, C.c_char_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
         L.ahfgpu_particles_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ahfgpu_input_peek.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]

@@ -150,7 +150,7 @@ void ahfgpu_ctx::free_halos()
   ahf::dfree(h_scal); ahf::dfree(h_moff); ahf::dfree(h_members); ahf::dfree(h_poff); ahf::dfree(h_prof);
   ahf::dfree(h_species); ahf::dfree(h_prof_species); h_species = nullptr; h_prof_species = nullptr;
   h_scal = nullptr; h_moff = nullptr; h_members = nullptr; h_poff = nullptr; h_prof = nullptr;
-  nhalo = 0; h_total_members = h_total_bins = 0;
+  nhalo = 0; h_total_members = h_total_bins = 0; early_sent = false;
 }
 
 #define API_BEGIN try {
@@ -268,6 +268,7 @@ int ahfgpu_finalize(ahfgpu_ctx *c)
   for (auto &e : c->event_pool) cudaEventDestroy(e);
   c->event_pool.clear();
   for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+  if (c->ev_members) { cudaEventSynchronize(c->ev_members); cudaEventDestroy(c->ev_members); }
   {                                                   // blocks cached for this context's stream go back to the driver pool
     std::lock_guard<std::mutex> lk(g_cache_mu);
     for (auto it = g_cache_free.begin(); it != g_cache_free.end();) {
@@ -601,6 +602,17 @@ int ahfgpu_construct_halos(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, 
   API_END
 }
 
+int ahfgpu_halo_members_buffer(ahfgpu_ctx *c, int64_t *members_pinned, int64_t capacity)
+{
+  API_BEGIN
+  if (!c) AHF_FAIL("null ctx");
+  if (members_pinned && capacity < 0) AHF_FAIL("negative capacity");
+  CUDA_CHECK(cudaSetDevice(c->dev));
+  if (c->early_sent && c->ev_members) CUDA_CHECK(cudaEventSynchronize(c->ev_members));       // a copy into the old buffer may still be in flight
+  c->early_members = members_pinned; c->early_cap = members_pinned ? capacity : 0; c->early_sent = false;
+  API_END
+}
+
 int ahfgpu_halo_fetch(ahfgpu_ctx *c, double *scal, int64_t *member_offset, int64_t *members, int64_t *prof_offset, double *prof)
 {
   API_BEGIN
@@ -609,7 +621,10 @@ int ahfgpu_halo_fetch(ahfgpu_ctx *c, double *scal, int64_t *member_offset, int64
   CUDA_CHECK(cudaStreamSynchronize(c->stream));       // the library's stream is non-blocking: the legacy-stream copies below do not wait for it
   if (scal && c->nhalo) CUDA_CHECK(cudaMemcpy(scal, c->h_scal, sizeof(double) * AHFGPU_NSCAL * c->nhalo, cudaMemcpyDeviceToHost));
   if (member_offset) CUDA_CHECK(cudaMemcpy(member_offset, c->h_moff, sizeof(int64_t) * (c->nhalo + 1), cudaMemcpyDeviceToHost));
-  if (members && c->h_total_members) CUDA_CHECK(cudaMemcpy(members, c->h_members, sizeof(int64_t) * c->h_total_members, cudaMemcpyDeviceToHost));
+  if (members && c->h_total_members) {
+    if (c->early_sent && members == c->early_members) CUDA_CHECK(cudaEventSynchronize(c->ev_members));      // already on its way (ahfgpu_halo_members_buffer)
+    else CUDA_CHECK(cudaMemcpy(members, c->h_members, sizeof(int64_t) * c->h_total_members, cudaMemcpyDeviceToHost));
+  }
   if (prof_offset) CUDA_CHECK(cudaMemcpy(prof_offset, c->h_poff, sizeof(int64_t) * (c->nhalo + 1), cudaMemcpyDeviceToHost));
   if (prof && c->h_total_bins) CUDA_CHECK(cudaMemcpy(prof, c->h_prof, sizeof(double) * AHFGPU_NPROFCOL * c->h_total_bins, cudaMemcpyDeviceToHost));
   API_END

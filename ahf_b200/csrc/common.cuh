@@ -188,6 +188,8 @@ struct ahfgpu_ctx {
   double   *h_species = nullptr;     // device [nhalo*64]      (GAS_PARTICLES build: gas_only at 0, stars_only at 32)
   double   *h_prof_species = nullptr;// device [total bins*3]  (M_gas, M_star, u_gas)
   int64_t   h_total_members = 0, h_total_bins = 0;
+  // ahfgpu_halo_members_buffer: the caller's pinned buffer, and whether the lists of the last halo pass already travel / sit there
+  int64_t  *early_members = nullptr; int64_t early_cap = 0; bool early_sent = false; cudaEvent_t ev_members = nullptr;
   // stage timing
   std::vector<ahf::StageRec> stages;
   std::map<std::string, double>  stage_ms;

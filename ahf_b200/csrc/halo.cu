@@ -2453,6 +2453,25 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
   CUDA_CHECK(cudaMemcpyAsync(d_soff, soff.data(), sizeof(int64_t) * (nhalo + 1), cudaMemcpyHostToDevice, c->stream));
   c->h_prof = dalloc<double>((size_t)tot_b * AHFGPU_NPROFCOL);
   c->h_members = dalloc<int64_t>(tot_m);
+  const uint32_t *out_ids = d_gid ? d_gid : (c->slab ? c->order : (uint32_t *)nullptr);
+  // the member lists are final: with a registered pinned buffer (ahfgpu_halo_members_buffer) they leave for the host now, on the copy
+  // stream, while the profiles are computed
+  bool members_written = false;
+  if (c->early_members && tot_m > 0 && tot_m <= c->early_cap) {
+    if (!c->copy_stream) {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+      for (auto &e : c->ev_copy) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_mom, cudaEventDisableTiming));
+    }
+    if (!c->ev_members) CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_members, cudaEventDisableTiming));
+    LAUNCH(c, k_members_out, nblk(tot_m, 256), 256, 0, d_moff0, c->h_moff, nhalo, (int64_t)tot_m, d_members, out_ids, c->h_members);
+    CUDA_CHECK(cudaEventRecord(c->ev_main, c->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
+    CUDA_CHECK(cudaMemcpyAsync(c->early_members, c->h_members, sizeof(int64_t) * tot_m, cudaMemcpyDeviceToHost, c->copy_stream));
+    CUDA_CHECK(cudaEventRecord(c->ev_members, c->copy_stream));
+    c->early_sent = true; members_written = true;
+  }
   const bool prof_v1 = getenv("AHFGPU_PROFILES_V1") != nullptr;      // previous form: one CTA per halo (kept for A/B timing)
   double *d_scratch = prof_v1 ? dalloc<double>((size_t)tot_s * 3) : nullptr;
   {
@@ -2463,7 +2482,7 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
     else
       profiles_cooperative(c, nhalo, P, d_ctr, d_moff0, d_members, tot_g, d_np, h_np);
     // a slab of a distributed box reports GLOBAL INPUT INDICES (the resident `order` array), not offsets into its own sorted set
-    if (tot_m > 0) LAUNCH(c, k_members_out, nblk(tot_m, 256), 256, 0, d_moff0, c->h_moff, nhalo, (int64_t)tot_m, d_members, d_gid ? d_gid : (c->slab ? c->order : (uint32_t *)nullptr), c->h_members);
+    if (tot_m > 0 && !members_written) LAUNCH(c, k_members_out, nblk(tot_m, 256), 256, 0, d_moff0, c->h_moff, nhalo, (int64_t)tot_m, d_members, out_ids, c->h_members);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
   }
   ahf::dfree(d_ctr); ahf::dfree(d_rad); ahf::dfree(d_seed); ahf::dfree(d_rlo); ahf::dfree(d_rhi); ahf::dfree(d_cand); ahf::dfree(d_candoff); ahf::dfree(d_ng);

@@ -579,6 +579,8 @@ def main():
             for k, v in res.items():
                 if k in ("scal", "members", "prof"):
                     pinned[k] = torch.empty((int(v.size * 1.25) + 1024,), dtype=torch.float64 if v.dtype == np.float64 else torch.int64, pin_memory=True)
+            # the member lists are final after the unbinding: from now on they travel home while the profiles are computed
+            g._chk(g._L.ahfgpu_halo_members_buffer(g._h, pinned["members"].data_ptr(), pinned["members"].numel()))
         return res
 
     # ---- HBM-resident timing

@@ -158,6 +158,11 @@ int  ahfgpu_construct_halos(ahfgpu_ctx *ctx, int64_t nhalo, const double *centre
 int  ahfgpu_halo_sizes(ahfgpu_ctx *ctx, int64_t *total_members, int64_t *total_bins);
 int  ahfgpu_halo_fetch(ahfgpu_ctx *ctx, double *scal, int64_t *member_offset, int64_t *members,
                        int64_t *prof_offset, double *prof);
+/* Optional: a PINNED host buffer for the member lists, registered before ahfgpu_construct_halos.  The lists are final once the
+ * unbinding is done (src/libahf/ahf_halos.c:3361ff reads them only after the halo loop), so the library sends them home on its copy
+ * stream while the profiles are still being computed; ahfgpu_halo_fetch called with the same `members` pointer then only waits for that
+ * copy.  capacity in entries; a call whose lists do not fit falls back to the copy inside ahfgpu_halo_fetch.  NULL unregisters. */
+int  ahfgpu_halo_members_buffer(ahfgpu_ctx *ctx, int64_t *members_pinned, int64_t capacity);
 /* -DGAS_PARTICLES build of the reference (particles carry `u`): the per-species blocks of HaloProfiles
  * (src/libahf/ahf_halos.c:4420-4582, :4712-4715, :5020-5181).
  *   species       nhalo x 64 doubles: HALO.gas_only at 0, HALO.stars_only at 32 (SPECIESPROP, src/tdef.h:560-587):

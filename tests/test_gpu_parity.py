@@ -224,3 +224,27 @@ def test_overlapped_upload_gives_the_same_results(A, golden):
             _check_levels(g, golden)
             _check_halos(g, golden)                                            # construct_halos has returned: the copy is complete
             assert np.array_equal(ho.numpy().view(np.uint32), g.particle_ids())
+
+
+def test_member_lists_sent_early_equal_the_fetched_ones(A, golden):
+    """ahfgpu_halo_members_buffer: with a registered pinned buffer the member lists leave for the host while the profiles are computed and
+    ahfgpu_halo_fetch only waits for that copy; same lists as the plain fetch, also when the buffer is too small (fallback), and again
+    after it is unregistered."""
+    import torch
+    hs = golden.hs
+    with _ctx(A, golden) as g:
+        g.sfc_sort(golden.pos, golden.mom, golden.weight, golden.u)
+        plain = g.construct_halos(hs[:, 0:3].copy(), hs[:, 3].copy(), hs[:, 4].astype(np.int64))
+        nm = len(plain["members"])
+        assert nm > 0
+        for cap in (nm + 100, max(nm // 2, 1)):
+            buf = torch.full((nm + 100,), -7, dtype=torch.int64).pin_memory()
+            g._chk(g._L.ahfgpu_halo_members_buffer(g._h, buf.data_ptr(), cap))
+            g.construct_halos(hs[:, 0:3].copy(), hs[:, 3].copy(), hs[:, 4].astype(np.int64), fetch=False)
+            res = g.fetch_halos(len(hs), bufs={"members": buf.numpy()})
+            assert np.array_equal(res["members"], plain["members"]) and np.array_equal(res["member_offset"], plain["member_offset"])
+            assert np.all(buf.numpy()[nm:] == -7)
+            assert np.array_equal(res["scal"], plain["scal"]) and np.array_equal(res["prof"], plain["prof"])
+        g._chk(g._L.ahfgpu_halo_members_buffer(g._h, None, 0))
+        again = g.construct_halos(hs[:, 0:3].copy(), hs[:, 3].copy(), hs[:, 4].astype(np.int64))
+        assert np.array_equal(again["members"], plain["members"])
