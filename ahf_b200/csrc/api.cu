@@ -127,6 +127,11 @@ void ahfgpu_ctx::ktime_dump(const char *label)
 }
 void ahfgpu_ctx::wait_mom(bool host)
 {
+  if (ids_pending) {
+    if (host) cudaEventSynchronize(ev_ids);
+    cudaStreamWaitEvent(stream, ev_ids, 0);
+    ids_pending = false;
+  }
   if (!mom_pending) return;
   if (host) cudaEventSynchronize(ev_mom);
   cudaStreamWaitEvent(stream, ev_mom, 0);
@@ -269,6 +274,7 @@ int ahfgpu_finalize(ahfgpu_ctx *c)
   c->event_pool.clear();
   for (auto &e : c->ev) if (e) cudaEventDestroy(e);
   if (c->ev_members) { cudaEventSynchronize(c->ev_members); cudaEventDestroy(c->ev_members); }
+  if (c->d2h_stream) { cudaStreamSynchronize(c->d2h_stream); cudaStreamDestroy(c->d2h_stream); cudaEventDestroy(c->ev_ids); }
   {                                                   // blocks cached for this context's stream go back to the driver pool
     std::lock_guard<std::mutex> lk(g_cache_mu);
     for (auto it = g_cache_free.begin(); it != g_cache_free.end();) {
@@ -486,8 +492,15 @@ int ahfgpu_particle_ids_async(ahfgpu_ctx *c, uint32_t *ids)
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     if (c->n) CUDA_CHECK(cudaMemcpy(ids, c->order, sizeof(uint32_t) * c->n, cudaMemcpyDeviceToHost));
   } else {
-    if (c->n) CUDA_CHECK(cudaMemcpyAsync(ids, c->order, sizeof(uint32_t) * c->n, cudaMemcpyDeviceToHost, c->copy_stream));
-    CUDA_CHECK(cudaEventRecord(c->ev_mom, c->copy_stream));       // whoever waits for the momenta now waits for this copy as well
+    // ahfgpu_sfc_sort_soa_async has returned: the main stream is idle and `order` is final.  Own stream: the copy shares the bus with the
+    // incoming momenta (other direction) instead of queueing behind them
+    if (!c->d2h_stream) {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+      CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_ids, cudaEventDisableTiming));
+    }
+    if (c->n) CUDA_CHECK(cudaMemcpyAsync(ids, c->order, sizeof(uint32_t) * c->n, cudaMemcpyDeviceToHost, c->d2h_stream));
+    CUDA_CHECK(cudaEventRecord(c->ev_ids, c->d2h_stream));        // whoever waits for the momenta waits for this copy as well (wait_mom)
+    c->ids_pending = true;
   }
   API_END
 }

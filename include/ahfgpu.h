@@ -205,8 +205,8 @@ int  ahfgpu_slab_info(ahfgpu_ctx *ctx, int64_t *iout, double *dout);
 int  ahfgpu_slab_owner_of(ahfgpu_ctx *ctx, int64_t n, const double *pos3, int32_t *owner);
 int  ahfgpu_amr_level_owned(ahfgpu_ctx *ctx, int32_t lev, uint8_t *owned);
 int  ahfgpu_particle_ids(ahfgpu_ctx *ctx, uint32_t *ids);
-/* the same, enqueued behind the momentum upload of ahfgpu_sfc_sort_soa_async (device -> host while the hierarchy is built); `ids` (pinned)
- * is complete when ahfgpu_construct_halos has returned */
+/* the same after ahfgpu_sfc_sort_soa_async, on a stream of its own (device -> host while the momenta come in and the hierarchy is built);
+ * `ids` (pinned) is complete when ahfgpu_construct_halos has returned */
 int  ahfgpu_particle_ids_async(ahfgpu_ctx *ctx, uint32_t *ids);
 /* lower-level pieces kept for callers that place particles themselves:
  *   ahfgpu_set_global_count : N of the whole box (masstopartdens = L^3 / N, generate_grids.c:66-69)
