@@ -2269,8 +2269,14 @@ static void profiles_cooperative(ahfgpu_ctx *c, int64_t nhalo, const HP &P, cons
   LAUNCH(c, k_g_scan<PNC>, (unsigned)nact, HB, 0, d_act, d_tile0, d_ntile, d_tt4, d_tc4, d_ht4);
   LAUNCH(c, k_p_phi, (unsigned)nt, HB, 0, c->pos4, has_w, d_ctr, d_moff0, d_members, G, d_tiles, d_tc4, d_tt1);
   LAUNCH(c, k_g_scan<1>, (unsigned)nact, HB, 0, d_act, d_tile0, d_ntile, d_tt1, d_tc1, d_ht1);
-  const int nslot = exclusive_scan<int32_t>(c, G.tile_ns, d_slot, (uint64_t)nt);
-  G.partial = dalloc<double>((size_t)nslot * NACC);
+  // slots of the (tile, bin) partial table: consecutive tiles of a halo share at most their boundary bin, so a halo needs at most
+  // tiles + bins - 1 of them -- sized from what the host already knows, the prefix sum stays on the device (no read-back here)
+  {
+    DevBuf<int> bs;
+    exclusive_scan_async<int32_t>(c, G.tile_ns, d_slot, (uint64_t)nt, nullptr, bs);
+    bs.release();
+  }
+  G.partial = dalloc<double>(((size_t)nt + (size_t)c->h_total_bins) * NACC);
   if (nt >= 4096 && nt < 2 * nact && !getenv("AHFGPU_PMAIN_MB2")) LAUNCH(c, k_p_main<3>, (unsigned)nt, HB, 0, c->pos4, c->mom4, has_w, has_u, d_ctr, d_moff0, d_members, G, d_tiles, d_tc4, d_tc1, c->h_scal, P);
   else LAUNCH(c, k_p_main<2>, (unsigned)nt, HB, 0, c->pos4, c->mom4, has_w, has_u, d_ctr, d_moff0, d_members, G, d_tiles, d_tc4, d_tc1, c->h_scal, P);
   if (nact >= 2048 && nt < 4 * nact) LAUNCH(c, k_p_finish<64>, (unsigned)nact, 64, 0, c->pos4, c->mom4, d_ctr, d_moff0, d_members, G, d_act, c->h_scal, c->h_poff, c->h_prof, P);
@@ -2317,24 +2323,29 @@ void halos_construct(ahfgpu_ctx *c, int64_t nhalo, const double *centre3, const 
   {
     Stage st(c, "halo_gather", 0);
     LAUNCH(c, k_gather_ranges, nblk(nhalo * 32, 128), 128, 0, c->keys, n, d_ctr, d_rad, d_seed, nhalo, d_rlo, d_rhi, d_cand);
+    // tile list of the gather (chunks of HT candidates of every (halo, search cell) range): its count is read back together with the
+    // candidate counts -- one host synchronisation for both
+    const bool  gather_v1 = getenv("AHFGPU_GATHER_V1") != nullptr;
+    const int64_t nrange = 27 * nhalo;
+    if (nrange >= (1ll << 31)) AHF_FAIL("too many haloes in one call");
+    DevBuf<int> ntr, toff, bs, ttot;
+    int nt = 0;
+    if (!gather_v1) {
+      ntr.reserve(nrange); toff.reserve(nrange); ttot.reserve(1);
+      CUDA_CHECK(cudaMemsetAsync(ttot.p, 0, sizeof(int), c->stream));
+      LAUNCH(c, k_gt_count, nblk(nrange, 256), 256, 0, d_rlo, d_rhi, nrange, ntr.p);
+      exclusive_scan_async<int>(c, ntr.p, toff.p, (uint64_t)nrange, ttot.p, bs);
+      CUDA_CHECK(cudaMemcpyAsync(&nt, ttot.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    }
     CUDA_CHECK(cudaMemcpyAsync(h_cand.data(), d_cand, sizeof(int64_t) * nhalo, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     candoff = host_excl(h_cand, &tot_cand);
     CUDA_CHECK(cudaMemcpyAsync(d_candoff, candoff.data(), sizeof(int64_t) * (nhalo + 1), cudaMemcpyHostToDevice, c->stream));
     d_r2 = dalloc<double>(tot_cand); d_idx = dalloc<uint32_t>(tot_cand);
-    if (getenv("AHFGPU_GATHER_V1")) {
+    if (gather_v1) {
       LAUNCH(c, k_gather_fill, (unsigned)nhalo, HB, 0, c->pos4, d_ctr, d_rad, d_rlo, d_rhi, d_candoff, d_r2, d_idx, d_ng);
     } else {
-      // tile list: chunks of HT candidates of every (halo, search cell) range, in the reference's append order
-      const int64_t nrange = 27 * nhalo;
-      if (nrange >= (1ll << 31)) AHF_FAIL("too many haloes in one call");
-      DevBuf<int> ntr, toff, bs, ttot;
-      ntr.reserve(nrange); toff.reserve(nrange); ttot.reserve(1);
-      CUDA_CHECK(cudaMemsetAsync(ttot.p, 0, sizeof(int), c->stream));
-      LAUNCH(c, k_gt_count, nblk(nrange, 256), 256, 0, d_rlo, d_rhi, nrange, ntr.p);
-      exclusive_scan_async<int>(c, ntr.p, toff.p, (uint64_t)nrange, ttot.p, bs);
-      int nt = 0;
-      read_back(c, &nt, ttot.p, sizeof(int));
+      // tile list in the reference's append order
       int4 *d_gt = dalloc<int4>(nt); int32_t *d_act = dalloc<int32_t>(nhalo), *d_t0 = dalloc<int32_t>(nhalo), *d_ntl = dalloc<int32_t>(nhalo);
       double *d_tt = dalloc<double>(nt), *d_tc = dalloc<double>(nt), *d_ht = dalloc<double>(nhalo);
       LAUNCH(c, k_gt_fill, nblk(nrange, 256), 256, 0, d_rlo, d_rhi, nrange, toff.p, ttot.p, d_gt, d_act, d_t0, d_ntl);
