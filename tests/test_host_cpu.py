@@ -236,6 +236,24 @@ def test_committed_bench_lines_follow_the_contract():
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(full["cpu_baseline"]) and full["cpu_baseline"]["kind"] == "reference"
 
 
+def test_final_bench_line_and_traffic_source():
+    """the last bench line of round 2 follows the contract as well, and `roofline.traffic` is read from a `k_deposit_dom` launch of the
+    newest ncu summary that holds one (an earlier version picked the first launch of the alphabetically last file: a k_deposit_runs launch)"""
+    import json
+    import bench
+    d = json.loads([l for l in open(os.path.join(ROOT, "profiles", "r3q_bench_256_n1.json")) if l.startswith("{")][0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["cpu_baseline"]["kind"] == "reference" and "256^3" in d["cpu_baseline"]["sample"] and "256^3" in d["config"]["workload"]
+    assert d["e2e"]["h2d_bytes_per_step"] > 4e8 and d["e2e"]["d2h_bytes_per_step"] > 1e8          # members, profiles and the permutation come back
+    t = bench.ncu_traffic_bytes(256)
+    alg = 16.0 * 256 ** 3 + 4.0 * 256 ** 3
+    assert t is not None and 1.0 * alg < t < 2.0 * alg, t                    # u64 accumulators: ~1.45x the algorithmic bytes
+    assert d["roofline"]["traffic"] == t
+    assert bench.ncu_traffic_bytes(128) is None
+
+
 def test_min_ref_follows_reference(golden):
     """host arithmetic of ahf_gridinfo.c:147-175 (ahf.min_ref) against the first coloured level of the reference (tests/golden/patches.npz);
     frag16 sits on the edge: its level 3 has refine_ovdens = 199.99999999999997 against ovlim = 200"""
