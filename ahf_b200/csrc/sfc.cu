@@ -310,6 +310,60 @@ void sort_keys63(ahfgpu_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t *keys_t
 }
 
 // ------------------------------------------------------------------------------------------------
+// Stable merge of two key-sorted runs of (u64, u32) pairs, A before B on equal keys (ahfgpu_sfc_sort_soa_async sorts the position chunks
+// as they arrive over the bus and merges them once the last one is there: only one chunk sort and two merge sweeps are left behind the
+// upload instead of the whole sort).  A CTA produces MG_TILE consecutive outputs: its share of A and of B by two merge-path searches
+// (the split of diagonal d takes one more element of A as long as A[a] <= B[d - a - 1]), both shares into shared memory, then every
+// element finds its output slot by one binary search in the other share (A: elements of B strictly smaller; B: elements of A not larger).
+// ------------------------------------------------------------------------------------------------
+constexpr int MG_THREADS = 256, MG_TILE = 2048;
+__device__ __forceinline__ int64_t merge_path_split(const uint64_t *__restrict__ ka, int64_t na, const uint64_t *__restrict__ kb, int64_t nb, int64_t d)
+{
+  int64_t lo = d > nb ? d - nb : 0, hi = d < na ? d : na;
+  while (lo < hi) {
+    const int64_t mid = lo + ((hi - lo) >> 1);
+    if (ka[mid] <= kb[d - mid - 1]) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__global__ void __launch_bounds__(MG_THREADS) k_merge_pairs(const uint64_t *__restrict__ ka, const uint32_t *__restrict__ va, int64_t na,
+                                                           const uint64_t *__restrict__ kb, const uint32_t *__restrict__ vb, int64_t nb,
+                                                           uint64_t *__restrict__ ko, uint32_t *__restrict__ vo)
+{
+  __shared__ uint64_t sk[MG_TILE];
+  __shared__ uint32_t sv[MG_TILE];
+  __shared__ int64_t  s_split[2];
+  const int64_t d0 = (int64_t)blockIdx.x * MG_TILE, d1 = d0 + MG_TILE < na + nb ? d0 + MG_TILE : na + nb;
+  if (threadIdx.x == 0) s_split[0] = merge_path_split(ka, na, kb, nb, d0);
+  if (threadIdx.x == 32) s_split[1] = merge_path_split(ka, na, kb, nb, d1);
+  __syncthreads();
+  const int64_t a0 = s_split[0], a1 = s_split[1], b0 = d0 - a0, b1 = d1 - a1;
+  const int     ca = (int)(a1 - a0), cb = (int)(b1 - b0);                 // ca + cb = d1 - d0 <= MG_TILE
+  for (int i = threadIdx.x; i < ca; i += MG_THREADS) { sk[i] = ka[a0 + i]; sv[i] = va[a0 + i]; }
+  for (int i = threadIdx.x; i < cb; i += MG_THREADS) { sk[ca + i] = kb[b0 + i]; sv[ca + i] = vb[b0 + i]; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ca + cb; i += MG_THREADS) {
+    const uint64_t k = sk[i];
+    int pos;
+    if (i < ca) {                                       // from A: behind the elements of B that are strictly smaller
+      int lo = 0, hi = cb;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (sk[ca + mid] < k) lo = mid + 1; else hi = mid; }
+      pos = i + lo;
+    } else {                                            // from B: behind the elements of A that are not larger
+      int lo = 0, hi = ca;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (sk[mid] <= k) lo = mid + 1; else hi = mid; }
+      pos = (i - ca) + lo;
+    }
+    ko[d0 + pos] = k; vo[d0 + pos] = sv[i];
+  }
+}
+static void merge_pairs(ahfgpu_ctx *c, const uint64_t *ka, const uint32_t *va, int64_t na, const uint64_t *kb, const uint32_t *vb, int64_t nb, uint64_t *ko, uint32_t *vo)
+{
+  if (na + nb == 0) return;
+  LAUNCH(c, k_merge_pairs, (unsigned)((na + nb + MG_TILE - 1) / MG_TILE), MG_THREADS, 0, ka, va, na, kb, vb, nb, ko, vo);
+}
+
+// ------------------------------------------------------------------------------------------------
 // payload gather
 // ------------------------------------------------------------------------------------------------
 __global__ void k_gather_soa(const float *__restrict__ pos3, const float *__restrict__ mom3, const float *__restrict__ w,
@@ -487,26 +541,47 @@ void sfc_sort_soa_async(ahfgpu_ctx *c, const float *pos3, const float *mom3, con
   constexpr int NCH = 4;
   upload_hil_tab3();
   const bool odd = (sort_keys63_passes() & 1) != 0;      // see sfc_sort_resident
+  // chunk-wise sort + merge (default for boxes that are worth it; AHFGPU_ASYNC_SORT_WHOLE=1: keys per chunk, ONE sort behind the upload)
+  const bool chunked = n >= (1u << 20) && !odd && getenv("AHFGPU_ASYNC_SORT_WHOLE") == nullptr;
   uint64_t *kA = odd ? k1.p : c->keys, *kB = odd ? c->keys : k1.p;
   uint32_t *vA = odd ? v1.p : c->order, *vB = odd ? c->order : v1.p;
   const uint64_t per = ((n + NCH - 1) / NCH + 255) & ~255ull;
-  {
-    Stage st(c, "keys", (int64_t)n);
-    for (int q = 0; q < NCH; q++) {
-      const uint64_t i0 = std::min(n, per * q), i1 = std::min(n, per * (q + 1));
-      if (i1 > i0) CUDA_CHECK(cudaMemcpyAsync(c->in_pos + 3 * i0, pos3 + 3 * i0, 3 * (i1 - i0) * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
-      CUDA_CHECK(cudaEventRecord(c->ev_copy[q], c->copy_stream));
-      CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_copy[q], 0));
-      if (i1 > i0) LAUNCH(c, k_keys_soa_tab, keys_tab_grid(i1 - i0), KT_THREADS, 0, c->in_pos, i0, i1, kA, vA);
-    }
+  uint64_t ci0[NCH], ci1[NCH];
+  // all copies are queued first: the copy stream runs on its own while the host waits for the tie flag of a chunk's sort
+  for (int q = 0; q < NCH; q++) {
+    ci0[q] = std::min(n, per * q); ci1[q] = std::min(n, per * (q + 1));
+    if (ci1[q] > ci0[q]) CUDA_CHECK(cudaMemcpyAsync(c->in_pos + 3 * ci0[q], pos3 + 3 * ci0[q], 3 * (ci1[q] - ci0[q]) * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+    CUDA_CHECK(cudaEventRecord(c->ev_copy[q], c->copy_stream));
   }
   if (w) CUDA_CHECK(cudaMemcpyAsync(c->in_w, w, n * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
   CUDA_CHECK(cudaEventRecord(c->ev_copy[NCH], c->copy_stream));
   CUDA_CHECK(cudaMemcpyAsync(c->in_mom, mom3, 3 * n * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
   if (u) CUDA_CHECK(cudaMemcpyAsync(c->in_u, u, n * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+  {
+    Stage st(c, "keys", (int64_t)n);
+    for (int q = 0; q < NCH; q++) {
+      CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_copy[q], 0));
+      const uint64_t i0 = ci0[q], i1 = ci1[q];
+      if (i1 > i0) LAUNCH(c, k_keys_soa_tab, keys_tab_grid(i1 - i0), KT_THREADS, 0, c->in_pos, i0, i1, kA, vA);
+      if (chunked && i1 > i0) {
+        // the chunk is sorted in place (an even number of passes ends in the buffer it started in) while the next one is on the bus
+        uint64_t *cks; uint32_t *cvs;
+        sort_keys63(c, kA + i0, vA + i0, kB + i0, vB + i0, i1 - i0, &cks, &cvs);
+        if (cks != kA + i0) AHF_FAIL("chunk sort did not end in its own buffer");
+        // chunks 0+1 merge as soon as both are sorted (kA -> kB), 2+3 likewise, the two halves at the end (kB -> kA)
+        if (q == 1) merge_pairs(c, kA + ci0[0], vA + ci0[0], (int64_t)(ci1[0] - ci0[0]), kA + ci0[1], vA + ci0[1], (int64_t)(ci1[1] - ci0[1]), kB + ci0[0], vB + ci0[0]);
+      }
+    }
+  }
   uint64_t *ks; uint32_t *vs;
   {
     Stage st(c, "sort", (int64_t)n);
+    if (chunked) {
+      static_assert(NCH == 4, "merge tree of sfc_sort_soa_async is written for four chunks");
+      merge_pairs(c, kA + ci0[2], vA + ci0[2], (int64_t)(ci1[2] - ci0[2]), kA + ci0[3], vA + ci0[3], (int64_t)(ci1[3] - ci0[3]), kB + ci0[2], vB + ci0[2]);
+      merge_pairs(c, kB, vB, (int64_t)ci0[2], kB + ci0[2], vB + ci0[2], (int64_t)(n - ci0[2]), kA, vA);
+      ks = kA; vs = vA;
+    } else
     sort_keys63(c, kA, vA, kB, vB, n, &ks, &vs);
     if (ks != c->keys) {
       CUDA_CHECK(cudaMemcpyAsync(c->keys, ks, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));

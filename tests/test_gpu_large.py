@@ -242,3 +242,36 @@ def test_large_multispecies_host_against_oracle(A):
     out = m.run(1_500_000, 2)
     assert out["host_gathered"] > 1_000_000 and out["members_identical"]
     print(out)
+
+
+@pytest.mark.parametrize("whole", [False, True])
+def test_overlapped_upload_sorts_chunks_and_merges_them(A, whole, monkeypatch):
+    """ahfgpu_sfc_sort_soa_async on a box large enough for its chunk-wise path (>= 2^20 particles): the four position chunks are sorted as
+    they arrive and merged, stable across the chunks (equal keys keep their input order: positions repeated in different chunks, a dense
+    blob whose tie runs the six-pass sort has to fix, and a chunk of already sorted input).  Permutation = the stable sort of the
+    oracle's keys, also with the single sort behind the upload (AHFGPU_ASYNC_SORT_WHOLE)."""
+    import torch
+    from oracle import oracle as O
+    if whole:
+        monkeypatch.setenv("AHFGPU_ASYNC_SORT_WHOLE", "1")
+    rng = np.random.default_rng(5)
+    n = (1 << 20) + 77777
+    pos = rng.random((n, 3), dtype=np.float32)
+    pos[n - 5000:] = pos[:5000]                                   # equal keys in the first and the last chunk
+    pos[n // 2:n // 2 + 3000] = pos[100:3100]                     # ... and in the third
+    pos[300000:340000] = (np.float32(0.7) + rng.random((40000, 3), dtype=np.float32) * np.float32(2.0 ** -14)).astype(np.float32)   # tie runs
+    q = n // 4
+    pos[q:q + 50000] = pos[q:q + 50000][np.argsort(O.hilbert_keys(pos[q:q + 50000]), kind="stable")]
+    mom = rng.standard_normal((n, 3)).astype(np.float32)
+    okeys = O.hilbert_keys(pos)
+    oorder = np.argsort(okeys, kind="stable")
+    hp = torch.from_numpy(pos).pin_memory(); hm = torch.from_numpy(mom).pin_memory()
+    par = A.make_params(boxsize=20.0, pmass=1.0, lgrid_dom=64)
+    with A.AhfGpu(par) as g:
+        for _ in range(2):
+            g.sfc_sort_async_ptr(hp.data_ptr(), hm.data_ptr(), n)
+            g.synchronize()
+            order = g.particle_ids()
+            assert np.array_equal(order.astype(np.int64), oorder)
+        keys, order2 = g.sfc_sort(pos, mom)
+        assert np.array_equal(keys, okeys[oorder]) and np.array_equal(order2, order)
