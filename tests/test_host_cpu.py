@@ -116,6 +116,81 @@ def test_two_rank_partition_gloo(tmp_path):
         assert "ok" in o
 
 
+_WORKER_CAT = r"""
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+from ahf_b200 import ahf, multigpu, parallel as P, synth
+from oracle import oracle as O
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+out_dir = sys.argv[2]
+box = synth.make_host_box(30000, n_sub=12, n1d_bg=32, seed=48)            # a host halo with sub-haloes: the re-hash has work to do
+n1d = 64
+keys = O.hilbert_keys(box.pos); order = np.argsort(keys, kind="stable"); keys = keys[order]
+pos = box.pos[order]; mom = box.mom[order]
+par = ahf.make_params(boxsize=box.boxsize, pmass=box.pmass, lgrid_dom=n1d)
+# every rank derives the same seeds (CPU oracle hierarchy -> the library's host tree), as every rank of a split box does
+H = O.build_hierarchy(pos, n1d, patches=True)
+m = ahf.min_ref(par, [lv.l1dim for lv in H])
+stats = [np.hstack([lv.patch, O.patch_extents(lv).reshape(len(lv.patch), 6)]) for lv in H[m:]]
+seeds = ahf.tree_halos(stats, 3.0 / box.boxsize)
+c, r, n = np.ascontiguousarray(seeds["pos"]), np.ascontiguousarray(seeds["gather_rad"]), np.ascontiguousarray(seeds["npart"], np.int64)
+assert len(n) >= 8
+opar = dict(r_fac=par.r_fac, x_fac=par.x_fac, v_fac=par.v_fac, m_fac=par.m_fac, rho_fac=par.rho_fac, phi_fac=par.phi_fac,
+            Hubble=par.hubble, ovlim=par.ovlim, rho_vir=par.rho_vir, vesc_tune=par.vesc_tune, min_part=par.min_part)
+
+def serve(sel):
+    # the halo pass of the haloes `sel` (CPU oracle) in the layout ahfgpu_halo_fetch delivers
+    rs = O.construct_halos(keys, pos, mom, None, None, opar, c[sel], r[sel], n[sel])
+    scal = np.array([q["s"] for q in rs]).reshape(len(sel), 64)
+    moff = np.zeros(len(sel) + 1, np.int64); poff = np.zeros(len(sel) + 1, np.int64)
+    for k, q in enumerate(rs):
+        moff[k + 1] = moff[k] + q["npart"]; poff[k + 1] = poff[k] + q["nbins"]
+    mem = np.concatenate([q["ipart"].astype(np.int64) for q in rs]) if moff[-1] else np.zeros(0, np.int64)
+    prof = np.concatenate([q["prof"].reshape(-1) for q in rs if q["nbins"] > 0]) if poff[-1] else np.zeros(0)
+    return dict(scal=scal, member_offset=moff, members=mem, prof_offset=poff, prof=prof)
+
+mine = np.nonzero(P.assign_halos_lpt(n, 2) == rank)[0]                     # the same assignment on every rank
+assert len(mine) > 0
+parts = multigpu.gather_parts_torch(mine, serve(mine), dst=0)              # results travel to rank 0 (gloo here, NCCL's host side on a GPU box)
+if rank == 0:
+    assert sorted(np.concatenate([p[0] for p in parts]).tolist()) == list(range(len(n)))
+    ids = order.astype(np.uint64)                                          # ID of the particle at sorted offset i = its input index
+    two = multigpu.catalogue_from_ranks(os.path.join(out_dir, "two.z0.000"), par, seeds, parts, ids)
+    allh = np.arange(len(n))
+    one = multigpu.catalogue_from_ranks(os.path.join(out_dir, "one.z0.000"), par, seeds, [(allh, serve(allh))], ids)
+    for k in ("host", "nsub", "rank"):
+        assert np.array_equal(two[k], one[k]), k
+    for ext in ("AHF_halos", "AHF_profiles", "AHF_substructure", "AHF_particles"):
+        a = open(os.path.join(out_dir, "one.z0.000." + ext), "rb").read(); b = open(os.path.join(out_dir, "two.z0.000." + ext), "rb").read()
+        assert len(a) > 0 and a == b, ext
+    # a halo served twice, or not at all, is refused
+    try:
+        multigpu.catalogue_from_ranks(None, par, seeds, parts + [parts[0]], ids); raise SystemExit("duplicate halo accepted")
+    except ahf.AhfGpuError:
+        pass
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_two_rank_catalogue_gloo(tmp_path):
+    """N > 1 host path on the CPU (world_size 2, gloo): both ranks derive the same halo seeds, each serves the haloes assigned to it, the
+    results are gathered on rank 0 (multigpu.gather_parts_torch) and written by multigpu.catalogue_from_ranks -- the four catalogue files
+    and the re-hashed links must equal those of one process serving every halo."""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker_cat.py"
+    script.write_text(_WORKER_CAT % dict(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o
+
+
 def test_table_driven_hilbert_index_equals_the_step_form(tmp_path, golden):
     """hilbert.cuh is host+device code: the three-levels-per-look-up form the key kernel uses (hilbert_index21_tab) against the
     21-step form, compiled for the host, on random cells, the box corners and the golden particle keys of the reference."""
